@@ -1,0 +1,155 @@
+/*
+ * mom6cu.h -- C ABI of the B200-native split-explicit dycore hot path.
+ *
+ * Every entry point mirrors one Fortran module procedure of the reference
+ * (mom-ocean/MOM6) that the src/core driver calls; the reference routine each
+ * one replaces is cited as file:line.  Fortran host code binds these through
+ * ISO_C_BINDING (see fortran/mom6cu_interface.F90 and INTEGRATION.md).
+ *
+ * Conventions
+ *  - All reals are IEEE binary64 ("real" in a default MOM6 build, -fdefault-real-8).
+ *  - Arrays are contiguous, column-major (i fastest), exactly as the Fortran
+ *    dummy arguments are declared.  Extents follow the reference's symmetric
+ *    memory macros (src/framework/MOM_memory_macros.h, dynamic branch):
+ *        h-points  (isd:ied,   jsd:jed)
+ *        u-points  (isd-1:ied, jsd:jed)      SZIB_(G),SZJ_(G)
+ *        v-points  (isd:ied,   jsd-1:jed)    SZI_(G),SZJB_(G)
+ *        q-points  (isd-1:ied, jsd-1:jed)
+ *    "wide" barotropic arrays use (isdw,iedw,jsdw,jedw) the same way
+ *    (SZIW_/SZIBW_/SZJW_/SZJBW_, MOM_barotropic.F90:46-51).
+ *  - A pointer argument may be a HOST pointer (the Fortran array) or a DEVICE
+ *    pointer to a buffer of the same shape; the library detects which with
+ *    cudaPointerGetAttributes.  Host arrays are staged to the device-resident
+ *    layout and results copied back inside the call.
+ *  - Return value: 0 = success; >0 = FATAL (message via mom6cu_last_error),
+ *    the Fortran shim turns it into MOM_error(FATAL, msg)
+ *    (src/framework/MOM_error_handler.F90); <0 = -(number of WARNINGs).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry
+ *    returns MOM6CU_ERR_NO_DEVICE.
+ */
+#ifndef MOM6CU_H
+#define MOM6CU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOM6CU_OK 0
+#define MOM6CU_ERR_NO_DEVICE 1
+#define MOM6CU_ERR_BAD_ARG 2
+#define MOM6CU_ERR_UNSUPPORTED 3 /* a run-time option outside the frozen option set */
+#define MOM6CU_ERR_CUDA 4
+#define MOM6CU_ERR_NCCL 5
+
+typedef struct mom6cu_ctx mom6cu_ctx; /* opaque: one per MPI rank / GPU */
+
+/* Index bounds of one rank's tile: the subset of hor_index_type
+ * (src/framework/MOM_hor_index.F90) and of barotropic_CS%isdw.. that the hot
+ * path uses.  Fortran (1-based, halo-offset) indices. */
+typedef struct mom6cu_domain {
+  int isc, iec, jsc, jec;     /* computational domain, tracer points           */
+  int isd, ied, jsd, jed;     /* data (memory) domain of G                     */
+  int isdw, iedw, jsdw, jedw; /* data domain of the wide-halo barotropic arrays */
+  int nk;                     /* GV%ke                                          */
+  int cyclic_x, cyclic_y;     /* 1 = reentrant in that direction (MOM_domains.F90 REENTRANT_X/Y) */
+  int first_direction;        /* G%first_direction (MOM_grid.F90)               */
+  /* layout of tiles over ranks (MOM_domains.F90 LAYOUT): rank = pj*npi + pi    */
+  int npi, npj, pi, pj;
+} mom6cu_domain;
+
+/* ---------------------------------------------------------------- lifecycle */
+/* Replaces nothing in the reference; called once from the Fortran shim's
+ * initialize_dyn_split_RK2 wrapper (MOM_dynamics_split_RK2.F90:1338). */
+int mom6cu_create(mom6cu_ctx** ctx, const mom6cu_domain* dom, int device);
+int mom6cu_destroy(mom6cu_ctx* ctx);
+/* Copies the last error/warning message (NUL terminated) into buf. */
+int mom6cu_last_error(const mom6cu_ctx* ctx, char* buf, size_t len);
+/* Library/build information: returns the sm arch the kernels were built for (100). */
+int mom6cu_build_arch(void);
+/* Number of kernel launches issued by this context since creation. */
+long long mom6cu_launch_count(const mom6cu_ctx* ctx);
+/* Block until all work queued on the context's streams is done. */
+int mom6cu_sync(mom6cu_ctx* ctx);
+/* Device-time (ms) of the most recent compute entry, measured with CUDA
+ * events on the launching stream (excludes host<->device staging). */
+double mom6cu_last_kernel_ms(const mom6cu_ctx* ctx);
+
+/* ------------------------------------------------ barotropic substep loop  */
+/* btstep_timeloop, src/core/MOM_barotropic.F90:2175-2832 (private to the
+ * module in the reference; exposed here because it is the BASELINE.json
+ * "btstep microbench" unit and the inner stage of mom6cu_btstep).
+ * Frozen options: no OBCs, no dynamic_psurf, no linear_wave_drag, no
+ * clip_velocity, INTEGRAL_BT_CONTINUITY=False, evolving face areas off. */
+typedef struct mom6cu_bt_timeloop_args {
+  /* state, wide arrays, inout (MOM_barotropic.F90:2188-2193) */
+  double* eta; /* h-points wide */
+  double* ubt; /* u-points wide */
+  double* vbt; /* v-points wide */
+  /* transports closure (:2194-2207).  BTCL_* are arrays of the derived types
+   * local_BT_cont_u_type / _v_type (:367-416): 10 reals per point in
+   * declaration order {FA_EE,FA_E0,FA_W0,FA_WW,uBT_WW,uBT_EE,uh_crvW,uh_crvE,uh_WW,uh_EE}
+   * (v: {NN,N0,S0,SS,vBT_SS,vBT_NN,crvS,crvN,vh_SS,vh_NN}); used when use_BT_cont. */
+  const double* uhbt0;
+  const double* vhbt0;
+  const double* Datu; /* used when !use_BT_cont */
+  const double* Datv;
+  const double* BTCL_u;
+  const double* BTCL_v;
+  const double* eta_src; /* :2215 */
+  const double* eta_PF;  /* :2272 */
+  const double* gtot_E;
+  const double* gtot_W;
+  const double* gtot_N;
+  const double* gtot_S;
+  const double* f_4_u; /* (4,SZIBW,SZJW) :2232 */
+  const double* f_4_v; /* (4,SZIW,SZJBW) :2239 */
+  const double* bt_rem_u;
+  const double* bt_rem_v;
+  const double* BT_force_u;
+  const double* BT_force_v;
+  const double* Cor_ref_u;
+  const double* Cor_ref_v;
+  /* control-structure arrays (barotropic_CS, :144-166), wide */
+  const double* IareaT_OBCmask; /* h */
+  const double* IdxCu;          /* u */
+  const double* IdyCv;          /* v */
+  /* accumulators */
+  double* u_accel_bt; /* wide u, inout :2226 */
+  double* v_accel_bt; /* wide v, inout */
+  double* eta_sum;    /* wide h, out (only if find_etaav) :2302 */
+  double* eta_wtd;    /* wide h, out :2304 */
+  double* ubtav;      /* G u-points, out (CS%ubtav :125) */
+  double* vbtav;      /* G v-points, out */
+  double* uhbtav;     /* G u-points, out :2220 */
+  double* vhbtav;     /* G v-points, out */
+  double* ubt_wtd;    /* G u-points, out :2306 */
+  double* vbt_wtd;    /* G v-points, out */
+  /* per-step weights, host arrays (:2331-2345) */
+  const double* wt_vel;    /* nstep+nfilter   */
+  const double* wt_eta;    /* nstep+nfilter   */
+  const double* wt_accel;  /* nstep+nfilter+1 */
+  const double* wt_trans;  /* nstep+nfilter+1 */
+  const double* wt_accel2; /* nstep+nfilter+1 */
+  /* scalars */
+  double dtbt, dgeo_de, bebt, vel_underflow;
+  int nstep, nfilter;
+  int use_BT_cont, find_etaav, BT_project_velocity, use_old_coriolis_bracket_bug;
+  int use_wide_halos, min_stencil;
+} mom6cu_bt_timeloop_args;
+
+int mom6cu_btstep_timeloop(mom6cu_ctx* ctx, const mom6cu_bt_timeloop_args* a);
+
+/* Microbenchmark form: upload once (state + coefficients stay resident in
+ * HBM), run the substep loop `reps` times from the same initial state, and
+ * return the device time of the LAST repetition through mom6cu_last_kernel_ms.
+ * No host<->device traffic happens inside the repetitions. */
+int mom6cu_btstep_timeloop_resident(mom6cu_ctx* ctx, const mom6cu_bt_timeloop_args* a,
+                                    int reps, int download);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOM6CU_H */

@@ -1,0 +1,76 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+Python is only the test/bench harness here (the reference host language is Fortran: see
+fortran/ and INTEGRATION.md); every method is a thin marshalling layer over one C-ABI entry
+point of include/mom6cu.h and carries the name of the reference subroutine it stands for.
+"""
+import ctypes as C
+
+from . import _lib
+from ._lib import Domain, BtTimeloopArgs, fill_struct
+
+
+class Mom6cuError(RuntimeError):
+    """A FATAL from the library (the Fortran shim maps this to MOM_error(FATAL, msg))."""
+
+
+class Context:
+    """One rank's device context (mom6cu_ctx)."""
+
+    def __init__(self, dom, device=0):
+        self.lib = _lib.load()
+        self.dom = dom if isinstance(dom, Domain) else make_domain(**dom)
+        self._h = C.c_void_p()
+        rc = self.lib.mom6cu_create(C.byref(self._h), C.byref(self.dom), device)
+        if rc != 0:
+            raise Mom6cuError({1: "no CUDA device visible (there is no CPU fallback)",
+                               2: "bad domain / device argument"}.get(rc, f"mom6cu_create failed rc={rc}"))
+
+    def close(self):
+        if self._h:
+            self.lib.mom6cu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc > 0:
+            buf = C.create_string_buffer(1024)
+            self.lib.mom6cu_last_error(self._h, buf, 1024)
+            raise Mom6cuError(f"rc={rc}: {buf.value.decode()}")
+        return rc
+
+    @property
+    def launches(self):
+        return int(self.lib.mom6cu_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.mom6cu_last_kernel_ms(self._h))
+
+    def sync(self):
+        self._check(self.lib.mom6cu_sync(self._h))
+
+    # ---- MOM_barotropic.F90:2175 btstep_timeloop
+    def btstep_timeloop(self, args, reps=1, download=True):
+        keep = []
+        st = fill_struct(BtTimeloopArgs(), args, keep)
+        return self._check(self.lib.mom6cu_btstep_timeloop_resident(self._h, C.byref(st), reps, 1 if download else 0))
+
+
+def make_domain(ni, nj, nk=1, halo=4, whalo=None, cyclic_x=True, cyclic_y=False, first_direction=0,
+                npi=1, npj=1, pi=0, pj=0):
+    """Index bounds the way MOM_domains / hor_index_init set them: isc = halo+1 (1-based)."""
+    d = Domain()
+    d.isc, d.iec, d.jsc, d.jec = halo + 1, halo + ni, halo + 1, halo + nj
+    d.isd, d.ied, d.jsd, d.jed = 1, ni + 2 * halo, 1, nj + 2 * halo
+    wh = halo if whalo is None else whalo
+    d.isdw, d.iedw, d.jsdw, d.jedw = d.isc - wh, d.iec + wh, d.jsc - wh, d.jec + wh
+    d.nk = nk
+    d.cyclic_x, d.cyclic_y, d.first_direction = int(cyclic_x), int(cyclic_y), first_direction
+    d.npi, d.npj, d.pi, d.pj = npi, npj, pi, pj
+    return d

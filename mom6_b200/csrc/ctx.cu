@@ -1,0 +1,191 @@
+// Context, device-memory and staging plumbing behind the C ABI.
+#include "ctx.h"
+#include <cstdarg>
+#include <algorithm>
+
+double* mom6cu_ctx::buf(const std::string& name, size_t n) {
+  auto it = bufs.find(name);
+  if (it != bufs.end() && buf_sz[name] >= n) return it->second;
+  if (it != bufs.end()) { cudaFree(it->second); bufs.erase(it); }
+  double* p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) {
+    fail(MOM6CU_ERR_CUDA, "cudaMalloc of %zu doubles for '%s' failed", n, name.c_str());
+    return nullptr;
+  }
+  cudaMemsetAsync(p, 0, n * sizeof(double), stream);
+  bufs[name] = p;
+  buf_sz[name] = n;
+  return p;
+}
+
+int mom6cu_ctx::fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, sizeof(err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void m6_extent(const mom6cu_ctx* c, int stagger, int wide, int* ilo, int* ihi, int* jlo, int* jhi) {
+  const mom6cu_domain& d = c->dom;
+  const int su = (stagger == ST_U || stagger == ST_Q) ? 1 : 0;
+  const int sv = (stagger == ST_V || stagger == ST_Q) ? 1 : 0;
+  *ilo = (wide ? d.isdw : d.isd) - su;
+  *ihi = wide ? d.iedw : d.ied;
+  *jlo = (wide ? d.jsdw : d.jsd) - sv;
+  *jhi = wide ? d.jedw : d.jed;
+}
+
+bool m6_is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int m6_up(mom6cu_ctx* c, const double* src, int stagger, int wide, int nk, double* dst) {
+  if (!src || !dst) return c->fail(MOM6CU_ERR_BAD_ARG, "m6_up: null pointer");
+  int ilo, ihi, jlo, jhi;
+  m6_extent(c, stagger, wide, &ilo, &ihi, &jlo, &jhi);
+  const size_t ni = ihi - ilo + 1, nj = jhi - jlo + 1;
+  cudaMemcpy3DParms p = {};
+  p.srcPtr = make_cudaPitchedPtr((void*)src, ni * sizeof(double), ni, nj);
+  p.dstPtr = make_cudaPitchedPtr((void*)(dst + c->g.idx(ilo, jlo)), (size_t)c->g.pitch * sizeof(double),
+                                 c->g.pitch, c->g.rows);
+  p.extent = make_cudaExtent(ni * sizeof(double), nj, nk);
+  p.kind = cudaMemcpyDefault;
+  M6_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+  return 0;
+}
+
+int m6_down(mom6cu_ctx* c, const double* src_plane, int stagger, int wide, int nk, double* dst) {
+  if (!src_plane || !dst) return c->fail(MOM6CU_ERR_BAD_ARG, "m6_down: null pointer");
+  int ilo, ihi, jlo, jhi;
+  m6_extent(c, stagger, wide, &ilo, &ihi, &jlo, &jhi);
+  const size_t ni = ihi - ilo + 1, nj = jhi - jlo + 1;
+  cudaMemcpy3DParms p = {};
+  p.srcPtr = make_cudaPitchedPtr((void*)(src_plane + c->g.idx(ilo, jlo)), (size_t)c->g.pitch * sizeof(double),
+                                 c->g.pitch, c->g.rows);
+  p.dstPtr = make_cudaPitchedPtr((void*)dst, ni * sizeof(double), ni, nj);
+  p.extent = make_cudaExtent(ni * sizeof(double), nj, nk);
+  p.kind = cudaMemcpyDefault;
+  M6_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+  return 0;
+}
+
+namespace {
+struct PlanePtrs { double* p[10]; };
+
+__global__ void aos_to_planes_kernel(const double* __restrict__ src, int nm, int ni, int nj, long long off0,
+                                     int pitch, PlanePtrs dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= ni || j >= nj) return;
+  const double* s = src + ((size_t)j * ni + i) * nm;
+  const long long o = off0 + (long long)j * pitch + i;
+  for (int m = 0; m < nm; ++m) dst.p[m][o] = s[m];
+}
+}  // namespace
+
+int m6_up_aos(mom6cu_ctx* c, const double* src, int nm, int stagger, int wide, double* const* dst) {
+  if (!src) return c->fail(MOM6CU_ERR_BAD_ARG, "m6_up_aos: null pointer");
+  if (nm > 10) return c->fail(MOM6CU_ERR_BAD_ARG, "m6_up_aos: nm > 10");
+  int ilo, ihi, jlo, jhi;
+  m6_extent(c, stagger, wide, &ilo, &ihi, &jlo, &jhi);
+  const int ni = ihi - ilo + 1, nj = jhi - jlo + 1;
+  const double* dsrc = src;
+  if (!m6_is_device_ptr(src)) {
+    double* stage = c->buf("__aos_stage", (size_t)10 * c->g.plane);
+    if (!stage) return MOM6CU_ERR_CUDA;
+    M6_CUDA(c, cudaMemcpyAsync(stage, src, (size_t)nm * ni * nj * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dsrc = stage;
+  }
+  PlanePtrs pp;
+  for (int m = 0; m < 10; ++m) pp.p[m] = (m < nm) ? dst[m] : nullptr;
+  dim3 block(128), grid((ni + 127) / 128, nj);
+  M6_LAUNCH(c, aos_to_planes_kernel, grid, block, 0, dsrc, nm, ni, nj, c->g.idx(ilo, jlo), c->g.pitch, pp);
+  M6_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int mom6cu_build_arch(void) { return 100; }
+
+int mom6cu_create(mom6cu_ctx** out, const mom6cu_domain* dom, int device) {
+  if (!out || !dom) return MOM6CU_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MOM6CU_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) return MOM6CU_ERR_BAD_ARG;
+  if (dom->iec < dom->isc || dom->jec < dom->jsc || dom->nk < 1) return MOM6CU_ERR_BAD_ARG;
+  if (dom->isd > dom->isc || dom->ied < dom->iec || dom->jsd > dom->jsc || dom->jed < dom->jec)
+    return MOM6CU_ERR_BAD_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return MOM6CU_ERR_CUDA;
+  mom6cu_ctx* c = new mom6cu_ctx();
+  c->dom = *dom;
+  c->device = device;
+  mom6cu_domain& d = c->dom;
+  // a degenerate wide domain means "same as G"
+  if (d.iedw < d.isdw) { d.isdw = d.isd; d.iedw = d.ied; d.jsdw = d.jsd; d.jedw = d.jed; }
+  if (d.npi < 1) d.npi = 1;
+  if (d.npj < 1) d.npj = 1;
+  m6::Geom& g = c->g;
+  const int ilo = std::min(d.isd, d.isdw) - 1, ihi = std::max(d.ied, d.iedw);
+  const int jlo = std::min(d.jsd, d.jsdw) - 1, jhi = std::max(d.jed, d.jedw);
+  // lead padding so that column isc sits on a 128-byte boundary
+  const int lead = (16 - ((d.isc - ilo) % 16)) % 16;
+  g.i0 = ilo - lead;
+  g.j0 = jlo;
+  g.nx = ihi - g.i0 + 1;
+  g.ny = jhi - g.j0 + 1;
+  g.pitch = ((g.nx + 15) / 16) * 16;
+  g.rows = g.ny;
+  g.nk = d.nk;
+  g.plane = (long long)g.pitch * g.rows;
+  g.isc = d.isc; g.iec = d.iec; g.jsc = d.jsc; g.jec = d.jec;
+  g.isd = d.isd; g.ied = d.ied; g.jsd = d.jsd; g.jed = d.jed;
+  g.isdw = d.isdw; g.iedw = d.iedw; g.jsdw = d.jsdw; g.jedw = d.jedw;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return MOM6CU_ERR_CUDA;
+  }
+  *out = c;
+  return 0;
+}
+
+int mom6cu_destroy(mom6cu_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->bufs) cudaFree(kv.second);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  delete c;
+  return 0;
+}
+
+int mom6cu_last_error(const mom6cu_ctx* c, char* b, size_t len) {
+  if (!b || len == 0) return MOM6CU_ERR_BAD_ARG;
+  if (!c) { b[0] = 0; return MOM6CU_ERR_BAD_ARG; }
+  strncpy(b, c->err, len - 1);
+  b[len - 1] = 0;
+  return 0;
+}
+
+long long mom6cu_launch_count(const mom6cu_ctx* c) { return c ? c->launches : 0; }
+double mom6cu_last_kernel_ms(const mom6cu_ctx* c) { return c ? c->last_ms : 0.0; }
+
+int mom6cu_sync(mom6cu_ctx* c) {
+  if (!c) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  M6_CUDA(c, cudaStreamSynchronize(c->side));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Host-side context of the C ABI (one per rank / GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+#include "../../include/mom6cu.h"
+#include "common.cuh"
+
+enum { ST_H = 0, ST_U = 1, ST_V = 2, ST_Q = 3 };
+
+struct mom6cu_ctx {
+  mom6cu_domain dom;
+  m6::Geom g;
+  int device = 0;
+  cudaStream_t stream = nullptr;  // compute stream
+  cudaStream_t side = nullptr;    // halo-exchange stream
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr;
+  double last_ms = 0.0;
+  long long launches = 0;
+  int warnings = 0;
+  char err[1024] = {0};
+  std::map<std::string, double*> bufs;
+  std::map<std::string, size_t> buf_sz;
+  void* comm = nullptr;  // ncclComm_t when multi-rank
+  int rank = 0, nranks = 1;
+
+  // named, persistent, zero-initialised device buffer of n doubles
+  double* buf(const std::string& name, size_t n);
+  double* plane2(const std::string& name) { return buf(name, (size_t)g.plane); }
+  double* plane3(const std::string& name) { return buf(name, (size_t)g.plane * g.nk); }
+  double* plane3k(const std::string& name, int nk) { return buf(name, (size_t)g.plane * nk); }
+  int fail(int code, const char* fmt, ...);
+};
+
+#define M6_CUDA(ctx, call)                                                              \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return (ctx)->fail(MOM6CU_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,   \
+                         cudaGetErrorString(e_));                                       \
+  } while (0)
+
+#define M6_LAUNCH(ctx, kern, grid, block, smem, ...)                                    \
+  do {                                                                                  \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+    (ctx)->launches++;                                                                  \
+  } while (0)
+
+// extents of a Fortran array of the given stagger on G (wide=0) or the wide domain
+void m6_extent(const mom6cu_ctx* c, int stagger, int wide, int* ilo, int* ihi, int* jlo, int* jhi);
+bool m6_is_device_ptr(const void* p);
+// copy a Fortran-shaped (host or device) array into / out of unified planes
+int m6_up(mom6cu_ctx* c, const double* src, int stagger, int wide, int nk, double* dst);
+int m6_down(mom6cu_ctx* c, const double* src_plane, int stagger, int wide, int nk, double* dst);
+// array-of-structs (nm reals per point, m fastest) -> nm separate planes
+int m6_up_aos(mom6cu_ctx* c, const double* src, int nm, int stagger, int wide, double* const* dst);

@@ -1,0 +1,215 @@
+"""Seeded synthetic inputs for the hot path: beta-plane Cartesian grid, reentrant
+in x, closed in y, Gaussian seamount, optional land blocks.  Used by tests/ and bench.py only.
+"""
+import numpy as np
+
+from . import fidx
+from .api import make_domain
+
+SEED = 102030405  # echoes config_src/drivers/timing_tests/time_MOM_remapping.F90:53
+
+
+def rng(seed=SEED):
+    return np.random.Generator(np.random.MT19937(seed))
+
+
+def _sym_u(dom, f):
+    """make a u-field periodic-consistent on the shared edge and fill its halos"""
+    if dom.cyclic_x:
+        f.s(dom.isc - 1, dom.isc - 1, f.jlo, f.jhi)[...] = f.s(dom.iec, dom.iec, f.jlo, f.jhi)
+    return fidx.fill_halo(dom, f, "u")
+
+
+def _sym_v(dom, f):
+    if dom.cyclic_y:
+        f.s(f.ilo, f.ihi, dom.jsc - 1, dom.jsc - 1)[...] = f.s(f.ilo, f.ihi, dom.jec, dom.jec)
+    return fidx.fill_halo(dom, f, "v")
+
+
+def masks_and_depth(dom, wide=True, land_blocks=0, seed=SEED, dx=1.0e4):
+    """mask2dT/Cu/Cv and bathyT on the (wide) memory domain."""
+    r = rng(seed + 7)
+    ni, nj = dom.iec - dom.isc + 1, dom.jec - dom.jsc + 1
+    mT = fidx.new(dom, "h", wide)
+    D = fidx.new(dom, "h", wide)
+    ii = np.arange(dom.isc, dom.iec + 1)[None, :]
+    jj = np.arange(dom.jsc, dom.jec + 1)[:, None]
+    x = (ii - dom.isc + 0.5) / ni - 0.5
+    y = (jj - dom.jsc + 0.5) / nj - 0.5
+    depth = 4000.0 - 2000.0 * np.exp(-((x / 0.15) ** 2 + (y / 0.15) ** 2))
+    m = np.ones((nj, ni))
+    if not dom.cyclic_y:
+        m[0, :] = 0.0
+        m[-1, :] = 0.0
+    if not dom.cyclic_x:
+        m[:, 0] = 0.0
+        m[:, -1] = 0.0
+    for _ in range(land_blocks):
+        bi, bj = int(r.integers(0, ni)), int(r.integers(1, max(2, nj - 1)))
+        wi, wj = int(r.integers(1, max(2, ni // 6))), int(r.integers(1, max(2, nj // 6)))
+        m[bj:bj + wj, bi:bi + wi] = 0.0
+    mT.s(dom.isc, dom.iec, dom.jsc, dom.jec)[...] = m
+    D.s(dom.isc, dom.iec, dom.jsc, dom.jec)[...] = depth * m
+    fidx.fill_halo(dom, mT, "h")
+    fidx.fill_halo(dom, D, "h")
+    mU = fidx.new(dom, "u", wide)
+    mV = fidx.new(dom, "v", wide)
+    # a face is open when both neighbouring cells are ocean
+    mU.s(mU.ilo + 1, mU.ihi - 1, mU.jlo, mU.jhi)[...] = (
+        mT.s(mT.ilo, mT.ihi - 1, mT.jlo, mT.jhi) * mT.s(mT.ilo + 1, mT.ihi, mT.jlo, mT.jhi))
+    mV.s(mV.ilo, mV.ihi, mV.jlo + 1, mV.jhi - 1)[...] = (
+        mT.s(mT.ilo, mT.ihi, mT.jlo, mT.jhi - 1) * mT.s(mT.ilo, mT.ihi, mT.jlo + 1, mT.jhi))
+    return mT, mU, mV, D
+
+
+def bt_timeloop_inputs(ni, nj, whalo=10, halo=4, nstep=60, nfilter=8, seed=SEED, use_BT_cont=True,
+                       project=False, find_etaav=True, cyclic_x=True, cyclic_y=False, first_direction=0,
+                       land_blocks=0, bracket_bug=False, dx=1.0e4, dtbt=None):
+    """Inputs of btstep_timeloop (MOM_barotropic.F90:2175) on the wide-halo domain -- the BASELINE.json
+    'btstep microbench' shape: eta~0.1U, ubt,vbt~0.05U, gtot=9.8, bt_rem=1-1e-4, f_4=f/4*D/D, ..."""
+    dom = make_domain(ni, nj, nk=1, halo=halo, whalo=whalo, cyclic_x=cyclic_x, cyclic_y=cyclic_y,
+                      first_direction=first_direction)
+    r = rng(seed)
+    mT, mU, mV, D = masks_and_depth(dom, True, land_blocks, seed, dx)
+
+    def U(st):
+        # random numbers live on the (symmetric) computational domain only, so the inputs do not
+        # depend on the halo width; halos are filled afterwards by the halo update.
+        f = fidx.new(dom, st, True)
+        f.s(dom.isc - 1, dom.iec, dom.jsc - 1, dom.jec)[...] = r.uniform(-1.0, 1.0, size=(nj + 1, ni + 1))
+        return f.a
+    g = 9.8
+    if dtbt is None:
+        dtbt = 0.5 * dx / np.sqrt(2.0 * g * 4000.0)  # gravity-wave CFL ~ 0.5
+
+    def hfield(scale, mask=True):
+        f = fidx.new(dom, "h", True)
+        f.a[...] = scale * U("h") * (mT.a if mask else 1.0)
+        return fidx.fill_halo(dom, f, "h")
+
+    def ufield(scale):
+        f = fidx.new(dom, "u", True)
+        f.a[...] = scale * U("u") * mU.a
+        return _sym_u(dom, f)
+
+    def vfield(scale):
+        f = fidx.new(dom, "v", True)
+        f.a[...] = scale * U("v") * mV.a
+        return _sym_v(dom, f)
+
+    a = {}
+    a["eta"] = hfield(0.1)
+    a["ubt"] = ufield(0.05)
+    a["vbt"] = vfield(0.05)
+    a["uhbt0"] = ufield(1.0e2)
+    a["vhbt0"] = vfield(1.0e2)
+    a["eta_src"] = hfield(1.0e-6)
+    a["eta_PF"] = hfield(0.05)
+    for k in ("gtot_E", "gtot_W", "gtot_N", "gtot_S"):
+        f = fidx.new(dom, "h", True)
+        f.a[...] = g * (1.0 + 1.0e-3 * U("h")) * mT.a
+        a[k] = fidx.fill_halo(dom, f, "h")
+    # depths at faces
+    Du = fidx.new(dom, "u", True)
+    Du.s(Du.ilo + 1, Du.ihi - 1, Du.jlo, Du.jhi)[...] = 0.5 * (
+        D.s(D.ilo, D.ihi - 1, D.jlo, D.jhi) + D.s(D.ilo + 1, D.ihi, D.jlo, D.jhi))
+    Du.a *= mU.a
+    Dv = fidx.new(dom, "v", True)
+    Dv.s(Dv.ilo, Dv.ihi, Dv.jlo + 1, Dv.jhi - 1)[...] = 0.5 * (
+        D.s(D.ilo, D.ihi, D.jlo, D.jhi - 1) + D.s(D.ilo, D.ihi, D.jlo + 1, D.jhi))
+    Dv.a *= mV.a
+    # Sadourny-style Coriolis weights ~ f/4 (btstep_find_Cor :2866-2880), here simply f/4 with noise
+    f0, beta = 1.0e-4, 2.0e-11
+    jv = np.arange(dom.jsdw - 1, dom.jedw + 1)
+    f4u = fidx.new(dom, "u", True, nm=4)
+    f4v = fidx.new(dom, "v", True, nm=4)
+    yu = (np.arange(dom.jsdw, dom.jedw + 1) - dom.jsc) * dx
+    yv = (jv - dom.jsc + 0.5) * dx
+    for m in range(4):
+        fu = fidx.new(dom, "u", True)
+        fu.a[...] = 0.25 * (f0 + beta * yu)[:, None] * (1.0 + 0.01 * U("u")) * mU.a
+        f4u.a[..., m] = _sym_u(dom, fu).a
+        fv = fidx.new(dom, "v", True)
+        fv.a[...] = 0.25 * (f0 + beta * yv)[:, None] * (1.0 + 0.01 * U("v")) * mV.a
+        f4v.a[..., m] = _sym_v(dom, fv).a
+    a["f_4_u"], a["f_4_v"] = f4u, f4v
+    for nm, mk, sym, st in (("bt_rem_u", mU, _sym_u, "u"), ("bt_rem_v", mV, _sym_v, "v")):
+        f = fidx.new(dom, st, True)
+        f.a[...] = (1.0 - 1.0e-4 * (1.0 + 0.5 * U(st))) * mk.a
+        a[nm] = sym(dom, f)
+    a["BT_force_u"] = ufield(1.0e-6)
+    a["BT_force_v"] = vfield(1.0e-6)
+    a["Cor_ref_u"] = ufield(1.0e-7)
+    a["Cor_ref_v"] = vfield(1.0e-7)
+    IareaT = fidx.new(dom, "h", True)
+    IareaT.a[...] = mT.a / (dx * dx)
+    a["IareaT_OBCmask"] = IareaT
+    Idx = fidx.new(dom, "u", True); Idx.a[...] = 1.0 / dx
+    Idy = fidx.new(dom, "v", True); Idy.a[...] = 1.0 / dx
+    a["IdxCu"], a["IdyCv"] = Idx, Idy
+    # transport closure
+    FA0u = fidx.new(dom, "u", True); FA0u.a[...] = dx * Du.a * (1.0 + 0.01 * U("u")); _sym_u(dom, FA0u)
+    FA0v = fidx.new(dom, "v", True); FA0v.a[...] = dx * Dv.a * (1.0 + 0.01 * U("v")); _sym_v(dom, FA0v)
+    a["Datu"], a["Datv"] = FA0u, FA0v
+    C1_3 = 1.0 / 3.0
+
+    def btcl(FA0):
+        # set_local_BT_cont_types, MOM_barotropic.F90:4956-4977; field order :367-390
+        b = fidx.FA(FA0.ilo, FA0.ihi, FA0.jlo, FA0.jhi, nm=10)
+        FA_EE = 1.02 * FA0.a; FA_E0 = FA0.a; FA_W0 = FA0.a * 1.0; FA_WW = 1.02 * FA0.a
+        uBT_WW = np.where(FA0.a > 0.0, 0.03, 0.0); uBT_EE = -uBT_WW
+        uh_EE = uBT_EE * (C1_3 * (2.0 * FA_E0 + FA_EE))
+        uh_WW = uBT_WW * (C1_3 * (2.0 * FA_W0 + FA_WW))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            crvW = np.where(np.abs(uBT_WW) > 0.0, (C1_3 * (FA_WW - FA_W0)) / uBT_WW ** 2, 0.0)
+            crvE = np.where(np.abs(uBT_EE) > 0.0, (C1_3 * (FA_EE - FA_E0)) / uBT_EE ** 2, 0.0)
+        for m, v in enumerate((FA_EE, FA_E0, FA_W0, FA_WW, uBT_WW, uBT_EE, crvW, crvE, uh_WW, uh_EE)):
+            b.a[..., m] = v
+        return b
+
+    a["BTCL_u"], a["BTCL_v"] = btcl(FA0u), btcl(FA0v)
+    # accumulators
+    a["u_accel_bt"] = fidx.new(dom, "u", True)
+    a["v_accel_bt"] = fidx.new(dom, "v", True)
+    a["eta_sum"] = fidx.new(dom, "h", True)
+    a["eta_wtd"] = fidx.new(dom, "h", True)
+    for k, st in (("ubtav", "u"), ("vbtav", "v"), ("uhbtav", "u"), ("vhbtav", "v"), ("ubt_wtd", "u"), ("vbt_wtd", "v")):
+        a[k] = fidx.new(dom, st, False)
+    # filter weights, MOM_barotropic.F90:1727-1781 (answer_date >= 20190101 branch)
+    wts = bt_weights(nstep, nfilter, dtbt)
+    arrays = {k: (v.a if isinstance(v, fidx.FA) else v) for k, v in a.items()}
+    arrays.update(wts)
+    arrays.update(dict(dtbt=float(dtbt), dgeo_de=1.0, bebt=0.1, vel_underflow=1.0e-30, nstep=nstep, nfilter=nfilter,
+                       use_BT_cont=int(use_BT_cont), find_etaav=int(find_etaav), BT_project_velocity=int(project),
+                       use_old_coriolis_bracket_bug=int(bracket_bug), use_wide_halos=1, min_stencil=0))
+    return dom, arrays
+
+
+def bt_weights(nstep, nfilter, dtbt):
+    """wt_vel, wt_eta, wt_accel, wt_trans, wt_accel2 -- MOM_barotropic.F90:1738-1781 with the ramp
+    filter width implied by nfilter (dt_filt = nfilter*dtbt)."""
+    dt_filt = nfilter * dtbt
+    n_tot = nstep + nfilter
+    wt_vel = np.zeros(n_tot); wt_eta = np.zeros(n_tot)
+    wt_trans = np.zeros(n_tot + 1); wt_accel = np.zeros(n_tot + 1); wt_accel2 = np.zeros(n_tot + 1)
+    sum_wt_vel = sum_wt_eta = sum_wt_accel = sum_wt_trans = 0.0
+    for n in range(1, n_tot + 1):
+        if (n == nstep) or (dt_filt - abs(n - nstep) * dtbt >= 0.0):
+            wt_vel[n - 1] = 1.0; wt_eta[n - 1] = 1.0
+        elif dtbt + dt_filt - abs(n - nstep) * dtbt > 0.0:
+            wt_vel[n - 1] = 1.0 + (dt_filt / dtbt) - abs(n - nstep); wt_eta[n - 1] = wt_vel[n - 1]
+        else:
+            wt_vel[n - 1] = 0.0; wt_eta[n - 1] = 0.0
+        sum_wt_vel += wt_vel[n - 1]; sum_wt_eta += wt_eta[n - 1]
+    for n in range(n_tot, 0, -1):
+        wt_trans[n - 1] = wt_trans[n] + wt_eta[n - 1]
+        wt_accel[n - 1] = wt_accel[n] + wt_vel[n - 1]
+        sum_wt_accel += wt_accel[n - 1]; sum_wt_trans += wt_trans[n - 1]
+    I_vel, I_accel, I_eta, I_trans = 1.0 / sum_wt_vel, 1.0 / sum_wt_accel, 1.0 / sum_wt_eta, 1.0 / sum_wt_trans
+    for n in range(n_tot):
+        wt_vel[n] *= I_vel
+        wt_accel2[n] = wt_accel[n] * I_accel
+        wt_trans[n] *= I_trans
+        wt_accel[n] *= I_accel
+        wt_eta[n] *= I_eta
+    return dict(wt_vel=wt_vel, wt_eta=wt_eta, wt_accel=wt_accel, wt_trans=wt_trans, wt_accel2=wt_accel2)

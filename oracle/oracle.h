@@ -1,0 +1,39 @@
+/* TEST INFRASTRUCTURE ONLY.
+ * CPU oracle: a plain C++ restatement of the reference Fortran (mom-ocean/MOM6 @ b18bca24)
+ * for the split-explicit dycore hot path.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library; the product
+ * (mom6_b200/) never links, imports or calls it.
+ *
+ * Parity status: the reference cannot be compiled in the build container (no Fortran
+ * compiler, MPI, netCDF or FMS), so every routine here follows the cited Fortran lines
+ * loop-for-loop with identical parenthesisation and is compiled -O2 -ffp-contract=off.
+ *   - ALE remapping: PINNED against the reference's known-answer vectors
+ *     (src/ALE/MOM_remapping.F90:2072+), see tests/test_oracle_remap_kat.py.
+ *   - everything else: "parity unpinned" by static vectors (the reference holds none);
+ *     pinned only by the reference's own invariance properties re-expressed in tests/.
+ */
+#ifndef MOM6_ORACLE_H
+#define MOM6_ORACLE_H
+#include "../include/mom6cu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Optional hook standing in for do_group_pass(CS%pass_eta_ubt, CS%BT_Domain)
+ * (MOM_barotropic.F90:2512).  NULL = single tile: cyclic wrap where the domain
+ * says cyclic, no-op at closed edges (what mpp_update_domains does there). */
+typedef void (*oracle_halo_fn)(void* user, double* eta, double* ubt, double* vbt);
+
+/* btstep_timeloop, MOM_barotropic.F90:2175-2832 */
+int oracle_btstep_timeloop(const mom6cu_domain* dom, const mom6cu_bt_timeloop_args* a,
+                           oracle_halo_fn halo, void* user, int nthreads);
+
+/* single-tile halo fill used by the default hook and by tests:
+ * stagger 0=h,1=u,2=v,3=q; fills halo points of a wide (wide=1) or G-sized array */
+void oracle_fill_halo_2d(const mom6cu_domain* dom, double* f, int stagger, int wide);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,36 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/oracle.h)."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile the C++ restatement with the committed recipe (oracle/Makefile)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+    return _lib
+
+
+def btstep_timeloop(dom, args, nthreads=1):
+    """oracle_btstep_timeloop: MOM_barotropic.F90:2175-2832 on host arrays, in place."""
+    from mom6_b200._lib import BtTimeloopArgs, fill_struct
+    lib = load()
+    keep = []
+    st = fill_struct(BtTimeloopArgs(), args, keep)
+    lib.oracle_btstep_timeloop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = lib.oracle_btstep_timeloop(C.byref(dom), C.byref(st), None, None, nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_btstep_timeloop rc={rc}")
+    return rc
