@@ -76,6 +76,28 @@ int mom6cu_sync(mom6cu_ctx* ctx);
 /* Device-time (ms) of the most recent compute entry, measured with CUDA
  * events on the launching stream (excludes host<->device staging). */
 double mom6cu_last_kernel_ms(const mom6cu_ctx* ctx);
+/* Sum of the device times of all repetitions of the most recent *_resident call. */
+double mom6cu_total_kernel_ms(const mom6cu_ctx* ctx);
+
+/* ------------------------------------------------------- halo communication */
+/* The reference's halo API (pass_var / pass_vector / do_group_pass,
+ * src/framework/MOM_domains.F90 -> config_src/infra/FMS2/MOM_domain_infra.F90:171-216,
+ * :1141-1200) is FMS mpp_update_domains over MPI.  Here each group pass is one pack
+ * kernel + ncclSend/ncclRecv to the <=8 neighbour tiles + one unpack kernel.
+ * mom6cu_comm_unique_id: rank 0 creates the ncclUniqueId (>=128 bytes buffer), the host
+ * (MPI_Bcast in the Fortran shim, torch.distributed in the harness) broadcasts it, every
+ * rank calls mom6cu_comm_init. */
+int mom6cu_comm_unique_id(void* out, int nbytes);
+int mom6cu_comm_init(mom6cu_ctx* ctx, const void* id_bytes, int nbytes, int rank, int nranks);
+int mom6cu_comm_destroy(mom6cu_ctx* ctx);
+/* Host-only planning of one neighbour message (no device needed): for direction
+ * dir in 0..7 = {E,W,N,S,NE,SW,SE,NW} returns the peer rank (-1: closed edge) and the
+ * inclusive Fortran index boxes {i0,i1,j0,j1} of what is sent (from the computational
+ * domain) and what is received (into the halo), with the symmetric-memory rule that the
+ * shared edge of staggered fields is never overwritten.  stagger 0=h,1=u,2=v,3=q;
+ * halo<0 = full halo width of the (wide ? barotropic : G) memory domain. */
+int mom6cu_halo_plan(const mom6cu_domain* dom, int stagger, int wide, int halo, int dir,
+                     int* send_box, int* recv_box);
 
 /* ------------------------------------------------ barotropic substep loop  */
 /* btstep_timeloop, src/core/MOM_barotropic.F90:2175-2832 (private to the

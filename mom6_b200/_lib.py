@@ -75,6 +75,13 @@ def bind(lib):
     lib.mom6cu_sync.argtypes = [vp]
     lib.mom6cu_last_kernel_ms.argtypes = [vp]
     lib.mom6cu_last_kernel_ms.restype = C.c_double
+    lib.mom6cu_total_kernel_ms.argtypes = [vp]
+    lib.mom6cu_total_kernel_ms.restype = C.c_double
+    lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
+    lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.mom6cu_comm_destroy.argtypes = [vp]
+    lib.mom6cu_halo_plan.argtypes = [C.POINTER(Domain), C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mom6cu_btstep_timeloop.argtypes = [vp, C.POINTER(BtTimeloopArgs)]
     lib.mom6cu_btstep_timeloop_resident.argtypes = [vp, C.POINTER(BtTimeloopArgs), C.c_int, C.c_int]
     return lib

@@ -52,6 +52,25 @@ class Context:
     def last_kernel_ms(self):
         return float(self.lib.mom6cu_last_kernel_ms(self._h))
 
+    @property
+    def total_kernel_ms(self):
+        return float(self.lib.mom6cu_total_kernel_ms(self._h))
+
+    def attach_comm(self, dist):
+        """Create the NCCL communicator for halo exchanges; torch.distributed only ferries the
+        ncclUniqueId (plumbing)."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            self._check(self.lib.mom6cu_comm_unique_id(idbuf, 128))
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self._check(self.lib.mom6cu_comm_init(self._h, raw, len(raw), rank, world))
+
     def sync(self):
         self._check(self.lib.mom6cu_sync(self._h))
 

@@ -453,31 +453,32 @@ extern "C" int mom6cu_btstep_timeloop_resident(mom6cu_ctx* c, const mom6cu_bt_ti
   if ((rc = bt_alloc(c, D))) return rc;
   if ((rc = bt_upload(c, D, a))) return rc;
   int slot = 0;
-  if (reps <= 1) {
+  // keep pristine copies of everything the loop modifies so every repetition starts from the
+  // same state (device-to-device restores, outside the timed region)
+  const size_t pb = (size_t)c->g.plane * sizeof(double);
+  double* keep = nullptr;
+  double* srcs[5] = {D.eta[0], D.ubt[0], D.vbt[0], D.P.u_accel_bt, D.P.v_accel_bt};
+  if (reps > 1) {
+    keep = c->buf("bt.__keep", (size_t)5 * c->g.plane);
+    if (!keep) return MOM6CU_ERR_CUDA;
+    for (int m = 0; m < 5; ++m)
+      M6_CUDA(c, cudaMemcpyAsync(keep + (size_t)m * c->g.plane, srcs[m], pb, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  c->total_ms = 0.0;
+  for (int r = 0; r < (reps > 1 ? reps : 1); ++r) {
+    if (reps > 1)
+      for (int m = 0; m < 5; ++m)
+        M6_CUDA(c, cudaMemcpyAsync(srcs[m], keep + (size_t)m * c->g.plane, pb, cudaMemcpyDeviceToDevice, c->stream));
     M6_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if ((rc = bt_run(c, D, a, &slot))) return rc;
     M6_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-  } else {
-    // keep pristine copies of everything the loop modifies so every repetition starts
-    // from the same state (device-to-device restores, outside the timed region)
-    const size_t pb = (size_t)c->g.plane * sizeof(double);
-    double* keep = c->buf("bt.__keep", (size_t)5 * c->g.plane);
-    if (!keep) return MOM6CU_ERR_CUDA;
-    double* srcs[5] = {D.eta[0], D.ubt[0], D.vbt[0], D.P.u_accel_bt, D.P.v_accel_bt};
-    for (int m = 0; m < 5; ++m)
-      M6_CUDA(c, cudaMemcpyAsync(keep + (size_t)m * c->g.plane, srcs[m], pb, cudaMemcpyDeviceToDevice, c->stream));
-    for (int r = 0; r < reps; ++r) {
-      for (int m = 0; m < 5; ++m)
-        M6_CUDA(c, cudaMemcpyAsync(srcs[m], keep + (size_t)m * c->g.plane, pb, cudaMemcpyDeviceToDevice, c->stream));
-      M6_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-      if ((rc = bt_run(c, D, a, &slot))) return rc;
-      M6_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    }
+    M6_CUDA(c, cudaEventSynchronize(c->ev1));
+    float ms1 = 0.f;
+    M6_CUDA(c, cudaEventElapsedTime(&ms1, c->ev0, c->ev1));
+    c->total_ms += ms1;
+    c->last_ms = ms1;
   }
   if (download && (rc = bt_download(c, D, a, slot))) return rc;
   M6_CUDA(c, cudaStreamSynchronize(c->stream));
-  float ms = 0.f;
-  M6_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->last_ms = ms;
   return 0;
 }

@@ -18,7 +18,8 @@ struct mom6cu_ctx {
   cudaStream_t stream = nullptr;  // compute stream
   cudaStream_t side = nullptr;    // halo-exchange stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr;
-  double last_ms = 0.0;
+  double last_ms = 0.0;   // device time of the most recent compute entry / repetition
+  double total_ms = 0.0;  // summed over the repetitions of the most recent resident call
   long long launches = 0;
   int warnings = 0;
   char err[1024] = {0};

@@ -213,3 +213,54 @@ def bt_weights(nstep, nfilter, dtbt):
         wt_accel[n] *= I_accel
         wt_eta[n] *= I_eta
     return dict(wt_vel=wt_vel, wt_eta=wt_eta, wt_accel=wt_accel, wt_trans=wt_trans, wt_accel2=wt_accel2)
+
+
+def split_tile(dom_g, arrays_g, npi, npj, pi, pj):
+    """Cut one rank's tile (with its halos) out of single-tile (global) inputs: what each PE of a
+    LAYOUT=npi,npj run holds after the reference's halo updates (MOM_domains.F90:154-222)."""
+    NI, NJ = dom_g.iec - dom_g.isc + 1, dom_g.jec - dom_g.jsc + 1
+    ni, nj = NI // npi, NJ // npj
+    halo, whalo = dom_g.isc - dom_g.isd, dom_g.isc - dom_g.isdw
+    dom = make_domain(ni, nj, nk=dom_g.nk, halo=halo, whalo=whalo, cyclic_x=bool(dom_g.cyclic_x),
+                      cyclic_y=bool(dom_g.cyclic_y), first_direction=dom_g.first_direction,
+                      npi=npi, npj=npj, pi=pi, pj=pj)
+    oi, oj = pi * ni, pj * nj
+    out = {}
+    for k, v in arrays_g.items():
+        if not isinstance(v, np.ndarray) or k.startswith("wt_"):
+            out[k] = v
+            continue
+        # identify stagger / domain from the global shape
+        found = False
+        for st in ("h", "u", "v", "q"):
+            for wide in (True, False):
+                ilo, ihi, jlo, jhi = fidx.extent(dom_g, st, wide)
+                if v.shape[-2 if v.ndim == 2 or v.shape[-1] not in (4, 10) else -3:][:2] == (jhi - jlo + 1, ihi - ilo + 1) \
+                        and _stagger_of(k) == st:
+                    tl = fidx.extent(dom, st, wide)
+                    j0, i0 = tl[2] + oj - jlo, tl[0] + oi - ilo
+                    sl = (slice(j0, j0 + tl[3] - tl[2] + 1), slice(i0, i0 + tl[1] - tl[0] + 1))
+                    if v.ndim == 3 and v.shape[-1] not in (4, 10):
+                        sl = (slice(None),) + sl
+                    out[k] = np.ascontiguousarray(v[sl])
+                    found = True
+                    break
+            if found:
+                break
+        if not found:
+            raise ValueError(f"split_tile: cannot place {k} {v.shape}")
+    return dom, out
+
+
+_U_KEYS = {"ubt", "uhbt0", "Datu", "BTCL_u", "f_4_u", "bt_rem_u", "BT_force_u", "Cor_ref_u", "IdxCu", "u_accel_bt",
+           "ubtav", "uhbtav", "ubt_wtd"}
+_V_KEYS = {"vbt", "vhbt0", "Datv", "BTCL_v", "f_4_v", "bt_rem_v", "BT_force_v", "Cor_ref_v", "IdyCv", "v_accel_bt",
+           "vbtav", "vhbtav", "vbt_wtd"}
+
+
+def _stagger_of(key):
+    if key in _U_KEYS:
+        return "u"
+    if key in _V_KEYS:
+        return "v"
+    return "h"

@@ -7,6 +7,7 @@
 #include "farray.hpp"
 #include <cstdlib>
 #include <algorithm>
+#include <omp.h>
 
 using namespace orc;
 
@@ -50,6 +51,7 @@ extern "C" void oracle_fill_halo_2d(const mom6cu_domain* d, double* f, int stagg
   // mpp_update_domains): points of the (symmetric) computational domain, including the
   // shared edge I=isc-1 / J=jsc-1 of staggered fields, are never overwritten.
   if (d->cyclic_x) {
+    _Pragma("omp parallel for")
     for (int j = jsd - sv; j <= jed; ++j) {
       for (int i = isd - su; i <= d->isc - 1 - su; ++i) A(i, j) = A(i + ni, j);
       for (int i = d->iec + 1; i <= ied; ++i) A(i, j) = A(i - ni, j);
@@ -65,7 +67,7 @@ extern "C" void oracle_fill_halo_2d(const mom6cu_domain* d, double* f, int stagg
 
 extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_timeloop_args* a,
                                       oracle_halo_fn halo, void* user, int nthreads) {
-  (void)nthreads;
+  if (nthreads > 0) omp_set_num_threads(nthreads);
   const int is = d->isc, ie = d->iec, js = d->jsc, je = d->jec;
   const int isdw = d->isdw, iedw = d->iedw, jsdw = d->jsdw, jedw = d->jedw;
   const int isd = d->isd, ied = d->ied, jsd = d->jsd, jed = d->jed;
@@ -122,19 +124,25 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
 
   // :2455-2486  Zero out the arrays for various time-averaged quantities.
   if (find_etaav) {
+    _Pragma("omp parallel for")
     for (int j = jsvf - 1; j <= jevf + 1; ++j) for (int i = isvf - 1; i <= ievf + 1; ++i) {
       eta_sum(i, j) = 0.0; eta_wtd(i, j) = 0.0;
     }
   } else {
+    _Pragma("omp parallel for")
     for (int j = jsvf - 1; j <= jevf + 1; ++j) for (int i = isvf - 1; i <= ievf + 1; ++i) eta_wtd(i, j) = 0.0;
   }
+  _Pragma("omp parallel for")
   for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I) {
     ubtav(I, j) = 0.0; uhbtav(I, j) = 0.0; ubt_wtd(I, j) = 0.0;
   }
+  _Pragma("omp parallel for")
   for (int j = jsvf - 1; j <= jevf + 1; ++j) for (int I = isvf - 1; I <= ievf; ++I) ubt_trans(I, j) = 0.0;
+  _Pragma("omp parallel for")
   for (int J = js - 1; J <= je; ++J) for (int i = is; i <= ie; ++i) {
     vbtav(i, J) = 0.0; vhbtav(i, J) = 0.0; vbt_wtd(i, J) = 0.0;
   }
+  _Pragma("omp parallel for")
   for (int J = jsvf - 1; J <= jevf; ++J) for (int i = isvf - 1; i <= ievf + 1; ++i) vbt_trans(i, J) = 0.0;
 
   // :2504-2827  The following loop contains all of the time steps.
@@ -156,20 +164,26 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
     }
 
     // :2520-2526 Store the previous velocities for time-filtered transports.
+    _Pragma("omp parallel for")
     for (int j = jsv; j <= jev; ++j) for (int I = isv - 2; I <= iev + 1; ++I) ubt_prev(I, j) = ubt(I, j);
+    _Pragma("omp parallel for")
     for (int J = jsv - 2; J <= jev + 1; ++J) for (int i = isv; i <= iev; ++i) vbt_prev(i, J) = vbt(i, J);
 
     // :2545-2550 -> btloop_eta_predictor :3035-3058
     if (!project) {
       if (use_BT_cont) {
+        _Pragma("omp parallel for")
         for (int j = jsv - 1; j <= jev + 1; ++j) for (int I = isv - 2; I <= iev + 1; ++I)
           uhbt(I, j) = find_uhbt(ubt(I, j), BTCL_u.at(I, j)) + uhbt0(I, j);
+        _Pragma("omp parallel for")
         for (int J = jsv - 2; J <= jev + 1; ++J) for (int i = isv - 1; i <= iev + 1; ++i)
           vhbt(i, J) = find_uhbt(vbt(i, J), BTCL_v.at(i, J)) + vhbt0(i, J);
+        _Pragma("omp parallel for")
         for (int j = jsv - 1; j <= jev + 1; ++j) for (int i = isv - 1; i <= iev + 1; ++i)
           eta_pred(i, j) = (eta(i, j) + eta_src(i, j)) + (dtbt * IareaT_OBCmask(i, j)) *
                            ((uhbt(i - 1, j) - uhbt(i, j)) + (vhbt(i, j - 1) - vhbt(i, j)));
       } else {
+        _Pragma("omp parallel for")
         for (int j = jsv - 1; j <= jev + 1; ++j) for (int i = isv - 1; i <= iev + 1; ++i)
           eta_pred(i, j) = (eta(i, j) + eta_src(i, j)) + (dtbt * IareaT_OBCmask(i, j)) *
                            (((Datu(i - 1, j) * ubt(i - 1, j) + uhbt0(i - 1, j)) -
@@ -188,12 +202,14 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
       int is_v, ie_v, js_u, je_u;
       if (v_first) { is_v = isv - 1; ie_v = iev + 1; js_u = jsv; je_u = jev; }
       else { is_v = isv; ie_v = iev; js_u = jsv - 1; je_u = jev + 1; }
+      _Pragma("omp parallel for")
       for (int j = js_u; j <= je_u; ++j) for (int I = isv - 1; I <= iev; ++I) {
         const int i = I;
         PFu(I, j) = (((eta_PF_BT(i, j) - eta_PF(i, j)) * gtot_E(i, j)) -
                      ((eta_PF_BT(i + 1, j) - eta_PF(i + 1, j)) * gtot_W(i + 1, j))) *
                     dgeo_de * IdxCu(I, j);
       }
+      _Pragma("omp parallel for")
       for (int J = jsv - 1; J <= jev; ++J) for (int i = is_v; i <= ie_v; ++i) {
         const int j = J;
         PFv(i, J) = (((eta_PF_BT(i, j) - eta_PF(i, j)) * gtot_N(i, j)) -
@@ -202,6 +218,7 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
       }
       const double wt_accel2_n = a->wt_accel2[n - 1];
       if (find_etaav && (std::fabs(wt_accel2_n) > 0.0)) {
+        _Pragma("omp parallel for")
         for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i)
           eta_sum(i, j) = eta_sum(i, j) + wt_accel2_n * eta_PF_BT(i, j);
       }
@@ -211,6 +228,7 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
     // btloop_update_v :3209-3303
     auto update_v = [&](int is_v, int ie_v, int Js_v, int Je_v, bool use_bracket_bug) {
       if (use_bracket_bug) {
+        _Pragma("omp parallel for")
         for (int J = Js_v; J <= Je_v; ++J) for (int i = is_v; i <= ie_v; ++i) {
           const int I = i, j = J;
           Cor_v(i, J) = -1.0 * (((f_4_v(1, i, J) * ubt(I - 1, j)) + (f_4_v(2, i, J) * ubt(I, j))) +
@@ -218,6 +236,7 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
                         Cor_ref_v(i, J);
         }
       } else {
+        _Pragma("omp parallel for")
         for (int J = Js_v; J <= Je_v; ++J) for (int i = is_v; i <= ie_v; ++i) {
           const int I = i, j = J;
           Cor_v(i, J) = -1.0 * (((f_4_v(1, i, J) * ubt(I - 1, j)) + (f_4_v(4, i, J) * ubt(I, j + 1))) +
@@ -225,15 +244,18 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
                         Cor_ref_v(i, J);
         }
       }
+      _Pragma("omp parallel for")
       for (int J = Js_v; J <= Je_v; ++J) for (int i = is_v; i <= ie_v; ++i) {
         vbt(i, J) = bt_rem_v(i, J) * (vbt(i, J) + dtbt * ((BT_force_v(i, J) + Cor_v(i, J)) + PFv(i, J)));
         if (std::fabs(vbt(i, J)) < a->vel_underflow) vbt(i, J) = 0.0;
       }
+      _Pragma("omp parallel for")
       for (int J = Js_v; J <= Je_v; ++J) for (int i = is_v; i <= ie_v; ++i)
         v_accel_bt(i, J) = v_accel_bt(i, J) + wt_accel_n * (Cor_v(i, J) + PFv(i, J));
     };
     // btloop_update_u :3306-3384
     auto update_u = [&](int Is_u, int Ie_u, int js_u, int je_u) {
+      _Pragma("omp parallel for")
       for (int j = js_u; j <= je_u; ++j) for (int I = Is_u; I <= Ie_u; ++I) {
         const int i = I, J = j;
         Cor_u(I, j) = (((f_4_u(4, I, j) * vbt(i + 1, J)) + (f_4_u(1, I, j) * vbt(i, J - 1))) +
@@ -242,6 +264,7 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
         ubt(I, j) = bt_rem_u(I, j) * (ubt(I, j) + dtbt * ((BT_force_u(I, j) + Cor_u(I, j)) + PFu(I, j)));
         if (std::fabs(ubt(I, j)) < a->vel_underflow) ubt(I, j) = 0.0;
       }
+      _Pragma("omp parallel for")
       for (int j = js_u; j <= je_u; ++j) for (int I = Is_u; I <= Ie_u; ++I)
         u_accel_bt(I, j) = u_accel_bt(I, j) + wt_accel_n * (Cor_u(I, j) + PFu(I, j));
     };
@@ -257,19 +280,23 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
 
     // :2602-2647 Determine the transports based on the updated velocities.
     if (use_BT_cont) {
+      _Pragma("omp parallel for")
       for (int j = jsv; j <= jev; ++j) for (int I = isv - 1; I <= iev; ++I) {
         ubt_trans(I, j) = trans_wt1 * ubt(I, j) + trans_wt2 * ubt_prev(I, j);
         uhbt(I, j) = find_uhbt(ubt_trans(I, j), BTCL_u.at(I, j)) + uhbt0(I, j);
       }
+      _Pragma("omp parallel for")
       for (int J = jsv - 1; J <= jev; ++J) for (int i = isv; i <= iev; ++i) {
         vbt_trans(i, J) = trans_wt1 * vbt(i, J) + trans_wt2 * vbt_prev(i, J);
         vhbt(i, J) = find_uhbt(vbt_trans(i, J), BTCL_v.at(i, J)) + vhbt0(i, J);
       }
     } else {
+      _Pragma("omp parallel for")
       for (int j = jsv; j <= jev; ++j) for (int I = isv - 1; I <= iev; ++I) {
         ubt_trans(I, j) = trans_wt1 * ubt(I, j) + trans_wt2 * ubt_prev(I, j);
         uhbt(I, j) = Datu(I, j) * ubt_trans(I, j) + uhbt0(I, j);
       }
+      _Pragma("omp parallel for")
       for (int J = jsv - 1; J <= jev; ++J) for (int i = isv; i <= iev; ++i) {
         vbt_trans(i, J) = trans_wt1 * vbt(i, J) + trans_wt2 * vbt_prev(i, J);
         vhbt(i, J) = Datv(i, J) * vbt_trans(i, J) + vhbt0(i, J);
@@ -278,11 +305,13 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
 
     // :2689-2703 Contribute to the running sums of the transports and velocities.
     const double wt_trans_n = a->wt_trans[n - 1], wt_vel_n = a->wt_vel[n - 1];
+    _Pragma("omp parallel for")
     for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I) {
       ubtav(I, j) = ubtav(I, j) + wt_trans_n * ubt_trans(I, j);
       uhbtav(I, j) = uhbtav(I, j) + wt_trans_n * uhbt(I, j);
       ubt_wtd(I, j) = ubt_wtd(I, j) + wt_vel_n * ubt(I, j);
     }
+    _Pragma("omp parallel for")
     for (int J = js - 1; J <= je; ++J) for (int i = is; i <= ie; ++i) {
       vbtav(i, J) = vbtav(i, J) + wt_trans_n * vbt_trans(i, J);
       vhbtav(i, J) = vhbtav(i, J) + wt_trans_n * vhbt(i, J);
@@ -291,6 +320,7 @@ extern "C" int oracle_btstep_timeloop(const mom6cu_domain* d, const mom6cu_bt_ti
 
     // :2721-2727 Update eta in a corrector step using the barotropic continuity equation.
     const double wt_eta_n = a->wt_eta[n - 1];
+    _Pragma("omp parallel for")
     for (int j = jsv; j <= jev; ++j) for (int i = isv; i <= iev; ++i) {
       eta(i, j) = (eta(i, j) + eta_src(i, j)) + (dtbt * IareaT_OBCmask(i, j)) *
                   ((uhbt(i - 1, j) - uhbt(i, j)) + (vhbt(i, j - 1) - vhbt(i, j)));
