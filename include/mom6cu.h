@@ -79,6 +79,64 @@ double mom6cu_last_kernel_ms(const mom6cu_ctx* ctx);
 /* Sum of the device times of all repetitions of the most recent *_resident call. */
 double mom6cu_total_kernel_ms(const mom6cu_ctx* ctx);
 
+/* ------------------------------------------------------------ grid metrics */
+/* The fields of ocean_grid_type (src/core/MOM_grid.F90:75-175) the hot path reads.
+ * All are G-sized 2-D arrays of the staggering in the comment; uploaded once and
+ * kept resident (the reference computes them once in set_grid_metrics). */
+typedef struct mom6cu_grid {
+  const double *mask2dT, *mask2dCu, *mask2dCv, *mask2dBu;   /* h,u,v,q */
+  const double *dxT, *dyT, *IdxT, *IdyT, *areaT, *IareaT;   /* h */
+  const double *dxCu, *dyCu, *IdxCu, *IdyCu, *dy_Cu, *areaCu, *IareaCu; /* u */
+  const double *dxCv, *dyCv, *IdxCv, *IdyCv, *dx_Cv, *areaCv, *IareaCv; /* v */
+  const double *dxBu, *dyBu, *IdxBu, *IdyBu, *areaBu, *IareaBu;         /* q */
+  const double *bathyT;                                     /* h */
+  const double *CoriolisBu, *Coriolis2Bu;                   /* q */
+} mom6cu_grid;
+#define MOM6CU_GRID_NFIELDS 33
+int mom6cu_set_grid(mom6cu_ctx* ctx, const mom6cu_grid* G);
+
+/* verticalGrid_type scalars (src/core/MOM_verticalGrid.F90) */
+typedef struct mom6cu_vgrid {
+  double Angstrom_H, H_subroundoff, Z_to_H, H_to_Z, g_Earth, Rho0, H_to_RZ, RZ_to_H, H_to_m, m_to_H;
+  int Boussinesq;
+} mom6cu_vgrid;
+int mom6cu_set_vgrid(mom6cu_ctx* ctx, const mom6cu_vgrid* GV);
+
+/* ---------------------------------------------------------- continuity_PPM */
+/* continuity_PPM_CS, src/core/MOM_continuity_PPM.F90:35-67, resolved values */
+typedef struct mom6cu_continuity_cs {
+  int upwind_1st, monotonic, simple_2nd, aggress_adjust, vol_CFL, better_iter,
+      use_visc_rem_max, marginal_faces;
+  double tol_eta, tol_vel, CFL_limit_adjust;
+} mom6cu_continuity_cs;
+
+/* BT_cont_type, src/core/MOM_variables.F90:315-350 (G-sized; h_u/h_v 3-D or NULL) */
+typedef struct mom6cu_bt_cont {
+  double *FA_u_EE, *FA_u_E0, *FA_u_W0, *FA_u_WW, *uBT_WW, *uBT_EE; /* u-points */
+  double *FA_v_NN, *FA_v_N0, *FA_v_S0, *FA_v_SS, *vBT_SS, *vBT_NN; /* v-points */
+  double *h_u, *h_v;                                               /* 3-D u / v */
+} mom6cu_bt_cont;
+
+/* continuity_PPM(u, v, hin, h, uh, vh, dt, G, GV, US, CS, OBC, pbv, uhbt, vhbt, visc_rem_u,
+ *                visc_rem_v, u_cor, v_cor, BT_cont, du_cor, dv_cor)
+ * src/core/MOM_continuity_PPM.F90:86-194 (aliased `continuity`, MOM_continuity.F90:6).
+ * Optional Fortran dummies are NULL when absent (OBC must be absent: rejected).  hin and
+ * h may alias (the corrector call, MOM_dynamics_split_RK2.F90:1043). */
+typedef struct mom6cu_continuity_args {
+  const double *u, *v, *hin; /* 3-D u, v, h */
+  double *h, *uh, *vh;       /* 3-D h (inout), u, v (out) */
+  double dt;
+  const double *por_face_areaU, *por_face_areaV; /* 3-D u, v; NULL = 1 (USE_POROUS_BARRIER=False) */
+  const double *uhbt, *vhbt;             /* 2-D u, v, optional */
+  const double *visc_rem_u, *visc_rem_v; /* 3-D, optional (both or neither) */
+  double *u_cor, *v_cor;                 /* 3-D, optional out */
+  mom6cu_bt_cont* BT_cont;               /* optional */
+  double *du_cor, *dv_cor;               /* 2-D, optional out */
+} mom6cu_continuity_args;
+
+int mom6cu_set_cs_continuity(mom6cu_ctx* ctx, const mom6cu_continuity_cs* CS);
+int mom6cu_continuity(mom6cu_ctx* ctx, const mom6cu_continuity_args* a);
+
 /* ------------------------------------------------------- halo communication */
 /* The reference's halo API (pass_var / pass_vector / do_group_pass,
  * src/framework/MOM_domains.F90 -> config_src/infra/FMS2/MOM_domain_infra.F90:171-216,

@@ -37,10 +37,56 @@ class BtTimeloopArgs(C.Structure):
                 [(n, C.c_int) for n in _BT_INT])
 
 
+GRID_FIELDS = [
+    ("mask2dT", "h"), ("mask2dCu", "u"), ("mask2dCv", "v"), ("mask2dBu", "q"),
+    ("dxT", "h"), ("dyT", "h"), ("IdxT", "h"), ("IdyT", "h"), ("areaT", "h"), ("IareaT", "h"),
+    ("dxCu", "u"), ("dyCu", "u"), ("IdxCu", "u"), ("IdyCu", "u"), ("dy_Cu", "u"), ("areaCu", "u"), ("IareaCu", "u"),
+    ("dxCv", "v"), ("dyCv", "v"), ("IdxCv", "v"), ("IdyCv", "v"), ("dx_Cv", "v"), ("areaCv", "v"), ("IareaCv", "v"),
+    ("dxBu", "q"), ("dyBu", "q"), ("IdxBu", "q"), ("IdyBu", "q"), ("areaBu", "q"), ("IareaBu", "q"),
+    ("bathyT", "h"), ("CoriolisBu", "q"), ("Coriolis2Bu", "q")]
+
+
+class Grid(C.Structure):
+    """mom6cu_grid: the ocean_grid_type metrics the hot path reads (src/core/MOM_grid.F90:75-175)."""
+    _fields_ = [(n, C.c_void_p) for n, _ in GRID_FIELDS]
+
+
+class VGrid(C.Structure):
+    """mom6cu_vgrid: verticalGrid_type scalars (src/core/MOM_verticalGrid.F90)."""
+    _fields_ = [(n, C.c_double) for n in ("Angstrom_H", "H_subroundoff", "Z_to_H", "H_to_Z", "g_Earth", "Rho0",
+                                          "H_to_RZ", "RZ_to_H", "H_to_m", "m_to_H")] + [("Boussinesq", C.c_int)]
+
+
+class ContinuityCS(C.Structure):
+    """mom6cu_continuity_cs: continuity_PPM_CS (MOM_continuity_PPM.F90:35-67)."""
+    _fields_ = [(n, C.c_int) for n in ("upwind_1st", "monotonic", "simple_2nd", "aggress_adjust", "vol_CFL",
+                                       "better_iter", "use_visc_rem_max", "marginal_faces")] + \
+               [(n, C.c_double) for n in ("tol_eta", "tol_vel", "CFL_limit_adjust")]
+
+
+BT_CONT_FIELDS = ["FA_u_EE", "FA_u_E0", "FA_u_W0", "FA_u_WW", "uBT_WW", "uBT_EE",
+                  "FA_v_NN", "FA_v_N0", "FA_v_S0", "FA_v_SS", "vBT_SS", "vBT_NN", "h_u", "h_v"]
+
+
+class BTCont(C.Structure):
+    """mom6cu_bt_cont: BT_cont_type (src/core/MOM_variables.F90:315-350)."""
+    _fields_ = [(n, C.c_void_p) for n in BT_CONT_FIELDS]
+
+
+class ContinuityArgs(C.Structure):
+    """mom6cu_continuity_args: the dummy arguments of continuity_PPM (MOM_continuity_PPM.F90:86-141)."""
+    _fields_ = ([(n, C.c_void_p) for n in ("u", "v", "hin", "h", "uh", "vh")] + [("dt", C.c_double)] +
+                [(n, C.c_void_p) for n in ("por_face_areaU", "por_face_areaV", "uhbt", "vhbt", "visc_rem_u",
+                                           "visc_rem_v", "u_cor", "v_cor")] +
+                [("BT_cont", C.POINTER(BTCont))] + [(n, C.c_void_p) for n in ("du_cor", "dv_cor")])
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
         v = values.get(name)
+        if ctype is not C.c_void_p and ctype not in (C.c_int, C.c_double):
+            continue  # nested struct pointers are filled by the caller
         if ctype is C.c_void_p:
             if v is None:
                 setattr(struct, name, None)
@@ -77,6 +123,10 @@ def bind(lib):
     lib.mom6cu_last_kernel_ms.restype = C.c_double
     lib.mom6cu_total_kernel_ms.argtypes = [vp]
     lib.mom6cu_total_kernel_ms.restype = C.c_double
+    lib.mom6cu_set_grid.argtypes = [vp, C.POINTER(Grid)]
+    lib.mom6cu_set_vgrid.argtypes = [vp, C.POINTER(VGrid)]
+    lib.mom6cu_set_cs_continuity.argtypes = [vp, C.POINTER(ContinuityCS)]
+    lib.mom6cu_continuity.argtypes = [vp, C.POINTER(ContinuityArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

@@ -81,6 +81,34 @@ class Context:
         return self._check(self.lib.mom6cu_btstep_timeloop_resident(self._h, C.byref(st), reps, 1 if download else 0))
 
 
+def _ctx_methods():
+    from . import marshal
+
+    def set_grid(self, g):
+        """Upload the ocean_grid_type metrics once (src/core/MOM_grid.F90:75-175)."""
+        keep = []
+        return self._check(self.lib.mom6cu_set_grid(self._h, C.byref(marshal.grid(g, keep))))
+
+    def set_vgrid(self, gv):
+        return self._check(self.lib.mom6cu_set_vgrid(self._h, C.byref(marshal.vgrid(gv))))
+
+    def set_cs_continuity(self, cs):
+        """continuity_PPM_init's resolved parameters (MOM_continuity_PPM.F90:2674-2754)."""
+        return self._check(self.lib.mom6cu_set_cs_continuity(self._h, C.byref(marshal.continuity_cs(cs))))
+
+    def continuity(self, args):
+        """continuity_PPM, MOM_continuity_PPM.F90:86."""
+        keep = []
+        st = marshal.continuity_args(args, keep)
+        return self._check(self.lib.mom6cu_continuity(self._h, C.byref(st)))
+
+    for f in (set_grid, set_vgrid, set_cs_continuity, continuity):
+        setattr(Context, f.__name__, f)
+
+
+_ctx_methods()
+
+
 def make_domain(ni, nj, nk=1, halo=4, whalo=None, cyclic_x=True, cyclic_y=False, first_direction=0,
                 npi=1, npj=1, pi=0, pj=0):
     """Index bounds the way MOM_domains / hor_index_init set them: isc = halo+1 (1-based)."""

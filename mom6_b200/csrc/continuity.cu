@@ -1,0 +1,575 @@
+// continuity_PPM for sm_100a: one fused kernel per direction + a pointwise convergence kernel.
+//
+// Replaces src/core/MOM_continuity_PPM.F90: continuity_PPM :86-194, zonal/meridional_edge_thickness
+// :425/:472 (PPM_reconstruction_x/y :2307/:2442, PPM_limit_pos :2578, PPM_limit_CW84 :2620),
+// zonal/meridional_mass_flux :519/:1412 (flux_layer :896/:1787, flux_adjust :1093/:1992,
+// set_*_BT_cont :1246/:2143, flux_thickness :975/:1873) and the convergence updates :348/:386.
+//
+// Design (DESIGN.md "K7-K9"):
+//  * One thread owns one velocity-face column (I,j,:) [or (i,J,:)]; threads run along i so every
+//    load of a k-plane row is coalesced.  The column marches over k with everything else in
+//    registers: the layer fluxes, their k-ordered sums, the CFL bounds, the Newton/bisection
+//    iteration for the barotropic correction du (data-dependent trip count, per-thread convergence
+//    mask identical to the reference's do_I), the three test-velocity sweeps of set_*_BT_cont, and
+//    the final u_cor / BT_cont%h_u sweep.
+//  * The PPM edge thicknesses h_W/h_E (h_S/h_N) are never materialised: each flux evaluation
+//    rebuilds them from the 6 thicknesses h(i-2..i+3) with exactly the reference's arithmetic
+//    (4 fewer 3-D arrays written and re-read per call; the 6 loads replace the reference's 6 loads of
+//    h, h_W, h_E at i and i+1).
+//  * Sums over k are sequential in k (bitwise parity), never tree reductions.
+//  * The reference's rows are independent per face in every branch that the frozen option set
+//    (no OBCs) can reach, so the row-level `domore` exit is equivalent to the per-thread exit here;
+//    the oracle keeps the row structure and the parity tests check this equivalence.
+#include "ctx.h"
+#include "stage.h"
+#include <cmath>
+
+using m6::Geom;
+using m6::fmax2;
+using m6::fmin2;
+
+namespace {
+
+struct ContCS {
+  int upwind_1st, monotonic, simple_2nd, aggress_adjust, vol_CFL, better_iter, use_visc_rem_max, marginal_faces;
+  double tol_eta, tol_vel, CFL_limit_adjust, h_min_ppm /* 2*Angstrom_H */;
+};
+
+struct FluxArgs {
+  // inputs
+  const double* u; const double* h; const double* visc_rem; const double* por;  // 3-D (visc_rem/por may be null)
+  const double* uhbt;  // 2-D or null
+  // outputs
+  double* uh; double* u_cor; double* du_cor; double* h_u;  // u_cor/du_cor/h_u may be null
+  double* FA_W0; double* FA_WW; double* FA_E0; double* FA_EE; double* uBT_WW; double* uBT_EE;  // null if !set_BT_cont
+  // metrics (2-D planes)
+  const double* maskT; const double* dy_C; const double* IdxT; const double* dxT; const double* areaT;
+  const double* IareaT; const double* dxC; const double* maskC;
+  int nlo, nhi, olo, ohi;  // face index ranges
+  double dt;
+  int nk;
+};
+
+// PPM edge values of the cell whose thickness is hc, with neighbours hm2,hm1 | hp1,hp2 and the
+// masks of the same five cells.  PPM_reconstruction_x :2359-2406 + limiter.
+__device__ __forceinline__ void ppm_cell(const ContCS& CS, double hm2, double hm1, double hc, double hp1, double hp2,
+                                         double mm2, double mm1, double mc, double mp1, double mp2, double& hL,
+                                         double& hR) {
+  if (CS.upwind_1st) { hL = hc; hR = hc; return; }
+  const double h_im1 = mm1 * hm1 + (1.0 - mm1) * hc;
+  const double h_ip1 = mp1 * hp1 + (1.0 - mp1) * hc;
+  if (CS.simple_2nd) {
+    hL = 0.5 * (h_im1 + hc);
+    hR = 0.5 * (h_ip1 + hc);
+  } else {
+    const double oneSixth = 1. / 6.;
+    double s_m, s_c, s_p;
+    // slope of cell -1
+    if ((mm2 * mm1 * mc) == 0.0) s_m = 0.0;
+    else {
+      double s = 0.5 * (hc - hm2);
+      const double dMx = fmax2(fmax2(hc, hm2), hm1) - hm1;
+      const double dMn = hm1 - fmin2(fmin2(hc, hm2), hm1);
+      s_m = copysign(1., s) * fmin2(fabs(s), 2. * fmin2(dMx, dMn));
+    }
+    if ((mm1 * mc * mp1) == 0.0) s_c = 0.0;
+    else {
+      double s = 0.5 * (hp1 - hm1);
+      const double dMx = fmax2(fmax2(hp1, hm1), hc) - hc;
+      const double dMn = hc - fmin2(fmin2(hp1, hm1), hc);
+      s_c = copysign(1., s) * fmin2(fabs(s), 2. * fmin2(dMx, dMn));
+    }
+    if ((mc * mp1 * mp2) == 0.0) s_p = 0.0;
+    else {
+      double s = 0.5 * (hp2 - hc);
+      const double dMx = fmax2(fmax2(hp2, hc), hp1) - hp1;
+      const double dMn = hp1 - fmin2(fmin2(hp2, hc), hp1);
+      s_p = copysign(1., s) * fmin2(fabs(s), 2. * fmin2(dMx, dMn));
+    }
+    hL = 0.5 * (h_im1 + hc) + oneSixth * (s_m - s_c);
+    hR = 0.5 * (h_ip1 + hc) + oneSixth * (s_c - s_p);
+  }
+  if (CS.monotonic) {  // PPM_limit_CW84 :2640-2654
+    if ((hR - hc) * (hc - hL) <= 0.) { hL = hc; hR = hc; }
+    else {
+      const double RLdiff = hR - hL;
+      const double RLmean = 0.5 * (hR + hL);
+      const double FunFac = 6. * RLdiff * (hc - RLmean);
+      const double RLdiff2 = RLdiff * RLdiff;
+      if (FunFac > RLdiff2) hL = 3. * hc - 2. * hR;
+      if (FunFac < -RLdiff2) hR = 3. * hc - 2. * hL;
+    }
+  } else {  // PPM_limit_pos :2596-2614
+    const double curv = 3.0 * ((hL + hR) - 2.0 * hc);
+    if (curv > 0.0) {
+      const double dh = hR - hL;
+      if (fabs(dh) < curv) {
+        if (hc <= CS.h_min_ppm) { hL = hc; hR = hc; }
+        else if (12.0 * curv * (hc - CS.h_min_ppm) < (curv * curv + 3.0 * (dh * dh))) {
+          const double scale = 12.0 * curv * (hc - CS.h_min_ppm) / (curv * curv + 3.0 * (dh * dh));
+          hL = hc + scale * (hL - hc);
+          hR = hc + scale * (hR - hc);
+        }
+      }
+    }
+  }
+}
+
+// Per-thread column context
+struct Col {
+  double m[6];        // mask2dT of cells -2..+3 along the flow direction
+  double dy;          // G%dy_Cu(I,j) | G%dx_Cv(i,J)
+  double cfl0, cfl1;  // IdxT (or dy*IareaT when vol_CFL) of the cells 0 and +1
+  long long g;        // plane offset of the face / cell 0
+  long long sd;       // stride along the flow direction (1 | pitch)
+};
+
+// zonal_flux_layer :935-956 / merid_flux_layer; returns uh and the marginal/average thickness
+template <bool WANT_AVG>
+__device__ __forceinline__ void flux_layer(const ContCS& CS, const Col& C, const double* __restrict__ hk, double por,
+                                           double un, double visc_rem, double dt, double& uh, double& duhdu,
+                                           double& h_avg, double& h_marg) {
+  const double hm2 = __ldg(hk + C.g - 2 * C.sd), hm1 = __ldg(hk + C.g - C.sd), h0 = __ldg(hk + C.g),
+               hp1 = __ldg(hk + C.g + C.sd), hp2 = __ldg(hk + C.g + 2 * C.sd), hp3 = __ldg(hk + C.g + 3 * C.sd);
+  const double face = C.dy * por;
+  double CFL, curv_3;
+  if (un > 0.0) {
+    double hL, hR;
+    ppm_cell(CS, hm2, hm1, h0, hp1, hp2, C.m[0], C.m[1], C.m[2], C.m[3], C.m[4], hL, hR);
+    if (CS.vol_CFL) CFL = (un * dt) * C.cfl0; else CFL = un * dt * C.cfl0;
+    curv_3 = (hL + hR) - 2.0 * h0;
+    h_avg = hR + CFL * (0.5 * (hL - hR) + curv_3 * (CFL - 1.5));
+    uh = face * un * h_avg;
+    h_marg = hR + CFL * ((hL - hR) + 3.0 * curv_3 * (CFL - 1.0));
+  } else if (un < 0.0) {
+    double hL, hR;
+    ppm_cell(CS, hm1, h0, hp1, hp2, hp3, C.m[1], C.m[2], C.m[3], C.m[4], C.m[5], hL, hR);
+    if (CS.vol_CFL) CFL = (-un * dt) * C.cfl1; else CFL = -un * dt * C.cfl1;
+    curv_3 = (hL + hR) - 2.0 * hp1;
+    h_avg = hL + CFL * (0.5 * (hR - hL) + curv_3 * (CFL - 1.5));
+    uh = face * un * h_avg;
+    h_marg = hL + CFL * ((hR - hL) + 3.0 * curv_3 * (CFL - 1.0));
+  } else {
+    double hL0, hR0, hL1, hR1;
+    ppm_cell(CS, hm2, hm1, h0, hp1, hp2, C.m[0], C.m[1], C.m[2], C.m[3], C.m[4], hL0, hR0);
+    ppm_cell(CS, hm1, h0, hp1, hp2, hp3, C.m[1], C.m[2], C.m[3], C.m[4], C.m[5], hL1, hR1);
+    uh = 0.0;
+    h_marg = 0.5 * (hL1 + hR0);
+    h_avg = h_marg;
+  }
+  duhdu = face * h_marg * visc_rem;
+}
+
+// zonal_flux_adjust :1093-1242 for one column.  HAVE3D: uh_3d present (fluxes are stored).
+template <bool HAVE3D>
+__device__ void flux_adjust(const ContCS& CS, const Col& C, const FluxArgs& A, const Geom& G, double uhbt,
+                            double uh_tot_0, double duhdu_tot_0, double du_max_CFL, double du_min_CFL, double IareaT_min,
+                            double& du_out) {
+  const int nz = A.nk, max_itts = 20;
+  double du = 0.0, du_max = du_max_CFL, du_min = du_min_CFL;
+  double uh_err = uh_tot_0 - uhbt, duhdu_tot = duhdu_tot_0;
+  double uh_err_best = fabs(uh_err);
+  bool do_I = true;
+  for (int itt = 1; itt <= max_itts; ++itt) {
+    double tol_eta;
+    if (itt <= 1) tol_eta = 1e-6 * CS.tol_eta;
+    else if (itt == 2) tol_eta = 1e-4 * CS.tol_eta;
+    else if (itt == 3) tol_eta = 1e-2 * CS.tol_eta;
+    else tol_eta = CS.tol_eta;
+    const double tol_vel = CS.tol_vel;
+    if (uh_err > 0.0) du_max = du;
+    else if (uh_err < 0.0) du_min = du;
+    else do_I = false;
+    if (do_I) {
+      if ((A.dt * IareaT_min * fabs(uh_err) > tol_eta) ||
+          (CS.better_iter && ((fabs(uh_err) > tol_vel * duhdu_tot) || (fabs(uh_err) > uh_err_best)))) {
+        const double ddu = -uh_err / duhdu_tot;
+        const double du_prev = du;
+        du = du + ddu;
+        if (fabs(ddu) < 1.0e-15 * fabs(du)) {
+          do_I = false;
+        } else if (ddu > 0.0) {
+          if (du >= du_max) {
+            du = 0.5 * (du_prev + du_max);
+            if (du_max - du_prev < 1.0e-15 * fabs(du)) do_I = false;
+          }
+        } else {
+          if (du <= du_min) {
+            du = 0.5 * (du_prev + du_min);
+            if (du_prev - du_min < 1.0e-15 * fabs(du)) do_I = false;
+          }
+        }
+      } else {
+        do_I = false;
+      }
+    }
+    if (!do_I) break;
+    if ((itt < max_itts) || HAVE3D) {
+      double err = -uhbt, dtot = 0.0;
+      for (int k = 0; k < nz; ++k) {
+        const long long gk = C.g + (long long)k * G.plane;
+        const double vr = A.visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
+        const double por = A.por ? __ldg(A.por + gk) : 1.0;
+        const double u_new = __ldg(A.u + gk) + du * vr;
+        double uh, dd, ha, hm;
+        flux_layer<false>(CS, C, A.h + (long long)k * G.plane, por, u_new, vr, A.dt, uh, dd, ha, hm);
+        if (HAVE3D) A.uh[gk] = uh;
+        err = err + uh;
+        dtot = dtot + dd;
+      }
+      if (itt < max_itts) {
+        uh_err = err; duhdu_tot = dtot;
+        uh_err_best = fmin2(uh_err_best, fabs(uh_err));
+      }
+    }
+  }
+  du_out = du;
+}
+
+__device__ __forceinline__ double ratio_max(double a, double b, double maxrat) {
+  if (fabs(a) > fabs(maxrat * b)) return maxrat;
+  return a / b;
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(128) cont_flux_kernel(const Geom G, const ContCS CS, const FluxArgs A) {
+  const int n = A.nlo + blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = A.olo + blockIdx.y;
+  if (n > A.nhi || o > A.ohi) return;
+  const int nz = A.nk;
+  Col C;
+  C.g = G.idx(n, o);
+  C.sd = Z ? 1 : G.pitch;
+#pragma unroll
+  for (int m = 0; m < 6; ++m) C.m[m] = __ldg(A.maskT + C.g + (m - 2) * C.sd);
+  C.dy = __ldg(A.dy_C + C.g);
+  const double IareaT0 = __ldg(A.IareaT + C.g), IareaT1 = __ldg(A.IareaT + C.g + C.sd);
+  if (CS.vol_CFL) { C.cfl0 = C.dy * IareaT0; C.cfl1 = C.dy * IareaT1; }
+  else { C.cfl0 = __ldg(A.IdxT + C.g); C.cfl1 = __ldg(A.IdxT + C.g + C.sd); }
+  const bool use_visc_rem = A.visc_rem != nullptr;
+  const bool set_BT = A.FA_W0 != nullptr;
+  const double dt = A.dt;
+
+  // ---- Set uh and duhdu (:621-635) and their k-ordered sums (:659-662)
+  double uh_tot_0 = 0.0, duhdu_tot_0 = 0.0;
+  double visc_rem_max = (use_visc_rem && CS.use_visc_rem_max) ? 0.0 : 1.0;
+  for (int k = 0; k < nz; ++k) {
+    const long long gk = C.g + (long long)k * G.plane;
+    const double vr = use_visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
+    const double por = A.por ? __ldg(A.por + gk) : 1.0;
+    double uh, dd, ha, hm;
+    flux_layer<false>(CS, C, A.h + (long long)k * G.plane, por, __ldg(A.u + gk), vr, dt, uh, dd, ha, hm);
+    A.uh[gk] = uh;
+    duhdu_tot_0 = duhdu_tot_0 + dd;
+    uh_tot_0 = uh_tot_0 + uh;
+    if (use_visc_rem && CS.use_visc_rem_max) visc_rem_max = fmax2(visc_rem_max, vr);
+  }
+  double du = 0.0;
+  if (A.uhbt || set_BT) {
+    // ---- limits on du that keep the CFL number between -1 and 1 (:646-720)
+    double CFL_dt = CS.CFL_limit_adjust / dt;
+    const double I_dt = 1.0 / dt;
+    if (CS.aggress_adjust) CFL_dt = I_dt;
+    double I_vrm = 0.0;
+    if (visc_rem_max > 0.0) I_vrm = 1.0 / visc_rem_max;
+    double dx_W, dx_E;
+    if (CS.vol_CFL) {
+      dx_W = ratio_max(__ldg(A.areaT + C.g), C.dy, 1000.0 * __ldg(A.dxT + C.g));
+      dx_E = ratio_max(__ldg(A.areaT + C.g + C.sd), C.dy, 1000.0 * __ldg(A.dxT + C.g + C.sd));
+    } else { dx_W = __ldg(A.dxT + C.g); dx_E = __ldg(A.dxT + C.g + C.sd); }
+    double du_max_CFL = 2.0 * (CFL_dt * dx_W) * I_vrm;
+    double du_min_CFL = -2.0 * (CFL_dt * dx_E) * I_vrm;
+    const double maskC = __ldg(A.maskC + C.g);
+    for (int k = 0; k < nz; ++k) {
+      const long long gk = C.g + (long long)k * G.plane;
+      const double uk = __ldg(A.u + gk);
+      if (use_visc_rem) {
+        const double vr = __ldg(A.visc_rem + gk);
+        if (CS.aggress_adjust) {
+          double du_lim = 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + gk - C.sd)));
+          if (du_max_CFL * vr > du_lim) du_max_CFL = du_lim / vr;
+          du_lim = 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + gk + C.sd)));
+          if (du_min_CFL * vr < du_lim) du_min_CFL = du_lim / vr;
+        } else {
+          if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = (dx_W * CFL_dt - uk) / vr;
+          if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = -(dx_E * CFL_dt + uk) / vr;
+        }
+      } else {
+        if (CS.aggress_adjust) {
+          du_max_CFL = fmin2(du_max_CFL, 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + gk - C.sd))));
+          du_min_CFL = fmax2(du_min_CFL, 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + gk + C.sd))));
+        } else {
+          du_max_CFL = fmin2(du_max_CFL, dx_W * CFL_dt - uk);
+          du_min_CFL = fmax2(du_min_CFL, -(dx_E * CFL_dt + uk));
+        }
+      }
+    }
+    du_max_CFL = fmax2(du_max_CFL, 0.0);
+    du_min_CFL = fmin2(du_min_CFL, 0.0);
+    const double IareaT_min = fmin2(IareaT0, IareaT1);
+
+    if (A.uhbt) {
+      // ---- Find du and uh (:737-752)
+      flux_adjust<true>(CS, C, A, G, __ldg(A.uhbt + C.g), uh_tot_0, duhdu_tot_0, du_max_CFL, du_min_CFL, IareaT_min, du);
+      if (A.du_cor) A.du_cor[C.g] = du;
+    }
+    if (set_BT) {
+      // ---- set_zonal_BT_cont :1318-1407
+      const double Idt = 1.0 / dt;
+      const double min_visc_rem = 0.1, CFL_min = 1e-6;
+      double du0;
+      flux_adjust<false>(CS, C, A, G, 0.0, uh_tot_0, duhdu_tot_0, du_max_CFL, du_min_CFL, IareaT_min, du0);
+      const double du_CFL = (CFL_min * Idt) * __ldg(A.dxC + C.g);
+      double duR = fmin2(0.0, du0 - du_CFL);
+      double duL = fmax2(0.0, du0 + du_CFL);
+      for (int k = 0; k < nz; ++k) {
+        const long long gk = C.g + (long long)k * G.plane;
+        const double vr = use_visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
+        const double uk = __ldg(A.u + gk);
+        const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
+        if (visc_rem_lim > 0.0) {
+          if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = -(uk + du_CFL * vr) / visc_rem_lim;
+          if (uk + duL * visc_rem_lim < du_CFL * vr) duL = -(uk - du_CFL * vr) / visc_rem_lim;
+        }
+      }
+      double FAmt_L = 0.0, FAmt_R = 0.0, FAmt_0 = 0.0, uhtot_L = 0.0, uhtot_R = 0.0;
+      for (int k = 0; k < nz; ++k) {
+        const long long gk = C.g + (long long)k * G.plane;
+        const double vr = use_visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
+        const double por = A.por ? __ldg(A.por + gk) : 1.0;
+        const double uk = __ldg(A.u + gk);
+        const double u_L = uk + duL * vr, u_R = uk + duR * vr, u_0 = uk + du0 * vr;
+        double uh_0, dd_0, uh_L, dd_L, uh_R, dd_R, ha, hm;
+        const double* hk = A.h + (long long)k * G.plane;
+        flux_layer<false>(CS, C, hk, por, u_0, vr, dt, uh_0, dd_0, ha, hm);
+        flux_layer<false>(CS, C, hk, por, u_L, vr, dt, uh_L, dd_L, ha, hm);
+        flux_layer<false>(CS, C, hk, por, u_R, vr, dt, uh_R, dd_R, ha, hm);
+        FAmt_0 = FAmt_0 + dd_0;
+        FAmt_L = FAmt_L + dd_L;
+        FAmt_R = FAmt_R + dd_R;
+        uhtot_L = uhtot_L + uh_L;
+        uhtot_R = uhtot_R + uh_R;
+      }
+      double FA_0 = FAmt_0, FA_avg = FAmt_0;
+      if ((duL - du0) != 0.0) FA_avg = uhtot_L / (duL - du0);
+      if (FA_avg > fmax2(FA_0, FAmt_L)) FA_avg = fmax2(FA_0, FAmt_L);
+      else if (FA_avg < fmin2(FA_0, FAmt_L)) FA_0 = FA_avg;
+      A.FA_W0[C.g] = FA_0; A.FA_WW[C.g] = FAmt_L;
+      if (fabs(FA_0 - FAmt_L) <= 1e-12 * FA_0) A.uBT_WW[C.g] = 0.0;
+      else A.uBT_WW[C.g] = (1.5 * (duL - du0)) * ((FAmt_L - FA_avg) / (FAmt_L - FA_0));
+      FA_0 = FAmt_0; FA_avg = FAmt_0;
+      if ((duR - du0) != 0.0) FA_avg = uhtot_R / (duR - du0);
+      if (FA_avg > fmax2(FA_0, FAmt_R)) FA_avg = fmax2(FA_0, FAmt_R);
+      else if (FA_avg < fmin2(FA_0, FAmt_R)) FA_0 = FA_avg;
+      A.FA_E0[C.g] = FA_0; A.FA_EE[C.g] = FAmt_R;
+      if (fabs(FAmt_R - FA_0) <= 1e-12 * FA_0) A.uBT_EE[C.g] = 0.0;
+      else A.uBT_EE[C.g] = (1.5 * (duR - du0)) * ((FAmt_R - FA_avg) / (FAmt_R - FA_0));
+    }
+  }
+  // ---- u_cor (:743-748) and BT_cont%h_u (zonal_flux_thickness :1017-1056, called at :807-815)
+  const bool want_ucor = (A.u_cor != nullptr) && (A.uhbt != nullptr);
+  const bool want_hu = set_BT && (A.h_u != nullptr);
+  if (want_ucor || want_hu) {
+    for (int k = 0; k < nz; ++k) {
+      const long long gk = C.g + (long long)k * G.plane;
+      const double vr = use_visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
+      const double uk = __ldg(A.u + gk);
+      const double uc = uk + du * vr;
+      if (want_ucor) A.u_cor[gk] = uc;
+      if (want_hu) {
+        const double por = A.por ? __ldg(A.por + gk) : 1.0;
+        // flux_thickness uses u_cor when it is present, else u
+        const double ut = (A.u_cor != nullptr) ? ((A.uhbt != nullptr) ? uc : __ldg(A.u_cor + gk)) : uk;
+        double uh, dd, ha, hm;
+        flux_layer<true>(CS, C, A.h + (long long)k * G.plane, 1.0, ut, 1.0, dt, uh, dd, ha, hm);
+        double hu = CS.marginal_faces ? hm : ha;
+        if (use_visc_rem) hu = hu * (vr * por);
+        else if (A.por) hu = hu * por;
+        A.h_u[gk] = hu;
+      }
+    }
+  }
+}
+
+// continuity_zonal_convergence :371-378 / continuity_merdional_convergence :409-416
+template <bool Z>
+__global__ void cont_convergence_kernel(const Geom G, double* h, const double* hin, const double* uh,
+                                        const double* IareaT, double dt, double h_min, int ish, int ieh, int jsh, int jeh,
+                                        int nk) {
+  const int i = ish + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = jsh + blockIdx.y;
+  if (i > ieh || j > jeh) return;
+  const long long g = G.idx(i, j);
+  const long long sd = Z ? 1 : G.pitch;
+  const double Ia = __ldg(IareaT + g);
+  for (int k = blockIdx.z; k < nk; k += gridDim.z) {
+    const long long gk = g + (long long)k * G.plane;
+    h[gk] = fmax2(hin[gk] - dt * Ia * (uh[gk] - uh[gk - sd]), h_min);
+  }
+}
+
+__global__ void zero_plane_rect(const Geom G, double* a, int ilo, int ihi, int jlo, int jhi) {
+  const int i = ilo + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = jlo + blockIdx.y;
+  if (i <= ihi && j <= jhi) a[G.idx(i, j)] = 0.0;
+}
+
+}  // namespace
+
+// Device-resident entry: all pointers are unified planes.  Used by mom6cu_continuity and by the
+// fused step driver.
+int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D) {
+  const mom6cu_continuity_cs& S = c->cont_cs;
+  if (!c->have_cont_cs) return c->fail(MOM6CU_ERR_BAD_ARG, "MOM_continuity_PPM: Module must be initialized before it is used.");
+  if (!c->have_grid) return c->fail(MOM6CU_ERR_BAD_ARG, "continuity: mom6cu_set_grid has not been called");
+  const Geom& G = c->g;
+  const GridDev& M = c->grid;
+  ContCS CS;
+  CS.upwind_1st = S.upwind_1st; CS.monotonic = S.monotonic; CS.simple_2nd = S.simple_2nd; CS.aggress_adjust = S.aggress_adjust;
+  CS.vol_CFL = S.vol_CFL; CS.better_iter = S.better_iter; CS.use_visc_rem_max = S.use_visc_rem_max;
+  CS.marginal_faces = S.marginal_faces; CS.tol_eta = S.tol_eta; CS.tol_vel = S.tol_vel;
+  CS.CFL_limit_adjust = S.CFL_limit_adjust; CS.h_min_ppm = 2.0 * c->vgrid.Angstrom_H;
+  const int stencil = S.upwind_1st ? 1 : (S.simple_2nd ? 2 : 3);
+  const mom6cu_domain& d = c->dom;
+  if ((d.isc - d.isd) < stencil || (d.jsc - d.jsd) < stencil)
+    return c->fail(MOM6CU_ERR_BAD_ARG, "In MOM_continuity_PPM, the halo needs to be at least %d wide", stencil);
+  const double h_min = c->vgrid.Angstrom_H;  // :152
+  const bool x_first = ((d.first_direction % 2) == 0);
+  const int nk = G.nk;
+
+  auto zonal = [&](const double* hsrc, int ish, int ieh, int jsh, int jeh) {
+    FluxArgs A = {};
+    A.u = D.u; A.h = hsrc; A.visc_rem = D.visc_rem_u; A.por = D.por_face_areaU; A.uhbt = D.uhbt;
+    A.uh = D.uh; A.u_cor = D.u_cor; A.du_cor = D.du_cor; A.h_u = D.have_BT_cont ? D.h_u : nullptr;
+    if (D.have_BT_cont) { A.FA_W0 = D.FA_u_W0; A.FA_WW = D.FA_u_WW; A.FA_E0 = D.FA_u_E0; A.FA_EE = D.FA_u_EE; A.uBT_WW = D.uBT_WW; A.uBT_EE = D.uBT_EE; }
+    A.maskT = M.mask2dT; A.dy_C = M.dy_Cu; A.IdxT = M.IdxT; A.dxT = M.dxT; A.areaT = M.areaT; A.IareaT = M.IareaT;
+    A.dxC = M.dxCu; A.maskC = M.mask2dCu;
+    A.nlo = ish - 1; A.nhi = ieh; A.olo = jsh; A.ohi = jeh; A.dt = D.dt; A.nk = nk;
+    if (D.du_cor) {  // du_cor(:,:) = 0.0 (:601)
+      dim3 gz((G.ied - (G.isd - 1) + 128) / 128, G.jed - G.jsd + 1);
+      M6_LAUNCH(c, zero_plane_rect, gz, 128, 0, G, D.du_cor, G.isd - 1, G.ied, G.jsd, G.jed);
+    }
+    dim3 grid((A.nhi - A.nlo + 128) / 128, A.ohi - A.olo + 1);
+    M6_LAUNCH(c, cont_flux_kernel<true>, grid, 128, 0, G, CS, A);
+  };
+  auto merid = [&](const double* hsrc, int ish, int ieh, int jsh, int jeh) {
+    FluxArgs A = {};
+    A.u = D.v; A.h = hsrc; A.visc_rem = D.visc_rem_v; A.por = D.por_face_areaV; A.uhbt = D.vhbt;
+    A.uh = D.vh; A.u_cor = D.v_cor; A.du_cor = D.dv_cor; A.h_u = D.have_BT_cont ? D.h_v : nullptr;
+    if (D.have_BT_cont) { A.FA_W0 = D.FA_v_S0; A.FA_WW = D.FA_v_SS; A.FA_E0 = D.FA_v_N0; A.FA_EE = D.FA_v_NN; A.uBT_WW = D.vBT_SS; A.uBT_EE = D.vBT_NN; }
+    A.maskT = M.mask2dT; A.dy_C = M.dx_Cv; A.IdxT = M.IdyT; A.dxT = M.dyT; A.areaT = M.areaT; A.IareaT = M.IareaT;
+    A.dxC = M.dyCv; A.maskC = M.mask2dCv;
+    A.nlo = ish; A.nhi = ieh; A.olo = jsh - 1; A.ohi = jeh; A.dt = D.dt; A.nk = nk;
+    if (D.dv_cor) {
+      dim3 gz((G.ied - G.isd + 128) / 128, G.jed - (G.jsd - 1) + 1);
+      M6_LAUNCH(c, zero_plane_rect, gz, 128, 0, G, D.dv_cor, G.isd, G.ied, G.jsd - 1, G.jed);
+    }
+    dim3 grid((A.nhi - A.nlo + 128) / 128, A.ohi - A.olo + 1);
+    M6_LAUNCH(c, cont_flux_kernel<false>, grid, 128, 0, G, CS, A);
+  };
+  auto conv = [&](bool z, const double* hsrc, const double* flux, double hmin, int ish, int ieh, int jsh, int jeh) {
+    dim3 grid((ieh - ish + 128) / 128, jeh - jsh + 1, nk < 32 ? nk : 32);
+    if (z) M6_LAUNCH(c, cont_convergence_kernel<true>, grid, 128, 0, G, D.h, hsrc, flux, M.IareaT, D.dt, hmin, ish, ieh, jsh, jeh, nk);
+    else M6_LAUNCH(c, cont_convergence_kernel<false>, grid, 128, 0, G, D.h, hsrc, flux, M.IareaT, D.dt, hmin, ish, ieh, jsh, jeh, nk);
+  };
+  if (x_first) {
+    // First advect zonally, with loop bounds that accomodate the subsequent meridional advection (:163-169)
+    zonal(D.hin, d.isc, d.iec, d.jsc - stencil, d.jec + stencil);
+    conv(true, D.hin, D.uh, 0.0, d.isc, d.iec, d.jsc - stencil, d.jec + stencil);
+    // Now advect meridionally, using the updated thicknesses to determine the fluxes (:171-176)
+    merid(D.h, d.isc, d.iec, d.jsc, d.jec);
+    conv(false, D.h, D.vh, h_min, d.isc, d.iec, d.jsc, d.jec);
+  } else {
+    merid(D.hin, d.isc - stencil, d.iec + stencil, d.jsc, d.jec);
+    conv(false, D.hin, D.vh, 0.0, d.isc - stencil, d.iec + stencil, d.jsc, d.jec);
+    zonal(D.h, d.isc, d.iec, d.jsc, d.jec);
+    conv(true, D.h, D.uh, h_min, d.isc, d.iec, d.jsc, d.jec);
+  }
+  M6_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mom6cu_set_cs_continuity(mom6cu_ctx* c, const mom6cu_continuity_cs* CS) {
+  if (!c || !CS) return MOM6CU_ERR_BAD_ARG;
+  c->cont_cs = *CS;
+  c->have_cont_cs = true;
+  return 0;
+}
+
+extern "C" int mom6cu_continuity(mom6cu_ctx* c, const mom6cu_continuity_args* a) {
+  if (!c || !a) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  if (!a->u || !a->v || !a->hin || !a->h || !a->uh || !a->vh) return c->fail(MOM6CU_ERR_BAD_ARG, "continuity: null required argument");
+  // MOM_continuity_PPM.F90:159-161
+  if ((a->visc_rem_u != nullptr) != (a->visc_rem_v != nullptr))
+    return c->fail(MOM6CU_ERR_BAD_ARG, "MOM_continuity_PPM: Either both visc_rem_u and visc_rem_v or neither one must be "
+                                       "present in call to continuity_PPM.");
+  const int nk = c->g.nk;
+  int rc;
+  ContinuityDev D = {};
+  D.dt = a->dt;
+  auto up3 = [&](const char* name, const double* src, int st, double** dst) -> int {
+    *dst = nullptr;
+    if (!src) return 0;
+    *dst = c->plane3(std::string("cont.") + name);
+    if (!*dst) return MOM6CU_ERR_CUDA;
+    return m6_up(c, src, st, 0, nk, *dst);
+  };
+  auto up2 = [&](const char* name, const double* src, int st, double** dst) -> int {
+    *dst = nullptr;
+    if (!src) return 0;
+    *dst = c->plane2(std::string("cont.") + name);
+    if (!*dst) return MOM6CU_ERR_CUDA;
+    return m6_up(c, src, st, 0, 1, *dst);
+  };
+  double *u, *v, *hin, *h, *uh, *vh, *pu, *pv, *vru, *vrv, *ucor, *vcor, *uhbt, *vhbt, *ducor, *dvcor;
+  if ((rc = up3("u", a->u, ST_U, &u)) || (rc = up3("v", a->v, ST_V, &v)) || (rc = up3("hin", a->hin, ST_H, &hin))) return rc;
+  // h is inout: points outside the updated ranges keep the caller's values
+  if ((rc = up3("h", a->h, ST_H, &h)) || (rc = up3("uh", a->uh, ST_U, &uh)) || (rc = up3("vh", a->vh, ST_V, &vh))) return rc;
+  if ((rc = up3("porU", a->por_face_areaU, ST_U, &pu)) || (rc = up3("porV", a->por_face_areaV, ST_V, &pv))) return rc;
+  if ((rc = up3("vru", a->visc_rem_u, ST_U, &vru)) || (rc = up3("vrv", a->visc_rem_v, ST_V, &vrv))) return rc;
+  if ((rc = up3("ucor", a->u_cor, ST_U, &ucor)) || (rc = up3("vcor", a->v_cor, ST_V, &vcor))) return rc;
+  if ((rc = up2("uhbt", a->uhbt, ST_U, &uhbt)) || (rc = up2("vhbt", a->vhbt, ST_V, &vhbt))) return rc;
+  if ((rc = up2("ducor", a->du_cor, ST_U, &ducor)) || (rc = up2("dvcor", a->dv_cor, ST_V, &dvcor))) return rc;
+  D.u = u; D.v = v; D.hin = (a->hin == a->h) ? h : hin; D.h = h; D.uh = uh; D.vh = vh;
+  D.por_face_areaU = pu; D.por_face_areaV = pv; D.visc_rem_u = vru; D.visc_rem_v = vrv; D.u_cor = ucor; D.v_cor = vcor;
+  D.uhbt = uhbt; D.vhbt = vhbt; D.du_cor = ducor; D.dv_cor = dvcor;
+  const mom6cu_bt_cont* B = a->BT_cont;
+  if (B) {
+    D.have_BT_cont = 1;
+    double** dst2[12] = {&D.FA_u_EE, &D.FA_u_E0, &D.FA_u_W0, &D.FA_u_WW, &D.uBT_WW, &D.uBT_EE,
+                         &D.FA_v_NN, &D.FA_v_N0, &D.FA_v_S0, &D.FA_v_SS, &D.vBT_SS, &D.vBT_NN};
+    double* src2[12] = {B->FA_u_EE, B->FA_u_E0, B->FA_u_W0, B->FA_u_WW, B->uBT_WW, B->uBT_EE,
+                        B->FA_v_NN, B->FA_v_N0, B->FA_v_S0, B->FA_v_SS, B->vBT_SS, B->vBT_NN};
+    static const char* nm[12] = {"FA_u_EE", "FA_u_E0", "FA_u_W0", "FA_u_WW", "uBT_WW", "uBT_EE",
+                                 "FA_v_NN", "FA_v_N0", "FA_v_S0", "FA_v_SS", "vBT_SS", "vBT_NN"};
+    for (int m = 0; m < 12; ++m) {
+      if (!src2[m]) return c->fail(MOM6CU_ERR_BAD_ARG, "continuity: BT_cont%%%s is not allocated", nm[m]);
+      if ((rc = up2(nm[m], src2[m], m < 6 ? ST_U : ST_V, dst2[m]))) return rc;
+    }
+    if ((rc = up3("h_u", B->h_u, ST_U, &D.h_u)) || (rc = up3("h_v", B->h_v, ST_V, &D.h_v))) return rc;
+  }
+  M6_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  if ((rc = m6_continuity_run(c, D))) return rc;
+  M6_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+#define DN3(src, st, dst) if ((dst) && (rc = m6_down(c, (src), (st), 0, nk, (dst)))) return rc
+#define DN2(src, st, dst) if ((dst) && (rc = m6_down(c, (src), (st), 0, 1, (dst)))) return rc
+  DN3(h, ST_H, a->h); DN3(uh, ST_U, a->uh); DN3(vh, ST_V, a->vh);
+  DN3(ucor, ST_U, a->u_cor); DN3(vcor, ST_V, a->v_cor);
+  DN2(ducor, ST_U, a->du_cor); DN2(dvcor, ST_V, a->dv_cor);
+  if (B) {
+    DN2(D.FA_u_EE, ST_U, B->FA_u_EE); DN2(D.FA_u_E0, ST_U, B->FA_u_E0); DN2(D.FA_u_W0, ST_U, B->FA_u_W0);
+    DN2(D.FA_u_WW, ST_U, B->FA_u_WW); DN2(D.uBT_WW, ST_U, B->uBT_WW); DN2(D.uBT_EE, ST_U, B->uBT_EE);
+    DN2(D.FA_v_NN, ST_V, B->FA_v_NN); DN2(D.FA_v_N0, ST_V, B->FA_v_N0); DN2(D.FA_v_S0, ST_V, B->FA_v_S0);
+    DN2(D.FA_v_SS, ST_V, B->FA_v_SS); DN2(D.vBT_SS, ST_V, B->vBT_SS); DN2(D.vBT_NN, ST_V, B->vBT_NN);
+    DN3(D.h_u, ST_U, B->h_u); DN3(D.h_v, ST_V, B->h_v);
+  }
+#undef DN3
+#undef DN2
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  M6_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  c->total_ms = ms;
+  return 0;
+}

@@ -8,6 +8,7 @@
 #include <cstring>
 #include "../../include/mom6cu.h"
 #include "common.cuh"
+#include "stage.h"
 
 enum { ST_H = 0, ST_U = 1, ST_V = 2, ST_Q = 3 };
 
@@ -26,6 +27,13 @@ struct mom6cu_ctx {
   std::map<std::string, double*> bufs;
   std::map<std::string, size_t> buf_sz;
   void* comm = nullptr;  // ncclComm_t when multi-rank
+  // resident grid metrics and resolved control structures
+  GridDev grid = {};
+  bool have_grid = false;
+  mom6cu_vgrid vgrid = {};
+  bool have_vgrid = false;
+  mom6cu_continuity_cs cont_cs = {};
+  bool have_cont_cs = false;
   int rank = 0, nranks = 1;
 
   // named, persistent, zero-initialised device buffer of n doubles

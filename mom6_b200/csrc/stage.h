@@ -1,0 +1,33 @@
+// Device-resident argument blocks of the dycore stages: every pointer is a unified plane
+// (common.cuh).  The C-ABI entries stage host arrays into these; the fused step driver passes its
+// own resident planes, so no stage ever touches host memory.
+#pragma once
+#include "../../include/mom6cu.h"
+
+// ocean_grid_type metrics on the device (src/core/MOM_grid.F90:75-175)
+struct GridDev {
+  const double *mask2dT, *mask2dCu, *mask2dCv, *mask2dBu;
+  const double *dxT, *dyT, *IdxT, *IdyT, *areaT, *IareaT;
+  const double *dxCu, *dyCu, *IdxCu, *IdyCu, *dy_Cu, *areaCu, *IareaCu;
+  const double *dxCv, *dyCv, *IdxCv, *IdyCv, *dx_Cv, *areaCv, *IareaCv;
+  const double *dxBu, *dyBu, *IdxBu, *IdyBu, *areaBu, *IareaBu;
+  const double *bathyT, *CoriolisBu, *Coriolis2Bu;
+};
+
+// continuity_PPM dummy arguments (MOM_continuity_PPM.F90:86-141); null = absent optional
+struct ContinuityDev {
+  const double *u, *v, *hin;
+  double *h, *uh, *vh;
+  double dt;
+  const double *por_face_areaU, *por_face_areaV;
+  const double *uhbt, *vhbt;
+  const double *visc_rem_u, *visc_rem_v;
+  double *u_cor, *v_cor, *du_cor, *dv_cor;
+  int have_BT_cont;
+  double *FA_u_EE, *FA_u_E0, *FA_u_W0, *FA_u_WW, *uBT_WW, *uBT_EE;
+  double *FA_v_NN, *FA_v_N0, *FA_v_S0, *FA_v_SS, *vBT_SS, *vBT_NN;
+  double *h_u, *h_v;
+};
+
+struct mom6cu_ctx;
+int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D);

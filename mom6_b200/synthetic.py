@@ -264,3 +264,152 @@ def _stagger_of(key):
     if key in _V_KEYS:
         return "v"
     return "h"
+
+
+# --------------------------------------------------------------------------------------------
+# 3-D stages: grid metrics, vertical grid and a split-RK2-like state
+
+def make_grid(dom, land_blocks=0, seed=SEED, dx0=2.5e4, dy0=2.5e4, f0=1.0e-4, beta=2.0e-11):
+    """ocean_grid_type metrics (src/core/MOM_grid.F90:75-175) on G's memory domain for a beta-plane
+    with a mildly non-uniform (periodic in i) mesh so every metric term is exercised."""
+    ni, nj = dom.iec - dom.isc + 1, dom.jec - dom.jsc + 1
+    mT, mU, mV, D = masks_and_depth(dom, False, land_blocks, seed)
+    g = {}
+
+    def pts(st):
+        ilo, ihi, jlo, jhi = fidx.extent(dom, st)
+        su = 0.5 if st in ("u", "q") else 0.0
+        sv = 0.5 if st in ("v", "q") else 0.0
+        ii = (np.arange(ilo, ihi + 1) - dom.isc + 0.5 + su)[None, :]
+        jj = (np.arange(jlo, jhi + 1) - dom.jsc + 0.5 + sv)[:, None]
+        return ii, jj
+
+    def dxf(ii, jj):
+        return dx0 * (1.0 - 0.3 * ((jj / nj) - 0.5) ** 2) * (1.0 + 0.0 * ii)
+
+    def dyf(ii, jj):
+        return dy0 * (1.0 + 0.05 * np.sin(2.0 * np.pi * ii / ni)) * (1.0 + 0.0 * jj)
+
+    for st, sfx in (("h", "T"), ("u", "Cu"), ("v", "Cv"), ("q", "Bu")):
+        ii, jj = pts(st)
+        dx, dy = dxf(ii, jj), dyf(ii, jj)
+        g["dx" + sfx], g["dy" + sfx] = dx, dy
+        g["Idx" + sfx], g["Idy" + sfx] = 1.0 / dx, 1.0 / dy
+        g["area" + sfx] = dx * dy
+        g["Iarea" + sfx] = 1.0 / (dx * dy)
+    mQ = fidx.new(dom, "q")
+    mQ.s(mQ.ilo + 1, mQ.ihi - 1, mQ.jlo + 1, mQ.jhi - 1)[...] = (
+        mT.s(mT.ilo, mT.ihi - 1, mT.jlo, mT.jhi - 1) * mT.s(mT.ilo + 1, mT.ihi, mT.jlo, mT.jhi - 1) *
+        mT.s(mT.ilo, mT.ihi - 1, mT.jlo + 1, mT.jhi) * mT.s(mT.ilo + 1, mT.ihi, mT.jlo + 1, mT.jhi))
+    fidx.fill_halo(dom, mQ, "q")
+    fidx.fill_halo(dom, mU, "u")
+    fidx.fill_halo(dom, mV, "v")
+    if dom.cyclic_x:
+        # the symmetric edge of the staggered masks
+        mU.s(dom.isc - 1, dom.isc - 1, mU.jlo, mU.jhi)[...] = mU.s(dom.iec, dom.iec, mU.jlo, mU.jhi)
+        mQ.s(dom.isc - 1, dom.isc - 1, mQ.jlo, mQ.jhi)[...] = mQ.s(dom.iec, dom.iec, mQ.jlo, mQ.jhi)
+        fidx.fill_halo(dom, mU, "u"); fidx.fill_halo(dom, mQ, "q")
+    g["mask2dT"], g["mask2dCu"], g["mask2dCv"], g["mask2dBu"] = mT.a, mU.a, mV.a, mQ.a
+    g["dy_Cu"] = g["dyCu"] * mU.a
+    g["dx_Cv"] = g["dxCv"] * mV.a
+    g["bathyT"] = D.a
+    ii, jj = pts("q")
+    fq = f0 + beta * (jj * dy0) + 0.0 * ii
+    g["CoriolisBu"] = fq
+    g["Coriolis2Bu"] = fq * fq
+    return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in g.items()}
+
+
+def make_vgrid(Angstrom_H=1.0e-10, H_subroundoff=1.0e-30):
+    return dict(Angstrom_H=Angstrom_H, H_subroundoff=H_subroundoff, Z_to_H=1.0, H_to_Z=1.0, g_Earth=9.8, Rho0=1035.0,
+                H_to_RZ=1035.0, RZ_to_H=1.0 / 1035.0, H_to_m=1.0, m_to_H=1.0, Boussinesq=1)
+
+
+def continuity_cs(nk, Angstrom_H=1.0e-10, **over):
+    """continuity_PPM_init defaults (MOM_continuity_PPM.F90:2693-2747)."""
+    cs = dict(upwind_1st=0, monotonic=0, simple_2nd=0, aggress_adjust=0, vol_CFL=0, better_iter=1, use_visc_rem_max=1,
+              marginal_faces=1, tol_eta=0.5 * nk * Angstrom_H, tol_vel=3.0e8, CFL_limit_adjust=0.5)
+    cs.update(over)
+    return cs
+
+
+def dyn_state(dom, grid, seed=SEED, vel=0.3, thin_layers=True):
+    """h, u, v, visc_rem_u/v on G's memory domain: Z*-like layers over the synthetic bathymetry with
+    noise, some vanished layers over the seamount, velocities ~ vel*U*mask."""
+    r = rng(seed + 101)
+    nk = dom.nk
+    ni, nj = dom.iec - dom.isc + 1, dom.jec - dom.jsc + 1
+
+    def U3(st):
+        f = fidx.new(dom, st, nk=nk)
+        f.s(dom.isc - 1, dom.iec, dom.jsc - 1, dom.jec)[...] = r.uniform(-1.0, 1.0, size=(nk, nj + 1, ni + 1))
+        return f
+
+    def fill3(f, st):
+        if dom.cyclic_x and st in ("u", "q"):
+            f.s(dom.isc - 1, dom.isc - 1, f.jlo, f.jhi)[...] = f.s(dom.iec, dom.iec, f.jlo, f.jhi)
+        if dom.cyclic_y and st in ("v", "q"):
+            f.s(f.ilo, f.ihi, dom.jsc - 1, dom.jsc - 1)[...] = f.s(f.ilo, f.ihi, dom.jec, dom.jec)
+        return fidx.fill_halo(dom, f, st)
+
+    w = np.linspace(1.0, 3.0, nk); w /= w.sum()
+    h = U3("h")
+    D = grid["bathyT"]
+    h.a[...] = D[None, :, :] * w[:, None, None] * (1.0 + 0.2 * h.a)
+    if thin_layers:
+        # vanished layers where the water is shallower than the nominal interface depth
+        zbot = np.cumsum(4000.0 * w)
+        for k in range(nk):
+            h.a[k][D < zbot[k] - 4000.0 * w[k] * 0.5] = 1.0e-10
+    h.a[...] = np.maximum(h.a, 1.0e-10) * grid["mask2dT"][None] + 1.0e-10 * (1.0 - grid["mask2dT"][None])
+    fill3(h, "h")
+    u = U3("u"); u.a[...] = vel * u.a * grid["mask2dCu"][None]; fill3(u, "u")
+    v = U3("v"); v.a[...] = vel * v.a * grid["mask2dCv"][None]; fill3(v, "v")
+    zf = np.linspace(0.0, 1.0, nk)[:, None, None]
+    vru = U3("u"); vru.a[...] = (1.0 - 0.6 * np.exp(-(1.0 - zf) / 0.1) * (1.0 + 0.2 * vru.a)) * grid["mask2dCu"][None]; fill3(vru, "u")
+    vrv = U3("v"); vrv.a[...] = (1.0 - 0.6 * np.exp(-(1.0 - zf) / 0.1) * (1.0 + 0.2 * vrv.a)) * grid["mask2dCv"][None]; fill3(vrv, "v")
+    return dict(h=h.a, u=u.a, v=v.a, visc_rem_u=vru.a, visc_rem_v=vrv.a)
+
+
+def continuity_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, with_uhbt=True, with_visc_rem=True, with_BT_cont=True,
+                      with_cor=True, first_direction=0, cyclic_x=True, cyclic_y=False, dt=900.0, alias_h=False, cs_over=None):
+    """Everything a continuity_PPM call needs (MOM_continuity_PPM.F90:86): returns dom, grid, vgrid, cs, args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y, first_direction=first_direction)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    cs = continuity_cs(nk, **(cs_over or {}))
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 5)
+    a = dict(u=st["u"], v=st["v"], hin=st["h"], dt=dt)
+    a["h"] = a["hin"] if alias_h else st["h"].copy()
+    a["uh"] = fidx.new(dom, "u", nk=nk).a
+    a["vh"] = fidx.new(dom, "v", nk=nk).a
+    if with_visc_rem:
+        a["visc_rem_u"], a["visc_rem_v"] = st["visc_rem_u"], st["visc_rem_v"]
+    if with_uhbt:
+        # a target transport near the layer-summed first-guess transport
+        hu = 0.5 * (st["h"][:, :, :-1] + st["h"][:, :, 1:])
+        uh0 = fidx.new(dom, "u")
+        uh0.a[:, 1:-1] = (st["u"][:, :, 1:-1] * hu * grid["dy_Cu"][None, :, 1:-1]).sum(axis=0)
+        uh0.a[...] = uh0.a * (1.0 + 0.05 * r.uniform(-1, 1, size=uh0.a.shape)) * grid["mask2dCu"]
+        a["uhbt"] = _sym_u(dom, uh0).a
+        hv = 0.5 * (st["h"][:, :-1, :] + st["h"][:, 1:, :])
+        vh0 = fidx.new(dom, "v")
+        vh0.a[1:-1, :] = (st["v"][:, 1:-1, :] * hv * grid["dx_Cv"][None, 1:-1, :]).sum(axis=0)
+        vh0.a[...] = vh0.a * (1.0 + 0.05 * r.uniform(-1, 1, size=vh0.a.shape)) * grid["mask2dCv"]
+        a["vhbt"] = _sym_v(dom, vh0).a
+        if with_cor:
+            a["u_cor"] = fidx.new(dom, "u", nk=nk).a
+            a["v_cor"] = fidx.new(dom, "v", nk=nk).a
+            a["du_cor"] = fidx.new(dom, "u").a
+            a["dv_cor"] = fidx.new(dom, "v").a
+    if with_BT_cont:
+        b = {}
+        for k in ("FA_u_EE", "FA_u_E0", "FA_u_W0", "FA_u_WW", "uBT_WW", "uBT_EE"):
+            b[k] = fidx.new(dom, "u").a
+        for k in ("FA_v_NN", "FA_v_N0", "FA_v_S0", "FA_v_SS", "vBT_SS", "vBT_NN"):
+            b[k] = fidx.new(dom, "v").a
+        b["h_u"] = fidx.new(dom, "u", nk=nk).a
+        b["h_v"] = fidx.new(dom, "v", nk=nk).a
+        a["BT_cont"] = b
+    return dom, grid, gv, cs, a

@@ -33,6 +33,10 @@ int oracle_btstep_timeloop(const mom6cu_domain* dom, const mom6cu_bt_timeloop_ar
  * stagger 0=h,1=u,2=v,3=q; fills halo points of a wide (wide=1) or G-sized array */
 void oracle_fill_halo_2d(const mom6cu_domain* dom, double* f, int stagger, int wide);
 
+/* continuity_PPM, MOM_continuity_PPM.F90:86-194 */
+int oracle_continuity(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
+                      const mom6cu_continuity_cs* CS, const mom6cu_continuity_args* a, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,3 +34,19 @@ def btstep_timeloop(dom, args, nthreads=1):
     if rc != 0:
         raise RuntimeError(f"oracle_btstep_timeloop rc={rc}")
     return rc
+
+
+def continuity(dom, grid, gv, cs, args, nthreads=1):
+    """oracle_continuity: continuity_PPM, MOM_continuity_PPM.F90:86-194, on host arrays."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    v = marshal.vgrid(gv)
+    c = marshal.continuity_cs(cs)
+    a = marshal.continuity_args(args, keep)
+    lib.oracle_continuity.argtypes = [C.c_void_p] * 5 + [C.c_int]
+    rc = lib.oracle_continuity(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(a), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_continuity rc={rc}")
+    return rc
