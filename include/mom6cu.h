@@ -137,6 +137,47 @@ typedef struct mom6cu_continuity_args {
 int mom6cu_set_cs_continuity(mom6cu_ctx* ctx, const mom6cu_continuity_cs* CS);
 int mom6cu_continuity(mom6cu_ctx* ctx, const mom6cu_continuity_args* a);
 
+/* unit_scale_type factors the hot path uses (src/framework/MOM_unit_scaling.F90); all 1 in an
+ * unscaled run.  Defaults to all ones when never set. */
+typedef struct mom6cu_unit_scale {
+  double m_to_L, L_to_m, m_s_to_L_T, L_T_to_m_s, s_to_T, T_to_s, m_to_Z, Z_to_m, Z_to_L, L_to_Z;
+} mom6cu_unit_scale;
+int mom6cu_set_unit_scale(mom6cu_ctx* ctx, const mom6cu_unit_scale* US);
+
+/* --------------------------------------------------------------- CorAdCalc */
+/* CoriolisAdv_CS, src/core/MOM_CoriolisAdv.F90:30-91, resolved by CoriolisAdv_init :1054.
+ * Enumeration values are the reference's (:94-119). */
+#define MOM6CU_SADOURNY75_ENERGY 1
+#define MOM6CU_ARAKAWA_HSU90 2
+#define MOM6CU_ROBUST_ENSTRO 3
+#define MOM6CU_SADOURNY75_ENSTRO 4
+#define MOM6CU_ARAKAWA_LAMB81 5
+#define MOM6CU_AL_BLEND 6
+#define MOM6CU_KE_ARAKAWA 10
+#define MOM6CU_KE_SIMPLE_GUDONOV 11
+#define MOM6CU_KE_GUDONOV 12
+#define MOM6CU_PV_ADV_CENTERED 21
+#define MOM6CU_PV_ADV_UPWIND1 22
+typedef struct mom6cu_coriolisadv_cs {
+  int Coriolis_Scheme, KE_Scheme, PV_Adv_Scheme;
+  int no_slip, bound_Coriolis, Coriolis_En_Dis;
+  double F_eff_max_blend, wt_lin_blend;
+} mom6cu_coriolisadv_cs;
+
+/* CorAdCalc(u, v, h, uh, vh, CAu, CAv, OBC, AD, G, GV, US, CS, pbv, Waves)
+ * src/core/MOM_CoriolisAdv.F90:125-965 (+ gradKE :969-1051).  OBC and Waves must be absent.
+ * Optional diagnostics (NULL = not requested): RV/PV (q-points, 3-D; CS%id_rv/id_PV),
+ * gradKEu/gradKEv (AD%gradKEu/v). */
+typedef struct mom6cu_coradcalc_args {
+  const double *u, *v, *h, *uh, *vh; /* 3-D u, v, h, u, v */
+  double *CAu, *CAv;                 /* 3-D u, v (out) */
+  const double *por_face_areaU, *por_face_areaV; /* pbv, 3-D u, v; NULL = 1 */
+  double *RV, *PV;                   /* 3-D q, optional out */
+  double *gradKEu, *gradKEv;         /* 3-D u, v, optional out */
+} mom6cu_coradcalc_args;
+int mom6cu_set_cs_coriolisadv(mom6cu_ctx* ctx, const mom6cu_coriolisadv_cs* CS);
+int mom6cu_coradcalc(mom6cu_ctx* ctx, const mom6cu_coradcalc_args* a);
+
 /* ------------------------------------------------------- halo communication */
 /* The reference's halo API (pass_var / pass_vector / do_group_pass,
  * src/framework/MOM_domains.F90 -> config_src/infra/FMS2/MOM_domain_infra.F90:171-216,

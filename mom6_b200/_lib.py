@@ -81,6 +81,31 @@ class ContinuityArgs(C.Structure):
                 [("BT_cont", C.POINTER(BTCont))] + [(n, C.c_void_p) for n in ("du_cor", "dv_cor")])
 
 
+class UnitScale(C.Structure):
+    """mom6cu_unit_scale: unit_scale_type factors (src/framework/MOM_unit_scaling.F90)."""
+    _fields_ = [(n, C.c_double) for n in ("m_to_L", "L_to_m", "m_s_to_L_T", "L_T_to_m_s", "s_to_T", "T_to_s",
+                                          "m_to_Z", "Z_to_m", "Z_to_L", "L_to_Z")]
+
+
+# CoriolisAdv enumerations, src/core/MOM_CoriolisAdv.F90:94-119
+SADOURNY75_ENERGY, ARAKAWA_HSU90, ROBUST_ENSTRO, SADOURNY75_ENSTRO, ARAKAWA_LAMB81, AL_BLEND = 1, 2, 3, 4, 5, 6
+KE_ARAKAWA, KE_SIMPLE_GUDONOV, KE_GUDONOV = 10, 11, 12
+PV_ADV_CENTERED, PV_ADV_UPWIND1 = 21, 22
+
+
+class CoriolisAdvCS(C.Structure):
+    """mom6cu_coriolisadv_cs: CoriolisAdv_CS (MOM_CoriolisAdv.F90:30-91)."""
+    _fields_ = [(n, C.c_int) for n in ("Coriolis_Scheme", "KE_Scheme", "PV_Adv_Scheme", "no_slip", "bound_Coriolis",
+                                       "Coriolis_En_Dis")] + \
+               [(n, C.c_double) for n in ("F_eff_max_blend", "wt_lin_blend")]
+
+
+class CorAdCalcArgs(C.Structure):
+    """mom6cu_coradcalc_args: the dummy arguments of CorAdCalc (MOM_CoriolisAdv.F90:125-144)."""
+    _fields_ = [(n, C.c_void_p) for n in ("u", "v", "h", "uh", "vh", "CAu", "CAv", "por_face_areaU", "por_face_areaV",
+                                          "RV", "PV", "gradKEu", "gradKEv")]
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
@@ -127,6 +152,9 @@ def bind(lib):
     lib.mom6cu_set_vgrid.argtypes = [vp, C.POINTER(VGrid)]
     lib.mom6cu_set_cs_continuity.argtypes = [vp, C.POINTER(ContinuityCS)]
     lib.mom6cu_continuity.argtypes = [vp, C.POINTER(ContinuityArgs)]
+    lib.mom6cu_set_unit_scale.argtypes = [vp, C.POINTER(UnitScale)]
+    lib.mom6cu_set_cs_coriolisadv.argtypes = [vp, C.POINTER(CoriolisAdvCS)]
+    lib.mom6cu_coradcalc.argtypes = [vp, C.POINTER(CorAdCalcArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

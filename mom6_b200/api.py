@@ -102,7 +102,20 @@ def _ctx_methods():
         st = marshal.continuity_args(args, keep)
         return self._check(self.lib.mom6cu_continuity(self._h, C.byref(st)))
 
-    for f in (set_grid, set_vgrid, set_cs_continuity, continuity):
+    def set_unit_scale(self, us=None):
+        return self._check(self.lib.mom6cu_set_unit_scale(self._h, C.byref(marshal.unit_scale(us))))
+
+    def set_cs_coriolisadv(self, cs):
+        """CoriolisAdv_init's resolved parameters (MOM_CoriolisAdv.F90:1054-1200)."""
+        return self._check(self.lib.mom6cu_set_cs_coriolisadv(self._h, C.byref(marshal.coriolisadv_cs(cs))))
+
+    def coradcalc(self, args):
+        """CorAdCalc, MOM_CoriolisAdv.F90:125."""
+        keep = []
+        st = marshal.coradcalc_args(args, keep)
+        return self._check(self.lib.mom6cu_coradcalc(self._h, C.byref(st)))
+
+    for f in (set_grid, set_vgrid, set_cs_continuity, continuity, set_unit_scale, set_cs_coriolisadv, coradcalc):
         setattr(Context, f.__name__, f)
 
 

@@ -34,6 +34,9 @@ struct mom6cu_ctx {
   bool have_vgrid = false;
   mom6cu_continuity_cs cont_cs = {};
   bool have_cont_cs = false;
+  mom6cu_unit_scale US = {1., 1., 1., 1., 1., 1., 1., 1., 1., 1.};
+  mom6cu_coriolisadv_cs corad_cs = {};
+  bool have_corad_cs = false;
   int rank = 0, nranks = 1;
 
   // named, persistent, zero-initialised device buffer of n doubles
@@ -66,3 +69,44 @@ int m6_up(mom6cu_ctx* c, const double* src, int stagger, int wide, int nk, doubl
 int m6_down(mom6cu_ctx* c, const double* src_plane, int stagger, int wide, int nk, double* dst);
 // array-of-structs (nm reals per point, m fastest) -> nm separate planes
 int m6_up_aos(mom6cu_ctx* c, const double* src, int nm, int stagger, int wide, double* const* dst);
+
+// Staging of one C-ABI call: Fortran-shaped (host or device) arrays -> named resident planes, and the
+// outputs back.  in*: intent(in) (null stays null); io*: intent(out)/(inout) -- uploaded first so that points
+// the stage does not touch keep the caller's values, downloaded by finish().  begin()/finish() bracket the
+// stage kernels with CUDA events on the compute stream (mom6cu_last_kernel_ms).
+struct Stager {
+  mom6cu_ctx* c;
+  std::string pfx;
+  struct Out { const double* dev; double* host; int st, wide, nk; };
+  std::vector<Out> outs;
+  Stager(mom6cu_ctx* c_, const char* prefix) : c(c_), pfx(prefix) {}
+  int in(const double* src, int st, int wide, int nk, const char* name, const double** dst) {
+    *dst = nullptr;
+    if (!src) return 0;
+    double* p = c->buf(pfx + name, (size_t)c->g.plane * nk);
+    if (!p) return MOM6CU_ERR_CUDA;
+    *dst = p;
+    return m6_up(c, src, st, wide, nk, p);
+  }
+  int io(double* src, int st, int wide, int nk, const char* name, double** dst) {
+    const double* p = nullptr;
+    int rc = in(src, st, wide, nk, name, &p);
+    *dst = (double*)p;
+    if (!rc && p) outs.push_back({p, src, st, wide, nk});
+    return rc;
+  }
+  int in3(const double* s, int st, const char* n, const double** d) { return in(s, st, 0, c->g.nk, n, d); }
+  int in2(const double* s, int st, const char* n, const double** d) { return in(s, st, 0, 1, n, d); }
+  int io3(double* s, int st, const char* n, double** d) { return io(s, st, 0, c->g.nk, n, d); }
+  int io2(double* s, int st, const char* n, double** d) { return io(s, st, 0, 1, n, d); }
+  int begin() { M6_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return 0; }
+  int finish() {
+    M6_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    for (const Out& o : outs) { int rc = m6_down(c, o.dev, o.st, o.wide, o.nk, o.host); if (rc) return rc; }
+    M6_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    M6_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms; c->total_ms = ms;
+    return 0;
+  }
+};

@@ -40,3 +40,9 @@ extern "C" int mom6cu_set_vgrid(mom6cu_ctx* c, const mom6cu_vgrid* GV) {
   c->have_vgrid = true;
   return 0;
 }
+
+extern "C" int mom6cu_set_unit_scale(mom6cu_ctx* c, const mom6cu_unit_scale* US) {
+  if (!c || !US) return MOM6CU_ERR_BAD_ARG;
+  c->US = *US;
+  return 0;
+}

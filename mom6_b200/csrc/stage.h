@@ -29,5 +29,14 @@ struct ContinuityDev {
   double *h_u, *h_v;
 };
 
+// CorAdCalc dummy arguments (MOM_CoriolisAdv.F90:125-144); null = absent optional / diagnostic not requested
+struct CorAdDev {
+  const double *u, *v, *h, *uh, *vh;
+  double *CAu, *CAv;
+  const double *por_face_areaU, *por_face_areaV;
+  double *RV, *PV, *gradKEu, *gradKEv;
+};
+
 struct mom6cu_ctx;
+int m6_coradcalc_run(mom6cu_ctx* c, const CorAdDev& D);
 int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D);

@@ -1,7 +1,8 @@
 """dict -> ctypes struct marshalling shared by the product binding (api.py) and the oracle binding."""
 import ctypes as C
 
-from ._lib import Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, fill_struct
+from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
+                   fill_struct)
 
 
 def _scalars(struct, d):
@@ -30,3 +31,18 @@ def continuity_args(a, keep):
         keep.append(bs)
         st.BT_cont = C.pointer(bs)
     return st
+
+
+def unit_scale(d=None):
+    st = UnitScale()
+    for name, _ in UnitScale._fields_:
+        setattr(st, name, (d or {}).get(name, 1.0))
+    return st
+
+
+def coriolisadv_cs(d):
+    return _scalars(CoriolisAdvCS(), d)
+
+
+def coradcalc_args(a, keep):
+    return fill_struct(CorAdCalcArgs(), a, keep)

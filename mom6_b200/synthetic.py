@@ -413,3 +413,48 @@ def continuity_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, with_uhbt=Tr
         b["h_v"] = fidx.new(dom, "v", nk=nk).a
         a["BT_cont"] = b
     return dom, grid, gv, cs, a
+
+
+def coriolisadv_cs(**over):
+    """CoriolisAdv_init defaults (MOM_CoriolisAdv.F90:1077-1178)."""
+    cs = dict(Coriolis_Scheme=1, KE_Scheme=10, PV_Adv_Scheme=21, no_slip=0, bound_Coriolis=0, Coriolis_En_Dis=0,
+              F_eff_max_blend=4.0, wt_lin_blend=0.125)
+    cs.update(over)
+    return cs
+
+
+def transports(dom, grid, st):
+    """uh, vh consistent with (u, v, h): upwind face thickness times face length (what continuity returns)."""
+    h, u, v = st["h"], st["u"], st["v"]
+    nk = dom.nk
+    uh = fidx.new(dom, "u", nk=nk)
+    hu = np.where(u[:, :, 1:-1] > 0, h[:, :, :-1], h[:, :, 1:])
+    uh.a[:, :, 1:-1] = u[:, :, 1:-1] * hu * grid["dy_Cu"][None, :, 1:-1]
+    vh = fidx.new(dom, "v", nk=nk)
+    hv = np.where(v[:, 1:-1, :] > 0, h[:, :-1, :], h[:, 1:, :])
+    vh.a[:, 1:-1, :] = v[:, 1:-1, :] * hv * grid["dx_Cv"][None, 1:-1, :]
+    return uh.a, vh.a
+
+
+def coradcalc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, cs_over=None,
+                     diags=False, por=False):
+    """Everything a CorAdCalc call needs (MOM_CoriolisAdv.F90:125): returns dom, grid, vgrid, cs, args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    cs = coriolisadv_cs(**(cs_over or {}))
+    st = dyn_state(dom, grid, seed)
+    uh, vh = transports(dom, grid, st)
+    a = dict(u=st["u"], v=st["v"], h=st["h"], uh=uh, vh=vh)
+    a["CAu"] = fidx.new(dom, "u", nk=nk).a
+    a["CAv"] = fidx.new(dom, "v", nk=nk).a
+    if diags:
+        a["RV"] = fidx.new(dom, "q", nk=nk).a
+        a["PV"] = fidx.new(dom, "q", nk=nk).a
+        a["gradKEu"] = fidx.new(dom, "u", nk=nk).a
+        a["gradKEv"] = fidx.new(dom, "v", nk=nk).a
+    if por:
+        r = rng(seed + 77)
+        a["por_face_areaU"] = 1.0 - 0.3 * r.uniform(0, 1, size=a["u"].shape)
+        a["por_face_areaV"] = 1.0 - 0.3 * r.uniform(0, 1, size=a["v"].shape)
+    return dom, grid, gv, cs, a

@@ -37,6 +37,11 @@ void oracle_fill_halo_2d(const mom6cu_domain* dom, double* f, int stagger, int w
 int oracle_continuity(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
                       const mom6cu_continuity_cs* CS, const mom6cu_continuity_args* a, int nthreads);
 
+/* CorAdCalc, MOM_CoriolisAdv.F90:125-965 (US may be NULL = unscaled) */
+int oracle_coradcalc(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
+                     const mom6cu_unit_scale* US, const mom6cu_coriolisadv_cs* CS,
+                     const mom6cu_coradcalc_args* a, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

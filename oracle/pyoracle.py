@@ -50,3 +50,20 @@ def continuity(dom, grid, gv, cs, args, nthreads=1):
     if rc != 0:
         raise RuntimeError(f"oracle_continuity rc={rc}")
     return rc
+
+
+def coradcalc(dom, grid, gv, cs, args, us=None, nthreads=1):
+    """oracle_coradcalc: CorAdCalc, MOM_CoriolisAdv.F90:125-965, on host arrays."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    v = marshal.vgrid(gv)
+    u = marshal.unit_scale(us)
+    c = marshal.coriolisadv_cs(cs)
+    a = marshal.coradcalc_args(args, keep)
+    lib.oracle_coradcalc.argtypes = [C.c_void_p] * 6 + [C.c_int]
+    rc = lib.oracle_coradcalc(C.byref(dom), C.byref(g), C.byref(v), C.byref(u), C.byref(c), C.byref(a), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_coradcalc rc={rc}")
+    return rc
