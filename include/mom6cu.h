@@ -178,6 +178,41 @@ typedef struct mom6cu_coradcalc_args {
 int mom6cu_set_cs_coriolisadv(mom6cu_ctx* ctx, const mom6cu_coriolisadv_cs* CS);
 int mom6cu_coradcalc(mom6cu_ctx* ctx, const mom6cu_coradcalc_args* a);
 
+/* ---------------------------------------------------- horizontal_viscosity */
+/* hor_visc_CS, src/parameterizations/lateral/MOM_hor_visc.F90:38-250, as resolved by hor_visc_init
+ * (:2322-3302).  The 2-D members are the static arrays hor_visc_init precomputes (:2834-3120), passed as the
+ * Fortran arrays they are (h-, q-, u- or v-point, G-sized); an array an option does not use may be NULL.
+ * Frozen options: Leith / Leith+E / QG-Leith, GME, MEKE viscosities and backscatter, anisotropic viscosity,
+ * ZB2020, resolution-function scaling and OBCs are rejected (MOM6CU_ERR_UNSUPPORTED). */
+typedef struct mom6cu_hor_visc_cs {
+  int Laplacian, biharmonic, no_slip, bound_Kh, better_bound_Kh, bound_Ah, better_bound_Ah,
+      backscatter_underbound, Smagorinsky_Kh, Smagorinsky_Ah, bound_Coriolis, use_land_mask,
+      add_LES_viscosity, use_cont_thick, use_cont_thick_bug;
+  int unsupported; /* nonzero if any of the rejected options is set in the run's parameters */
+  double Kh_bg_min, Re_Ah;
+  /* h-points */
+  const double *dx2h, *dy2h, *DX_dyT, *DY_dxT, *reduction_xx, *Kh_bg_xx, *Ah_bg_xx, *Kh_Max_xx, *Ah_Max_xx,
+      *Laplac2_const_xx, *Biharm_const_xx, *Biharm_const2_xx, *Re_Ah_const_xx;
+  /* q-points */
+  const double *dx2q, *dy2q, *DX_dyBu, *DY_dxBu, *reduction_xy, *Kh_bg_xy, *Ah_bg_xy, *Kh_Max_xy, *Ah_Max_xy,
+      *Laplac2_const_xy, *Biharm_const_xy, *Biharm_const2_xy, *Re_Ah_const_xy;
+  /* u-points, v-points */
+  const double *Idx2dyCu, *Idxdy2u, *Idx2dyCv, *Idxdy2v;
+} mom6cu_hor_visc_cs;
+#define MOM6CU_HOR_VISC_NARRAYS 30
+
+/* horizontal_viscosity(u, v, h, uh, vh, diffu, diffv, MEKE, VarMix, G, GV, US, CS, tv, dt, OBC, BT, TD, ADp,
+ *                      hu_cont, hv_cont, STOCH)   MOM_hor_visc.F90:266-267.
+ * uh, vh feed only the FrictWork diagnostics (not computed here) and may be NULL. */
+typedef struct mom6cu_hor_visc_args {
+  const double *u, *v, *h, *uh, *vh; /* 3-D u, v, h, u, v */
+  double *diffu, *diffv;             /* 3-D u, v (out) */
+  const double *hu_cont, *hv_cont;   /* 3-D u, v, optional */
+  double dt;
+} mom6cu_hor_visc_args;
+int mom6cu_set_cs_hor_visc(mom6cu_ctx* ctx, const mom6cu_hor_visc_cs* CS);
+int mom6cu_horizontal_viscosity(mom6cu_ctx* ctx, const mom6cu_hor_visc_args* a);
+
 /* ------------------------------------------------------- halo communication */
 /* The reference's halo API (pass_var / pass_vector / do_group_pass,
  * src/framework/MOM_domains.F90 -> config_src/infra/FMS2/MOM_domain_infra.F90:171-216,

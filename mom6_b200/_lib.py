@@ -106,6 +106,28 @@ class CorAdCalcArgs(C.Structure):
                                           "RV", "PV", "gradKEu", "gradKEv")]
 
 
+HV_FLAGS = ["Laplacian", "biharmonic", "no_slip", "bound_Kh", "better_bound_Kh", "bound_Ah", "better_bound_Ah",
+            "backscatter_underbound", "Smagorinsky_Kh", "Smagorinsky_Ah", "bound_Coriolis", "use_land_mask",
+            "add_LES_viscosity", "use_cont_thick", "use_cont_thick_bug", "unsupported"]
+HV_H = ["dx2h", "dy2h", "DX_dyT", "DY_dxT", "reduction_xx", "Kh_bg_xx", "Ah_bg_xx", "Kh_Max_xx", "Ah_Max_xx",
+        "Laplac2_const_xx", "Biharm_const_xx", "Biharm_const2_xx", "Re_Ah_const_xx"]
+HV_Q = ["dx2q", "dy2q", "DX_dyBu", "DY_dxBu", "reduction_xy", "Kh_bg_xy", "Ah_bg_xy", "Kh_Max_xy", "Ah_Max_xy",
+        "Laplac2_const_xy", "Biharm_const_xy", "Biharm_const2_xy", "Re_Ah_const_xy"]
+HV_UV = ["Idx2dyCu", "Idxdy2u", "Idx2dyCv", "Idxdy2v"]
+
+
+class HorViscCS(C.Structure):
+    """mom6cu_hor_visc_cs: hor_visc_CS (MOM_hor_visc.F90:38-250) as resolved by hor_visc_init (:2322)."""
+    _fields_ = ([(n, C.c_int) for n in HV_FLAGS] + [("Kh_bg_min", C.c_double), ("Re_Ah", C.c_double)] +
+                [(n, C.c_void_p) for n in HV_H + HV_Q + HV_UV])
+
+
+class HorViscArgs(C.Structure):
+    """mom6cu_hor_visc_args: the dummy arguments of horizontal_viscosity (MOM_hor_visc.F90:266)."""
+    _fields_ = [(n, C.c_void_p) for n in ("u", "v", "h", "uh", "vh", "diffu", "diffv", "hu_cont", "hv_cont")] + \
+               [("dt", C.c_double)]
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
@@ -155,6 +177,8 @@ def bind(lib):
     lib.mom6cu_set_unit_scale.argtypes = [vp, C.POINTER(UnitScale)]
     lib.mom6cu_set_cs_coriolisadv.argtypes = [vp, C.POINTER(CoriolisAdvCS)]
     lib.mom6cu_coradcalc.argtypes = [vp, C.POINTER(CorAdCalcArgs)]
+    lib.mom6cu_set_cs_hor_visc.argtypes = [vp, C.POINTER(HorViscCS)]
+    lib.mom6cu_horizontal_viscosity.argtypes = [vp, C.POINTER(HorViscArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

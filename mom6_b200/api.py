@@ -115,7 +115,19 @@ def _ctx_methods():
         st = marshal.coradcalc_args(args, keep)
         return self._check(self.lib.mom6cu_coradcalc(self._h, C.byref(st)))
 
-    for f in (set_grid, set_vgrid, set_cs_continuity, continuity, set_unit_scale, set_cs_coriolisadv, coradcalc):
+    def set_cs_hor_visc(self, cs):
+        """hor_visc_init's resolved parameters and static arrays (MOM_hor_visc.F90:2322-3302)."""
+        keep = []
+        return self._check(self.lib.mom6cu_set_cs_hor_visc(self._h, C.byref(marshal.hor_visc_cs(cs, keep))))
+
+    def horizontal_viscosity(self, args):
+        """horizontal_viscosity, MOM_hor_visc.F90:266."""
+        keep = []
+        st = marshal.hor_visc_args(args, keep)
+        return self._check(self.lib.mom6cu_horizontal_viscosity(self._h, C.byref(st)))
+
+    for f in (set_grid, set_vgrid, set_cs_continuity, continuity, set_unit_scale, set_cs_coriolisadv, coradcalc,
+              set_cs_hor_visc, horizontal_viscosity):
         setattr(Context, f.__name__, f)
 
 

@@ -391,6 +391,359 @@ __global__ void __launch_bounds__(128) cont_flux_kernel(const Geom G, const Cont
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled flux kernel (the production path for nk <= 128): one CTA owns NF neighbouring faces of one
+// row and all nk layers; threadIdx = (face f, k-slice s), thread (f,s) owns layers s, s+NS, ...
+//  * The PPM edge values of the two cells adjacent to each owned (face,k) are built ONCE and kept in
+//    registers (6 doubles per layer), so each of the ~10-20 flux evaluations the Newton / BT_cont
+//    logic needs is ~15 flops instead of a 6-point reconstruction, and h is read from HBM once.
+//  * u and visc_rem of the CTA's columns live in shared memory.
+//  * Every sum over k is sequential in k (bitwise parity): the owners write their layers' terms to a
+//    shared plane, then one thread per (face, quantity) adds them in k order -- different quantities
+//    (uh and duhdu; the 5 sums of set_*_BT_cont) run on different warps at the same time.
+//  * All per-face scalar logic (CFL bounds, Newton bracketing, convergence mask do_I) is replicated in
+//    every thread of the face, so the only barriers are around the k-sums.
+struct CellSt { double hR0, hL0, c30, hL1, hR1, c31; };
+
+__device__ __forceinline__ void flux_from_state(const ContCS& CS, const CellSt& S, double face, double un, double visc_rem,
+                                                double dt, double cfl0, double cfl1, double& uh, double& duhdu,
+                                                double& h_avg, double& h_marg) {
+  double CFL;
+  if (un > 0.0) {
+    if (CS.vol_CFL) CFL = (un * dt) * cfl0; else CFL = un * dt * cfl0;
+    h_avg = S.hR0 + CFL * (0.5 * (S.hL0 - S.hR0) + S.c30 * (CFL - 1.5));
+    uh = face * un * h_avg;
+    h_marg = S.hR0 + CFL * ((S.hL0 - S.hR0) + 3.0 * S.c30 * (CFL - 1.0));
+  } else if (un < 0.0) {
+    if (CS.vol_CFL) CFL = (-un * dt) * cfl1; else CFL = -un * dt * cfl1;
+    h_avg = S.hL1 + CFL * (0.5 * (S.hR1 - S.hL1) + S.c31 * (CFL - 1.5));
+    uh = face * un * h_avg;
+    h_marg = S.hL1 + CFL * ((S.hR1 - S.hL1) + 3.0 * S.c31 * (CFL - 1.0));
+  } else {
+    uh = 0.0;
+    h_marg = 0.5 * (S.hL1 + S.hR0);
+    h_avg = h_marg;
+  }
+  duhdu = face * h_marg * visc_rem;
+}
+
+template <bool Z, int NF, int NS, int KPT>
+__global__ void __launch_bounds__(NF* NS, (KPT <= 5) ? 2 : 1)
+cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
+  extern __shared__ double sm[];
+  const int nz = A.nk;
+  const int PL = nz * NF;
+  double* sU = sm;             // u(f,k)
+  double* sVR = sU + PL;       // visc_rem(f,k)
+  double* sP = sVR + PL;       // 5 planes of per-layer terms
+  double* sR = sP + 5 * PL;    // [8][NF] per-face results of the k-ordered sums
+  const int tid = threadIdx.x, f = tid % NF, s = tid / NF;
+  const int n = A.nlo + blockIdx.x * NF + f, o = A.olo + blockIdx.y;
+  const bool valid = n <= A.nhi;
+  const bool use_visc_rem = A.visc_rem != nullptr;
+  const bool set_BT = A.FA_W0 != nullptr;
+  const double dt = A.dt;
+  const long long sd = Z ? 1 : G.pitch;
+  const long long g = G.idx(valid ? n : A.nhi, o);
+  double dy = 0.0, cfl0 = 0.0, cfl1 = 0.0, IareaT0 = 0.0, IareaT1 = 0.0;
+  CellSt st[KPT];
+  // ---- load, reconstruct, first flux evaluation (:621-635)
+  {
+    double m[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) m[q] = __ldg(A.maskT + g + (q - 2) * sd);
+    dy = __ldg(A.dy_C + g);
+    IareaT0 = __ldg(A.IareaT + g); IareaT1 = __ldg(A.IareaT + g + sd);
+    if (CS.vol_CFL) { cfl0 = dy * IareaT0; cfl1 = dy * IareaT1; }
+    else { cfl0 = __ldg(A.IdxT + g); cfl1 = __ldg(A.IdxT + g + sd); }
+#pragma unroll
+    for (int mm = 0; mm < KPT; ++mm) {
+      const int k = s + mm * NS;
+      if (k < nz) {
+        const long long gk = g + (long long)k * G.plane;
+        const double* hk = A.h + gk;
+        const double hm2 = __ldg(hk - 2 * sd), hm1 = __ldg(hk - sd), h0 = __ldg(hk), hp1 = __ldg(hk + sd),
+                     hp2 = __ldg(hk + 2 * sd), hp3 = __ldg(hk + 3 * sd);
+        double hL, hR;
+        ppm_cell(CS, hm2, hm1, h0, hp1, hp2, m[0], m[1], m[2], m[3], m[4], hL, hR);
+        st[mm].hR0 = hR; st[mm].hL0 = hL; st[mm].c30 = (hL + hR) - 2.0 * h0;
+        ppm_cell(CS, hm1, h0, hp1, hp2, hp3, m[1], m[2], m[3], m[4], m[5], hL, hR);
+        st[mm].hL1 = hL; st[mm].hR1 = hR; st[mm].c31 = (hL + hR) - 2.0 * hp1;
+        const double uk = __ldg(A.u + gk);
+        const double vr = use_visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
+        const double por = A.por ? __ldg(A.por + gk) : 1.0;
+        sU[k * NF + f] = uk; sVR[k * NF + f] = vr;
+        double uh, dd, ha, hm;
+        flux_from_state(CS, st[mm], dy * por, uk, vr, dt, cfl0, cfl1, uh, dd, ha, hm);
+        if (valid) A.uh[gk] = uh;
+        sP[k * NF + f] = uh; sP[PL + k * NF + f] = dd;
+      }
+    }
+  }
+  double du = 0.0;
+  if (A.uhbt || set_BT) {  // uniform over the grid
+    __syncthreads();
+    // ---- k-ordered sums (:659-662) and the column maximum of visc_rem (:637-644)
+    if (s == 0) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
+    else if (s == 1) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
+    else if (s == 2) {
+      double t = 1.0;
+      if (use_visc_rem && CS.use_visc_rem_max) { t = 0.0; for (int k = 0; k < nz; ++k) t = fmax2(t, sVR[k * NF + f]); }
+      sR[2 * NF + f] = t;
+    }
+    __syncthreads();
+    const double uh_tot_0 = sR[f], duhdu_tot_0 = sR[NF + f], visc_rem_max = sR[2 * NF + f];
+    // ---- limits on du that keep the CFL number between -1 and 1 (:646-720)
+    double CFL_dt = CS.CFL_limit_adjust / dt;
+    const double I_dt = 1.0 / dt;
+    if (CS.aggress_adjust) CFL_dt = I_dt;
+    double I_vrm = 0.0;
+    if (visc_rem_max > 0.0) I_vrm = 1.0 / visc_rem_max;
+    double dx_W, dx_E;
+    if (CS.vol_CFL) {
+      dx_W = ratio_max(__ldg(A.areaT + g), dy, 1000.0 * __ldg(A.dxT + g));
+      dx_E = ratio_max(__ldg(A.areaT + g + sd), dy, 1000.0 * __ldg(A.dxT + g + sd));
+    } else { dx_W = __ldg(A.dxT + g); dx_E = __ldg(A.dxT + g + sd); }
+    const double maskC = __ldg(A.maskC + g);
+    __syncthreads();  // sR is about to be reused
+    if (s == 0) {
+      double du_max_CFL = 2.0 * (CFL_dt * dx_W) * I_vrm;
+      for (int k = 0; k < nz; ++k) {
+        const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+        if (use_visc_rem) {
+          if (CS.aggress_adjust) {
+            const double du_lim = 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd)));
+            if (du_max_CFL * vr > du_lim) du_max_CFL = du_lim / vr;
+          } else if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = (dx_W * CFL_dt - uk) / vr;
+        } else {
+          if (CS.aggress_adjust)
+            du_max_CFL = fmin2(du_max_CFL, 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd))));
+          else du_max_CFL = fmin2(du_max_CFL, dx_W * CFL_dt - uk);
+        }
+      }
+      sR[f] = fmax2(du_max_CFL, 0.0);
+    } else if (s == 1) {
+      double du_min_CFL = -2.0 * (CFL_dt * dx_E) * I_vrm;
+      for (int k = 0; k < nz; ++k) {
+        const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+        if (use_visc_rem) {
+          if (CS.aggress_adjust) {
+            const double du_lim = 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd)));
+            if (du_min_CFL * vr < du_lim) du_min_CFL = du_lim / vr;
+          } else if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = -(dx_E * CFL_dt + uk) / vr;
+        } else {
+          if (CS.aggress_adjust)
+            du_min_CFL = fmax2(du_min_CFL, 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd))));
+          else du_min_CFL = fmax2(du_min_CFL, -(dx_E * CFL_dt + uk));
+        }
+      }
+      sR[NF + f] = fmin2(du_min_CFL, 0.0);
+    }
+    __syncthreads();
+    const double du_max_CFL = sR[f], du_min_CFL = sR[NF + f];
+    const double IareaT_min = fmin2(IareaT0, IareaT1);
+
+    // zonal_flux_adjust :1093-1242, distributed.  pass 0: with uhbt, storing uh (:737); pass 1: for BT_cont (:1318)
+    double du0 = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool HAVE3D = (pass == 0);
+      if (pass == 0 && !A.uhbt) continue;
+      if (pass == 1 && !set_BT) continue;
+      const double uhbt = (pass == 0 && valid) ? __ldg(A.uhbt + g) : 0.0;
+      const int max_itts = 20;
+      double dux = 0.0, du_max = du_max_CFL, du_min = du_min_CFL;
+      double uh_err = uh_tot_0 - uhbt, duhdu_tot = duhdu_tot_0;
+      double uh_err_best = fabs(uh_err);
+      bool do_I = valid;
+      for (int itt = 1; itt <= max_itts; ++itt) {
+        double tol_eta;
+        if (itt <= 1) tol_eta = 1e-6 * CS.tol_eta;
+        else if (itt == 2) tol_eta = 1e-4 * CS.tol_eta;
+        else if (itt == 3) tol_eta = 1e-2 * CS.tol_eta;
+        else tol_eta = CS.tol_eta;
+        const double tol_vel = CS.tol_vel;
+        if (do_I) {
+          if (uh_err > 0.0) du_max = dux;
+          else if (uh_err < 0.0) du_min = dux;
+          else do_I = false;
+        }
+        if (do_I) {
+          if ((dt * IareaT_min * fabs(uh_err) > tol_eta) ||
+              (CS.better_iter && ((fabs(uh_err) > tol_vel * duhdu_tot) || (fabs(uh_err) > uh_err_best)))) {
+            const double ddu = -uh_err / duhdu_tot;
+            const double du_prev = dux;
+            dux = dux + ddu;
+            if (fabs(ddu) < 1.0e-15 * fabs(dux)) {
+              do_I = false;
+            } else if (ddu > 0.0) {
+              if (dux >= du_max) {
+                dux = 0.5 * (du_prev + du_max);
+                if (du_max - du_prev < 1.0e-15 * fabs(dux)) do_I = false;
+              }
+            } else {
+              if (dux <= du_min) {
+                dux = 0.5 * (du_prev + du_min);
+                if (du_prev - du_min < 1.0e-15 * fabs(dux)) do_I = false;
+              }
+            }
+          } else {
+            do_I = false;
+          }
+        }
+        if (!__syncthreads_or(do_I ? 1 : 0)) break;  // "if (.not.domore) exit"
+        if ((itt < max_itts) || HAVE3D) {
+          if (do_I) {
+#pragma unroll
+            for (int mm = 0; mm < KPT; ++mm) {
+              const int k = s + mm * NS;
+              if (k < nz) {
+                const long long gk = g + (long long)k * G.plane;
+                const double vr = sVR[k * NF + f];
+                const double por = A.por ? __ldg(A.por + gk) : 1.0;
+                const double u_new = sU[k * NF + f] + dux * vr;
+                double uh, dd, ha, hm;
+                flux_from_state(CS, st[mm], dy * por, u_new, vr, dt, cfl0, cfl1, uh, dd, ha, hm);
+                if (HAVE3D) A.uh[gk] = uh;
+                sP[k * NF + f] = uh; sP[PL + k * NF + f] = dd;
+              }
+            }
+          }
+          if (itt < max_itts) {
+            __syncthreads();
+            if (do_I) {
+              if (s == 0) { double t = -uhbt; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
+              else if (s == 1) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
+            }
+            __syncthreads();
+            if (do_I) {
+              uh_err = sR[f]; duhdu_tot = sR[NF + f];
+              uh_err_best = fmin2(uh_err_best, fabs(uh_err));
+            }
+          }
+        }
+      }
+      if (pass == 0) { du = dux; if (A.du_cor && valid && s == 0) A.du_cor[g] = dux; }
+      else du0 = dux;
+    }
+
+    if (set_BT) {
+      // ---- set_zonal_BT_cont :1318-1407
+      const double Idt = 1.0 / dt;
+      const double min_visc_rem = 0.1, CFL_min = 1e-6;
+      const double du_CFL = (CFL_min * Idt) * __ldg(A.dxC + g);
+      __syncthreads();
+      if (s == 0) {
+        double duR = fmin2(0.0, du0 - du_CFL);
+        for (int k = 0; k < nz; ++k) {
+          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+          const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
+          if (visc_rem_lim > 0.0)
+            if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = -(uk + du_CFL * vr) / visc_rem_lim;
+        }
+        sR[f] = duR;
+      } else if (s == 1) {
+        double duL = fmax2(0.0, du0 + du_CFL);
+        for (int k = 0; k < nz; ++k) {
+          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+          const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
+          if (visc_rem_lim > 0.0)
+            if (uk + duL * visc_rem_lim < du_CFL * vr) duL = -(uk - du_CFL * vr) / visc_rem_lim;
+        }
+        sR[NF + f] = duL;
+      }
+      __syncthreads();
+      const double duR = sR[f], duL = sR[NF + f];
+#pragma unroll
+      for (int mm = 0; mm < KPT; ++mm) {
+        const int k = s + mm * NS;
+        if (k < nz) {
+          const long long gk = g + (long long)k * G.plane;
+          const double vr = sVR[k * NF + f], uk = sU[k * NF + f];
+          const double por = A.por ? __ldg(A.por + gk) : 1.0;
+          const double u_L = uk + duL * vr, u_R = uk + duR * vr, u_0 = uk + du0 * vr;
+          double uh_0, dd_0, uh_L, dd_L, uh_R, dd_R, ha, hm;
+          flux_from_state(CS, st[mm], dy * por, u_0, vr, dt, cfl0, cfl1, uh_0, dd_0, ha, hm);
+          flux_from_state(CS, st[mm], dy * por, u_L, vr, dt, cfl0, cfl1, uh_L, dd_L, ha, hm);
+          flux_from_state(CS, st[mm], dy * por, u_R, vr, dt, cfl0, cfl1, uh_R, dd_R, ha, hm);
+          sP[k * NF + f] = dd_0; sP[PL + k * NF + f] = dd_L; sP[2 * PL + k * NF + f] = dd_R;
+          sP[3 * PL + k * NF + f] = uh_L; sP[4 * PL + k * NF + f] = uh_R;
+        }
+      }
+      __syncthreads();
+      if (s < 5) { double t = 0.0; const double* p = sP + s * PL + f; for (int k = 0; k < nz; ++k) t = t + p[k * NF]; sR[s * NF + f] = t; }
+      __syncthreads();
+      if (s == 0 && valid) {
+        const double FAmt_0 = sR[f], FAmt_L = sR[NF + f], FAmt_R = sR[2 * NF + f], uhtot_L = sR[3 * NF + f], uhtot_R = sR[4 * NF + f];
+        double FA_0 = FAmt_0, FA_avg = FAmt_0;
+        if ((duL - du0) != 0.0) FA_avg = uhtot_L / (duL - du0);
+        if (FA_avg > fmax2(FA_0, FAmt_L)) FA_avg = fmax2(FA_0, FAmt_L);
+        else if (FA_avg < fmin2(FA_0, FAmt_L)) FA_0 = FA_avg;
+        A.FA_W0[g] = FA_0; A.FA_WW[g] = FAmt_L;
+        if (fabs(FA_0 - FAmt_L) <= 1e-12 * FA_0) A.uBT_WW[g] = 0.0;
+        else A.uBT_WW[g] = (1.5 * (duL - du0)) * ((FAmt_L - FA_avg) / (FAmt_L - FA_0));
+        FA_0 = FAmt_0; FA_avg = FAmt_0;
+        if ((duR - du0) != 0.0) FA_avg = uhtot_R / (duR - du0);
+        if (FA_avg > fmax2(FA_0, FAmt_R)) FA_avg = fmax2(FA_0, FAmt_R);
+        else if (FA_avg < fmin2(FA_0, FAmt_R)) FA_0 = FA_avg;
+        A.FA_E0[g] = FA_0; A.FA_EE[g] = FAmt_R;
+        if (fabs(FAmt_R - FA_0) <= 1e-12 * FA_0) A.uBT_EE[g] = 0.0;
+        else A.uBT_EE[g] = (1.5 * (duR - du0)) * ((FAmt_R - FA_avg) / (FAmt_R - FA_0));
+      }
+    }
+  }
+  // ---- u_cor (:743-748) and BT_cont%h_u (zonal_flux_thickness :1017-1056, called at :807-815)
+  const bool want_ucor = (A.u_cor != nullptr) && (A.uhbt != nullptr);
+  const bool want_hu = set_BT && (A.h_u != nullptr);
+  if ((want_ucor || want_hu) && valid) {
+#pragma unroll
+    for (int mm = 0; mm < KPT; ++mm) {
+      const int k = s + mm * NS;
+      if (k < nz) {
+        const long long gk = g + (long long)k * G.plane;
+        const double vr = sVR[k * NF + f], uk = sU[k * NF + f];
+        const double uc = uk + du * vr;
+        if (want_ucor) A.u_cor[gk] = uc;
+        if (want_hu) {
+          const double por = A.por ? __ldg(A.por + gk) : 1.0;
+          const double ut = (A.u_cor != nullptr) ? ((A.uhbt != nullptr) ? uc : __ldg(A.u_cor + gk)) : uk;
+          double uh, dd, ha, hm;
+          flux_from_state(CS, st[mm], 1.0, ut, 1.0, dt, cfl0, cfl1, uh, dd, ha, hm);
+          double hu = CS.marginal_faces ? hm : ha;
+          if (use_visc_rem) hu = hu * (vr * por);
+          else if (A.por) hu = hu * por;
+          A.h_u[gk] = hu;
+        }
+      }
+    }
+  }
+}
+
+constexpr int CF_NF = 16, CF_NS = 16;
+
+template <bool Z, int KPT>
+int launch_flux_tiled(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& A) {
+  auto kern = cont_flux_tiled<Z, CF_NF, CF_NS, KPT>;
+  const size_t smem = ((size_t)7 * A.nk * CF_NF + 8 * CF_NF) * sizeof(double);
+  M6_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((A.nhi - A.nlo + CF_NF) / CF_NF, A.ohi - A.olo + 1);
+  M6_LAUNCH(c, kern, grid, CF_NF * CF_NS, smem, G, CS, A);
+  return 0;
+}
+
+template <bool Z>
+int launch_flux(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& A) {
+  const int kpt = (A.nk + CF_NS - 1) / CF_NS;
+  if (kpt <= 1) return launch_flux_tiled<Z, 1>(c, G, CS, A);
+  if (kpt <= 2) return launch_flux_tiled<Z, 2>(c, G, CS, A);
+  if (kpt <= 3) return launch_flux_tiled<Z, 3>(c, G, CS, A);
+  if (kpt <= 5) return launch_flux_tiled<Z, 5>(c, G, CS, A);
+  if (kpt <= 8) return launch_flux_tiled<Z, 8>(c, G, CS, A);
+  // very deep columns: one thread per column
+  dim3 grid((A.nhi - A.nlo + 128) / 128, A.ohi - A.olo + 1);
+  M6_LAUNCH(c, cont_flux_kernel<Z>, grid, 128, 0, G, CS, A);
+  return 0;
+}
+
 // continuity_zonal_convergence :371-378 / continuity_merdional_convergence :409-416
 template <bool Z>
 __global__ void cont_convergence_kernel(const Geom G, double* h, const double* hin, const double* uh,
@@ -437,7 +790,7 @@ int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D) {
   const bool x_first = ((d.first_direction % 2) == 0);
   const int nk = G.nk;
 
-  auto zonal = [&](const double* hsrc, int ish, int ieh, int jsh, int jeh) {
+  auto zonal = [&](const double* hsrc, int ish, int ieh, int jsh, int jeh) -> int {
     FluxArgs A = {};
     A.u = D.u; A.h = hsrc; A.visc_rem = D.visc_rem_u; A.por = D.por_face_areaU; A.uhbt = D.uhbt;
     A.uh = D.uh; A.u_cor = D.u_cor; A.du_cor = D.du_cor; A.h_u = D.have_BT_cont ? D.h_u : nullptr;
@@ -449,10 +802,9 @@ int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D) {
       dim3 gz((G.ied - (G.isd - 1) + 128) / 128, G.jed - G.jsd + 1);
       M6_LAUNCH(c, zero_plane_rect, gz, 128, 0, G, D.du_cor, G.isd - 1, G.ied, G.jsd, G.jed);
     }
-    dim3 grid((A.nhi - A.nlo + 128) / 128, A.ohi - A.olo + 1);
-    M6_LAUNCH(c, cont_flux_kernel<true>, grid, 128, 0, G, CS, A);
+    return launch_flux<true>(c, G, CS, A);
   };
-  auto merid = [&](const double* hsrc, int ish, int ieh, int jsh, int jeh) {
+  auto merid = [&](const double* hsrc, int ish, int ieh, int jsh, int jeh) -> int {
     FluxArgs A = {};
     A.u = D.v; A.h = hsrc; A.visc_rem = D.visc_rem_v; A.por = D.por_face_areaV; A.uhbt = D.vhbt;
     A.uh = D.vh; A.u_cor = D.v_cor; A.du_cor = D.dv_cor; A.h_u = D.have_BT_cont ? D.h_v : nullptr;
@@ -464,25 +816,25 @@ int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D) {
       dim3 gz((G.ied - G.isd + 128) / 128, G.jed - (G.jsd - 1) + 1);
       M6_LAUNCH(c, zero_plane_rect, gz, 128, 0, G, D.dv_cor, G.isd, G.ied, G.jsd - 1, G.jed);
     }
-    dim3 grid((A.nhi - A.nlo + 128) / 128, A.ohi - A.olo + 1);
-    M6_LAUNCH(c, cont_flux_kernel<false>, grid, 128, 0, G, CS, A);
+    return launch_flux<false>(c, G, CS, A);
   };
   auto conv = [&](bool z, const double* hsrc, const double* flux, double hmin, int ish, int ieh, int jsh, int jeh) {
     dim3 grid((ieh - ish + 128) / 128, jeh - jsh + 1, nk < 32 ? nk : 32);
     if (z) M6_LAUNCH(c, cont_convergence_kernel<true>, grid, 128, 0, G, D.h, hsrc, flux, M.IareaT, D.dt, hmin, ish, ieh, jsh, jeh, nk);
     else M6_LAUNCH(c, cont_convergence_kernel<false>, grid, 128, 0, G, D.h, hsrc, flux, M.IareaT, D.dt, hmin, ish, ieh, jsh, jeh, nk);
   };
+  int rc = 0;
   if (x_first) {
     // First advect zonally, with loop bounds that accomodate the subsequent meridional advection (:163-169)
-    zonal(D.hin, d.isc, d.iec, d.jsc - stencil, d.jec + stencil);
+    if ((rc = zonal(D.hin, d.isc, d.iec, d.jsc - stencil, d.jec + stencil))) return rc;
     conv(true, D.hin, D.uh, 0.0, d.isc, d.iec, d.jsc - stencil, d.jec + stencil);
     // Now advect meridionally, using the updated thicknesses to determine the fluxes (:171-176)
-    merid(D.h, d.isc, d.iec, d.jsc, d.jec);
+    if ((rc = merid(D.h, d.isc, d.iec, d.jsc, d.jec))) return rc;
     conv(false, D.h, D.vh, h_min, d.isc, d.iec, d.jsc, d.jec);
   } else {
-    merid(D.hin, d.isc - stencil, d.iec + stencil, d.jsc, d.jec);
+    if ((rc = merid(D.hin, d.isc - stencil, d.iec + stencil, d.jsc, d.jec))) return rc;
     conv(false, D.hin, D.vh, 0.0, d.isc - stencil, d.iec + stencil, d.jsc, d.jec);
-    zonal(D.h, d.isc, d.iec, d.jsc, d.jec);
+    if ((rc = zonal(D.h, d.isc, d.iec, d.jsc, d.jec))) return rc;
     conv(true, D.h, D.uh, h_min, d.isc, d.iec, d.jsc, d.jec);
   }
   M6_CUDA(c, cudaGetLastError());

@@ -59,7 +59,7 @@ __device__ __forceinline__ void en_dis_minmax(const CorAdK& K, const Geom& G, lo
 }
 
 template <int TX, int TY>
-__global__ void __launch_bounds__(TX* TY) corad_kernel(const Geom G, const CorAdK K) {
+__global__ void __launch_bounds__(TX* TY, 3) corad_kernel(const Geom G, const CorAdK K) {
   constexpr int NT = TX * TY, QW = TX + 2, QH = TY + 2, QN = QW * QH, KW = TX + 1, KH = TY + 1, KN = KW * KH;
   __shared__ double sq[QN];    // q(I,J),   I = ti0-1 .. ti0+TX, J = tj0-1 .. tj0+TY
   __shared__ double saux[QN];  // Ih_q (AL_BLEND) or abs_vort (ROBUST_ENSTRO / bound_Coriolis)
@@ -103,8 +103,11 @@ __global__ void __launch_bounds__(TX* TY) corad_kernel(const Geom G, const CorAd
       const double Ih_q = Area_q / (hArea_q + K.vol_neglect);
       qv = abs_vort * Ih_q;
       aux = want_absv ? abs_vort : Ih_q;
-      // diagnostics are owned by the CTA whose tile holds the point
-      if (qx >= 1 && qx <= TX && qy >= 1 && qy <= TY) {
+      // diagnostics are owned by the CTA whose tile holds the point; the first / last tiles also own
+      // the extra row and column of the reference's Isq-1:Ieq+1 range
+      const bool own_x = (qx >= 1 && qx <= TX) || (qx == 0 && blockIdx.y == 0) || (qx == TX + 1 && blockIdx.y == gridDim.y - 1);
+      const bool own_y = (qy >= 1 && qy <= TY) || (qy == 0 && blockIdx.z == 0) || (qy == TY + 1 && blockIdx.z == gridDim.z - 1);
+      if ((K.RV || K.PV) && own_x && own_y) {
         if (K.RV) K.RV[g + koff] = rel_vort;
         if (K.PV) K.PV[g + koff] = qv;
       }

@@ -37,6 +37,13 @@ struct CorAdDev {
   double *RV, *PV, *gradKEu, *gradKEv;
 };
 
+// horizontal_viscosity dummy arguments (MOM_hor_visc.F90:266-305)
+struct HorViscDev {
+  const double *u, *v, *h, *hu_cont, *hv_cont;
+  double *diffu, *diffv;
+};
+
 struct mom6cu_ctx;
+int m6_hor_visc_run(mom6cu_ctx* c, const HorViscDev& D);
 int m6_coradcalc_run(mom6cu_ctx* c, const CorAdDev& D);
 int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D);

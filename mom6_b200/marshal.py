@@ -2,7 +2,7 @@
 import ctypes as C
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
-                   fill_struct)
+                   HorViscCS, HorViscArgs, fill_struct)
 
 
 def _scalars(struct, d):
@@ -46,3 +46,11 @@ def coriolisadv_cs(d):
 
 def coradcalc_args(a, keep):
     return fill_struct(CorAdCalcArgs(), a, keep)
+
+
+def hor_visc_cs(d, keep):
+    return fill_struct(HorViscCS(), d, keep)
+
+
+def hor_visc_args(a, keep):
+    return fill_struct(HorViscArgs(), a, keep)

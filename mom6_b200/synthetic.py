@@ -458,3 +458,176 @@ def coradcalc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True
         a["por_face_areaU"] = 1.0 - 0.3 * r.uniform(0, 1, size=a["u"].shape)
         a["por_face_areaV"] = 1.0 - 0.3 * r.uniform(0, 1, size=a["v"].shape)
     return dom, grid, gv, cs, a
+
+
+def hor_visc_cs(dom, grid, dt=900.0, Laplacian=False, biharmonic=True, Kh=0.0, Kh_vel_scale=0.0, Ah=0.0, Ah_vel_scale=0.0,
+                Ah_time_scale=0.0, Smagorinsky_Kh=False, Smag_Lap_const=0.15, Smagorinsky_Ah=True, Smag_bi_const=0.06,
+                bound_Kh=True, better_bound_Kh=True, bound_Ah=True, better_bound_Ah=True, bound_Coriolis=False,
+                bound_Cor_vel=6.0, bound_coef=0.8, no_slip=False, use_land_mask=False, add_LES_viscosity=False,
+                Kh_bg_min=0.0, Re_Ah=0.0, backscatter_underbound=False, use_cont_thick=False):
+    """hor_visc_init's static arrays (MOM_hor_visc.F90:2834-3120) in numpy, the way the Fortran host computes them
+    once; defaults follow hor_visc_init's get_param defaults with BIHARMONIC + SMAGORINSKY_AH (benchmark-like)."""
+    G = grid
+    if not Laplacian:
+        Smagorinsky_Kh = False; bound_Kh = False; better_bound_Kh = False
+    if not biharmonic:
+        Smagorinsky_Ah = False; bound_Ah = False; better_bound_Ah = False
+    if not Smagorinsky_Ah:
+        bound_Coriolis = False
+    cs = dict(Laplacian=int(Laplacian), biharmonic=int(biharmonic), no_slip=int(no_slip), bound_Kh=int(bound_Kh),
+              better_bound_Kh=int(better_bound_Kh), bound_Ah=int(bound_Ah), better_bound_Ah=int(better_bound_Ah),
+              backscatter_underbound=int(backscatter_underbound), Smagorinsky_Kh=int(Smagorinsky_Kh),
+              Smagorinsky_Ah=int(Smagorinsky_Ah), bound_Coriolis=int(bound_Coriolis), use_land_mask=int(use_land_mask),
+              add_LES_viscosity=int(add_LES_viscosity), use_cont_thick=int(use_cont_thick), use_cont_thick_bug=0,
+              unsupported=0, Kh_bg_min=float(Kh_bg_min), Re_Ah=float(Re_Ah))
+    Idt = 1.0 / dt
+    # faces / corners around an h point (array index shifts, see fidx): E, W faces; N, S faces; corners
+    E = lambda U: U[:, 1:]; W = lambda U: U[:, :-1]        # noqa: E731
+    N = lambda V: V[1:, :]; S = lambda V: V[:-1, :]        # noqa: E731
+    dx2q = G["dxBu"] * G["dxBu"]; dy2q = G["dyBu"] * G["dyBu"]
+    DX_dyBu = G["dxBu"] * G["IdyBu"]; DY_dxBu = G["dyBu"] * G["IdxBu"]
+    dx2h = G["dxT"] * G["dxT"]; dy2h = G["dyT"] * G["dyT"]
+    DX_dyT = G["dxT"] * G["IdyT"]; DY_dxT = G["dyT"] * G["IdxT"]
+    cs.update(dx2q=dx2q, dy2q=dy2q, DX_dyBu=DX_dyBu, DY_dxBu=DY_dxBu, dx2h=dx2h, dy2h=dy2h, DX_dyT=DX_dyT, DY_dxT=DY_dxT)
+
+    def reduce(red, d_, dC):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ok = (d_ > 0.0) & (d_ < dC) & (d_ < dC * red)
+            return np.where(ok, d_ / dC, red)
+    red = np.ones_like(dx2h)
+    for d_, dC in ((E(G["dy_Cu"]), E(G["dyCu"])), (W(G["dy_Cu"]), W(G["dyCu"])), (N(G["dx_Cv"]), N(G["dxCv"])),
+                   (S(G["dx_Cv"]), S(G["dxCv"]))):
+        red = reduce(red, d_, dC)
+    cs["reduction_xx"] = red
+    redq = np.ones_like(dx2q)
+    inner = redq[1:-1, 1:-1]
+    # q(I,J): faces u(I,j), u(I,j+1), v(i,J), v(i+1,J)
+    dyu, dyCu, dxv, dxCv = G["dy_Cu"], G["dyCu"], G["dx_Cv"], G["dxCv"]
+    for d_, dC in ((dyu[:-1, 1:-1], dyCu[:-1, 1:-1]), (dyu[1:, 1:-1], dyCu[1:, 1:-1]),
+                   (dxv[1:-1, :-1], dxCv[1:-1, :-1]), (dxv[1:-1, 1:], dxCv[1:-1, 1:])):
+        inner = reduce(inner, d_, dC)
+    redq[1:-1, 1:-1] = inner
+    cs["reduction_xy"] = redq
+
+    grid_sp_h2 = (2.0 * dx2h * dy2h) / (dx2h + dy2h)
+    grid_sp_h3 = grid_sp_h2 * np.sqrt(grid_sp_h2)
+    grid_sp_q2 = (2.0 * dx2q * dy2q) / (dx2q + dy2q)
+    grid_sp_q3 = grid_sp_q2 * np.sqrt(grid_sp_q2)
+    if Laplacian:
+        Kh_Limit = 0.3 / (dt * 4.0)
+        if Smagorinsky_Kh:
+            cs["Laplac2_const_xx"] = Smag_Lap_const * grid_sp_h2
+            cs["Laplac2_const_xy"] = Smag_Lap_const * grid_sp_q2
+        Kh_bg_xx = np.maximum(Kh, Kh_vel_scale * np.sqrt(grid_sp_h2))
+        Kh_bg_xy = np.maximum(Kh, Kh_vel_scale * np.sqrt(grid_sp_q2))
+        if bound_Kh and not better_bound_Kh:
+            cs["Kh_Max_xx"] = Kh_Limit * grid_sp_h2
+            cs["Kh_Max_xy"] = Kh_Limit * grid_sp_q2
+            Kh_bg_xx = np.minimum(Kh_bg_xx, cs["Kh_Max_xx"]); Kh_bg_xy = np.minimum(Kh_bg_xy, cs["Kh_Max_xy"])
+        cs["Kh_bg_xx"], cs["Kh_bg_xy"] = Kh_bg_xx, Kh_bg_xy
+    IdxCu, IdyCu, IdxCv, IdyCv = G["IdxCu"], G["IdyCu"], G["IdxCv"], G["IdyCv"]
+    IareaCu, IareaCv = G["IareaCu"], G["IareaCv"]
+    if biharmonic:
+        cs["Idx2dyCu"] = (IdxCu * IdxCu) * IdyCu; cs["Idxdy2u"] = IdxCu * (IdyCu * IdyCu)
+        cs["Idx2dyCv"] = (IdxCv * IdxCv) * IdyCv; cs["Idxdy2v"] = IdxCv * (IdyCv * IdyCv)
+        Ah_Limit = 0.3 / (dt * 64.0)
+        if Smagorinsky_Ah:
+            cs["Biharm_const_xx"] = Smag_bi_const * (grid_sp_h2 * grid_sp_h2)
+            cs["Biharm_const_xy"] = Smag_bi_const * (grid_sp_q2 * grid_sp_q2)
+            if bound_Coriolis:
+                BoundCorConst = 1.0 / (5.0 * (bound_Cor_vel * bound_Cor_vel))
+                f = np.abs(G["CoriolisBu"])
+                fmax = np.maximum(np.maximum(f[:-1, :-1], f[:-1, 1:]), np.maximum(f[1:, :-1], f[1:, 1:]))
+                cs["Biharm_const2_xx"] = (grid_sp_h2 * grid_sp_h2 * grid_sp_h2) * (fmax * BoundCorConst)
+                cs["Biharm_const2_xy"] = (grid_sp_q2 * grid_sp_q2 * grid_sp_q2) * (f * BoundCorConst)
+        Ah_bg_xx = np.maximum(Ah, Ah_vel_scale * grid_sp_h2 * np.sqrt(grid_sp_h2))
+        Ah_bg_xy = np.maximum(Ah, Ah_vel_scale * grid_sp_q2 * np.sqrt(grid_sp_q2))
+        if Re_Ah > 0.0:
+            cs["Re_Ah_const_xx"] = grid_sp_h3 / Re_Ah; cs["Re_Ah_const_xy"] = grid_sp_q3 / Re_Ah
+        if Ah_time_scale > 0.0:
+            Ah_bg_xx = np.maximum(Ah_bg_xx, (grid_sp_h2 * grid_sp_h2) / Ah_time_scale)
+            Ah_bg_xy = np.maximum(Ah_bg_xy, (grid_sp_q2 * grid_sp_q2) / Ah_time_scale)
+        if bound_Ah and not better_bound_Ah:
+            cs["Ah_Max_xx"] = Ah_Limit * (grid_sp_h2 * grid_sp_h2); cs["Ah_Max_xy"] = Ah_Limit * (grid_sp_q2 * grid_sp_q2)
+            Ah_bg_xx = np.minimum(Ah_bg_xx, cs["Ah_Max_xx"]); Ah_bg_xy = np.minimum(Ah_bg_xy, cs["Ah_Max_xy"])
+        cs["Ah_bg_xx"], cs["Ah_bg_xy"] = Ah_bg_xx, Ah_bg_xy
+    if Laplacian and better_bound_Kh:   # :3028-3048
+        den = np.maximum(dy2h * DY_dxT * (E(IdyCu) + W(IdyCu)) * np.maximum(E(IdyCu) * E(IareaCu), W(IdyCu) * W(IareaCu)),
+                         dx2h * DX_dyT * (N(IdxCv) + S(IdxCv)) * np.maximum(N(IdxCv) * N(IareaCv), S(IdxCv) * S(IareaCv)))
+        cs["Kh_Max_xx"] = np.where(den > 0.0, bound_coef * 0.25 * Idt / np.where(den > 0, den, 1.0), 0.0)
+        Kq = np.zeros_like(dx2q)
+        q = (slice(1, -1), slice(1, -1))
+        # u(I,j) -> [:-1, 1:-1]; u(I,j+1) -> [1:, 1:-1]; v(i,J) -> [1:-1, :-1]; v(i+1,J) -> [1:-1, 1:]
+        uj, uj1 = (slice(None, -1), slice(1, -1)), (slice(1, None), slice(1, -1))
+        vi, vi1 = (slice(1, -1), slice(None, -1)), (slice(1, -1), slice(1, None))
+        den = np.maximum(dx2q[q] * DX_dyBu[q] * (IdxCu[uj1] + IdxCu[uj]) * np.maximum(IdxCu[uj] * IareaCu[uj], IdxCu[uj1] * IareaCu[uj1]),
+                         dy2q[q] * DY_dxBu[q] * (IdyCv[vi1] + IdyCv[vi]) * np.maximum(IdyCv[vi] * IareaCv[vi], IdyCv[vi1] * IareaCv[vi1]))
+        Kq[q] = np.where(den > 0.0, bound_coef * 0.25 * Idt / np.where(den > 0, den, 1.0), 0.0)
+        cs["Kh_Max_xy"] = Kq
+    if biharmonic and better_bound_Ah:  # :3056-3113
+        Idxdy2u, Idx2dyCu, Idxdy2v, Idx2dyCv = cs["Idxdy2u"], cs["Idx2dyCu"], cs["Idxdy2v"], cs["Idx2dyCv"]
+        nj, ni = dx2h.shape
+        u0u = np.zeros_like(IdxCu); u0v = np.zeros_like(IdxCu); v0u = np.zeros_like(IdxCv); v0v = np.zeros_like(IdxCv)
+        # u point (I,j), interior: h(i,j)=[r,c-1]... use explicit index arrays on the interior (c=1..ni-1, r=1..nj-2)
+        r = slice(1, nj - 1)
+        c = slice(1, ni)            # u columns with both neighbours
+        hW = (r, slice(0, ni - 1)); hE = (r, slice(1, ni))         # h(i,j), h(i+1,j) for u col c
+        uC = (r, c); uE = (r, slice(2, ni + 1)); uW = (r, slice(0, ni - 1))
+        qN = (slice(2, nj), c); qS = (slice(1, nj - 1), c)          # q(I,J), q(I,J-1)
+        uN = (slice(2, nj), c); uS = (slice(0, nj - 2), c)          # u(I,j+1), u(I,j-1)
+        # v at (i,J),(i+1,J),(i,J-1),(i+1,J-1) around u(I,j)
+        vNW = (slice(2, nj), slice(0, ni - 1)); vNE = (slice(2, nj), slice(1, ni))
+        vSW = (slice(1, nj - 1), slice(0, ni - 1)); vSE = (slice(1, nj - 1), slice(1, ni))
+        u0u[uC] = ((Idxdy2u[uC] * ((dy2h[hE] * DY_dxT[hE] * (IdyCu[uE] + IdyCu[uC])) + (dy2h[hW] * DY_dxT[hW] * (IdyCu[uC] + IdyCu[uW])))) +
+                   (Idx2dyCu[uC] * ((dx2q[qN] * DX_dyBu[qN] * (IdxCu[uN] + IdxCu[uC])) + (dx2q[qS] * DX_dyBu[qS] * (IdxCu[uC] + IdxCu[uS])))))
+        u0v[uC] = ((Idxdy2u[uC] * ((dy2h[hE] * DX_dyT[hE] * (IdxCv[vNE] + IdxCv[vSE])) + (dy2h[hW] * DX_dyT[hW] * (IdxCv[vNW] + IdxCv[vSW])))) +
+                   (Idx2dyCu[uC] * ((dx2q[qN] * DY_dxBu[qN] * (IdyCv[vNE] + IdyCv[vNW])) + (dx2q[qS] * DY_dxBu[qS] * (IdyCv[vSE] + IdyCv[vSW])))))
+        # v point (i,J): rows 1..nj-1, cols 1..ni-2
+        rr = slice(1, nj); cc = slice(1, ni - 1)
+        vC = (rr, cc); vNn = (slice(2, nj + 1), cc); vSs = (slice(0, nj - 1), cc); vEe = (rr, slice(2, ni)); vWw = (rr, slice(0, ni - 2))
+        qE = (rr, slice(2, ni)); qW = (rr, slice(1, ni - 1))       # q(I,J), q(I-1,J)
+        hN = (slice(1, nj), cc); hS = (slice(0, nj - 1), cc)       # h(i,j+1), h(i,j)
+        # u at (I,j+1),(I,j),(I-1,j+1),(I-1,j) around v(i,J)
+        uNE = (slice(1, nj), slice(2, ni)); uSE = (slice(0, nj - 1), slice(2, ni))
+        uNW = (slice(1, nj), slice(1, ni - 1)); uSW = (slice(0, nj - 1), slice(1, ni - 1))
+        v0u[vC] = ((Idxdy2v[vC] * ((dy2q[qE] * DX_dyBu[qE] * (IdxCu[uNE] + IdxCu[uSE])) + (dy2q[qW] * DX_dyBu[qW] * (IdxCu[uNW] + IdxCu[uSW])))) +
+                   (Idx2dyCv[vC] * ((dx2h[hN] * DY_dxT[hN] * (IdyCu[uNE] + IdyCu[uNW])) + (dx2h[hS] * DY_dxT[hS] * (IdyCu[uSE] + IdyCu[uSW])))))
+        v0v[vC] = ((Idxdy2v[vC] * ((dy2q[qE] * DY_dxBu[qE] * (IdyCv[vEe] + IdyCv[vC])) + (dy2q[qW] * DY_dxBu[qW] * (IdyCv[vC] + IdyCv[vWw])))) +
+                   (Idx2dyCv[vC] * ((dx2h[hN] * DX_dyT[hN] * (IdxCv[vNn] + IdxCv[vC])) + (dx2h[hS] * DX_dyT[hS] * (IdxCv[vC] + IdxCv[vSs])))))
+        den = np.maximum(
+            dy2h * ((DY_dxT * ((E(IdyCu) * E(u0u)) + (W(IdyCu) * W(u0u)))) + (DX_dyT * ((N(IdxCv) * N(v0u)) + (S(IdxCv) * S(v0u))))) *
+            np.maximum(E(IdyCu) * E(IareaCu), W(IdyCu) * W(IareaCu)),
+            dx2h * ((DY_dxT * ((E(IdyCu) * E(u0v)) + (W(IdyCu) * W(u0v)))) + (DX_dyT * ((N(IdxCv) * N(v0v)) + (S(IdxCv) * S(v0v))))) *
+            np.maximum(N(IdxCv) * N(IareaCv), S(IdxCv) * S(IareaCv)))
+        cs["Ah_Max_xx"] = np.where(den > 0.0, bound_coef * 0.5 * Idt / np.where(den > 0, den, 1.0), 0.0)
+        Aq = np.zeros_like(dx2q)
+        q = (slice(1, -1), slice(1, -1))
+        uj, uj1 = (slice(None, -1), slice(1, -1)), (slice(1, None), slice(1, -1))
+        vi, vi1 = (slice(1, -1), slice(None, -1)), (slice(1, -1), slice(1, None))
+        den = np.maximum(
+            dx2q[q] * ((DX_dyBu[q] * ((u0u[uj1] * IdxCu[uj1]) + (u0u[uj] * IdxCu[uj]))) + (DY_dxBu[q] * ((v0u[vi1] * IdyCv[vi1]) + (v0u[vi] * IdyCv[vi])))) *
+            np.maximum(IdxCu[uj] * IareaCu[uj], IdxCu[uj1] * IareaCu[uj1]),
+            dy2q[q] * ((DX_dyBu[q] * ((u0v[uj1] * IdxCu[uj1]) + (u0v[uj] * IdxCu[uj]))) + (DY_dxBu[q] * ((v0v[vi1] * IdyCv[vi1]) + (v0v[vi] * IdyCv[vi])))) *
+            np.maximum(IdyCv[vi] * IareaCv[vi], IdyCv[vi1] * IareaCv[vi1]))
+        Aq[q] = np.where(den > 0.0, bound_coef * 0.5 * Idt / np.where(den > 0, den, 1.0), 0.0)
+        cs["Ah_Max_xy"] = Aq
+    return {k: (np.ascontiguousarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in cs.items()}
+
+
+def hor_visc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, dt=900.0, cont_thick=False,
+                    vel=0.3, **cs_kw):
+    """Everything a horizontal_viscosity call needs (MOM_hor_visc.F90:266): returns dom, grid, vgrid, cs, args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    cs = hor_visc_cs(dom, grid, dt=dt, use_cont_thick=cont_thick, **cs_kw)
+    st = dyn_state(dom, grid, seed, vel=vel)
+    a = dict(u=st["u"], v=st["v"], h=st["h"], dt=dt)
+    a["diffu"] = fidx.new(dom, "u", nk=nk).a
+    a["diffv"] = fidx.new(dom, "v", nk=nk).a
+    if cont_thick:
+        h = st["h"]
+        hu = fidx.new(dom, "u", nk=nk); hu.a[:, :, 1:-1] = np.minimum(h[:, :, :-1], h[:, :, 1:]); hu.a[:, :, 0] = h[:, :, 0]; hu.a[:, :, -1] = h[:, :, -1]
+        hv = fidx.new(dom, "v", nk=nk); hv.a[:, 1:-1, :] = np.minimum(h[:, :-1, :], h[:, 1:, :]); hv.a[:, 0, :] = h[:, 0, :]; hv.a[:, -1, :] = h[:, -1, :]
+        a["hu_cont"], a["hv_cont"] = hu.a, hv.a
+    return dom, grid, gv, cs, a

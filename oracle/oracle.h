@@ -42,6 +42,10 @@ int oracle_coradcalc(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6c
                      const mom6cu_unit_scale* US, const mom6cu_coriolisadv_cs* CS,
                      const mom6cu_coradcalc_args* a, int nthreads);
 
+/* horizontal_viscosity, MOM_hor_visc.F90:266-2317 (frozen option set) */
+int oracle_horizontal_viscosity(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
+                                const mom6cu_hor_visc_cs* CS, const mom6cu_hor_visc_args* a, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,19 @@ def coradcalc(dom, grid, gv, cs, args, us=None, nthreads=1):
     if rc != 0:
         raise RuntimeError(f"oracle_coradcalc rc={rc}")
     return rc
+
+
+def horizontal_viscosity(dom, grid, gv, cs, args, nthreads=1):
+    """oracle_horizontal_viscosity: MOM_hor_visc.F90:266-2317 (frozen option set) on host arrays."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    v = marshal.vgrid(gv)
+    c = marshal.hor_visc_cs(cs, keep)
+    a = marshal.hor_visc_args(args, keep)
+    lib.oracle_horizontal_viscosity.argtypes = [C.c_void_p] * 5 + [C.c_int]
+    rc = lib.oracle_horizontal_viscosity(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(a), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_horizontal_viscosity rc={rc}")
+    return rc

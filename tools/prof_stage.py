@@ -1,0 +1,37 @@
+"""Per-stage timing: python tools/prof_stage.py <stage> [ni nj nk reps]   (run under ncu for captures)
+Device time = CUDA events around the stage kernels (mom6cu_last_kernel_ms).  Algorithmic bytes per cell
+are SURVEY 8d's figures."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mom6_b200 import synthetic
+from mom6_b200.api import Context
+stage = sys.argv[1]
+ni = int(sys.argv[2]) if len(sys.argv) > 2 else 1440
+nj = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
+nk = int(sys.argv[4]) if len(sys.argv) > 4 else 75
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+BYTES = {"continuity": 96, "corad": 56, "hor_visc": 56, "pgf": 48}
+t0 = time.time()
+if stage == "corad":
+    dom, grid, gv, cs, a = synthetic.coradcalc_inputs(ni, nj, nk, land_blocks=40)
+elif stage == "continuity":
+    dom, grid, gv, cs, a = synthetic.continuity_inputs(ni, nj, nk, land_blocks=40)
+elif stage == "hor_visc":
+    dom, grid, gv, cs, a = synthetic.hor_visc_inputs(ni, nj, nk, land_blocks=40)
+else:
+    raise SystemExit("unknown stage " + stage)
+print(f"inputs built in {time.time()-t0:.1f}s", flush=True)
+ctx = Context(dom, 0)
+ctx.set_grid(grid); ctx.set_vgrid(gv)
+if stage == "corad":
+    ctx.set_cs_coriolisadv(cs); run = ctx.coradcalc
+elif stage == "continuity":
+    ctx.set_cs_continuity(cs); run = ctx.continuity
+elif stage == "hor_visc":
+    ctx.set_cs_hor_visc(cs); run = ctx.horizontal_viscosity
+for r in range(reps):
+    run(a)
+    ms = ctx.last_kernel_ms
+    print(f"{stage} {ni}x{nj}x{nk}: {ms:.3f} ms, {ni*nj*nk/ms/1e6:.3f} Gcell/s, "
+          f"{ni*nj*nk*BYTES[stage]/ms/1e6:.1f} GB/s algorithmic ({BYTES[stage]} B/cell)", flush=True)
+ctx.close()
