@@ -1,0 +1,198 @@
+!> ISO_C_BINDING interfaces to the B200-native dycore library (include/mom6cu.h, libmom6cu.so).
+!!
+!! This module is what a MOM6 maintainer adds to the source tree (e.g. under config_src/external/mom6cu/,
+!! selected at build time exactly like the other config_src/external/* and config_src/infra/FMS1|FMS2
+!! directory swaps, ac/configure.ac:227-264).  The drop-in replacement modules (MOM_continuity_PPM.F90,
+!! MOM_CoriolisAdv.F90, MOM_hor_visc.F90, MOM_barotropic.F90 ...) keep the reference's module names and
+!! public procedure signatures and forward to these interfaces; see fortran/MOM_continuity_PPM_cu.F90 for
+!! the worked example and INTEGRATION.md for the rest.
+!!
+!! NOTE: no Fortran compiler exists in the build container, so this file has not been compiled there; it
+!! uses only standard Fortran 2003 interoperability (bind(C), c_ptr, c_loc on contiguous targets).
+module mom6cu_interface
+  use, intrinsic :: iso_c_binding
+  implicit none ; public
+
+  integer(c_int), parameter :: MOM6CU_OK = 0
+
+  !> mom6cu_domain (include/mom6cu.h): the hor_index_type / barotropic_CS bounds the hot path uses
+  type, bind(C) :: mom6cu_domain
+    integer(c_int) :: isc, iec, jsc, jec
+    integer(c_int) :: isd, ied, jsd, jed
+    integer(c_int) :: isdw, iedw, jsdw, jedw
+    integer(c_int) :: nk
+    integer(c_int) :: cyclic_x, cyclic_y
+    integer(c_int) :: first_direction
+    integer(c_int) :: npi, npj, pi, pj
+  end type mom6cu_domain
+
+  !> mom6cu_grid: pointers to the ocean_grid_type metrics (src/core/MOM_grid.F90:75-175)
+  type, bind(C) :: mom6cu_grid
+    type(c_ptr) :: mask2dT, mask2dCu, mask2dCv, mask2dBu
+    type(c_ptr) :: dxT, dyT, IdxT, IdyT, areaT, IareaT
+    type(c_ptr) :: dxCu, dyCu, IdxCu, IdyCu, dy_Cu, areaCu, IareaCu
+    type(c_ptr) :: dxCv, dyCv, IdxCv, IdyCv, dx_Cv, areaCv, IareaCv
+    type(c_ptr) :: dxBu, dyBu, IdxBu, IdyBu, areaBu, IareaBu
+    type(c_ptr) :: bathyT, CoriolisBu, Coriolis2Bu
+  end type mom6cu_grid
+
+  type, bind(C) :: mom6cu_vgrid
+    real(c_double) :: Angstrom_H, H_subroundoff, Z_to_H, H_to_Z, g_Earth, Rho0, H_to_RZ, RZ_to_H, H_to_m, m_to_H
+    integer(c_int) :: Boussinesq
+  end type mom6cu_vgrid
+
+  !> continuity_PPM_CS (src/core/MOM_continuity_PPM.F90:35-67)
+  type, bind(C) :: mom6cu_continuity_cs
+    integer(c_int) :: upwind_1st, monotonic, simple_2nd, aggress_adjust, vol_CFL, better_iter, &
+                      use_visc_rem_max, marginal_faces
+    real(c_double) :: tol_eta, tol_vel, CFL_limit_adjust
+  end type mom6cu_continuity_cs
+
+  !> BT_cont_type (src/core/MOM_variables.F90:315-350)
+  type, bind(C) :: mom6cu_bt_cont
+    type(c_ptr) :: FA_u_EE, FA_u_E0, FA_u_W0, FA_u_WW, uBT_WW, uBT_EE
+    type(c_ptr) :: FA_v_NN, FA_v_N0, FA_v_S0, FA_v_SS, vBT_SS, vBT_NN
+    type(c_ptr) :: h_u, h_v
+  end type mom6cu_bt_cont
+
+  !> Arguments of continuity_PPM (src/core/MOM_continuity_PPM.F90:86-141); absent optionals are c_null_ptr
+  type, bind(C) :: mom6cu_continuity_args
+    type(c_ptr) :: u, v, hin, h, uh, vh
+    real(c_double) :: dt
+    type(c_ptr) :: por_face_areaU, por_face_areaV, uhbt, vhbt, visc_rem_u, visc_rem_v, u_cor, v_cor
+    type(c_ptr) :: BT_cont
+    type(c_ptr) :: du_cor, dv_cor
+  end type mom6cu_continuity_args
+
+  !> CoriolisAdv_CS (src/core/MOM_CoriolisAdv.F90:30-91)
+  type, bind(C) :: mom6cu_coriolisadv_cs
+    integer(c_int) :: Coriolis_Scheme, KE_Scheme, PV_Adv_Scheme, no_slip, bound_Coriolis, Coriolis_En_Dis
+    real(c_double) :: F_eff_max_blend, wt_lin_blend
+  end type mom6cu_coriolisadv_cs
+
+  !> Arguments of CorAdCalc (src/core/MOM_CoriolisAdv.F90:125-144)
+  type, bind(C) :: mom6cu_coradcalc_args
+    type(c_ptr) :: u, v, h, uh, vh, CAu, CAv, por_face_areaU, por_face_areaV, RV, PV, gradKEu, gradKEv
+  end type mom6cu_coradcalc_args
+
+  !> Arguments of horizontal_viscosity (src/parameterizations/lateral/MOM_hor_visc.F90:266-305)
+  type, bind(C) :: mom6cu_hor_visc_args
+    type(c_ptr) :: u, v, h, uh, vh, diffu, diffv, hu_cont, hv_cont
+    real(c_double) :: dt
+  end type mom6cu_hor_visc_args
+
+  interface
+    integer(c_int) function mom6cu_create(ctx, dom, device) bind(C, name="mom6cu_create")
+      import :: c_int, c_ptr, mom6cu_domain
+      type(c_ptr), intent(out) :: ctx
+      type(mom6cu_domain), intent(in) :: dom
+      integer(c_int), value :: device
+    end function mom6cu_create
+    integer(c_int) function mom6cu_destroy(ctx) bind(C, name="mom6cu_destroy")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+    end function mom6cu_destroy
+    integer(c_int) function mom6cu_last_error(ctx, buf, len) bind(C, name="mom6cu_last_error")
+      import :: c_int, c_ptr, c_char, c_size_t
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(out) :: buf(*)
+      integer(c_size_t), value :: len
+    end function mom6cu_last_error
+    integer(c_int) function mom6cu_set_grid(ctx, G) bind(C, name="mom6cu_set_grid")
+      import :: c_int, c_ptr, mom6cu_grid
+      type(c_ptr), value :: ctx
+      type(mom6cu_grid), intent(in) :: G
+    end function mom6cu_set_grid
+    integer(c_int) function mom6cu_set_vgrid(ctx, GV) bind(C, name="mom6cu_set_vgrid")
+      import :: c_int, c_ptr, mom6cu_vgrid
+      type(c_ptr), value :: ctx
+      type(mom6cu_vgrid), intent(in) :: GV
+    end function mom6cu_set_vgrid
+    integer(c_int) function mom6cu_set_cs_continuity(ctx, CS) bind(C, name="mom6cu_set_cs_continuity")
+      import :: c_int, c_ptr, mom6cu_continuity_cs
+      type(c_ptr), value :: ctx
+      type(mom6cu_continuity_cs), intent(in) :: CS
+    end function mom6cu_set_cs_continuity
+    integer(c_int) function mom6cu_continuity(ctx, a) bind(C, name="mom6cu_continuity")
+      import :: c_int, c_ptr, mom6cu_continuity_args
+      type(c_ptr), value :: ctx
+      type(mom6cu_continuity_args), intent(in) :: a
+    end function mom6cu_continuity
+    integer(c_int) function mom6cu_set_cs_coriolisadv(ctx, CS) bind(C, name="mom6cu_set_cs_coriolisadv")
+      import :: c_int, c_ptr, mom6cu_coriolisadv_cs
+      type(c_ptr), value :: ctx
+      type(mom6cu_coriolisadv_cs), intent(in) :: CS
+    end function mom6cu_set_cs_coriolisadv
+    integer(c_int) function mom6cu_coradcalc(ctx, a) bind(C, name="mom6cu_coradcalc")
+      import :: c_int, c_ptr, mom6cu_coradcalc_args
+      type(c_ptr), value :: ctx
+      type(mom6cu_coradcalc_args), intent(in) :: a
+    end function mom6cu_coradcalc
+    !> mom6cu_set_cs_hor_visc takes the C struct mom6cu_hor_visc_cs (16 ints, 2 doubles, 30 pointers in the order
+    !! of include/mom6cu.h); it is passed here as an opaque pointer to a bind(C) copy built by hor_visc_init.
+    integer(c_int) function mom6cu_set_cs_hor_visc(ctx, CS) bind(C, name="mom6cu_set_cs_hor_visc")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: CS
+    end function mom6cu_set_cs_hor_visc
+    integer(c_int) function mom6cu_horizontal_viscosity(ctx, a) bind(C, name="mom6cu_horizontal_viscosity")
+      import :: c_int, c_ptr, mom6cu_hor_visc_args
+      type(c_ptr), value :: ctx
+      type(mom6cu_hor_visc_args), intent(in) :: a
+    end function mom6cu_horizontal_viscosity
+    !> btstep_timeloop (MOM_barotropic.F90:2175): takes the C struct mom6cu_bt_timeloop_args
+    integer(c_int) function mom6cu_btstep_timeloop(ctx, a) bind(C, name="mom6cu_btstep_timeloop")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: a
+    end function mom6cu_btstep_timeloop
+    integer(c_int) function mom6cu_comm_unique_id(buf, nbytes) bind(C, name="mom6cu_comm_unique_id")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: buf
+      integer(c_int), value :: nbytes
+    end function mom6cu_comm_unique_id
+    integer(c_int) function mom6cu_comm_init(ctx, id, nbytes, rank, nranks) bind(C, name="mom6cu_comm_init")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx, id
+      integer(c_int), value :: nbytes, rank, nranks
+    end function mom6cu_comm_init
+  end interface
+
+  !> The one device context of this PE (one MPI rank = one tile = one GPU)
+  type(c_ptr), save :: mom6cu_ctx = c_null_ptr
+
+contains
+
+  !> Turn a nonzero status into MOM_error(FATAL, msg) / MOM_error(WARNING, ...), the reference's error convention
+  !! (src/framework/MOM_error_handler.F90).
+  subroutine mom6cu_check(rc, where)
+    use MOM_error_handler, only : MOM_error, FATAL, WARNING
+    integer(c_int),   intent(in) :: rc
+    character(len=*), intent(in) :: where
+    character(kind=c_char) :: buf(1024)
+    character(len=1024) :: msg
+    integer :: n, ierr
+    if (rc == 0) return
+    if (rc < 0) then
+      call MOM_error(WARNING, trim(where)//": the device path issued warnings.")
+      return
+    endif
+    ierr = mom6cu_last_error(mom6cu_ctx, buf, int(1024, c_size_t))
+    msg = " "
+    do n=1,1024 ; if (buf(n) == c_null_char) exit ; msg(n:n) = buf(n) ; enddo
+    call MOM_error(FATAL, trim(where)//": "//trim(msg))
+  end subroutine mom6cu_check
+
+  !> c_loc of an optional array, or c_null_ptr when it is absent (Fortran optional -> NULL)
+  function opt_loc3(a) result(p)
+    real(c_double), dimension(:,:,:), optional, target, intent(in) :: a
+    type(c_ptr) :: p
+    p = c_null_ptr ; if (present(a)) p = c_loc(a)
+  end function opt_loc3
+  function opt_loc2(a) result(p)
+    real(c_double), dimension(:,:), optional, target, intent(in) :: a
+    type(c_ptr) :: p
+    p = c_null_ptr ; if (present(a)) p = c_loc(a)
+  end function opt_loc2
+
+end module mom6cu_interface
