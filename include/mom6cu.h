@@ -298,6 +298,68 @@ typedef struct mom6cu_bt_timeloop_args {
 
 int mom6cu_btstep_timeloop(mom6cu_ctx* ctx, const mom6cu_bt_timeloop_args* a);
 
+/* ------------------------------------------------------------------ btstep */
+/* barotropic_CS, src/core/MOM_barotropic.F90:112-364, as resolved by barotropic_init (:5301) and kept current by
+ * btcalc / bt_mass_source / set_dtbt.  "wide" members have the BT_Domain extents (isdw..iedw), the others G's.
+ * Frozen options (rejected through `unsupported` or at call time): OBCs, tides/SAL, dynamic_psurf,
+ * linear_wave_drag, streaming filter / frequency-dependent drag, INTEGRAL_BT_CONTINUITY, nonlinear continuity
+ * (USE_BT_CONT_TYPE=False), NONLIN_BT_STRESS, gradual_BT_ICs, eta_PF_start interpolation, answer_date < 20190101. */
+typedef struct mom6cu_barotropic_cs {
+  int Sadourny, BT_project_velocity, strong_drag, bound_BT_corr, BT_cont_bounds, wt_uv_bug, visc_rem_u_uh0,
+      adjust_BT_cont, use_wide_halos, min_stencil, use_old_coriolis_bracket_bug, unsupported;
+  double dtbt, bebt, vel_underflow, maxCFL_BT_cont, G_extra, dt_bt_filter;
+  /* wide */
+  const double *IareaT, *IareaT_OBCmask, *bathyT, *IdxCu, *IdyCv; /* h, h, h, u, v */
+  const double *q_D, *D_u_Cor, *D_v_Cor;                          /* q, u, v (LINEARIZED_BT_CORIOLIS) */
+  const double *ua_polarity, *va_polarity;                        /* h */
+  const double *OBCmask_u, *OBCmask_v;                            /* u, v (all ones without OBCs) */
+  /* G-sized */
+  const double *frhatu, *frhatv;   /* 3-D u, v: set by btcalc */
+  double *eta_cor;                 /* h, inout: set by bt_mass_source, bounded here (:1552-1585) */
+  const double *eta_cor_bound;     /* h, used when bound_BT_corr && !BT_cont_bounds */
+  const double *IDatu, *IDatv;     /* u, v */
+  double *ubtav, *vbtav;           /* u, v (out) */
+} mom6cu_barotropic_cs;
+
+/* btstep(U_in, V_in, eta_in, dt, bc_accel_u, bc_accel_v, forces, pbce, eta_PF_in, U_Cor, V_Cor, accel_layer_u,
+ *        accel_layer_v, eta_out, uhbtav, vhbtav, G, GV, US, CS, visc_rem_u, visc_rem_v, SpV_avg, ADp, OBC, BT_cont,
+ *        eta_PF_start, taux_bot, tauy_bot, uh0, vh0, u_uh0, v_vh0, etaav)       MOM_barotropic.F90:455-2172
+ * Pointer optionals are NULL when not associated / absent; BT_cont is required (USE_BT_CONT_TYPE=True). */
+typedef struct mom6cu_btstep_args {
+  const double *U_in, *V_in;             /* 3-D u, v */
+  const double *eta_in;                  /* 2-D h */
+  double dt;
+  const double *bc_accel_u, *bc_accel_v; /* 3-D u, v */
+  const double *taux, *tauy;             /* forces%taux, forces%tauy: 2-D u, v */
+  const double *pbce;                    /* 3-D h */
+  const double *eta_PF_in;               /* 2-D h */
+  const double *U_Cor, *V_Cor;           /* 3-D u, v */
+  double *accel_layer_u, *accel_layer_v; /* 3-D u, v (out) */
+  double *eta_out;                       /* 2-D h (out; may alias eta_in) */
+  double *uhbtav, *vhbtav;               /* 2-D u, v (out) */
+  const double *visc_rem_u, *visc_rem_v; /* 3-D u, v */
+  const mom6cu_bt_cont* BT_cont;
+  const double *taux_bot, *tauy_bot;     /* 2-D u, v, optional */
+  const double *uh0, *vh0, *u_uh0, *v_vh0; /* 3-D, optional (all or none) */
+  double *etaav;                         /* 2-D h, optional out */
+} mom6cu_btstep_args;
+int mom6cu_btstep(mom6cu_ctx* ctx, const mom6cu_barotropic_cs* CS, const mom6cu_btstep_args* a);
+
+/* btcalc(h, G, GV, CS, h_u, h_v, may_use_default, OBC)  MOM_barotropic.F90:4360-4605: the layer weights
+ * frhatu/frhatv (3-D u, v; out) from h or, when given, from BT_cont%h_u, h_v.  hvel_scheme: 1 HARMONIC,
+ * 2 ARITHMETIC, 3 HYBRID, 4 FROM_BT_CONT (:432-435). */
+typedef struct mom6cu_btcalc_args {
+  const double *h, *h_u, *h_v; /* 3-D h; optional 3-D u, v */
+  double *frhatu, *frhatv;     /* 3-D u, v (out) */
+  const double *bathyT;        /* G-sized h (G%bathyT) */
+  int hvel_scheme, may_use_default;
+} mom6cu_btcalc_args;
+int mom6cu_btcalc(mom6cu_ctx* ctx, const mom6cu_btcalc_args* a);
+
+/* bt_mass_source(h, eta, set_cor, G, GV, CS)  MOM_barotropic.F90:5243-5296; eta_cor 2-D h (inout),
+ * eta_mass_source: CS%eta_source (2-D h) or NULL. */
+int mom6cu_bt_mass_source(mom6cu_ctx* ctx, const double* h, const double* eta, int set_cor, double* eta_cor);
+
 /* Microbenchmark form: upload once (state + coefficients stay resident in
  * HBM), run the substep loop `reps` times from the same initial state, and
  * return the device time of the LAST repetition through mom6cu_last_kernel_ms.

@@ -128,6 +128,37 @@ class HorViscArgs(C.Structure):
                [("dt", C.c_double)]
 
 
+BT_CS_INT = ["Sadourny", "BT_project_velocity", "strong_drag", "bound_BT_corr", "BT_cont_bounds", "wt_uv_bug",
+             "visc_rem_u_uh0", "adjust_BT_cont", "use_wide_halos", "min_stencil", "use_old_coriolis_bracket_bug",
+             "unsupported"]
+BT_CS_DBL = ["dtbt", "bebt", "vel_underflow", "maxCFL_BT_cont", "G_extra", "dt_bt_filter"]
+BT_CS_PTR = ["IareaT", "IareaT_OBCmask", "bathyT", "IdxCu", "IdyCv", "q_D", "D_u_Cor", "D_v_Cor", "ua_polarity",
+             "va_polarity", "OBCmask_u", "OBCmask_v", "frhatu", "frhatv", "eta_cor", "eta_cor_bound", "IDatu", "IDatv",
+             "ubtav", "vbtav"]
+
+
+class BarotropicCS(C.Structure):
+    """mom6cu_barotropic_cs: barotropic_CS (MOM_barotropic.F90:112-364)."""
+    _fields_ = ([(n, C.c_int) for n in BT_CS_INT] + [(n, C.c_double) for n in BT_CS_DBL] +
+                [(n, C.c_void_p) for n in BT_CS_PTR])
+
+
+class BtstepArgs(C.Structure):
+    """mom6cu_btstep_args: the dummy arguments of btstep (MOM_barotropic.F90:455-529)."""
+    _fields_ = ([(n, C.c_void_p) for n in ("U_in", "V_in", "eta_in")] + [("dt", C.c_double)] +
+                [(n, C.c_void_p) for n in ("bc_accel_u", "bc_accel_v", "taux", "tauy", "pbce", "eta_PF_in", "U_Cor", "V_Cor",
+                                           "accel_layer_u", "accel_layer_v", "eta_out", "uhbtav", "vhbtav", "visc_rem_u",
+                                           "visc_rem_v")] +
+                [("BT_cont", C.POINTER(BTCont))] +
+                [(n, C.c_void_p) for n in ("taux_bot", "tauy_bot", "uh0", "vh0", "u_uh0", "v_vh0", "etaav")])
+
+
+class BtcalcArgs(C.Structure):
+    """mom6cu_btcalc_args: btcalc (MOM_barotropic.F90:4360)."""
+    _fields_ = [(n, C.c_void_p) for n in ("h", "h_u", "h_v", "frhatu", "frhatv", "bathyT")] + \
+               [("hvel_scheme", C.c_int), ("may_use_default", C.c_int)]
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
@@ -179,6 +210,9 @@ def bind(lib):
     lib.mom6cu_coradcalc.argtypes = [vp, C.POINTER(CorAdCalcArgs)]
     lib.mom6cu_set_cs_hor_visc.argtypes = [vp, C.POINTER(HorViscCS)]
     lib.mom6cu_horizontal_viscosity.argtypes = [vp, C.POINTER(HorViscArgs)]
+    lib.mom6cu_btstep.argtypes = [vp, C.POINTER(BarotropicCS), C.POINTER(BtstepArgs)]
+    lib.mom6cu_btcalc.argtypes = [vp, C.POINTER(BtcalcArgs)]
+    lib.mom6cu_bt_mass_source.argtypes = [vp, vp, vp, C.c_int, vp]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

@@ -126,8 +126,24 @@ def _ctx_methods():
         st = marshal.hor_visc_args(args, keep)
         return self._check(self.lib.mom6cu_horizontal_viscosity(self._h, C.byref(st)))
 
+    def btstep(self, cs, args):
+        """btstep, MOM_barotropic.F90:455 (cs = the barotropic_CS members it reads / updates)."""
+        keep = []
+        return self._check(self.lib.mom6cu_btstep(self._h, C.byref(marshal.barotropic_cs(cs, keep)),
+                                                  C.byref(marshal.btstep_args(args, keep))))
+
+    def btcalc(self, args):
+        """btcalc, MOM_barotropic.F90:4360."""
+        keep = []
+        return self._check(self.lib.mom6cu_btcalc(self._h, C.byref(marshal.btcalc_args(args, keep))))
+
+    def bt_mass_source(self, h, eta, set_cor, eta_cor):
+        """bt_mass_source, MOM_barotropic.F90:5243."""
+        return self._check(self.lib.mom6cu_bt_mass_source(self._h, h.ctypes.data, eta.ctypes.data, int(set_cor),
+                                                          eta_cor.ctypes.data))
+
     for f in (set_grid, set_vgrid, set_cs_continuity, continuity, set_unit_scale, set_cs_coriolisadv, coradcalc,
-              set_cs_hor_visc, horizontal_viscosity):
+              set_cs_hor_visc, horizontal_viscosity, btstep, btcalc, bt_mass_source):
         setattr(Context, f.__name__, f)
 
 

@@ -24,6 +24,7 @@
 //    (the reference's BTCL_u/v array-of-structs is split into 10 planes at upload) so
 //    each warp load is a contiguous 256-byte request.
 #include "ctx.h"
+#include "bt_planes.h"
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -34,24 +35,6 @@ using m6::Geom;
 
 // local_BT_cont_u_type field order, MOM_barotropic.F90:367-390
 enum { FA_EE = 0, FA_E0, FA_W0, FA_WW, UBT_WW, UBT_EE, CRV_W, CRV_E, UH_WW, UH_EE };
-
-struct BtPlanes {
-  // ping-pong state
-  const double* eta_in; const double* ubt_in; const double* vbt_in;
-  double* eta_out; double* ubt_out; double* vbt_out;
-  // coefficients
-  const double* uhbt0; const double* vhbt0; const double* Datu; const double* Datv;
-  const double* bu[10]; const double* bv[10];
-  const double* eta_src; const double* eta_PF;
-  const double* gtot_E; const double* gtot_W; const double* gtot_N; const double* gtot_S;
-  const double* f4u[4]; const double* f4v[4];
-  const double* bt_rem_u; const double* bt_rem_v; const double* BT_force_u; const double* BT_force_v;
-  const double* Cor_ref_u; const double* Cor_ref_v;
-  const double* IareaT; const double* IdxCu; const double* IdyCv;
-  // accumulators
-  double* u_accel_bt; double* v_accel_bt; double* eta_sum; double* eta_wtd;
-  double* ubtav; double* vbtav; double* uhbtav; double* vhbtav; double* ubt_wtd; double* vbt_wtd;
-};
 
 struct BtStep {
   int isv, iev, jsv, jev;  // valid range of this substep
@@ -270,12 +253,8 @@ int launch_substep(mom6cu_ctx* c, const BtPlanes& P, const BtStep& S) {
   return 0;
 }
 
-struct BtDevice {  // device planes of one timeloop call
-  BtPlanes P;
-  double* eta[2]; double* ubt[2]; double* vbt[2];
-};
-
-int bt_alloc(mom6cu_ctx* c, BtDevice& D) {
+}  // namespace
+int m6_bt_alloc(mom6cu_ctx* c, BtDevice& D) {
   auto pl = [&](const char* n) { return c->plane2(std::string("bt.") + n); };
   for (int s = 0; s < 2; ++s) {
     D.eta[s] = pl(s ? "eta1" : "eta0"); D.ubt[s] = pl(s ? "ubt1" : "ubt0"); D.vbt[s] = pl(s ? "vbt1" : "vbt0");
@@ -305,6 +284,7 @@ int bt_alloc(mom6cu_ctx* c, BtDevice& D) {
   return 0;
 }
 
+namespace {
 int bt_check(mom6cu_ctx* c, const mom6cu_bt_timeloop_args* a) {
   if (!a) return c->fail(MOM6CU_ERR_BAD_ARG, "btstep_timeloop: null args");
   if (a->nstep + a->nfilter <= 0)
@@ -364,7 +344,8 @@ int m6_bt_halo_exchange(mom6cu_ctx* c, double* eta, double* ubt, double* vbt);  
 namespace {
 
 // The substep loop proper: everything inside is device work on c->stream.
-int bt_run(mom6cu_ctx* c, BtDevice& D, const mom6cu_bt_timeloop_args* a, int* final_slot) {
+}  // namespace
+int m6_bt_run(mom6cu_ctx* c, BtDevice& D, const mom6cu_bt_timeloop_args* a, int* final_slot) {
   const mom6cu_domain& d = c->dom;
   const Geom& G = c->g;
   const int is = d.isc, ie = d.iec, js = d.jsc, je = d.jec;
@@ -422,6 +403,7 @@ int bt_run(mom6cu_ctx* c, BtDevice& D, const mom6cu_bt_timeloop_args* a, int* fi
   return 0;
 }
 
+namespace {
 int bt_download(mom6cu_ctx* c, BtDevice& D, const mom6cu_bt_timeloop_args* a, int slot) {
   int rc;
   BtPlanes& P = D.P;
@@ -450,7 +432,7 @@ extern "C" int mom6cu_btstep_timeloop_resident(mom6cu_ctx* c, const mom6cu_bt_ti
   int rc = bt_check(c, a);
   if (rc) return rc;
   BtDevice D;
-  if ((rc = bt_alloc(c, D))) return rc;
+  if ((rc = m6_bt_alloc(c, D))) return rc;
   if ((rc = bt_upload(c, D, a))) return rc;
   int slot = 0;
   // keep pristine copies of everything the loop modifies so every repetition starts from the
@@ -470,7 +452,7 @@ extern "C" int mom6cu_btstep_timeloop_resident(mom6cu_ctx* c, const mom6cu_bt_ti
       for (int m = 0; m < 5; ++m)
         M6_CUDA(c, cudaMemcpyAsync(srcs[m], keep + (size_t)m * c->g.plane, pb, cudaMemcpyDeviceToDevice, c->stream));
     M6_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    if ((rc = bt_run(c, D, a, &slot))) return rc;
+    if ((rc = m6_bt_run(c, D, a, &slot))) return rc;
     M6_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     M6_CUDA(c, cudaEventSynchronize(c->ev1));
     float ms1 = 0.f;

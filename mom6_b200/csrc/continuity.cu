@@ -408,28 +408,25 @@ struct CellSt { double hR0, hL0, c30, hL1, hR1, c31; };
 __device__ __forceinline__ void flux_from_state(const ContCS& CS, const CellSt& S, double face, double un, double visc_rem,
                                                 double dt, double cfl0, double cfl1, double& uh, double& duhdu,
                                                 double& h_avg, double& h_marg) {
-  double CFL;
-  if (un > 0.0) {
-    if (CS.vol_CFL) CFL = (un * dt) * cfl0; else CFL = un * dt * cfl0;
-    h_avg = S.hR0 + CFL * (0.5 * (S.hL0 - S.hR0) + S.c30 * (CFL - 1.5));
-    uh = face * un * h_avg;
-    h_marg = S.hR0 + CFL * ((S.hL0 - S.hR0) + 3.0 * S.c30 * (CFL - 1.0));
-  } else if (un < 0.0) {
-    if (CS.vol_CFL) CFL = (-un * dt) * cfl1; else CFL = -un * dt * cfl1;
-    h_avg = S.hL1 + CFL * (0.5 * (S.hR1 - S.hL1) + S.c31 * (CFL - 1.5));
-    uh = face * un * h_avg;
-    h_marg = S.hL1 + CFL * ((S.hR1 - S.hL1) + 3.0 * S.c31 * (CFL - 1.0));
-  } else {
-    uh = 0.0;
-    h_marg = 0.5 * (S.hL1 + S.hR0);
-    h_avg = h_marg;
-  }
+  // zonal_flux_layer :935-956 without divergent branches: the upwind cell's (edge toward the face, far edge,
+  // curvature) are selected by the sign of un; -un*dt*cfl1 == |un|*dt*cfl1 bit for bit when un < 0.
+  const bool pos = un > 0.0;
+  const double a = pos ? S.hR0 : S.hL1, b = pos ? S.hL0 : S.hR1, c3 = pos ? S.c30 : S.c31;
+  const double CFL = fabs(un) * dt * (pos ? cfl0 : cfl1);
+  const double ha = a + CFL * (0.5 * (b - a) + c3 * (CFL - 1.5));
+  const double hm = a + CFL * ((b - a) + 3.0 * c3 * (CFL - 1.0));
+  const bool zero = (un == 0.0);
+  const double hz = 0.5 * (S.hL1 + S.hR0);
+  h_avg = zero ? hz : ha;
+  h_marg = zero ? hz : hm;
+  uh = zero ? 0.0 : face * un * ha;
   duhdu = face * h_marg * visc_rem;
 }
 
 template <bool Z, int NF, int NS, int KPT>
 __global__ void __launch_bounds__(NF* NS, (KPT <= 5) ? 2 : 1)
 cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
+  static_assert(NS >= 10 && (NF % 16) == 0 && NF <= 32, "k-ordered sums use one warp per quantity (slices 0,2,..,8)");
   extern __shared__ double sm[];
   const int nz = A.nk;
   const int PL = nz * NF;
@@ -482,65 +479,65 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   }
   double du = 0.0;
   if (A.uhbt || set_BT) {  // uniform over the grid
-    __syncthreads();
-    // ---- k-ordered sums (:659-662) and the column maximum of visc_rem (:637-644)
-    if (s == 0) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
-    else if (s == 1) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
-    else if (s == 2) {
-      double t = 1.0;
-      if (use_visc_rem && CS.use_visc_rem_max) { t = 0.0; for (int k = 0; k < nz; ++k) t = fmax2(t, sVR[k * NF + f]); }
-      sR[2 * NF + f] = t;
-    }
-    __syncthreads();
-    const double uh_tot_0 = sR[f], duhdu_tot_0 = sR[NF + f], visc_rem_max = sR[2 * NF + f];
-    // ---- limits on du that keep the CFL number between -1 and 1 (:646-720)
+    // ---- per-face constants of the CFL limits (:646-655)
     double CFL_dt = CS.CFL_limit_adjust / dt;
     const double I_dt = 1.0 / dt;
     if (CS.aggress_adjust) CFL_dt = I_dt;
-    double I_vrm = 0.0;
-    if (visc_rem_max > 0.0) I_vrm = 1.0 / visc_rem_max;
     double dx_W, dx_E;
     if (CS.vol_CFL) {
       dx_W = ratio_max(__ldg(A.areaT + g), dy, 1000.0 * __ldg(A.dxT + g));
       dx_E = ratio_max(__ldg(A.areaT + g + sd), dy, 1000.0 * __ldg(A.dxT + g + sd));
     } else { dx_W = __ldg(A.dxT + g); dx_E = __ldg(A.dxT + g + sd); }
     const double maskC = __ldg(A.maskC + g);
-    __syncthreads();  // sR is about to be reused
-    if (s == 0) {
-      double du_max_CFL = 2.0 * (CFL_dt * dx_W) * I_vrm;
-      for (int k = 0; k < nz; ++k) {
-        const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
-        if (use_visc_rem) {
-          if (CS.aggress_adjust) {
-            const double du_lim = 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd)));
-            if (du_max_CFL * vr > du_lim) du_max_CFL = du_lim / vr;
-          } else if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = (dx_W * CFL_dt - uk) / vr;
-        } else {
-          if (CS.aggress_adjust)
-            du_max_CFL = fmin2(du_max_CFL, 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd))));
-          else du_max_CFL = fmin2(du_max_CFL, dx_W * CFL_dt - uk);
+    __syncthreads();
+    // ---- one round of k-ordered work, one warp per quantity (s = 2*warp for lanes 0..NF-1):
+    //      uh_tot_0, duhdu_tot_0 (:659-662); visc_rem_max (:637-644) followed by du_max_CFL / du_min_CFL (:646-720)
+    if (s == 0) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
+    else if (s == 2) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
+    else if (s == 4 || s == 6) {
+      double vrm = 1.0;
+      if (use_visc_rem && CS.use_visc_rem_max) { vrm = 0.0; for (int k = 0; k < nz; ++k) vrm = fmax2(vrm, sVR[k * NF + f]); }
+      double I_vrm = 0.0;
+      if (vrm > 0.0) I_vrm = 1.0 / vrm;
+      if (s == 4) {
+        sR[2 * NF + f] = vrm;
+        double du_max_CFL = 2.0 * (CFL_dt * dx_W) * I_vrm;
+        for (int k = 0; k < nz; ++k) {
+          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+          if (use_visc_rem) {
+            if (CS.aggress_adjust) {
+              const double du_lim = 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd)));
+              if (du_max_CFL * vr > du_lim) du_max_CFL = du_lim / vr;
+            } else if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = (dx_W * CFL_dt - uk) / vr;
+          } else {
+            if (CS.aggress_adjust)
+              du_max_CFL = fmin2(du_max_CFL, 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd))));
+            else du_max_CFL = fmin2(du_max_CFL, dx_W * CFL_dt - uk);
+          }
         }
-      }
-      sR[f] = fmax2(du_max_CFL, 0.0);
-    } else if (s == 1) {
-      double du_min_CFL = -2.0 * (CFL_dt * dx_E) * I_vrm;
-      for (int k = 0; k < nz; ++k) {
-        const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
-        if (use_visc_rem) {
-          if (CS.aggress_adjust) {
-            const double du_lim = 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd)));
-            if (du_min_CFL * vr < du_lim) du_min_CFL = du_lim / vr;
-          } else if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = -(dx_E * CFL_dt + uk) / vr;
-        } else {
-          if (CS.aggress_adjust)
-            du_min_CFL = fmax2(du_min_CFL, 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd))));
-          else du_min_CFL = fmax2(du_min_CFL, -(dx_E * CFL_dt + uk));
+        sR[3 * NF + f] = fmax2(du_max_CFL, 0.0);
+      } else {
+        double du_min_CFL = -2.0 * (CFL_dt * dx_E) * I_vrm;
+        for (int k = 0; k < nz; ++k) {
+          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+          if (use_visc_rem) {
+            if (CS.aggress_adjust) {
+              const double du_lim = 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd)));
+              if (du_min_CFL * vr < du_lim) du_min_CFL = du_lim / vr;
+            } else if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = -(dx_E * CFL_dt + uk) / vr;
+          } else {
+            if (CS.aggress_adjust)
+              du_min_CFL = fmax2(du_min_CFL, 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd))));
+            else du_min_CFL = fmax2(du_min_CFL, -(dx_E * CFL_dt + uk));
+          }
         }
+        sR[4 * NF + f] = fmin2(du_min_CFL, 0.0);
       }
-      sR[NF + f] = fmin2(du_min_CFL, 0.0);
     }
     __syncthreads();
-    const double du_max_CFL = sR[f], du_min_CFL = sR[NF + f];
+    const double uh_tot_0 = sR[f], duhdu_tot_0 = sR[NF + f], visc_rem_max = sR[2 * NF + f];
+    const double du_max_CFL = sR[3 * NF + f], du_min_CFL = sR[4 * NF + f];
+    __syncthreads();  // sR is reused by the iterations below
     const double IareaT_min = fmin2(IareaT0, IareaT1);
 
     // zonal_flux_adjust :1093-1242, distributed.  pass 0: with uhbt, storing uh (:737); pass 1: for BT_cont (:1318)
@@ -612,7 +609,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
             __syncthreads();
             if (do_I) {
               if (s == 0) { double t = -uhbt; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
-              else if (s == 1) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
+              else if (s == 2) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
             }
             __syncthreads();
             if (do_I) {
@@ -641,7 +638,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
             if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = -(uk + du_CFL * vr) / visc_rem_lim;
         }
         sR[f] = duR;
-      } else if (s == 1) {
+      } else if (s == 2) {
         double duL = fmax2(0.0, du0 + du_CFL);
         for (int k = 0; k < nz; ++k) {
           const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
@@ -670,7 +667,10 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         }
       }
       __syncthreads();
-      if (s < 5) { double t = 0.0; const double* p = sP + s * PL + f; for (int k = 0; k < nz; ++k) t = t + p[k * NF]; sR[s * NF + f] = t; }
+      if ((s & 1) == 0 && s < 10) {
+        const int qn = s >> 1;
+        double t = 0.0; const double* p = sP + qn * PL + f; for (int k = 0; k < nz; ++k) t = t + p[k * NF]; sR[qn * NF + f] = t;
+      }
       __syncthreads();
       if (s == 0 && valid) {
         const double FAmt_0 = sR[f], FAmt_L = sR[NF + f], FAmt_R = sR[2 * NF + f], uhtot_L = sR[3 * NF + f], uhtot_R = sR[4 * NF + f];

@@ -43,7 +43,23 @@ struct HorViscDev {
   double *diffu, *diffv;
 };
 
+// btstep dummy arguments (MOM_barotropic.F90:455-529); null = absent / not associated
+struct BtstepDev {
+  double dt;
+  const double *U_in, *V_in, *eta_in, *bc_accel_u, *bc_accel_v, *taux, *tauy, *pbce, *eta_PF_in, *U_Cor, *V_Cor;
+  const double *visc_rem_u, *visc_rem_v, *taux_bot, *tauy_bot, *uh0, *vh0, *u_uh0, *v_vh0;
+  double *accel_layer_u, *accel_layer_v, *eta_out, *uhbtav, *vhbtav, *etaav;
+  int have_BT_cont;
+  const double *FA_u_EE, *FA_u_E0, *FA_u_W0, *FA_u_WW, *uBT_WW, *uBT_EE;
+  const double *FA_v_NN, *FA_v_N0, *FA_v_S0, *FA_v_SS, *vBT_SS, *vBT_NN;
+};
+
 struct mom6cu_ctx;
+// CS holds device pointers (resident planes) for every array member
+int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev& D);
+int m6_btcalc_run(mom6cu_ctx* c, const double* h, const double* h_u, const double* h_v, const double* bathyT, int hvel_scheme,
+                  int may_use_default, double* frhatu, double* frhatv);
+int m6_bt_mass_source_run(mom6cu_ctx* c, const double* h, const double* eta, int set_cor, double* eta_cor);
 int m6_hor_visc_run(mom6cu_ctx* c, const HorViscDev& D);
 int m6_coradcalc_run(mom6cu_ctx* c, const CorAdDev& D);
 int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D);

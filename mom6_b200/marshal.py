@@ -2,7 +2,7 @@
 import ctypes as C
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
-                   HorViscCS, HorViscArgs, fill_struct)
+                   HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, fill_struct)
 
 
 def _scalars(struct, d):
@@ -54,3 +54,19 @@ def hor_visc_cs(d, keep):
 
 def hor_visc_args(a, keep):
     return fill_struct(HorViscArgs(), a, keep)
+
+
+def barotropic_cs(d, keep):
+    return fill_struct(BarotropicCS(), d, keep)
+
+
+def btstep_args(a, keep):
+    st = fill_struct(BtstepArgs(), a, keep)
+    bs = fill_struct(BTCont(), a["BT_cont"], keep)
+    keep.append(bs)
+    st.BT_cont = C.pointer(bs)
+    return st
+
+
+def btcalc_args(a, keep):
+    return fill_struct(BtcalcArgs(), a, keep)

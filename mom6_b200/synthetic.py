@@ -631,3 +631,95 @@ def hor_visc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True,
         hv = fidx.new(dom, "v", nk=nk); hv.a[:, 1:-1, :] = np.minimum(h[:, :-1, :], h[:, 1:, :]); hv.a[:, 0, :] = h[:, 0, :]; hv.a[:, -1, :] = h[:, -1, :]
         a["hu_cont"], a["hv_cont"] = hu.a, hv.a
     return dom, grid, gv, cs, a
+
+
+def btstep_inputs(ni, nj, nk, halo=4, whalo=6, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, dt=900.0,
+                  first_direction=0, with_uh0=True, with_etaav=True, with_bot=False, **cs_over):
+    """Everything a btstep call needs (MOM_barotropic.F90:455): returns dom, grid, vgrid, cs, args.
+    The barotropic_CS members (wide-halo copies of the metrics, linearised Coriolis thicknesses, frhatu/v ...) are
+    built the way barotropic_init (:5301) / btcalc build them."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, whalo=whalo, cyclic_x=cyclic_x, cyclic_y=cyclic_y, first_direction=first_direction)
+    domw = make_domain(ni, nj, nk=nk, halo=whalo, whalo=whalo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gw = make_grid(domw, land_blocks, seed)   # the same metrics on the wide-halo memory domain
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed, vel=0.2, thin_layers=False)
+    r = rng(seed + 303)
+    h = st["h"]
+    D = grid["bathyT"]
+    # btcalc-like weights (arithmetic mean thickness fractions)
+    hu = np.zeros_like(st["u"]); hu[:, :, 1:-1] = 0.5 * (h[:, :, :-1] + h[:, :, 1:])
+    hv = np.zeros_like(st["v"]); hv[:, 1:-1, :] = 0.5 * (h[:, :-1, :] + h[:, 1:, :])
+    frhatu = hu * (grid["mask2dCu"] / (hu.sum(axis=0) + 1e-30))[None]
+    frhatv = hv * (grid["mask2dCv"] / (hv.sum(axis=0) + 1e-30))[None]
+    Du = np.zeros_like(grid["mask2dCu"]); Du[:, 1:-1] = 0.5 * (D[:, :-1] + D[:, 1:])
+    Dv = np.zeros_like(grid["mask2dCv"]); Dv[1:-1, :] = 0.5 * (D[:-1, :] + D[1:, :])
+    with np.errstate(divide="ignore"):
+        IDatu = np.where(Du * grid["mask2dCu"] > 0, 1.0 / np.where(Du > 0, Du, 1.0), 0.0)
+        IDatv = np.where(Dv * grid["mask2dCv"] > 0, 1.0 / np.where(Dv > 0, Dv, 1.0), 0.0)
+    Dw = gw["bathyT"]
+    Duw = np.zeros_like(gw["mask2dCu"]); Duw[:, 1:-1] = 0.5 * (Dw[:, :-1] + Dw[:, 1:])
+    Dvw = np.zeros_like(gw["mask2dCv"]); Dvw[1:-1, :] = 0.5 * (Dw[:-1, :] + Dw[1:, :])
+    aw = gw["areaT"]
+    qD = np.zeros_like(gw["CoriolisBu"])
+    den = ((aw[:-1, :-1] * Dw[:-1, :-1] + aw[1:, 1:] * Dw[1:, 1:]) + (aw[:-1, 1:] * Dw[:-1, 1:] + aw[1:, :-1] * Dw[1:, :-1]))
+    qD[1:-1, 1:-1] = 0.25 * gw["CoriolisBu"][1:-1, 1:-1] * ((aw[:-1, :-1] + aw[1:, 1:]) + (aw[:-1, 1:] + aw[1:, :-1])) / np.maximum(den, 1e-30)
+    cs = dict(Sadourny=1, BT_project_velocity=0, strong_drag=0, bound_BT_corr=0, BT_cont_bounds=1, wt_uv_bug=0, visc_rem_u_uh0=0,
+              adjust_BT_cont=0, use_wide_halos=1, min_stencil=0, use_old_coriolis_bracket_bug=0, unsupported=0,
+              dtbt=0.9 * 0.5 * 2.5e4 / np.sqrt(9.8 * 4000.0 * 2), bebt=0.1, vel_underflow=1e-30, maxCFL_BT_cont=0.25, G_extra=0.0,
+              dt_bt_filter=-0.25)
+    cs.update(cs_over)
+    cs.update(IareaT=gw["IareaT"] * gw["mask2dT"], IareaT_OBCmask=gw["IareaT"] * gw["mask2dT"], bathyT=Dw, IdxCu=gw["IdxCu"],
+              IdyCv=gw["IdyCv"], q_D=qD, D_u_Cor=Duw * gw["mask2dCu"], D_v_Cor=Dvw * gw["mask2dCv"],
+              ua_polarity=np.ones_like(Dw), va_polarity=np.ones_like(Dw), OBCmask_u=np.ones_like(Duw), OBCmask_v=np.ones_like(Dvw),
+              frhatu=frhatu, frhatv=frhatv, eta_cor=1e-3 * r.uniform(-1, 1, size=D.shape) * grid["mask2dT"],
+              eta_cor_bound=np.full_like(D, 1e-7), IDatu=IDatu, IDatv=IDatv,
+              ubtav=fidx.new(dom, "u").a, vbtav=fidx.new(dom, "v").a)
+    cs = {k: (np.ascontiguousarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in cs.items()}
+
+    def U3(stg, scale, mask):
+        f = fidx.new(dom, stg, nk=nk)
+        f.s(dom.isc - 1, dom.iec, dom.jsc - 1, dom.jec)[...] = scale * r.uniform(-1.0, 1.0, size=(nk, nj + 1, ni + 1))
+        f.a *= mask[None]
+        if dom.cyclic_x and stg == "u":
+            f.s(dom.isc - 1, dom.isc - 1, f.jlo, f.jhi)[...] = f.s(dom.iec, dom.iec, f.jlo, f.jhi)
+        if dom.cyclic_y and stg == "v":
+            f.s(f.ilo, f.ihi, dom.jsc - 1, dom.jsc - 1)[...] = f.s(f.ilo, f.ihi, dom.jec, dom.jec)
+        return fidx.fill_halo(dom, f, stg).a
+
+    def U2(stg, scale, mask):
+        f = fidx.new(dom, stg)
+        f.s(dom.isc - 1, dom.iec, dom.jsc - 1, dom.jec)[...] = scale * r.uniform(-1.0, 1.0, size=(nj + 1, ni + 1))
+        f.a *= mask
+        if dom.cyclic_x and stg == "u":
+            f.s(dom.isc - 1, dom.isc - 1, f.jlo, f.jhi)[...] = f.s(dom.iec, dom.iec, f.jlo, f.jhi)
+        if dom.cyclic_y and stg == "v":
+            f.s(f.ilo, f.ihi, dom.jsc - 1, dom.jsc - 1)[...] = f.s(f.ilo, f.ihi, dom.jec, dom.jec)
+        return fidx.fill_halo(dom, f, stg).a
+    mU, mV, mT = grid["mask2dCu"], grid["mask2dCv"], grid["mask2dT"]
+    eta_in = U2("h", 0.1, mT)
+    pb = fidx.new(dom, "h", nk=nk)
+    pb.a[...] = (9.8 * (1.0 + 1e-3 * np.arange(nk) / nk))[:, None, None] * (1.0 + 1e-3 * U3("h", 1.0, np.ones_like(mT)))
+    a = dict(U_in=st["u"], V_in=st["v"], eta_in=eta_in, dt=dt, bc_accel_u=U3("u", 1e-5, mU), bc_accel_v=U3("v", 1e-5, mV),
+             taux=U2("u", 0.1, mU), tauy=U2("v", 0.1, mV), pbce=pb.a, eta_PF_in=eta_in + U2("h", 0.01, mT),
+             U_Cor=st["u"] + U3("u", 0.01, mU), V_Cor=st["v"] + U3("v", 0.01, mV),
+             accel_layer_u=fidx.new(dom, "u", nk=nk).a, accel_layer_v=fidx.new(dom, "v", nk=nk).a,
+             eta_out=fidx.new(dom, "h").a, uhbtav=fidx.new(dom, "u").a, vhbtav=fidx.new(dom, "v").a,
+             visc_rem_u=st["visc_rem_u"], visc_rem_v=st["visc_rem_v"])
+    # a BT_cont like the one continuity leaves behind (face areas ~ dy*D with a 2% flare, |uBT| ~ 0.03)
+    FAu = grid["dy_Cu"] * Du * (1.0 + 0.01 * U2("u", 1.0, np.ones_like(mU)))
+    FAv = grid["dx_Cv"] * Dv * (1.0 + 0.01 * U2("v", 1.0, np.ones_like(mV)))
+    a["BT_cont"] = dict(FA_u_EE=1.02 * FAu, FA_u_E0=FAu.copy(), FA_u_W0=FAu.copy(), FA_u_WW=1.03 * FAu,
+                        uBT_WW=np.where(FAu > 0, 0.03, 0.0), uBT_EE=np.where(FAu > 0, -0.025, 0.0),
+                        FA_v_NN=1.02 * FAv, FA_v_N0=FAv.copy(), FA_v_S0=FAv.copy(), FA_v_SS=1.03 * FAv,
+                        vBT_SS=np.where(FAv > 0, 0.03, 0.0), vBT_NN=np.where(FAv > 0, -0.025, 0.0), h_u=None, h_v=None)
+    if with_uh0:
+        a["u_uh0"] = st["u"] + U3("u", 0.02, mU); a["v_vh0"] = st["v"] + U3("v", 0.02, mV)
+        a["uh0"] = a["u_uh0"] * hu * grid["dy_Cu"][None]; a["vh0"] = a["v_vh0"] * hv * grid["dx_Cv"][None]
+    if with_etaav:
+        a["etaav"] = fidx.new(dom, "h").a
+    if with_bot:
+        a["taux_bot"] = U2("u", 0.01, mU); a["tauy_bot"] = U2("v", 0.01, mV)
+    a = {k: (np.ascontiguousarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+    a["BT_cont"] = {k: (np.ascontiguousarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in a["BT_cont"].items()}
+    return dom, grid, gv, cs, a

@@ -46,6 +46,14 @@ int oracle_coradcalc(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6c
 int oracle_horizontal_viscosity(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
                                 const mom6cu_hor_visc_cs* CS, const mom6cu_hor_visc_args* a, int nthreads);
 
+/* btstep, MOM_barotropic.F90:455-2172 (frozen option set, single tile); btcalc :4360; bt_mass_source :5243 */
+int oracle_btstep(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
+                  const mom6cu_barotropic_cs* CS, const mom6cu_btstep_args* a, int nthreads);
+int oracle_btcalc(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
+                  const mom6cu_btcalc_args* a, int nthreads);
+int oracle_bt_mass_source(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const double* h,
+                          const double* eta, int set_cor, double* eta_cor);
+
 #ifdef __cplusplus
 }
 #endif

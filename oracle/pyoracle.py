@@ -83,3 +83,46 @@ def horizontal_viscosity(dom, grid, gv, cs, args, nthreads=1):
     if rc != 0:
         raise RuntimeError(f"oracle_horizontal_viscosity rc={rc}")
     return rc
+
+
+def btstep(dom, grid, gv, cs, args, nthreads=1):
+    """oracle_btstep: btstep, MOM_barotropic.F90:455-2172 (frozen option set) on host arrays."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    v = marshal.vgrid(gv)
+    c = marshal.barotropic_cs(cs, keep)
+    a = marshal.btstep_args(args, keep)
+    lib.oracle_btstep.argtypes = [C.c_void_p] * 5 + [C.c_int]
+    rc = lib.oracle_btstep(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(a), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_btstep rc={rc}")
+    return rc
+
+
+def btcalc(dom, grid, gv, args, nthreads=1):
+    """oracle_btcalc: btcalc, MOM_barotropic.F90:4360-4605."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    v = marshal.vgrid(gv)
+    a = marshal.btcalc_args(args, keep)
+    lib.oracle_btcalc.argtypes = [C.c_void_p] * 4 + [C.c_int]
+    rc = lib.oracle_btcalc(C.byref(dom), C.byref(g), C.byref(v), C.byref(a), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_btcalc rc={rc}")
+    return rc
+
+
+def bt_mass_source(dom, grid, gv, h, eta, set_cor, eta_cor):
+    """oracle_bt_mass_source: MOM_barotropic.F90:5243-5296."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    v = marshal.vgrid(gv)
+    lib.oracle_bt_mass_source.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    return lib.oracle_bt_mass_source(C.byref(dom), C.byref(g), C.byref(v), h.ctypes.data, eta.ctypes.data, int(set_cor),
+                                     eta_cor.ctypes.data)
