@@ -3,14 +3,16 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A "step" is one baroclinic dynamics step of the OM4_025-shaped synthetic configuration
-(1440 x 1080 x 75, BASELINE.json configs[3]) through the stages implemented so far (listed in
-config.stages); value = cell-updates/s = ni*nj*nk*K / t, t = device time (CUDA events on the
-launching stream) with every input already resident in HBM.  e2e = the same metric through the
-reference-facing C ABI with HOST arrays (host->device and device->host copies inside the timed
-region).  roofline = the dominant kernel (fused barotropic substep) against the measured HBM peak.
-cpu_baseline / --impl reference = the oracle restatement of the reference CPU path (the Fortran
-reference cannot be built: no Fortran/MPI/netCDF/FMS in the image) on the host cores.
+A "step" is one baroclinic dynamics step (step_MOM_dyn_split_RK2, MOM_dynamics_split_RK2.F90:294-1205) of the
+OM4_025-shaped synthetic configuration (1440 x 1080 x 75, BASELINE.json configs[3]) through every stage implemented
+so far, in the call counts of one reference step (config.stages; the stages of the step not yet on the device are
+listed in config.stages_missing -- the number is a lower bound on the work of a full step, not a full step).
+value = cell-updates/s = ni*nj*nk*K / t with every field resident in HBM (mom6cu_plane_*), t = device time of the K
+steps (CUDA events on the launching stream, per stage, summed) -- ms_per_step_wall is the host wall clock of the same
+loop.  e2e = the same step through the C ABI with HOST arrays (staging copies inside the timed region).
+roofline = the dominant kernel group against the measured HBM peak.  cpu_baseline / --impl reference = the oracle
+restatement of the reference CPU path with OpenMP on the host cores, on a bounded sample tile (the Fortran reference
+cannot be built: no Fortran/MPI/netCDF/FMS in the image).
 """
 import argparse
 import json
@@ -26,10 +28,15 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 NI, NJ, NK = 1440, 1080, 75
-NSTEP, NFILTER = 60, 8          # barotropic substeps per btstep call
-BT_CALLS_PER_STEP = 2           # predictor + corrector (MOM_dynamics_split_RK2.F90:673,:939)
+SAMPLE = (360, 270)             # CPU-baseline sample tile (1/16 of the horizontal domain, all 75 layers)
 BT_BYTES_PER_PT_SUBSTEP = 552   # 69 fp64 operands on the BT_cont path
-STAGES = ["btstep_timeloop x2 (predictor+corrector barotropic subcycling, 68 substeps each)"]
+# stage -> (calls per baroclinic step [MOM_dynamics_split_RK2.F90 line], algorithmic bytes per cell per call [SURVEY 8d])
+STEP = [("continuity", 3, 96), ("btcalc", 1, 32), ("bt_mass_source", 2, 8), ("btstep", 2, 136), ("coradcalc", 2, 56),
+        ("horizontal_viscosity", 1, 40)]
+STAGES = ["continuity_PPM x3 (:646,:781,:1043)", "btcalc x1 (:650)", "bt_mass_source x2 (:629,:821)",
+          "btstep x2 incl. the 68-substep barotropic loop (:673,:939)", "CorAdCalc x2 (:895,:1090)", "horizontal_viscosity x1 (:886)"]
+MISSING = ["PressureForce_FV x1 (:503)", "vertvisc_coef/vertvisc/vertvisc_remnant x3 (:609,:754,:1003)", "set_viscous_ML (:602)",
+           "elementwise glue up/vp/u/v/h_av/uhtr (:565-1082)", "inter-stage 3-D halo updates (:616-1056)"]
 
 
 def peaks():
@@ -85,40 +92,99 @@ def tile_of(rank, n):
     return npi, npj, rank % npi, rank // npi
 
 
-def make_inputs(ni, nj):
+STAGGER = dict(u="u", v="v", hin="h", h="h", uh="u", vh="v", visc_rem_u="u", visc_rem_v="v", uhbt="u", vhbt="v", u_cor="u", v_cor="v",
+               CAu="u", CAv="v", diffu="u", diffv="v", U_in="u", V_in="v", eta_in="h", bc_accel_u="u", bc_accel_v="v", taux="u",
+               tauy="v", pbce="h", eta_PF_in="h", U_Cor="u", V_Cor="v", accel_layer_u="u", accel_layer_v="v", eta_out="h",
+               uhbtav="u", vhbtav="v", uh0="u", vh0="v", u_uh0="u", v_vh0="v", etaav="h", h_u="u", h_v="v", frhatu="u",
+               frhatv="v", bathyT="h", eta="h", eta_cor="h", FA_u_EE="u", FA_u_E0="u", FA_u_W0="u", FA_u_WW="u", uBT_WW="u",
+               uBT_EE="u", FA_v_NN="v", FA_v_N0="v", FA_v_S0="v", FA_v_SS="v", vBT_SS="v", vBT_NN="v", IDatu="u", IDatv="v",
+               eta_cor_bound="h", ubtav="u", vbtav="v", IareaT="h", IareaT_OBCmask="h", IdxCu="u", IdyCv="v", q_D="q",
+               D_u_Cor="u", D_v_Cor="v", ua_polarity="h", va_polarity="h", OBCmask_u="u", OBCmask_v="v")
+WIDE = {"IareaT", "IareaT_OBCmask", "IdxCu", "IdyCv", "q_D", "D_u_Cor", "D_v_Cor", "ua_polarity", "va_polarity", "OBCmask_u", "OBCmask_v"}
+
+
+def make_resident(ctx, stages, nk):
+    """Upload every array argument of every stage once; the same host array maps to the same plane."""
+    cache = {}
+
+    def res(name, arr, wide=False):
+        if not isinstance(arr, np.ndarray) or name.startswith("_"):
+            return arr
+        key = id(arr)
+        if key not in cache:
+            n3 = nk if arr.ndim == 3 else 1
+            cache[key] = ctx.plane(f"{name}.{len(cache)}", arr, STAGGER[name], wide, n3)
+        return cache[key]
+
+    out = {}
+    for st, (cs, a) in stages.items():
+        ra = {k: ({kk: res(kk, vv) for kk, vv in v.items()} if isinstance(v, dict) else res(k, v)) for k, v in a.items()}
+        rcs = cs
+        if st == "btstep":
+            rcs = {k: res(k, v, k in WIDE or k == "bathyT") for k, v in cs.items()}
+        out[st] = (rcs, ra)
+    return out, sum(v.nk for v in cache.values())
+
+
+def run_step(ctx, stages, times=None):
+    """One baroclinic step: the implemented stages in the reference's call counts."""
+    for name, calls, _ in STEP:
+        cs, a = stages[name]
+        for _ in range(calls):
+            if name == "btstep":
+                ctx.btstep(cs, a)
+            elif name == "bt_mass_source":
+                ctx.bt_mass_source(a["h"], a["eta"], 1, a["eta_cor"])
+            else:
+                getattr(ctx, name)(a)
+            if times is not None:
+                times[name] = times.get(name, 0.0) + ctx.last_kernel_ms
+
+
+def oracle_step(orc, dom, grid, gv, stages, cores):
+    for name, calls, _ in STEP:
+        cs, a = stages[name]
+        for _ in range(calls):
+            if name == "continuity":
+                orc.continuity(dom, grid, gv, cs, a, nthreads=cores)
+            elif name == "coradcalc":
+                orc.coradcalc(dom, grid, gv, cs, a, nthreads=cores)
+            elif name == "horizontal_viscosity":
+                orc.horizontal_viscosity(dom, grid, gv, cs, a, nthreads=cores)
+            elif name == "btstep":
+                orc.btstep(dom, grid, gv, cs, a, nthreads=cores)
+            elif name == "btcalc":
+                orc.btcalc(dom, grid, gv, a, nthreads=cores)
+            elif name == "bt_mass_source":
+                orc.bt_mass_source(dom, grid, gv, a["h"], a["eta"], 1, a["eta_cor"])
+
+
+def cpu_reference(steps, warmup):
+    """The oracle restatement of the reference CPU path on a bounded sample tile, all host threads."""
+    import oracle
     from mom6_b200 import synthetic
-    return synthetic.bt_timeloop_inputs(ni, nj, whalo=10, halo=4, nstep=NSTEP, nfilter=NFILTER, land_blocks=40)
-
-
-def synthetic_bt(ni, nj):
-    return make_inputs(ni, nj)
+    cores = os.cpu_count() or 1
+    ni, nj = SAMPLE
+    dom, grid, gv, stages = synthetic.step_inputs(ni, nj, NK, whalo=10, land_blocks=10)
+    for _ in range(warmup):
+        oracle_step(oracle, dom, grid, gv, stages, cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(oracle, dom, grid, gv, stages, cores)
+    t = time.perf_counter() - t0
+    return ni * nj * NK * steps / t, t, cores, f"{steps} step(s) of the same stage list on a {ni}x{nj}x{NK} tile (1/16 of the workload)"
 
 
 def run_reference(args):
-    """--impl reference: the oracle restatement of the reference CPU path, all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU implementation of the path (oracle port; see module docstring)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    import oracle
-    cores = os.cpu_count() or 1
-    dom, a = make_inputs(NI, NJ)
-    times = []
-    for s in range(args.warmup + args.steps):
-        b = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
-        t0 = time.perf_counter()
-        for _ in range(BT_CALLS_PER_STEP):
-            oracle.btstep_timeloop(dom, b, nthreads=cores)
-        t1 = time.perf_counter()
-        if s >= args.warmup:
-            times.append(t1 - t0)
-    t = sum(times)
-    val = NI * NJ * NK * args.steps / t
-    line = {"impl": "reference", "metric": "cell-updates/sec", "value": val, "unit": "cell-updates/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"OM4_025-shaped {NI}x{NJ}x{NK} split-RK2 dynamics step", "stages": STAGES},
-            "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} full steps of the same workload (oracle C++ restatement, OpenMP)"},
+    val, t, cores, sample = cpu_reference(args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "cell-updates/sec", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"OM4_025-shaped {NI}x{NJ}x{NK} split-RK2 dynamics step", "stages": STAGES, "stages_missing": MISSING},
+            "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -127,10 +193,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-array leg")
+    ap.add_argument("--size", default=None, help="ni,nj override (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -145,50 +213,64 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mom6_b200 import synthetic
     from mom6_b200.api import Context
 
-    # strong scaling: the global 1440x1080 domain is split into npi x npj tiles (one per GPU)
+    gni, gnj = (NI, NJ) if not args.size else tuple(int(x) for x in args.size.split(","))
+    # strong scaling: the global domain is split into npi x npj tiles (one per GPU)
     npi, npj, pi, pj = tile_of(rank, world)
-    ni, nj = NI // npi, NJ // npj
-    dom, a = make_inputs(ni, nj)
+    ni, nj = gni // npi, gnj // npj
+    dom, grid, gv, stages = synthetic.step_inputs(ni, nj, NK, whalo=10, land_blocks=40, seed=synthetic.SEED + rank)
     if world > 1:
         dom.npi, dom.npj, dom.pi, dom.pj = npi, npj, pi, pj
     ctx = Context(dom, local)
     if world > 1:
         ctx.attach_comm(dist)
+    ctx.set_grid(grid); ctx.set_vgrid(gv)
+    ctx.set_cs_continuity(stages["continuity"][0]); ctx.set_cs_coriolisadv(stages["coradcalc"][0])
+    ctx.set_cs_hor_visc(stages["horizontal_viscosity"][0])
+    resident, nplanes = make_resident(ctx, stages, NK)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: W warm-up then exactly K steps
-    n0 = ctx.launches
-    ctx.btstep_timeloop(a, reps=max(1, args.warmup * BT_CALLS_PER_STEP), download=False)
+    # ---- device-resident timing: W warm-up steps, then exactly K steps
+    for _ in range(args.warmup):
+        run_step(ctx, resident)
     barrier()
     n1 = ctx.launches
+    times = {}
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
-        ctx.btstep_timeloop(a, reps=args.steps * BT_CALLS_PER_STEP, download=False)
+        for _ in range(args.steps):
+            run_step(ctx, resident, times)
         barrier()
         wall = time.perf_counter() - t0
-    dev_ms = ctx.total_kernel_ms
+    dev_ms = sum(times.values())
     launches = ctx.launches - n1
-    # ---- e2e: host arrays through the C ABI, copies inside the timed region
-    e2e_steps = max(1, min(args.steps, 3))
-    h2d = sum(v.nbytes for k, v in a.items() if isinstance(v, np.ndarray)) * BT_CALLS_PER_STEP
-    outs = ["eta", "ubt", "vbt", "u_accel_bt", "v_accel_bt", "eta_wtd", "eta_sum", "ubtav", "vbtav", "uhbtav", "vhbtav",
-            "ubt_wtd", "vbt_wtd"]
-    d2h = sum(a[k].nbytes for k in outs) * BT_CALLS_PER_STEP
-    ctx.btstep_timeloop({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()})
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps * BT_CALLS_PER_STEP):
-        ctx.btstep_timeloop(a)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    # ---- e2e: host arrays through the C ABI, staging copies inside the timed region
+    e2e_s, e2e_steps, h2d, d2h = None, 0, 0, 0
+    if not args.no_e2e:
+        e2e_steps = 1
+        OUT = {"continuity": ("h", "uh", "vh", "u_cor", "v_cor"), "coradcalc": ("CAu", "CAv"), "horizontal_viscosity": ("diffu", "diffv"),
+               "btstep": ("accel_layer_u", "accel_layer_v", "eta_out", "uhbtav", "vhbtav", "etaav"), "btcalc": ("frhatu", "frhatv"),
+               "bt_mass_source": ("eta_cor",)}
+        for name, calls, _ in STEP:
+            cs, a = stages[name]
+            arrs = [v for v in a.values() if isinstance(v, np.ndarray)] + [vv for v in a.values() if isinstance(v, dict) for vv in v.values() if isinstance(vv, np.ndarray)]
+            if name == "btstep":
+                arrs += [v for v in cs.values() if isinstance(v, np.ndarray)]
+            h2d += calls * sum(x.nbytes for x in arrs)
+            d2h += calls * sum(a[k].nbytes for k in OUT[name] if isinstance(a.get(k), np.ndarray))
+        barrier()
+        t0 = time.perf_counter()
+        run_step(ctx, stages)
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
-    tmax = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([dev_ms, e2e_s or 0.0, wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s, wall = [float(x) for x in tmax.cpu()]
@@ -197,46 +279,47 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    cells = NI * NJ * NK
+    cells = gni * gnj * NK
+    tile_cells = ni * nj * NK
     value = cells * args.steps / (dev_ms * 1e-3)
-    e2e_val = cells * e2e_steps / e2e_s
     peak, peak_src = peaks()
-    n_sub = (NSTEP + NFILTER) * BT_CALLS_PER_STEP * args.steps
-    k_ms = dev_ms / n_sub                     # average substep-kernel duration (events over the timed region)
-    alg_bytes = ni * nj * BT_BYTES_PER_PT_SUBSTEP
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    per_stage = {}
+    for name, calls, bpc in STEP:
+        ms = times[name] / (args.steps * calls)
+        per_stage[name] = {"calls_per_step": calls, "ms_per_call": ms, "algorithmic_B_per_cell": bpc,
+                           "achieved_GBps": tile_cells * bpc / (ms * 1e-3) / 1e9, "frac_of_peak": tile_cells * bpc / (ms * 1e-3) / 1e9 / peak}
+    dom_stage = max(per_stage, key=lambda k: per_stage[k]["ms_per_call"] * per_stage[k]["calls_per_step"])
+    ds = per_stage[dom_stage]
+    kernel_of = {"continuity": "cont_flux_tiled<zonal|meridional> + cont_convergence_kernel", "btstep": "bt_substep_kernel x68 + bt_col_kernel + bt_layer_accel_kernel",
+                 "coradcalc": "corad_kernel", "horizontal_viscosity": "hor_visc_kernel", "btcalc": "btcalc_kernel", "bt_mass_source": "bt_mass_source_kernel"}
     line = {"metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"OM4_025-shaped {NI}x{NJ}x{NK} split-RK2 dynamics step", "stages": STAGES,
-                       "tiles": f"{npi}x{npj}", "l2": "inputs larger than L2 (>= 0.7 GB of 2-D planes per substep sweep)"},
-            "e2e": {"value": e2e_val, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "wall_ms_per_step": 1e3 * wall / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "bt_substep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes},
-            "clocks": clk.summary()}
+            "config": {"workload": f"OM4_025-shaped {gni}x{gnj}x{NK} split-RK2 dynamics step", "stages": STAGES, "stages_missing": MISSING,
+                       "tiles": f"{npi}x{npj}", "resident_planes": nplanes,
+                       "l2": f"inputs larger than L2 ({nplanes * ni * nj * 8 / 1e9:.1f} GB of resident fields swept per step)"},
+            "e2e": None if e2e_s is None else {"value": cells * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
+                                               "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "ms_per_step_wall": 1e3 * wall / args.steps,
+            "roofline": {"bound": "hbm", "kernel": kernel_of[dom_stage], "stage": dom_stage, "achieved": ds["achieved_GBps"], "peak": peak,
+                         "unit": "GB/s", "frac": ds["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": tile_cells * ds["algorithmic_B_per_cell"],
+                         "note": "stage-level: algorithmic bytes of one stage call / CUDA-event time of its kernels"},
+            "per_stage": per_stage, "clocks": clk.summary()}
     # BASELINE.json configs[4]: btstep microbench, 4320x3240 subcycle sweep at 1 GPU
-    if world == 1:
-        domb, ab = synthetic_bt(4320, 3240)
+    if world == 1 and not args.size:
+        ctx.close()
+        domb, ab = synthetic.bt_timeloop_inputs(4320, 3240, whalo=10, halo=4, nstep=60, nfilter=8, land_blocks=40)
         ctxb = Context(domb, local)
         ctxb.btstep_timeloop(ab, reps=3, download=False)
         msb = ctxb.last_kernel_ms
-        gbs = 4320 * 3240 * (NSTEP + NFILTER) * BT_BYTES_PER_PT_SUBSTEP / (msb * 1e-3) / 1e9
-        line["btstep_microbench"] = {"grid": "4320x3240", "substeps": NSTEP + NFILTER, "ms_per_call": msb,
-                                     "achieved_GBps": gbs, "frac_of_peak": gbs / peak}
+        gbs = 4320 * 3240 * 68 * BT_BYTES_PER_PT_SUBSTEP / (msb * 1e-3) / 1e9
+        line["btstep_microbench"] = {"grid": "4320x3240", "substeps": 68, "ms_per_call": msb, "achieved_GBps": gbs, "frac_of_peak": gbs / peak,
+                                     "kernel": "bt_substep_kernel", "algorithmic_B_per_pt_substep": BT_BYTES_PER_PT_SUBSTEP}
         ctxb.close()
     if not args.no_cpu:
-        import oracle
-        cores = os.cpu_count() or 1
-        dom1, a1 = make_inputs(NI, NJ)
-        oracle.btstep_timeloop(dom1, {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a1.items()}, nthreads=cores)
-        t0 = time.perf_counter()
-        for _ in range(BT_CALLS_PER_STEP):
-            oracle.btstep_timeloop(dom1, a1, nthreads=cores)
-        ts = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": cells / ts, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-                                "sample": "1 full step of the same workload (oracle C++ restatement of the reference, OpenMP over j)"}
+        val, t, cores, sample = cpu_reference(1, 0)
+        line["cpu_baseline"] = {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -79,6 +79,17 @@ double mom6cu_last_kernel_ms(const mom6cu_ctx* ctx);
 /* Sum of the device times of all repetitions of the most recent *_resident call. */
 double mom6cu_total_kernel_ms(const mom6cu_ctx* ctx);
 
+/* --------------------------------------------------------- field residency */
+/* The Fortran driver owns the model state; these calls let it keep a field on the device between stages
+ * (SURVEY 8b "ownership"): a plane is a device buffer in the library's resident layout.  Passing a plane
+ * pointer wherever an entry point takes an array skips the staging copies entirely (inputs are used in place,
+ * outputs are left on the device), so a sequence of stages runs with no host traffic; mom6cu_plane_download is
+ * the sync point (diagnostics, restarts, halo updates done by un-replaced host code).
+ *   stagger 0=h,1=u,2=v,3=q; wide=1 for the barotropic wide-halo arrays; nk = number of levels (1 for 2-D). */
+double* mom6cu_plane_alloc(mom6cu_ctx* ctx, const char* name, int nk);
+int mom6cu_plane_upload(mom6cu_ctx* ctx, double* plane, const double* host, int stagger, int wide, int nk);
+int mom6cu_plane_download(mom6cu_ctx* ctx, const double* plane, double* host, int stagger, int wide, int nk);
+
 /* ------------------------------------------------------------ grid metrics */
 /* The fields of ocean_grid_type (src/core/MOM_grid.F90:75-175) the hot path reads.
  * All are G-sized 2-D arrays of the staggering in the comment; uploaded once and

@@ -168,6 +168,10 @@ def fill_struct(struct, values, keep):
         if ctype is C.c_void_p:
             if v is None:
                 setattr(struct, name, None)
+            elif isinstance(v, int):               # raw device pointer (resident plane)
+                setattr(struct, name, v)
+            elif hasattr(v, "ptr") and isinstance(getattr(v, "ptr"), int):   # api.Plane
+                setattr(struct, name, v.ptr)
             elif hasattr(v, "data_ptr"):          # torch tensor (device or host)
                 keep.append(v)
                 setattr(struct, name, v.data_ptr())
@@ -213,6 +217,10 @@ def bind(lib):
     lib.mom6cu_btstep.argtypes = [vp, C.POINTER(BarotropicCS), C.POINTER(BtstepArgs)]
     lib.mom6cu_btcalc.argtypes = [vp, C.POINTER(BtcalcArgs)]
     lib.mom6cu_bt_mass_source.argtypes = [vp, vp, vp, C.c_int, vp]
+    lib.mom6cu_plane_alloc.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.mom6cu_plane_alloc.restype = C.c_void_p
+    lib.mom6cu_plane_upload.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    lib.mom6cu_plane_download.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]
@@ -223,6 +231,22 @@ def bind(lib):
     return lib
 
 
+def _preload_nccl():
+    """libmom6cu.so needs libnccl.so.2.  PyTorch bundles a newer NCCL under the same SONAME; whichever is loaded
+    first wins for the whole process, so load the bundled (newer) one first when it exists -- otherwise a later
+    `import torch` would bind to the older system library and fail on missing symbols."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def load():
     """Load libmom6cu.so (built in-tree by __graft_entry__.build()); fail loudly if absent."""
     global _lib
@@ -231,5 +255,6 @@ def load():
             raise RuntimeError(
                 f"{LIB_PATH} not found: build the CUDA extension first "
                 "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+        _preload_nccl()
         _lib = bind(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
     return _lib

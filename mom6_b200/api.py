@@ -71,6 +71,17 @@ class Context:
         raw = bytes(t.cpu().numpy().tobytes())
         self._check(self.lib.mom6cu_comm_init(self._h, raw, len(raw), rank, world))
 
+    # ---- field residency (mom6cu_plane_*)
+    def plane(self, name, host=None, stagger="h", wide=False, nk=1):
+        """Allocate a resident plane (and upload `host` into it)."""
+        p = self.lib.mom6cu_plane_alloc(self._h, name.encode(), nk)
+        if not p:
+            raise Mom6cuError("mom6cu_plane_alloc failed")
+        pl = Plane(self, p, stagger, wide, nk)
+        if host is not None:
+            pl.upload(host)
+        return pl
+
     def sync(self):
         self._check(self.lib.mom6cu_sync(self._h))
 
@@ -79,6 +90,23 @@ class Context:
         keep = []
         st = fill_struct(BtTimeloopArgs(), args, keep)
         return self._check(self.lib.mom6cu_btstep_timeloop_resident(self._h, C.byref(st), reps, 1 if download else 0))
+
+
+class Plane:
+    """A device-resident field (mom6cu_plane_alloc); pass it wherever an array argument is expected."""
+    ST = {"h": 0, "u": 1, "v": 2, "q": 3}
+
+    def __init__(self, ctx, ptr, stagger, wide, nk):
+        self.ctx, self.ptr, self.stagger, self.wide, self.nk = ctx, int(ptr), stagger, bool(wide), nk
+
+    def upload(self, host):
+        self.ctx._check(self.ctx.lib.mom6cu_plane_upload(self.ctx._h, self.ptr, host.ctypes.data, self.ST[self.stagger],
+                                                         int(self.wide), self.nk))
+
+    def download(self, host):
+        self.ctx._check(self.ctx.lib.mom6cu_plane_download(self.ctx._h, self.ptr, host.ctypes.data, self.ST[self.stagger],
+                                                           int(self.wide), self.nk))
+        return host
 
 
 def _ctx_methods():
@@ -139,8 +167,8 @@ def _ctx_methods():
 
     def bt_mass_source(self, h, eta, set_cor, eta_cor):
         """bt_mass_source, MOM_barotropic.F90:5243."""
-        return self._check(self.lib.mom6cu_bt_mass_source(self._h, h.ctypes.data, eta.ctypes.data, int(set_cor),
-                                                          eta_cor.ctypes.data))
+        ptr = lambda x: x.ptr if isinstance(x, Plane) else x.ctypes.data  # noqa: E731
+        return self._check(self.lib.mom6cu_bt_mass_source(self._h, ptr(h), ptr(eta), int(set_cor), ptr(eta_cor)))
 
     for f in (set_grid, set_vgrid, set_cs_continuity, continuity, set_unit_scale, set_cs_coriolisadv, coradcalc,
               set_cs_hor_visc, horizontal_viscosity, btstep, btcalc, bt_mass_source):

@@ -856,36 +856,23 @@ extern "C" int mom6cu_continuity(mom6cu_ctx* c, const mom6cu_continuity_args* a)
   if ((a->visc_rem_u != nullptr) != (a->visc_rem_v != nullptr))
     return c->fail(MOM6CU_ERR_BAD_ARG, "MOM_continuity_PPM: Either both visc_rem_u and visc_rem_v or neither one must be "
                                        "present in call to continuity_PPM.");
-  const int nk = c->g.nk;
-  int rc;
+  Stager S(c, "cont.");
   ContinuityDev D = {};
   D.dt = a->dt;
-  auto up3 = [&](const char* name, const double* src, int st, double** dst) -> int {
-    *dst = nullptr;
-    if (!src) return 0;
-    *dst = c->plane3(std::string("cont.") + name);
-    if (!*dst) return MOM6CU_ERR_CUDA;
-    return m6_up(c, src, st, 0, nk, *dst);
-  };
-  auto up2 = [&](const char* name, const double* src, int st, double** dst) -> int {
-    *dst = nullptr;
-    if (!src) return 0;
-    *dst = c->plane2(std::string("cont.") + name);
-    if (!*dst) return MOM6CU_ERR_CUDA;
-    return m6_up(c, src, st, 0, 1, *dst);
-  };
-  double *u, *v, *hin, *h, *uh, *vh, *pu, *pv, *vru, *vrv, *ucor, *vcor, *uhbt, *vhbt, *ducor, *dvcor;
-  if ((rc = up3("u", a->u, ST_U, &u)) || (rc = up3("v", a->v, ST_V, &v)) || (rc = up3("hin", a->hin, ST_H, &hin))) return rc;
+  int rc;
+  const double* hin = nullptr;
   // h is inout: points outside the updated ranges keep the caller's values
-  if ((rc = up3("h", a->h, ST_H, &h)) || (rc = up3("uh", a->uh, ST_U, &uh)) || (rc = up3("vh", a->vh, ST_V, &vh))) return rc;
-  if ((rc = up3("porU", a->por_face_areaU, ST_U, &pu)) || (rc = up3("porV", a->por_face_areaV, ST_V, &pv))) return rc;
-  if ((rc = up3("vru", a->visc_rem_u, ST_U, &vru)) || (rc = up3("vrv", a->visc_rem_v, ST_V, &vrv))) return rc;
-  if ((rc = up3("ucor", a->u_cor, ST_U, &ucor)) || (rc = up3("vcor", a->v_cor, ST_V, &vcor))) return rc;
-  if ((rc = up2("uhbt", a->uhbt, ST_U, &uhbt)) || (rc = up2("vhbt", a->vhbt, ST_V, &vhbt))) return rc;
-  if ((rc = up2("ducor", a->du_cor, ST_U, &ducor)) || (rc = up2("dvcor", a->dv_cor, ST_V, &dvcor))) return rc;
-  D.u = u; D.v = v; D.hin = (a->hin == a->h) ? h : hin; D.h = h; D.uh = uh; D.vh = vh;
-  D.por_face_areaU = pu; D.por_face_areaV = pv; D.visc_rem_u = vru; D.visc_rem_v = vrv; D.u_cor = ucor; D.v_cor = vcor;
-  D.uhbt = uhbt; D.vhbt = vhbt; D.du_cor = ducor; D.dv_cor = dvcor;
+  if ((rc = S.in3(a->u, ST_U, "u", &D.u)) || (rc = S.in3(a->v, ST_V, "v", &D.v)) || (rc = S.io3(a->h, ST_H, "h", &D.h)) ||
+      (rc = S.io3(a->uh, ST_U, "uh", &D.uh)) || (rc = S.io3(a->vh, ST_V, "vh", &D.vh)) ||
+      (rc = S.in3(a->por_face_areaU, ST_U, "porU", &D.por_face_areaU)) || (rc = S.in3(a->por_face_areaV, ST_V, "porV", &D.por_face_areaV)) ||
+      (rc = S.in3(a->visc_rem_u, ST_U, "vru", &D.visc_rem_u)) || (rc = S.in3(a->visc_rem_v, ST_V, "vrv", &D.visc_rem_v)) ||
+      (rc = S.io3(a->u_cor, ST_U, "ucor", &D.u_cor)) || (rc = S.io3(a->v_cor, ST_V, "vcor", &D.v_cor)) ||
+      (rc = S.in2(a->uhbt, ST_U, "uhbt", &D.uhbt)) || (rc = S.in2(a->vhbt, ST_V, "vhbt", &D.vhbt)) ||
+      (rc = S.io2(a->du_cor, ST_U, "ducor", &D.du_cor)) || (rc = S.io2(a->dv_cor, ST_V, "dvcor", &D.dv_cor)))
+    return rc;
+  if (a->hin == a->h) hin = D.h;  // the corrector call passes the same array (MOM_dynamics_split_RK2.F90:1043)
+  else if ((rc = S.in3(a->hin, ST_H, "hin", &hin))) return rc;
+  D.hin = hin;
   const mom6cu_bt_cont* B = a->BT_cont;
   if (B) {
     D.have_BT_cont = 1;
@@ -897,31 +884,11 @@ extern "C" int mom6cu_continuity(mom6cu_ctx* c, const mom6cu_continuity_args* a)
                                  "FA_v_NN", "FA_v_N0", "FA_v_S0", "FA_v_SS", "vBT_SS", "vBT_NN"};
     for (int m = 0; m < 12; ++m) {
       if (!src2[m]) return c->fail(MOM6CU_ERR_BAD_ARG, "continuity: BT_cont%%%s is not allocated", nm[m]);
-      if ((rc = up2(nm[m], src2[m], m < 6 ? ST_U : ST_V, dst2[m]))) return rc;
+      if ((rc = S.io2(src2[m], m < 6 ? ST_U : ST_V, nm[m], dst2[m]))) return rc;
     }
-    if ((rc = up3("h_u", B->h_u, ST_U, &D.h_u)) || (rc = up3("h_v", B->h_v, ST_V, &D.h_v))) return rc;
+    if ((rc = S.io3(B->h_u, ST_U, "h_u", &D.h_u)) || (rc = S.io3(B->h_v, ST_V, "h_v", &D.h_v))) return rc;
   }
-  M6_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  if ((rc = S.begin())) return rc;
   if ((rc = m6_continuity_run(c, D))) return rc;
-  M6_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-#define DN3(src, st, dst) if ((dst) && (rc = m6_down(c, (src), (st), 0, nk, (dst)))) return rc
-#define DN2(src, st, dst) if ((dst) && (rc = m6_down(c, (src), (st), 0, 1, (dst)))) return rc
-  DN3(h, ST_H, a->h); DN3(uh, ST_U, a->uh); DN3(vh, ST_V, a->vh);
-  DN3(ucor, ST_U, a->u_cor); DN3(vcor, ST_V, a->v_cor);
-  DN2(ducor, ST_U, a->du_cor); DN2(dvcor, ST_V, a->dv_cor);
-  if (B) {
-    DN2(D.FA_u_EE, ST_U, B->FA_u_EE); DN2(D.FA_u_E0, ST_U, B->FA_u_E0); DN2(D.FA_u_W0, ST_U, B->FA_u_W0);
-    DN2(D.FA_u_WW, ST_U, B->FA_u_WW); DN2(D.uBT_WW, ST_U, B->uBT_WW); DN2(D.uBT_EE, ST_U, B->uBT_EE);
-    DN2(D.FA_v_NN, ST_V, B->FA_v_NN); DN2(D.FA_v_N0, ST_V, B->FA_v_N0); DN2(D.FA_v_S0, ST_V, B->FA_v_S0);
-    DN2(D.FA_v_SS, ST_V, B->FA_v_SS); DN2(D.vBT_SS, ST_V, B->vBT_SS); DN2(D.vBT_NN, ST_V, B->vBT_NN);
-    DN3(D.h_u, ST_U, B->h_u); DN3(D.h_v, ST_V, B->h_v);
-  }
-#undef DN3
-#undef DN2
-  M6_CUDA(c, cudaStreamSynchronize(c->stream));
-  float ms = 0.f;
-  M6_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->last_ms = ms;
-  c->total_ms = ms;
-  return 0;
+  return S.finish();
 }

@@ -182,6 +182,30 @@ long long mom6cu_launch_count(const mom6cu_ctx* c) { return c ? c->launches : 0;
 double mom6cu_last_kernel_ms(const mom6cu_ctx* c) { return c ? c->last_ms : 0.0; }
 double mom6cu_total_kernel_ms(const mom6cu_ctx* c) { return c ? c->total_ms : 0.0; }
 
+double* mom6cu_plane_alloc(mom6cu_ctx* c, const char* name, int nk) {
+  if (!c || !name || nk < 1) return nullptr;
+  cudaSetDevice(c->device);
+  return c->buf(std::string("user.") + name, (size_t)c->g.plane * nk);
+}
+
+int mom6cu_plane_upload(mom6cu_ctx* c, double* plane, const double* host, int stagger, int wide, int nk) {
+  if (!c || !plane || !host) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  int rc = m6_up(c, host, stagger, wide, nk, plane);
+  if (rc) return rc;
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int mom6cu_plane_download(mom6cu_ctx* c, const double* plane, double* host, int stagger, int wide, int nk) {
+  if (!c || !plane || !host) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  int rc = m6_down(c, plane, stagger, wide, nk, host);
+  if (rc) return rc;
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int mom6cu_sync(mom6cu_ctx* c) {
   if (!c) return MOM6CU_ERR_BAD_ARG;
   M6_CUDA(c, cudaStreamSynchronize(c->stream));

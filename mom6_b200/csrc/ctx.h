@@ -48,6 +48,11 @@ struct mom6cu_ctx {
   double* plane3(const std::string& name) { return buf(name, (size_t)g.plane * g.nk); }
   double* plane3k(const std::string& name, int nk) { return buf(name, (size_t)g.plane * nk); }
   int fail(int code, const char* fmt, ...);
+  // true if p points at the start of one of this context's resident buffers
+  bool is_plane(const void* p) const {
+    for (const auto& kv : bufs) if ((const void*)kv.second == p) return true;
+    return false;
+  }
 };
 
 #define M6_CUDA(ctx, call)                                                              \
@@ -86,6 +91,7 @@ struct Stager {
   int in(const double* src, int st, int wide, int nk, const char* name, const double** dst) {
     *dst = nullptr;
     if (!src) return 0;
+    if (c->is_plane(src)) { *dst = src; return 0; }  // already resident: use in place
     double* p = c->buf(pfx + name, (size_t)c->g.plane * nk);
     if (!p) return MOM6CU_ERR_CUDA;
     *dst = p;
@@ -95,7 +101,7 @@ struct Stager {
     const double* p = nullptr;
     int rc = in(src, st, wide, nk, name, &p);
     *dst = (double*)p;
-    if (!rc && p) outs.push_back({p, src, st, wide, nk});
+    if (!rc && p && p != src) outs.push_back({p, src, st, wide, nk});  // resident outputs stay on the device
     return rc;
   }
   int in3(const double* s, int st, const char* n, const double** d) { return in(s, st, 0, c->g.nk, n, d); }

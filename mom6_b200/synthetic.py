@@ -722,4 +722,31 @@ def btstep_inputs(ni, nj, nk, halo=4, whalo=6, seed=SEED, land_blocks=0, cyclic_
         a["taux_bot"] = U2("u", 0.01, mU); a["tauy_bot"] = U2("v", 0.01, mV)
     a = {k: (np.ascontiguousarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in a.items()}
     a["BT_cont"] = {k: (np.ascontiguousarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in a["BT_cont"].items()}
+    a["_h"] = st["h"]   # not an argument of btstep (ignored by the marshalling); lets step_inputs share the state
     return dom, grid, gv, cs, a
+
+
+def step_inputs(ni, nj, nk, halo=4, whalo=10, seed=SEED, land_blocks=0, dt=900.0, **bt_over):
+    """Inputs of every implemented stage of one split-RK2 baroclinic step (MOM_dynamics_split_RK2.F90:294-1205), sharing
+    one grid and one model state.  Returns dom, grid, gv and a dict of per-stage (cs, args)."""
+    dom, grid, gv, cs_bt, a_bt = btstep_inputs(ni, nj, nk, halo=halo, whalo=whalo, seed=seed, land_blocks=land_blocks, dt=dt, **bt_over)
+    h = a_bt["_h"]
+    u, v, vru, vrv = a_bt["U_in"], a_bt["V_in"], a_bt["visc_rem_u"], a_bt["visc_rem_v"]
+    new3 = lambda st: fidx.new(dom, st, nk=nk).a          # noqa: E731
+    new2 = lambda st: fidx.new(dom, st).a                 # noqa: E731
+    uh, vh = transports(dom, grid, dict(h=h, u=u, v=v))
+    b = {k: (x.copy() if isinstance(x, np.ndarray) else x) for k, x in a_bt["BT_cont"].items()}
+    b["h_u"], b["h_v"] = new3("u"), new3("v")
+    cont = dict(u=u, v=v, hin=h, h=h.copy(), uh=new3("u"), vh=new3("v"), dt=dt, visc_rem_u=vru, visc_rem_v=vrv,
+                uhbt=np.ascontiguousarray(uh.sum(axis=0)), vhbt=np.ascontiguousarray(vh.sum(axis=0)),
+                u_cor=new3("u"), v_cor=new3("v"), BT_cont=b)
+    corad = dict(u=u, v=v, h=h, uh=uh, vh=vh, CAu=new3("u"), CAv=new3("v"))
+    hv = dict(u=u, v=v, h=h, diffu=new3("u"), diffv=new3("v"), dt=dt)
+    btc = dict(h=h, h_u=b["h_u"], h_v=b["h_v"], frhatu=cs_bt["frhatu"], frhatv=cs_bt["frhatv"], bathyT=grid["bathyT"],
+               hvel_scheme=4, may_use_default=0)
+    stages = dict(continuity=(continuity_cs(nk), cont), coradcalc=(coriolisadv_cs(), corad),
+                  horizontal_viscosity=(hor_visc_cs(dom, grid, dt=dt), hv), btstep=(cs_bt, a_bt), btcalc=(None, btc),
+                  # eta consistent with the layer thicknesses, so the mass-source correction stays small (:5268-5292)
+                  bt_mass_source=(None, dict(h=h, eta=np.ascontiguousarray((h.sum(axis=0) - grid["bathyT"]) * grid["mask2dT"] +
+                                                                            1e-4 * a_bt["eta_in"]), eta_cor=cs_bt["eta_cor"])))
+    return dom, grid, gv, stages
