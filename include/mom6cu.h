@@ -224,6 +224,37 @@ typedef struct mom6cu_hor_visc_args {
 int mom6cu_set_cs_hor_visc(mom6cu_ctx* ctx, const mom6cu_hor_visc_cs* CS);
 int mom6cu_horizontal_viscosity(mom6cu_ctx* ctx, const mom6cu_hor_visc_args* a);
 
+/* ----------------------------------------------------------- PressureForce */
+/* PressureForce (src/core/MOM_PressureForce.F90:40-82) with ANALYTIC_FV_PGF=True and GV%Boussinesq, i.e.
+ * PressureForce_FV_Bouss (src/core/MOM_PressureForce_FV.F90:947-2017) with the analytic layer integrals
+ * int_density_dz (src/core/MOM_density_integrals.F90:42-103 -> src/equation_of_state/MOM_EOS.F90:1384-1499 ->
+ * int_density_dz_linear MOM_EOS_linear.F90:275 / int_density_dz_wright MOM_EOS_Wright.F90:389) and
+ * Set_pbce_Bouss (src/core/MOM_PressureForce_Montgomery.F90:649-748).
+ * PressureForce_FV_CS (:40-107) + the EOS_type / verticalGrid members the routine reads.
+ * Frozen options: no tides / SAL, no Stanley SGS term, no RESET_INTXPA_INTEGRAL / CORRECTION_INTXPA, no bulk
+ * mixed layer (GV%nk_rho_varies = 0), piecewise-constant T,S within layers (RECONSTRUCT_FOR_PRESSURE off or no ALE);
+ * EOS forms: none (layered), LINEAR, WRIGHT (analytic integrals, EOS_quadrature off). */
+#define MOM6CU_EOS_NONE 0
+#define MOM6CU_EOS_LINEAR 1
+#define MOM6CU_EOS_WRIGHT 3
+typedef struct mom6cu_pressureforce_cs {
+  int EOS_form, MassWghtInterp, use_SSH_in_Z0p, rho_ref_bug, unsupported;
+  double rho_ref, GFS_scale, Z_ref, dZ_subroundoff;
+  double Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp; /* EOS_LINEAR */
+  const double *Rlay, *g_prime;                /* GV%Rlay(1:nk), GV%g_prime(1:nk+1), host arrays (EOS_NONE) */
+} mom6cu_pressureforce_cs;
+
+/* PressureForce(h, tv, PFu, PFv, G, GV, US, CS, ALE_CSp, ADp, p_atm, pbce, eta)  MOM_PressureForce.F90:40 */
+typedef struct mom6cu_pressureforce_args {
+  const double *h, *T, *S; /* 3-D h; tv%T, tv%S (NULL with EOS_NONE) */
+  double *PFu, *PFv;       /* 3-D u, v (out) */
+  const double* p_atm;     /* 2-D h, optional */
+  double* pbce;            /* 3-D h, optional out */
+  double* eta;             /* 2-D h, optional out */
+} mom6cu_pressureforce_args;
+int mom6cu_set_cs_pressureforce(mom6cu_ctx* ctx, const mom6cu_pressureforce_cs* CS);
+int mom6cu_pressure_force(mom6cu_ctx* ctx, const mom6cu_pressureforce_args* a);
+
 /* ------------------------------------------------------- halo communication */
 /* The reference's halo API (pass_var / pass_vector / do_group_pass,
  * src/framework/MOM_domains.F90 -> config_src/infra/FMS2/MOM_domain_infra.F90:171-216,

@@ -159,6 +159,21 @@ class BtcalcArgs(C.Structure):
                [("hvel_scheme", C.c_int), ("may_use_default", C.c_int)]
 
 
+EOS_NONE, EOS_LINEAR, EOS_WRIGHT = 0, 1, 3
+
+
+class PressureForceCS(C.Structure):
+    """mom6cu_pressureforce_cs: PressureForce_FV_CS (MOM_PressureForce_FV.F90:40-107) + EOS / vertical-grid members."""
+    _fields_ = ([(n, C.c_int) for n in ("EOS_form", "MassWghtInterp", "use_SSH_in_Z0p", "rho_ref_bug", "unsupported")] +
+                [(n, C.c_double) for n in ("rho_ref", "GFS_scale", "Z_ref", "dZ_subroundoff", "Rho_T0_S0", "dRho_dT", "dRho_dS",
+                                           "dRho_dp")] + [(n, C.c_void_p) for n in ("Rlay", "g_prime")])
+
+
+class PressureForceArgs(C.Structure):
+    """mom6cu_pressureforce_args: the dummy arguments of PressureForce (MOM_PressureForce.F90:40)."""
+    _fields_ = [(n, C.c_void_p) for n in ("h", "T", "S", "PFu", "PFv", "p_atm", "pbce", "eta")]
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
@@ -221,6 +236,8 @@ def bind(lib):
     lib.mom6cu_plane_alloc.restype = C.c_void_p
     lib.mom6cu_plane_upload.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_plane_download.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    lib.mom6cu_set_cs_pressureforce.argtypes = [vp, C.POINTER(PressureForceCS)]
+    lib.mom6cu_pressure_force.argtypes = [vp, C.POINTER(PressureForceArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

@@ -170,8 +170,18 @@ def _ctx_methods():
         ptr = lambda x: x.ptr if isinstance(x, Plane) else x.ctypes.data  # noqa: E731
         return self._check(self.lib.mom6cu_bt_mass_source(self._h, ptr(h), ptr(eta), int(set_cor), ptr(eta_cor)))
 
+    def set_cs_pressureforce(self, cs):
+        """PressureForce_FV_init's resolved parameters (MOM_PressureForce_FV.F90:2020+) and the EOS parameters."""
+        keep = []
+        return self._check(self.lib.mom6cu_set_cs_pressureforce(self._h, C.byref(marshal.pressureforce_cs(cs, keep))))
+
+    def pressure_force(self, args):
+        """PressureForce, MOM_PressureForce.F90:40 (-> PressureForce_FV_Bouss)."""
+        keep = []
+        return self._check(self.lib.mom6cu_pressure_force(self._h, C.byref(marshal.pressureforce_args(args, keep))))
+
     for f in (set_grid, set_vgrid, set_cs_continuity, continuity, set_unit_scale, set_cs_coriolisadv, coradcalc,
-              set_cs_hor_visc, horizontal_viscosity, btstep, btcalc, bt_mass_source):
+              set_cs_hor_visc, horizontal_viscosity, btstep, btcalc, bt_mass_source, set_cs_pressureforce, pressure_force):
         setattr(Context, f.__name__, f)
 
 

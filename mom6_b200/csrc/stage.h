@@ -54,7 +54,14 @@ struct BtstepDev {
   const double *FA_v_NN, *FA_v_N0, *FA_v_S0, *FA_v_SS, *vBT_SS, *vBT_NN;
 };
 
+// PressureForce dummy arguments (MOM_PressureForce.F90:40-61)
+struct PgfDev {
+  const double *h, *T, *S, *p_atm;
+  double *PFu, *PFv, *pbce, *eta;
+};
+
 struct mom6cu_ctx;
+int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D);
 // CS holds device pointers (resident planes) for every array member
 int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev& D);
 int m6_btcalc_run(mom6cu_ctx* c, const double* h, const double* h_u, const double* h_v, const double* bathyT, int hvel_scheme,

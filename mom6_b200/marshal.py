@@ -2,7 +2,8 @@
 import ctypes as C
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
-                   HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, fill_struct)
+                   HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
+                   PressureForceArgs, fill_struct)
 
 
 def _scalars(struct, d):
@@ -70,3 +71,11 @@ def btstep_args(a, keep):
 
 def btcalc_args(a, keep):
     return fill_struct(BtcalcArgs(), a, keep)
+
+
+def pressureforce_cs(d, keep):
+    return fill_struct(PressureForceCS(), d, keep)
+
+
+def pressureforce_args(a, keep):
+    return fill_struct(PressureForceArgs(), a, keep)

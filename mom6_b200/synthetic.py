@@ -750,3 +750,33 @@ def step_inputs(ni, nj, nk, halo=4, whalo=10, seed=SEED, land_blocks=0, dt=900.0
                   bt_mass_source=(None, dict(h=h, eta=np.ascontiguousarray((h.sum(axis=0) - grid["bathyT"]) * grid["mask2dT"] +
                                                                             1e-4 * a_bt["eta_in"]), eta_cor=cs_bt["eta_cor"])))
     return dom, grid, gv, stages
+
+
+def pressureforce_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, eos="WRIGHT",
+                         with_p_atm=False, with_pbce=True, with_eta=True, **cs_over):
+    """Everything a PressureForce call needs (MOM_PressureForce.F90:40): returns dom, grid, vgrid, cs, args.
+    T = 20 exp(z/1000) + noise, S = 35 + noise, Z*-like h with vanished layers over the seamount."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 404)
+    h = st["h"]
+    zmid = -(np.cumsum(h, axis=0) - 0.5 * h)
+    T = 20.0 * np.exp(zmid / 1000.0) + 0.05 * r.uniform(-1, 1, size=h.shape)
+    S = 35.0 + 0.5 * np.exp(zmid / 500.0) + 0.01 * r.uniform(-1, 1, size=h.shape)
+    form = dict(NONE=0, LINEAR=1, WRIGHT=3)[eos]
+    cs = dict(EOS_form=form, MassWghtInterp=0, use_SSH_in_Z0p=0, rho_ref_bug=0, unsupported=0, rho_ref=1035.0, GFS_scale=1.0,
+              Z_ref=0.0, dZ_subroundoff=1e-30, Rho_T0_S0=1000.0, dRho_dT=-0.2, dRho_dS=0.8, dRho_dp=0.0,
+              Rlay=np.ascontiguousarray(1026.0 + 2.0 * np.arange(nk) / max(nk - 1, 1)),
+              g_prime=np.ascontiguousarray(np.concatenate(([9.8], np.full(nk, 9.8 * 2.0 / max(nk - 1, 1) / 1035.0)))))
+    cs.update(cs_over)
+    a = dict(h=h, T=np.ascontiguousarray(T) if form else None, S=np.ascontiguousarray(S) if form else None,
+             PFu=fidx.new(dom, "u", nk=nk).a, PFv=fidx.new(dom, "v", nk=nk).a)
+    if with_p_atm:
+        a["p_atm"] = np.ascontiguousarray(1.0e5 + 500.0 * r.uniform(-1, 1, size=grid["bathyT"].shape))
+    if with_pbce:
+        a["pbce"] = fidx.new(dom, "h", nk=nk).a
+    if with_eta:
+        a["eta"] = fidx.new(dom, "h").a
+    return dom, grid, gv, cs, a

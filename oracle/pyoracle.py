@@ -126,3 +126,19 @@ def bt_mass_source(dom, grid, gv, h, eta, set_cor, eta_cor):
     lib.oracle_bt_mass_source.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     return lib.oracle_bt_mass_source(C.byref(dom), C.byref(g), C.byref(v), h.ctypes.data, eta.ctypes.data, int(set_cor),
                                      eta_cor.ctypes.data)
+
+
+def pressure_force(dom, grid, gv, cs, args, nthreads=1):
+    """oracle_pressure_force: PressureForce_FV_Bouss, MOM_PressureForce_FV.F90:947-2017 (frozen option set)."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    v = marshal.vgrid(gv)
+    c = marshal.pressureforce_cs(cs, keep)
+    a = marshal.pressureforce_args(args, keep)
+    lib.oracle_pressure_force.argtypes = [C.c_void_p] * 5 + [C.c_int]
+    rc = lib.oracle_pressure_force(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(a), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_pressure_force rc={rc}")
+    return rc
