@@ -255,6 +255,35 @@ typedef struct mom6cu_pressureforce_args {
 int mom6cu_set_cs_pressureforce(mom6cu_ctx* ctx, const mom6cu_pressureforce_cs* CS);
 int mom6cu_pressure_force(mom6cu_ctx* ctx, const mom6cu_pressureforce_args* a);
 
+/* ---------------------------------------------------------------- ALE remap */
+/* remapping_CS, src/ALE/MOM_remapping.F90:37-85, as resolved by initialize_remapping.  Schemes (:89-94):
+ * PCM 0, PLM 2, PPM_H4 4, PPM_IH4 5.  Frozen: answer_date >= 20190101, the OM4-era reconstruction functions
+ * (not the Recon1d classes), no PQM / hybgen / PPM_CW schemes. */
+#define MOM6CU_REMAPPING_PCM 0
+#define MOM6CU_REMAPPING_PLM 2
+#define MOM6CU_REMAPPING_PPM_H4 4
+#define MOM6CU_REMAPPING_PPM_IH4 5
+typedef struct mom6cu_remapping_cs {
+  int remapping_scheme, boundary_extrapolation, force_bounds_in_subcell, force_bounds_in_target,
+      om4_remap_via_sub_cells, answer_date;
+  double h_neglect, h_neglect_edge;
+} mom6cu_remapping_cs;
+
+/* ALE_remap_tracers(CS, G, GV, h_old, h_new, Reg, ...)  src/ALE/MOM_ALE.F90:760-879: every column of each of the ntr
+ * h-point fields (Reg%Tr(m)%t) with mask2dT > 0 is remapped conservatively from h_old to h_new with
+ * remapping_core_h (MOM_remapping.F90:234); conc_underflow[m] > 0 flushes tiny values (:822-824). */
+int mom6cu_ale_remap_tracers(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, const double* h_old, const double* h_new, int ntr,
+                             double* const* tr, const double* conc_underflow);
+/* ALE_remap_set_h_vel, MOM_ALE.F90:882-925 and ALE_remap_velocities :1089-1300 (vel_remapCS; no KE-conserving
+ * correction, no near-bottom masking). */
+int mom6cu_ale_remap_set_h_vel(mom6cu_ctx* ctx, const double* h_new, double* h_u, double* h_v);
+int mom6cu_ale_remap_velocities(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, const double* h_old_u, const double* h_old_v,
+                                const double* h_new_u, const double* h_new_v, double* u, double* v);
+/* remapping_core_h on a batch of independent columns (the reference's unit-test / diagnostic entry point,
+ * MOM_remapping.F90:234): h0,u0 are (ncol,n0), h1,u1 (ncol,n1), row-major, host or device. */
+int mom6cu_remapping_core_h(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, int ncol, int n0, const double* h0, const double* u0,
+                            int n1, const double* h1, double* u1);
+
 /* ------------------------------------------------------- halo communication */
 /* The reference's halo API (pass_var / pass_vector / do_group_pass,
  * src/framework/MOM_domains.F90 -> config_src/infra/FMS2/MOM_domain_infra.F90:171-216,

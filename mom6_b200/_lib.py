@@ -174,6 +174,16 @@ class PressureForceArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("h", "T", "S", "PFu", "PFv", "p_atm", "pbce", "eta")]
 
 
+REMAPPING_PCM, REMAPPING_PLM, REMAPPING_PPM_H4, REMAPPING_PPM_IH4 = 0, 2, 4, 5
+
+
+class RemappingCS(C.Structure):
+    """mom6cu_remapping_cs: remapping_CS (src/ALE/MOM_remapping.F90:37-85)."""
+    _fields_ = [(n, C.c_int) for n in ("remapping_scheme", "boundary_extrapolation", "force_bounds_in_subcell",
+                                       "force_bounds_in_target", "om4_remap_via_sub_cells", "answer_date")] + \
+               [(n, C.c_double) for n in ("h_neglect", "h_neglect_edge")]
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
@@ -238,6 +248,10 @@ def bind(lib):
     lib.mom6cu_plane_download.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_set_cs_pressureforce.argtypes = [vp, C.POINTER(PressureForceCS)]
     lib.mom6cu_pressure_force.argtypes = [vp, C.POINTER(PressureForceArgs)]
+    lib.mom6cu_ale_remap_tracers.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, C.c_int, C.POINTER(vp), vp]
+    lib.mom6cu_ale_remap_set_h_vel.argtypes = [vp, vp, vp, vp]
+    lib.mom6cu_ale_remap_velocities.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, vp, vp, vp, vp]
+    lib.mom6cu_remapping_core_h.argtypes = [vp, C.POINTER(RemappingCS), C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

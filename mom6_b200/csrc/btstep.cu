@@ -182,6 +182,29 @@ __global__ void bt_find_Cor_kernel(const Geom G, const Setup2D S) {  // btstep_f
   }
 }
 
+// Gathers the bases of bt_rem = mask * av_rem**Instep (:1497-1509) over (is-1:ie, js-1:je): 0 wherever the result is 0.
+__global__ void bt_rem_pack_kernel(m6::Geom G, const double* __restrict__ mu, const double* __restrict__ mv,
+                                   const double* __restrict__ au, const double* __restrict__ av, int is, int js, int nx, int ny,
+                                   double* __restrict__ pk) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nx * ny) return;
+  const int i = is - 1 + n % nx, j = js - 1 + n / nx;
+  const size_t g = (size_t)G.idx(i, j);
+  pk[n] = (j >= js && mu[g] * au[g] > 0.0) ? au[g] : 0.0;
+  pk[(size_t)nx * ny + n] = (i >= is && mv[g] * av[g] > 0.0) ? av[g] : 0.0;
+}
+__global__ void bt_rem_unpack_kernel(m6::Geom G, const double* __restrict__ mu, const double* __restrict__ mv,
+                                     const double* __restrict__ pk, int is, int js, int nx, int ny, double* __restrict__ ru,
+                                     double* __restrict__ rv) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nx * ny) return;
+  const int i = is - 1 + n % nx, j = js - 1 + n / nx;
+  const size_t g = (size_t)G.idx(i, j);
+  const double pu = pk[n], pv = pk[(size_t)nx * ny + n];
+  if (j >= js) ru[g] = (pu > 0.0) ? mu[g] * pu : 0.0;
+  if (i >= is) rv[g] = (pv > 0.0) ? mv[g] * pv : 0.0;
+}
+
 __global__ void bt_Cor_ref_kernel(const Geom G, Pl4 f4u, Pl4 f4v, const double* ubt_Cor, const double* vbt_Cor,
                                   double* Cor_ref_u, double* Cor_ref_v) {  // :1452-1461
   const int i = G.isc - 1 + blockIdx.x * blockDim.x + threadIdx.x, j = G.jsc - 1 + blockIdx.y;
@@ -439,29 +462,26 @@ int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev
             (double*)P.Cor_ref_u, (double*)P.Cor_ref_v);
   // ---- the viscous remnant with BT_STRONG_DRAG=False: av_rem**Instep by the host libm (:1497-1509) ----
   if (!CS.strong_drag) {
-    const size_t np = (size_t)G.plane;
-    std::vector<double> hu(np), hv(np), mu(np), mv(np);
-    M6_CUDA(c, cudaMemcpyAsync(hu.data(), av_rem_u, pb, cudaMemcpyDeviceToHost, c->stream));
-    M6_CUDA(c, cudaMemcpyAsync(hv.data(), av_rem_v, pb, cudaMemcpyDeviceToHost, c->stream));
-    M6_CUDA(c, cudaMemcpyAsync(mu.data(), M.mask2dCu, pb, cudaMemcpyDeviceToHost, c->stream));
-    M6_CUDA(c, cudaMemcpyAsync(mv.data(), M.mask2dCv, pb, cudaMemcpyDeviceToHost, c->stream));
+    // The base of the power is gathered on the device into one packed rectangle per face set (0 where the result is 0),
+    // the power itself is the host libm's (the only operation of the path that is not IEEE-exact, so the only one that has
+    // to be the reference platform's own routine), and mask*pow is scattered back on the device.
+    const int nx = ie - is + 2, ny = je - js + 2;  // covers (is-1:ie, js-1:je)
+    const size_t npk = (size_t)nx * ny;
+    double* dpk = c->buf("bt.rem_pack", 2 * npk);
+    double* hpk = c->host_scratch("bt.rem_pack", 2 * npk);
+    if (!dpk || !hpk) return MOM6CU_ERR_CUDA;
+    M6_LAUNCH(c, bt_rem_pack_kernel, dim3((unsigned)((npk + 127) / 128)), 128, 0, G, M.mask2dCu, M.mask2dCv, av_rem_u, av_rem_v, is, js, nx, ny, dpk);
+    M6_CUDA(c, cudaMemcpyAsync(hpk, dpk, 2 * npk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     M6_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int j = js - 1; j <= je; ++j) for (int i = is - 1; i <= ie; ++i) {
-      const size_t g = (size_t)G.idx(i, j);
-      double ru = 0.0, rv = 0.0;
-      if (j >= js && mu[g] * hu[g] > 0.0) ru = mu[g] * std::pow(hu[g], Instep);
-      if (i >= is && mv[g] * hv[g] > 0.0) rv = mv[g] * std::pow(hv[g], Instep);
-      hu[g] = ru; hv[g] = rv;
-    }
-    // rows/columns outside the computational faces are zero, as in the reference's zero-initialised wide arrays
-    for (size_t g = 0; g < np; ++g) {
-      const int j = (int)(g / G.pitch) + G.j0, i = (int)(g % G.pitch) + G.i0;
-      if (!(i >= is - 1 && i <= ie && j >= js && j <= je)) hu[g] = 0.0;
-      if (!(i >= is && i <= ie && j >= js - 1 && j <= je)) hv[g] = 0.0;
-    }
-    M6_CUDA(c, cudaMemcpyAsync((double*)P.bt_rem_u, hu.data(), pb, cudaMemcpyHostToDevice, c->stream));
-    M6_CUDA(c, cudaMemcpyAsync((double*)P.bt_rem_v, hv.data(), pb, cudaMemcpyHostToDevice, c->stream));
-    M6_CUDA(c, cudaStreamSynchronize(c->stream));
+    const long long n2 = (long long)(2 * npk);
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < n2; ++n) hpk[n] = (hpk[n] > 0.0) ? std::pow(hpk[n], Instep) : 0.0;
+    M6_CUDA(c, cudaMemcpyAsync(dpk, hpk, 2 * npk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // rows/columns outside the computational faces stay zero, as in the reference's zero-initialised wide arrays
+    M6_CUDA(c, cudaMemsetAsync((double*)P.bt_rem_u, 0, pb, c->stream));
+    M6_CUDA(c, cudaMemsetAsync((double*)P.bt_rem_v, 0, pb, c->stream));
+    M6_LAUNCH(c, bt_rem_unpack_kernel, dim3((unsigned)((npk + 127) / 128)), 128, 0, G, M.mask2dCu, M.mask2dCv, dpk, is, js, nx, ny,
+              (double*)P.bt_rem_u, (double*)P.bt_rem_v);
   }
   // ---- eta, eta_PF (:997-1003) and the mass source (:1549-1587) ----
   M6_LAUNCH(c, bt_copy_G_kernel, grid2(d.ied - d.isd + 1, d.jed - d.jsd + 1, 128), 128, 0, G, D.eta_in, B.eta[0], D.eta_PF_in, (double*)P.eta_PF);

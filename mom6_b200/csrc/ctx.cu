@@ -18,6 +18,19 @@ double* mom6cu_ctx::buf(const std::string& name, size_t n) {
   return p;
 }
 
+double* mom6cu_ctx::host_scratch(const std::string& name, size_t n) {
+  auto it = pinned.find(name);
+  if (it != pinned.end() && it->second.second >= n) return it->second.first;
+  if (it != pinned.end()) { cudaFreeHost(it->second.first); pinned.erase(it); }
+  double* p = nullptr;
+  if (cudaHostAlloc(&p, n * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+    fail(MOM6CU_ERR_CUDA, "cudaHostAlloc of %zu doubles for '%s' failed", n, name.c_str());
+    return nullptr;
+  }
+  pinned[name] = {p, n};
+  return p;
+}
+
 int mom6cu_ctx::fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -161,6 +174,7 @@ int mom6cu_destroy(mom6cu_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto& kv : c->bufs) cudaFree(kv.second);
+  for (auto& kv : c->pinned) cudaFreeHost(kv.second.first);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_side) cudaEventDestroy(c->ev_side);

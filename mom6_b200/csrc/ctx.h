@@ -26,6 +26,7 @@ struct mom6cu_ctx {
   char err[1024] = {0};
   std::map<std::string, double*> bufs;
   std::map<std::string, size_t> buf_sz;
+  std::map<std::string, std::pair<double*, size_t>> pinned;  // page-locked host scratch
   void* comm = nullptr;  // ncclComm_t when multi-rank
   // resident grid metrics and resolved control structures
   GridDev grid = {};
@@ -50,6 +51,8 @@ struct mom6cu_ctx {
   double* plane2(const std::string& name) { return buf(name, (size_t)g.plane); }
   double* plane3(const std::string& name) { return buf(name, (size_t)g.plane * g.nk); }
   double* plane3k(const std::string& name, int nk) { return buf(name, (size_t)g.plane * nk); }
+  // named, persistent, page-locked host scratch of n doubles
+  double* host_scratch(const std::string& name, size_t n);
   int fail(int code, const char* fmt, ...);
   // true if p points at the start of one of this context's resident buffers
   bool is_plane(const void* p) const {

@@ -3,7 +3,7 @@ import ctypes as C
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, fill_struct)
+                   PressureForceArgs, RemappingCS, fill_struct)
 
 
 def _scalars(struct, d):
@@ -79,3 +79,7 @@ def pressureforce_cs(d, keep):
 
 def pressureforce_args(a, keep):
     return fill_struct(PressureForceArgs(), a, keep)
+
+
+def remapping_cs(d):
+    return _scalars(RemappingCS(), d)

@@ -58,6 +58,21 @@ int oracle_bt_mass_source(const mom6cu_domain* dom, const mom6cu_grid* G, const 
 int oracle_pressure_force(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
                           const mom6cu_pressureforce_cs* CS, const mom6cu_pressureforce_args* a, int nthreads);
 
+/* ALE remapping (MOM_remapping.F90, PLM/PPM_functions.F90, regrid_edge_values.F90, MOM_ALE.F90): see remap.cpp.
+ * PINNED by the reference's known-answer vectors (tests/test_oracle_remap_kat.py). */
+int oracle_remapping_core_h(const mom6cu_remapping_cs* CS, int n0, const double* h0, const double* u0, int n1, const double* h1,
+                            double* u1, double* net_err);
+int oracle_remap_intersect(int n0, const double* h0, int n1, const double* h1, double* h_sub, double* h0_eff, int* isrc_start,
+                           int* isrc_end, int* isrc_max, int* itgt_start, int* itgt_end, int* isub_src);
+int oracle_remap_reconstruct(int which, int N, const double* h, const double* u, double h_neglect, double* E, double* coefs);
+int oracle_remap_plm_sub(int om4, int n0, const double* h0, const double* u0, int n1, const double* h1, double h_neglect, double* u_sub,
+                         double* u1);
+int oracle_ale_remap_scalar(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_remapping_cs* CS, const double* h_old,
+                            const double* h_new, double* field, double conc_underflow, int nthreads);
+int oracle_ale_remap_set_h_vel(const mom6cu_domain* dom, const mom6cu_grid* G, const double* h_new, double* h_u, double* h_v);
+int oracle_ale_remap_velocities(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_remapping_cs* CS, const double* h_old_u,
+                                const double* h_old_v, const double* h_new_u, const double* h_new_v, double* u, double* v, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,3 +142,92 @@ def pressure_force(dom, grid, gv, cs, args, nthreads=1):
     if rc != 0:
         raise RuntimeError(f"oracle_pressure_force rc={rc}")
     return rc
+
+
+# ---- ALE remapping (oracle/remap.cpp)
+def _dp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def remapping_core_h(cs, h0, u0, h1):
+    """oracle_remapping_core_h: remapping_core_h (MOM_remapping.F90:234) for one column; returns (u1, net_err)."""
+    import numpy as np
+    from mom6_b200 import marshal
+    lib = load()
+    h0, u0, h1 = (np.ascontiguousarray(x, dtype=np.float64) for x in (h0, u0, h1))
+    u1 = np.zeros(len(h1)); err = C.c_double(0.0)
+    lib.oracle_remapping_core_h.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    c = marshal.remapping_cs(cs)
+    lib.oracle_remapping_core_h(C.byref(c), len(h0), _dp(h0), _dp(u0), len(h1), _dp(h1), _dp(u1), C.byref(err))
+    return u1, err.value
+
+
+def remap_intersect(h0, h1):
+    """intersect_src_tgt_grids (MOM_remapping.F90:642): returns a dict of its 8 outputs."""
+    import numpy as np
+    lib = load()
+    h0, h1 = (np.ascontiguousarray(x, dtype=np.float64) for x in (h0, h1))
+    n0, n1 = len(h0), len(h1)
+    o = dict(h_sub=np.zeros(n0 + n1 + 1), h0_eff=np.zeros(n0), isrc_start=np.zeros(n0, np.int32), isrc_end=np.zeros(n0, np.int32),
+             isrc_max=np.zeros(n0, np.int32), itgt_start=np.zeros(n1, np.int32), itgt_end=np.zeros(n1, np.int32),
+             isub_src=np.zeros(n0 + n1 + 1, np.int32))
+    lib.oracle_remap_intersect.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 8
+    lib.oracle_remap_intersect(n0, _dp(h0), n1, _dp(h1), *[_dp(o[k]) for k in ("h_sub", "h0_eff", "isrc_start", "isrc_end", "isrc_max",
+                                                                               "itgt_start", "itgt_end", "isub_src")])
+    return o
+
+
+RECON = dict(PCM=0, PLM=1, PLM_extrap=2, edge_h4=3, PPM=4, edge_ih4=5)
+
+
+def remap_reconstruct(which, h, u, h_neglect=1.0e-30, E=None):
+    """One of the reconstruction routines (see oracle_remap_reconstruct); returns (E[2,N], coefs[3,N])."""
+    import numpy as np
+    lib = load()
+    h, u = (np.ascontiguousarray(x, dtype=np.float64) for x in (h, u))
+    N = len(h)
+    Ea = np.zeros((2, N)) if E is None else np.ascontiguousarray(np.array(E, dtype=np.float64).reshape(2, N))
+    co = np.zeros((3, N))
+    lib.oracle_remap_reconstruct.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    rc = lib.oracle_remap_reconstruct(RECON[which], N, _dp(h), _dp(u), h_neglect, _dp(Ea), _dp(co))
+    assert rc == 0
+    return Ea, co
+
+
+def remap_plm_sub(om4, h0, u0, h1, h_neglect=1.0e-30):
+    """PLM + boundary extrapolation, remap_src_to_sub_grid[_om4], remap_sub_to_tgt_grid_om4; returns (u_sub, u1)."""
+    import numpy as np
+    lib = load()
+    h0, u0, h1 = (np.ascontiguousarray(x, dtype=np.float64) for x in (h0, u0, h1))
+    us = np.zeros(len(h0) + len(h1) + 1); u1 = np.zeros(len(h1))
+    lib.oracle_remap_plm_sub.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    lib.oracle_remap_plm_sub(int(om4), len(h0), _dp(h0), _dp(u0), len(h1), _dp(h1), h_neglect, _dp(us), _dp(u1))
+    return us, u1
+
+
+def ale_remap_scalar(dom, grid, cs, h_old, h_new, field, conc_underflow=0.0, nthreads=1):
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); c = marshal.remapping_cs(cs)
+    lib.oracle_ale_remap_scalar.argtypes = [C.c_void_p] * 6 + [C.c_double, C.c_int]
+    return lib.oracle_ale_remap_scalar(C.byref(dom), C.byref(g), C.byref(c), _dp(h_old), _dp(h_new), _dp(field), conc_underflow, nthreads)
+
+
+def ale_remap_set_h_vel(dom, grid, h_new, h_u, h_v):
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    lib.oracle_ale_remap_set_h_vel.argtypes = [C.c_void_p] * 5
+    return lib.oracle_ale_remap_set_h_vel(C.byref(dom), C.byref(g), _dp(h_new), _dp(h_u), _dp(h_v))
+
+
+def ale_remap_velocities(dom, grid, cs, h_old_u, h_old_v, h_new_u, h_new_v, u, v, nthreads=1):
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); c = marshal.remapping_cs(cs)
+    lib.oracle_ale_remap_velocities.argtypes = [C.c_void_p] * 9 + [C.c_int]
+    return lib.oracle_ale_remap_velocities(C.byref(dom), C.byref(g), C.byref(c), _dp(h_old_u), _dp(h_old_v), _dp(h_new_u), _dp(h_new_v),
+                                           _dp(u), _dp(v), nthreads)
