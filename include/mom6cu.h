@@ -76,6 +76,8 @@ int mom6cu_sync(mom6cu_ctx* ctx);
 /* Device-time (ms) of the most recent compute entry, measured with CUDA
  * events on the launching stream (excludes host<->device staging). */
 double mom6cu_last_kernel_ms(const mom6cu_ctx* ctx);
+/* passes made by the most recent iterative entry (mom6cu_advect_tracer: the itt loop, MOM_tracer_advect.F90:222-340) */
+int mom6cu_last_iterations(const mom6cu_ctx* ctx);
 /* Sum of the device times of all repetitions of the most recent *_resident call. */
 double mom6cu_total_kernel_ms(const mom6cu_ctx* ctx);
 
@@ -283,6 +285,35 @@ int mom6cu_ale_remap_velocities(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, 
  * MOM_remapping.F90:234): h0,u0 are (ncol,n0), h1,u1 (ncol,n1), row-major, host or device. */
 int mom6cu_remapping_core_h(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, int ncol, int n0, const double* h0, const double* u0,
                             int n1, const double* h1, double* u1);
+
+/* ------------------------------------------------------------ advect_tracer */
+/* tracer_advect_CS, src/tracer/MOM_tracer_advect.F90:32-41; schemes MOM_tracer_advect_schemes.F90:10-12 */
+#define MOM6CU_ADVECT_PLM 0
+#define MOM6CU_ADVECT_PPMH3 1
+#define MOM6CU_ADVECT_PPM 2
+typedef struct mom6cu_tracer_advect_cs {
+  double dt;                  /* CS%dt, the baroclinic time step (sets max_iter, :176) */
+  int default_advect_scheme;  /* TRACER_ADVECTION_SCHEME */
+  int useHuynhStencilBug;
+} mom6cu_tracer_advect_cs;
+/* advect_tracer(h_end, uhtr, vhtr, OBC, dt, G, GV, US, CS, Reg, x_first_in, vol_prev, max_iter_in, update_vol_prev,
+ * uhr_out, vhr_out)  MOM_tracer_advect.F90:53-54.  Reg is passed as ntr field pointers with their per-tracer
+ * advect_scheme (< 0: CS default) and conc_underflow; OBCs are rejected; the flux diagnostics (ad_x, ad_y, ad2d_*,
+ * advection_xy) are not produced. */
+typedef struct mom6cu_advect_tracer_args {
+  const double *h_end, *uhtr, *vhtr; /* 3-D h, u, v */
+  double dt;
+  int ntr;
+  double* const* tr;            /* ntr 3-D h fields, in/out (halos valid on entry, as in the reference) */
+  const int* advect_scheme;     /* ntr, may be NULL (all default) */
+  const double* conc_underflow; /* ntr, may be NULL */
+  int x_first_in;               /* -1 absent, else 0/1 */
+  int max_iter_in;              /* < 0 absent */
+  double* vol_prev;             /* optional 3-D h, in(/out) */
+  int update_vol_prev;
+  double *uhr_out, *vhr_out;    /* optional 3-D u, v out */
+} mom6cu_advect_tracer_args;
+int mom6cu_advect_tracer(mom6cu_ctx* ctx, const mom6cu_tracer_advect_cs* CS, const mom6cu_advect_tracer_args* a);
 
 /* ------------------------------------------------------- halo communication */
 /* The reference's halo API (pass_var / pass_vector / do_group_pass,

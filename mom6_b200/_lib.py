@@ -184,6 +184,19 @@ class RemappingCS(C.Structure):
                [(n, C.c_double) for n in ("h_neglect", "h_neglect_edge")]
 
 
+class TracerAdvectCS(C.Structure):
+    """mom6cu_tracer_advect_cs: tracer_advect_CS (src/tracer/MOM_tracer_advect.F90:32-41)."""
+    _fields_ = [("dt", C.c_double), ("default_advect_scheme", C.c_int), ("useHuynhStencilBug", C.c_int)]
+
+
+class AdvectTracerArgs(C.Structure):
+    """mom6cu_advect_tracer_args: the arguments of advect_tracer (MOM_tracer_advect.F90:53-54)."""
+    _fields_ = [("h_end", C.c_void_p), ("uhtr", C.c_void_p), ("vhtr", C.c_void_p), ("dt", C.c_double), ("ntr", C.c_int),
+                ("tr", C.POINTER(C.c_void_p)), ("advect_scheme", C.POINTER(C.c_int)), ("conc_underflow", C.c_void_p),
+                ("x_first_in", C.c_int), ("max_iter_in", C.c_int), ("vol_prev", C.c_void_p), ("update_vol_prev", C.c_int),
+                ("uhr_out", C.c_void_p), ("vhr_out", C.c_void_p)]
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
@@ -227,6 +240,7 @@ def bind(lib):
     lib.mom6cu_launch_count.restype = C.c_longlong
     lib.mom6cu_sync.argtypes = [vp]
     lib.mom6cu_last_kernel_ms.argtypes = [vp]
+    lib.mom6cu_last_iterations.argtypes = [vp]
     lib.mom6cu_last_kernel_ms.restype = C.c_double
     lib.mom6cu_total_kernel_ms.argtypes = [vp]
     lib.mom6cu_total_kernel_ms.restype = C.c_double
@@ -252,6 +266,7 @@ def bind(lib):
     lib.mom6cu_ale_remap_set_h_vel.argtypes = [vp, vp, vp, vp]
     lib.mom6cu_ale_remap_velocities.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, vp, vp, vp, vp]
     lib.mom6cu_remapping_core_h.argtypes = [vp, C.POINTER(RemappingCS), C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.mom6cu_advect_tracer.argtypes = [vp, C.POINTER(TracerAdvectCS), C.POINTER(AdvectTracerArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

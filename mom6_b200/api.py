@@ -6,6 +6,8 @@ point of include/mom6cu.h and carries the name of the reference subroutine it st
 """
 import ctypes as C
 
+import numpy as np
+
 from . import _lib
 from ._lib import Domain, BtTimeloopArgs, fill_struct
 
@@ -180,6 +182,52 @@ def _ctx_methods():
         keep = []
         return self._check(self.lib.mom6cu_pressure_force(self._h, C.byref(marshal.pressureforce_args(args, keep))))
 
+    def _p(x):
+        """Address of a numpy array / Plane / None for a plain-pointer argument."""
+        if x is None:
+            return None
+        if isinstance(x, Plane):
+            return x.ptr
+        if isinstance(x, np.ndarray):
+            if not x.flags["C_CONTIGUOUS"] or x.dtype != np.float64:
+                raise Mom6cuError("array arguments must be C-contiguous float64")
+            return x.ctypes.data
+        return int(x)
+
+    def ale_remap_tracers(self, cs, h_old, h_new, tracers, conc_underflow=None):
+        """ALE_remap_tracers, src/ALE/MOM_ALE.F90:760 (the column loop :806-826) for a list of h-point fields."""
+        n = len(tracers)
+        ptrs = (C.c_void_p * max(n, 1))(*[_p(t) for t in tracers])
+        cu = None if conc_underflow is None else np.ascontiguousarray(conc_underflow, dtype=np.float64)
+        return self._check(self.lib.mom6cu_ale_remap_tracers(self._h, C.byref(marshal.remapping_cs(cs)), _p(h_old), _p(h_new), n, ptrs,
+                                                             None if cu is None else cu.ctypes.data))
+
+    def ale_remap_set_h_vel(self, h_new, h_u, h_v):
+        """ALE_remap_set_h_vel, MOM_ALE.F90:882."""
+        return self._check(self.lib.mom6cu_ale_remap_set_h_vel(self._h, _p(h_new), _p(h_u), _p(h_v)))
+
+    def ale_remap_velocities(self, cs, h_old_u, h_old_v, h_new_u, h_new_v, u, v):
+        """ALE_remap_velocities, MOM_ALE.F90:1089."""
+        return self._check(self.lib.mom6cu_ale_remap_velocities(self._h, C.byref(marshal.remapping_cs(cs)), _p(h_old_u), _p(h_old_v),
+                                                                _p(h_new_u), _p(h_new_v), _p(u), _p(v)))
+
+    def remapping_core_h(self, cs, h0, u0, h1):
+        """remapping_core_h, MOM_remapping.F90:234, on a batch of columns: h0, u0 (ncol, n0); h1 (ncol, n1) -> u1 (ncol, n1)."""
+        h0, u0, h1 = (np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64) for x in (h0, u0, h1))
+        u1 = np.zeros_like(h1)
+        self._check(self.lib.mom6cu_remapping_core_h(self._h, C.byref(marshal.remapping_cs(cs)), h0.shape[0], h0.shape[1], _p(h0), _p(u0),
+                                                     h1.shape[1], _p(h1), _p(u1)))
+        return u1
+
+    def advect_tracer(self, cs, args):
+        """advect_tracer, src/tracer/MOM_tracer_advect.F90:53; returns the number of passes made."""
+        keep = []
+        self._check(self.lib.mom6cu_advect_tracer(self._h, C.byref(marshal.tracer_advect_cs(cs)), C.byref(marshal.advect_tracer_args(args, keep))))
+        return int(self.lib.mom6cu_last_iterations(self._h))
+
+    setattr(Context, "advect_tracer", advect_tracer)
+    for f in (ale_remap_tracers, ale_remap_set_h_vel, ale_remap_velocities, remapping_core_h):
+        setattr(Context, f.__name__, f)
     for f in (set_grid, set_vgrid, set_cs_continuity, continuity, set_unit_scale, set_cs_coriolisadv, coradcalc,
               set_cs_hor_visc, horizontal_viscosity, btstep, btcalc, bt_mass_source, set_cs_pressureforce, pressure_force):
         setattr(Context, f.__name__, f)

@@ -28,7 +28,6 @@ using m6::Geom;
 using m6::fmax2;
 using m6::fmin2;
 
-int m6_halo_update(mom6cu_ctx* c, double* const* fields, const int* staggers, int nfields, int wide, int nk);  // halo.cu
 
 namespace {
 

@@ -194,6 +194,7 @@ int mom6cu_last_error(const mom6cu_ctx* c, char* b, size_t len) {
 
 long long mom6cu_launch_count(const mom6cu_ctx* c) { return c ? c->launches : 0; }
 double mom6cu_last_kernel_ms(const mom6cu_ctx* c) { return c ? c->last_ms : 0.0; }
+int mom6cu_last_iterations(const mom6cu_ctx* c) { return c ? c->last_iterations : 0; }
 double mom6cu_total_kernel_ms(const mom6cu_ctx* c) { return c ? c->total_ms : 0.0; }
 
 double* mom6cu_plane_alloc(mom6cu_ctx* c, const char* name, int nk) {

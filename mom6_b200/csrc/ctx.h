@@ -22,6 +22,7 @@ struct mom6cu_ctx {
   double last_ms = 0.0;   // device time of the most recent compute entry / repetition
   double total_ms = 0.0;  // summed over the repetitions of the most recent resident call
   long long launches = 0;
+  int last_iterations = 0;  // passes made by the most recent iterative entry (advect_tracer)
   int warnings = 0;
   char err[1024] = {0};
   std::map<std::string, double*> bufs;
@@ -78,6 +79,10 @@ struct mom6cu_ctx {
 // extents of a Fortran array of the given stagger on G (wide=0) or the wide domain
 void m6_extent(const mom6cu_ctx* c, int stagger, int wide, int* ilo, int* ihi, int* jlo, int* jhi);
 bool m6_is_device_ptr(const void* p);
+// halo update of nfields unified planes (nk levels each): cyclic wrap on one tile, NCCL between tiles (halo.cu)
+int m6_halo_update(mom6cu_ctx* c, double* const* fields, const int* staggers, int nfields, int wide, int nk);
+// max over ranks of one host int (sum_across_PEs of a flag, MOM_coms.F90); identity on one rank
+int m6_allreduce_max_int(mom6cu_ctx* c, int* v);
 // copy a Fortran-shaped (host or device) array into / out of unified planes
 int m6_up(mom6cu_ctx* c, const double* src, int stagger, int wide, int nk, double* dst);
 int m6_down(mom6cu_ctx* c, const double* src_plane, int stagger, int wide, int nk, double* dst);

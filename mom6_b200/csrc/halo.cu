@@ -57,7 +57,13 @@ int m6_halo_nccl(mom6cu_ctx* c, double* const* fields, const int* staggers, int 
 // memory domain (wide=1: the barotropic wide-halo domain; wide=0: G's).
 int m6_halo_update(mom6cu_ctx* c, double* const* fields, const int* staggers, int nfields, int wide, int nk) {
   const mom6cu_domain& d = c->dom;
-  if (d.npi * d.npj > 1) return m6_halo_nccl(c, fields, staggers, nfields, wide, nk, -1);
+  if (d.npi * d.npj > 1) {  // one message set per group of at most 8 fields
+    for (int f0 = 0; f0 < nfields; f0 += 8) {
+      const int rc = m6_halo_nccl(c, fields + f0, staggers + f0, nfields - f0 < 8 ? nfields - f0 : 8, wide, nk, -1);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   const Geom& G = c->g;
   for (int f = 0; f < nfields; ++f) {
     int ilo, ihi, jlo, jhi;

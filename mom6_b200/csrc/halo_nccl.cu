@@ -99,6 +99,22 @@ extern "C" int mom6cu_comm_init(mom6cu_ctx* c, const void* id_bytes, int nbytes,
   return 0;
 }
 
+int m6_allreduce_max_int(mom6cu_ctx* c, int* v) {
+  if (c->nranks <= 1) return 0;
+  if (!c->comm) return c->fail(MOM6CU_ERR_NCCL, "multi-rank reduction requested but no communicator is attached");
+  int* d = (int*)c->buf("comm.flag", 2);
+  int* h = (int*)c->host_scratch("comm.flag", 2);
+  if (!d || !h) return MOM6CU_ERR_CUDA;
+  h[0] = *v;
+  M6_CUDA(c, cudaMemcpyAsync(d, h, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  ncclResult_t r = ncclAllReduce(d, d, 1, ncclInt, ncclMax, (ncclComm_t)c->comm, c->stream);
+  if (r != ncclSuccess) return c->fail(MOM6CU_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r));
+  M6_CUDA(c, cudaMemcpyAsync(h, d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  *v = h[0];
+  return 0;
+}
+
 extern "C" int mom6cu_comm_destroy(mom6cu_ctx* c) {
   if (c && c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
   return 0;

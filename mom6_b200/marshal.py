@@ -1,9 +1,11 @@
 """dict -> ctypes struct marshalling shared by the product binding (api.py) and the oracle binding."""
 import ctypes as C
 
+import numpy as np
+
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, fill_struct)
 
 
 def _scalars(struct, d):
@@ -83,3 +85,46 @@ def pressureforce_args(a, keep):
 
 def remapping_cs(d):
     return _scalars(RemappingCS(), d)
+
+
+def _addr(x):
+    if x is None:
+        return None
+    if hasattr(x, "ptr") and isinstance(getattr(x, "ptr"), int):   # api.Plane
+        return x.ptr
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"] or x.dtype != np.float64:
+            raise ValueError("array arguments must be C-contiguous float64")
+        return x.ctypes.data
+    return int(x)
+
+
+def tracer_advect_cs(d):
+    return _scalars(TracerAdvectCS(), d)
+
+
+def advect_tracer_args(a, keep):
+    """a: dict(h_end, uhtr, vhtr, dt, tr=[...], advect_scheme=None, conc_underflow=None, x_first_in=None, max_iter_in=None,
+    vol_prev=None, update_vol_prev=False, uhr_out=None, vhr_out=None)."""
+    s = AdvectTracerArgs()
+    s.h_end, s.uhtr, s.vhtr = _addr(a["h_end"]), _addr(a["uhtr"]), _addr(a["vhtr"])
+    s.dt = float(a["dt"])
+    tr = a["tr"]
+    s.ntr = len(tr)
+    ptrs = (C.c_void_p * max(len(tr), 1))(*[_addr(t) for t in tr])
+    keep.append(ptrs)
+    s.tr = C.cast(ptrs, C.POINTER(C.c_void_p))
+    if a.get("advect_scheme") is not None:
+        sch = (C.c_int * max(len(tr), 1))(*[int(x) for x in a["advect_scheme"]])
+        keep.append(sch)
+        s.advect_scheme = C.cast(sch, C.POINTER(C.c_int))
+    if a.get("conc_underflow") is not None:
+        cu = np.ascontiguousarray(a["conc_underflow"], dtype=np.float64)
+        keep.append(cu)
+        s.conc_underflow = cu.ctypes.data
+    s.x_first_in = -1 if a.get("x_first_in") is None else int(bool(a["x_first_in"]))
+    s.max_iter_in = -1 if a.get("max_iter_in") is None else int(a["max_iter_in"])
+    s.vol_prev = _addr(a.get("vol_prev"))
+    s.update_vol_prev = int(bool(a.get("update_vol_prev", False)))
+    s.uhr_out, s.vhr_out = _addr(a.get("uhr_out")), _addr(a.get("vhr_out"))
+    return s

@@ -780,3 +780,61 @@ def pressureforce_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=
     if with_eta:
         a["eta"] = fidx.new(dom, "h").a
     return dom, grid, gv, cs, a
+
+
+def remap_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, ntr=2, kind="zstar", **cs_over):
+    """ALE remapping inputs (MOM_ALE.F90:760-925, :1089): h_old (Z*-like with vanished layers), h_new (kind 'zstar': the
+    same column depth redistributed on a perturbed grid; 'uniform': equal layers), ntr tracers, u, v."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 505)
+    h_old = st["h"]
+    tot = h_old.sum(axis=0, keepdims=True)
+    if kind == "uniform":
+        w = np.ones_like(h_old)
+    else:
+        w = h_old * (1.0 + 0.3 * r.uniform(-1, 1, size=h_old.shape)) + 1.0e-3 * tot * (r.uniform(0, 1, size=h_old.shape) > 0.7)
+    h_new = np.ascontiguousarray(w * (tot / w.sum(axis=0, keepdims=True)))
+    zmid = -(np.cumsum(h_old, axis=0) - 0.5 * h_old)
+    tr = [np.ascontiguousarray(20.0 * np.exp(zmid / 1000.0) + 0.05 * r.uniform(-1, 1, size=h_old.shape)),
+          np.ascontiguousarray(35.0 + 0.5 * np.exp(zmid / 500.0) + 0.01 * r.uniform(-1, 1, size=h_old.shape))]
+    for m in range(2, ntr):
+        tr.append(np.ascontiguousarray(r.uniform(0, 1, size=h_old.shape) * 10.0 ** r.integers(-30, 1, size=h_old.shape)))
+    cs = dict(remapping_scheme=4, boundary_extrapolation=0, force_bounds_in_subcell=0, force_bounds_in_target=1,
+              om4_remap_via_sub_cells=1, answer_date=20190101, h_neglect=1.0e-30, h_neglect_edge=1.0e-30)   # OM4 defaults: PPM_H4
+    cs.update(cs_over)
+    return dom, grid, cs, dict(h_old=h_old, h_new=h_new, tr=tr[:ntr], u=st["u"], v=st["v"])
+
+
+def advect_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, ntr=2, dt=3600.0, dt_dyn=900.0,
+                  cfl=0.7, scheme=0, **over):
+    """advect_tracer inputs (MOM_tracer_advect.F90:53): transports accumulated over dt, each face moving up to cfl/4 of the
+    upwind cell volume (cfl < 1: no cell is drained; cfl > 2: the flux limiter of :513-542 needs several passes and some
+    cells are drained to the h_end floor), h_end consistent with them, T/S-like tracers plus random ones.  Returns dom, grid, gv, cs, args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 606)
+    h = st["h"]
+    vol = h * grid["areaT"][None]
+    # transports as a fraction of the upwind cell volume, so CFL is controlled everywhere (thin layers included)
+    fu = cfl * st["u"] / max(np.abs(st["u"]).max(), 1e-30)
+    fv = cfl * st["v"] / max(np.abs(st["v"]).max(), 1e-30)
+    uhtr = fidx.new(dom, "u", nk=nk).a; vhtr = fidx.new(dom, "v", nk=nk).a
+    uhtr[:, :, 1:-1] = fu[:, :, 1:-1] * np.where(fu[:, :, 1:-1] > 0, vol[:, :, :-1], vol[:, :, 1:]) * 0.25
+    vhtr[:, 1:-1, :] = fv[:, 1:-1, :] * np.where(fv[:, 1:-1, :] > 0, vol[:, :-1, :], vol[:, 1:, :]) * 0.25
+    uhtr *= grid["mask2dCu"][None]; vhtr *= grid["mask2dCv"][None]
+    div = np.zeros_like(h)
+    div[:, 1:-1, 1:-1] = (uhtr[:, 1:-1, 2:-1] - uhtr[:, 1:-1, 1:-2]) + (vhtr[:, 2:-1, 1:-1] - vhtr[:, 1:-2, 1:-1])
+    h_end = np.ascontiguousarray(np.maximum(h - div * grid["IareaT"][None], 1.0e-10))
+    zmid = -(np.cumsum(h, axis=0) - 0.5 * h)
+    tr = [np.ascontiguousarray(20.0 * np.exp(zmid / 1000.0) + 2.0 * r.uniform(-1, 1, size=h.shape)),
+          np.ascontiguousarray(35.0 + 0.5 * r.uniform(-1, 1, size=h.shape))]
+    for m in range(2, ntr):
+        tr.append(np.ascontiguousarray(r.uniform(0, 1, size=h.shape) * (r.uniform(0, 1, size=h.shape) > 0.5)))
+    cs = dict(dt=dt_dyn, default_advect_scheme=scheme, useHuynhStencilBug=0)
+    a = dict(h_end=h_end, uhtr=uhtr, vhtr=vhtr, dt=dt, tr=tr[:ntr])
+    a.update(over)
+    return dom, grid, gv, cs, a

@@ -231,3 +231,17 @@ def ale_remap_velocities(dom, grid, cs, h_old_u, h_old_v, h_new_u, h_new_v, u, v
     lib.oracle_ale_remap_velocities.argtypes = [C.c_void_p] * 9 + [C.c_int]
     return lib.oracle_ale_remap_velocities(C.byref(dom), C.byref(g), C.byref(c), _dp(h_old_u), _dp(h_old_v), _dp(h_new_u), _dp(h_new_v),
                                            _dp(u), _dp(v), nthreads)
+
+
+def advect_tracer(dom, grid, gv, cs, a):
+    """oracle_advect_tracer: advect_tracer (MOM_tracer_advect.F90:53); returns the number of passes made."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); c = marshal.tracer_advect_cs(cs); st = marshal.advect_tracer_args(a, keep)
+    it = C.c_int(0)
+    lib.oracle_advect_tracer.argtypes = [C.c_void_p] * 6
+    rc = lib.oracle_advect_tracer(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(st), C.byref(it))
+    if rc:
+        raise RuntimeError(f"oracle_advect_tracer rc={rc}")
+    return it.value

@@ -10,7 +10,7 @@ ni = int(sys.argv[2]) if len(sys.argv) > 2 else 1440
 nj = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
 nk = int(sys.argv[4]) if len(sys.argv) > 4 else 75
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-BYTES = {"continuity": 96, "corad": 56, "hor_visc": 56, "pgf": 48}
+BYTES = {"continuity": 96, "corad": 56, "hor_visc": 56, "pgf": 48, "remap": 32, "btstep": 136}
 t0 = time.time()
 if stage == "corad":
     dom, grid, gv, cs, a = synthetic.coradcalc_inputs(ni, nj, nk, land_blocks=40)
@@ -18,6 +18,13 @@ elif stage == "continuity":
     dom, grid, gv, cs, a = synthetic.continuity_inputs(ni, nj, nk, land_blocks=40)
 elif stage == "hor_visc":
     dom, grid, gv, cs, a = synthetic.hor_visc_inputs(ni, nj, nk, land_blocks=40)
+elif stage == "pgf":
+    dom, grid, gv, cs, a = synthetic.pressureforce_inputs(ni, nj, nk, land_blocks=40)
+elif stage == "remap":
+    dom, grid, cs, a = synthetic.remap_inputs(ni, nj, nk, land_blocks=40)
+    gv = synthetic.make_vgrid()
+elif stage == "btstep":
+    dom, grid, gv, cs, a = synthetic.btstep_inputs(ni, nj, nk, whalo=10, land_blocks=40)
 else:
     raise SystemExit("unknown stage " + stage)
 print(f"inputs built in {time.time()-t0:.1f}s", flush=True)
@@ -29,6 +36,12 @@ elif stage == "continuity":
     ctx.set_cs_continuity(cs); run = ctx.continuity
 elif stage == "hor_visc":
     ctx.set_cs_hor_visc(cs); run = ctx.horizontal_viscosity
+elif stage == "pgf":
+    ctx.set_cs_pressureforce(cs); run = ctx.pressure_force
+elif stage == "remap":   # one tracer per call: 32 B/cell = h_old + h_new + tracer in + tracer out
+    run = lambda a: ctx.ale_remap_tracers(cs, a["h_old"], a["h_new"], [a["tr"][0].copy()])
+elif stage == "btstep":
+    run = lambda a: ctx.btstep(cs, a)
 for r in range(reps):
     run(a)
     ms = ctx.last_kernel_ms
