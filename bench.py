@@ -31,11 +31,11 @@ NI, NJ, NK = 1440, 1080, 75
 SAMPLE = (90, 135)              # CPU-baseline tile: 1440x1080 over a 16x8 rank layout, all 75 layers
 BT_BYTES_PER_PT_SUBSTEP = 552   # 69 fp64 operands on the BT_cont path
 # stage -> (calls per baroclinic step [MOM_dynamics_split_RK2.F90 line], algorithmic bytes per cell per call [SURVEY 8d])
-STEP = [("continuity", 3, 96), ("btcalc", 1, 32), ("bt_mass_source", 2, 8), ("btstep", 2, 136), ("coradcalc", 2, 56),
+STEP = [("pressure_force", 1, 48), ("continuity", 3, 96), ("btcalc", 1, 32), ("bt_mass_source", 2, 8), ("btstep", 2, 136), ("coradcalc", 2, 56),
         ("horizontal_viscosity", 1, 40)]
-STAGES = ["continuity_PPM x3 (:646,:781,:1043)", "btcalc x1 (:650)", "bt_mass_source x2 (:629,:821)",
+STAGES = ["PressureForce_FV_Bouss x1, Wright EOS analytic (:503)", "continuity_PPM x3 (:646,:781,:1043)", "btcalc x1 (:650)", "bt_mass_source x2 (:629,:821)",
           "btstep x2 incl. the 68-substep barotropic loop (:673,:939)", "CorAdCalc x2 (:895,:1090)", "horizontal_viscosity x1 (:886)"]
-MISSING = ["PressureForce_FV x1 (:503)", "vertvisc_coef/vertvisc/vertvisc_remnant x3 (:609,:754,:1003)", "set_viscous_ML (:602)",
+MISSING = ["vertvisc_coef/vertvisc/vertvisc_remnant x3 (:609,:754,:1003)", "set_viscous_ML (:602)",
            "elementwise glue up/vp/u/v/h_av/uhtr (:565-1082)", "inter-stage 3-D halo updates (:616-1056)"]
 
 
@@ -98,7 +98,7 @@ STAGGER = dict(u="u", v="v", hin="h", h="h", uh="u", vh="v", visc_rem_u="u", vis
                uhbtav="u", vhbtav="v", uh0="u", vh0="v", u_uh0="u", v_vh0="v", etaav="h", h_u="u", h_v="v", frhatu="u",
                frhatv="v", bathyT="h", eta="h", eta_cor="h", FA_u_EE="u", FA_u_E0="u", FA_u_W0="u", FA_u_WW="u", uBT_WW="u",
                uBT_EE="u", FA_v_NN="v", FA_v_N0="v", FA_v_S0="v", FA_v_SS="v", vBT_SS="v", vBT_NN="v", IDatu="u", IDatv="v",
-               eta_cor_bound="h", ubtav="u", vbtav="v", IareaT="h", IareaT_OBCmask="h", IdxCu="u", IdyCv="v", q_D="q",
+               T="h", S="h", PFu="u", PFv="v", eta_cor_bound="h", ubtav="u", vbtav="v", IareaT="h", IareaT_OBCmask="h", IdxCu="u", IdyCv="v", q_D="q",
                D_u_Cor="u", D_v_Cor="v", ua_polarity="h", va_polarity="h", OBCmask_u="u", OBCmask_v="v")
 WIDE = {"IareaT", "IareaT_OBCmask", "IdxCu", "IdyCv", "q_D", "D_u_Cor", "D_v_Cor", "ua_polarity", "va_polarity", "OBCmask_u", "OBCmask_v"}
 
@@ -153,6 +153,8 @@ def oracle_step(orc, dom, grid, gv, stages, cores):
                 orc.horizontal_viscosity(dom, grid, gv, cs, a, nthreads=cores)
             elif name == "btstep":
                 orc.btstep(dom, grid, gv, cs, a, nthreads=cores)
+            elif name == "pressure_force":
+                orc.pressure_force(dom, grid, gv, cs, a, nthreads=cores)
             elif name == "btcalc":
                 orc.btcalc(dom, grid, gv, a, nthreads=cores)
             elif name == "bt_mass_source":
@@ -245,7 +247,7 @@ def main():
         ctx.attach_comm(dist)
     ctx.set_grid(grid); ctx.set_vgrid(gv)
     ctx.set_cs_continuity(stages["continuity"][0]); ctx.set_cs_coriolisadv(stages["coradcalc"][0])
-    ctx.set_cs_hor_visc(stages["horizontal_viscosity"][0])
+    ctx.set_cs_hor_visc(stages["horizontal_viscosity"][0]); ctx.set_cs_pressureforce(stages["pressure_force"][0])
     resident, nplanes = make_resident(ctx, stages, NK)
 
     def barrier():
@@ -273,7 +275,7 @@ def main():
         e2e_steps = 1
         OUT = {"continuity": ("h", "uh", "vh", "u_cor", "v_cor"), "coradcalc": ("CAu", "CAv"), "horizontal_viscosity": ("diffu", "diffv"),
                "btstep": ("accel_layer_u", "accel_layer_v", "eta_out", "uhbtav", "vhbtav", "etaav"), "btcalc": ("frhatu", "frhatv"),
-               "bt_mass_source": ("eta_cor",)}
+               "bt_mass_source": ("eta_cor",), "pressure_force": ("PFu", "PFv", "pbce", "eta")}
         for name, calls, _ in STEP:
             cs, a = stages[name]
             arrs = [v for v in a.values() if isinstance(v, np.ndarray)] + [vv for v in a.values() if isinstance(v, dict) for vv in v.values() if isinstance(vv, np.ndarray)]

@@ -286,6 +286,64 @@ int mom6cu_ale_remap_velocities(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, 
 int mom6cu_remapping_core_h(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, int ncol, int n0, const double* h0, const double* u0,
                             int n1, const double* h1, double* u1);
 
+/* ---------------------------------------------------------- vertical friction */
+/* vertvisc_CS members read by vertvisc_coef / vertvisc / vertvisc_remnant
+ * (src/parameterizations/vertical/MOM_vert_friction.F90:48-170).  Frozen: answer_date >= 20190101 (I_amax = 0),
+ * Boussinesq (thickness_to_dz: dz = H_to_Z*h, MOM_interface_heights.F90:939; find_ustar = forces%ustar), GV%nkml = 0,
+ * DYNAMIC_VISCOUS_ML off, no GL90, no ice shelves, no OBCs, no Stokes mixing / fpmix; the a_u/h_u diagnostics are not
+ * produced.  Set `unsupported` when the host configuration enables any of those. */
+typedef struct mom6cu_vertvisc_cs {
+  int bottomdraglaw, harmonic_visc, direct_stress, fixed_LOTW_ML, apply_LOTW_floor, dynamic_viscous_ML, nkml, answer_date,
+      unsupported;
+  double Hbbl, Kv, Kv_extra_bbl, Kvml_invZ2, Hmix, Hmix_stress, harm_BL_val, vonKar, vel_underflow;
+  double dZ_subroundoff; /* GV%dZ_subroundoff */
+} mom6cu_vertvisc_cs;
+int mom6cu_set_cs_vertvisc(mom6cu_ctx* ctx, const mom6cu_vertvisc_cs* CS);
+/* vertvisc_coef(u, v, h, dz, forces, visc, tv, dt, G, GV, US, CS, OBC, VarMix)  MOM_vert_friction.F90:1357: sets the
+ * resident CS%a_u, CS%a_v (nk+1 interfaces) and CS%h_u, CS%h_v (nk layers). */
+typedef struct mom6cu_vertvisc_coef_args {
+  const double *u, *v, *h;                                       /* 3-D u, v, h */
+  const double *Kv_bbl_u, *Kv_bbl_v, *bbl_thick_u, *bbl_thick_v; /* visc%, 2-D u / v (bottomdraglaw) */
+  const double* Kv_shear;    /* visc%Kv_shear, h-points, nk+1 interfaces; NULL if not associated */
+  const double* Kv_shear_Bu; /* visc%Kv_shear_Bu, q-points, nk+1 interfaces; NULL if not associated */
+  const double* ustar;       /* forces%ustar, 2-D h (LOTW options only) */
+  double dt;
+} mom6cu_vertvisc_coef_args;
+int mom6cu_vertvisc_coef(mom6cu_ctx* ctx, const mom6cu_vertvisc_coef_args* a);
+/* copies of the resident coupling coefficients (tests / diagnostics): a_u, a_v are 3-D u / v with nk+1 levels, h_u, h_v nk */
+int mom6cu_vertvisc_get_coef(mom6cu_ctx* ctx, double* a_u, double* a_v, double* h_u, double* h_v);
+/* vertvisc(u, v, h, forces, visc, dt, OBC, ADp, CDp, G, GV, US, CS, taux_bot, tauy_bot)  :557 */
+typedef struct mom6cu_vertvisc_args {
+  double *u, *v;               /* 3-D, in/out */
+  const double* h;             /* 3-D (direct_stress only) */
+  const double *taux, *tauy;   /* forces%taux, tauy, 2-D u / v */
+  const double *Ray_u, *Ray_v; /* visc%Ray_u/v 3-D, NULL if not allocated */
+  double dt;
+  double *taux_bot, *tauy_bot; /* optional 2-D out */
+} mom6cu_vertvisc_args;
+int mom6cu_vertvisc(mom6cu_ctx* ctx, const mom6cu_vertvisc_args* a);
+/* vertvisc_remnant(visc, visc_rem_u, visc_rem_v, dt, G, GV, US, CS)  :1229 */
+int mom6cu_vertvisc_remnant(mom6cu_ctx* ctx, const double* Ray_u, const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt);
+
+/* ---------------------------------------------------------------- ALE regrid */
+/* regridding_CS members read by the Z* path (src/ALE/MOM_regridding.F90:49-160) with zlike_CS (coord_zlike.F90:12-22).
+ * Frozen: REGRIDDING_ZSTAR (regrid_consts.F90:14), CS%nk == GV%ke, no ice shelf (frac_shelf_h absent), Boussinesq
+ * (tv%SpV_avg not allocated), no PCM_cell output. */
+#define MOM6CU_REGRIDDING_ZSTAR 2
+typedef struct mom6cu_regridding_cs {
+  int regridding_scheme, nk;
+  double min_thickness;                 /* CS%min_thickness == CS%zlike_CS%min_thickness (set_regrid_params :2425-2440) */
+  double old_grid_weight, depth_of_time_filter_shallow, depth_of_time_filter_deep;
+  double Z_ref;                         /* G%Z_ref */
+  const double* coordinateResolution;   /* (nk), host array [Z] */
+} mom6cu_regridding_cs;
+/* ALE_regrid(G, GV, US, h, h_new, dzRegrid, tv, CS)  src/ALE/MOM_ALE.F90:518-554 -> regridding_main
+ * (MOM_regridding.F90:846-972) -> build_zstar_grid :1257 + calc_h_new_by_dz :1008.  h_new is a 3-D h field,
+ * dzRegrid a 3-D h field with nk+1 levels; both are set on (isc-1:iec+1, jsc-1:jec+1) as in the reference.
+ * A column with a negative thickness, or whose implied new thickness is negative beyond roundoff
+ * (adjust_interface_motion :1808-1817), is FATAL. */
+int mom6cu_ale_regrid(mom6cu_ctx* ctx, const mom6cu_regridding_cs* CS, const double* h, double* h_new, double* dzRegrid);
+
 /* ------------------------------------------------------------ advect_tracer */
 /* tracer_advect_CS, src/tracer/MOM_tracer_advect.F90:32-41; schemes MOM_tracer_advect_schemes.F90:10-12 */
 #define MOM6CU_ADVECT_PLM 0

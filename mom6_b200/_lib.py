@@ -184,6 +184,31 @@ class RemappingCS(C.Structure):
                [(n, C.c_double) for n in ("h_neglect", "h_neglect_edge")]
 
 
+class VertviscCS(C.Structure):
+    """mom6cu_vertvisc_cs: vertvisc_CS members (src/parameterizations/vertical/MOM_vert_friction.F90:48-170)."""
+    _fields_ = [(n, C.c_int) for n in ("bottomdraglaw", "harmonic_visc", "direct_stress", "fixed_LOTW_ML", "apply_LOTW_floor",
+                                       "dynamic_viscous_ML", "nkml", "answer_date", "unsupported")] + \
+               [(n, C.c_double) for n in ("Hbbl", "Kv", "Kv_extra_bbl", "Kvml_invZ2", "Hmix", "Hmix_stress", "harm_BL_val", "vonKar",
+                                          "vel_underflow", "dZ_subroundoff")]
+
+
+class VertviscCoefArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("u", "v", "h", "Kv_bbl_u", "Kv_bbl_v", "bbl_thick_u", "bbl_thick_v", "Kv_shear", "Kv_shear_Bu",
+                                          "ustar")] + [("dt", C.c_double)]
+
+
+class VertviscArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("u", "v", "h", "taux", "tauy", "Ray_u", "Ray_v")] + [("dt", C.c_double)] + \
+               [(n, C.c_void_p) for n in ("taux_bot", "tauy_bot")]
+
+
+class RegriddingCS(C.Structure):
+    """mom6cu_regridding_cs: the regridding_CS members of the Z* path (src/ALE/MOM_regridding.F90:49-160)."""
+    _fields_ = [("regridding_scheme", C.c_int), ("nk", C.c_int), ("min_thickness", C.c_double), ("old_grid_weight", C.c_double),
+                ("depth_of_time_filter_shallow", C.c_double), ("depth_of_time_filter_deep", C.c_double), ("Z_ref", C.c_double),
+                ("coordinateResolution", C.c_void_p)]
+
+
 class TracerAdvectCS(C.Structure):
     """mom6cu_tracer_advect_cs: tracer_advect_CS (src/tracer/MOM_tracer_advect.F90:32-41)."""
     _fields_ = [("dt", C.c_double), ("default_advect_scheme", C.c_int), ("useHuynhStencilBug", C.c_int)]
@@ -266,6 +291,12 @@ def bind(lib):
     lib.mom6cu_ale_remap_set_h_vel.argtypes = [vp, vp, vp, vp]
     lib.mom6cu_ale_remap_velocities.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, vp, vp, vp, vp]
     lib.mom6cu_remapping_core_h.argtypes = [vp, C.POINTER(RemappingCS), C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.mom6cu_set_cs_vertvisc.argtypes = [vp, C.POINTER(VertviscCS)]
+    lib.mom6cu_vertvisc_coef.argtypes = [vp, C.POINTER(VertviscCoefArgs)]
+    lib.mom6cu_vertvisc_get_coef.argtypes = [vp, vp, vp, vp, vp]
+    lib.mom6cu_vertvisc.argtypes = [vp, C.POINTER(VertviscArgs)]
+    lib.mom6cu_vertvisc_remnant.argtypes = [vp, vp, vp, vp, vp, C.c_double]
+    lib.mom6cu_ale_regrid.argtypes = [vp, C.POINTER(RegriddingCS), vp, vp, vp]
     lib.mom6cu_advect_tracer.argtypes = [vp, C.POINTER(TracerAdvectCS), C.POINTER(AdvectTracerArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]

@@ -225,6 +225,35 @@ def _ctx_methods():
         self._check(self.lib.mom6cu_advect_tracer(self._h, C.byref(marshal.tracer_advect_cs(cs)), C.byref(marshal.advect_tracer_args(args, keep))))
         return int(self.lib.mom6cu_last_iterations(self._h))
 
+    def ale_regrid(self, cs, h, h_new, dzRegrid):
+        """ALE_regrid, src/ALE/MOM_ALE.F90:518 (Z* coordinate)."""
+        keep = []
+        return self._check(self.lib.mom6cu_ale_regrid(self._h, C.byref(marshal.regridding_cs(cs, keep)), _p(h), _p(h_new), _p(dzRegrid)))
+
+    def set_cs_vertvisc(self, cs):
+        """vertvisc_init, MOM_vert_friction.F90:2929 (resolved values)."""
+        return self._check(self.lib.mom6cu_set_cs_vertvisc(self._h, C.byref(marshal.vertvisc_cs(cs))))
+
+    def vertvisc_coef(self, args):
+        """vertvisc_coef, MOM_vert_friction.F90:1357: sets the resident CS%a_u, a_v, h_u, h_v."""
+        keep = []
+        return self._check(self.lib.mom6cu_vertvisc_coef(self._h, C.byref(marshal.vertvisc_coef_args(args, keep))))
+
+    def vertvisc_get_coef(self, a_u=None, a_v=None, h_u=None, h_v=None):
+        return self._check(self.lib.mom6cu_vertvisc_get_coef(self._h, _p(a_u), _p(a_v), _p(h_u), _p(h_v)))
+
+    def vertvisc(self, args):
+        """vertvisc, MOM_vert_friction.F90:557."""
+        keep = []
+        return self._check(self.lib.mom6cu_vertvisc(self._h, C.byref(marshal.vertvisc_args(args, keep))))
+
+    def vertvisc_remnant(self, visc_rem_u, visc_rem_v, dt, Ray_u=None, Ray_v=None):
+        """vertvisc_remnant, MOM_vert_friction.F90:1229."""
+        return self._check(self.lib.mom6cu_vertvisc_remnant(self._h, _p(Ray_u), _p(Ray_v), _p(visc_rem_u), _p(visc_rem_v), float(dt)))
+
+    for f in (set_cs_vertvisc, vertvisc_coef, vertvisc_get_coef, vertvisc, vertvisc_remnant):
+        setattr(Context, f.__name__, f)
+    setattr(Context, "ale_regrid", ale_regrid)
     setattr(Context, "advect_tracer", advect_tracer)
     for f in (ale_remap_tracers, ale_remap_set_h_vel, ale_remap_velocities, remapping_core_h):
         setattr(Context, f.__name__, f)

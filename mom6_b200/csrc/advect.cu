@@ -39,6 +39,9 @@ struct AdvPass {
   const double* T_old[NTB]; double* T_new[NTB];
   int scheme[NTB]; double underflow[NTB];
   int* limited;                // set to 1 when a face of the pass was limited
+  // x pass only: domore_u(j,k) of the reference (:433): rows whose flag is clear keep uhr untouched (so a -0.0 stays
+  // -0.0); the flag of the next pass is raised where a face of the row was limited (:524,:535).  Indexed (k, j - jsd).
+  const int* row_old; int* row_new; int nrow, jsd;
 };
 
 __device__ __forceinline__ double min3(double a, double b, double c) { return fmin2(fmin2(a, b), c); }
@@ -147,21 +150,26 @@ __global__ void __launch_bounds__(XB) advect_x_kernel(Geom G, AdvPass P) {
   const int j = P.js + blockIdx.y, k = blockIdx.z;
   const long long o2 = G.idx(I, j), o = (long long)k * G.plane + o2;
   const bool face = (I <= P.ie);
+  const int row = k * P.nrow + (j - P.jsd);
+  const bool domore = P.row_old[row] != 0;
   double uhh = 0., CFL = 0., fl[NTB];
   bool lim = false;
-  if (face) face_transport(P, o, o2, 1, 1, uhh, CFL, lim);
+  if (face && domore) face_transport(P, o, o2, 1, 1, uhh, CFL, lim);
 #pragma unroll
   for (int m = 0; m < NTB; ++m) {
     fl[m] = (face && m < P.nt) ? face_flux(P.scheme[m], P.T_old[m] + (long long)k * G.plane, P.maskC, o2, o2, 1, 1, uhh, CFL) : 0.;
     s_fl[m][t] = fl[m];
   }
   s_uhh[t] = uhh;
-  if (lim) *P.limited = 1;
+  if (lim) { *P.limited = 1; P.row_new[row] = 1; }
   __syncthreads();
   if (!face) return;
   if (P.first && (t > 0 || blockIdx.x == 0)) {  // :609-612: each face is written by one block
-    double r = P.tr_old[o] - uhh;
-    if (fabs(r) < P.H_subroundoff * fmin2(P.areaT[o2], P.areaT[o2 + 1])) r = 0.0;
+    double r = P.tr_old[o];
+    if (domore) {
+      r = r - uhh;
+      if (fabs(r) < P.H_subroundoff * fmin2(P.areaT[o2], P.areaT[o2 + 1])) r = 0.0;
+    }
     P.tr_new[o] = r;
   }
   if (t == 0) return;
@@ -202,6 +210,15 @@ __global__ void __launch_bounds__(128) advect_y_kernel(Geom G, AdvPass P) {
     for (int m = 0; m < NTB; ++m) fl_lo[m] = fl[m];
   }
   if (any_lim) *P.limited = 1;
+}
+
+// domore_u(j,k) = any(uhr(I,j,k) /= 0) over the faces of the x pass (:228-233); one warp per row
+__global__ void advect_rowflag_kernel(Geom G, const double* __restrict__ uhr, int is, int ie, int js, int nrow, int jsd, int* __restrict__ flag) {
+  const int j = js + blockIdx.x, k = blockIdx.y;
+  int any = 0;
+  for (int I = is - 1 + threadIdx.x; I <= ie; I += blockDim.x) any |= (uhr[(long long)k * G.plane + G.idx(I, j)] != 0.0);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flag[k * nrow + (j - jsd)] = any ? 1 : 0;
 }
 
 // :152-200: uhr, vhr, hprev
@@ -285,6 +302,10 @@ extern "C" int mom6cu_advect_tracer(mom6cu_ctx* c, const mom6cu_tracer_advect_cs
   }
   double *hp[2] = {c->plane3("adv.hprevA"), c->plane3("adv.hprevB")}, *uhr[2] = {c->plane3("adv.uhrA"), c->plane3("adv.uhrB")},
          *vhr[2] = {c->plane3("adv.vhrA"), c->plane3("adv.vhrB")};
+  const int nrow = d.jed - d.jsd + 1;
+  int* d_row[2] = {(int*)c->buf("adv.rowA", (size_t)(nrow * nz + 1) / 2 + 1), (int*)c->buf("adv.rowB", (size_t)(nrow * nz + 1) / 2 + 1)};
+  if (!d_row[0] || !d_row[1]) return MOM6CU_ERR_CUDA;
+  int irow = 0;
   int* d_flags = (int*)c->buf("adv.flags", 64);
   int* h_flags = (int*)c->host_scratch("adv.flags", 64);
   if (!hp[0] || !hp[1] || !uhr[0] || !uhr[1] || !vhr[0] || !vhr[1] || !d_flags || !h_flags) return MOM6CU_ERR_CUDA;
@@ -312,6 +333,10 @@ extern "C" int mom6cu_advect_tracer(mom6cu_ctx* c, const mom6cu_tracer_advect_cs
     P.maskC = xdir ? c->grid.mask2dCu : c->grid.mask2dCv;
     P.hp_old = hp[ihp]; P.hp_new = hp[1 - ihp];
     P.tr_old = xdir ? uhr[iu] : vhr[iv]; P.tr_new = xdir ? uhr[1 - iu] : vhr[1 - iv];
+    if (xdir) {
+      P.row_old = d_row[irow]; P.row_new = d_row[1 - irow]; P.nrow = nrow; P.jsd = d.jsd;
+      M6_CUDA(c, cudaMemsetAsync(d_row[1 - irow], 0, sizeof(int) * (size_t)nrow * nz, c->stream));
+    }
     for (int m0 = 0; m0 < ntr; m0 += NTB) {
       P.nt = std::min(NTB, ntr - m0); P.first = (m0 == 0);
       for (int m = 0; m < NTB; ++m) {
@@ -328,7 +353,7 @@ extern "C" int mom6cu_advect_tracer(mom6cu_ctx* c, const mom6cu_tracer_advect_cs
       }
     }
     ihp = 1 - ihp;
-    if (xdir) iu = 1 - iu; else iv = 1 - iv;
+    if (xdir) { iu = 1 - iu; irow = 1 - irow; } else iv = 1 - iv;
     std::swap(Tcur, Toth);
     return 0;
   };
@@ -343,6 +368,11 @@ extern "C" int mom6cu_advect_tracer(mom6cu_ctx* c, const mom6cu_tracer_advect_cs
         if ((rc = m6_halo_update(c, f.data() + f0, st.data() + f0, (int)std::min<size_t>(8, f.size() - f0), 0, nz))) return rc;
     }
     M6_CUDA(c, cudaMemsetAsync(d_flags, 0, sizeof(int), c->stream));
+    if (itt == 1) {  // the first evaluation of domore_u (:226-233), on every row an x pass may visit
+      M6_CUDA(c, cudaMemsetAsync(d_row[irow], 0, sizeof(int) * (size_t)nrow * nz, c->stream));
+      const int r0 = js - stencil, r1 = je + stencil;
+      M6_LAUNCH(c, advect_rowflag_kernel, dim3(r1 - r0 + 1, nz), 128, 0, G, uhr[iu], is, ie, r0, nrow, d.jsd, d_row[irow]);
+    }
     if (x_first) {
       if ((rc = pass(true, is, ie, js - stencil, je + stencil)) || (rc = pass(false, is, ie, js, je))) return rc;
     } else {

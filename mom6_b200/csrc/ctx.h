@@ -42,6 +42,8 @@ struct mom6cu_ctx {
   mom6cu_pressureforce_cs pgf_cs = {};
   bool have_pgf_cs = false;
   const double *pgf_Rlay = nullptr, *pgf_gprime = nullptr;  // device copies of GV%Rlay, GV%g_prime
+  mom6cu_vertvisc_cs vv_cs = {};
+  bool have_vv_cs = false;
   mom6cu_hor_visc_cs hv_cs = {};      // as given (host pointers)
   mom6cu_hor_visc_cs hv_cs_dev = {};  // same flags, pointers to the resident planes
   bool have_hv_cs = false;

@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, fill_struct)
 
 
 def _scalars(struct, d):
@@ -128,3 +128,19 @@ def advect_tracer_args(a, keep):
     s.update_vol_prev = int(bool(a.get("update_vol_prev", False)))
     s.uhr_out, s.vhr_out = _addr(a.get("uhr_out")), _addr(a.get("vhr_out"))
     return s
+
+
+def regridding_cs(d, keep):
+    return fill_struct(RegriddingCS(), d, keep)
+
+
+def vertvisc_cs(d):
+    return _scalars(VertviscCS(), d)
+
+
+def vertvisc_coef_args(a, keep):
+    return fill_struct(VertviscCoefArgs(), a, keep)
+
+
+def vertvisc_args(a, keep):
+    return fill_struct(VertviscArgs(), a, keep)

@@ -749,6 +749,14 @@ def step_inputs(ni, nj, nk, halo=4, whalo=10, seed=SEED, land_blocks=0, dt=900.0
                   # eta consistent with the layer thicknesses, so the mass-source correction stays small (:5268-5292)
                   bt_mass_source=(None, dict(h=h, eta=np.ascontiguousarray((h.sum(axis=0) - grid["bathyT"]) * grid["mask2dT"] +
                                                                             1e-4 * a_bt["eta_in"]), eta_cor=cs_bt["eta_cor"])))
+    # PressureForce (:503): T, S as in pressureforce_inputs on this state's h; pbce feeds btstep (:673)
+    r = rng(seed + 404)
+    zmid = -(np.cumsum(h, axis=0) - 0.5 * h)
+    T = np.ascontiguousarray(20.0 * np.exp(zmid / 1000.0) + 0.05 * r.uniform(-1, 1, size=h.shape))
+    S = np.ascontiguousarray(35.0 + 0.5 * np.exp(zmid / 500.0) + 0.01 * r.uniform(-1, 1, size=h.shape))
+    pcs = dict(EOS_form=3, MassWghtInterp=0, use_SSH_in_Z0p=0, rho_ref_bug=0, unsupported=0, rho_ref=1035.0, GFS_scale=1.0, Z_ref=0.0,
+               dZ_subroundoff=1e-30, Rho_T0_S0=1000.0, dRho_dT=-0.2, dRho_dS=0.8, dRho_dp=0.0, Rlay=None, g_prime=None)
+    stages["pressure_force"] = (pcs, dict(h=h, T=T, S=S, PFu=new3("u"), PFv=new3("v"), pbce=new3("h"), eta=new2("h")))
     return dom, grid, gv, stages
 
 
@@ -838,3 +846,59 @@ def advect_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, c
     a = dict(h_end=h_end, uhtr=uhtr, vhtr=vhtr, dt=dt, tr=tr[:ntr])
     a.update(over)
     return dom, grid, gv, cs, a
+
+
+def regrid_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, eta_amp=0.5, **cs_over):
+    """ALE_regrid inputs (MOM_ALE.F90:518): the Z*-like state of dyn_state with a sea-surface anomaly of up to eta_amp m
+    added to the top layers, a stretched target resolution summing to the maximum depth, and the OM4-like time filter."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 707)
+    h = st["h"].copy()
+    h[0] += eta_amp * r.uniform(0, 1, size=h[0].shape) * grid["mask2dT"]
+    w = np.linspace(1.0, 3.0, nk); w /= w.sum()
+    cs = dict(regridding_scheme=2, nk=nk, min_thickness=1.0e-3, old_grid_weight=0.0, depth_of_time_filter_shallow=0.0,
+              depth_of_time_filter_deep=0.0, Z_ref=0.0, coordinateResolution=np.ascontiguousarray(4000.0 * w))
+    cs.update(cs_over)
+    return dom, grid, gv, cs, dict(h=np.ascontiguousarray(h), h_new=np.zeros_like(h), dzRegrid=np.zeros((nk + 1,) + h.shape[1:]))
+
+
+def vertvisc_cs(**over):
+    """vertvisc_init defaults (MOM_vert_friction.F90:2929-3250) as OM4-like ALE runs resolve them."""
+    cs = dict(bottomdraglaw=1, harmonic_visc=0, direct_stress=0, fixed_LOTW_ML=0, apply_LOTW_floor=0, dynamic_viscous_ML=0, nkml=0,
+              answer_date=99991231, unsupported=0, Hbbl=10.0, Kv=1.0e-4, Kv_extra_bbl=0.0, Kvml_invZ2=0.0, Hmix=40.0, Hmix_stress=20.0,
+              harm_BL_val=0.0, vonKar=0.41, vel_underflow=0.0, dZ_subroundoff=1.0e-30)
+    cs.update(over)
+    return cs
+
+
+def vertvisc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, dt=900.0, with_shear=True, with_Bu=False,
+                    with_Ray=False, **cs_over):
+    """Inputs of vertvisc_coef / vertvisc / vertvisc_remnant (MOM_vert_friction.F90:1357, :557, :1229): the dyn_state
+    velocities and thicknesses, a bottom boundary layer of 2-20 m with a viscosity of 1e-3..1e-2 m2 s-1 (what
+    set_viscous_BBL hands over), a shear-driven interface viscosity and a wind stress.  Returns dom, grid, gv, cs, coef
+    args, solver args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 808)
+    new2 = lambda s, lo, hi: np.ascontiguousarray(r.uniform(lo, hi, size=fidx.new(dom, s).a.shape))   # noqa: E731
+    coef = dict(u=st["u"], v=st["v"], h=st["h"], Kv_bbl_u=new2("u", 1e-3, 1e-2), Kv_bbl_v=new2("v", 1e-3, 1e-2),
+                bbl_thick_u=new2("u", 2.0, 20.0), bbl_thick_v=new2("v", 2.0, 20.0), Kv_shear=None, Kv_shear_Bu=None,
+                ustar=new2("h", 0.0, 0.02), dt=dt)
+    if with_shear:
+        ks = r.uniform(0, 1, size=(nk + 1,) + st["h"].shape[1:]) ** 8 * 0.05
+        ks[0] = 0.0; ks[-1] = 0.0
+        coef["Kv_shear"] = np.ascontiguousarray(ks)
+    if with_Bu:
+        kq = r.uniform(0, 1, size=(nk + 1,) + fidx.new(dom, "q").a.shape) ** 8 * 0.05
+        coef["Kv_shear_Bu"] = np.ascontiguousarray(kq)
+    sol = dict(u=st["u"].copy(), v=st["v"].copy(), h=st["h"], taux=new2("u", -0.2, 0.2), tauy=new2("v", -0.2, 0.2), Ray_u=None, Ray_v=None,
+               dt=dt, taux_bot=fidx.new(dom, "u").a, tauy_bot=fidx.new(dom, "v").a)
+    if with_Ray:
+        sol["Ray_u"] = np.ascontiguousarray(r.uniform(0, 1e-5, size=st["u"].shape))
+        sol["Ray_v"] = np.ascontiguousarray(r.uniform(0, 1e-5, size=st["v"].shape))
+    return dom, grid, gv, vertvisc_cs(**cs_over), coef, sol

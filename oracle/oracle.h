@@ -77,6 +77,20 @@ int oracle_ale_remap_velocities(const mom6cu_domain* dom, const mom6cu_grid* G, 
 int oracle_advect_tracer(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_tracer_advect_cs* CS,
                          const mom6cu_advect_tracer_args* a, int* iterations);
 
+/* ALE_regrid, Z* (MOM_ALE.F90:518, MOM_regridding.F90:846-1857, coord_zlike.F90:63): see regrid.cpp.  UNPINNED. */
+int oracle_ale_regrid(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
+                      const mom6cu_regridding_cs* CS, const double* h, double* h_new, double* dzRegrid);
+
+/* vertvisc_coef / vertvisc / vertvisc_remnant (MOM_vert_friction.F90:557-2924): see vertvisc.cpp.  UNPINNED.
+ * The CS%a_u, a_v (nk+1 levels), h_u, h_v arrays the reference keeps in vertvisc_CS are explicit arguments here. */
+int oracle_vertvisc_coef(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
+                         const mom6cu_vertvisc_cs* CS, const mom6cu_vertvisc_coef_args* a, double* a_u, double* a_v, double* h_u, double* h_v);
+int oracle_vertvisc(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_vertvisc_cs* CS,
+                    const mom6cu_vertvisc_args* a, const double* a_u, const double* a_v, const double* h_u, const double* h_v);
+int oracle_vertvisc_remnant(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vertvisc_cs* CS, const double* Ray_u,
+                            const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt, const double* a_u, const double* a_v,
+                            const double* h_u, const double* h_v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,3 +245,53 @@ def advect_tracer(dom, grid, gv, cs, a):
     if rc:
         raise RuntimeError(f"oracle_advect_tracer rc={rc}")
     return it.value
+
+
+US_ONE = dict(m_to_L=1., L_to_m=1., m_s_to_L_T=1., L_T_to_m_s=1., s_to_T=1., T_to_s=1., m_to_Z=1., Z_to_m=1., Z_to_L=1., L_to_Z=1.)
+
+
+def ale_regrid(dom, grid, gv, cs, h, h_new, dzRegrid, us=None):
+    """oracle_ale_regrid: ALE_regrid (MOM_ALE.F90:518), Z* coordinate; returns 0 or 10 + the code of the first FATAL."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); u = marshal.unit_scale(us or US_ONE); c = marshal.regridding_cs(cs, keep)
+    lib.oracle_ale_regrid.argtypes = [C.c_void_p] * 8
+    return lib.oracle_ale_regrid(C.byref(dom), C.byref(g), C.byref(v), C.byref(u), C.byref(c), _dp(h), _dp(h_new), _dp(dzRegrid))
+
+
+def vertvisc_coef(dom, grid, gv, cs, a, a_u, a_v, h_u, h_v, us=None):
+    """oracle_vertvisc_coef: vertvisc_coef (MOM_vert_friction.F90:1357); the CS%a_u.. arrays are explicit."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); u = marshal.unit_scale(us or US_ONE); c = marshal.vertvisc_cs(cs)
+    st = marshal.vertvisc_coef_args(a, keep)
+    lib.oracle_vertvisc_coef.argtypes = [C.c_void_p] * 10
+    rc = lib.oracle_vertvisc_coef(C.byref(dom), C.byref(g), C.byref(v), C.byref(u), C.byref(c), C.byref(st), _dp(a_u), _dp(a_v), _dp(h_u), _dp(h_v))
+    if rc:
+        raise RuntimeError(f"oracle_vertvisc_coef rc={rc}")
+
+
+def vertvisc(dom, grid, gv, cs, a, a_u, a_v, h_u, h_v):
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); c = marshal.vertvisc_cs(cs); st = marshal.vertvisc_args(a, keep)
+    lib.oracle_vertvisc.argtypes = [C.c_void_p] * 9
+    rc = lib.oracle_vertvisc(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(st), _dp(a_u), _dp(a_v), _dp(h_u), _dp(h_v))
+    if rc:
+        raise RuntimeError(f"oracle_vertvisc rc={rc}")
+
+
+def vertvisc_remnant(dom, grid, cs, visc_rem_u, visc_rem_v, dt, a_u, a_v, h_u, h_v, Ray_u=None, Ray_v=None):
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); c = marshal.vertvisc_cs(cs)
+    lib.oracle_vertvisc_remnant.argtypes = [C.c_void_p] * 7 + [C.c_double] + [C.c_void_p] * 4
+    rc = lib.oracle_vertvisc_remnant(C.byref(dom), C.byref(g), C.byref(c), None if Ray_u is None else _dp(Ray_u),
+                                     None if Ray_v is None else _dp(Ray_v), _dp(visc_rem_u), _dp(visc_rem_v), float(dt), _dp(a_u), _dp(a_v),
+                                     _dp(h_u), _dp(h_v))
+    if rc:
+        raise RuntimeError(f"oracle_vertvisc_remnant rc={rc}")

@@ -10,7 +10,7 @@ ni = int(sys.argv[2]) if len(sys.argv) > 2 else 1440
 nj = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
 nk = int(sys.argv[4]) if len(sys.argv) > 4 else 75
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-BYTES = {"continuity": 96, "corad": 56, "hor_visc": 56, "pgf": 48, "remap": 32, "btstep": 136}
+BYTES = {"continuity": 96, "corad": 56, "hor_visc": 56, "pgf": 48, "remap": 32, "btstep": 136, "advect": 128}
 t0 = time.time()
 if stage == "corad":
     dom, grid, gv, cs, a = synthetic.coradcalc_inputs(ni, nj, nk, land_blocks=40)
@@ -23,6 +23,8 @@ elif stage == "pgf":
 elif stage == "remap":
     dom, grid, cs, a = synthetic.remap_inputs(ni, nj, nk, land_blocks=40)
     gv = synthetic.make_vgrid()
+elif stage == "advect":   # 2 tracers, 1 iteration = x pass + y pass: 2 x (hprev, uhr|vhr, 2 T) x (read + write) = 128 B/cell
+    dom, grid, gv, cs, a = synthetic.advect_inputs(ni, nj, nk, land_blocks=40, cfl=0.9)
 elif stage == "btstep":
     dom, grid, gv, cs, a = synthetic.btstep_inputs(ni, nj, nk, whalo=10, land_blocks=40)
 else:
@@ -40,6 +42,10 @@ elif stage == "pgf":
     ctx.set_cs_pressureforce(cs); run = ctx.pressure_force
 elif stage == "remap":   # one tracer per call: 32 B/cell = h_old + h_new + tracer in + tracer out
     run = lambda a: ctx.ale_remap_tracers(cs, a["h_old"], a["h_new"], [a["tr"][0].copy()])
+elif stage == "advect":
+    def run(a):
+        b = dict(a); b["tr"] = [t.copy() for t in a["tr"]]
+        print("iterations", ctx.advect_tracer(cs, b))
 elif stage == "btstep":
     run = lambda a: ctx.btstep(cs, a)
 for r in range(reps):
