@@ -527,6 +527,41 @@ int mom6cu_bt_mass_source(mom6cu_ctx* ctx, const double* h, const double* eta, i
 int mom6cu_btstep_timeloop_resident(mom6cu_ctx* ctx, const mom6cu_bt_timeloop_args* a,
                                     int reps, int download);
 
+/* ------------------------------------------------- step_MOM_dyn_split_RK2 */
+/* MOM_dyn_split_RK2_CS members the step reads / updates (src/core/MOM_dynamics_split_RK2.F90:85-273).  Every array is
+ * in/out and may be a resident plane (mom6cu_plane_alloc) -- the intended use: the control structure lives on the
+ * device between steps -- or a host array (staged in and out by the call).  The stage control structures are the ones
+ * given to mom6cu_set_cs_{continuity,coriolisadv,hor_visc,pressureforce,vertvisc}.
+ * Frozen: no OBCs, no Stokes / fpmix, no dynamic surface pressure (p_surf_begin/end absent), BT_USE_LAYER_FLUXES=True,
+ * BT_cont associated with h_u/h_v allocated (BT_THICK_SCHEME=FROM_BT_CONT), calc_dtbt=.false. (CS%dtbt as stored),
+ * set_viscous_ML a no-op (DYNAMIC_VISCOUS_ML=False), no diagnostics. */
+typedef struct mom6cu_dyn_split_rk2_cs {
+  double be, begw;
+  int split_bottom_stress, store_CAu, CAu_pred_stored /* updated */, visc_rem_dt_bug, hvel_scheme /* barotropic CS%hvel_scheme */,
+      unsupported;
+  double *CAu, *CAv, *CAu_pred, *CAv_pred, *PFu, *PFv, *diffu, *diffv; /* 3-D u / v */
+  double *visc_rem_u, *visc_rem_v, *u_accel_bt, *v_accel_bt, *u_av, *v_av; /* 3-D u / v */
+  double *h_av, *pbce;                                                  /* 3-D h */
+  double *eta, *eta_PF;                                                 /* 2-D h */
+  double *uhbt, *vhbt, *taux_bot, *tauy_bot;                            /* 2-D u / v */
+  mom6cu_bt_cont* BT_cont;
+  const mom6cu_barotropic_cs* barotropic;
+} mom6cu_dyn_split_rk2_cs;
+/* step_MOM_dyn_split_RK2(u_inst, v_inst, h, tv, visc, Time_local, dt, forces, p_surf_begin, p_surf_end, uh, vh, uhtr,
+ *   vhtr, eta_av, G, GV, US, CS, calc_dtbt, VarMix, MEKE, thickness_diffuse_CSp, pbv, STOCH, Waves)   :294-296 */
+typedef struct mom6cu_step_dyn_args {
+  double *u_inst, *v_inst, *h;  /* 3-D, in/out */
+  const double *T, *S;          /* tv%T, tv%S (NULL with EOS_NONE) */
+  const double *Kv_bbl_u, *Kv_bbl_v, *bbl_thick_u, *bbl_thick_v, *Kv_shear, *Kv_shear_Bu, *Ray_u, *Ray_v; /* visc% */
+  const double *taux, *tauy, *ustar, *p_surf;  /* forces% (p_surf optional) */
+  double dt;
+  double *uh, *vh;      /* 3-D u / v, in/out */
+  double *uhtr, *vhtr;  /* 3-D u / v, in/out */
+  double *eta_av;       /* 2-D h, out */
+  int calc_dtbt;        /* must be 0 */
+} mom6cu_step_dyn_args;
+int mom6cu_step_dyn_split_rk2(mom6cu_ctx* ctx, mom6cu_dyn_split_rk2_cs* CS, const mom6cu_step_dyn_args* a);
+
 #ifdef __cplusplus
 }
 #endif

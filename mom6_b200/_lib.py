@@ -184,6 +184,23 @@ class RemappingCS(C.Structure):
                [(n, C.c_double) for n in ("h_neglect", "h_neglect_edge")]
 
 
+class DynSplitRK2CS(C.Structure):
+    """mom6cu_dyn_split_rk2_cs: MOM_dyn_split_RK2_CS members (src/core/MOM_dynamics_split_RK2.F90:85-273)."""
+    _fields_ = [("be", C.c_double), ("begw", C.c_double)] + \
+               [(n, C.c_int) for n in ("split_bottom_stress", "store_CAu", "CAu_pred_stored", "visc_rem_dt_bug", "hvel_scheme", "unsupported")] + \
+               [(n, C.c_void_p) for n in ("CAu", "CAv", "CAu_pred", "CAv_pred", "PFu", "PFv", "diffu", "diffv", "visc_rem_u", "visc_rem_v",
+                                          "u_accel_bt", "v_accel_bt", "u_av", "v_av", "h_av", "pbce", "eta", "eta_PF", "uhbt", "vhbt",
+                                          "taux_bot", "tauy_bot")] + \
+               [("BT_cont", C.POINTER(BTCont)), ("barotropic", C.POINTER(BarotropicCS))]
+
+
+class StepDynArgs(C.Structure):
+    """mom6cu_step_dyn_args: the arguments of step_MOM_dyn_split_RK2 (:294-296)."""
+    _fields_ = [(n, C.c_void_p) for n in ("u_inst", "v_inst", "h", "T", "S", "Kv_bbl_u", "Kv_bbl_v", "bbl_thick_u", "bbl_thick_v", "Kv_shear",
+                                          "Kv_shear_Bu", "Ray_u", "Ray_v", "taux", "tauy", "ustar", "p_surf")] + [("dt", C.c_double)] + \
+               [(n, C.c_void_p) for n in ("uh", "vh", "uhtr", "vhtr", "eta_av")] + [("calc_dtbt", C.c_int)]
+
+
 class VertviscCS(C.Structure):
     """mom6cu_vertvisc_cs: vertvisc_CS members (src/parameterizations/vertical/MOM_vert_friction.F90:48-170)."""
     _fields_ = [(n, C.c_int) for n in ("bottomdraglaw", "harmonic_visc", "direct_stress", "fixed_LOTW_ML", "apply_LOTW_floor",
@@ -291,6 +308,7 @@ def bind(lib):
     lib.mom6cu_ale_remap_set_h_vel.argtypes = [vp, vp, vp, vp]
     lib.mom6cu_ale_remap_velocities.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, vp, vp, vp, vp]
     lib.mom6cu_remapping_core_h.argtypes = [vp, C.POINTER(RemappingCS), C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.mom6cu_step_dyn_split_rk2.argtypes = [vp, C.POINTER(DynSplitRK2CS), C.POINTER(StepDynArgs)]
     lib.mom6cu_set_cs_vertvisc.argtypes = [vp, C.POINTER(VertviscCS)]
     lib.mom6cu_vertvisc_coef.argtypes = [vp, C.POINTER(VertviscCoefArgs)]
     lib.mom6cu_vertvisc_get_coef.argtypes = [vp, vp, vp, vp, vp]

@@ -251,6 +251,15 @@ def _ctx_methods():
         """vertvisc_remnant, MOM_vert_friction.F90:1229."""
         return self._check(self.lib.mom6cu_vertvisc_remnant(self._h, _p(Ray_u), _p(Ray_v), _p(visc_rem_u), _p(visc_rem_v), float(dt)))
 
+    def step_dyn_split_rk2(self, cs, args):
+        """step_MOM_dyn_split_RK2, src/core/MOM_dynamics_split_RK2.F90:294; cs["CAu_pred_stored"] is updated."""
+        keep = []
+        st = marshal.dyn_split_rk2_cs(cs, keep)
+        rc = self._check(self.lib.mom6cu_step_dyn_split_rk2(self._h, C.byref(st), C.byref(marshal.step_dyn_args(args, keep))))
+        cs["CAu_pred_stored"] = int(st.CAu_pred_stored)
+        return rc
+
+    setattr(Context, "step_dyn_split_rk2", step_dyn_split_rk2)
     for f in (set_cs_vertvisc, vertvisc_coef, vertvisc_get_coef, vertvisc, vertvisc_remnant):
         setattr(Context, f.__name__, f)
     setattr(Context, "ale_regrid", ale_regrid)

@@ -579,19 +579,8 @@ int m6_bt_mass_source_run(mom6cu_ctx* c, const double* h, const double* eta, int
 }
 
 // ------------------------------------------------------------------------------------------- C ABI
-extern "C" int mom6cu_btstep(mom6cu_ctx* c, const mom6cu_barotropic_cs* CSh, const mom6cu_btstep_args* a) {
-  if (!c || !CSh || !a) return MOM6CU_ERR_BAD_ARG;
-  M6_CUDA(c, cudaSetDevice(c->device));
-  if (!a->U_in || !a->V_in || !a->eta_in || !a->bc_accel_u || !a->bc_accel_v || !a->taux || !a->tauy || !a->pbce || !a->eta_PF_in ||
-      !a->U_Cor || !a->V_Cor || !a->accel_layer_u || !a->accel_layer_v || !a->eta_out || !a->uhbtav || !a->vhbtav ||
-      !a->visc_rem_u || !a->visc_rem_v)
-    return c->fail(MOM6CU_ERR_BAD_ARG, "btstep: null required argument");
-  if (!a->BT_cont) return c->fail(MOM6CU_ERR_UNSUPPORTED, "btstep: USE_BT_CONT_TYPE=False is outside the frozen option set");
-  Stager S(c, "btstep.");
-  const int nk = c->g.nk;
-  mom6cu_barotropic_cs CS = *CSh;
-  BtstepDev D = {};
-  D.dt = a->dt;
+int m6_stage_barotropic_cs(mom6cu_ctx* c, Stager& S, const mom6cu_barotropic_cs* CSh, mom6cu_barotropic_cs* CSp) {
+  mom6cu_barotropic_cs& CS = *CSp;
   int rc;
   // control-structure arrays (wide / G-sized)
 #define W2(f, st) if ((rc = S.in(CSh->f, st, 1, 1, "cs." #f, &CS.f))) return rc; if (!CS.f) return c->fail(MOM6CU_ERR_BAD_ARG, "btstep: CS%%" #f " is null")
@@ -616,6 +605,24 @@ extern "C" int mom6cu_btstep(mom6cu_ctx* c, const mom6cu_barotropic_cs* CSh, con
     return rc;
   if (!CS.frhatu || !CS.frhatv || !CS.IDatu || !CS.IDatv || !CS.eta_cor || !CS.ubtav || !CS.vbtav)
     return c->fail(MOM6CU_ERR_BAD_ARG, "btstep: a required control-structure array is null");
+  return 0;
+}
+
+extern "C" int mom6cu_btstep(mom6cu_ctx* c, const mom6cu_barotropic_cs* CSh, const mom6cu_btstep_args* a) {
+  if (!c || !CSh || !a) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  if (!a->U_in || !a->V_in || !a->eta_in || !a->bc_accel_u || !a->bc_accel_v || !a->taux || !a->tauy || !a->pbce || !a->eta_PF_in ||
+      !a->U_Cor || !a->V_Cor || !a->accel_layer_u || !a->accel_layer_v || !a->eta_out || !a->uhbtav || !a->vhbtav ||
+      !a->visc_rem_u || !a->visc_rem_v)
+    return c->fail(MOM6CU_ERR_BAD_ARG, "btstep: null required argument");
+  if (!a->BT_cont) return c->fail(MOM6CU_ERR_UNSUPPORTED, "btstep: USE_BT_CONT_TYPE=False is outside the frozen option set");
+  Stager S(c, "btstep.");
+  const int nk = c->g.nk;
+  mom6cu_barotropic_cs CS = *CSh;
+  BtstepDev D = {};
+  D.dt = a->dt;
+  int rc;
+  if ((rc = m6_stage_barotropic_cs(c, S, CSh, &CS))) return rc;
   // arguments
   if ((rc = S.in3(a->U_in, ST_U, "U_in", &D.U_in)) || (rc = S.in3(a->V_in, ST_V, "V_in", &D.V_in)) ||
       (rc = S.in2(a->eta_in, ST_H, "eta_in", &D.eta_in)) || (rc = S.in3(a->bc_accel_u, ST_U, "bcu", &D.bc_accel_u)) ||

@@ -60,7 +60,25 @@ struct PgfDev {
   double *PFu, *PFv, *pbce, *eta;
 };
 
+// vertvisc_coef / vertvisc dummy arguments (MOM_vert_friction.F90:1357, :557)
+struct VvCoefDev {
+  const double *u, *v, *h, *Kv_bbl_u, *Kv_bbl_v, *bbl_thick_u, *bbl_thick_v, *Kv_shear, *Kv_shear_Bu, *ustar;
+  double dt;
+};
+struct VvDev {
+  double *u, *v;
+  const double *h, *taux, *tauy, *Ray_u, *Ray_v;
+  double dt;
+  double *taux_bot, *tauy_bot;
+};
+
 struct mom6cu_ctx;
+struct Stager;
+int m6_vertvisc_coef_run(mom6cu_ctx* c, const VvCoefDev& D);
+int m6_vertvisc_run(mom6cu_ctx* c, const VvDev& D);
+int m6_vertvisc_remnant_run(mom6cu_ctx* c, const double* Ray_u, const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt);
+// stage the array members of a barotropic_CS given with host or resident pointers into *CS (device pointers)
+int m6_stage_barotropic_cs(mom6cu_ctx* c, Stager& S, const mom6cu_barotropic_cs* CSh, mom6cu_barotropic_cs* CS);
 int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D);
 // CS holds device pointers (resident planes) for every array member
 int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev& D);

@@ -8,6 +8,8 @@
 // with -fmad=false).
 #include "ctx.h"
 #include "common.cuh"
+#include "stage.h"
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -288,45 +290,54 @@ extern "C" int mom6cu_set_cs_vertvisc(mom6cu_ctx* c, const mom6cu_vertvisc_cs* C
   return 0;
 }
 
+int m6_vertvisc_coef_run(mom6cu_ctx* c, const VvCoefDev& D) {
+  int rc;
+  if ((rc = need_cs(c, "coef"))) return rc;
+  if (!c->vgrid.Boussinesq) return c->fail(MOM6CU_ERR_UNSUPPORTED, "vertvisc_coef: non-Boussinesq thickness_to_dz / find_ustar are not implemented");
+  const mom6cu_vertvisc_cs& CS = c->vv_cs;
+  const bool lotw = CS.fixed_LOTW_ML || CS.apply_LOTW_floor, surf = lotw || CS.Kvml_invZ2 > 0.;
+  if (CS.bottomdraglaw && (!D.Kv_bbl_u || !D.Kv_bbl_v || !D.bbl_thick_u || !D.bbl_thick_v))
+    return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc_coef: BOTTOMDRAGLAW needs visc%%Kv_bbl_[uv] and visc%%bbl_thick_[uv]");
+  if (lotw && !D.ustar) return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc_coef: the law-of-the-wall options need forces%%ustar");
+  const Geom& G = c->g;
+  Coefs K;
+  if ((rc = coef_planes(c, &K))) return rc;
+  double *sc1 = nullptr, *sc2 = nullptr;
+  if (surf && (!(sc1 = c->plane3("vv.dzvel")) || !(sc2 = c->plane3("vv.dzharm")))) return MOM6CU_ERR_CUDA;
+  const mom6cu_domain& d = c->dom;
+  CoefK U = {}, V = {};
+  U.CS = CS; U.nz = G.nk; U.h_neglect = c->vgrid.H_subroundoff; U.H_to_Z = c->vgrid.H_to_Z; U.Z_to_H = c->vgrid.Z_to_H;
+  U.a_cpl_max = 1.0e37 * c->vgrid.m_to_H * c->US.T_to_s;
+  U.bathyT = c->grid.bathyT; U.CoriolisBu = c->grid.CoriolisBu; U.h = D.h; U.Kv_shear = D.Kv_shear; U.Kv_shear_Bu = D.Kv_shear_Bu; U.ustar = D.ustar;
+  U.dzvel = sc1; U.dzharm = sc2;
+  V = U;
+  U.mask = c->grid.mask2dCu; U.vel = D.u; U.kv_bbl = D.Kv_bbl_u; U.bbl_thick = D.bbl_thick_u; U.a_out = K.a_u; U.h_out = K.h_u;
+  U.i0 = d.isc - 1; U.i1 = d.iec; U.j0 = d.jsc; U.j1 = d.jec;
+  V.mask = c->grid.mask2dCv; V.vel = D.v; V.kv_bbl = D.Kv_bbl_v; V.bbl_thick = D.bbl_thick_v; V.a_out = K.a_v; V.h_out = K.h_v;
+  V.i0 = d.isc; V.i1 = d.iec; V.j0 = d.jsc - 1; V.j1 = d.jec;
+  M6_LAUNCH(c, vv_coef_kernel<0>, dim3((U.i1 - U.i0 + 128) / 128, U.j1 - U.j0 + 1), 128, 0, G, U);
+  M6_LAUNCH(c, vv_coef_kernel<1>, dim3((V.i1 - V.i0 + 128) / 128, V.j1 - V.j0 + 1), 128, 0, G, V);
+  M6_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mom6cu_vertvisc_coef(mom6cu_ctx* c, const mom6cu_vertvisc_coef_args* a) {
   if (!c || !a) return MOM6CU_ERR_BAD_ARG;
   M6_CUDA(c, cudaSetDevice(c->device));
   int rc;
   if ((rc = need_cs(c, "coef"))) return rc;
-  if (!c->vgrid.Boussinesq) return c->fail(MOM6CU_ERR_UNSUPPORTED, "vertvisc_coef: non-Boussinesq thickness_to_dz / find_ustar are not implemented");
   if (!a->u || !a->v || !a->h) return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc_coef: null required argument");
-  const mom6cu_vertvisc_cs& CS = c->vv_cs;
-  const bool lotw = CS.fixed_LOTW_ML || CS.apply_LOTW_floor, surf = lotw || CS.Kvml_invZ2 > 0.;
-  if (CS.bottomdraglaw && (!a->Kv_bbl_u || !a->Kv_bbl_v || !a->bbl_thick_u || !a->bbl_thick_v))
-    return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc_coef: BOTTOMDRAGLAW needs visc%%Kv_bbl_[uv] and visc%%bbl_thick_[uv]");
-  if (lotw && !a->ustar) return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc_coef: the law-of-the-wall options need forces%%ustar");
   const Geom& G = c->g;
   Stager S(c, "vvc.");
-  CoefK U = {}, V = {};
-  const double *d_u, *d_v, *d_h, *d_kbu, *d_kbv, *d_btu, *d_btv, *d_kvs, *d_kbq, *d_ust;
-  if ((rc = S.in3(a->u, ST_U, "u", &d_u)) || (rc = S.in3(a->v, ST_V, "v", &d_v)) || (rc = S.in3(a->h, ST_H, "h", &d_h)) ||
-      (rc = S.in2(a->Kv_bbl_u, ST_U, "kbu", &d_kbu)) || (rc = S.in2(a->Kv_bbl_v, ST_V, "kbv", &d_kbv)) ||
-      (rc = S.in2(a->bbl_thick_u, ST_U, "btu", &d_btu)) || (rc = S.in2(a->bbl_thick_v, ST_V, "btv", &d_btv)) ||
-      (rc = S.in(a->Kv_shear, ST_H, 0, G.nk + 1, "kvs", &d_kvs)) || (rc = S.in(a->Kv_shear_Bu, ST_Q, 0, G.nk + 1, "kvq", &d_kbq)) ||
-      (rc = S.in2(a->ustar, ST_H, "ustar", &d_ust))) return rc;
-  Coefs K;
-  if ((rc = coef_planes(c, &K))) return rc;
-  double *sc1 = nullptr, *sc2 = nullptr;
-  if (surf && (!(sc1 = c->plane3("vv.dzvel")) || !(sc2 = c->plane3("vv.dzharm")))) return MOM6CU_ERR_CUDA;
+  VvCoefDev D = {};
+  D.dt = a->dt;
+  if ((rc = S.in3(a->u, ST_U, "u", &D.u)) || (rc = S.in3(a->v, ST_V, "v", &D.v)) || (rc = S.in3(a->h, ST_H, "h", &D.h)) ||
+      (rc = S.in2(a->Kv_bbl_u, ST_U, "kbu", &D.Kv_bbl_u)) || (rc = S.in2(a->Kv_bbl_v, ST_V, "kbv", &D.Kv_bbl_v)) ||
+      (rc = S.in2(a->bbl_thick_u, ST_U, "btu", &D.bbl_thick_u)) || (rc = S.in2(a->bbl_thick_v, ST_V, "btv", &D.bbl_thick_v)) ||
+      (rc = S.in(a->Kv_shear, ST_H, 0, G.nk + 1, "kvs", &D.Kv_shear)) || (rc = S.in(a->Kv_shear_Bu, ST_Q, 0, G.nk + 1, "kvq", &D.Kv_shear_Bu)) ||
+      (rc = S.in2(a->ustar, ST_H, "ustar", &D.ustar))) return rc;
   if ((rc = S.begin())) return rc;
-  const mom6cu_domain& d = c->dom;
-  U.CS = CS; U.nz = G.nk; U.h_neglect = c->vgrid.H_subroundoff; U.H_to_Z = c->vgrid.H_to_Z; U.Z_to_H = c->vgrid.Z_to_H;
-  U.a_cpl_max = 1.0e37 * c->vgrid.m_to_H * c->US.T_to_s;
-  U.bathyT = c->grid.bathyT; U.CoriolisBu = c->grid.CoriolisBu; U.h = d_h; U.Kv_shear = d_kvs; U.Kv_shear_Bu = d_kbq; U.ustar = d_ust;
-  U.dzvel = sc1; U.dzharm = sc2;
-  V = U;
-  U.mask = c->grid.mask2dCu; U.vel = d_u; U.kv_bbl = d_kbu; U.bbl_thick = d_btu; U.a_out = K.a_u; U.h_out = K.h_u;
-  U.i0 = d.isc - 1; U.i1 = d.iec; U.j0 = d.jsc; U.j1 = d.jec;
-  V.mask = c->grid.mask2dCv; V.vel = d_v; V.kv_bbl = d_kbv; V.bbl_thick = d_btv; V.a_out = K.a_v; V.h_out = K.h_v;
-  V.i0 = d.isc; V.i1 = d.iec; V.j0 = d.jsc - 1; V.j1 = d.jec;
-  M6_LAUNCH(c, vv_coef_kernel<0>, dim3((U.i1 - U.i0 + 128) / 128, U.j1 - U.j0 + 1), 128, 0, G, U);
-  M6_LAUNCH(c, vv_coef_kernel<1>, dim3((V.i1 - V.i0 + 128) / 128, V.j1 - V.j0 + 1), 128, 0, G, V);
-  M6_CUDA(c, cudaGetLastError());
+  if ((rc = m6_vertvisc_coef_run(c, D))) return rc;
   return S.finish();
 }
 
@@ -345,39 +356,66 @@ extern "C" int mom6cu_vertvisc_get_coef(mom6cu_ctx* c, double* a_u, double* a_v,
   return 0;
 }
 
+int m6_vertvisc_run(mom6cu_ctx* c, const VvDev& D) {
+  int rc;
+  if ((rc = need_cs(c, "visc"))) return rc;
+  const mom6cu_vertvisc_cs& CS = c->vv_cs;
+  if (CS.direct_stress && !D.h) return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc: DIRECT_STRESS needs h");
+  const Geom& G = c->g;
+  Coefs K;
+  if ((rc = coef_planes(c, &K))) return rc;
+  const mom6cu_domain& d = c->dom;
+  SolveK U = {};
+  U.nz = G.nk; U.direct_stress = CS.direct_stress; U.dt = D.dt; U.dt_Rho0 = D.dt / c->vgrid.H_to_RZ; U.h_neglect = c->vgrid.H_subroundoff;
+  U.Hmix = CS.Hmix_stress; U.I_Hmix = CS.direct_stress ? 1.0 / CS.Hmix_stress : 0.0; U.H_to_RZ = c->vgrid.H_to_RZ; U.h = D.h;
+  SolveK V = U;
+  U.mask = c->grid.mask2dCu; U.a = K.a_u; U.hh = K.h_u; U.Ray = D.Ray_u; U.tau = D.taux; U.x = D.u; U.tau_bot = D.taux_bot;
+  U.i0 = d.isc - 1; U.i1 = d.iec; U.j0 = std::min(d.jsc, d.isc); U.j1 = d.jec; U.js_stress = d.jsc; U.js_solve = d.isc;  // `do j=G%isc,G%jec` (:778)
+  V.mask = c->grid.mask2dCv; V.a = K.a_v; V.hh = K.h_v; V.Ray = D.Ray_v; V.tau = D.tauy; V.x = D.v; V.tau_bot = D.tauy_bot;
+  V.i0 = d.isc; V.i1 = d.iec; V.j0 = d.jsc - 1; V.j1 = d.jec; V.js_stress = V.j0; V.js_solve = V.j0;
+  M6_LAUNCH(c, (vv_solve_kernel<0, false>), dim3((U.i1 - U.i0 + 128) / 128, U.j1 - U.j0 + 1), 128, 0, G, U);
+  M6_LAUNCH(c, (vv_solve_kernel<1, false>), dim3((V.i1 - V.i0 + 128) / 128, V.j1 - V.j0 + 1), 128, 0, G, V);
+  M6_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mom6cu_vertvisc(mom6cu_ctx* c, const mom6cu_vertvisc_args* a) {
   if (!c || !a) return MOM6CU_ERR_BAD_ARG;
   M6_CUDA(c, cudaSetDevice(c->device));
   int rc;
   if ((rc = need_cs(c, "visc"))) return rc;
   if (!a->u || !a->v || !a->taux || !a->tauy) return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc: null required argument");
-  const mom6cu_vertvisc_cs& CS = c->vv_cs;
-  if (CS.direct_stress && !a->h) return c->fail(MOM6CU_ERR_BAD_ARG, "vertvisc: DIRECT_STRESS needs h");
-  const Geom& G = c->g;
   Stager S(c, "vv.");
-  double *d_u, *d_v, *d_tbu = nullptr, *d_tbv = nullptr;
-  const double *d_h, *d_tx, *d_ty, *d_ru, *d_rv;
-  if ((rc = S.io3(a->u, ST_U, "u", &d_u)) || (rc = S.io3(a->v, ST_V, "v", &d_v)) || (rc = S.in3(a->h, ST_H, "h", &d_h)) ||
-      (rc = S.in2(a->taux, ST_U, "taux", &d_tx)) || (rc = S.in2(a->tauy, ST_V, "tauy", &d_ty)) ||
-      (rc = S.in3(a->Ray_u, ST_U, "Ray_u", &d_ru)) || (rc = S.in3(a->Ray_v, ST_V, "Ray_v", &d_rv))) return rc;
-  if (a->taux_bot && (rc = S.io2(a->taux_bot, ST_U, "taux_bot", &d_tbu))) return rc;
-  if (a->tauy_bot && (rc = S.io2(a->tauy_bot, ST_V, "tauy_bot", &d_tbv))) return rc;
+  VvDev D = {};
+  D.dt = a->dt;
+  if ((rc = S.io3(a->u, ST_U, "u", &D.u)) || (rc = S.io3(a->v, ST_V, "v", &D.v)) || (rc = S.in3(a->h, ST_H, "h", &D.h)) ||
+      (rc = S.in2(a->taux, ST_U, "taux", &D.taux)) || (rc = S.in2(a->tauy, ST_V, "tauy", &D.tauy)) ||
+      (rc = S.in3(a->Ray_u, ST_U, "Ray_u", &D.Ray_u)) || (rc = S.in3(a->Ray_v, ST_V, "Ray_v", &D.Ray_v))) return rc;
+  if (a->taux_bot && (rc = S.io2(a->taux_bot, ST_U, "taux_bot", &D.taux_bot))) return rc;
+  if (a->tauy_bot && (rc = S.io2(a->tauy_bot, ST_V, "tauy_bot", &D.tauy_bot))) return rc;
+  if ((rc = S.begin())) return rc;
+  if ((rc = m6_vertvisc_run(c, D))) return rc;
+  return S.finish();
+}
+
+int m6_vertvisc_remnant_run(mom6cu_ctx* c, const double* Ray_u, const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt) {
+  int rc;
+  if ((rc = need_cs(c, "remant"))) return rc;
+  const Geom& G = c->g;
   Coefs K;
   if ((rc = coef_planes(c, &K))) return rc;
-  if ((rc = S.begin())) return rc;
   const mom6cu_domain& d = c->dom;
   SolveK U = {};
-  U.nz = G.nk; U.direct_stress = CS.direct_stress; U.dt = a->dt; U.dt_Rho0 = a->dt / c->vgrid.H_to_RZ; U.h_neglect = c->vgrid.H_subroundoff;
-  U.Hmix = CS.Hmix_stress; U.I_Hmix = CS.direct_stress ? 1.0 / CS.Hmix_stress : 0.0; U.H_to_RZ = c->vgrid.H_to_RZ; U.h = d_h;
+  U.nz = G.nk; U.dt = dt;
   SolveK V = U;
-  U.mask = c->grid.mask2dCu; U.a = K.a_u; U.hh = K.h_u; U.Ray = d_ru; U.tau = d_tx; U.x = d_u; U.tau_bot = d_tbu;
-  U.i0 = d.isc - 1; U.i1 = d.iec; U.j0 = std::min(d.jsc, d.isc); U.j1 = d.jec; U.js_stress = d.jsc; U.js_solve = d.isc;  // `do j=G%isc,G%jec` (:778)
-  V.mask = c->grid.mask2dCv; V.a = K.a_v; V.hh = K.h_v; V.Ray = d_rv; V.tau = d_ty; V.x = d_v; V.tau_bot = d_tbv;
+  U.mask = c->grid.mask2dCu; U.a = K.a_u; U.hh = K.h_u; U.Ray = Ray_u; U.x = visc_rem_u;
+  U.i0 = d.isc - 1; U.i1 = d.iec; U.j0 = d.jsc; U.j1 = d.jec; U.js_stress = U.j0; U.js_solve = U.j0;
+  V.mask = c->grid.mask2dCv; V.a = K.a_v; V.hh = K.h_v; V.Ray = Ray_v; V.x = visc_rem_v;
   V.i0 = d.isc; V.i1 = d.iec; V.j0 = d.jsc - 1; V.j1 = d.jec; V.js_stress = V.j0; V.js_solve = V.j0;
-  M6_LAUNCH(c, (vv_solve_kernel<0, false>), dim3((U.i1 - U.i0 + 128) / 128, U.j1 - U.j0 + 1), 128, 0, G, U);
-  M6_LAUNCH(c, (vv_solve_kernel<1, false>), dim3((V.i1 - V.i0 + 128) / 128, V.j1 - V.j0 + 1), 128, 0, G, V);
+  M6_LAUNCH(c, (vv_solve_kernel<0, true>), dim3((U.i1 - U.i0 + 128) / 128, U.j1 - U.j0 + 1), 128, 0, G, U);
+  M6_LAUNCH(c, (vv_solve_kernel<1, true>), dim3((V.i1 - V.i0 + 128) / 128, V.j1 - V.j0 + 1), 128, 0, G, V);
   M6_CUDA(c, cudaGetLastError());
-  return S.finish();
+  return 0;
 }
 
 extern "C" int mom6cu_vertvisc_remnant(mom6cu_ctx* c, const double* Ray_u, const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt) {
@@ -385,25 +423,12 @@ extern "C" int mom6cu_vertvisc_remnant(mom6cu_ctx* c, const double* Ray_u, const
   M6_CUDA(c, cudaSetDevice(c->device));
   int rc;
   if ((rc = need_cs(c, "remant"))) return rc;
-  const Geom& G = c->g;
   Stager S(c, "vvr.");
   double *d_ru_out, *d_rv_out;
   const double *d_ru, *d_rv;
   if ((rc = S.io3(visc_rem_u, ST_U, "vru", &d_ru_out)) || (rc = S.io3(visc_rem_v, ST_V, "vrv", &d_rv_out)) ||
       (rc = S.in3(Ray_u, ST_U, "Ray_u", &d_ru)) || (rc = S.in3(Ray_v, ST_V, "Ray_v", &d_rv))) return rc;
-  Coefs K;
-  if ((rc = coef_planes(c, &K))) return rc;
   if ((rc = S.begin())) return rc;
-  const mom6cu_domain& d = c->dom;
-  SolveK U = {};
-  U.nz = G.nk; U.dt = dt;
-  SolveK V = U;
-  U.mask = c->grid.mask2dCu; U.a = K.a_u; U.hh = K.h_u; U.Ray = d_ru; U.x = d_ru_out;
-  U.i0 = d.isc - 1; U.i1 = d.iec; U.j0 = d.jsc; U.j1 = d.jec; U.js_stress = U.j0; U.js_solve = U.j0;
-  V.mask = c->grid.mask2dCv; V.a = K.a_v; V.hh = K.h_v; V.Ray = d_rv; V.x = d_rv_out;
-  V.i0 = d.isc; V.i1 = d.iec; V.j0 = d.jsc - 1; V.j1 = d.jec; V.js_stress = V.j0; V.js_solve = V.j0;
-  M6_LAUNCH(c, (vv_solve_kernel<0, true>), dim3((U.i1 - U.i0 + 128) / 128, U.j1 - U.j0 + 1), 128, 0, G, U);
-  M6_LAUNCH(c, (vv_solve_kernel<1, true>), dim3((V.i1 - V.i0 + 128) / 128, V.j1 - V.j0 + 1), 128, 0, G, V);
-  M6_CUDA(c, cudaGetLastError());
+  if ((rc = m6_vertvisc_remnant_run(c, d_ru, d_rv, d_ru_out, d_rv_out, dt))) return rc;
   return S.finish();
 }

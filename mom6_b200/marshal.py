@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, fill_struct)
 
 
 def _scalars(struct, d):
@@ -144,3 +144,18 @@ def vertvisc_coef_args(a, keep):
 
 def vertvisc_args(a, keep):
     return fill_struct(VertviscArgs(), a, keep)
+
+
+def dyn_split_rk2_cs(d, keep):
+    """d: the scalar members, the arrays, BT_cont (dict) and barotropic (dict of barotropic_CS members)."""
+    st = fill_struct(DynSplitRK2CS(), d, keep)
+    bs = fill_struct(BTCont(), d["BT_cont"], keep)
+    bt = fill_struct(BarotropicCS(), d["barotropic"], keep)
+    keep += [bs, bt]
+    st.BT_cont = C.pointer(bs)
+    st.barotropic = C.pointer(bt)
+    return st
+
+
+def step_dyn_args(a, keep):
+    return fill_struct(StepDynArgs(), a, keep)

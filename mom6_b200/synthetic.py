@@ -333,7 +333,7 @@ def continuity_cs(nk, Angstrom_H=1.0e-10, **over):
     return cs
 
 
-def dyn_state(dom, grid, seed=SEED, vel=0.3, thin_layers=True):
+def dyn_state(dom, grid, seed=SEED, vel=0.3, thin_layers=True, hnoise=0.2):
     """h, u, v, visc_rem_u/v on G's memory domain: Z*-like layers over the synthetic bathymetry with
     noise, some vanished layers over the seamount, velocities ~ vel*U*mask."""
     r = rng(seed + 101)
@@ -355,7 +355,7 @@ def dyn_state(dom, grid, seed=SEED, vel=0.3, thin_layers=True):
     w = np.linspace(1.0, 3.0, nk); w /= w.sum()
     h = U3("h")
     D = grid["bathyT"]
-    h.a[...] = D[None, :, :] * w[:, None, None] * (1.0 + 0.2 * h.a)
+    h.a[...] = D[None, :, :] * w[:, None, None] * (1.0 + hnoise * h.a)
     if thin_layers:
         # vanished layers where the water is shallower than the nominal interface depth
         zbot = np.cumsum(4000.0 * w)
@@ -634,7 +634,7 @@ def hor_visc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True,
 
 
 def btstep_inputs(ni, nj, nk, halo=4, whalo=6, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, dt=900.0,
-                  first_direction=0, with_uh0=True, with_etaav=True, with_bot=False, **cs_over):
+                  first_direction=0, with_uh0=True, with_etaav=True, with_bot=False, vel=0.2, hnoise=0.2, **cs_over):
     """Everything a btstep call needs (MOM_barotropic.F90:455): returns dom, grid, vgrid, cs, args.
     The barotropic_CS members (wide-halo copies of the metrics, linearised Coriolis thicknesses, frhatu/v ...) are
     built the way barotropic_init (:5301) / btcalc build them."""
@@ -643,7 +643,7 @@ def btstep_inputs(ni, nj, nk, halo=4, whalo=6, seed=SEED, land_blocks=0, cyclic_
     grid = make_grid(dom, land_blocks, seed)
     gw = make_grid(domw, land_blocks, seed)   # the same metrics on the wide-halo memory domain
     gv = make_vgrid()
-    st = dyn_state(dom, grid, seed, vel=0.2, thin_layers=False)
+    st = dyn_state(dom, grid, seed, vel=vel, thin_layers=False, hnoise=hnoise)
     r = rng(seed + 303)
     h = st["h"]
     D = grid["bathyT"]
@@ -902,3 +902,35 @@ def vertvisc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True,
         sol["Ray_u"] = np.ascontiguousarray(r.uniform(0, 1e-5, size=st["u"].shape))
         sol["Ray_v"] = np.ascontiguousarray(r.uniform(0, 1e-5, size=st["v"].shape))
     return dom, grid, gv, vertvisc_cs(**cs_over), coef, sol
+
+
+def step_dyn_inputs(ni, nj, nk, halo=4, whalo=10, seed=SEED, land_blocks=0, dt=900.0, vel=0.05, hnoise=1.0e-4, store_CAu=0, begw=0.0,
+                    split_bottom_stress=0, **bt_over):
+    """A full step_MOM_dyn_split_RK2 call (MOM_dynamics_split_RK2.F90:294): the shared state of step_inputs with a nearly
+    level sea surface (so one step stays well inside CFL), the MOM_dyn_split_RK2_CS arrays as a previous step would have
+    left them, visc% and forces%.  Returns dom, grid, gv, css (the stage control structures), cs, args."""
+    dom, grid, gv, stages = step_inputs(ni, nj, nk, halo=halo, whalo=whalo, seed=seed, land_blocks=land_blocks, dt=dt, vel=vel, hnoise=hnoise,
+                                        **bt_over)
+    r = rng(seed + 909)
+    cs_bt, a_bt = stages["btstep"]
+    cont = stages["continuity"][1]; pf = stages["pressure_force"][1]
+    u, v, h = cont["u"].copy(), cont["v"].copy(), cont["hin"].copy()
+    new3 = lambda st: fidx.new(dom, st, nk=nk).a          # noqa: E731
+    new2 = lambda st: fidx.new(dom, st).a                 # noqa: E731
+    rnd2 = lambda st, lo, hi: np.ascontiguousarray(r.uniform(lo, hi, size=new2(st).shape))   # noqa: E731
+    uh, vh = transports(dom, grid, dict(h=h, u=u, v=v))
+    eta = np.ascontiguousarray((h.sum(axis=0) - grid["bathyT"]) * grid["mask2dT"])
+    css = dict(continuity=stages["continuity"][0], coriolisadv=stages["coradcalc"][0], hor_visc=stages["horizontal_viscosity"][0],
+               pressureforce=stages["pressure_force"][0], vertvisc=vertvisc_cs())
+    cs = dict(be=0.6, begw=begw, split_bottom_stress=split_bottom_stress, store_CAu=store_CAu, CAu_pred_stored=0, visc_rem_dt_bug=1, hvel_scheme=4,
+              unsupported=0, CAu=new3("u"), CAv=new3("v"), CAu_pred=new3("u"), CAv_pred=new3("v"), PFu=new3("u"), PFv=new3("v"),
+              diffu=new3("u"), diffv=new3("v"), visc_rem_u=new3("u"), visc_rem_v=new3("v"), u_accel_bt=new3("u"), v_accel_bt=new3("v"),
+              u_av=u.copy(), v_av=v.copy(), h_av=h.copy(), pbce=new3("h"), eta=eta, eta_PF=new2("h"), uhbt=new2("u"), vhbt=new2("v"),
+              taux_bot=new2("u"), tauy_bot=new2("v"), BT_cont=dict(cont["BT_cont"]), barotropic=dict(cs_bt))
+    kvs = r.uniform(0, 1, size=(nk + 1,) + h.shape[1:]) ** 8 * 0.02
+    kvs[0] = 0.0; kvs[-1] = 0.0
+    a = dict(u_inst=u, v_inst=v, h=h, T=pf["T"], S=pf["S"], Kv_bbl_u=rnd2("u", 1e-3, 1e-2), Kv_bbl_v=rnd2("v", 1e-3, 1e-2),
+             bbl_thick_u=rnd2("u", 2.0, 20.0), bbl_thick_v=rnd2("v", 2.0, 20.0), Kv_shear=np.ascontiguousarray(kvs), Kv_shear_Bu=None, Ray_u=None,
+             Ray_v=None, taux=np.ascontiguousarray(a_bt["taux"]), tauy=np.ascontiguousarray(a_bt["tauy"]), ustar=rnd2("h", 0.0, 0.02), p_surf=None,
+             dt=dt, uh=uh, vh=vh, uhtr=new3("u"), vhtr=new3("v"), eta_av=new2("h"), calc_dtbt=0)
+    return dom, grid, gv, css, cs, a

@@ -91,6 +91,12 @@ int oracle_vertvisc_remnant(const mom6cu_domain* dom, const mom6cu_grid* G, cons
                             const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt, const double* a_u, const double* a_v,
                             const double* h_u, const double* h_v);
 
+/* step_MOM_dyn_split_RK2 (MOM_dynamics_split_RK2.F90:294-1205): see step.cpp.  UNPINNED. */
+int oracle_step_dyn_split_rk2(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
+                              const mom6cu_continuity_cs* cont_cs, const mom6cu_coriolisadv_cs* corad_cs, const mom6cu_hor_visc_cs* hv_cs,
+                              const mom6cu_pressureforce_cs* pgf_cs, const mom6cu_vertvisc_cs* vv_cs, mom6cu_dyn_split_rk2_cs* CS,
+                              const mom6cu_step_dyn_args* a, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

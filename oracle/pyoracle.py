@@ -295,3 +295,21 @@ def vertvisc_remnant(dom, grid, cs, visc_rem_u, visc_rem_v, dt, a_u, a_v, h_u, h
                                      _dp(h_u), _dp(h_v))
     if rc:
         raise RuntimeError(f"oracle_vertvisc_remnant rc={rc}")
+
+
+def step_dyn_split_rk2(dom, grid, gv, css, cs, args, us=None, nthreads=1):
+    """oracle_step_dyn_split_rk2: step_MOM_dyn_split_RK2 (MOM_dynamics_split_RK2.F90:294).  css: dict of the stage control
+    structures (continuity, coriolisadv, hor_visc, pressureforce, vertvisc); cs["CAu_pred_stored"] is updated."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); u = marshal.unit_scale(us or US_ONE)
+    cc = marshal.continuity_cs(css["continuity"]); ca = marshal.coriolisadv_cs(css["coriolisadv"]); hv = marshal.hor_visc_cs(css["hor_visc"], keep)
+    pg = marshal.pressureforce_cs(css["pressureforce"], keep); vv = marshal.vertvisc_cs(css["vertvisc"])
+    st = marshal.dyn_split_rk2_cs(cs, keep); a = marshal.step_dyn_args(args, keep)
+    lib.oracle_step_dyn_split_rk2.argtypes = [C.c_void_p] * 11 + [C.c_int]
+    rc = lib.oracle_step_dyn_split_rk2(C.byref(dom), C.byref(g), C.byref(v), C.byref(u), C.byref(cc), C.byref(ca), C.byref(hv), C.byref(pg),
+                                       C.byref(vv), C.byref(st), C.byref(a), nthreads)
+    if rc:
+        raise RuntimeError(f"oracle_step_dyn_split_rk2 rc={rc}")
+    cs["CAu_pred_stored"] = int(st.CAu_pred_stored)
