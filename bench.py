@@ -33,10 +33,10 @@ BT_BYTES_PER_PT_SUBSTEP = 552   # 69 fp64 operands on the BT_cont pat
 # stage -> (calls per baroclinic step [MOM_dynamics_split_RK2.F90 line], algorithmic bytes per cell per call [SURVEY 8d])
 STEP = [("pressure_force", 1, 48), ("continuity", 3, 96), ("btcalc", 1, 32), ("bt_mass_source", 2, 8), ("btstep", 2, 136), ("coradcalc", 2, 56),
         ("horizontal_viscosity", 1, 40)]
-STAGES = ["PressureForce_FV_Bouss x1, Wright EOS analytic (:503)", "continuity_PPM x3 (:646,:781,:1043)", "btcalc x1 (:650)", "bt_mass_source x2 (:629,:821)",
-          "btstep x2 incl. the 68-substep barotropic loop (:673,:939)", "CorAdCalc x2 (:895,:1090)", "horizontal_viscosity x1 (:886)"]
-MISSING = ["vertvisc_coef/vertvisc/vertvisc_remnant x3 (:609,:754,:1003)", "set_viscous_ML (:602)",
-           "elementwise glue up/vp/u/v/h_av/uhtr (:565-1082)", "inter-stage 3-D halo updates (:616-1056)"]
+STAGES = ["step_MOM_dyn_split_RK2 (MOM_dynamics_split_RK2.F90:294-1205) as ONE device-resident call: PressureForce_FV_Bouss (Wright EOS) x1, "
+          "CorAdCalc x2(+1 with store_CAu), vertvisc_coef x3 + vertvisc x2 + vertvisc_remnant x3, continuity_PPM x3, btcalc x2, "
+          "bt_mass_source x2, btstep x2 (68 barotropic substeps each), horizontal_viscosity x1, the elementwise glue and the 7 group passes"]
+MISSING = ["set_viscous_ML (a no-op with DYNAMIC_VISCOUS_ML=False)", "set_dtbt (calc_dtbt=False: CS%dtbt as stored)", "diagnostics / checksums"]
 
 
 def peaks():
@@ -126,6 +126,35 @@ def make_resident(ctx, stages, nk):
     return out, sum(v.nk for v in cache.values())
 
 
+CS_ST = dict(CAu="u", CAv="v", CAu_pred="u", CAv_pred="v", PFu="u", PFv="v", diffu="u", diffv="v", visc_rem_u="u", visc_rem_v="v", u_accel_bt="u",
+             v_accel_bt="v", u_av="u", v_av="v", h_av="h", pbce="h", eta="h", eta_PF="h", uhbt="u", vhbt="v", taux_bot="u", tauy_bot="v")
+ARG_ST = dict(u_inst="u", v_inst="v", h="h", T="h", S="h", Kv_bbl_u="u", Kv_bbl_v="v", bbl_thick_u="u", bbl_thick_v="v", Kv_shear="h", taux="u",
+              tauy="v", ustar="h", uh="u", vh="v", uhtr="u", vhtr="v", eta_av="h")
+
+
+def step_resident(ctx, dom, cs, sa):
+    """Upload everything a step touches once: MOM_dyn_split_RK2_CS arrays, BT_cont, barotropic_CS and the arguments."""
+    n = [0]
+
+    def pl(name, arr, st, wide=False):
+        nk = arr.shape[0] if arr.ndim == 3 else 1
+        n[0] += nk
+        return ctx.plane(name, arr, st, wide, nk)
+
+    rcs = dict(cs)
+    for k, st in CS_ST.items():
+        rcs[k] = pl("cs." + k, cs[k], st)
+    rcs["BT_cont"] = {k: (pl("btc." + k, v, "u" if ("_u" in k or k.startswith("uBT")) else "v") if isinstance(v, np.ndarray) else v)
+                      for k, v in cs["BT_cont"].items()}
+    rcs["barotropic"] = {k: (pl("bt." + k, v, STAGGER[k], k in WIDE or k == "bathyT") if isinstance(v, np.ndarray) else v)
+                         for k, v in cs["barotropic"].items()}
+    rsa = dict(sa)
+    for k, st in ARG_ST.items():
+        if isinstance(sa.get(k), np.ndarray):
+            rsa[k] = pl("arg." + k, sa[k], st)
+    return rcs, rsa, n[0]
+
+
 def run_step(ctx, stages, times=None):
     """One baroclinic step: the implemented stages in the reference's call counts."""
     for name, calls, _ in STEP:
@@ -164,18 +193,19 @@ def oracle_step(orc, dom, grid, gv, stages, cores):
 def cpu_reference(steps, warmup):
     """The oracle restatement of the reference CPU path, run the way the reference runs on a node: one single-threaded
     worker per host core, each stepping its own tile of the MPI-style decomposition of the workload (SAMPLE = the tile of
-    a 16x8 layout of 1440x1080), no halo exchange (which only flatters the CPU arm)."""
+    a 16x8 layout of 1440x1080) through the whole step_MOM_dyn_split_RK2, no halo exchange between tiles (which only
+    flatters the CPU arm)."""
     import oracle
     import threading
     from mom6_b200 import synthetic
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     ni, nj = SAMPLE
-    work = [synthetic.step_inputs(ni, nj, NK, whalo=10, land_blocks=3, seed=w) for w in range(cores)]
+    work = [synthetic.step_dyn_inputs(ni, nj, NK, whalo=10, land_blocks=3, seed=synthetic.SEED + w, store_CAu=1) for w in range(cores)]
 
     def run(w, n):
-        dom, grid, gv, stages = work[w]
+        dom, grid, gv, css, cs, a = work[w]
         for _ in range(n):
-            oracle_step(oracle, dom, grid, gv, stages, 1)
+            oracle.step_dyn_split_rk2(dom, grid, gv, css, cs, a, nthreads=1)
 
     def all_workers(n):
         th = [threading.Thread(target=run, args=(w, n)) for w in range(cores)]
@@ -190,7 +220,7 @@ def cpu_reference(steps, warmup):
     all_workers(steps)
     t = time.perf_counter() - t0
     return (cores * ni * nj * NK * steps / t, t, cores,
-            f"{steps} step(s) of the same stage list on {cores} concurrent {ni}x{nj}x{NK} tiles (the 16x8 MPI-style decomposition of "
+            f"{steps} step(s) of step_MOM_dyn_split_RK2 on {cores} concurrent {ni}x{nj}x{NK} tiles (the 16x8 MPI-style decomposition of "
             f"the workload, one single-threaded rank per core, no halo exchange)")
 
 
@@ -217,6 +247,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-array leg")
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-stage breakdown")
     ap.add_argument("--size", default=None, help="ni,nj override (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -239,55 +270,74 @@ def main():
     # strong scaling: the global domain is split into npi x npj tiles (one per GPU)
     npi, npj, pi, pj = tile_of(rank, world)
     ni, nj = gni // npi, gnj // npj
-    dom, grid, gv, stages = synthetic.step_inputs(ni, nj, NK, whalo=10, land_blocks=40, seed=synthetic.SEED + rank)
+    dom, grid, gv, css, cs, sa = synthetic.step_dyn_inputs(ni, nj, NK, whalo=10, land_blocks=40, seed=synthetic.SEED + rank, store_CAu=1)
     if world > 1:
         dom.npi, dom.npj, dom.pi, dom.pj = npi, npj, pi, pj
     ctx = Context(dom, local)
     if world > 1:
         ctx.attach_comm(dist)
     ctx.set_grid(grid); ctx.set_vgrid(gv)
-    ctx.set_cs_continuity(stages["continuity"][0]); ctx.set_cs_coriolisadv(stages["coradcalc"][0])
-    ctx.set_cs_hor_visc(stages["horizontal_viscosity"][0]); ctx.set_cs_pressureforce(stages["pressure_force"][0])
-    resident, nplanes = make_resident(ctx, stages, NK)
+    ctx.set_cs_continuity(css["continuity"]); ctx.set_cs_coriolisadv(css["coriolisadv"]); ctx.set_cs_hor_visc(css["hor_visc"])
+    ctx.set_cs_pressureforce(css["pressureforce"]); ctx.set_cs_vertvisc(css["vertvisc"])
+    rcs, rsa, nplanes = step_resident(ctx, dom, cs, sa)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: W warm-up steps, then exactly K steps
+    # ---- device-resident timing: W warm-up steps, then exactly K steps of the whole baroclinic step
     for _ in range(args.warmup):
-        run_step(ctx, resident)
+        ctx.step_dyn_split_rk2(rcs, rsa)
     barrier()
     n1 = ctx.launches
-    times = {}
+    dev_ms = 0.0
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            run_step(ctx, resident, times)
+            ctx.step_dyn_split_rk2(rcs, rsa)
+            dev_ms += ctx.last_kernel_ms
         barrier()
         wall = time.perf_counter() - t0
-    dev_ms = sum(times.values())
     launches = ctx.launches - n1
-    # ---- e2e: host arrays through the C ABI, staging copies inside the timed region
+    # ---- e2e: the model state, tracers and forcing come from pinned HOST arrays every step and the new state goes back to
+    # the host; the control structure (MOM_dyn_split_RK2_CS, BT_cont, barotropic_CS) and the transports stay on the device,
+    # as they do between the reference's own steps.
     e2e_s, e2e_steps, h2d, d2h = None, 0, 0, 0
     if not args.no_e2e:
-        e2e_steps = 1
-        OUT = {"continuity": ("h", "uh", "vh", "u_cor", "v_cor"), "coradcalc": ("CAu", "CAv"), "horizontal_viscosity": ("diffu", "diffv"),
-               "btstep": ("accel_layer_u", "accel_layer_v", "eta_out", "uhbtav", "vhbtav", "etaav"), "btcalc": ("frhatu", "frhatv"),
-               "bt_mass_source": ("eta_cor",), "pressure_force": ("PFu", "PFv", "pbce", "eta")}
-        for name, calls, _ in STEP:
-            cs, a = stages[name]
-            arrs = [v for v in a.values() if isinstance(v, np.ndarray)] + [vv for v in a.values() if isinstance(v, dict) for vv in v.values() if isinstance(vv, np.ndarray)]
-            if name == "btstep":
-                arrs += [v for v in cs.values() if isinstance(v, np.ndarray)]
-            h2d += calls * sum(x.nbytes for x in arrs)
-            d2h += calls * sum(a[k].nbytes for k in OUT[name] if isinstance(a.get(k), np.ndarray))
+        e2e_steps = max(1, min(args.steps, 3))
+        HOST_IN = ("u_inst", "v_inst", "h", "T", "S", "Kv_bbl_u", "Kv_bbl_v", "bbl_thick_u", "bbl_thick_v", "Kv_shear", "taux", "tauy", "ustar")
+        HOST_OUT = ("u_inst", "v_inst", "h", "eta_av")
+        esa = dict(rsa)
+        for k in set(HOST_IN + HOST_OUT):
+            if isinstance(sa.get(k), np.ndarray):
+                t = torch.empty(sa[k].shape, dtype=torch.float64, pin_memory=True)
+                esa[k] = t.numpy()
+                esa[k][...] = sa[k]
+        h2d = sum(esa[k].nbytes for k in HOST_IN if isinstance(esa.get(k), np.ndarray)) + esa["eta_av"].nbytes
+        d2h = sum(esa[k].nbytes for k in HOST_OUT)
+        ctx.step_dyn_split_rk2(rcs, esa)      # first call allocates the staging planes
         barrier()
         t0 = time.perf_counter()
-        run_step(ctx, stages)
+        for _ in range(e2e_steps):
+            ctx.step_dyn_split_rk2(rcs, esa)
         barrier()
         e2e_s = time.perf_counter() - t0
+    # ---- per-stage breakdown (separate stage calls on resident fields; not part of the headline)
+    times, stage_passes = {}, 0
+    if world == 1 and not args.no_stages:
+        ctx.close()
+        domS, gridS, gvS, stages = synthetic.step_inputs(ni, nj, NK, whalo=10, land_blocks=40, seed=synthetic.SEED + rank)
+        ctx = Context(domS, local)
+        ctx.set_grid(gridS); ctx.set_vgrid(gvS)
+        ctx.set_cs_continuity(stages["continuity"][0]); ctx.set_cs_coriolisadv(stages["coradcalc"][0])
+        ctx.set_cs_hor_visc(stages["horizontal_viscosity"][0]); ctx.set_cs_pressureforce(stages["pressure_force"][0])
+        resident, _ = make_resident(ctx, stages, NK)
+        run_step(ctx, resident)
+        stage_passes = 2
+        for _ in range(stage_passes):
+            run_step(ctx, resident, times)
+        barrier()
 
     tmax = torch.tensor([dev_ms, e2e_s or 0.0, wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -304,20 +354,29 @@ def main():
     value = cells * args.steps / (dev_ms * 1e-3)
     peak, peak_src = peaks()
     per_stage = {}
-    for name, calls, bpc in STEP:
-        ms = times[name] / (args.steps * calls)
+    for name, calls, bpc in (STEP if times else []):
+        ms = times[name] / (stage_passes * calls)
         per_stage[name] = {"calls_per_step": calls, "ms_per_call": ms, "algorithmic_B_per_cell": bpc,
                            "achieved_GBps": tile_cells * bpc / (ms * 1e-3) / 1e9, "frac_of_peak": tile_cells * bpc / (ms * 1e-3) / 1e9 / peak}
-    dom_stage = max(per_stage, key=lambda k: per_stage[k]["ms_per_call"] * per_stage[k]["calls_per_step"])
-    ds = per_stage[dom_stage]
+    if per_stage:
+        dom_stage = max(per_stage, key=lambda k: per_stage[k]["ms_per_call"] * per_stage[k]["calls_per_step"])
+        ds = per_stage[dom_stage]
+    else:   # multi-GPU runs: the whole step against the sum of the stages' algorithmic bytes
+        dom_stage = "step"
+        bpc = sum(calls * b for _, calls, b in STEP)
+        ms = dev_ms / args.steps
+        ds = {"achieved_GBps": tile_cells * bpc / (ms * 1e-3) / 1e9, "frac_of_peak": tile_cells * bpc / (ms * 1e-3) / 1e9 / peak,
+              "algorithmic_B_per_cell": bpc}
     kernel_of = {"continuity": "cont_flux_tiled<zonal|meridional> + cont_convergence_kernel", "btstep": "bt_substep_kernel x68 + bt_col_kernel + bt_layer_accel_kernel",
-                 "coradcalc": "corad_kernel", "horizontal_viscosity": "hor_visc_kernel", "btcalc": "btcalc_kernel", "bt_mass_source": "bt_mass_source_kernel"}
+                 "coradcalc": "corad_kernel", "horizontal_viscosity": "hor_visc_kernel", "btcalc": "btcalc_kernel", "bt_mass_source": "bt_mass_source_kernel",
+                 "pressure_force": "pgf_main_kernel", "step": "all stage kernels of one step"}
     line = {"metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"OM4_025-shaped {gni}x{gnj}x{NK} split-RK2 dynamics step", "stages": STAGES, "stages_missing": MISSING,
                        "tiles": f"{npi}x{npj}", "resident_planes": nplanes,
-                       "l2": f"inputs larger than L2 ({nplanes * ni * nj * 8 / 1e9:.1f} GB of resident fields swept per step)"},
+                       "l2": f"inputs larger than L2 ({nplanes * ni * nj * 8 / 1e9:.1f} GB of resident fields swept per step)",
+                       "e2e": "state u,v,h + T,S + visc% + forces% from pinned host arrays each step, u,v,h,eta_av back; CS arrays and transports resident"},
             "e2e": None if e2e_s is None else {"value": cells * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
                                                "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "ms_per_step_wall": 1e3 * wall / args.steps,

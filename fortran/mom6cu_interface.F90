@@ -81,6 +81,99 @@ module mom6cu_interface
     real(c_double) :: dt
   end type mom6cu_hor_visc_args
 
+  !> unit_scale_type factors (src/framework/MOM_unit_scaling.F90)
+  type, bind(C) :: mom6cu_unit_scale
+    real(c_double) :: m_to_L, L_to_m, m_s_to_L_T, L_T_to_m_s, s_to_T, T_to_s, m_to_Z, Z_to_m, Z_to_L, L_to_Z
+  end type mom6cu_unit_scale
+
+  !> PressureForce_FV_CS / EOS parameters (src/core/MOM_PressureForce_FV.F90:40-107)
+  type, bind(C) :: mom6cu_pressureforce_cs
+    integer(c_int) :: EOS_form, MassWghtInterp, use_SSH_in_Z0p, rho_ref_bug, unsupported
+    real(c_double) :: rho_ref, GFS_scale, Z_ref, dZ_subroundoff
+    real(c_double) :: Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp
+    type(c_ptr) :: Rlay, g_prime
+  end type mom6cu_pressureforce_cs
+  !> Arguments of PressureForce (src/core/MOM_PressureForce.F90:40-61)
+  type, bind(C) :: mom6cu_pressureforce_args
+    type(c_ptr) :: h, T, S, PFu, PFv, p_atm, pbce, eta
+  end type mom6cu_pressureforce_args
+
+  !> vertvisc_CS (src/parameterizations/vertical/MOM_vert_friction.F90:48-170)
+  type, bind(C) :: mom6cu_vertvisc_cs
+    integer(c_int) :: bottomdraglaw, harmonic_visc, direct_stress, fixed_LOTW_ML, apply_LOTW_floor, dynamic_viscous_ML, &
+                      nkml, answer_date, unsupported
+    real(c_double) :: Hbbl, Kv, Kv_extra_bbl, Kvml_invZ2, Hmix, Hmix_stress, harm_BL_val, vonKar, vel_underflow, dZ_subroundoff
+  end type mom6cu_vertvisc_cs
+  type, bind(C) :: mom6cu_vertvisc_coef_args
+    type(c_ptr) :: u, v, h, Kv_bbl_u, Kv_bbl_v, bbl_thick_u, bbl_thick_v, Kv_shear, Kv_shear_Bu, ustar
+    real(c_double) :: dt
+  end type mom6cu_vertvisc_coef_args
+  type, bind(C) :: mom6cu_vertvisc_args
+    type(c_ptr) :: u, v, h, taux, tauy, Ray_u, Ray_v
+    real(c_double) :: dt
+    type(c_ptr) :: taux_bot, tauy_bot
+  end type mom6cu_vertvisc_args
+
+  !> barotropic_CS members (src/core/MOM_barotropic.F90:112-364) and the arguments of btstep (:455-529)
+  type, bind(C) :: mom6cu_barotropic_cs
+    integer(c_int) :: Sadourny, BT_project_velocity, strong_drag, bound_BT_corr, BT_cont_bounds, wt_uv_bug, visc_rem_u_uh0, &
+                      adjust_BT_cont, use_wide_halos, min_stencil, use_old_coriolis_bracket_bug, unsupported
+    real(c_double) :: dtbt, bebt, vel_underflow, maxCFL_BT_cont, G_extra, dt_bt_filter
+    type(c_ptr) :: IareaT, IareaT_OBCmask, bathyT, IdxCu, IdyCv, q_D, D_u_Cor, D_v_Cor, ua_polarity, va_polarity, OBCmask_u, OBCmask_v
+    type(c_ptr) :: frhatu, frhatv, eta_cor, eta_cor_bound, IDatu, IDatv, ubtav, vbtav
+  end type mom6cu_barotropic_cs
+  type, bind(C) :: mom6cu_btstep_args
+    type(c_ptr) :: U_in, V_in, eta_in
+    real(c_double) :: dt
+    type(c_ptr) :: bc_accel_u, bc_accel_v, taux, tauy, pbce, eta_PF_in, U_Cor, V_Cor, accel_layer_u, accel_layer_v, eta_out, &
+                   uhbtav, vhbtav, visc_rem_u, visc_rem_v, BT_cont, taux_bot, tauy_bot, uh0, vh0, u_uh0, v_vh0, etaav
+  end type mom6cu_btstep_args
+
+  !> MOM_dyn_split_RK2_CS members (src/core/MOM_dynamics_split_RK2.F90:85-273) and the arguments of
+  !! step_MOM_dyn_split_RK2 (:294-296)
+  type, bind(C) :: mom6cu_dyn_split_rk2_cs
+    real(c_double) :: be, begw
+    integer(c_int) :: split_bottom_stress, store_CAu, CAu_pred_stored, visc_rem_dt_bug, hvel_scheme, unsupported
+    type(c_ptr) :: CAu, CAv, CAu_pred, CAv_pred, PFu, PFv, diffu, diffv, visc_rem_u, visc_rem_v, u_accel_bt, v_accel_bt, &
+                   u_av, v_av, h_av, pbce, eta, eta_PF, uhbt, vhbt, taux_bot, tauy_bot
+    type(c_ptr) :: BT_cont, barotropic
+  end type mom6cu_dyn_split_rk2_cs
+  type, bind(C) :: mom6cu_step_dyn_args
+    type(c_ptr) :: u_inst, v_inst, h, T, S, Kv_bbl_u, Kv_bbl_v, bbl_thick_u, bbl_thick_v, Kv_shear, Kv_shear_Bu, Ray_u, Ray_v, &
+                   taux, tauy, ustar, p_surf
+    real(c_double) :: dt
+    type(c_ptr) :: uh, vh, uhtr, vhtr, eta_av
+    integer(c_int) :: calc_dtbt
+  end type mom6cu_step_dyn_args
+
+  !> tracer_advect_CS and the arguments of advect_tracer (src/tracer/MOM_tracer_advect.F90:32-54)
+  type, bind(C) :: mom6cu_tracer_advect_cs
+    real(c_double) :: dt
+    integer(c_int) :: default_advect_scheme, useHuynhStencilBug
+  end type mom6cu_tracer_advect_cs
+  type, bind(C) :: mom6cu_advect_tracer_args
+    type(c_ptr) :: h_end, uhtr, vhtr
+    real(c_double) :: dt
+    integer(c_int) :: ntr
+    type(c_ptr) :: tr, advect_scheme, conc_underflow   ! tr: array of ntr c_ptr (Reg%Tr(m)%t)
+    integer(c_int) :: x_first_in, max_iter_in
+    type(c_ptr) :: vol_prev
+    integer(c_int) :: update_vol_prev
+    type(c_ptr) :: uhr_out, vhr_out
+  end type mom6cu_advect_tracer_args
+
+  !> remapping_CS (src/ALE/MOM_remapping.F90:37-85) and regridding_CS (src/ALE/MOM_regridding.F90:49-160)
+  type, bind(C) :: mom6cu_remapping_cs
+    integer(c_int) :: remapping_scheme, boundary_extrapolation, force_bounds_in_subcell, force_bounds_in_target, &
+                      om4_remap_via_sub_cells, answer_date
+    real(c_double) :: h_neglect, h_neglect_edge
+  end type mom6cu_remapping_cs
+  type, bind(C) :: mom6cu_regridding_cs
+    integer(c_int) :: regridding_scheme, nk
+    real(c_double) :: min_thickness, old_grid_weight, depth_of_time_filter_shallow, depth_of_time_filter_deep, Z_ref
+    type(c_ptr) :: coordinateResolution
+  end type mom6cu_regridding_cs
+
   interface
     integer(c_int) function mom6cu_create(ctx, dom, device) bind(C, name="mom6cu_create")
       import :: c_int, c_ptr, mom6cu_domain
@@ -156,6 +249,56 @@ module mom6cu_interface
       type(c_ptr), value :: ctx, id
       integer(c_int), value :: nbytes, rank, nranks
     end function mom6cu_comm_init
+    integer(c_int) function mom6cu_set_unit_scale(ctx, US) bind(C, name="mom6cu_set_unit_scale")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_unit_scale), intent(in) :: US
+    end function mom6cu_set_unit_scale
+    integer(c_int) function mom6cu_set_cs_pressureforce(ctx, CS) bind(C, name="mom6cu_set_cs_pressureforce")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_pressureforce_cs), intent(in) :: CS
+    end function mom6cu_set_cs_pressureforce
+    integer(c_int) function mom6cu_pressure_force(ctx, a) bind(C, name="mom6cu_pressure_force")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_pressureforce_args), intent(in) :: a
+    end function mom6cu_pressure_force
+    integer(c_int) function mom6cu_set_cs_vertvisc(ctx, CS) bind(C, name="mom6cu_set_cs_vertvisc")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_vertvisc_cs), intent(in) :: CS
+    end function mom6cu_set_cs_vertvisc
+    integer(c_int) function mom6cu_vertvisc_coef(ctx, a) bind(C, name="mom6cu_vertvisc_coef")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_vertvisc_coef_args), intent(in) :: a
+    end function mom6cu_vertvisc_coef
+    integer(c_int) function mom6cu_vertvisc(ctx, a) bind(C, name="mom6cu_vertvisc")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_vertvisc_args), intent(in) :: a
+    end function mom6cu_vertvisc
+    integer(c_int) function mom6cu_vertvisc_remnant(ctx, Ray_u, Ray_v, visc_rem_u, visc_rem_v, dt) bind(C, name="mom6cu_vertvisc_remnant")
+      import ; type(c_ptr), value :: ctx, Ray_u, Ray_v, visc_rem_u, visc_rem_v ; real(c_double), value :: dt
+    end function mom6cu_vertvisc_remnant
+    integer(c_int) function mom6cu_btstep(ctx, CS, a) bind(C, name="mom6cu_btstep")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_barotropic_cs), intent(in) :: CS ; type(mom6cu_btstep_args), intent(in) :: a
+    end function mom6cu_btstep
+    integer(c_int) function mom6cu_bt_mass_source(ctx, h, eta, set_cor, eta_cor) bind(C, name="mom6cu_bt_mass_source")
+      import ; type(c_ptr), value :: ctx, h, eta, eta_cor ; integer(c_int), value :: set_cor
+    end function mom6cu_bt_mass_source
+    integer(c_int) function mom6cu_step_dyn_split_rk2(ctx, CS, a) bind(C, name="mom6cu_step_dyn_split_rk2")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_dyn_split_rk2_cs), intent(inout) :: CS ; type(mom6cu_step_dyn_args), intent(in) :: a
+    end function mom6cu_step_dyn_split_rk2
+    integer(c_int) function mom6cu_advect_tracer(ctx, CS, a) bind(C, name="mom6cu_advect_tracer")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_tracer_advect_cs), intent(in) :: CS ; type(mom6cu_advect_tracer_args), intent(in) :: a
+    end function mom6cu_advect_tracer
+    integer(c_int) function mom6cu_ale_regrid(ctx, CS, h, h_new, dzRegrid) bind(C, name="mom6cu_ale_regrid")
+      import ; type(c_ptr), value :: ctx, h, h_new, dzRegrid ; type(mom6cu_regridding_cs), intent(in) :: CS
+    end function mom6cu_ale_regrid
+    integer(c_int) function mom6cu_ale_remap_tracers(ctx, CS, h_old, h_new, ntr, tr, conc_underflow) bind(C, name="mom6cu_ale_remap_tracers")
+      import ; type(c_ptr), value :: ctx, h_old, h_new, tr, conc_underflow ; type(mom6cu_remapping_cs), intent(in) :: CS
+      integer(c_int), value :: ntr
+    end function mom6cu_ale_remap_tracers
+    integer(c_int) function mom6cu_ale_remap_set_h_vel(ctx, h_new, h_u, h_v) bind(C, name="mom6cu_ale_remap_set_h_vel")
+      import ; type(c_ptr), value :: ctx, h_new, h_u, h_v
+    end function mom6cu_ale_remap_set_h_vel
+    integer(c_int) function mom6cu_ale_remap_velocities(ctx, CS, h_old_u, h_old_v, h_new_u, h_new_v, u, v) &
+        bind(C, name="mom6cu_ale_remap_velocities")
+      import ; type(c_ptr), value :: ctx, h_old_u, h_old_v, h_new_u, h_new_v, u, v ; type(mom6cu_remapping_cs), intent(in) :: CS
+    end function mom6cu_ale_remap_velocities
+    type(c_ptr) function mom6cu_plane_alloc(ctx, name, nk) bind(C, name="mom6cu_plane_alloc")
+      import ; type(c_ptr), value :: ctx ; character(kind=c_char), intent(in) :: name(*) ; integer(c_int), value :: nk
+    end function mom6cu_plane_alloc
   end interface
 
   !> The one device context of this PE (one MPI rank = one tile = one GPU)

@@ -520,6 +520,23 @@ int mom6cu_btcalc(mom6cu_ctx* ctx, const mom6cu_btcalc_args* a);
  * eta_mass_source: CS%eta_source (2-D h) or NULL. */
 int mom6cu_bt_mass_source(mom6cu_ctx* ctx, const double* h, const double* eta, int set_cor, double* eta_cor);
 
+/* set_dtbt(G, GV, US, CS, pbce, gtot_est, BT_cont, eta, SSH_add)  MOM_barotropic.F90:3509-3633: the stable barotropic
+ * time step.  The barotropic_CS members it reads are explicit; CS%dy_Cu / dx_Cv are G's.  No SAL (det_de = 0).
+ * Returns CS%dtbt and CS%dtbt_max (min_across_PEs included). */
+typedef struct mom6cu_set_dtbt_args {
+  const double* pbce;            /* 3-D h, or NULL when gtot_est is given */
+  double gtot_est;
+  int have_gtot_est;
+  const mom6cu_bt_cont* BT_cont; /* or NULL */
+  const double* eta;             /* 2-D h, or NULL */
+  double SSH_add;
+  const double *frhatu, *frhatv; /* CS%frhatu, frhatv (3-D u, v) */
+  const double* bathyT;          /* CS%bathyT on G's memory domain */
+  double bebt, G_extra, dtbt_fraction, BT_Coriolis_scale, Z_ref;
+  int Nonlinear_continuity;
+} mom6cu_set_dtbt_args;
+int mom6cu_set_dtbt(mom6cu_ctx* ctx, const mom6cu_set_dtbt_args* a, double* dtbt, double* dtbt_max);
+
 /* Microbenchmark form: upload once (state + coefficients stay resident in
  * HBM), run the substep loop `reps` times from the same initial state, and
  * return the device time of the LAST repetition through mom6cu_last_kernel_ms.
@@ -533,19 +550,22 @@ int mom6cu_btstep_timeloop_resident(mom6cu_ctx* ctx, const mom6cu_bt_timeloop_ar
  * device between steps -- or a host array (staged in and out by the call).  The stage control structures are the ones
  * given to mom6cu_set_cs_{continuity,coriolisadv,hor_visc,pressureforce,vertvisc}.
  * Frozen: no OBCs, no Stokes / fpmix, no dynamic surface pressure (p_surf_begin/end absent), BT_USE_LAYER_FLUXES=True,
- * BT_cont associated with h_u/h_v allocated (BT_THICK_SCHEME=FROM_BT_CONT), calc_dtbt=.false. (CS%dtbt as stored),
- * set_viscous_ML a no-op (DYNAMIC_VISCOUS_ML=False), no diagnostics. */
+ * BT_cont associated with h_u/h_v allocated (BT_THICK_SCHEME=FROM_BT_CONT), set_viscous_ML a no-op
+ * (DYNAMIC_VISCOUS_ML=False), no diagnostics.  With calc_dtbt the step calls set_dtbt (:665-669) and stores the new
+ * barotropic%dtbt. */
 typedef struct mom6cu_dyn_split_rk2_cs {
   double be, begw;
   int split_bottom_stress, store_CAu, CAu_pred_stored /* updated */, visc_rem_dt_bug, hvel_scheme /* barotropic CS%hvel_scheme */,
       unsupported;
+  int dtbt_use_bt_cont, BT_Nonlinear_continuity;           /* CS%dtbt_use_bt_cont; barotropic CS%Nonlinear_continuity */
+  double dtbt_fraction, BT_Coriolis_scale, Z_ref, dtbt_max; /* barotropic CS%dtbt_fraction, BT_Coriolis_scale; G%Z_ref; dtbt_max out */
   double *CAu, *CAv, *CAu_pred, *CAv_pred, *PFu, *PFv, *diffu, *diffv; /* 3-D u / v */
   double *visc_rem_u, *visc_rem_v, *u_accel_bt, *v_accel_bt, *u_av, *v_av; /* 3-D u / v */
   double *h_av, *pbce;                                                  /* 3-D h */
   double *eta, *eta_PF;                                                 /* 2-D h */
   double *uhbt, *vhbt, *taux_bot, *tauy_bot;                            /* 2-D u / v */
   mom6cu_bt_cont* BT_cont;
-  const mom6cu_barotropic_cs* barotropic;
+  mom6cu_barotropic_cs* barotropic; /* dtbt is updated when calc_dtbt */
 } mom6cu_dyn_split_rk2_cs;
 /* step_MOM_dyn_split_RK2(u_inst, v_inst, h, tv, visc, Time_local, dt, forces, p_surf_begin, p_surf_end, uh, vh, uhtr,
  *   vhtr, eta_av, G, GV, US, CS, calc_dtbt, VarMix, MEKE, thickness_diffuse_CSp, pbv, STOCH, Waves)   :294-296 */
@@ -558,7 +578,7 @@ typedef struct mom6cu_step_dyn_args {
   double *uh, *vh;      /* 3-D u / v, in/out */
   double *uhtr, *vhtr;  /* 3-D u / v, in/out */
   double *eta_av;       /* 2-D h, out */
-  int calc_dtbt;        /* must be 0 */
+  int calc_dtbt;
 } mom6cu_step_dyn_args;
 int mom6cu_step_dyn_split_rk2(mom6cu_ctx* ctx, mom6cu_dyn_split_rk2_cs* CS, const mom6cu_step_dyn_args* a);
 

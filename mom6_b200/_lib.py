@@ -187,11 +187,20 @@ class RemappingCS(C.Structure):
 class DynSplitRK2CS(C.Structure):
     """mom6cu_dyn_split_rk2_cs: MOM_dyn_split_RK2_CS members (src/core/MOM_dynamics_split_RK2.F90:85-273)."""
     _fields_ = [("be", C.c_double), ("begw", C.c_double)] + \
-               [(n, C.c_int) for n in ("split_bottom_stress", "store_CAu", "CAu_pred_stored", "visc_rem_dt_bug", "hvel_scheme", "unsupported")] + \
+               [(n, C.c_int) for n in ("split_bottom_stress", "store_CAu", "CAu_pred_stored", "visc_rem_dt_bug", "hvel_scheme", "unsupported",
+                                       "dtbt_use_bt_cont", "BT_Nonlinear_continuity")] + \
+               [(n, C.c_double) for n in ("dtbt_fraction", "BT_Coriolis_scale", "Z_ref", "dtbt_max")] + \
                [(n, C.c_void_p) for n in ("CAu", "CAv", "CAu_pred", "CAv_pred", "PFu", "PFv", "diffu", "diffv", "visc_rem_u", "visc_rem_v",
                                           "u_accel_bt", "v_accel_bt", "u_av", "v_av", "h_av", "pbce", "eta", "eta_PF", "uhbt", "vhbt",
                                           "taux_bot", "tauy_bot")] + \
                [("BT_cont", C.POINTER(BTCont)), ("barotropic", C.POINTER(BarotropicCS))]
+
+
+class SetDtbtArgs(C.Structure):
+    """mom6cu_set_dtbt_args: set_dtbt (MOM_barotropic.F90:3509)."""
+    _fields_ = [("pbce", C.c_void_p), ("gtot_est", C.c_double), ("have_gtot_est", C.c_int), ("BT_cont", C.POINTER(BTCont)), ("eta", C.c_void_p),
+                ("SSH_add", C.c_double), ("frhatu", C.c_void_p), ("frhatv", C.c_void_p), ("bathyT", C.c_void_p)] + \
+               [(n, C.c_double) for n in ("bebt", "G_extra", "dtbt_fraction", "BT_Coriolis_scale", "Z_ref")] + [("Nonlinear_continuity", C.c_int)]
 
 
 class StepDynArgs(C.Structure):
@@ -308,6 +317,7 @@ def bind(lib):
     lib.mom6cu_ale_remap_set_h_vel.argtypes = [vp, vp, vp, vp]
     lib.mom6cu_ale_remap_velocities.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, vp, vp, vp, vp]
     lib.mom6cu_remapping_core_h.argtypes = [vp, C.POINTER(RemappingCS), C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.mom6cu_set_dtbt.argtypes = [vp, C.POINTER(SetDtbtArgs), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.mom6cu_step_dyn_split_rk2.argtypes = [vp, C.POINTER(DynSplitRK2CS), C.POINTER(StepDynArgs)]
     lib.mom6cu_set_cs_vertvisc.argtypes = [vp, C.POINTER(VertviscCS)]
     lib.mom6cu_vertvisc_coef.argtypes = [vp, C.POINTER(VertviscCoefArgs)]

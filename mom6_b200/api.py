@@ -257,8 +257,18 @@ def _ctx_methods():
         st = marshal.dyn_split_rk2_cs(cs, keep)
         rc = self._check(self.lib.mom6cu_step_dyn_split_rk2(self._h, C.byref(st), C.byref(marshal.step_dyn_args(args, keep))))
         cs["CAu_pred_stored"] = int(st.CAu_pred_stored)
+        cs["dtbt_max"] = float(st.dtbt_max)
+        cs["barotropic"]["dtbt"] = float(st.barotropic.contents.dtbt)
         return rc
 
+    def set_dtbt(self, args):
+        """set_dtbt, MOM_barotropic.F90:3509; returns (CS%dtbt, CS%dtbt_max)."""
+        keep = []
+        dtbt, dmax = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.lib.mom6cu_set_dtbt(self._h, C.byref(marshal.set_dtbt_args(args, keep)), C.byref(dtbt), C.byref(dmax)))
+        return dtbt.value, dmax.value
+
+    setattr(Context, "set_dtbt", set_dtbt)
     setattr(Context, "step_dyn_split_rk2", step_dyn_split_rk2)
     for f in (set_cs_vertvisc, vertvisc_coef, vertvisc_get_coef, vertvisc, vertvisc_remnant):
         setattr(Context, f.__name__, f)

@@ -682,3 +682,119 @@ extern "C" int mom6cu_bt_mass_source(mom6cu_ctx* c, const double* h, const doubl
   if ((rc = m6_bt_mass_source_run(c, dh, de, set_cor, dc))) return rc;
   return S.finish();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// set_dtbt, MOM_barotropic.F90:3509-3633.  One thread per h-point: the four k-ordered sums gtot_[EWNS] (:3593-3598), the
+// face areas of its four faces (BT_cont_to_face_areas :5107 / find_face_areas :5146, halo 0) and Idt_max2 (:3611-3616).
+// The reference then scans the points in memory order with `if (Idt_max2*min_max_dt2 > 1.) min_max_dt2 = 1./Idt_max2`,
+// which is not exactly a minimum of 1/Idt_max2 in floating point, so that scan is done in the same order on the host
+// from a pinned copy of the 2-D field (one 2-D download per call; set_dtbt runs once per coupling step at most).
+namespace {
+struct DtbtK {
+  int is, ie, js, je, nz, mode;  // mode 0: BT_cont, 1: eta (Nonlinear_continuity), 2: bathymetry + add_max
+  double gtot_est, Z_to_H, zadd, bebt, cor_scale2;
+  const double *pbce, *frhatu, *frhatv, *bathyT, *eta;
+  const double *EE, *E0, *W0, *WW, *NN, *N0, *S0, *SS;
+  const double *dy_Cu, *dx_Cv, *IdxCu, *IdyCv, *IareaT, *Coriolis2Bu;
+  double* out;  // packed (je-js+1) x (ie-is+1)
+};
+__device__ __forceinline__ double dtbt_face(const DtbtK& P, const Geom& G, long long g, bool uface) {
+  const long long s = uface ? 1 : G.pitch;
+  if (P.mode == 0) {
+    const double* a = uface ? P.EE : P.NN; const double* b = uface ? P.E0 : P.N0; const double* c = uface ? P.W0 : P.S0;
+    const double* d = uface ? P.WW : P.SS;
+    return fmax2(fmax2(fmax2(a[g], b[g]), c[g]), d[g]);
+  }
+  const double len = uface ? P.dy_Cu[g] : P.dx_Cv[g];
+  if (P.mode == 1) {
+    const double H1 = P.bathyT[g] * P.Z_to_H + P.eta[g], H2 = P.bathyT[g + s] * P.Z_to_H + P.eta[g + s];
+    return ((H1 > 0.0) && (H2 > 0.0)) ? len * (2.0 * H1 * H2) / (H1 + H2) : 0.0;
+  }
+  return len * P.Z_to_H * fmax2(fmax2(P.bathyT[g + s], P.bathyT[g]) + P.zadd, 0.0);
+}
+__global__ void set_dtbt_kernel(Geom G, DtbtK P) {
+  const int i = P.is + blockIdx.x * blockDim.x + threadIdx.x, j = P.js + blockIdx.y;
+  if (i > P.ie) return;
+  const long long g = G.idx(i, j), pl = G.plane, pt = G.pitch;
+  double gE = 0.0, gW = 0.0, gN = 0.0, gS = 0.0;
+  if (P.pbce) {
+    for (int k = 0; k < P.nz; ++k) {
+      const long long o = (long long)k * pl + g;
+      const double pb = P.pbce[o];
+      gE = gE + pb * P.frhatu[o]; gW = gW + pb * P.frhatu[o - 1];
+      gN = gN + pb * P.frhatv[o]; gS = gS + pb * P.frhatv[o - pt];
+    }
+  } else { gE = gW = gN = gS = P.gtot_est; }
+  const double DuE = dtbt_face(P, G, g, true), DuW = dtbt_face(P, G, g - 1, true);
+  const double DvN = dtbt_face(P, G, g, false), DvS = dtbt_face(P, G, g - pt, false);
+  const double* C2 = P.Coriolis2Bu;
+  const double Idt_max2 = 0.5 * (1.0 + 2.0 * P.bebt) * (P.IareaT[g] *
+      (((gE * DuE * P.IdxCu[g]) + (gW * DuW * P.IdxCu[g - 1])) + ((gN * DvN * P.IdyCv[g]) + (gS * DvS * P.IdyCv[g - pt]))) +
+      ((C2[g] + C2[g - 1 - pt]) + (C2[g - 1] + C2[g - pt])) * P.cor_scale2);
+  P.out[(size_t)(j - P.js) * (P.ie - P.is + 1) + (i - P.is)] = Idt_max2;
+}
+}  // namespace
+
+// device-level: every array pointer is a resident plane
+int m6_set_dtbt_run(mom6cu_ctx* c, const mom6cu_set_dtbt_args& a, double* dtbt, double* dtbt_max) {
+  const Geom& G = c->g;
+  const mom6cu_domain& d = c->dom;
+  const int ni = d.iec - d.isc + 1, nj = d.jec - d.jsc + 1;
+  const size_t n = (size_t)ni * nj;
+  double* dev = c->buf("dtbt.Idt", n);
+  double* host = c->host_scratch("dtbt.Idt", n);
+  if (!dev || !host) return MOM6CU_ERR_CUDA;
+  DtbtK P = {};
+  P.is = d.isc; P.ie = d.iec; P.js = d.jsc; P.je = d.jec; P.nz = G.nk;
+  P.gtot_est = a.gtot_est; P.Z_to_H = c->vgrid.Z_to_H; P.zadd = a.Z_ref + a.SSH_add; P.bebt = a.bebt;
+  P.cor_scale2 = a.BT_Coriolis_scale * a.BT_Coriolis_scale;
+  P.pbce = a.pbce; P.frhatu = a.frhatu; P.frhatv = a.frhatv; P.bathyT = a.bathyT; P.eta = a.eta;
+  if (a.BT_cont) {
+    const mom6cu_bt_cont* B = a.BT_cont;
+    P.mode = 0; P.EE = B->FA_u_EE; P.E0 = B->FA_u_E0; P.W0 = B->FA_u_W0; P.WW = B->FA_u_WW; P.NN = B->FA_v_NN; P.N0 = B->FA_v_N0;
+    P.S0 = B->FA_v_S0; P.SS = B->FA_v_SS;
+  } else if (a.Nonlinear_continuity && a.eta) P.mode = 1;
+  else P.mode = 2;
+  P.dy_Cu = c->grid.dy_Cu; P.dx_Cv = c->grid.dx_Cv; P.IdxCu = c->grid.IdxCu; P.IdyCv = c->grid.IdyCv; P.IareaT = c->grid.IareaT;
+  P.Coriolis2Bu = c->grid.Coriolis2Bu; P.out = dev;
+  M6_LAUNCH(c, set_dtbt_kernel, dim3((ni + 127) / 128, nj), 128, 0, G, P);
+  M6_CUDA(c, cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  double min_max_dt2 = 1.0e38 * (c->US.s_to_T * c->US.s_to_T);
+  for (size_t q = 0; q < n; ++q) if (host[q] * min_max_dt2 > 1.0) min_max_dt2 = 1.0 / host[q];
+  const double dgeo_de = 1.0 + std::max(0.0, a.G_extra - 0.0);
+  double mx = std::sqrt(min_max_dt2 / dgeo_de);
+  int rc;
+  if (c->nranks > 1 && (rc = m6_allreduce_min_double(c, &mx))) return rc;  // min_across_PEs :3621
+  *dtbt = a.dtbt_fraction * mx;
+  *dtbt_max = mx;
+  return 0;
+}
+
+extern "C" int mom6cu_set_dtbt(mom6cu_ctx* c, const mom6cu_set_dtbt_args* a, double* dtbt, double* dtbt_max) {
+  if (!c || !a || !dtbt || !dtbt_max) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  if (!c->have_grid || !c->have_vgrid) return c->fail(MOM6CU_ERR_BAD_ARG, "set_dtbt: mom6cu_set_grid / mom6cu_set_vgrid have not been called");
+  if (!(a->pbce || a->have_gtot_est)) return c->fail(MOM6CU_ERR_BAD_ARG, "set_dtbt: Either pbce or gtot_est must be present.");
+  if (!c->vgrid.Boussinesq) return c->fail(MOM6CU_ERR_UNSUPPORTED, "set_dtbt: non-Boussinesq face areas are not implemented");
+  if (a->pbce && (!a->frhatu || !a->frhatv)) return c->fail(MOM6CU_ERR_BAD_ARG, "set_dtbt: CS%%frhatu / frhatv are null");
+  if (!a->bathyT) return c->fail(MOM6CU_ERR_BAD_ARG, "set_dtbt: CS%%bathyT is null");
+  Stager S(c, "dtbt.");
+  mom6cu_set_dtbt_args D = *a;
+  mom6cu_bt_cont B = {};
+  int rc;
+  if ((rc = S.in3(a->pbce, ST_H, "pbce", &D.pbce)) || (rc = S.in3(a->frhatu, ST_U, "frhatu", &D.frhatu)) ||
+      (rc = S.in3(a->frhatv, ST_V, "frhatv", &D.frhatv)) || (rc = S.in2(a->bathyT, ST_H, "bathyT", &D.bathyT)) ||
+      (rc = S.in2(a->eta, ST_H, "eta", &D.eta))) return rc;
+  if (a->BT_cont) {
+    const mom6cu_bt_cont* H = a->BT_cont;
+    const double* p;
+#define FA(f, st) if (!H->f) return c->fail(MOM6CU_ERR_BAD_ARG, "set_dtbt: BT_cont%%" #f " is not allocated"); if ((rc = S.in2(H->f, st, #f, &p))) return rc; B.f = (double*)p
+    FA(FA_u_EE, ST_U); FA(FA_u_E0, ST_U); FA(FA_u_W0, ST_U); FA(FA_u_WW, ST_U); FA(FA_v_NN, ST_V); FA(FA_v_N0, ST_V); FA(FA_v_S0, ST_V); FA(FA_v_SS, ST_V);
+#undef FA
+    D.BT_cont = &B;
+  }
+  if ((rc = S.begin())) return rc;
+  if ((rc = m6_set_dtbt_run(c, D, dtbt, dtbt_max))) return rc;
+  return S.finish();
+}

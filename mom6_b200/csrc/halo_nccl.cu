@@ -115,6 +115,22 @@ int m6_allreduce_max_int(mom6cu_ctx* c, int* v) {
   return 0;
 }
 
+int m6_allreduce_min_double(mom6cu_ctx* c, double* v) {
+  if (c->nranks <= 1) return 0;
+  if (!c->comm) return c->fail(MOM6CU_ERR_NCCL, "multi-rank reduction requested but no communicator is attached");
+  double* d = c->buf("comm.dmin", 2);
+  double* h = c->host_scratch("comm.dmin", 2);
+  if (!d || !h) return MOM6CU_ERR_CUDA;
+  h[0] = *v;
+  M6_CUDA(c, cudaMemcpyAsync(d, h, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  ncclResult_t r = ncclAllReduce(d, d, 1, ncclDouble, ncclMin, (ncclComm_t)c->comm, c->stream);
+  if (r != ncclSuccess) return c->fail(MOM6CU_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r));
+  M6_CUDA(c, cudaMemcpyAsync(h, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  *v = h[0];
+  return 0;
+}
+
 extern "C" int mom6cu_comm_destroy(mom6cu_ctx* c) {
   if (c && c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
   return 0;

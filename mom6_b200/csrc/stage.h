@@ -79,6 +79,7 @@ int m6_vertvisc_run(mom6cu_ctx* c, const VvDev& D);
 int m6_vertvisc_remnant_run(mom6cu_ctx* c, const double* Ray_u, const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt);
 // stage the array members of a barotropic_CS given with host or resident pointers into *CS (device pointers)
 int m6_stage_barotropic_cs(mom6cu_ctx* c, Stager& S, const mom6cu_barotropic_cs* CSh, mom6cu_barotropic_cs* CS);
+int m6_set_dtbt_run(mom6cu_ctx* c, const mom6cu_set_dtbt_args& a, double* dtbt, double* dtbt_max);
 int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D);
 // CS holds device pointers (resident planes) for every array member
 int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev& D);

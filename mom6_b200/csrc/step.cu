@@ -89,7 +89,6 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
     return c->fail(MOM6CU_ERR_BAD_ARG, "step_MOM_dyn_split_RK2: the grid and the continuity, CoriolisAdv, hor_visc, PressureForce and "
                                        "vertvisc control structures must be set first");
   if (CS->unsupported) return c->fail(MOM6CU_ERR_UNSUPPORTED, "step_MOM_dyn_split_RK2: the host configuration uses an option outside the frozen set");
-  if (a->calc_dtbt) return c->fail(MOM6CU_ERR_UNSUPPORTED, "step_MOM_dyn_split_RK2: calc_dtbt (set_dtbt) is not implemented; pass CS%%dtbt");
   if (!CS->BT_cont || !CS->BT_cont->h_u || !CS->BT_cont->h_v || !CS->barotropic)
     return c->fail(MOM6CU_ERR_UNSUPPORTED, "step_MOM_dyn_split_RK2: BT_cont with h_u, h_v (BT_THICK_SCHEME=FROM_BT_CONT) is required");
   if (!a->u_inst || !a->v_inst || !a->h || !a->uh || !a->vh || !a->uhtr || !a->vhtr || !a->eta_av || !a->taux || !a->tauy)
@@ -189,6 +188,19 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   C1.u = u; C1.v = v; C1.hin = h; C1.h = hp; C1.uh = uh_in; C1.vh = vh_in; C1.dt = dt; C1.visc_rem_u = vru; C1.visc_rem_v = vrv; C1.have_BT_cont = 1;
   if ((rc = m6_continuity_run(c, C1))) return rc;
   if ((rc = m6_btcalc_run(c, h, CD.h_u, CD.h_v, c->grid.bathyT, CS->hvel_scheme, 0, (double*)BCS.frhatu, (double*)BCS.frhatv))) return rc;
+  // :663-669 set_dtbt
+  if (a->calc_dtbt) {
+    mom6cu_set_dtbt_args sd = {};
+    mom6cu_bt_cont Bd = {};
+    Bd.FA_u_EE = CD.FA_u_EE; Bd.FA_u_E0 = CD.FA_u_E0; Bd.FA_u_W0 = CD.FA_u_W0; Bd.FA_u_WW = CD.FA_u_WW;
+    Bd.FA_v_NN = CD.FA_v_NN; Bd.FA_v_N0 = CD.FA_v_N0; Bd.FA_v_S0 = CD.FA_v_S0; Bd.FA_v_SS = CD.FA_v_SS;
+    sd.pbce = pbce; sd.frhatu = BCS.frhatu; sd.frhatv = BCS.frhatv; sd.bathyT = c->grid.bathyT; sd.bebt = BCS.bebt; sd.G_extra = BCS.G_extra;
+    sd.dtbt_fraction = CS->dtbt_fraction; sd.BT_Coriolis_scale = CS->BT_Coriolis_scale; sd.Z_ref = CS->Z_ref;
+    sd.Nonlinear_continuity = CS->BT_Nonlinear_continuity;
+    if (CS->dtbt_use_bt_cont) sd.BT_cont = &Bd; else sd.eta = eta;
+    if ((rc = m6_set_dtbt_run(c, sd, &BCS.dtbt, &CS->dtbt_max))) return rc;
+    CS->barotropic->dtbt = BCS.dtbt;
+  }
   // :673 btstep (predictor)
   BtstepDev B1 = {};
   B1.dt = dt; B1.U_in = u; B1.V_in = v; B1.eta_in = eta; B1.bc_accel_u = bcu; B1.bc_accel_v = bcv; B1.taux = VS.taux; B1.tauy = VS.tauy;

@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, fill_struct)
 
 
 def _scalars(struct, d):
@@ -159,3 +159,12 @@ def dyn_split_rk2_cs(d, keep):
 
 def step_dyn_args(a, keep):
     return fill_struct(StepDynArgs(), a, keep)
+
+
+def set_dtbt_args(a, keep):
+    st = fill_struct(SetDtbtArgs(), a, keep)
+    if a.get("BT_cont") is not None:
+        bs = fill_struct(BTCont(), a["BT_cont"], keep)
+        keep.append(bs)
+        st.BT_cont = C.pointer(bs)
+    return st

@@ -905,7 +905,7 @@ def vertvisc_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True,
 
 
 def step_dyn_inputs(ni, nj, nk, halo=4, whalo=10, seed=SEED, land_blocks=0, dt=900.0, vel=0.05, hnoise=1.0e-4, store_CAu=0, begw=0.0,
-                    split_bottom_stress=0, **bt_over):
+                    split_bottom_stress=0, calc_dtbt=0, **bt_over):
     """A full step_MOM_dyn_split_RK2 call (MOM_dynamics_split_RK2.F90:294): the shared state of step_inputs with a nearly
     level sea surface (so one step stays well inside CFL), the MOM_dyn_split_RK2_CS arrays as a previous step would have
     left them, visc% and forces%.  Returns dom, grid, gv, css (the stage control structures), cs, args."""
@@ -923,7 +923,7 @@ def step_dyn_inputs(ni, nj, nk, halo=4, whalo=10, seed=SEED, land_blocks=0, dt=9
     css = dict(continuity=stages["continuity"][0], coriolisadv=stages["coradcalc"][0], hor_visc=stages["horizontal_viscosity"][0],
                pressureforce=stages["pressure_force"][0], vertvisc=vertvisc_cs())
     cs = dict(be=0.6, begw=begw, split_bottom_stress=split_bottom_stress, store_CAu=store_CAu, CAu_pred_stored=0, visc_rem_dt_bug=1, hvel_scheme=4,
-              unsupported=0, CAu=new3("u"), CAv=new3("v"), CAu_pred=new3("u"), CAv_pred=new3("v"), PFu=new3("u"), PFv=new3("v"),
+              unsupported=0, dtbt_use_bt_cont=0, BT_Nonlinear_continuity=0, dtbt_fraction=0.98, BT_Coriolis_scale=1.0, Z_ref=0.0, dtbt_max=0.0, CAu=new3("u"), CAv=new3("v"), CAu_pred=new3("u"), CAv_pred=new3("v"), PFu=new3("u"), PFv=new3("v"),
               diffu=new3("u"), diffv=new3("v"), visc_rem_u=new3("u"), visc_rem_v=new3("v"), u_accel_bt=new3("u"), v_accel_bt=new3("v"),
               u_av=u.copy(), v_av=v.copy(), h_av=h.copy(), pbce=new3("h"), eta=eta, eta_PF=new2("h"), uhbt=new2("u"), vhbt=new2("v"),
               taux_bot=new2("u"), tauy_bot=new2("v"), BT_cont=dict(cont["BT_cont"]), barotropic=dict(cs_bt))
@@ -932,5 +932,59 @@ def step_dyn_inputs(ni, nj, nk, halo=4, whalo=10, seed=SEED, land_blocks=0, dt=9
     a = dict(u_inst=u, v_inst=v, h=h, T=pf["T"], S=pf["S"], Kv_bbl_u=rnd2("u", 1e-3, 1e-2), Kv_bbl_v=rnd2("v", 1e-3, 1e-2),
              bbl_thick_u=rnd2("u", 2.0, 20.0), bbl_thick_v=rnd2("v", 2.0, 20.0), Kv_shear=np.ascontiguousarray(kvs), Kv_shear_Bu=None, Ray_u=None,
              Ray_v=None, taux=np.ascontiguousarray(a_bt["taux"]), tauy=np.ascontiguousarray(a_bt["tauy"]), ustar=rnd2("h", 0.0, 0.02), p_surf=None,
-             dt=dt, uh=uh, vh=vh, uhtr=new3("u"), vhtr=new3("v"), eta_av=new2("h"), calc_dtbt=0)
+             dt=dt, uh=uh, vh=vh, uhtr=new3("u"), vhtr=new3("v"), eta_av=new2("h"), calc_dtbt=calc_dtbt)
     return dom, grid, gv, css, cs, a
+
+
+# stagger / memory domain of every array argument of the step (for tile splitting and for resident uploads)
+STEP_STAGGER = dict(
+    CAu="u", CAv="v", CAu_pred="u", CAv_pred="v", PFu="u", PFv="v", diffu="u", diffv="v", visc_rem_u="u", visc_rem_v="v", u_accel_bt="u",
+    v_accel_bt="v", u_av="u", v_av="v", h_av="h", pbce="h", eta="h", eta_PF="h", uhbt="u", vhbt="v", taux_bot="u", tauy_bot="v",
+    u_inst="u", v_inst="v", h="h", T="h", S="h", Kv_bbl_u="u", Kv_bbl_v="v", bbl_thick_u="u", bbl_thick_v="v", Kv_shear="h", Kv_shear_Bu="q",
+    Ray_u="u", Ray_v="v", taux="u", tauy="v", ustar="h", p_surf="h", uh="u", vh="v", uhtr="u", vhtr="v", eta_av="h",
+    FA_u_EE="u", FA_u_E0="u", FA_u_W0="u", FA_u_WW="u", uBT_WW="u", uBT_EE="u", FA_v_NN="v", FA_v_N0="v", FA_v_S0="v", FA_v_SS="v",
+    vBT_SS="v", vBT_NN="v", h_u="u", h_v="v",
+    IareaT="h", IareaT_OBCmask="h", bathyT="h", IdxCu="u", IdyCv="v", q_D="q", D_u_Cor="u", D_v_Cor="v", ua_polarity="h", va_polarity="h",
+    OBCmask_u="u", OBCmask_v="v", frhatu="u", frhatv="v", eta_cor="h", eta_cor_bound="h", IDatu="u", IDatv="v", ubtav="u", vbtav="v")
+BT_WIDE = {"IareaT", "IareaT_OBCmask", "bathyT", "IdxCu", "IdyCv", "q_D", "D_u_Cor", "D_v_Cor", "ua_polarity", "va_polarity", "OBCmask_u", "OBCmask_v"}
+GRID_STAGGER = dict(mask2dT="h", mask2dCu="u", mask2dCv="v", mask2dBu="q", dxT="h", dyT="h", IdxT="h", IdyT="h", areaT="h", IareaT="h",
+                    dxCu="u", dyCu="u", IdxCu="u", IdyCu="u", dy_Cu="u", areaCu="u", IareaCu="u", dxCv="v", dyCv="v", IdxCv="v", IdyCv="v",
+                    dx_Cv="v", areaCv="v", IareaCv="v", dxBu="q", dyBu="q", IdxBu="q", IdyBu="q", areaBu="q", IareaBu="q", bathyT="h",
+                    CoriolisBu="q", Coriolis2Bu="q")
+
+
+def _cut(dom_g, dom, arr, st, wide, oi, oj):
+    gl, tl = fidx.extent(dom_g, st, wide), fidx.extent(dom, st, wide)
+    j0, i0 = tl[2] + oj - gl[2], tl[0] + oi - gl[0]
+    return np.ascontiguousarray(arr[..., j0:j0 + tl[3] - tl[2] + 1, i0:i0 + tl[1] - tl[0] + 1])
+
+
+def split_step_tile(dom_g, grid, cs, a, npi, npj, pi, pj, hor_visc_cs_g=None):
+    """One rank's tile (with halos) of global step_dyn_inputs: dom, grid, cs, args (and the hor_visc CS arrays)."""
+    NI, NJ = dom_g.iec - dom_g.isc + 1, dom_g.jec - dom_g.jsc + 1
+    ni, nj = NI // npi, NJ // npj
+    halo, whalo = dom_g.isc - dom_g.isd, dom_g.isc - dom_g.isdw
+    dom = make_domain(ni, nj, nk=dom_g.nk, halo=halo, whalo=whalo, cyclic_x=bool(dom_g.cyclic_x), cyclic_y=bool(dom_g.cyclic_y),
+                      first_direction=dom_g.first_direction, npi=npi, npj=npj, pi=pi, pj=pj)
+    oi, oj = pi * ni, pj * nj
+    cut = lambda k, v, wide=False: (_cut(dom_g, dom, v, STEP_STAGGER[k], wide, oi, oj) if isinstance(v, np.ndarray) else v)   # noqa: E731
+    g = {k: (_cut(dom_g, dom, v, GRID_STAGGER[k], False, oi, oj) if isinstance(v, np.ndarray) else v) for k, v in grid.items()}
+    c = {k: cut(k, v) for k, v in cs.items() if k not in ("BT_cont", "barotropic")}
+    c["BT_cont"] = {k: cut(k, v) for k, v in cs["BT_cont"].items()}
+    c["barotropic"] = {k: cut(k, v, k in BT_WIDE) for k, v in cs["barotropic"].items()}
+    t = {k: cut(k, v) for k, v in a.items()}
+    hv = None
+    if hor_visc_cs_g is not None:
+        hv = {}
+        for k, v in hor_visc_cs_g.items():
+            if isinstance(v, np.ndarray):
+                for st in ("h", "q", "u", "v"):
+                    gl = fidx.extent(dom_g, st, False)
+                    if v.shape == (gl[3] - gl[2] + 1, gl[1] - gl[0] + 1):
+                        hv[k] = _cut(dom_g, dom, v, st, False, oi, oj)
+                        break
+                else:
+                    raise ValueError(f"split_step_tile: cannot place hor_visc CS array {k} {v.shape}")
+            else:
+                hv[k] = v
+    return dom, g, c, t, hv

@@ -530,3 +530,66 @@ extern "C" int oracle_bt_mass_source(const mom6cu_domain* d, const mom6cu_grid* 
   }
   return 0;
 }
+
+// set_dtbt :3509-3633 with BT_cont_to_face_areas :5107-5134 / find_face_areas :5146-5237 (halo = 0, Boussinesq, no SAL)
+extern "C" int oracle_set_dtbt(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
+                               const mom6cu_set_dtbt_args* a, double* dtbt, double* dtbt_max_out) {
+  const OGrid G(d, Gp);
+  const int is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, nz = G.ke;
+  if (!(a->pbce || a->have_gtot_est)) return 2;  // FATAL :3565
+  if (!GV->Boussinesq) return 3;
+  const double add_SSH = a->SSH_add;
+  A2 Datu = G.aU(), Datv = G.aV(), gtot_E = G.aH(), gtot_W = G.aH(), gtot_N = G.aH(), gtot_S = G.aH();
+  const V2 bathyT = G.H(a->bathyT);
+  if (a->BT_cont) {
+    const mom6cu_bt_cont* B = a->BT_cont;
+    const V2 EE = G.U(B->FA_u_EE), E0 = G.U(B->FA_u_E0), W0 = G.U(B->FA_u_W0), WW = G.U(B->FA_u_WW);
+    const V2 NN = G.V(B->FA_v_NN), N0 = G.V(B->FA_v_N0), S0 = G.V(B->FA_v_S0), SS = G.V(B->FA_v_SS);
+    for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I) Datu(I, j) = max4(EE(I, j), E0(I, j), W0(I, j), WW(I, j));
+    for (int J = js - 1; J <= je; ++J) for (int i = is; i <= ie; ++i) Datv(i, J) = max4(NN(i, J), N0(i, J), S0(i, J), SS(i, J));
+  } else if (a->Nonlinear_continuity && a->eta) {
+    const V2 eta = G.H(a->eta);
+    for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I) {
+      const double H1 = bathyT(I, j) * GV->Z_to_H + eta(I, j), H2 = bathyT(I + 1, j) * GV->Z_to_H + eta(I + 1, j);
+      Datu(I, j) = 0.0; if ((H1 > 0.0) && (H2 > 0.0)) Datu(I, j) = G.dy_Cu(I, j) * (2.0 * H1 * H2) / (H1 + H2);
+    }
+    for (int J = js - 1; J <= je; ++J) for (int i = is; i <= ie; ++i) {
+      const double H1 = bathyT(i, J) * GV->Z_to_H + eta(i, J), H2 = bathyT(i, J + 1) * GV->Z_to_H + eta(i, J + 1);
+      Datv(i, J) = 0.0; if ((H1 > 0.0) && (H2 > 0.0)) Datv(i, J) = G.dx_Cv(i, J) * (2.0 * H1 * H2) / (H1 + H2);
+    }
+  } else {
+    const double Z_to_H = GV->Z_to_H;
+    for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I)
+      Datu(I, j) = G.dy_Cu(I, j) * Z_to_H * fmax2(fmax2(bathyT(I + 1, j), bathyT(I, j)) + (a->Z_ref + add_SSH), 0.0);
+    for (int J = js - 1; J <= je; ++J) for (int i = is; i <= ie; ++i)
+      Datv(i, J) = G.dx_Cv(i, J) * Z_to_H * fmax2(fmax2(bathyT(i, J + 1), bathyT(i, J)) + (a->Z_ref + add_SSH), 0.0);
+  }
+  const double det_de = 0.0;
+  const double dgeo_de = 1.0 + fmax2(0.0, a->G_extra - det_de);
+  if (a->pbce) {
+    const V3 pbce = G.H3(a->pbce), frhatu = G.U3(a->frhatu), frhatv = G.V3_(a->frhatv);
+    for (int k = 1; k <= nz; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+      gtot_E(i, j) = gtot_E(i, j) + pbce(i, j, k) * frhatu(i, j, k);
+      gtot_W(i, j) = gtot_W(i, j) + pbce(i, j, k) * frhatu(i - 1, j, k);
+      gtot_N(i, j) = gtot_N(i, j) + pbce(i, j, k) * frhatv(i, j, k);
+      gtot_S(i, j) = gtot_S(i, j) + pbce(i, j, k) * frhatv(i, j - 1, k);
+    }
+  } else {
+    for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+      gtot_E(i, j) = a->gtot_est; gtot_W(i, j) = a->gtot_est; gtot_N(i, j) = a->gtot_est; gtot_S(i, j) = a->gtot_est;
+    }
+  }
+  double min_max_dt2 = 1.0e38 * (US->s_to_T * US->s_to_T);
+  for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i) {
+    const double Idt_max2 = 0.5 * (1.0 + 2.0 * a->bebt) * (G.IareaT(i, j) *
+        (((gtot_E(i, j) * Datu(i, j) * G.IdxCu(i, j)) + (gtot_W(i, j) * Datu(i - 1, j) * G.IdxCu(i - 1, j))) +
+         ((gtot_N(i, j) * Datv(i, j) * G.IdyCv(i, j)) + (gtot_S(i, j) * Datv(i, j - 1) * G.IdyCv(i, j - 1)))) +
+        ((G.Coriolis2Bu(i, j) + G.Coriolis2Bu(i - 1, j - 1)) + (G.Coriolis2Bu(i - 1, j) + G.Coriolis2Bu(i, j - 1))) *
+            (a->BT_Coriolis_scale * a->BT_Coriolis_scale));
+    if (Idt_max2 * min_max_dt2 > 1.0) min_max_dt2 = 1.0 / Idt_max2;
+  }
+  const double dtbt_max = std::sqrt(min_max_dt2 / dgeo_de);
+  *dtbt = a->dtbt_fraction * dtbt_max;
+  *dtbt_max_out = dtbt_max;
+  return 0;
+}

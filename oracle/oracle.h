@@ -54,6 +54,9 @@ int oracle_btcalc(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_v
 int oracle_bt_mass_source(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const double* h,
                           const double* eta, int set_cor, double* eta_cor);
 
+int oracle_set_dtbt(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
+                    const mom6cu_set_dtbt_args* a, double* dtbt, double* dtbt_max);
+
 /* PressureForce_FV_Bouss, MOM_PressureForce_FV.F90:947-2017 (frozen option set) */
 int oracle_pressure_force(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV,
                           const mom6cu_pressureforce_cs* CS, const mom6cu_pressureforce_args* a, int nthreads);

@@ -313,3 +313,19 @@ def step_dyn_split_rk2(dom, grid, gv, css, cs, args, us=None, nthreads=1):
     if rc:
         raise RuntimeError(f"oracle_step_dyn_split_rk2 rc={rc}")
     cs["CAu_pred_stored"] = int(st.CAu_pred_stored)
+    cs["dtbt_max"] = float(st.dtbt_max)
+    cs["barotropic"]["dtbt"] = float(st.barotropic.contents.dtbt)
+
+
+def set_dtbt(dom, grid, gv, args, us=None):
+    """oracle_set_dtbt: set_dtbt (MOM_barotropic.F90:3509); returns (dtbt, dtbt_max)."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); u = marshal.unit_scale(us or US_ONE); a = marshal.set_dtbt_args(args, keep)
+    dtbt, dmax = C.c_double(0.0), C.c_double(0.0)
+    lib.oracle_set_dtbt.argtypes = [C.c_void_p] * 7
+    rc = lib.oracle_set_dtbt(C.byref(dom), C.byref(g), C.byref(v), C.byref(u), C.byref(a), C.byref(dtbt), C.byref(dmax))
+    if rc:
+        raise RuntimeError(f"oracle_set_dtbt rc={rc}")
+    return dtbt.value, dmax.value

@@ -26,7 +26,7 @@ extern "C" int oracle_step_dyn_split_rk2(const mom6cu_domain* d, const mom6cu_gr
                                          int nthreads) {
   const OGrid G(d, Gp);
   const int nz = G.ke, is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, Isq = G.IscB, Ieq = G.IecB, Jsq = G.JscB, Jeq = G.JecB;
-  if (CS->unsupported || a->calc_dtbt || !CS->BT_cont || !CS->BT_cont->h_u || !CS->BT_cont->h_v || !CS->barotropic) return 3;
+  if (CS->unsupported || !CS->BT_cont || !CS->BT_cont->h_u || !CS->BT_cont->h_v || !CS->barotropic) return 3;
   const double dt = a->dt;
   int rc;
   A3 up(G.isd - 1, G.ied, G.jsd, G.jed, nz), vp(G.isd, G.ied, G.jsd - 1, G.jed, nz), hp(G.isd, G.ied, G.jsd, G.jed, nz);
@@ -76,6 +76,15 @@ extern "C" int oracle_step_dyn_split_rk2(const mom6cu_domain* d, const mom6cu_gr
   mom6cu_btcalc_args bc = {a->h, CS->BT_cont->h_u, CS->BT_cont->h_v, (double*)CS->barotropic->frhatu, (double*)CS->barotropic->frhatv,
                            Gp->bathyT, CS->hvel_scheme, 0};
   if ((rc = oracle_btcalc(d, Gp, GV, &bc, nthreads))) return 600 + rc;
+  // :663-669 set_dtbt
+  if (a->calc_dtbt) {
+    mom6cu_set_dtbt_args sd = {};
+    sd.pbce = CS->pbce; sd.frhatu = CS->barotropic->frhatu; sd.frhatv = CS->barotropic->frhatv; sd.bathyT = Gp->bathyT;
+    sd.bebt = CS->barotropic->bebt; sd.G_extra = CS->barotropic->G_extra; sd.dtbt_fraction = CS->dtbt_fraction;
+    sd.BT_Coriolis_scale = CS->BT_Coriolis_scale; sd.Z_ref = CS->Z_ref; sd.Nonlinear_continuity = CS->BT_Nonlinear_continuity;
+    if (CS->dtbt_use_bt_cont) sd.BT_cont = CS->BT_cont; else sd.eta = CS->eta;
+    if ((rc = oracle_set_dtbt(d, Gp, GV, US, &sd, &CS->barotropic->dtbt, &CS->dtbt_max))) return 650 + rc;
+  }
   // :673 btstep (predictor)
   mom6cu_btstep_args b1 = {};
   b1.U_in = a->u_inst; b1.V_in = a->v_inst; b1.eta_in = CS->eta; b1.dt = dt; b1.bc_accel_u = u_bc_accel.p; b1.bc_accel_v = v_bc_accel.p;

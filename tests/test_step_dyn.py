@@ -53,7 +53,44 @@ def test_store_cau_skips_the_first_coradcalc(oracle):
     assert cs2["CAu_pred_stored"] == 1 and not np.array_equal(cs2["CAu_pred"], kept)
 
 
-CASES = [dict(), dict(land_blocks=4, store_CAu=1, begw=0.5), dict(land_blocks=2, split_bottom_stress=1, BT_project_velocity=1)]
+CASES = [dict(), dict(land_blocks=4, store_CAu=1, begw=0.5), dict(land_blocks=2, split_bottom_stress=1, BT_project_velocity=1),
+         dict(land_blocks=3, calc_dtbt=1, store_CAu=1)]
+
+
+def _dtbt_args(dom, grid, cs, mode):
+    a = dict(pbce=cs["pbce"], gtot_est=0.0, have_gtot_est=0, BT_cont=None, eta=None, SSH_add=0.0, frhatu=cs["barotropic"]["frhatu"],
+             frhatv=cs["barotropic"]["frhatv"], bathyT=grid["bathyT"], bebt=0.1, G_extra=0.0, dtbt_fraction=0.98, BT_Coriolis_scale=1.0, Z_ref=0.0,
+             Nonlinear_continuity=0)
+    if mode == "BT_cont":
+        a["BT_cont"] = cs["BT_cont"]
+    elif mode == "eta":
+        a["eta"] = cs["eta"]; a["Nonlinear_continuity"] = 1
+    elif mode == "gtot":
+        a["pbce"] = None; a["gtot_est"] = 9.8; a["have_gtot_est"] = 1; a["SSH_add"] = 2.0
+    return a
+
+
+def test_set_dtbt_is_the_gravity_wave_limit(oracle):
+    """dtbt_max ~ 1/sqrt(g H (1/dx^2 + 1/dy^2) 2 (1+2 bebt)/2 ...): within a factor of 2 of dx / sqrt(2 g H) for the deepest column."""
+    dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(32, 24, 6)
+    cs["pbce"][...] = 9.8
+    dtbt, dmax = oracle.set_dtbt(dom, grid, gv, _dtbt_args(dom, grid, cs, "bathy"))
+    dx = float(grid["dxT"].min()); H = float(grid["bathyT"].max())
+    est = dx / np.sqrt(2.0 * 9.8 * H * 1.2)
+    assert 0.5 * est < dmax < 2.0 * est and dtbt == 0.98 * dmax
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["BT_cont", "eta", "bathy", "gtot"])
+def test_set_dtbt_bitwise(oracle, ctx_factory, mode):
+    dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(44, 40, 8, land_blocks=3)
+    oracle.step_dyn_split_rk2(dom, grid, gv, css, cs, a)          # gives pbce, BT_cont, eta realistic values
+    args = _dtbt_args(dom, grid, cs, mode)
+    ref = oracle.set_dtbt(dom, grid, gv, args)
+    ctx = ctx_factory(dom)
+    ctx.set_grid(grid); ctx.set_vgrid(gv)
+    got = ctx.set_dtbt(args)
+    assert ref == got and got[0] > 0.0
 
 
 @pytest.mark.gpu
@@ -86,6 +123,7 @@ def test_step_bitwise(oracle, ctx_factory, kw):
                 bad.append(("BT_cont%" + k, 0))
         assert not bad, (step, kw, bad)
         assert rcs["CAu_pred_stored"] == gcs["CAu_pred_stored"]
+        assert rcs["barotropic"]["dtbt"] == gcs["barotropic"]["dtbt"] and rcs["dtbt_max"] == gcs["dtbt_max"]
 
 
 @pytest.mark.gpu
