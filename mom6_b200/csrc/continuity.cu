@@ -444,6 +444,22 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   const long long g = G.idx(valid ? n : A.nhi, o);
   double dy = 0.0, cfl0 = 0.0, cfl1 = 0.0, IareaT0 = 0.0, IareaT1 = 0.0;
   CellSt st[KPT];
+  // ---- per-face constants of the CFL limits (:646-655); also used to precompute, in parallel, the quotients the serial
+  //      k-scans of :664-720 would otherwise evaluate one after the other
+  const bool adjust = (A.uhbt != nullptr) || set_BT;
+  double CFL_dt = CS.CFL_limit_adjust / dt;
+  const double I_dt = 1.0 / dt;
+  if (CS.aggress_adjust) CFL_dt = I_dt;
+  double dx_W = 0.0, dx_E = 0.0, maskC = 0.0;
+  if (adjust) {
+    if (CS.vol_CFL) {
+      const double dyf = __ldg(A.dy_C + g);
+      dx_W = ratio_max(__ldg(A.areaT + g), dyf, 1000.0 * __ldg(A.dxT + g));
+      dx_E = ratio_max(__ldg(A.areaT + g + sd), dyf, 1000.0 * __ldg(A.dxT + g + sd));
+    } else { dx_W = __ldg(A.dxT + g); dx_E = __ldg(A.dxT + g + sd); }
+    maskC = __ldg(A.maskC + g);
+  }
+  const bool fast_cfl = adjust && use_visc_rem && !CS.aggress_adjust;  // the default options
   // ---- load, reconstruct, first flux evaluation (:621-635)
   {
     double m[6];
@@ -474,21 +490,15 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         flux_from_state(CS, st[mm], dy * por, uk, vr, dt, cfl0, cfl1, uh, dd, ha, hm);
         if (valid) A.uh[gk] = uh;
         sP[k * NF + f] = uh; sP[PL + k * NF + f] = dd;
+        if (fast_cfl) {  // the values du_max_CFL / du_min_CFL take when layer k limits them (:671, :687)
+          sP[2 * PL + k * NF + f] = (dx_W * CFL_dt - uk) / vr;
+          sP[3 * PL + k * NF + f] = -(dx_E * CFL_dt + uk) / vr;
+        }
       }
     }
   }
   double du = 0.0;
-  if (A.uhbt || set_BT) {  // uniform over the grid
-    // ---- per-face constants of the CFL limits (:646-655)
-    double CFL_dt = CS.CFL_limit_adjust / dt;
-    const double I_dt = 1.0 / dt;
-    if (CS.aggress_adjust) CFL_dt = I_dt;
-    double dx_W, dx_E;
-    if (CS.vol_CFL) {
-      dx_W = ratio_max(__ldg(A.areaT + g), dy, 1000.0 * __ldg(A.dxT + g));
-      dx_E = ratio_max(__ldg(A.areaT + g + sd), dy, 1000.0 * __ldg(A.dxT + g + sd));
-    } else { dx_W = __ldg(A.dxT + g); dx_E = __ldg(A.dxT + g + sd); }
-    const double maskC = __ldg(A.maskC + g);
+  if (adjust) {  // uniform over the grid
     __syncthreads();
     // ---- one round of k-ordered work, one warp per quantity (s = 2*warp for lanes 0..NF-1):
     //      uh_tot_0, duhdu_tot_0 (:659-662); visc_rem_max (:637-644) followed by du_max_CFL / du_min_CFL (:646-720)
@@ -508,7 +518,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
             if (CS.aggress_adjust) {
               const double du_lim = 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd)));
               if (du_max_CFL * vr > du_lim) du_max_CFL = du_lim / vr;
-            } else if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = (dx_W * CFL_dt - uk) / vr;
+            } else if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = sP[2 * PL + k * NF + f];
           } else {
             if (CS.aggress_adjust)
               du_max_CFL = fmin2(du_max_CFL, 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd))));
@@ -524,7 +534,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
             if (CS.aggress_adjust) {
               const double du_lim = 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd)));
               if (du_min_CFL * vr < du_lim) du_min_CFL = du_lim / vr;
-            } else if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = -(dx_E * CFL_dt + uk) / vr;
+            } else if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = sP[3 * PL + k * NF + f];
           } else {
             if (CS.aggress_adjust)
               du_min_CFL = fmax2(du_min_CFL, 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd))));
@@ -629,13 +639,25 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
       const double min_visc_rem = 0.1, CFL_min = 1e-6;
       const double du_CFL = (CFL_min * Idt) * __ldg(A.dxC + g);
       __syncthreads();
+      // the quotients of :1336-1341 for every layer, in parallel; the k-scans below only compare and select
+#pragma unroll
+      for (int mm = 0; mm < KPT; ++mm) {
+        const int k = s + mm * NS;
+        if (k < nz) {
+          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+          const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
+          sP[k * NF + f] = -(uk + du_CFL * vr) / visc_rem_lim;
+          sP[PL + k * NF + f] = -(uk - du_CFL * vr) / visc_rem_lim;
+        }
+      }
+      __syncthreads();
       if (s == 0) {
         double duR = fmin2(0.0, du0 - du_CFL);
         for (int k = 0; k < nz; ++k) {
           const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
           const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
           if (visc_rem_lim > 0.0)
-            if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = -(uk + du_CFL * vr) / visc_rem_lim;
+            if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = sP[k * NF + f];
         }
         sR[f] = duR;
       } else if (s == 2) {
@@ -644,7 +666,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
           const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
           const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
           if (visc_rem_lim > 0.0)
-            if (uk + duL * visc_rem_lim < du_CFL * vr) duL = -(uk - du_CFL * vr) / visc_rem_lim;
+            if (uk + duL * visc_rem_lim < du_CFL * vr) duL = sP[PL + k * NF + f];
         }
         sR[NF + f] = duL;
       }
