@@ -155,6 +155,47 @@ def step_resident(ctx, dom, cs, sa):
     return rcs, rsa, n[0]
 
 
+THERMO_EVERY = 8   # DT_THERM / DT of OM4_025 (7200 s / 900 s)
+
+
+def thermo_pass(Context, synthetic, ni, nj, device):
+    """advect_tracer (T, S; PLM) + ALE_regrid (Z*) + ALE_remap_tracers (T, S) + ALE_remap_set_h_vel x2 + ALE_remap_velocities on
+    resident fields; returns the device times [ms]."""
+    out = {}
+    dom, grid, gv, cs, a = synthetic.advect_inputs(ni, nj, NK, land_blocks=40, cfl=1.5, dt=900.0 * THERMO_EVERY, dt_dyn=900.0)
+    ctx = Context(dom, device)
+    ctx.set_grid(grid); ctx.set_vgrid(gv)
+    ra = dict(a)
+    for k, st in (("h_end", "h"), ("uhtr", "u"), ("vhtr", "v")):
+        ra[k] = ctx.plane("adv." + k, a[k], st, False, NK)
+    ra["tr"] = [ctx.plane(f"adv.tr{m}", t, "h", False, NK) for m, t in enumerate(a["tr"])]
+    ctx.advect_tracer(cs, ra)
+    it = ctx.advect_tracer(cs, ra)
+    out["advect_tracer_ms"] = ctx.last_kernel_ms; out["advect_tracer_iterations"] = it
+    ctx.close()
+    dom, grid, gv, rcs, ga = synthetic.regrid_inputs(ni, nj, NK, land_blocks=40)
+    _, _, mcs, ma = synthetic.remap_inputs(ni, nj, NK, land_blocks=40)
+    ctx = Context(dom, device)
+    ctx.set_grid(grid); ctx.set_vgrid(gv)
+    h = ctx.plane("ale.h", ga["h"], "h", False, NK); hn = ctx.plane("ale.h_new", ga["h_new"], "h", False, NK)
+    dz = ctx.plane("ale.dz", ga["dzRegrid"], "h", False, NK + 1)
+    ctx.ale_regrid(rcs, h, hn, dz); ctx.ale_regrid(rcs, h, hn, dz)
+    out["ale_regrid_ms"] = ctx.last_kernel_ms
+    T = ctx.plane("ale.T", ma["tr"][0], "h", False, NK); S = ctx.plane("ale.S", ma["tr"][1], "h", False, NK)
+    ctx.ale_remap_tracers(mcs, h, hn, [T, S]); ctx.ale_remap_tracers(mcs, h, hn, [T, S])
+    out["ale_remap_tracers_ms"] = ctx.last_kernel_ms
+    u = ctx.plane("ale.u", ma["u"], "u", False, NK); v = ctx.plane("ale.v", ma["v"], "v", False, NK)
+    hu0 = ctx.plane("ale.hu0", ma["u"], "u", False, NK); hv0 = ctx.plane("ale.hv0", ma["v"], "v", False, NK)
+    hu1 = ctx.plane("ale.hu1", ma["u"], "u", False, NK); hv1 = ctx.plane("ale.hv1", ma["v"], "v", False, NK)
+    ctx.ale_remap_set_h_vel(h, hu0, hv0); ctx.ale_remap_set_h_vel(hn, hu1, hv1)
+    out["ale_remap_set_h_vel_ms"] = 2.0 * ctx.last_kernel_ms
+    ctx.ale_remap_velocities(mcs, hu0, hv0, hu1, hv1, u, v); ctx.ale_remap_velocities(mcs, hu0, hv0, hu1, hv1, u, v)
+    out["ale_remap_velocities_ms"] = ctx.last_kernel_ms
+    ctx.close()
+    out["total_ms"] = sum(v for k, v in out.items() if k.endswith("_ms"))
+    return out
+
+
 def run_step(ctx, stages, times=None):
     """One baroclinic step: the implemented stages in the reference's call counts."""
     for name, calls, _ in STEP:
@@ -248,11 +289,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-array leg")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-stage breakdown")
+    ap.add_argument("--no-thermo", action="store_true", help="skip the tracer-advection / ALE pass that runs every DT_THERM/DT steps")
     ap.add_argument("--size", default=None, help="ni,nj override (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -339,6 +384,13 @@ def main():
             run_step(ctx, resident, times)
         barrier()
 
+    # ---- the thermodynamic-cadence pass (every DT_THERM/DT = 8 steps in OM4_025): advect_tracer of T and S over the 8 steps'
+    # transports, Z* regrid, remap of T, S, u, v -- timed on its own, reported next to the dynamics step
+    thermo = None
+    if world == 1 and not args.no_thermo:
+        thermo = thermo_pass(Context, synthetic, ni, nj, local)
+        barrier()
+
     tmax = torch.tensor([dev_ms, e2e_s or 0.0, wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -385,6 +437,11 @@ def main():
                          "algorithmic_bytes_per_launch": tile_cells * ds["algorithmic_B_per_cell"],
                          "note": "stage-level: algorithmic bytes of one stage call / CUDA-event time of its kernels"},
             "per_stage": per_stage, "clocks": clk.summary()}
+    if thermo:
+        per8 = THERMO_EVERY * dev_ms / args.steps + thermo["total_ms"]
+        thermo["every_n_steps"] = THERMO_EVERY
+        thermo["cell_updates_per_s_with_thermo"] = cells * THERMO_EVERY / (per8 * 1e-3)
+        line["thermo_pass"] = thermo
     # BASELINE.json configs[4]: btstep microbench, 4320x3240 subcycle sweep at 1 GPU
     if world == 1 and not args.size:
         ctx.close()

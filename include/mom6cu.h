@@ -581,6 +581,11 @@ typedef struct mom6cu_step_dyn_args {
   int calc_dtbt;
 } mom6cu_step_dyn_args;
 int mom6cu_step_dyn_split_rk2(mom6cu_ctx* ctx, mom6cu_dyn_split_rk2_cs* CS, const mom6cu_step_dyn_args* a);
+/* remap_dyn_split_RK2_aux_vars(G, GV, CS, h_old_u, h_old_v, h_new_u, h_new_v, ALE_CSp)  MOM_dynamics_split_RK2.F90:1302-1331
+ * (CS%remap_aux true): with store_CAu, u_av/v_av and CAu_pred/CAv_pred are remapped and their halos updated; diffu/diffv
+ * are remapped.  remapCS is ALE_CSp%vel_remapCS. */
+int mom6cu_remap_dyn_split_rk2_aux_vars(mom6cu_ctx* ctx, const mom6cu_remapping_cs* remapCS, const mom6cu_dyn_split_rk2_cs* CS,
+                                        const double* h_old_u, const double* h_old_v, const double* h_new_u, const double* h_new_v);
 
 #ifdef __cplusplus
 }

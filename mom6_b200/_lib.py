@@ -318,6 +318,7 @@ def bind(lib):
     lib.mom6cu_ale_remap_velocities.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, vp, vp, vp, vp]
     lib.mom6cu_remapping_core_h.argtypes = [vp, C.POINTER(RemappingCS), C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     lib.mom6cu_set_dtbt.argtypes = [vp, C.POINTER(SetDtbtArgs), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.mom6cu_remap_dyn_split_rk2_aux_vars.argtypes = [vp, C.POINTER(RemappingCS), C.POINTER(DynSplitRK2CS), vp, vp, vp, vp]
     lib.mom6cu_step_dyn_split_rk2.argtypes = [vp, C.POINTER(DynSplitRK2CS), C.POINTER(StepDynArgs)]
     lib.mom6cu_set_cs_vertvisc.argtypes = [vp, C.POINTER(VertviscCS)]
     lib.mom6cu_vertvisc_coef.argtypes = [vp, C.POINTER(VertviscCoefArgs)]

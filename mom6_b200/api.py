@@ -268,6 +268,14 @@ def _ctx_methods():
         self._check(self.lib.mom6cu_set_dtbt(self._h, C.byref(marshal.set_dtbt_args(args, keep)), C.byref(dtbt), C.byref(dmax)))
         return dtbt.value, dmax.value
 
+    def remap_dyn_split_rk2_aux_vars(self, remap_cs, cs, h_old_u, h_old_v, h_new_u, h_new_v):
+        """remap_dyn_split_RK2_aux_vars, MOM_dynamics_split_RK2.F90:1302."""
+        keep = []
+        st = marshal.dyn_split_rk2_cs(cs, keep)
+        return self._check(self.lib.mom6cu_remap_dyn_split_rk2_aux_vars(self._h, C.byref(marshal.remapping_cs(remap_cs)), C.byref(st), _p(h_old_u),
+                                                                       _p(h_old_v), _p(h_new_u), _p(h_new_v)))
+
+    setattr(Context, "remap_dyn_split_rk2_aux_vars", remap_dyn_split_rk2_aux_vars)
     setattr(Context, "set_dtbt", set_dtbt)
     setattr(Context, "step_dyn_split_rk2", step_dyn_split_rk2)
     for f in (set_cs_vertvisc, vertvisc_coef, vertvisc_get_coef, vertvisc, vertvisc_remnant):

@@ -17,12 +17,15 @@
 #include "ctx.h"
 #include "stage.h"
 #include <cmath>
+#include <cstdlib>
 
 using m6::Geom;
 using m6::fmax2;
 using m6::fmin2;
 
 namespace {
+
+constexpr int PGF_MINB_DEFAULT = 4;  // measured at 1440x1080x75: 10.0 ms (2 CTAs/SM), 8.6 (3), 8.45 (4)
 
 // Wright (1997) fit used by EOS_WRIGHT, MOM_EOS_Wright.F90:23-37
 #define W_a0 7.057924e-4
@@ -176,7 +179,8 @@ __device__ __forceinline__ void eos_derivs(const PgfK& K, double T, double S, do
   drho_dS = I_denom2 * (lambda * (W_b4 + W_b5 * T) - (p + p0) * ((p + p0) * W_a2 + (W_c4 + W_c5 * T)));
 }
 
-__global__ void __launch_bounds__(128) pgf_main_kernel(const Geom G, const PgfK K) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) pgf_main_kernel(const Geom G, const PgfK K) {
   const int i = G.isc - 1 + blockIdx.x * blockDim.x + threadIdx.x, j = G.jsc - 1 + blockIdx.y;
   if (i > G.iec + 1 || j > G.jec + 1) return;
   const long long g = G.idx(i, j), P = G.pitch;
@@ -306,7 +310,13 @@ int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D) {
   K.PFu = D.PFu; K.PFv = D.PFv; K.pbce = D.pbce; K.eta = D.eta;
   dim3 grid((d.iec - d.isc + 3 + 127) / 128, d.jec - d.jsc + 3);
   M6_LAUNCH(c, pgf_e_kernel, grid, 128, 0, G, K);
-  M6_LAUNCH(c, pgf_main_kernel, grid, 128, 0, G, K);
+  {  // resident CTAs per SM: 2 (194 registers, no spills), 3 (168) or 4 (128, ~30 doubles spilled); MOM6CU_PGF_MINB overrides
+    static int minb = -1;
+    if (minb < 0) { const char* e = getenv("MOM6CU_PGF_MINB"); minb = e ? atoi(e) : PGF_MINB_DEFAULT; }
+    if (minb >= 4) M6_LAUNCH(c, pgf_main_kernel<4>, grid, 128, 0, G, K);
+    else if (minb == 3) M6_LAUNCH(c, pgf_main_kernel<3>, grid, 128, 0, G, K);
+    else M6_LAUNCH(c, pgf_main_kernel<1>, grid, 128, 0, G, K);
+  }
   M6_CUDA(c, cudaGetLastError());
   return 0;
 }

@@ -202,3 +202,41 @@ extern "C" int mom6cu_remapping_core_h(mom6cu_ctx* c, const mom6cu_remapping_cs*
   c->last_ms = ms; c->total_ms = ms;
   return 0;
 }
+
+extern "C" int mom6cu_remap_dyn_split_rk2_aux_vars(mom6cu_ctx* c, const mom6cu_remapping_cs* remapCS, const mom6cu_dyn_split_rk2_cs* CS,
+                                                   const double* h_old_u, const double* h_old_v, const double* h_new_u, const double* h_new_v) {
+  if (!c || !CS || !h_old_u || !h_old_v || !h_new_u || !h_new_v) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  if (!c->have_grid) return c->fail(MOM6CU_ERR_BAD_ARG, "remap_dyn_split_RK2_aux_vars: mom6cu_set_grid has not been called");
+  if (!CS->diffu || !CS->diffv || (CS->store_CAu && (!CS->u_av || !CS->v_av || !CS->CAu_pred || !CS->CAv_pred)))
+    return c->fail(MOM6CU_ERR_BAD_ARG, "remap_dyn_split_RK2_aux_vars: a control-structure array is null");
+  Params P;
+  int rc;
+  if ((rc = check_cs(c, remapCS, c->g.nk, &P))) return rc;
+  Stager S(c, "remapx.");
+  const double *d_hou, *d_hov, *d_hnu, *d_hnv;
+  double *uav = nullptr, *vav = nullptr, *cau = nullptr, *cav = nullptr, *du, *dv;
+  if ((rc = S.in3(h_old_u, ST_U, "h_old_u", &d_hou)) || (rc = S.in3(h_old_v, ST_V, "h_old_v", &d_hov)) ||
+      (rc = S.in3(h_new_u, ST_U, "h_new_u", &d_hnu)) || (rc = S.in3(h_new_v, ST_V, "h_new_v", &d_hnv)) ||
+      (rc = S.io3(CS->diffu, ST_U, "diffu", &du)) || (rc = S.io3(CS->diffv, ST_V, "diffv", &dv))) return rc;
+  if (CS->store_CAu && ((rc = S.io3(CS->u_av, ST_U, "u_av", &uav)) || (rc = S.io3(CS->v_av, ST_V, "v_av", &vav)) ||
+                        (rc = S.io3(CS->CAu_pred, ST_U, "CAu_pred", &cau)) || (rc = S.io3(CS->CAv_pred, ST_V, "CAv_pred", &cav)))) return rc;
+  if ((rc = S.begin())) return rc;
+  const mom6cu_domain& d = c->dom;
+  auto remap_pair = [&](double* u, double* v) -> int {
+    Fields F = {};
+    F.n = 1; F.p[0] = u;
+    int r = launch_planes(c, P, d.isc - 1, d.iec, d.jsc, d.jec, c->grid.mask2dCu, d_hou, d_hnu, F);
+    if (r) return r;
+    F.p[0] = v;
+    return launch_planes(c, P, d.isc, d.iec, d.jsc - 1, d.jec, c->grid.mask2dCv, d_hov, d_hnv, F);
+  };
+  if (CS->store_CAu) {
+    if ((rc = remap_pair(uav, vav)) || (rc = remap_pair(cau, cav))) return rc;
+    double* f[4] = {uav, vav, cau, cav};
+    const int st[4] = {ST_U, ST_V, ST_U, ST_V};
+    if ((rc = m6_halo_update(c, f, st, 4, 0, c->g.nk))) return rc;  // pass_vector :1322-1325
+  }
+  if ((rc = remap_pair(du, dv))) return rc;
+  return S.finish();
+}

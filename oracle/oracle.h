@@ -76,6 +76,10 @@ int oracle_ale_remap_set_h_vel(const mom6cu_domain* dom, const mom6cu_grid* G, c
 int oracle_ale_remap_velocities(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_remapping_cs* CS, const double* h_old_u,
                                 const double* h_old_v, const double* h_new_u, const double* h_new_v, double* u, double* v, int nthreads);
 
+int oracle_remap_dyn_split_rk2_aux_vars(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_remapping_cs* remapCS,
+                                        const mom6cu_dyn_split_rk2_cs* CS, const double* h_old_u, const double* h_old_v,
+                                        const double* h_new_u, const double* h_new_v, int nthreads);
+
 /* advect_tracer (MOM_tracer_advect.F90:53-1152): see advect.cpp.  UNPINNED.  *iterations returns the number of passes made. */
 int oracle_advect_tracer(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_tracer_advect_cs* CS,
                          const mom6cu_advect_tracer_args* a, int* iterations);

@@ -329,3 +329,13 @@ def set_dtbt(dom, grid, gv, args, us=None):
     if rc:
         raise RuntimeError(f"oracle_set_dtbt rc={rc}")
     return dtbt.value, dmax.value
+
+
+def remap_dyn_split_rk2_aux_vars(dom, grid, remap_cs, cs, h_old_u, h_old_v, h_new_u, h_new_v, nthreads=1):
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); r = marshal.remapping_cs(remap_cs); st = marshal.dyn_split_rk2_cs(cs, keep)
+    lib.oracle_remap_dyn_split_rk2_aux_vars.argtypes = [C.c_void_p] * 8 + [C.c_int]
+    return lib.oracle_remap_dyn_split_rk2_aux_vars(C.byref(dom), C.byref(g), C.byref(r), C.byref(st), _dp(h_old_u), _dp(h_old_v), _dp(h_new_u),
+                                                   _dp(h_new_v), nthreads)

@@ -623,4 +623,22 @@ int oracle_ale_remap_velocities(const mom6cu_domain* d, const mom6cu_grid* Gp, c
   return 0;
 }
 
+// remap_dyn_split_RK2_aux_vars, MOM_dynamics_split_RK2.F90:1302-1331 (CS%remap_aux true; single tile halo fill)
+int oracle_remap_dyn_split_rk2_aux_vars(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_remapping_cs* rCS,
+                                        const mom6cu_dyn_split_rk2_cs* CS, const double* h_old_u, const double* h_old_v,
+                                        const double* h_new_u, const double* h_new_v, int nthreads) {
+  const OGrid G(d, Gp);
+  auto fill = [&](double* f, int st) {
+    const int su = (st == 1), sv = (st == 2);
+    const size_t plane = (size_t)(d->ied - d->isd + 1 + su) * (d->jed - d->jsd + 1 + sv);
+    for (int k = 0; k < G.ke; ++k) oracle_fill_halo_2d(d, f + plane * k, st, 0);
+  };
+  if (CS->store_CAu) {
+    oracle_ale_remap_velocities(d, Gp, rCS, h_old_u, h_old_v, h_new_u, h_new_v, CS->u_av, CS->v_av, nthreads);
+    oracle_ale_remap_velocities(d, Gp, rCS, h_old_u, h_old_v, h_new_u, h_new_v, CS->CAu_pred, CS->CAv_pred, nthreads);
+    fill(CS->u_av, 1); fill(CS->v_av, 2); fill(CS->CAu_pred, 1); fill(CS->CAv_pred, 2);
+  }
+  return oracle_ale_remap_velocities(d, Gp, rCS, h_old_u, h_old_v, h_new_u, h_new_v, CS->diffu, CS->diffv, nthreads);
+}
+
 }  // extern "C"

@@ -94,3 +94,22 @@ def test_remap_rejects_what_is_not_implemented(ctx_factory):
             ctx.remapping_core_h(dict(CS_PPM_H4, **bad), [1., 1.], [1., 2.], [2.])
     with pytest.raises(Mom6cuError):
         ctx.remapping_core_h(CS_PPM_H4, np.ones((1, 200)), np.ones((1, 200)), np.ones((1, 3)))
+
+
+@pytest.mark.gpu
+def test_remap_dyn_split_rk2_aux_vars_bitwise(oracle, ctx_factory):
+    """MOM_dynamics_split_RK2.F90:1302: the auxiliary restart variables follow the grid with the velocities."""
+    dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(44, 40, 8, whalo=6, land_blocks=2, store_CAu=1)
+    oracle.step_dyn_split_rk2(dom, grid, gv, css, cs, a)                  # realistic u_av, CAu_pred, diffu
+    _, _, rcs, ra = synthetic.remap_inputs(44, 40, 8, land_blocks=2)
+    hu = {k: np.zeros_like(a["u_inst"]) for k in ("o", "n")}; hv = {k: np.zeros_like(a["v_inst"]) for k in ("o", "n")}
+    oracle.ale_remap_set_h_vel(dom, grid, ra["h_old"], hu["o"], hv["o"]); oracle.ale_remap_set_h_vel(dom, grid, ra["h_new"], hu["n"], hv["n"])
+    ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in cs.items()}
+    got = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in cs.items()}
+    oracle.remap_dyn_split_rk2_aux_vars(dom, grid, rcs, ref, hu["o"], hv["o"], hu["n"], hv["n"])
+    ctx = ctx_factory(dom)
+    ctx.set_grid(grid)
+    ctx.remap_dyn_split_rk2_aux_vars(rcs, got, hu["o"], hv["o"], hu["n"], hv["n"])
+    for k in ("u_av", "v_av", "CAu_pred", "CAv_pred", "diffu", "diffv"):
+        assert _beq(ref[k], got[k]), k
+    assert not _beq(ref["u_av"], cs["u_av"])
