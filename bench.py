@@ -241,7 +241,15 @@ def cpu_reference(steps, warmup):
     from mom6_b200 import synthetic
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     ni, nj = SAMPLE
-    work = [synthetic.step_dyn_inputs(ni, nj, NK, whalo=10, land_blocks=3, seed=synthetic.SEED + w, store_CAu=1) for w in range(cores)]
+    def clone(x):
+        if isinstance(x, np.ndarray):
+            return x.copy()
+        if isinstance(x, dict):
+            return {k: clone(v) for k, v in x.items()}
+        return x
+
+    base = synthetic.step_dyn_inputs(ni, nj, NK, whalo=10, land_blocks=3, store_CAu=1)
+    work = [base] + [(base[0], base[1], base[2], base[3], clone(base[4]), clone(base[5])) for _ in range(cores - 1)]
 
     def run(w, n):
         dom, grid, gv, css, cs, a = work[w]

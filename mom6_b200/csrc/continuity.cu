@@ -21,6 +21,7 @@
 //    (no OBCs) can reach, so the row-level `domore` exit is equivalent to the per-thread exit here;
 //    the oracle keeps the row structure and the parity tests check this equivalence.
 #include "ctx.h"
+#include <cstdlib>
 #include "stage.h"
 #include <cmath>
 
@@ -403,6 +404,7 @@ __global__ void __launch_bounds__(128) cont_flux_kernel(const Geom G, const Cont
 //    (uh and duhdu; the 5 sums of set_*_BT_cont) run on different warps at the same time.
 //  * All per-face scalar logic (CFL bounds, Newton bracketing, convergence mask do_I) is replicated in
 //    every thread of the face, so the only barriers are around the k-sums.
+constexpr int CF_NF_DEFAULT = 16;
 struct CellSt { double hR0, hL0, c30, hL1, hR1, c31; };
 
 __device__ __forceinline__ void flux_from_state(const ContCS& CS, const CellSt& S, double face, double un, double visc_rem,
@@ -423,10 +425,15 @@ __device__ __forceinline__ void flux_from_state(const ContCS& CS, const CellSt& 
   duhdu = face * h_marg * visc_rem;
 }
 
+// slice whose threads run the k-ordered task q (q = 0..4): one task per warp, so that the tasks of a phase run concurrently
+template <int NF, int NS>
+__host__ __device__ constexpr int task_slice(int q) { return (q * (32 / NF)) % NS + (q * (32 / NF)) / NS; }
+
 template <bool Z, int NF, int NS, int KPT>
-__global__ void __launch_bounds__(NF* NS, (KPT <= 5) ? 2 : 1)
+__global__ void __launch_bounds__(NF* NS, (KPT <= 5) ? (512 / (NF * NS)) : 1)
 cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
-  static_assert(NS >= 10 && (NF % 16) == 0 && NF <= 32, "k-ordered sums use one warp per quantity (slices 0,2,..,8)");
+  static_assert(NF <= 32 && (32 % NF) == 0 && NF * NS >= 4 * 32, "the four k-ordered tasks of a phase use one warp each");
+  constexpr int T0 = task_slice<NF, NS>(0), T1 = task_slice<NF, NS>(1), T2 = task_slice<NF, NS>(2), T3 = task_slice<NF, NS>(3);
   extern __shared__ double sm[];
   const int nz = A.nk;
   const int PL = nz * NF;
@@ -502,14 +509,14 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
     __syncthreads();
     // ---- one round of k-ordered work, one warp per quantity (s = 2*warp for lanes 0..NF-1):
     //      uh_tot_0, duhdu_tot_0 (:659-662); visc_rem_max (:637-644) followed by du_max_CFL / du_min_CFL (:646-720)
-    if (s == 0) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
-    else if (s == 2) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
-    else if (s == 4 || s == 6) {
+    if (s == T0) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
+    else if (s == T1) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
+    else if (s == T2 || s == T3) {
       double vrm = 1.0;
       if (use_visc_rem && CS.use_visc_rem_max) { vrm = 0.0; for (int k = 0; k < nz; ++k) vrm = fmax2(vrm, sVR[k * NF + f]); }
       double I_vrm = 0.0;
       if (vrm > 0.0) I_vrm = 1.0 / vrm;
-      if (s == 4) {
+      if (s == T2) {
         sR[2 * NF + f] = vrm;
         double du_max_CFL = 2.0 * (CFL_dt * dx_W) * I_vrm;
         for (int k = 0; k < nz; ++k) {
@@ -618,8 +625,8 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
           if (itt < max_itts) {
             __syncthreads();
             if (do_I) {
-              if (s == 0) { double t = -uhbt; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
-              else if (s == 2) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
+              if (s == T0) { double t = -uhbt; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
+              else if (s == T1) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
             }
             __syncthreads();
             if (do_I) {
@@ -629,7 +636,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
           }
         }
       }
-      if (pass == 0) { du = dux; if (A.du_cor && valid && s == 0) A.du_cor[g] = dux; }
+      if (pass == 0) { du = dux; if (A.du_cor && valid && s == T0) A.du_cor[g] = dux; }
       else du0 = dux;
     }
 
@@ -651,7 +658,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         }
       }
       __syncthreads();
-      if (s == 0) {
+      if (s == T0) {
         double duR = fmin2(0.0, du0 - du_CFL);
         for (int k = 0; k < nz; ++k) {
           const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
@@ -660,7 +667,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
             if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = sP[k * NF + f];
         }
         sR[f] = duR;
-      } else if (s == 2) {
+      } else if (s == T1) {
         double duL = fmax2(0.0, du0 + du_CFL);
         for (int k = 0; k < nz; ++k) {
           const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
@@ -689,12 +696,14 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         }
       }
       __syncthreads();
-      if ((s & 1) == 0 && s < 10) {
-        const int qn = s >> 1;
+      int qn = -1;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) if (s == task_slice<NF, NS>(q)) qn = q;
+      if (qn >= 0) {
         double t = 0.0; const double* p = sP + qn * PL + f; for (int k = 0; k < nz; ++k) t = t + p[k * NF]; sR[qn * NF + f] = t;
       }
       __syncthreads();
-      if (s == 0 && valid) {
+      if (s == T0 && valid) {
         const double FAmt_0 = sR[f], FAmt_L = sR[NF + f], FAmt_R = sR[2 * NF + f], uhtot_L = sR[3 * NF + f], uhtot_R = sR[4 * NF + f];
         double FA_0 = FAmt_0, FA_avg = FAmt_0;
         if ((duL - du0) != 0.0) FA_avg = uhtot_L / (duL - du0);
@@ -740,26 +749,28 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   }
 }
 
-constexpr int CF_NF = 16, CF_NS = 16;
+constexpr int CF_NS = 16;
 
-template <bool Z, int KPT>
+template <bool Z, int NF, int KPT>
 int launch_flux_tiled(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& A) {
-  auto kern = cont_flux_tiled<Z, CF_NF, CF_NS, KPT>;
-  const size_t smem = ((size_t)7 * A.nk * CF_NF + 8 * CF_NF) * sizeof(double);
+  auto kern = cont_flux_tiled<Z, NF, CF_NS, KPT>;
+  const size_t smem = ((size_t)7 * A.nk * NF + 8 * NF) * sizeof(double);
   M6_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((A.nhi - A.nlo + CF_NF) / CF_NF, A.ohi - A.olo + 1);
-  M6_LAUNCH(c, kern, grid, CF_NF * CF_NS, smem, G, CS, A);
+  dim3 grid((A.nhi - A.nlo + NF) / NF, A.ohi - A.olo + 1);
+  M6_LAUNCH(c, kern, grid, NF * CF_NS, smem, G, CS, A);
   return 0;
 }
 
 template <bool Z>
 int launch_flux(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& A) {
   const int kpt = (A.nk + CF_NS - 1) / CF_NS;
-  if (kpt <= 1) return launch_flux_tiled<Z, 1>(c, G, CS, A);
-  if (kpt <= 2) return launch_flux_tiled<Z, 2>(c, G, CS, A);
-  if (kpt <= 3) return launch_flux_tiled<Z, 3>(c, G, CS, A);
-  if (kpt <= 5) return launch_flux_tiled<Z, 5>(c, G, CS, A);
-  if (kpt <= 8) return launch_flux_tiled<Z, 8>(c, G, CS, A);
+  static int nf = -1;  // faces per CTA: 16 (256 threads, 2 CTAs/SM) or 8 (128 threads, 4 CTAs/SM); MOM6CU_CONT_NF overrides
+  if (nf < 0) { const char* e = getenv("MOM6CU_CONT_NF"); nf = e ? atoi(e) : CF_NF_DEFAULT; }
+  if (kpt <= 1) return launch_flux_tiled<Z, 16, 1>(c, G, CS, A);
+  if (kpt <= 2) return launch_flux_tiled<Z, 16, 2>(c, G, CS, A);
+  if (kpt <= 3) return launch_flux_tiled<Z, 16, 3>(c, G, CS, A);
+  if (kpt <= 5) return (nf == 8) ? launch_flux_tiled<Z, 8, 5>(c, G, CS, A) : launch_flux_tiled<Z, 16, 5>(c, G, CS, A);
+  if (kpt <= 8) return launch_flux_tiled<Z, 16, 8>(c, G, CS, A);
   // very deep columns: one thread per column
   dim3 grid((A.nhi - A.nlo + 128) / 128, A.ohi - A.olo + 1);
   M6_LAUNCH(c, cont_flux_kernel<Z>, grid, 128, 0, G, CS, A);

@@ -5,6 +5,8 @@
 #include "ctx.h"
 #include "common.cuh"
 #include "remap_column.cuh"
+#include "remap_stream.cuh"
+#include <cstdlib>
 
 using m6::Geom;
 using namespace m6remap;
@@ -12,6 +14,7 @@ using namespace m6remap;
 namespace {
 
 constexpr int MAXF = 16;  // fields per launch
+constexpr int REMAP_MINB_DEFAULT = 1;
 struct Fields { double* p[MAXF]; double underflow[MAXF]; int n; };
 
 template <int KCAP>
@@ -42,6 +45,43 @@ __global__ void __launch_bounds__(128) remap_planes_kernel(Geom G, Params P, int
   if (!(mask[g] > 0.)) return;
   const long pl = G.plane;
   remap_one_column<KCAP>(P, nk, nk, Col{h_old + g, pl}, Col{h_new + g, pl}, F, g, pl, pl);
+}
+
+// streaming form (remap_stream.cuh) for PCM / PLM / PPM_H4: one thread per (column, field); the only thread-local array is the
+// output column, because a target cell may be completed before the source cells below it have been read
+template <int KCAP, int MINB>
+__global__ void __launch_bounds__(128, MINB) remap_planes_stream_kernel(Geom G, Params P, int nk, int ilo, int ihi, int jlo, int jhi,
+                                                                 const double* __restrict__ mask, const double* __restrict__ h_old,
+                                                                 const double* __restrict__ h_new, Fields F) {
+  const int i = ilo + blockIdx.x * blockDim.x + threadIdx.x, j = jlo + blockIdx.y, f = blockIdx.z;
+  if (i > ihi || j > jhi) return;
+  const long g = G.idx(i, j);
+  if (!(mask[g] > 0.)) return;
+  const long pl = G.plane;
+  const double* h0 = h_old + g - pl;  // 1-based level index
+  const double* h1 = h_new + g - pl;
+  double* col = F.p[f] + g - pl;
+  double u1[KCAP + 1];
+  remap_stream(P, nk, nk, [=](int k) { return __ldg(h0 + (long)k * pl); }, [=](int k) { return col[(long)k * pl]; },
+               [=](int k) { return __ldg(h1 + (long)k * pl); }, ColOut{u1 + 1, 1}, F.underflow[f]);
+  for (int k = 1; k <= nk; ++k) col[(long)k * pl] = u1[k];
+}
+
+template <int KCAP>
+__global__ void __launch_bounds__(128) remap_batch_stream_kernel(Params P, int ncol, int n0, int n1, const double* __restrict__ h0,
+                                                                const double* __restrict__ u0, const double* __restrict__ h1,
+                                                                double* __restrict__ u1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  const double *H0 = h0 + (long)c * n0 - 1, *U0 = u0 + (long)c * n0 - 1, *H1 = h1 + (long)c * n1 - 1;
+  remap_stream(P, n0, n1, [=](int k) { return H0[k]; }, [=](int k) { return U0[k]; }, [=](int k) { return H1[k]; },
+               ColOut{u1 + (long)c * n1, 1}, 0.0);
+}
+
+bool use_stream(const Params& P) {
+  static int force_array = -1;
+  if (force_array < 0) { const char* e = getenv("MOM6CU_REMAP_ARRAY"); force_array = (e && atoi(e)) ? 1 : 0; }
+  return !force_array && P.scheme != SCHEME_PPM_IH4;
 }
 
 // a batch of independent columns stored row-major (ncol, n): stride n between columns, 1 between levels
@@ -90,6 +130,17 @@ int launch_planes(mom6cu_ctx* c, const Params& P, int ilo, int ihi, int jlo, int
                   const double* h_new, const Fields& F) {
   const Geom& G = c->g;
   const dim3 grid((ihi - ilo + 1 + 127) / 128, jhi - jlo + 1), block(128);
+  if (use_stream(P)) {
+    const dim3 gs(grid.x, grid.y, F.n);
+    static int minb = -1;  // CTAs/SM the kernel is compiled for: 3 (156 registers) or 4 (128, a few spills); MOM6CU_REMAP_MINB overrides
+    if (minb < 0) { const char* e = getenv("MOM6CU_REMAP_MINB"); minb = e ? atoi(e) : REMAP_MINB_DEFAULT; }
+#define M6_RS(K, B) M6_LAUNCH(c, (remap_planes_stream_kernel<K, B>), gs, block, 0, G, P, G.nk, ilo, ihi, jlo, jhi, mask, h_old, h_new, F)
+    if (minb >= 4) { if (G.nk <= 40) M6_RS(40, 4); else if (G.nk <= 80) M6_RS(80, 4); else M6_RS(128, 4); }
+    else { if (G.nk <= 40) M6_RS(40, 1); else if (G.nk <= 80) M6_RS(80, 1); else M6_RS(128, 1); }
+#undef M6_RS
+    M6_CUDA(c, cudaGetLastError());
+    return 0;
+  }
   if (G.nk <= 40) M6_LAUNCH(c, remap_planes_kernel<40>, grid, block, 0, G, P, G.nk, ilo, ihi, jlo, jhi, mask, h_old, h_new, F);
   else if (G.nk <= 80) M6_LAUNCH(c, remap_planes_kernel<80>, grid, block, 0, G, P, G.nk, ilo, ihi, jlo, jhi, mask, h_old, h_new, F);
   else M6_LAUNCH(c, remap_planes_kernel<128>, grid, block, 0, G, P, G.nk, ilo, ihi, jlo, jhi, mask, h_old, h_new, F);
@@ -190,7 +241,8 @@ extern "C" int mom6cu_remapping_core_h(mom6cu_ctx* c, const mom6cu_remapping_cs*
   M6_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   const dim3 grid((ncol + 127) / 128), block(128);
   const int nmax = std::max(n0, n1);
-  if (nmax <= 40) M6_LAUNCH(c, remap_batch_kernel<40>, grid, block, 0, P, ncol, n0, n1, d_h0, d_u0, d_h1, d_u1);
+  if (use_stream(P)) M6_LAUNCH(c, remap_batch_stream_kernel<1>, grid, block, 0, P, ncol, n0, n1, d_h0, d_u0, d_h1, d_u1);
+  else if (nmax <= 40) M6_LAUNCH(c, remap_batch_kernel<40>, grid, block, 0, P, ncol, n0, n1, d_h0, d_u0, d_h1, d_u1);
   else if (nmax <= 80) M6_LAUNCH(c, remap_batch_kernel<80>, grid, block, 0, P, ncol, n0, n1, d_h0, d_u0, d_h1, d_u1);
   else M6_LAUNCH(c, remap_batch_kernel<128>, grid, block, 0, P, ncol, n0, n1, d_h0, d_u0, d_h1, d_u1);
   M6_CUDA(c, cudaGetLastError());

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(128) vv_coef_kernel(Geom G, CoefK P) {
   const double DA = P.bathyT[g], DB = P.bathyT[g + sB];
   const double Dmin = fmin2(DA, DB);
   const bool surf = (CS.Kvml_invZ2 > 0.) || CS.fixed_LOTW_ML || CS.apply_LOTW_floor;
+  const bool same_units = (P.H_to_Z == 1.0) && (h_neglect == dz_neglect);
   double z_i_below = 0., zh = 0., zcolA = -DA, zcolB = -DB;  // z_i(k+1)
   double hv_below = 0.;                                       // dz_vel(k+1)
   for (int k = nz; k >= 1; --k) {
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(128) vv_coef_kernel(Geom G, CoefK P) {
     const double h_harm = 2. * hA * hB / (hA + hB + h_neglect);
     const double h_arith = 0.5 * (hB + hA);
     const double h_delta = hB - hA;
-    const double dz_harm = 2. * dzA * dzB / (dzA + dzB + dz_neglect);
+    // with H_to_Z = 1 and equal roundoff thicknesses this is the very expression of h_harm: one division less per layer
+    const double dz_harm = same_units ? h_harm : 2. * dzA * dzB / (dzA + dzB + dz_neglect);
     const double dz_arith = 0.5 * (dzB + dzA);
     const double vel = P.vel[o];
     double hvel, dz_vel, z_i;
