@@ -33,6 +33,7 @@ namespace {
 
 struct ContCS {
   int upwind_1st, monotonic, simple_2nd, aggress_adjust, vol_CFL, better_iter, use_visc_rem_max, marginal_faces;
+  int serial_scans;  // MOM6CU_CONT_SERIAL=1: always take the serial select-scan loops (the checked fallback), for testing
   double tol_eta, tol_vel, CFL_limit_adjust, h_min_ppm /* 2*Angstrom_H */;
 };
 
@@ -425,12 +426,55 @@ __device__ __forceinline__ void flux_from_state(const ContCS& CS, const CellSt& 
   duhdu = face * h_marg * visc_rem;
 }
 
+// ---- Select-scans evaluated in parallel, checked exactly ----------------------------------------------------------------
+// The reference's k-loops of the form  "if (test_k(d)) d = c_k"  (:664-720, :1336-1341) are serial, but each one is a running
+// minimum (maximum) of its candidates c_k unless a comparison sits within rounding of its threshold.  The CTA therefore
+// evaluates g_k = min(d_0, c_0 .. c_{k-1}) by segments, then every thread re-applies the reference's own test to (g_k, k) for
+// its layers and checks that it reproduces g_{k+1} bit for bit.  If every check passes, induction on k makes g the serial result;
+// if any fails (or an input is NaN) the whole CTA falls back to the serial loops, so the outcome never depends on the shortcut.
+// Called by the warps >= 2 only (the first two run the k-ordered sums meanwhile): ss = slice index in that group of nss slices.
+template <int NF, class PartA, class CandA, class TrigA, class PartB, class CandB, class TrigB>
+__device__ __forceinline__ bool select_scans(int f, int ss, int nss, int nz, double* agg, double dA0, double dB0, PartA partA,
+                                             CandA candA, TrigA trigA, PartB partB, CandB candB, TrigB trigB, double& dA,
+                                             double& dB) {
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const int seg = (nz + nss - 1) / nss;
+  const int k0 = min(nz, ss * seg), k1 = min(nz, k0 + seg);
+  double mA = inf, mB = -inf;  // scan A is a running minimum, scan B a running maximum
+  for (int k = k0; k < k1; ++k) {
+    if (partA(k)) { const double c = candA(k); mA = (c < mA) ? c : mA; }  // ties keep the earlier element, as the serial loop does,
+    if (partB(k)) { const double c = candB(k); mB = (c > mB) ? c : mB; }  // so the two-level fold equals the one-level fold exactly
+  }
+  agg[ss * NF + f] = mA; agg[(nss + ss) * NF + f] = mB;
+  asm volatile("bar.sync 1, %0;" ::"r"(nss * NF) : "memory");
+  double pA = dA0, pB = dB0;
+  for (int q = 0; q < ss; ++q) {
+    const double a = agg[q * NF + f], b = agg[(nss + q) * NF + f];
+    pA = (a < pA) ? a : pA; pB = (b > pB) ? b : pB;
+  }
+  bool ok = true;
+  for (int k = k0; k < k1; ++k) {
+    if (partA(k)) {
+      const double c = candA(k), nx = (c < pA) ? c : pA, ex = trigA(k, pA) ? c : pA;
+      ok = ok && (__double_as_longlong(nx) == __double_as_longlong(ex));
+      pA = nx;
+    }
+    if (partB(k)) {
+      const double c = candB(k), nx = (c > pB) ? c : pB, ex = trigB(k, pB) ? c : pB;
+      ok = ok && (__double_as_longlong(nx) == __double_as_longlong(ex));
+      pB = nx;
+    }
+  }
+  dA = pA; dB = pB;  // the scans' results in the threads of the last slice (ss == nss-1)
+  return ok;
+}
+
 // slice whose threads run the k-ordered task q (q = 0..4): one task per warp, so that the tasks of a phase run concurrently
 template <int NF, int NS>
 __host__ __device__ constexpr int task_slice(int q) { return (q * (32 / NF)) % NS + (q * (32 / NF)) / NS; }
 
 template <bool Z, int NF, int NS, int KPT>
-__global__ void __launch_bounds__(NF* NS, (KPT <= 5) ? (512 / (NF * NS)) : 1)
+__global__ void __launch_bounds__(NF* NS, (KPT > 5) ? 1 : (NF * NS > 256 ? 2 : 512 / (NF * NS)))
 cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   static_assert(NF <= 32 && (32 % NF) == 0 && NF * NS >= 4 * 32, "the four k-ordered tasks of a phase use one warp each");
   constexpr int T0 = task_slice<NF, NS>(0), T1 = task_slice<NF, NS>(1), T2 = task_slice<NF, NS>(2), T3 = task_slice<NF, NS>(3);
@@ -441,6 +485,10 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   double* sVR = sU + PL;       // visc_rem(f,k)
   double* sP = sVR + PL;       // 5 planes of per-layer terms
   double* sR = sP + 5 * PL;    // [8][NF] per-face results of the k-ordered sums
+  double* sAgg = sR + 8 * NF;  // [2][NS][NF] segment aggregates of select_scans
+  double* sVm = sAgg + 2 * NS * NF;  // [NS][NF] per-thread maxima of visc_rem
+  constexpr int SS0 = 2 * (32 / NF), NSS = NS - SS0;  // select_scans runs on the slices >= SS0 (the warps >= 2)
+  static_assert(NSS >= 1 && (NSS * NF) % 32 == 0, "select_scans needs whole warps");
   const int tid = threadIdx.x, f = tid % NF, s = tid / NF;
   const int n = A.nlo + blockIdx.x * NF + f, o = A.olo + blockIdx.y;
   const bool valid = n <= A.nhi;
@@ -468,7 +516,9 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   }
   const bool fast_cfl = adjust && use_visc_rem && !CS.aggress_adjust;  // the default options
   // ---- load, reconstruct, first flux evaluation (:621-635)
+  bool vr_plain = true;  // every visc_rem of this thread is a non-negative number (so its maximum does not depend on the order)
   {
+    double vr_loc = 0.0;
     double m[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) m[q] = __ldg(A.maskT + g + (q - 2) * sd);
@@ -493,6 +543,8 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         const double vr = use_visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
         const double por = A.por ? __ldg(A.por + gk) : 1.0;
         sU[k * NF + f] = uk; sVR[k * NF + f] = vr;
+        vr_loc = fmax2(vr_loc, vr);
+        vr_plain = vr_plain && (vr >= 0.0) && (__double_as_longlong(vr) >= 0);
         double uh, dd, ha, hm;
         flux_from_state(CS, st[mm], dy * por, uk, vr, dt, cfl0, cfl1, uh, dd, ha, hm);
         if (valid) A.uh[gk] = uh;
@@ -503,6 +555,7 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         }
       }
     }
+    sVm[s * NF + f] = vr_loc;
   }
   double du = 0.0;
   if (adjust) {  // uniform over the grid
@@ -511,47 +564,70 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
     //      uh_tot_0, duhdu_tot_0 (:659-662); visc_rem_max (:637-644) followed by du_max_CFL / du_min_CFL (:646-720)
     if (s == T0) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[k * NF + f]; sR[f] = t; }
     else if (s == T1) { double t = 0.0; for (int k = 0; k < nz; ++k) t = t + sP[PL + k * NF + f]; sR[NF + f] = t; }
-    else if (s == T2 || s == T3) {
+    bool spec_ok = vr_plain && !CS.serial_scans;
+    if (fast_cfl && s >= SS0) {
+      // du_max_CFL / du_min_CFL (:664-720) as checked running extrema; visc_rem_max (:637-644) is an exact maximum
       double vrm = 1.0;
-      if (use_visc_rem && CS.use_visc_rem_max) { vrm = 0.0; for (int k = 0; k < nz; ++k) vrm = fmax2(vrm, sVR[k * NF + f]); }
+      if (CS.use_visc_rem_max) {
+        vrm = 0.0;
+        for (int q = 0; q < NS; ++q) vrm = fmax2(vrm, sVm[q * NF + f]);
+      }
       double I_vrm = 0.0;
       if (vrm > 0.0) I_vrm = 1.0 / vrm;
-      if (s == T2) {
-        sR[2 * NF + f] = vrm;
-        double du_max_CFL = 2.0 * (CFL_dt * dx_W) * I_vrm;
-        for (int k = 0; k < nz; ++k) {
-          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
-          if (use_visc_rem) {
-            if (CS.aggress_adjust) {
-              const double du_lim = 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd)));
-              if (du_max_CFL * vr > du_lim) du_max_CFL = du_lim / vr;
-            } else if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = sP[2 * PL + k * NF + f];
-          } else {
-            if (CS.aggress_adjust)
-              du_max_CFL = fmin2(du_max_CFL, 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd))));
-            else du_max_CFL = fmin2(du_max_CFL, dx_W * CFL_dt - uk);
-          }
-        }
-        sR[3 * NF + f] = fmax2(du_max_CFL, 0.0);
-      } else {
-        double du_min_CFL = -2.0 * (CFL_dt * dx_E) * I_vrm;
-        for (int k = 0; k < nz; ++k) {
-          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
-          if (use_visc_rem) {
-            if (CS.aggress_adjust) {
-              const double du_lim = 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd)));
-              if (du_min_CFL * vr < du_lim) du_min_CFL = du_lim / vr;
-            } else if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = sP[3 * PL + k * NF + f];
-          } else {
-            if (CS.aggress_adjust)
-              du_min_CFL = fmax2(du_min_CFL, 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd))));
-            else du_min_CFL = fmax2(du_min_CFL, -(dx_E * CFL_dt + uk));
-          }
-        }
-        sR[4 * NF + f] = fmin2(du_min_CFL, 0.0);
-      }
+      const double rW = dx_W * CFL_dt, rE = -dx_E * CFL_dt;
+      double dmax, dmin;
+      const bool ok = select_scans<NF>(
+          f, s - SS0, NSS, nz, sAgg, 2.0 * (CFL_dt * dx_W) * I_vrm, -2.0 * (CFL_dt * dx_E) * I_vrm,
+          [&](int) { return true; }, [&](int k) { return sP[2 * PL + k * NF + f]; },
+          [&](int k, double d) { return d * sVR[k * NF + f] > rW - sU[k * NF + f] * maskC; },
+          [&](int) { return true; }, [&](int k) { return sP[3 * PL + k * NF + f]; },
+          [&](int k, double d) { return d * sVR[k * NF + f] < rE - sU[k * NF + f] * maskC; }, dmax, dmin);
+      spec_ok = spec_ok && ok;
+      if (s == NS - 1) { sR[2 * NF + f] = vrm; sR[3 * NF + f] = fmax2(dmax, 0.0); sR[4 * NF + f] = fmin2(dmin, 0.0); }
     }
-    __syncthreads();
+    if (!(__syncthreads_and(spec_ok ? 1 : 0) && fast_cfl)) {  // uniform over the CTA: the reference's serial loops
+      if (s == T2 || s == T3) {
+        double vrm = 1.0;
+        if (use_visc_rem && CS.use_visc_rem_max) { vrm = 0.0; for (int k = 0; k < nz; ++k) vrm = fmax2(vrm, sVR[k * NF + f]); }
+        double I_vrm = 0.0;
+        if (vrm > 0.0) I_vrm = 1.0 / vrm;
+        if (s == T2) {
+          sR[2 * NF + f] = vrm;
+          double du_max_CFL = 2.0 * (CFL_dt * dx_W) * I_vrm;
+          for (int k = 0; k < nz; ++k) {
+            const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+            if (use_visc_rem) {
+              if (CS.aggress_adjust) {
+                const double du_lim = 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd)));
+                if (du_max_CFL * vr > du_lim) du_max_CFL = du_lim / vr;
+              } else if (du_max_CFL * vr > dx_W * CFL_dt - uk * maskC) du_max_CFL = sP[2 * PL + k * NF + f];
+            } else {
+              if (CS.aggress_adjust)
+                du_max_CFL = fmin2(du_max_CFL, 0.499 * ((dx_W * I_dt - uk) + fmin2(0.0, __ldg(A.u + g + (long long)k * G.plane - sd))));
+              else du_max_CFL = fmin2(du_max_CFL, dx_W * CFL_dt - uk);
+            }
+          }
+          sR[3 * NF + f] = fmax2(du_max_CFL, 0.0);
+        } else {
+          double du_min_CFL = -2.0 * (CFL_dt * dx_E) * I_vrm;
+          for (int k = 0; k < nz; ++k) {
+            const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+            if (use_visc_rem) {
+              if (CS.aggress_adjust) {
+                const double du_lim = 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd)));
+                if (du_min_CFL * vr < du_lim) du_min_CFL = du_lim / vr;
+              } else if (du_min_CFL * vr < -dx_E * CFL_dt - uk * maskC) du_min_CFL = sP[3 * PL + k * NF + f];
+            } else {
+              if (CS.aggress_adjust)
+                du_min_CFL = fmax2(du_min_CFL, 0.499 * ((-dx_E * I_dt - uk) + fmax2(0.0, __ldg(A.u + g + (long long)k * G.plane + sd))));
+              else du_min_CFL = fmax2(du_min_CFL, -(dx_E * CFL_dt + uk));
+            }
+          }
+          sR[4 * NF + f] = fmin2(du_min_CFL, 0.0);
+        }
+      }
+      __syncthreads();
+    }
     const double uh_tot_0 = sR[f], duhdu_tot_0 = sR[NF + f], visc_rem_max = sR[2 * NF + f];
     const double du_max_CFL = sR[3 * NF + f], du_min_CFL = sR[4 * NF + f];
     __syncthreads();  // sR is reused by the iterations below
@@ -658,26 +734,42 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         }
       }
       __syncthreads();
-      if (s == T0) {
-        double duR = fmin2(0.0, du0 - du_CFL);
-        for (int k = 0; k < nz; ++k) {
-          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
-          const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
-          if (visc_rem_lim > 0.0)
-            if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = sP[k * NF + f];
-        }
-        sR[f] = duR;
-      } else if (s == T1) {
-        double duL = fmax2(0.0, du0 + du_CFL);
-        for (int k = 0; k < nz; ++k) {
-          const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
-          const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
-          if (visc_rem_lim > 0.0)
-            if (uk + duL * visc_rem_lim < du_CFL * vr) duL = sP[PL + k * NF + f];
-        }
-        sR[NF + f] = duL;
+      bool spec_ok = vr_plain && !CS.serial_scans;
+      if (s >= SS0) {  // duR / duL (:1336-1341) as checked running extrema
+        const double vlim = min_visc_rem * visc_rem_max;
+        double dR, dL;
+        const bool ok = select_scans<NF>(
+            f, s - SS0, NSS, nz, sAgg, fmin2(0.0, du0 - du_CFL), fmax2(0.0, du0 + du_CFL),
+            [&](int k) { return fmax2(sVR[k * NF + f], vlim) > 0.0; }, [&](int k) { return sP[k * NF + f]; },
+            [&](int k, double d) { const double vr = sVR[k * NF + f]; return sU[k * NF + f] + d * fmax2(vr, vlim) > -du_CFL * vr; },
+            [&](int k) { return fmax2(sVR[k * NF + f], vlim) > 0.0; }, [&](int k) { return sP[PL + k * NF + f]; },
+            [&](int k, double d) { const double vr = sVR[k * NF + f]; return sU[k * NF + f] + d * fmax2(vr, vlim) < du_CFL * vr; },
+            dR, dL);
+        spec_ok = spec_ok && ok;
+        if (s == NS - 1) { sR[f] = dR; sR[NF + f] = dL; }
       }
-      __syncthreads();
+      if (!__syncthreads_and(spec_ok ? 1 : 0)) {  // uniform over the CTA: the reference's serial loops
+        if (s == T0) {
+          double duR = fmin2(0.0, du0 - du_CFL);
+          for (int k = 0; k < nz; ++k) {
+            const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+            const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
+            if (visc_rem_lim > 0.0)
+              if (uk + duR * visc_rem_lim > -du_CFL * vr) duR = sP[k * NF + f];
+          }
+          sR[f] = duR;
+        } else if (s == T1) {
+          double duL = fmax2(0.0, du0 + du_CFL);
+          for (int k = 0; k < nz; ++k) {
+            const double uk = sU[k * NF + f], vr = sVR[k * NF + f];
+            const double visc_rem_lim = fmax2(vr, min_visc_rem * visc_rem_max);
+            if (visc_rem_lim > 0.0)
+              if (uk + duL * visc_rem_lim < du_CFL * vr) duL = sP[PL + k * NF + f];
+          }
+          sR[NF + f] = duL;
+        }
+        __syncthreads();
+      }
       const double duR = sR[f], duL = sR[NF + f];
 #pragma unroll
       for (int mm = 0; mm < KPT; ++mm) {
@@ -751,13 +843,13 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
 
 constexpr int CF_NS = 16;
 
-template <bool Z, int NF, int KPT>
+template <bool Z, int NF, int KPT, int NS = CF_NS>
 int launch_flux_tiled(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& A) {
-  auto kern = cont_flux_tiled<Z, NF, CF_NS, KPT>;
-  const size_t smem = ((size_t)7 * A.nk * NF + 8 * NF) * sizeof(double);
+  auto kern = cont_flux_tiled<Z, NF, NS, KPT>;
+  const size_t smem = ((size_t)7 * A.nk * NF + 8 * NF + 3 * NS * NF) * sizeof(double);
   M6_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((A.nhi - A.nlo + NF) / NF, A.ohi - A.olo + 1);
-  M6_LAUNCH(c, kern, grid, NF * CF_NS, smem, G, CS, A);
+  M6_LAUNCH(c, kern, grid, NF * NS, smem, G, CS, A);
   return 0;
 }
 
@@ -815,6 +907,7 @@ int m6_continuity_run(mom6cu_ctx* c, const ContinuityDev& D) {
   CS.vol_CFL = S.vol_CFL; CS.better_iter = S.better_iter; CS.use_visc_rem_max = S.use_visc_rem_max;
   CS.marginal_faces = S.marginal_faces; CS.tol_eta = S.tol_eta; CS.tol_vel = S.tol_vel;
   CS.CFL_limit_adjust = S.CFL_limit_adjust; CS.h_min_ppm = 2.0 * c->vgrid.Angstrom_H;
+  { const char* e = getenv("MOM6CU_CONT_SERIAL"); CS.serial_scans = (e && atoi(e) != 0) ? 1 : 0; }
   const int stencil = S.upwind_1st ? 1 : (S.simple_2nd ? 2 : 3);
   const mom6cu_domain& d = c->dom;
   if ((d.isc - d.isd) < stencil || (d.jsc - d.jsd) < stencil)

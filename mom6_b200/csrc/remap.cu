@@ -14,7 +14,7 @@ using namespace m6remap;
 namespace {
 
 constexpr int MAXF = 16;  // fields per launch
-constexpr int REMAP_MINB_DEFAULT = 1;
+constexpr int REMAP_MINB_DEFAULT = 4;  // measured: 10.2 ms (4 CTAs/SM) vs 12.4 ms (1) per field at 1440x1080x75
 struct Fields { double* p[MAXF]; double underflow[MAXF]; int n; };
 
 template <int KCAP>

@@ -1,6 +1,6 @@
 """Tile-layout invariance of the whole baroclinic step (the reference's `layout` test, .testing/Makefile:607):
-step_MOM_dyn_split_RK2 on 2 tiles with NCCL halo exchanges == the single-tile oracle, bit for bit.
-Needs 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_step_multigpu.py -m gpu`."""
+step_MOM_dyn_split_RK2 on 2 (2x1, 1x2) or 4 (2x2, corner exchanges) tiles with NCCL halo exchanges == the single-tile oracle,
+bit for bit.  Needs 2 / 4 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_step_multigpu.py -m gpu`."""
 import os
 import socket
 
@@ -53,7 +53,7 @@ def _worker(rank, world, port, npi, npj, q):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("npi,npj", [(2, 1), (1, 2)])
+@pytest.mark.parametrize("npi,npj", [(2, 1), (1, 2), (2, 2)])
 def test_step_two_tiles_bitwise(oracle, npi, npj):
     import torch
     import torch.multiprocessing as mp
