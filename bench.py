@@ -3,16 +3,19 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A "step" is one baroclinic dynamics step (step_MOM_dyn_split_RK2, MOM_dynamics_split_RK2.F90:294-1205) of the
-OM4_025-shaped synthetic configuration (1440 x 1080 x 75, BASELINE.json configs[3]) through every stage implemented
-so far, in the call counts of one reference step (config.stages; the stages of the step not yet on the device are
-listed in config.stages_missing -- the number is a lower bound on the work of a full step, not a full step).
+A "step" is one whole baroclinic dynamics step (step_MOM_dyn_split_RK2, MOM_dynamics_split_RK2.F90:294-1205: pressure
+force, CorAdCalc, vertvisc_coef/vertvisc/vertvisc_remnant, 3 x continuity_PPM, 2 x btstep with its barotropic subcycle,
+horizontal_viscosity and the seven group passes) of the OM4_025-shaped synthetic configuration (1440 x 1080 x 75,
+BASELINE.json configs[1]) as ONE call of the C ABI (mom6cu_step_dyn_split_rk2).
 value = cell-updates/s = ni*nj*nk*K / t with every field resident in HBM (mom6cu_plane_*), t = device time of the K
-steps (CUDA events on the launching stream, per stage, summed) -- ms_per_step_wall is the host wall clock of the same
-loop.  e2e = the same step through the C ABI with HOST arrays (staging copies inside the timed region).
-roofline = the dominant kernel group against the measured HBM peak.  cpu_baseline / --impl reference = the oracle
-restatement of the reference CPU path with OpenMP on the host cores, on a bounded sample tile (the Fortran reference
-cannot be built: no Fortran/MPI/netCDF/FMS in the image).
+steps (CUDA events on the launching stream, max over ranks); ms_per_step_wall is the host wall clock of the same loop.
+e2e = the same call with the model state, T, S, visc% and forces% in pinned HOST arrays (staging copies inside the timed
+region, results copied back).  roofline = the dominant stage (continuity_PPM) against the measured HBM peak; per_stage =
+each stage timed alone; thermo_pass = tracer advection + ALE regrid/remap, which run once per DT_THERM/DT dynamics steps.
+cpu_baseline / --impl reference = the oracle restatement of the reference CPU path, one single-threaded rank per host
+core on the tiles of an MPI-style decomposition (the Fortran reference cannot be built here: no Fortran compiler, MPI,
+netCDF or FMS in the image).  N > 1: the same global grid on a 2x1 / 2x2 / 4x2 tile layout, one rank per GPU, NCCL halo
+exchanges (strong scaling).
 """
 import argparse
 import json

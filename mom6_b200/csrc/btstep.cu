@@ -22,6 +22,7 @@
 #include "stage.h"
 #include <algorithm>
 #include <cmath>
+#include <thread>
 #include <vector>
 
 using m6::Geom;
@@ -473,7 +474,16 @@ int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev
     M6_CUDA(c, cudaMemcpyAsync(hpk, dpk, 2 * npk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     M6_CUDA(c, cudaStreamSynchronize(c->stream));
     const long long n2 = (long long)(2 * npk);
-#pragma omp parallel for schedule(static)
+    // thread count chosen here, not by OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to every rank, which would leave this
+    // loop on one core (MOM6CU_HOST_THREADS overrides; default = the rank's share of the host cores, at most 32)
+    static int nthr = 0;
+    if (nthr == 0) {
+      const char* e = getenv("MOM6CU_HOST_THREADS");
+      const char* l = getenv("LOCAL_WORLD_SIZE");
+      const int hw = (int)std::thread::hardware_concurrency(), lws = (l && atoi(l) > 0) ? atoi(l) : 1;
+      nthr = (e && atoi(e) > 0) ? atoi(e) : std::max(1, std::min(32, hw / lws));
+    }
+#pragma omp parallel for schedule(static) num_threads(nthr)
     for (long long n = 0; n < n2; ++n) hpk[n] = (hpk[n] > 0.0) ? std::pow(hpk[n], Instep) : 0.0;
     M6_CUDA(c, cudaMemcpyAsync(dpk, hpk, 2 * npk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     // rows/columns outside the computational faces stay zero, as in the reference's zero-initialised wide arrays

@@ -117,6 +117,73 @@ __device__ __forceinline__ void ppm_cell(const ContCS& CS, double hm2, double hm
   }
 }
 
+// The limited slope of PPM_reconstruction_x :2372-2376 for the cell hc with neighbours hm | hp (0 next to land).
+__device__ __forceinline__ double ppm_slope(double hm, double hc, double hp, double mprod) {
+  if (mprod == 0.0) return 0.0;
+  const double s = 0.5 * (hp - hm);
+  const double dMx = fmax2(fmax2(hp, hm), hc) - hc;
+  const double dMn = hc - fmin2(fmin2(hp, hm), hc);
+  return copysign(1., s) * fmin2(fabs(s), 2. * fmin2(dMx, dMn));
+}
+
+// PPM_limit_pos :2596-2614 / PPM_limit_CW84 :2640-2654 on one cell's edge values.
+__device__ __forceinline__ void ppm_limit(const ContCS& CS, double hc, double& hL, double& hR) {
+  if (CS.monotonic) {
+    if ((hR - hc) * (hc - hL) <= 0.) { hL = hc; hR = hc; }
+    else {
+      const double RLdiff = hR - hL;
+      const double RLmean = 0.5 * (hR + hL);
+      const double FunFac = 6. * RLdiff * (hc - RLmean);
+      const double RLdiff2 = RLdiff * RLdiff;
+      if (FunFac > RLdiff2) hL = 3. * hc - 2. * hR;
+      if (FunFac < -RLdiff2) hR = 3. * hc - 2. * hL;
+    }
+  } else {
+    const double curv = 3.0 * ((hL + hR) - 2.0 * hc);
+    if (curv > 0.0) {
+      const double dh = hR - hL;
+      if (fabs(dh) < curv) {
+        if (hc <= CS.h_min_ppm) { hL = hc; hR = hc; }
+        else if (12.0 * curv * (hc - CS.h_min_ppm) < (curv * curv + 3.0 * (dh * dh))) {
+          const double scale = 12.0 * curv * (hc - CS.h_min_ppm) / (curv * curv + 3.0 * (dh * dh));
+          hL = hc + scale * (hL - hc);
+          hR = hc + scale * (hR - hc);
+        }
+      }
+    }
+  }
+}
+
+// Edge values of the two cells either side of a face (cells 0 and +1 of h[-2..+3], masks m[0..5]): the same arithmetic as two
+// ppm_cell calls, with the slopes of the cells 0 and +1 -- which both reconstructions use -- evaluated once.
+__device__ __forceinline__ void ppm_pair(const ContCS& CS, double hm2, double hm1, double h0, double hp1, double hp2, double hp3,
+                                         const double* m, double& hL0, double& hR0, double& hL1, double& hR1) {
+  if (CS.upwind_1st || CS.simple_2nd) {
+    ppm_cell(CS, hm2, hm1, h0, hp1, hp2, m[0], m[1], m[2], m[3], m[4], hL0, hR0);
+    ppm_cell(CS, hm1, h0, hp1, hp2, hp3, m[1], m[2], m[3], m[4], m[5], hL1, hR1);
+    return;
+  }
+  const double oneSixth = 1. / 6.;
+  const double s_a = ppm_slope(hm2, hm1, h0, m[0] * m[1] * m[2]);
+  const double s_b = ppm_slope(hm1, h0, hp1, m[1] * m[2] * m[3]);
+  const double s_c = ppm_slope(h0, hp1, hp2, m[2] * m[3] * m[4]);
+  const double s_d = ppm_slope(hp1, hp2, hp3, m[3] * m[4] * m[5]);
+  {
+    const double h_im1 = m[1] * hm1 + (1.0 - m[1]) * h0;
+    const double h_ip1 = m[3] * hp1 + (1.0 - m[3]) * h0;
+    hL0 = 0.5 * (h_im1 + h0) + oneSixth * (s_a - s_b);
+    hR0 = 0.5 * (h_ip1 + h0) + oneSixth * (s_b - s_c);
+    ppm_limit(CS, h0, hL0, hR0);
+  }
+  {
+    const double h_im1 = m[2] * h0 + (1.0 - m[2]) * hp1;
+    const double h_ip1 = m[4] * hp2 + (1.0 - m[4]) * hp1;
+    hL1 = 0.5 * (h_im1 + hp1) + oneSixth * (s_b - s_c);
+    hR1 = 0.5 * (h_ip1 + hp1) + oneSixth * (s_c - s_d);
+    ppm_limit(CS, hp1, hL1, hR1);
+  }
+}
+
 // Per-thread column context
 struct Col {
   double m[6];        // mask2dT of cells -2..+3 along the flow direction
@@ -474,7 +541,7 @@ template <int NF, int NS>
 __host__ __device__ constexpr int task_slice(int q) { return (q * (32 / NF)) % NS + (q * (32 / NF)) / NS; }
 
 template <bool Z, int NF, int NS, int KPT>
-__global__ void __launch_bounds__(NF* NS, (KPT > 5) ? 1 : (NF * NS > 256 ? 2 : 512 / (NF * NS)))
+__global__ void __launch_bounds__(NF* NS, (KPT > 5 || NF * NS > 512) ? 1 : (NF * NS > 256 ? 2 : 512 / (NF * NS)))
 cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   static_assert(NF <= 32 && (32 % NF) == 0 && NF * NS >= 4 * 32, "the four k-ordered tasks of a phase use one warp each");
   constexpr int T0 = task_slice<NF, NS>(0), T1 = task_slice<NF, NS>(1), T2 = task_slice<NF, NS>(2), T3 = task_slice<NF, NS>(3);
@@ -534,11 +601,10 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
         const double* hk = A.h + gk;
         const double hm2 = __ldg(hk - 2 * sd), hm1 = __ldg(hk - sd), h0 = __ldg(hk), hp1 = __ldg(hk + sd),
                      hp2 = __ldg(hk + 2 * sd), hp3 = __ldg(hk + 3 * sd);
-        double hL, hR;
-        ppm_cell(CS, hm2, hm1, h0, hp1, hp2, m[0], m[1], m[2], m[3], m[4], hL, hR);
+        double hL, hR, hL1, hR1;
+        ppm_pair(CS, hm2, hm1, h0, hp1, hp2, hp3, m, hL, hR, hL1, hR1);
         st[mm].hR0 = hR; st[mm].hL0 = hL; st[mm].c30 = (hL + hR) - 2.0 * h0;
-        ppm_cell(CS, hm1, h0, hp1, hp2, hp3, m[1], m[2], m[3], m[4], m[5], hL, hR);
-        st[mm].hL1 = hL; st[mm].hR1 = hR; st[mm].c31 = (hL + hR) - 2.0 * hp1;
+        st[mm].hL1 = hL1; st[mm].hR1 = hR1; st[mm].c31 = (hL1 + hR1) - 2.0 * hp1;
         const double uk = __ldg(A.u + gk);
         const double vr = use_visc_rem ? __ldg(A.visc_rem + gk) : 1.0;
         const double por = A.por ? __ldg(A.por + gk) : 1.0;
@@ -861,7 +927,10 @@ int launch_flux(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& 
   if (kpt <= 1) return launch_flux_tiled<Z, 16, 1>(c, G, CS, A);
   if (kpt <= 2) return launch_flux_tiled<Z, 16, 2>(c, G, CS, A);
   if (kpt <= 3) return launch_flux_tiled<Z, 16, 3>(c, G, CS, A);
-  if (kpt <= 5) return (nf == 8) ? launch_flux_tiled<Z, 8, 5>(c, G, CS, A) : launch_flux_tiled<Z, 16, 5>(c, G, CS, A);
+  if (kpt <= 5 && nf == 8) return launch_flux_tiled<Z, 8, 2, 40>(c, G, CS, A);    // 8 faces x 40 slices x 2 layers (nk <= 80), 2 CTAs/SM
+  if (kpt <= 5 && nf == 164) return launch_flux_tiled<Z, 16, 2, 40>(c, G, CS, A);  // 16 faces x 40 slices x 2 layers, 1 CTA/SM
+  if (kpt <= 5 && nf == 88) return launch_flux_tiled<Z, 8, 5>(c, G, CS, A);
+  if (kpt <= 5) return launch_flux_tiled<Z, 16, 5>(c, G, CS, A);
   if (kpt <= 8) return launch_flux_tiled<Z, 16, 8>(c, G, CS, A);
   // very deep columns: one thread per column
   dim3 grid((A.nhi - A.nlo + 128) / 128, A.ohi - A.olo + 1);

@@ -58,7 +58,7 @@ CASES = [dict(), dict(land_blocks=4, old_grid_weight=0.75, depth_of_time_filter_
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", CASES)
 def test_ale_regrid_bitwise(oracle, ctx_factory, kw):
-    for (ni, nj, nk) in ((44, 40, 20), (131, 9, 3)):
+    for (ni, nj, nk) in ((44, 40, 20), (131, 9, 3), (30, 22, 75)):
         dom, grid, gv, cs, a = synthetic.regrid_inputs(ni, nj, nk, **kw)
         ref = {k: v.copy() for k, v in a.items()}
         assert oracle.ale_regrid(dom, grid, gv, cs, ref["h"], ref["h_new"], ref["dzRegrid"]) == 0

@@ -57,9 +57,13 @@ def test_core_h_batch_bitwise(oracle, ctx_factory):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", [dict(), dict(remapping_scheme=2, boundary_extrapolation=1, om4_remap_via_sub_cells=0, land_blocks=4),
                                 dict(remapping_scheme=5, kind="uniform", land_blocks=3, cyclic_y=True),
-                                dict(remapping_scheme=0, ntr=1), dict(ntr=19, land_blocks=2, force_bounds_in_subcell=1)])
+                                dict(remapping_scheme=0, ntr=1), dict(ntr=19, land_blocks=2, force_bounds_in_subcell=1),
+                                dict(size=(36, 28, 75), land_blocks=2),                       # OM4 layer count (the 80-layer kernel variant)
+                                dict(size=(36, 28, 75), remapping_scheme=2, land_blocks=2),
+                                dict(size=(20, 16, 110), remapping_scheme=5, ntr=2)])         # the 128-layer variant
 def test_ale_remap_tracers_and_velocities_bitwise(oracle, ctx_factory, kw):
-    dom, grid, cs, a = synthetic.remap_inputs(44, 40, 12, **kw)
+    kw = dict(kw)
+    dom, grid, cs, a = synthetic.remap_inputs(*kw.pop("size", (44, 40, 12)), **kw)
     ctx = ctx_factory(dom)
     ctx.set_grid(grid)
     ntr = len(a["tr"])

@@ -20,6 +20,9 @@ CASES = [
     (40, 30, 8, dict(cs_over=dict(aggress_adjust=1, vol_CFL=1))),
     (40, 30, 8, dict(cs_over=dict(better_iter=0, use_visc_rem_max=0, marginal_faces=0))),
     (120, 60, 15, dict(land_blocks=8, first_direction=1)),
+    (52, 36, 75, dict(land_blocks=3)),                             # OM4 layer count: 5 layers per thread in the tiled flux kernel
+    (40, 30, 40, dict(land_blocks=2, with_uhbt=False)),            # 3 layers per thread
+    (33, 21, 130, dict(land_blocks=2)),                            # deeper than the tiled kernel: one thread per column
 ]
 
 

@@ -54,7 +54,8 @@ def test_store_cau_skips_the_first_coradcalc(oracle):
 
 
 CASES = [dict(), dict(land_blocks=4, store_CAu=1, begw=0.5), dict(land_blocks=2, split_bottom_stress=1, BT_project_velocity=1),
-         dict(land_blocks=3, calc_dtbt=1, store_CAu=1)]
+         dict(land_blocks=3, calc_dtbt=1, store_CAu=1),
+         dict(size=(36, 28, 75), land_blocks=2, store_CAu=1)]      # OM4 layer count: the nk-dependent kernel variants of the bench
 
 
 def _dtbt_args(dom, grid, cs, mode):
@@ -96,7 +97,8 @@ def test_set_dtbt_bitwise(oracle, ctx_factory, mode):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", CASES)
 def test_step_bitwise(oracle, ctx_factory, kw):
-    dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(44, 40, 8, **kw)
+    kw = dict(kw)
+    dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(*kw.pop("size", (44, 40, 8)), **kw)
     rcs, ra = _copy(cs), _copy(a)
     gcs, ga = _copy(cs), _copy(a)
     ctx = ctx_factory(dom)
