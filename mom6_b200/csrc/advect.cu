@@ -60,22 +60,22 @@ __device__ __forceinline__ void face_transport(const AdvPass& P, long long o, lo
                                                bool& lim) {
   // o: 3-D offset (hp, tr);  o2: 2-D offset (areaT);  s, s2: strides along the direction
   const double tiny_h = DBL_MIN;
-  const double u = P.tr_old[o];
+  const double u = __ldg(P.tr_old + o);
   lim = false;
-  if ((u == 0.0) || ((u < 0.0) && (P.hp_old[o + s] <= tiny_h)) || ((u > 0.0) && (P.hp_old[o] <= tiny_h))) {
+  if ((u == 0.0) || ((u < 0.0) && (__ldg(P.hp_old + o + s) <= tiny_h)) || ((u > 0.0) && (__ldg(P.hp_old + o) <= tiny_h))) {
     uhh = 0.0; CFL = 0.0;
   } else if (u < 0.0) {
-    const double hup = P.hp_old[o + s] - P.areaT[o2 + s2] * P.min_h;
-    const double hlos = fmax2(0.0, P.tr_old[o + s]);
+    const double hup = __ldg(P.hp_old + o + s) - __ldg(P.areaT + o2 + s2) * P.min_h;
+    const double hlos = fmax2(0.0, __ldg(P.tr_old + o + s));
     if ((((hup - hlos) + u) < 0.0) && ((0.5 * hup + u) < 0.0)) { uhh = min3(-0.5 * hup, -hup + hlos, 0.0); lim = true; }
     else uhh = u;
-    CFL = -uhh / (P.hp_old[o + s]);
+    CFL = -uhh / (__ldg(P.hp_old + o + s));
   } else {
-    const double hup = P.hp_old[o] - P.areaT[o2] * P.min_h;
-    const double hlos = fmax2(0.0, -P.tr_old[o - s]);
+    const double hup = __ldg(P.hp_old + o) - __ldg(P.areaT + o2) * P.min_h;
+    const double hlos = fmax2(0.0, -__ldg(P.tr_old + o - s));
     if ((((hup - hlos) - u) < 0.0) && ((0.5 * hup - u) < 0.0)) { uhh = max3(0.5 * hup, hup - hlos, 0.0); lim = true; }
     else uhh = u;
-    CFL = uhh / (P.hp_old[o]);
+    CFL = uhh / (__ldg(P.hp_old + o));
   }
 }
 
@@ -84,14 +84,14 @@ __device__ __forceinline__ double face_flux(int scheme, const double* __restrict
                                             long long s, long long s2, double uhh, double CFL) {
   if (scheme == MOM6CU_ADVECT_PLM) {
     if (uhh >= 0.0) {
-      const double sl = plm_slope(T[o + s], T[o], T[o - s], maskC[o2] * maskC[o2 - s2]);
-      return uhh * (T[o] + 0.5 * sl * (1. - CFL));
+      const double sl = plm_slope(__ldg(T + o + s), __ldg(T + o), __ldg(T + o - s), __ldg(maskC + o2) * __ldg(maskC + o2 - s2));
+      return uhh * (__ldg(T + o) + 0.5 * sl * (1. - CFL));
     }
-    const double sl = plm_slope(T[o + 2 * s], T[o + s], T[o], maskC[o2 + s2] * maskC[o2]);
-    return uhh * (T[o + s] - 0.5 * sl * (1. - CFL));
+    const double sl = plm_slope(__ldg(T + o + 2 * s), __ldg(T + o + s), __ldg(T + o), __ldg(maskC + o2 + s2) * __ldg(maskC + o2));
+    return uhh * (__ldg(T + o + s) - 0.5 * sl * (1. - CFL));
   }
   const long long u3 = (uhh >= 0.0) ? o : o + s, u2 = (uhh >= 0.0) ? o2 : o2 + s2;  // the upstream cell
-  const double Tp = T[u3 + s], Tc = T[u3], Tm = T[u3 - s];
+  const double Tp = __ldg(T + u3 + s), Tc = __ldg(T + u3), Tm = __ldg(T + u3 - s);
   double aL, aR;
   if (scheme == MOM6CU_ADVECT_PPMH3) {
     aL = (5. * Tc + (2. * Tm - Tp)) / 6.;
@@ -99,14 +99,14 @@ __device__ __forceinline__ double face_flux(int scheme, const double* __restrict
     aR = (5. * Tc + (2. * Tp - Tm)) / 6.;
     aR = fmax2(fmin2(Tc, Tp), aR); aR = fmin2(fmax2(Tc, Tp), aR);
   } else {
-    const double sl_m = plm_slope(Tc, Tm, T[u3 - 2 * s], maskC[u2 - s2] * maskC[u2 - 2 * s2]);
-    const double sl_c = plm_slope(Tp, Tc, Tm, maskC[u2] * maskC[u2 - s2]);
-    const double sl_p = plm_slope(T[u3 + 2 * s], Tp, Tc, maskC[u2 + s2] * maskC[u2]);
+    const double sl_m = plm_slope(Tc, Tm, __ldg(T + u3 - 2 * s), __ldg(maskC + u2 - s2) * __ldg(maskC + u2 - 2 * s2));
+    const double sl_c = plm_slope(Tp, Tc, Tm, __ldg(maskC + u2) * __ldg(maskC + u2 - s2));
+    const double sl_p = plm_slope(__ldg(T + u3 + 2 * s), Tp, Tc, __ldg(maskC + u2 + s2) * __ldg(maskC + u2));
     aL = 0.5 * ((Tm + Tc) + (sl_m - sl_c) / 3.);
     aR = 0.5 * ((Tc + Tp) + (sl_c - sl_p) / 3.);
   }
   const double dA = aR - aL, mA = 0.5 * (aR + aL);
-  if (maskC[u2] * maskC[u2 - s2] * (Tp - Tc) * (Tc - Tm) <= 0.) { aL = Tc; aR = Tc; }
+  if (__ldg(maskC + u2) * __ldg(maskC + u2 - s2) * (Tp - Tc) * (Tc - Tm) <= 0.) { aL = Tc; aR = Tc; }
   else if (dA * (Tc - mA) > (dA * dA) / 6.) aL = (3. * Tc) - 2. * aR;
   else if (dA * (Tc - mA) < -(dA * dA) / 6.) aR = (3. * Tc) - 2. * aL;
   const double a6 = 6. * Tc - 3. * (aR + aL);
@@ -120,13 +120,13 @@ __device__ __forceinline__ void cell_update(const AdvPass& P, long long o, long 
                                             const double* fl_hi) {
   bool do_i = false;
   double hlst = 0., Ihnew = 0.;
-  double hnew = P.hp_old[o];
+  double hnew = __ldg(P.hp_old + o);
   if ((uhh_hi != 0.0) || (uhh_lo != 0.0)) {
     do_i = true;
     hlst = hnew;
     hnew = hnew - (uhh_hi - uhh_lo);
     if (YPASS) hnew = fmax2(hnew, 0.0);
-    const double hmin = P.h_neglect * P.areaT[o2];
+    const double hmin = P.h_neglect * __ldg(P.areaT + o2);
     if (hnew <= 0.0) do_i = false;
     else if (hnew < hmin) { hlst = hlst + (hmin - hnew); Ihnew = 1.0 / hmin; }
     else Ihnew = 1.0 / hnew;
@@ -134,7 +134,7 @@ __device__ __forceinline__ void cell_update(const AdvPass& P, long long o, long 
   if (P.first) P.hp_new[o] = hnew;
 #pragma unroll
   for (int m = 0; m < NTB; ++m) if (m < P.nt) {
-    double T = P.T_old[m][o];
+    double T = __ldg(P.T_old[m] + o);
     if (do_i && (!YPASS ? (Ihnew > 0.0) : true)) T = (T * hlst - (fl_hi[m] - fl_lo[m])) * Ihnew;
     if (P.underflow[m] > 0.0 && fabs(T) < P.underflow[m]) T = 0.0;
     P.T_new[m][o] = T;
@@ -165,10 +165,10 @@ __global__ void __launch_bounds__(XB) advect_x_kernel(Geom G, AdvPass P) {
   __syncthreads();
   if (!face) return;
   if (P.first && (t > 0 || blockIdx.x == 0)) {  // :609-612: each face is written by one block
-    double r = P.tr_old[o];
+    double r = __ldg(P.tr_old + o);
     if (domore) {
       r = r - uhh;
-      if (fabs(r) < P.H_subroundoff * fmin2(P.areaT[o2], P.areaT[o2 + 1])) r = 0.0;
+      if (fabs(r) < P.H_subroundoff * fmin2(__ldg(P.areaT + o2), __ldg(P.areaT + o2 + 1))) r = 0.0;
     }
     P.tr_new[o] = r;
   }
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(128) advect_y_kernel(Geom G, AdvPass P) {
     if (own) {
       any_lim |= lim;
       if (P.first) {
-        double r = P.tr_old[o] - uhh;
-        if (fabs(r) < P.H_subroundoff * fmin2(P.areaT[o2], P.areaT[o2 + s2])) r = 0.0;
+        double r = __ldg(P.tr_old + o) - uhh;
+        if (fabs(r) < P.H_subroundoff * fmin2(__ldg(P.areaT + o2), __ldg(P.areaT + o2 + s2))) r = 0.0;
         P.tr_new[o] = r;
       }
     }

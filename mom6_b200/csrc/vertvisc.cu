@@ -36,7 +36,7 @@ struct CoefK {
 __device__ __forceinline__ double botfn6(double z2) { return 1. / (1. + 0.09 * z2 * z2 * z2 * z2 * z2 * z2); }
 
 template <int DIR>  // 0: u-points (I,j), 1: v-points (i,J)
-__global__ void __launch_bounds__(128) vv_coef_kernel(Geom G, CoefK P) {
+__global__ void __launch_bounds__(128, 6) vv_coef_kernel(Geom G, CoefK P) {
   const int i = P.i0 + blockIdx.x * blockDim.x + threadIdx.x, j = P.j0 + blockIdx.y;
   if (i > P.i1) return;
   const long long g = G.idx(i, j), pl = G.plane;
@@ -56,9 +56,24 @@ __global__ void __launch_bounds__(128) vv_coef_kernel(Geom G, CoefK P) {
   const bool same_units = (P.H_to_Z == 1.0) && (h_neglect == dz_neglect);
   double z_i_below = 0., zh = 0., zcolA = -DA, zcolB = -DB;  // z_i(k+1)
   double hv_below = 0.;                                       // dz_vel(k+1)
+  // The loads of the level above are issued before this level's arithmetic and stores (the compiler cannot move them across
+  // the stores itself: it has to assume h_out / a_out may alias the inputs), so two levels of a column are in flight.
+  double hA_n, hB_n, vel_n, ksA_n = 0., ksB_n = 0., kqA_n = 0., kqB_n = 0.;
+  {
+    const long long o = (long long)(nz - 1) * pl + g;
+    hA_n = __ldg(P.h + o); hB_n = __ldg(P.h + o + sB); vel_n = __ldg(P.vel + o);
+  }
   for (int k = nz; k >= 1; --k) {
     const long long o = (long long)(k - 1) * pl + g;
-    const double hA = P.h[o], hB = P.h[o + sB];
+    const double hA = hA_n, hB = hB_n;
+    const double ksA = ksA_n, ksB = ksB_n, kqA = kqA_n, kqB = kqB_n;   // Kv_shear[_Bu] at the interface K = k+1
+    const double vel_k = vel_n;
+    if (k > 1) {
+      const long long on = o - pl;
+      hA_n = __ldg(P.h + on); hB_n = __ldg(P.h + on + sB); vel_n = __ldg(P.vel + on);
+      if (P.Kv_shear) { ksA_n = __ldg(P.Kv_shear + o); ksB_n = __ldg(P.Kv_shear + o + sB); }             // interface K = k
+      if (P.Kv_shear_Bu) { kqA_n = __ldg(P.Kv_shear_Bu + o + sQ); kqB_n = __ldg(P.Kv_shear_Bu + o); }
+    }
     const double dzA = P.H_to_Z * hA, dzB = P.H_to_Z * hB;
     const double h_harm = 2. * hA * hB / (hA + hB + h_neglect);
     const double h_arith = 0.5 * (hB + hA);
@@ -66,7 +81,7 @@ __global__ void __launch_bounds__(128) vv_coef_kernel(Geom G, CoefK P) {
     // with H_to_Z = 1 and equal roundoff thicknesses this is the very expression of h_harm: one division less per layer
     const double dz_harm = same_units ? h_harm : 2. * dzA * dzB / (dzA + dzB + dz_neglect);
     const double dz_arith = 0.5 * (dzB + dzA);
-    const double vel = P.vel[o];
+    const double vel = vel_k;
     double hvel, dz_vel, z_i;
     if (CS.harmonic_visc) {
       hvel = h_harm; dz_vel = dz_harm;
@@ -108,9 +123,9 @@ __global__ void __launch_bounds__(128) vv_coef_kernel(Geom G, CoefK P) {
       double Kv_tot = CS.Kv;  // the Kvml_invZ2 term is added in the downward pass
       double Kv_extra = 0.;
       bool has_extra = false;
-      if (P.Kv_shear) { Kv_extra = 0.5 * (P.Kv_shear[oK + g] + P.Kv_shear[oK + g + sB]); has_extra = true; }
+      if (P.Kv_shear) { Kv_extra = 0.5 * (ksA + ksB); has_extra = true; }
       double Kv_bu = 0.;
-      if (P.Kv_shear_Bu) Kv_bu = 0.5 * (P.Kv_shear_Bu[oK + g + sQ] + P.Kv_shear_Bu[oK + g]);
+      if (P.Kv_shear_Bu) Kv_bu = 0.5 * (kqA + kqB);
       if (!(CS.Kvml_invZ2 > 0.)) {
         if (has_extra) Kv_tot = Kv_tot + Kv_extra;
         if (P.Kv_shear_Bu) Kv_tot = Kv_tot + Kv_bu;
@@ -237,25 +252,45 @@ __global__ void __launch_bounds__(128) vv_solve_kernel(Geom G, SolveK P) {
   }
   if (mask > 0. && j >= P.js_solve) {
     double c1[KMAX + 1];
-    double b_denom_1 = P.hh[g] + dt * ((P.Ray ? P.Ray[g] : 0.) + P.a[g]);
-    double b1 = 1.0 / (b_denom_1 + dt * P.a[pl + g]);
+    // a, hh, Ray are read-only here; x is read and written at different levels.  The next level's operands are loaded before
+    // this level's store (which the compiler must otherwise treat as a possible alias), so two levels are in flight.
+    double a_k1 = __ldg(P.a + pl + g);                                   // a(K=2)
+    double b_denom_1 = __ldg(P.hh + g) + dt * ((P.Ray ? __ldg(P.Ray + g) : 0.) + __ldg(P.a + g));
+    double b1 = 1.0 / (b_denom_1 + dt * a_k1);
     double d1 = b_denom_1 * b1;
-    double xm = REM ? b1 * P.hh[g] : b1 * (P.hh[g] * P.x[g] + surface_stress);
+    double xm = REM ? b1 * __ldg(P.hh + g) : b1 * (__ldg(P.hh + g) * P.x[g] + surface_stress);
+    double hk_n = 0., ray_n = 0., x_n = 0., a_n = 0.;
+    if (nz >= 2) {
+      hk_n = __ldg(P.hh + pl + g); if (P.Ray) ray_n = __ldg(P.Ray + pl + g);
+      if (!REM) x_n = P.x[pl + g];
+      a_n = __ldg(P.a + 2 * pl + g);                                       // a(K=3)
+    }
     P.x[g] = xm;
     for (int k = 2; k <= nz; ++k) {
       const long long o = (long long)(k - 1) * pl + g;
-      const double aK = P.a[o], hk = P.hh[o];
+      const double aK = a_k1, hk = hk_n, ray = ray_n, xk = x_n, a_below = a_n;
+      if (k < nz) {
+        hk_n = __ldg(P.hh + o + pl); if (P.Ray) ray_n = __ldg(P.Ray + o + pl);
+        if (!REM) x_n = P.x[o + pl];
+        a_n = __ldg(P.a + o + 2 * pl);
+      }
+      a_k1 = a_below;
       c1[k] = dt * aK * b1;
-      b_denom_1 = hk + dt * ((P.Ray ? P.Ray[o] : 0.) + aK * d1);
-      b1 = 1.0 / (b_denom_1 + dt * P.a[o + pl]);
+      b_denom_1 = hk + dt * ((P.Ray ? ray : 0.) + aK * d1);
+      b1 = 1.0 / (b_denom_1 + dt * a_below);
       d1 = b_denom_1 * b1;
-      xm = REM ? (hk + dt * aK * xm) * b1 : (hk * P.x[o] + dt * aK * xm) * b1;
+      xm = REM ? (hk + dt * aK * xm) * b1 : (hk * xk + dt * aK * xm) * b1;
       P.x[o] = xm;
     }
-    for (int k = nz - 1; k >= 1; --k) {
-      const long long o = (long long)(k - 1) * pl + g;
-      xm = P.x[o] + c1[k + 1] * xm;
-      P.x[o] = xm;
+    if (nz >= 2) {
+      double xk_n = P.x[(long long)(nz - 2) * pl + g];
+      for (int k = nz - 1; k >= 1; --k) {
+        const long long o = (long long)(k - 1) * pl + g;
+        const double xk = xk_n;
+        if (k > 1) xk_n = P.x[o - pl];
+        xm = xk + c1[k + 1] * xm;
+        P.x[o] = xm;
+      }
     }
   }
   if (!REM && P.tau_bot && j >= P.js_stress) {  // :903-912

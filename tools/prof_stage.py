@@ -10,7 +10,7 @@ ni = int(sys.argv[2]) if len(sys.argv) > 2 else 1440
 nj = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
 nk = int(sys.argv[4]) if len(sys.argv) > 4 else 75
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-BYTES = {"continuity": 96, "corad": 56, "hor_visc": 56, "pgf": 48, "remap": 32, "btstep": 136, "advect": 128}
+BYTES = {"continuity": 96, "corad": 56, "hor_visc": 56, "pgf": 48, "remap": 32, "btstep": 136, "advect": 128, "vertvisc": 144}
 t0 = time.time()
 if stage == "corad":
     dom, grid, gv, cs, a = synthetic.coradcalc_inputs(ni, nj, nk, land_blocks=40)
@@ -27,6 +27,8 @@ elif stage == "advect":   # 2 tracers, 1 iteration = x pass + y pass: 2 x (hprev
     dom, grid, gv, cs, a = synthetic.advect_inputs(ni, nj, nk, land_blocks=40, cfl=0.9)
 elif stage == "btstep":
     dom, grid, gv, cs, a = synthetic.btstep_inputs(ni, nj, nk, whalo=10, land_blocks=40)
+elif stage == "vertvisc":   # vertvisc_coef (u+v: 2 x 40 B) + vertvisc (2 x 32 B) per cell
+    dom, grid, gv, cs, a, sol = synthetic.vertvisc_inputs(ni, nj, nk, land_blocks=40)
 else:
     raise SystemExit("unknown stage " + stage)
 print(f"inputs built in {time.time()-t0:.1f}s", flush=True)
@@ -48,6 +50,12 @@ elif stage == "advect":
         print("iterations", ctx.advect_tracer(cs, b))
 elif stage == "btstep":
     run = lambda a: ctx.btstep(cs, a)
+elif stage == "vertvisc":
+    ctx.set_cs_vertvisc(cs)
+    def run(a):
+        ctx.vertvisc_coef(a); t1 = ctx.last_kernel_ms
+        ctx.vertvisc(sol); t2 = ctx.last_kernel_ms
+        print(f"vertvisc_coef {t1:.3f} ms, vertvisc {t2:.3f} ms")
 for r in range(reps):
     run(a)
     ms = ctx.last_kernel_ms
