@@ -10,8 +10,9 @@ BASELINE.json configs[1]) as ONE call of the C ABI (mom6cu_step_dyn_split_rk2).
 value = cell-updates/s = ni*nj*nk*K / t with every field resident in HBM (mom6cu_plane_*), t = device time of the K
 steps (CUDA events on the launching stream, max over ranks); ms_per_step_wall is the host wall clock of the same loop.
 e2e = the same call with the model state, T, S, visc% and forces% in pinned HOST arrays (staging copies inside the timed
-region, results copied back).  roofline = the dominant stage (continuity_PPM) against the measured HBM peak; per_stage =
-each stage timed alone; thermo_pass = tracer advection + ALE regrid/remap, which run once per DT_THERM/DT dynamics steps.
+region, results copied back).  in_step = device time of each stage INSIDE the timed steps (CUDA events around its kernels,
+mom6cu_last_step_stage_ms); roofline = the dominant of those (continuity_PPM) against the measured HBM peak;
+per_stage_isolated = each stage called alone on synthetic stage inputs; thermo_pass = tracer advection + ALE regrid/remap, which run once per DT_THERM/DT dynamics steps.
 cpu_baseline / --impl reference = the oracle restatement of the reference CPU path, one single-threaded rank per host
 core on the tiles of an MPI-style decomposition (the Fortran reference cannot be built here: no Fortran compiler, MPI,
 netCDF or FMS in the image).  N > 1: the same global grid on a 2x1 / 2x2 / 4x2 tile layout, one rank per GPU, NCCL halo
@@ -350,9 +351,12 @@ def main():
     dev_ms = 0.0
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
+        in_step = {}
         for _ in range(args.steps):
             ctx.step_dyn_split_rk2(rcs, rsa)
             dev_ms += ctx.last_kernel_ms
+            for k, v in ctx.last_step_stage_ms().items():   # CUDA events around each stage's kernels inside this step
+                in_step[k] = in_step.get(k, 0.0) + v
         barrier()
         wall = time.perf_counter() - t0
     launches = ctx.launches - n1
@@ -421,7 +425,25 @@ def main():
         ms = times[name] / (stage_passes * calls)
         per_stage[name] = {"calls_per_step": calls, "ms_per_call": ms, "algorithmic_B_per_cell": bpc,
                            "achieved_GBps": tile_cells * bpc / (ms * 1e-3) / 1e9, "frac_of_peak": tile_cells * bpc / (ms * 1e-3) / 1e9 / peak}
-    if per_stage:
+    # the same stages timed INSIDE the K timed steps (this rank's tile): calls per step as the step makes them
+    IN_STEP = {"pressure_force": (1, 48), "coradcalc": (2, 56), "vertvisc": (1, 512), "continuity": (3, 96), "btcalc": (2, 32), "btstep": (2, 136),
+               "horizontal_viscosity": (1, 40)}
+    in_step_tab = {}
+    for name, tot in in_step.items():
+        calls, bpc = IN_STEP[name]
+        ms_step = tot / args.steps
+        gbs = tile_cells * bpc * calls / (ms_step * 1e-3) / 1e9 if ms_step > 0 else 0.0
+        in_step_tab[name] = {"calls_per_step": calls, "ms_per_step": ms_step, "share_of_step": ms_step / (dev_ms / args.steps),
+                             "algorithmic_B_per_cell_per_call": bpc, "achieved_GBps": gbs, "frac_of_peak": gbs / peak}
+    if in_step_tab:
+        covered = sum(v["ms_per_step"] for v in in_step_tab.values())
+        in_step_tab["glue_and_halo_updates"] = {"ms_per_step": dev_ms / args.steps - covered, "share_of_step": 1.0 - covered / (dev_ms / args.steps)}
+    if in_step_tab and world == 1:
+        dom_stage = max(IN_STEP, key=lambda k: in_step_tab[k]["ms_per_step"])
+        t = in_step_tab[dom_stage]
+        ds = {"achieved_GBps": t["achieved_GBps"], "frac_of_peak": t["frac_of_peak"], "algorithmic_B_per_cell": IN_STEP[dom_stage][1],
+              "launch_ms": t["ms_per_step"] / t["calls_per_step"], "share": t["share_of_step"]}
+    elif per_stage:
         dom_stage = max(per_stage, key=lambda k: per_stage[k]["ms_per_call"] * per_stage[k]["calls_per_step"])
         ds = per_stage[dom_stage]
     else:   # multi-GPU runs: the whole step against the sum of the stages' algorithmic bytes
@@ -430,7 +452,7 @@ def main():
         ms = dev_ms / args.steps
         ds = {"achieved_GBps": tile_cells * bpc / (ms * 1e-3) / 1e9, "frac_of_peak": tile_cells * bpc / (ms * 1e-3) / 1e9 / peak,
               "algorithmic_B_per_cell": bpc}
-    kernel_of = {"continuity": "cont_flux_tiled<zonal|meridional> + cont_convergence_kernel", "btstep": "bt_substep_kernel x68 + bt_col_kernel + bt_layer_accel_kernel",
+    kernel_of = {"continuity": "cont_flux_tiled<zonal|meridional> + cont_convergence_kernel", "btstep": "bt_substep_kernel x26 + bt_col_kernel + bt_layer_accel_kernel", "vertvisc": "vv_coef_kernel + vv_solve_kernel",
                  "coradcalc": "corad_kernel", "horizontal_viscosity": "hor_visc_kernel", "btcalc": "btcalc_kernel", "bt_mass_source": "bt_mass_source_kernel",
                  "pressure_force": "pgf_main_kernel", "step": "all stage kernels of one step"}
     line = {"metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": world,
@@ -446,8 +468,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": kernel_of[dom_stage], "stage": dom_stage, "achieved": ds["achieved_GBps"], "peak": peak,
                          "unit": "GB/s", "frac": ds["frac_of_peak"], "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": tile_cells * ds["algorithmic_B_per_cell"],
-                         "note": "stage-level: algorithmic bytes of one stage call / CUDA-event time of its kernels"},
-            "per_stage": per_stage, "clocks": clk.summary()}
+                         "avg_launch_ms": ds.get("launch_ms"), "share_of_step": ds.get("share"),
+                         "note": "algorithmic bytes of one stage call / its average CUDA-event time INSIDE the timed steps (in_step); "
+                                 "per_stage_isolated = the same stages called alone on synthetic stage inputs"},
+            "in_step": in_step_tab, "per_stage_isolated": per_stage, "clocks": clk.summary()}
     if thermo:
         per8 = THERMO_EVERY * dev_ms / args.steps + thermo["total_ms"]
         thermo["every_n_steps"] = THERMO_EVERY

@@ -78,6 +78,18 @@ int mom6cu_sync(mom6cu_ctx* ctx);
 double mom6cu_last_kernel_ms(const mom6cu_ctx* ctx);
 /* passes made by the most recent iterative entry (mom6cu_advect_tracer: the itt loop, MOM_tracer_advect.F90:222-340) */
 int mom6cu_last_iterations(const mom6cu_ctx* ctx);
+/* Device time (ms) each stage took INSIDE the most recent mom6cu_step_dyn_split_rk2 call, summed over its calls in the step
+ * (CUDA events around the stage's kernels on the compute stream).  Fills ms[0..n): MOM6CU_STAGE_* below; returns the
+ * number of entries written. */
+#define MOM6CU_STAGE_PRESSURE_FORCE 0
+#define MOM6CU_STAGE_CORADCALC 1
+#define MOM6CU_STAGE_VERTVISC 2
+#define MOM6CU_STAGE_CONTINUITY 3
+#define MOM6CU_STAGE_BTCALC 4
+#define MOM6CU_STAGE_BTSTEP 5
+#define MOM6CU_STAGE_HOR_VISC 6
+#define MOM6CU_NSTAGES 7
+int mom6cu_last_step_stage_ms(const mom6cu_ctx* ctx, double* ms, int n);
 /* Sum of the device times of all repetitions of the most recent *_resident call. */
 double mom6cu_total_kernel_ms(const mom6cu_ctx* ctx);
 

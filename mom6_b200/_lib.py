@@ -293,6 +293,8 @@ def bind(lib):
     lib.mom6cu_last_kernel_ms.argtypes = [vp]
     lib.mom6cu_last_iterations.argtypes = [vp]
     lib.mom6cu_last_kernel_ms.restype = C.c_double
+    lib.mom6cu_last_step_stage_ms.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    lib.mom6cu_last_step_stage_ms.restype = C.c_int
     lib.mom6cu_total_kernel_ms.argtypes = [vp]
     lib.mom6cu_total_kernel_ms.restype = C.c_double
     lib.mom6cu_set_grid.argtypes = [vp, C.POINTER(Grid)]

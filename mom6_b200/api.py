@@ -54,6 +54,14 @@ class Context:
     def last_kernel_ms(self):
         return float(self.lib.mom6cu_last_kernel_ms(self._h))
 
+    STAGES = ("pressure_force", "coradcalc", "vertvisc", "continuity", "btcalc", "btstep", "horizontal_viscosity")
+
+    def last_step_stage_ms(self):
+        """Device time each stage took inside the most recent step_dyn_split_rk2 call (summed over its calls in the step)."""
+        buf = (C.c_double * len(self.STAGES))()
+        n = self.lib.mom6cu_last_step_stage_ms(self._h, buf, len(self.STAGES))
+        return {self.STAGES[i]: float(buf[i]) for i in range(n)}
+
     @property
     def total_kernel_ms(self):
         return float(self.lib.mom6cu_total_kernel_ms(self._h))

@@ -12,7 +12,8 @@ double* mom6cu_ctx::buf(const std::string& name, size_t n) {
     fail(MOM6CU_ERR_CUDA, "cudaMalloc of %zu doubles for '%s' failed", n, name.c_str());
     return nullptr;
   }
-  cudaMemsetAsync(p, 0, n * sizeof(double), stream);
+  // zero-filled on the stream the first upload will use, so that the fill can never land after it
+  cudaMemsetAsync(p, 0, n * sizeof(double), xfer ? xfer : stream);
   bufs[name] = p;
   buf_sz[name] = n;
   return p;
@@ -66,7 +67,7 @@ int m6_up(mom6cu_ctx* c, const double* src, int stagger, int wide, int nk, doubl
                                  c->g.pitch, c->g.rows);
   p.extent = make_cudaExtent(ni * sizeof(double), nj, nk);
   p.kind = cudaMemcpyDefault;
-  M6_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+  M6_CUDA(c, cudaMemcpy3DAsync(&p, c->xfer ? c->xfer : c->stream));
   return 0;
 }
 
@@ -81,7 +82,7 @@ int m6_down(mom6cu_ctx* c, const double* src_plane, int stagger, int wide, int n
   p.dstPtr = make_cudaPitchedPtr((void*)dst, ni * sizeof(double), ni, nj);
   p.extent = make_cudaExtent(ni * sizeof(double), nj, nk);
   p.kind = cudaMemcpyDefault;
-  M6_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+  M6_CUDA(c, cudaMemcpy3DAsync(&p, c->xfer ? c->xfer : c->stream));
   return 0;
 }
 
@@ -160,6 +161,8 @@ int mom6cu_create(mom6cu_ctx** out, const mom6cu_domain* dom, int device) {
   g.isdw = d.isdw; g.iedw = d.iedw; g.jsdw = d.jsdw; g.jedw = d.jedw;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
@@ -178,6 +181,9 @@ int mom6cu_destroy(mom6cu_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_side) cudaEventDestroy(c->ev_side);
+  for (cudaEvent_t e : c->stage_ev) cudaEventDestroy(e);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->copy) cudaStreamDestroy(c->copy);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->side) cudaStreamDestroy(c->side);
   delete c;
@@ -195,6 +201,12 @@ int mom6cu_last_error(const mom6cu_ctx* c, char* b, size_t len) {
 long long mom6cu_launch_count(const mom6cu_ctx* c) { return c ? c->launches : 0; }
 double mom6cu_last_kernel_ms(const mom6cu_ctx* c) { return c ? c->last_ms : 0.0; }
 int mom6cu_last_iterations(const mom6cu_ctx* c) { return c ? c->last_iterations : 0; }
+int mom6cu_last_step_stage_ms(const mom6cu_ctx* c, double* ms, int n) {
+  if (!c || !ms) return 0;
+  const int m = n < MOM6CU_NSTAGES ? n : MOM6CU_NSTAGES;
+  for (int i = 0; i < m; ++i) ms[i] = c->stage_ms[i];
+  return m;
+}
 double mom6cu_total_kernel_ms(const mom6cu_ctx* c) { return c ? c->total_ms : 0.0; }
 
 double* mom6cu_plane_alloc(mom6cu_ctx* c, const char* name, int nk) {

@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "../../include/mom6cu.h"
 #include "common.cuh"
@@ -18,11 +19,15 @@ struct mom6cu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;  // compute stream
   cudaStream_t side = nullptr;    // halo-exchange stream
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr;
+  cudaStream_t copy = nullptr;    // staging copies that overlap the stage kernels (Stager::defer / early)
+  cudaStream_t xfer = nullptr;    // stream m6_up / m6_down enqueue on (null: the compute stream)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_copy = nullptr;
   double last_ms = 0.0;   // device time of the most recent compute entry / repetition
   double total_ms = 0.0;  // summed over the repetitions of the most recent resident call
   long long launches = 0;
   int last_iterations = 0;  // passes made by the most recent iterative entry (advect_tracer)
+  double stage_ms[8] = {0};  // device time per stage inside the most recent step (mom6cu_last_step_stage_ms)
+  std::vector<cudaEvent_t> stage_ev;  // event pool of the in-step stage timer
   int warnings = 0;
   char err[1024] = {0};
   std::map<std::string, double*> bufs;
@@ -101,15 +106,25 @@ struct Stager {
   std::string pfx;
   struct Out { const double* dev; double* host; int st, wide, nk; };
   std::vector<Out> outs;
+  // Only page-locked host arrays take the overlapped path: copies from pageable memory block the host thread anyway.
+  static bool pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  }
   Stager(mom6cu_ctx* c_, const char* prefix) : c(c_), pfx(prefix) {}
+  ~Stager() { c->xfer = nullptr; }
   int in(const double* src, int st, int wide, int nk, const char* name, const double** dst) {
     *dst = nullptr;
     if (!src) return 0;
     if (c->is_plane(src)) { *dst = src; return 0; }  // already resident: use in place
-    double* p = c->buf(pfx + name, (size_t)c->g.plane * nk);
-    if (!p) return MOM6CU_ERR_CUDA;
-    *dst = p;
-    return m6_up(c, src, st, wide, nk, p);
+    cudaStream_t keep = c->xfer;
+    if (keep && !pinned(src)) c->xfer = nullptr;  // pageable sources stay on the compute stream (see defer_begin)
+    double* p = c->buf(pfx + name, (size_t)c->g.plane * nk);  // a new buffer is zero-filled on the stream of its upload
+    int rc = MOM6CU_ERR_CUDA;
+    if (p) { *dst = p; rc = m6_up(c, src, st, wide, nk, p); }
+    c->xfer = keep;
+    return rc;
   }
   int io(double* src, int st, int wide, int nk, const char* name, double** dst) {
     const double* p = nullptr;
@@ -122,11 +137,43 @@ struct Stager {
   int in2(const double* s, int st, const char* n, const double** d) { return in(s, st, 0, 1, n, d); }
   int io3(double* s, int st, const char* n, double** d) { return io(s, st, 0, c->g.nk, n, d); }
   int io2(double* s, int st, const char* n, double** d) { return io(s, st, 0, 1, n, d); }
+  // Overlapped staging (host-array callers only; resident planes never get here).  defer_begin(): the uploads registered from
+  // now on go to the copy stream, queued behind the uploads already issued on the compute stream (one H2D stream at a time, so
+  // the first group arrives at full PCIe speed); defer_end() closes the group and wait_deferred() makes the compute stream wait
+  // for it -- call it just before the first kernel that reads a deferred field.
+  static bool overlap_on() { static int v = -1; if (v < 0) { const char* e = getenv("MOM6CU_NO_OVERLAP"); v = (e && atoi(e) != 0) ? 0 : 1; } return v == 1; }
+  bool overlap = false;
+  int defer_begin() {
+    overlap = overlap_on();
+    if (!overlap) return 0;
+    M6_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+    M6_CUDA(c, cudaStreamWaitEvent(c->copy, c->ev_copy, 0));
+    c->xfer = c->copy;
+    return 0;
+  }
+  int defer_end() { if (!overlap) return 0; c->xfer = nullptr; M6_CUDA(c, cudaEventRecord(c->ev_copy, c->copy)); deferred = true; return 0; }
+  int wait_deferred() { if (deferred) { M6_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); deferred = false; } return 0; }
+  // early(dev): the output staged from `dev` is final -- download it now on the copy stream, under the kernels still to come.
+  int early(const double* dev) {
+    if (!overlap_on()) return 0;
+    for (Out& o : outs) if (o.dev == dev && o.host && pinned(o.host)) {
+      M6_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+      M6_CUDA(c, cudaStreamWaitEvent(c->copy, c->ev_copy, 0));
+      c->xfer = c->copy;
+      const int rc = m6_down(c, o.dev, o.st, o.wide, o.nk, o.host);
+      c->xfer = nullptr;
+      o.host = nullptr; used_copy = true;
+      return rc;
+    }
+    return 0;
+  }
+  bool deferred = false, used_copy = false;
   int begin() { M6_CUDA(c, cudaEventRecord(c->ev0, c->stream)); return 0; }
   int finish() {
     M6_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    for (const Out& o : outs) { int rc = m6_down(c, o.dev, o.st, o.wide, o.nk, o.host); if (rc) return rc; }
+    for (const Out& o : outs) { if (!o.host) continue; int rc = m6_down(c, o.dev, o.st, o.wide, o.nk, o.host); if (rc) return rc; }
     M6_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (used_copy || deferred) M6_CUDA(c, cudaStreamSynchronize(c->copy));
     float ms = 0.f;
     M6_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_ms = ms; c->total_ms = ms;

@@ -82,6 +82,29 @@ __global__ void step_copy2_kernel(Geom G, int is, int ie, int js, int je, const 
 
 }  // namespace
 
+// Device time of each stage inside the step (mom6cu_last_step_stage_ms): event pairs on the compute stream, read after finish().
+struct StageTimer {
+  mom6cu_ctx* c;
+  int n = 0;
+  int ids[40];
+  explicit StageTimer(mom6cu_ctx* c_) : c(c_) {}
+  void start(int id) {
+    if (n >= 40) return;
+    while ((int)c->stage_ev.size() < 2 * (n + 1)) { cudaEvent_t e = nullptr; cudaEventCreate(&e); c->stage_ev.push_back(e); }
+    ids[n] = id;
+    cudaEventRecord(c->stage_ev[2 * n], c->stream);
+  }
+  void stop() { if (n < 40) { cudaEventRecord(c->stage_ev[2 * n + 1], c->stream); ++n; } }
+  void collect() {  // the stream has been synchronised
+    for (int i = 0; i < 8; ++i) c->stage_ms[i] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->stage_ev[2 * i], c->stage_ev[2 * i + 1]) == cudaSuccess) c->stage_ms[ids[i]] += ms;
+    }
+  }
+};
+#define M6_TIMED(id, expr) do { ST_.start(id); rc = (expr); ST_.stop(); if (rc) return rc; } while (0)
+
 extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs* CS, const mom6cu_step_dyn_args* a) {
   if (!c || !CS || !a) return MOM6CU_ERR_BAD_ARG;
   M6_CUDA(c, cudaSetDevice(c->device));
@@ -98,23 +121,33 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   const int nz = G.nk, is = d.isc, ie = d.iec, js = d.jsc, je = d.jec;
   const double dt = a->dt;
   Stager S(c, "step.");
+  StageTimer ST_(c);
   int rc;
   // ---- arguments
   double *u, *v, *h, *uh, *vh, *uhtr, *vhtr, *eta_av;
   const double *T, *Sa, *p_surf;
   VvCoefDev VC = {};
   VvDev VS = {};
-  if ((rc = S.io3(a->u_inst, ST_U, "u", &u)) || (rc = S.io3(a->v_inst, ST_V, "v", &v)) || (rc = S.io3(a->h, ST_H, "h", &h)) ||
-      (rc = S.io3(a->uh, ST_U, "uh", &uh)) || (rc = S.io3(a->vh, ST_V, "vh", &vh)) || (rc = S.io3(a->uhtr, ST_U, "uhtr", &uhtr)) ||
-      (rc = S.io3(a->vhtr, ST_V, "vhtr", &vhtr)) || (rc = S.io2(a->eta_av, ST_H, "eta_av", &eta_av)) ||
-      (rc = S.in3(a->T, ST_H, "T", &T)) || (rc = S.in3(a->S, ST_H, "S", &Sa)) || (rc = S.in2(a->p_surf, ST_H, "p_surf", &p_surf)) ||
+  // What the pressure force reads goes first, on the compute stream; the velocities, viscosities and stresses follow on the copy
+  // stream while PressureForce runs (host-array callers only: a resident plane is used in place and costs nothing here).
+  if ((rc = S.io3(a->h, ST_H, "h", &h)) || (rc = S.in3(a->T, ST_H, "T", &T)) || (rc = S.in3(a->S, ST_H, "S", &Sa)) ||
+      (rc = S.in2(a->p_surf, ST_H, "p_surf", &p_surf)) || (rc = S.io3(a->uh, ST_U, "uh", &uh)) || (rc = S.io3(a->vh, ST_V, "vh", &vh)) ||
+      (rc = S.io3(a->uhtr, ST_U, "uhtr", &uhtr)) || (rc = S.io3(a->vhtr, ST_V, "vhtr", &vhtr)) || (rc = S.io2(a->eta_av, ST_H, "eta_av", &eta_av)))
+    return rc;
+  if ((rc = S.defer_begin())) return rc;  // page-locked sources only; pageable ones stay on the compute stream
+  rc = 0;
+  if ((rc = S.io3(a->u_inst, ST_U, "u", &u)) || (rc = S.io3(a->v_inst, ST_V, "v", &v)) ||
       (rc = S.in2(a->Kv_bbl_u, ST_U, "kbu", &VC.Kv_bbl_u)) || (rc = S.in2(a->Kv_bbl_v, ST_V, "kbv", &VC.Kv_bbl_v)) ||
       (rc = S.in2(a->bbl_thick_u, ST_U, "btu", &VC.bbl_thick_u)) || (rc = S.in2(a->bbl_thick_v, ST_V, "btv", &VC.bbl_thick_v)) ||
       (rc = S.in(a->Kv_shear, ST_H, 0, nz + 1, "kvs", &VC.Kv_shear)) || (rc = S.in(a->Kv_shear_Bu, ST_Q, 0, nz + 1, "kvq", &VC.Kv_shear_Bu)) ||
       (rc = S.in2(a->ustar, ST_H, "ustar", &VC.ustar)) || (rc = S.in2(a->taux, ST_U, "taux", &VS.taux)) ||
       (rc = S.in2(a->tauy, ST_V, "tauy", &VS.tauy)) || (rc = S.in3(a->Ray_u, ST_U, "Ray_u", &VS.Ray_u)) ||
-      (rc = S.in3(a->Ray_v, ST_V, "Ray_v", &VS.Ray_v)))
-    return rc;
+      (rc = S.in3(a->Ray_v, ST_V, "Ray_v", &VS.Ray_v))) {}
+  {
+    const int rc2 = S.defer_end();
+    if (rc) return rc;
+    if (rc2) return rc2;
+  }
   // ---- the control structure's arrays
   double *CAu, *CAv, *CAu_pred, *CAv_pred, *PFu, *PFv, *diffu, *diffv, *vru, *vrv, *abu, *abv, *u_av, *v_av, *h_av, *pbce, *eta, *eta_PF,
       *uhbt, *vhbt, *taux_bot, *tauy_bot;
@@ -168,17 +201,18 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   M6_CUDA(c, cudaMemcpyAsync(hp, h, b3, cudaMemcpyDeviceToDevice, c->stream));
   // :503 PressureForce
   PgfDev PD = {h, T, Sa, p_surf, PFu, PFv, pbce, eta_PF};
-  if ((rc = m6_pressure_force_run(c, PD))) return rc;
+  M6_TIMED(MOM6CU_STAGE_PRESSURE_FORCE, m6_pressure_force_run(c, PD));
+  if ((rc = S.wait_deferred())) return rc;  // u, v, visc%, forces% have arrived
   // :556 CorAdCalc (predictor accelerations, unless stored by the previous step)
   CorAdDev CA = {};
   CA.u = u_av; CA.v = v_av; CA.h = h_av; CA.uh = uh; CA.vh = vh;
-  if (!CS->CAu_pred_stored) { CA.CAu = CAu_pred; CA.CAv = CAv_pred; if ((rc = m6_coradcalc_run(c, CA))) return rc; }
+  if (!CS->CAu_pred_stored) { CA.CAu = CAu_pred; CA.CAv = CAv_pred; M6_TIMED(MOM6CU_STAGE_CORADCALC, m6_coradcalc_run(c, CA)); }
   // :565-601
   AccelK AK = {is, ie, js, je, c->grid.mask2dCu, c->grid.mask2dCv, CAu_pred, CAv_pred, PFu, PFv, diffu, diffv, u, v, bcu, bcv, up, vp, dt, 1};
   M6_LAUNCH(c, step_bc_accel_kernel, g3, 128, 0, G, AK);
   // :609-610 vertvisc_coef, vertvisc_remnant
   VC.u = up; VC.v = vp; VC.h = h; VC.dt = dt;
-  if ((rc = m6_vertvisc_coef_run(c, VC)) || (rc = m6_vertvisc_remnant_run(c, VS.Ray_u, VS.Ray_v, vru, vrv, dt))) return rc;
+  M6_TIMED(MOM6CU_STAGE_VERTVISC, (rc = m6_vertvisc_coef_run(c, VC)) ? rc : m6_vertvisc_remnant_run(c, VS.Ray_u, VS.Ray_v, vru, vrv, dt));
   // :616-617 pass_eta, pass_visc_rem
   if ((rc = halo({eta}, {ST_H}, 1)) || (rc = halo({vru, vrv}, {ST_U, ST_V}, nz))) return rc;
   // :629 bt_mass_source(h, eta, .true.)
@@ -186,8 +220,8 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   // :646-651 continuity (layer fluxes for the barotropic solver), btcalc
   ContinuityDev C1 = CD;
   C1.u = u; C1.v = v; C1.hin = h; C1.h = hp; C1.uh = uh_in; C1.vh = vh_in; C1.dt = dt; C1.visc_rem_u = vru; C1.visc_rem_v = vrv; C1.have_BT_cont = 1;
-  if ((rc = m6_continuity_run(c, C1))) return rc;
-  if ((rc = m6_btcalc_run(c, h, CD.h_u, CD.h_v, c->grid.bathyT, CS->hvel_scheme, 0, (double*)BCS.frhatu, (double*)BCS.frhatv))) return rc;
+  M6_TIMED(MOM6CU_STAGE_CONTINUITY, m6_continuity_run(c, C1));
+  M6_TIMED(MOM6CU_STAGE_BTCALC, m6_btcalc_run(c, h, CD.h_u, CD.h_v, c->grid.bathyT, CS->hvel_scheme, 0, (double*)BCS.frhatu, (double*)BCS.frhatv));
   // :663-669 set_dtbt
   if (a->calc_dtbt) {
     mom6cu_set_dtbt_args sd = {};
@@ -211,7 +245,7 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   B1.have_BT_cont = 1;
   B1.FA_u_EE = CD.FA_u_EE; B1.FA_u_E0 = CD.FA_u_E0; B1.FA_u_W0 = CD.FA_u_W0; B1.FA_u_WW = CD.FA_u_WW; B1.uBT_WW = CD.uBT_WW; B1.uBT_EE = CD.uBT_EE;
   B1.FA_v_NN = CD.FA_v_NN; B1.FA_v_N0 = CD.FA_v_N0; B1.FA_v_S0 = CD.FA_v_S0; B1.FA_v_SS = CD.FA_v_SS; B1.vBT_SS = CD.vBT_SS; B1.vBT_NN = CD.vBT_NN;
-  if ((rc = m6_btstep_run(c, BCS, B1))) return rc;
+  M6_TIMED(MOM6CU_STAGE_BTSTEP, m6_btstep_run(c, BCS, B1));
   // :681-691
   const double dt_pred = dt * CS->be;
   VelK VK = {is, ie, js, je, c->grid.mask2dCu, c->grid.mask2dCv, u, v, bcu, bcv, abu, abv, up, vp, dt_pred};
@@ -219,15 +253,14 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   // :738-768 vertvisc_coef, vertvisc, vertvisc_remnant
   VC.dt = dt_pred;
   VS.u = up; VS.v = vp; VS.h = h; VS.dt = dt_pred; VS.taux_bot = taux_bot; VS.tauy_bot = tauy_bot;
-  if ((rc = m6_vertvisc_coef_run(c, VC)) || (rc = m6_vertvisc_run(c, VS)) ||
-      (rc = m6_vertvisc_remnant_run(c, VS.Ray_u, VS.Ray_v, vru, vrv, CS->visc_rem_dt_bug ? dt_pred : dt)))
-    return rc;
+  M6_TIMED(MOM6CU_STAGE_VERTVISC, (rc = m6_vertvisc_coef_run(c, VC)) ? rc : (rc = m6_vertvisc_run(c, VS)) ? rc :
+           m6_vertvisc_remnant_run(c, VS.Ray_u, VS.Ray_v, vru, vrv, CS->visc_rem_dt_bug ? dt_pred : dt));
   if ((rc = halo({vru, vrv, up, vp}, {ST_U, ST_V, ST_U, ST_V}, nz))) return rc;
   // :781 continuity
   ContinuityDev C2 = CD;
   C2.u = up; C2.v = vp; C2.hin = h; C2.h = hp; C2.uh = uh; C2.vh = vh; C2.dt = dt; C2.uhbt = uhbt; C2.vhbt = vhbt; C2.visc_rem_u = vru;
   C2.visc_rem_v = vrv; C2.u_cor = u_av; C2.v_cor = v_av; C2.have_BT_cont = 1;
-  if ((rc = m6_continuity_run(c, C2))) return rc;
+  M6_TIMED(MOM6CU_STAGE_CONTINUITY, m6_continuity_run(c, C2));
   // :785 pass_hp_uv
   if ((rc = halo({hp, u_av, v_av, uh, vh}, {ST_H, ST_U, ST_V, ST_U, ST_V}, nz))) return rc;
   // :800-804
@@ -238,21 +271,21 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   if (CS->begw != 0.0) {
     hmix(1, 2, CS->begw, h, hp, hp);
     PgfDev P2 = {hp, T, Sa, p_surf, PFu, PFv, pbce, eta_PF};
-    if ((rc = m6_pressure_force_run(c, P2))) return rc;
+    M6_TIMED(MOM6CU_STAGE_PRESSURE_FORCE, m6_pressure_force_run(c, P2));
   }
   // :869 btcalc
-  if ((rc = m6_btcalc_run(c, h, CD.h_u, CD.h_v, c->grid.bathyT, CS->hvel_scheme, 0, (double*)BCS.frhatu, (double*)BCS.frhatv))) return rc;
+  M6_TIMED(MOM6CU_STAGE_BTCALC, m6_btcalc_run(c, h, CD.h_u, CD.h_v, c->grid.bathyT, CS->hvel_scheme, 0, (double*)BCS.frhatu, (double*)BCS.frhatv));
   // :886 horizontal_viscosity, :895 CorAdCalc
   HorViscDev HV = {u_av, v_av, h_av, CD.h_u, CD.h_v, diffu, diffv};
-  if ((rc = m6_hor_visc_run(c, HV))) return rc;
+  M6_TIMED(MOM6CU_STAGE_HOR_VISC, m6_hor_visc_run(c, HV));
   CA.CAu = CAu; CA.CAv = CAv;
-  if ((rc = m6_coradcalc_run(c, CA))) return rc;
+  M6_TIMED(MOM6CU_STAGE_CORADCALC, m6_coradcalc_run(c, CA));
   // :901-908
   AK.CAu = CAu; AK.CAv = CAv; AK.predict = 0;
   M6_LAUNCH(c, step_bc_accel_kernel, g3, 128, 0, G, AK);
   // :939 btstep (corrector)
   B1.uh0 = uh; B1.vh0 = vh; B1.u_uh0 = u_av; B1.v_vh0 = v_av; B1.etaav = eta_av;
-  if ((rc = m6_btstep_run(c, BCS, B1))) return rc;
+  M6_TIMED(MOM6CU_STAGE_BTSTEP, m6_btstep_run(c, BCS, B1));
   // :951, :961-975
   M6_LAUNCH(c, step_copy2_kernel, dim3((ie - is + 128) / 128, je - js + 1), 128, 0, G, is, ie, js, je, eta_pred, eta);
   VK.up = u; VK.vp = v; VK.dt = dt;
@@ -260,16 +293,17 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   // :1001-1016
   VC.u = u; VC.v = v; VC.dt = dt;
   VS.u = u; VS.v = v; VS.dt = dt;
-  if ((rc = m6_vertvisc_coef_run(c, VC)) || (rc = m6_vertvisc_run(c, VS)) || (rc = m6_vertvisc_remnant_run(c, VS.Ray_u, VS.Ray_v, vru, vrv, dt)))
-    return rc;
+  M6_TIMED(MOM6CU_STAGE_VERTVISC, (rc = m6_vertvisc_coef_run(c, VC)) ? rc : (rc = m6_vertvisc_run(c, VS)) ? rc :
+           m6_vertvisc_remnant_run(c, VS.Ray_u, VS.Ray_v, vru, vrv, dt));
   // :1021-1023
   hmix(2, 1, 0., h, h, h_av);
   if ((rc = halo({vru, vrv, u, v}, {ST_U, ST_V, ST_U, ST_V}, nz))) return rc;
+  if ((rc = S.early(u)) || (rc = S.early(v))) return rc;  // u_inst, v_inst are final: copy them back under the last continuity call
   // :1043 continuity (in place in h)
   ContinuityDev C3 = {};
   C3.u = u; C3.v = v; C3.hin = h; C3.h = h; C3.uh = uh; C3.vh = vh; C3.dt = dt; C3.uhbt = uhbt; C3.vhbt = vhbt; C3.visc_rem_u = vru;
   C3.visc_rem_v = vrv; C3.u_cor = u_av; C3.v_cor = v_av;
-  if ((rc = m6_continuity_run(c, C3))) return rc;
+  M6_TIMED(MOM6CU_STAGE_CONTINUITY, m6_continuity_run(c, C3));
   // :1047 pass_h, :1054 pass_av_uvh
   if ((rc = halo({h, u_av, v_av, uh, vh}, {ST_H, ST_U, ST_V, ST_U, ST_V}, nz))) return rc;
   // :1060-1062, :1067-1072
@@ -278,9 +312,11 @@ extern "C" int mom6cu_step_dyn_split_rk2(mom6cu_ctx* c, mom6cu_dyn_split_rk2_cs*
   // :1075-1083
   if (CS->store_CAu) {
     CA.CAu = CAu_pred; CA.CAv = CAv_pred;
-    if ((rc = m6_coradcalc_run(c, CA))) return rc;
+    M6_TIMED(MOM6CU_STAGE_CORADCALC, m6_coradcalc_run(c, CA));
     CS->CAu_pred_stored = 1;
   } else CS->CAu_pred_stored = 0;
   M6_CUDA(c, cudaGetLastError());
-  return S.finish();
+  rc = S.finish();
+  ST_.collect();
+  return rc;
 }

@@ -129,6 +129,38 @@ def test_step_bitwise(oracle, ctx_factory, kw):
 
 
 @pytest.mark.gpu
+def test_step_bitwise_with_page_locked_host_arrays(oracle, ctx_factory):
+    """Page-locked caller arrays take the overlapped staging path (u, v, visc%, forces% uploaded under PressureForce, u and v
+    copied back under the last continuity call): same bits as the oracle, over repeated calls."""
+    import torch
+
+    def pin(x):
+        if isinstance(x, np.ndarray) and x.dtype == np.float64:
+            t = torch.empty(x.shape, dtype=torch.float64, pin_memory=True)
+            y = t.numpy(); y[...] = x
+            keep.append(t)
+            return y
+        return x
+
+    keep = []
+    dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(44, 40, 8, land_blocks=3, store_CAu=1)
+    rcs, ra = _copy(cs), _copy(a)
+    gcs = _copy(cs)
+    ga = {k: pin(v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+    ctx = ctx_factory(dom)
+    ctx.set_grid(grid); ctx.set_vgrid(gv)
+    ctx.set_cs_continuity(css["continuity"]); ctx.set_cs_coriolisadv(css["coriolisadv"]); ctx.set_cs_hor_visc(css["hor_visc"])
+    ctx.set_cs_pressureforce(css["pressureforce"]); ctx.set_cs_vertvisc(css["vertvisc"])
+    for step in range(12):
+        oracle.step_dyn_split_rk2(dom, grid, gv, css, rcs, ra)
+        ctx.step_dyn_split_rk2(gcs, ga)
+        for k in STATE:
+            assert np.array_equal(_inner(dom, ra[k]).view(np.int64), _inner(dom, ga[k]).view(np.int64)), (step, k)
+        for k in CSARR:
+            assert np.array_equal(_inner(dom, rcs[k]).view(np.int64), _inner(dom, gcs[k]).view(np.int64)), (step, "CS%" + k)
+
+
+@pytest.mark.gpu
 def test_step_with_resident_control_structure(oracle, ctx_factory):
     """The intended use: the MOM_dyn_split_RK2_CS arrays stay on the device between steps."""
     dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(36, 28, 5, land_blocks=2)
