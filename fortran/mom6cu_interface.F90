@@ -41,6 +41,31 @@ module mom6cu_interface
     integer(c_int) :: Boussinesq
   end type mom6cu_vgrid
 
+  !> EFP_type (src/framework/MOM_coms.F90:76-78): the same six 64-bit integers, so an EFP_type argument can be passed as is
+  type, bind(C) :: mom6cu_efp
+    integer(c_int64_t) :: v(6)
+  end type mom6cu_efp
+
+  !> Sum_output_CS members write_energy uses (src/diagnostics/MOM_sum_output.F90:66-140)
+  type, bind(C) :: mom6cu_sum_output_cs
+    integer(c_int) :: do_APE_calc, use_temperature
+    real(c_double) :: dt_in_T
+    integer(c_int) :: DL_listsize
+    type(c_ptr)    :: DL_depth, DL_area, DL_vol_below, lH, g_prime
+    real(c_double) :: Z_ref, C_p
+    real(c_double) :: RZL2_to_kg, L_T_to_m_s, Q_to_J_kg, J_kg_to_Q, kg_m3_to_R, m_to_Z, m_to_L, Z_to_m, S_to_ppt, C_to_degC
+    integer(c_int) :: previous_calls, ntrunc
+    type(mom6cu_efp) :: fresh_water_in_EFP, net_salt_in_EFP, net_heat_in_EFP, mass_prev_EFP, salt_prev_EFP, heat_prev_EFP
+  end type mom6cu_sum_output_cs
+
+  !> The quantities write_energy puts on the ocean.stats line and in the energy file
+  type, bind(C) :: mom6cu_energy_out
+    real(c_double) :: En_mass, toten, KE_tot, PE_tot, mass_tot, mass_chg, mass_anom, max_CFL(2)
+    real(c_double) :: Salt, Salt_chg, Salt_anom, Heat, Heat_chg, Heat_anom, salin, salin_anom, temp, temp_anom
+    integer(c_int) :: ntrunc
+    type(c_ptr)    :: KE, mass_lay, PE, Z_0APE
+  end type mom6cu_energy_out
+
   !> continuity_PPM_CS (src/core/MOM_continuity_PPM.F90:35-67)
   type, bind(C) :: mom6cu_continuity_cs
     integer(c_int) :: upwind_1st, monotonic, simple_2nd, aggress_adjust, vol_CFL, better_iter, &
@@ -296,6 +321,33 @@ module mom6cu_interface
         bind(C, name="mom6cu_ale_remap_velocities")
       import ; type(c_ptr), value :: ctx, h_old_u, h_old_v, h_new_u, h_new_v, u, v ; type(mom6cu_remapping_cs), intent(in) :: CS
     end function mom6cu_ale_remap_velocities
+    !> reproducing_sum (src/framework/MOM_coms.F90:227, :337); absent optionals are c_null_ptr, isr..jer = 0 when absent
+    integer(c_int) function mom6cu_reproducing_sum(ctx, array, stagger, nk, isr, ier, jsr, jer, unscale, only_on_PE, &
+                                                   total, sums, EFP_sum, EFP_lay_sums) bind(C, name="mom6cu_reproducing_sum")
+      import ; type(c_ptr), value :: ctx, array, sums, EFP_sum, EFP_lay_sums
+      integer(c_int), value :: stagger, nk, isr, ier, jsr, jer, only_on_PE
+      real(c_double), value :: unscale ; real(c_double), intent(out) :: total
+    end function mom6cu_reproducing_sum
+    integer(c_int) function mom6cu_efp_sum_across_pes(ctx, EFPs, nval) bind(C, name="mom6cu_efp_sum_across_pes")
+      import ; type(c_ptr), value :: ctx ; type(mom6cu_efp), intent(inout) :: EFPs(*) ; integer(c_int), value :: nval
+    end function mom6cu_efp_sum_across_pes
+    !> hchksum / uvchksum / Bchksum (src/framework/MOM_checksums.F90)
+    integer(c_int) function mom6cu_chksum(ctx, array, stagger, nk, haloshift, symmetric, omit_corners, scale, bc, kind, stats) &
+        bind(C, name="mom6cu_chksum")
+      import ; type(c_ptr), value :: ctx, array, stats
+      integer(c_int), value :: stagger, nk, haloshift, symmetric, omit_corners ; real(c_double), value :: scale
+      integer(c_int), intent(out) :: bc(5), kind
+    end function mom6cu_chksum
+    !> write_energy (src/diagnostics/MOM_sum_output.F90:321)
+    integer(c_int) function mom6cu_write_energy(ctx, CS, u, v, h, T, S, res) bind(C, name="mom6cu_write_energy")
+      import ; type(c_ptr), value :: ctx, u, v, h, T, S
+      type(mom6cu_sum_output_cs), intent(inout) :: CS ; type(mom6cu_energy_out), intent(inout) :: res
+    end function mom6cu_write_energy
+    integer(c_int) function mom6cu_ocean_stats_line(CS, res, n, reday, buf, len) bind(C, name="mom6cu_ocean_stats_line")
+      import ; type(mom6cu_sum_output_cs), intent(in) :: CS ; type(mom6cu_energy_out), intent(in) :: res
+      integer(c_int), value :: n ; real(c_double), value :: reday
+      character(kind=c_char), intent(out) :: buf(*) ; integer(c_size_t), value :: len
+    end function mom6cu_ocean_stats_line
     type(c_ptr) function mom6cu_plane_alloc(ctx, name, nk) bind(C, name="mom6cu_plane_alloc")
       import ; type(c_ptr), value :: ctx ; character(kind=c_char), intent(in) :: name(*) ; integer(c_int), value :: nk
     end function mom6cu_plane_alloc

@@ -599,6 +599,74 @@ int mom6cu_step_dyn_split_rk2(mom6cu_ctx* ctx, mom6cu_dyn_split_rk2_cs* CS, cons
 int mom6cu_remap_dyn_split_rk2_aux_vars(mom6cu_ctx* ctx, const mom6cu_remapping_cs* remapCS, const mom6cu_dyn_split_rk2_cs* CS,
                                         const double* h_old_u, const double* h_old_v, const double* h_new_u, const double* h_new_v);
 
+/* ------------------------------------ reproducing sums, checksums, write_energy (the parity metric) */
+/* EFP_type, src/framework/MOM_coms.F90:76-78: ni = 6 integers of 46 bits each (prec = 2**46, :30-40). */
+typedef struct mom6cu_efp { int64_t v[6]; } mom6cu_efp;
+/* EFP_plus :775, EFP_minus :786, EFP_to_real :813 (regularises a in place, as the reference does), real_to_EFP :836,
+ * EFP_real_diff :822.  Host arithmetic on 6 integers: no device work. */
+void mom6cu_efp_plus(const mom6cu_efp* a, const mom6cu_efp* b, mom6cu_efp* out, int* overflow);
+void mom6cu_efp_minus(const mom6cu_efp* a, const mom6cu_efp* b, mom6cu_efp* out, int* overflow);
+double mom6cu_efp_to_real(mom6cu_efp* a);
+int mom6cu_real_to_efp(double val, mom6cu_efp* out); /* returns 1 on overflow, 2 on NaN (the reference's FATALs) */
+double mom6cu_efp_real_diff(const mom6cu_efp* a, const mom6cu_efp* b);
+/* reproducing_sum(array, isr, ier, jsr, jer, sums, EFP_sum, EFP_lay_sums, err, only_on_PE, unscale)
+ *   reproducing_sum_2d :227-325 (nk = 1), reproducing_sum_3d :337-545, reproducing_EFP_sum_2d :101-222.
+ * array: a field of the given stagger (nk levels) on G's memory domain, host array or resident plane.  isr..jer are the
+ * reference's 1-based positions inside the array (0 = absent: the whole array).  sums / EFP_lay_sums (nk entries) and EFP_sum
+ * may be NULL; with sums or EFP_lay_sums the result is the k-ordered floating sum of the layer sums (:470-476), otherwise the
+ * conversion of the one extended-fixed-point total (:528-529).  unscale = 1 means absent.  The order-invariant integer sums
+ * are accumulated on the device (conversion :640-648 per element, integer atomics), summed across ranks with NCCL
+ * (sum_across_PEs) unless only_on_PE, and regularised on the host (:717-754).  NaN or overflow: FATAL as in the reference. */
+int mom6cu_reproducing_sum(mom6cu_ctx* ctx, const double* array, int stagger, int nk, int isr, int ier, int jsr, int jer,
+                           double unscale, int only_on_PE, double* sum, double* sums, mom6cu_efp* EFP_sum, mom6cu_efp* EFP_lay_sums);
+/* EFP_sum_across_PEs(EFPs, nval) :870-916: in place, overflows carried. */
+int mom6cu_efp_sum_across_pes(mom6cu_ctx* ctx, mom6cu_efp* EFPs, int nval);
+
+/* hchksum / uvchksum / Bchksum, src/framework/MOM_checksums.F90: chksum_h_2d :387, chksum_h_3d :1413, chksum_u_2d :1005,
+ * chksum_u_3d :1782, chksum_v_2d :1209, chksum_v_3d :1986, chksum_B_2d :688, chksum_B_3d :1586; bitcount :2678.
+ * stagger 0=h,1=u,2=v,3=q; nk = 1 for the 2-D forms.  haloshift < 0 means the full halo (:470); symmetric / omit_corners as
+ * the optional arguments (0 = absent); scale = 1 means absent.
+ *   bc[0] = bc0; then, in the order the reference prints them:
+ *     kind 1 (haloshift 0, not symmetric): nothing else           (chk_sum_msg1)
+ *     kind 2 (corners):  bc[1..4] = SW, SE, NW, NE                 (chk_sum_msg5)
+ *     kind 3 (NSEW):     bc[1..4] = N, S, E, W                     (chk_sum_msg_NSEW)
+ *     kind 4 (u symmetric, haloshift 0): bc[1] = W                 (chk_sum_msg_W)
+ *     kind 5 (v symmetric, haloshift 0): bc[1] = S                 (chk_sum_msg_S)
+ *     kind 6 (q symmetric, haloshift 0): bc[1] = SW                (chk_sum_msg2)
+ *   *kind receives the case; stats (NULL = calculateStatistics off) receives mean, min, max (subStats). */
+int mom6cu_chksum(mom6cu_ctx* ctx, const double* array, int stagger, int nk, int haloshift, int symmetric, int omit_corners,
+                  double scale, int* bc, int* kind, double* stats);
+
+/* write_energy, src/diagnostics/MOM_sum_output.F90:321-1020 (Boussinesq; the quantities of one ocean.stats line and of
+ * the energy file).  Sum_output_CS members :66-140 as resolved by MOM_sum_output_init :147 and depth_list_setup :1161. */
+typedef struct mom6cu_sum_output_cs {
+  int do_APE_calc, use_temperature;
+  double dt_in_T;                       /* CS%dt_in_T */
+  int DL_listsize;                      /* CS%DL%listsize */
+  const double *DL_depth, *DL_area, *DL_vol_below; /* CS%DL (host, listsize entries) */
+  int* lH;                              /* CS%lH(nk), host, in/out (1-based list positions) */
+  const double* g_prime;                /* GV%g_prime(nk+1), host */
+  double Z_ref, C_p;                    /* G%Z_ref, tv%C_p */
+  /* unit_scale_type factors write_energy uses (all 1 in an unscaled run) */
+  double RZL2_to_kg, L_T_to_m_s, Q_to_J_kg, J_kg_to_Q, kg_m3_to_R, m_to_Z, m_to_L, Z_to_m, S_to_ppt, C_to_degC;
+  int previous_calls, ntrunc;           /* in/out */
+  mom6cu_efp fresh_water_in_EFP, net_salt_in_EFP, net_heat_in_EFP, mass_prev_EFP, salt_prev_EFP, heat_prev_EFP; /* in/out */
+} mom6cu_sum_output_cs;
+typedef struct mom6cu_energy_out {
+  double En_mass, toten, KE_tot, PE_tot, mass_tot, mass_chg, mass_anom, max_CFL[2];
+  double Salt, Salt_chg, Salt_anom, Heat, Heat_chg, Heat_anom, salin, salin_anom, temp, temp_anom;
+  int ntrunc;
+  double *KE, *mass_lay;      /* nk, host, may be NULL */
+  double *PE, *Z_0APE;        /* nk+1, host, may be NULL */
+} mom6cu_energy_out;
+/* u, v, h (3-D), T, S (tv%T, tv%S; NULL unless use_temperature): host arrays or resident planes.  Two passes over the
+ * state on the device (mass / KE / heat / salt / CFL, then -- with do_APE_calc -- the interface APE, which needs the
+ * layer volumes of the first pass); what returns to the host is 6 integers per sum. */
+int mom6cu_write_energy(mom6cu_ctx* ctx, mom6cu_sum_output_cs* CS, const double* u, const double* v, const double* h,
+                        const double* T, const double* S, mom6cu_energy_out* out);
+/* The line write_energy appends to ocean.stats (:874-902; day-stamped form), NUL terminated, without the newline. */
+int mom6cu_ocean_stats_line(const mom6cu_sum_output_cs* CS, const mom6cu_energy_out* e, int n, double reday, char* buf, size_t len);
+
 #ifdef __cplusplus
 }
 #endif

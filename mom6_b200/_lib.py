@@ -248,6 +248,34 @@ class AdvectTracerArgs(C.Structure):
                 ("uhr_out", C.c_void_p), ("vhr_out", C.c_void_p)]
 
 
+class Efp(C.Structure):
+    """mom6cu_efp: EFP_type (src/framework/MOM_coms.F90:76-78)."""
+    _fields_ = [("v", C.c_int64 * 6)]
+
+
+_SO_UNITS = ("RZL2_to_kg", "L_T_to_m_s", "Q_to_J_kg", "J_kg_to_Q", "kg_m3_to_R", "m_to_Z", "m_to_L", "Z_to_m", "S_to_ppt", "C_to_degC")
+_SO_EFPS = ("fresh_water_in_EFP", "net_salt_in_EFP", "net_heat_in_EFP", "mass_prev_EFP", "salt_prev_EFP", "heat_prev_EFP")
+
+
+class SumOutputCS(C.Structure):
+    """mom6cu_sum_output_cs: Sum_output_CS (src/diagnostics/MOM_sum_output.F90:66-140) as write_energy uses it."""
+    _fields_ = ([("do_APE_calc", C.c_int), ("use_temperature", C.c_int), ("dt_in_T", C.c_double), ("DL_listsize", C.c_int),
+                 ("DL_depth", C.c_void_p), ("DL_area", C.c_void_p), ("DL_vol_below", C.c_void_p), ("lH", C.c_void_p),
+                 ("g_prime", C.c_void_p), ("Z_ref", C.c_double), ("C_p", C.c_double)] +
+                [(n, C.c_double) for n in _SO_UNITS] + [("previous_calls", C.c_int), ("ntrunc", C.c_int)] +
+                [(n, Efp) for n in _SO_EFPS])
+
+
+_EO_SCALARS = ("En_mass", "toten", "KE_tot", "PE_tot", "mass_tot", "mass_chg", "mass_anom")
+_EO_SCALARS2 = ("Salt", "Salt_chg", "Salt_anom", "Heat", "Heat_chg", "Heat_anom", "salin", "salin_anom", "temp", "temp_anom")
+
+
+class EnergyOut(C.Structure):
+    """mom6cu_energy_out: what write_energy puts on the ocean.stats line and in the energy file."""
+    _fields_ = ([(n, C.c_double) for n in _EO_SCALARS] + [("max_CFL", C.c_double * 2)] + [(n, C.c_double) for n in _EO_SCALARS2] +
+                [("ntrunc", C.c_int)] + [(n, C.c_void_p) for n in ("KE", "mass_lay", "PE", "Z_0APE")])
+
+
 def fill_struct(struct, values, keep):
     """Fill a ctypes struct from a dict: numpy arrays / torch tensors -> pointers, scalars as is."""
     for name, ctype in struct._fields_:
@@ -329,6 +357,22 @@ def bind(lib):
     lib.mom6cu_vertvisc_remnant.argtypes = [vp, vp, vp, vp, vp, C.c_double]
     lib.mom6cu_ale_regrid.argtypes = [vp, C.POINTER(RegriddingCS), vp, vp, vp]
     lib.mom6cu_advect_tracer.argtypes = [vp, C.POINTER(TracerAdvectCS), C.POINTER(AdvectTracerArgs)]
+    lib.mom6cu_efp_plus.argtypes = [C.POINTER(Efp), C.POINTER(Efp), C.POINTER(Efp), C.POINTER(C.c_int)]
+    lib.mom6cu_efp_plus.restype = None
+    lib.mom6cu_efp_minus.argtypes = lib.mom6cu_efp_plus.argtypes
+    lib.mom6cu_efp_minus.restype = None
+    lib.mom6cu_efp_to_real.argtypes = [C.POINTER(Efp)]
+    lib.mom6cu_efp_to_real.restype = C.c_double
+    lib.mom6cu_real_to_efp.argtypes = [C.c_double, C.POINTER(Efp)]
+    lib.mom6cu_efp_real_diff.argtypes = [C.POINTER(Efp), C.POINTER(Efp)]
+    lib.mom6cu_efp_real_diff.restype = C.c_double
+    lib.mom6cu_reproducing_sum.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                           C.POINTER(C.c_double), vp, C.POINTER(Efp), C.POINTER(Efp)]
+    lib.mom6cu_efp_sum_across_pes.argtypes = [vp, C.POINTER(Efp), C.c_int]
+    lib.mom6cu_chksum.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    lib.mom6cu_write_energy.argtypes = [vp, C.POINTER(SumOutputCS), vp, vp, vp, vp, vp, C.POINTER(EnergyOut)]
+    lib.mom6cu_ocean_stats_line.argtypes = [C.POINTER(SumOutputCS), C.POINTER(EnergyOut), C.c_int, C.c_double, C.c_char_p, C.c_size_t]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

@@ -283,6 +283,54 @@ def _ctx_methods():
         return self._check(self.lib.mom6cu_remap_dyn_split_rk2_aux_vars(self._h, C.byref(marshal.remapping_cs(remap_cs)), C.byref(st), _p(h_old_u),
                                                                        _p(h_old_v), _p(h_new_u), _p(h_new_v)))
 
+    # ---- the parity metric: reproducing sums, checksums, write_energy (csrc/diag.cu)
+    def reproducing_sum(self, array, stagger=0, nk=None, isr=0, ier=0, jsr=0, jer=0, unscale=1.0, only_on_PE=False,
+                        want_sums=False, want_efp=False, want_lay_efp=False):
+        """reproducing_sum, src/framework/MOM_coms.F90:227 (2-D) / :337 (3-D).  array: (nk, nj, ni) / (nj, ni) host array or a Plane."""
+        from ._lib import Efp
+        if nk is None:
+            nk = array.nk if isinstance(array, Plane) else (1 if array.ndim == 2 else array.shape[0])
+        total = C.c_double(0.0)
+        sums = np.zeros(nk) if want_sums else None
+        e = Efp() if want_efp else None
+        le = (Efp * nk)() if want_lay_efp else None
+        self._check(self.lib.mom6cu_reproducing_sum(self._h, _p(array), stagger, nk, isr, ier, jsr, jer, float(unscale), int(only_on_PE),
+                                                    C.byref(total), _p(sums), C.byref(e) if e is not None else None, le))
+        r = {"sum": total.value}
+        if want_sums:
+            r["sums"] = sums
+        if want_efp:
+            r["EFP_sum"] = marshal.efp_back(e)
+        if want_lay_efp:
+            r["EFP_lay_sums"] = np.array([marshal.efp_back(le[k]) for k in range(nk)])
+        return r
+
+    def chksum(self, array, stagger=0, nk=None, haloshift=0, symmetric=False, omit_corners=False, scale=1.0, stats=False):
+        """hchksum / uvchksum / Bchksum, src/framework/MOM_checksums.F90; returns (bc[5], kind, (mean, min, max) or None)."""
+        if nk is None:
+            nk = array.nk if isinstance(array, Plane) else (1 if array.ndim == 2 else array.shape[0])
+        bc = (C.c_int * 5)()
+        kind = C.c_int(0)
+        st = (C.c_double * 3)()
+        self._check(self.lib.mom6cu_chksum(self._h, _p(array), stagger, nk, haloshift, int(symmetric), int(omit_corners), float(scale), bc,
+                                           C.byref(kind), st if stats else None))
+        return np.array(list(bc), dtype=np.int64), kind.value, (np.array(list(st)) if stats else None)
+
+    def write_energy(self, cs, u, v, h, T=None, S=None):
+        """write_energy, src/diagnostics/MOM_sum_output.F90:321; cs (dict) is updated like the reference's Sum_output_CS."""
+        keep = []
+        st = marshal.sum_output_cs(cs, keep)
+        out, arrs = marshal.energy_out(self.dom.nk, keep)
+        self._check(self.lib.mom6cu_write_energy(self._h, C.byref(st), _p(u), _p(v), _p(h), _p(T), _p(S), C.byref(out)))
+        marshal.sum_output_cs_back(st, cs)
+        return marshal.energy_out_back(out, arrs)
+
+    def ocean_stats_line(self, cs, e, n, reday):
+        """The line write_energy appends to ocean.stats (MOM_sum_output.F90:874-902)."""
+        return ocean_stats_line(self.lib, cs, e, n, reday)
+
+    for f in (reproducing_sum, chksum, write_energy, ocean_stats_line):
+        setattr(Context, f.__name__, f)
     setattr(Context, "remap_dyn_split_rk2_aux_vars", remap_dyn_split_rk2_aux_vars)
     setattr(Context, "set_dtbt", set_dtbt)
     setattr(Context, "step_dyn_split_rk2", step_dyn_split_rk2)
@@ -312,3 +360,44 @@ def make_domain(ni, nj, nk=1, halo=4, whalo=None, cyclic_x=True, cyclic_y=False,
     d.cyclic_x, d.cyclic_y, d.first_direction = int(cyclic_x), int(cyclic_y), first_direction
     d.npi, d.npj, d.pi, d.pj = npi, npj, pi, pj
     return d
+
+
+def ocean_stats_line(lib, cs, e, n, reday):
+    """mom6cu_ocean_stats_line on a write_energy result (host formatting only: needs no device)."""
+    from . import marshal
+    from ._lib import EnergyOut, _EO_SCALARS, _EO_SCALARS2
+    keep = []
+    st = marshal.sum_output_cs(cs, keep)
+    out = EnergyOut()
+    for k in _EO_SCALARS + _EO_SCALARS2:
+        setattr(out, k, float(e[k]))
+    out.max_CFL[0], out.max_CFL[1] = float(e["max_CFL"][0]), float(e["max_CFL"][1])
+    out.ntrunc = int(e["ntrunc"])
+    z = np.ascontiguousarray(e["Z_0APE"], dtype=np.float64)
+    out.Z_0APE = z.ctypes.data
+    buf = C.create_string_buffer(512)
+    rc = lib.mom6cu_ocean_stats_line(C.byref(st), C.byref(out), int(n), float(reday), buf, 512)
+    if rc != 0:
+        raise Mom6cuError(f"mom6cu_ocean_stats_line rc={rc}")
+    return buf.value.decode()
+
+
+def efp_op(lib, op, a, b=None):
+    """EFP_plus / EFP_minus / EFP_to_real / real_to_EFP / EFP_real_diff (MOM_coms.F90:737-815) through the C ABI; host-only."""
+    from . import marshal
+    from ._lib import Efp
+    if op == "from_real":
+        out = Efp()
+        rc = lib.mom6cu_real_to_efp(float(a), C.byref(out))
+        if rc:
+            raise OverflowError("Overflow in real_to_EFP conversion")
+        return marshal.efp_back(out)
+    ea = marshal.efp(a)
+    if op == "to_real":
+        return float(lib.mom6cu_efp_to_real(C.byref(ea)))
+    eb = marshal.efp(b)
+    if op == "diff":
+        return float(lib.mom6cu_efp_real_diff(C.byref(ea), C.byref(eb)))
+    out, ov = Efp(), C.c_int(0)
+    getattr(lib, "mom6cu_efp_" + op)(C.byref(ea), C.byref(eb), C.byref(out), C.byref(ov))
+    return marshal.efp_back(out)

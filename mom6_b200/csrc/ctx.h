@@ -91,6 +91,9 @@ int m6_halo_update(mom6cu_ctx* c, double* const* fields, const int* staggers, in
 // max over ranks of one host int (sum_across_PEs of a flag, MOM_coms.F90); identity on one rank
 int m6_allreduce_max_int(mom6cu_ctx* c, int* v);
 int m6_allreduce_min_double(mom6cu_ctx* c, double* v);  // min_across_PEs
+int m6_allreduce_sum_i64(mom6cu_ctx* c, long long* v, int n);      // sum_across_PEs of the EFP integers
+int m6_allreduce_max_doubles(mom6cu_ctx* c, double* v, int n);   // max_across_PEs
+int m6_allreduce_min_doubles(mom6cu_ctx* c, double* v, int n);
 // copy a Fortran-shaped (host or device) array into / out of unified planes
 int m6_up(mom6cu_ctx* c, const double* src, int stagger, int wide, int nk, double* dst);
 int m6_down(mom6cu_ctx* c, const double* src_plane, int stagger, int wide, int nk, double* dst);

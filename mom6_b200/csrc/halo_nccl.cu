@@ -131,6 +131,27 @@ int m6_allreduce_min_double(mom6cu_ctx* c, double* v) {
   return 0;
 }
 
+// sum_across_PEs of n 64-bit integers (the extended-fixed-point sums, MOM_coms.F90:214) / max_across_PEs of n reals; in place
+// on host values, identity on one rank.
+static int m6_allreduce_host(mom6cu_ctx* c, void* v, int n, ncclDataType_t type, ncclRedOp_t op) {
+  if (c->nranks <= 1 || n <= 0) return 0;
+  if (!c->comm) return c->fail(MOM6CU_ERR_NCCL, "multi-rank reduction requested but no communicator is attached");
+  double* d = c->buf("comm.vec", (size_t)n);
+  double* h = c->host_scratch("comm.vec", (size_t)n);
+  if (!d || !h) return MOM6CU_ERR_CUDA;
+  memcpy(h, v, (size_t)n * 8);
+  M6_CUDA(c, cudaMemcpyAsync(d, h, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  ncclResult_t r = ncclAllReduce(d, d, n, type, op, (ncclComm_t)c->comm, c->stream);
+  if (r != ncclSuccess) return c->fail(MOM6CU_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r));
+  M6_CUDA(c, cudaMemcpyAsync(h, d, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(v, h, (size_t)n * 8);
+  return 0;
+}
+int m6_allreduce_sum_i64(mom6cu_ctx* c, long long* v, int n) { return m6_allreduce_host(c, v, n, ncclInt64, ncclSum); }
+int m6_allreduce_max_doubles(mom6cu_ctx* c, double* v, int n) { return m6_allreduce_host(c, v, n, ncclDouble, ncclMax); }
+int m6_allreduce_min_doubles(mom6cu_ctx* c, double* v, int n) { return m6_allreduce_host(c, v, n, ncclDouble, ncclMin); }
+
 extern "C" int mom6cu_comm_destroy(mom6cu_ctx* c) {
   if (c && c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
   return 0;

@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
 
 
 def _scalars(struct, d):
@@ -168,3 +168,65 @@ def set_dtbt_args(a, keep):
         keep.append(bs)
         st.BT_cont = C.pointer(bs)
     return st
+
+
+def efp(v=None):
+    """numpy int64[6] (or None = zero) -> mom6cu_efp"""
+    e = Efp()
+    if v is not None:
+        for n in range(6):
+            e.v[n] = int(v[n])
+    return e
+
+
+def efp_back(e):
+    return np.array([int(e.v[n]) for n in range(6)], dtype=np.int64)
+
+
+def sum_output_cs(d, keep):
+    """Sum_output_CS as write_energy uses it.  Arrays: DL_depth / DL_area / DL_vol_below / g_prime float64, lH int32 (updated in
+    place); the six EFP members are int64[6] arrays (absent = zero)."""
+    st = SumOutputCS()
+    st.do_APE_calc, st.use_temperature = int(d["do_APE_calc"]), int(d["use_temperature"])
+    st.dt_in_T = float(d["dt_in_T"])
+    st.Z_ref, st.C_p = float(d.get("Z_ref", 0.0)), float(d.get("C_p", 3991.86795711963))
+    for n in _SO_UNITS:
+        setattr(st, n, float(d.get(n, 1.0)))
+    st.previous_calls, st.ntrunc = int(d.get("previous_calls", 0)), int(d.get("ntrunc", 0))
+    st.DL_listsize = int(d.get("DL_listsize", 0))
+    for n in ("DL_depth", "DL_area", "DL_vol_below", "g_prime"):
+        a = d.get(n)
+        if a is not None:
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+            keep.append(a)
+            setattr(st, n, a.ctypes.data)
+    if d.get("lH") is not None:
+        assert d["lH"].dtype == np.int32
+        keep.append(d["lH"])
+        st.lH = d["lH"].ctypes.data
+    for n in _SO_EFPS:
+        setattr(st, n, efp(d.get(n)))
+    return st
+
+
+def sum_output_cs_back(st, d):
+    d["previous_calls"], d["ntrunc"] = int(st.previous_calls), int(st.ntrunc)
+    for n in _SO_EFPS:
+        d[n] = efp_back(getattr(st, n))
+
+
+def energy_out(nk, keep):
+    st = EnergyOut()
+    arrs = {"KE": np.zeros(nk), "mass_lay": np.zeros(nk), "PE": np.zeros(nk + 1), "Z_0APE": np.zeros(nk + 1)}
+    for n, a in arrs.items():
+        keep.append(a)
+        setattr(st, n, a.ctypes.data)
+    return st, arrs
+
+
+def energy_out_back(st, arrs):
+    r = {n: float(getattr(st, n)) for n in _EO_SCALARS + _EO_SCALARS2}
+    r["max_CFL"] = np.array([st.max_CFL[0], st.max_CFL[1]])
+    r["ntrunc"] = int(st.ntrunc)
+    r.update(arrs)
+    return r

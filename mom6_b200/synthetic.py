@@ -988,3 +988,17 @@ def split_step_tile(dom_g, grid, cs, a, npi, npj, pi, pj, hor_visc_cs_g=None):
             else:
                 hv[k] = v
     return dom, g, c, t, hv
+
+
+def sum_output_cs(dom, depth_list, dt=900.0, do_APE_calc=True, use_temperature=True, Z_ref=0.0, **units):
+    """Sum_output_CS as MOM_sum_output_init :147 and depth_list_setup :1161 leave it (src/diagnostics/MOM_sum_output.F90).
+    depth_list = (depth, area, vol_below) from create_depth_list :1203 (host code of the reference; the tests take it from the
+    oracle's restatement)."""
+    nk = dom.nk
+    depth, area, vol = (np.ascontiguousarray(x, dtype=np.float64) for x in depth_list)
+    g_prime = np.ascontiguousarray(np.concatenate(([9.8], 9.8 * (0.5 + 0.02 * np.arange(1, nk + 1)) / 1035.0)))  # GV%g_prime(1:nk+1)
+    cs = dict(do_APE_calc=int(do_APE_calc), use_temperature=int(use_temperature), dt_in_T=dt, DL_listsize=len(depth), DL_depth=depth,
+              DL_area=area, DL_vol_below=vol, lH=np.full(nk, len(depth) - 1, dtype=np.int32), g_prime=g_prime, Z_ref=Z_ref,
+              C_p=3991.86795711963, previous_calls=0, ntrunc=0)
+    cs.update(units)
+    return cs

@@ -104,6 +104,25 @@ int oracle_step_dyn_split_rk2(const mom6cu_domain* dom, const mom6cu_grid* G, co
                               const mom6cu_pressureforce_cs* pgf_cs, const mom6cu_vertvisc_cs* vv_cs, mom6cu_dyn_split_rk2_cs* CS,
                               const mom6cu_step_dyn_args* a, int nthreads);
 
+/* Extended-fixed-point sums, bit-count checksums (efp.cpp) and write_energy (sum_output.cpp): the reference's
+ * answer-reproducibility metric.  The sums are PINNED by the reference's unit test test_reproducing_sum.F90
+ * (tests/test_oracle_efp.py). */
+int oracle_reproducing_sum(const mom6cu_domain* dom, const double* array, int stagger, int nk, int isr, int ier, int jsr, int jer,
+                           double unscale, int reproducing, int overflow_check, double* sum, double* sums, mom6cu_efp* EFP_sum,
+                           mom6cu_efp* EFP_lay_sums);
+void oracle_efp_plus(const mom6cu_efp* a, const mom6cu_efp* b, mom6cu_efp* out, int* overflow);
+void oracle_efp_minus(const mom6cu_efp* a, const mom6cu_efp* b, mom6cu_efp* out, int* overflow);
+double oracle_efp_to_real(mom6cu_efp* a);
+int oracle_real_to_efp(double v, mom6cu_efp* out);
+double oracle_efp_real_diff(const mom6cu_efp* a, const mom6cu_efp* b);
+int oracle_chksum(const mom6cu_domain* d, const double* array, int stagger, int nk, int haloshift, int symmetric, int omit_corners,
+                  double scale, int* bc, int* kind, double* stats);
+int oracle_create_depth_list(const mom6cu_domain* dom, const mom6cu_grid* G, double Z_ref, double min_depth_inc, int* listsize,
+                             double* depth, double* area, double* vol_below);
+int oracle_write_energy(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, mom6cu_sum_output_cs* CS,
+                        const double* u, const double* v, const double* h, const double* T, const double* S, mom6cu_energy_out* out);
+int oracle_ocean_stats_line(const mom6cu_sum_output_cs* CS, const mom6cu_energy_out* e, int n, double reday, char* buf, size_t len);
+
 #ifdef __cplusplus
 }
 #endif

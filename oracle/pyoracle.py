@@ -146,7 +146,7 @@ def pressure_force(dom, grid, gv, cs, args, nthreads=1):
 
 # ---- ALE remapping (oracle/remap.cpp)
 def _dp(a):
-    return a.ctypes.data_as(C.c_void_p)
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
 def remapping_core_h(cs, h0, u0, h1):
@@ -339,3 +339,129 @@ def remap_dyn_split_rk2_aux_vars(dom, grid, remap_cs, cs, h_old_u, h_old_v, h_ne
     lib.oracle_remap_dyn_split_rk2_aux_vars.argtypes = [C.c_void_p] * 8 + [C.c_int]
     return lib.oracle_remap_dyn_split_rk2_aux_vars(C.byref(dom), C.byref(g), C.byref(r), C.byref(st), _dp(h_old_u), _dp(h_old_v), _dp(h_new_u),
                                                    _dp(h_new_v), nthreads)
+
+
+# ---- reproducing sums, checksums, write_energy (efp.cpp, sum_output.cpp)
+def reproducing_sum(dom, array, stagger=0, isr=0, ier=0, jsr=0, jer=0, unscale=1.0, reproducing=True, overflow_check=True,
+                    want_sums=False, want_efp=False, want_lay_efp=False):
+    """oracle_reproducing_sum: reproducing_sum_2d / _3d (MOM_coms.F90:227, :337).  array is (nk, nj, ni) or (nj, ni).
+    Returns a dict: sum, and sums / EFP_sum / EFP_lay_sums (int64 arrays) when requested."""
+    import numpy as np
+    from mom6_b200 import marshal
+    from mom6_b200._lib import Efp
+    lib = load()
+    nk = 1 if array.ndim == 2 else array.shape[0]
+    total = C.c_double(0.0)
+    sums = np.zeros(nk) if want_sums else None
+    e = Efp() if want_efp else None
+    le = (Efp * nk)() if want_lay_efp else None
+    lib.oracle_reproducing_sum.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                                                    C.c_void_p, C.c_void_p]
+    rc = lib.oracle_reproducing_sum(C.byref(dom), _dp(array), stagger, nk, isr, ier, jsr, jer, float(unscale), int(reproducing),
+                                    int(overflow_check), C.byref(total), _dp(sums), C.byref(e) if e is not None else None,
+                                    C.cast(le, C.c_void_p) if le is not None else None)
+    if rc != 0:
+        raise RuntimeError(f"oracle_reproducing_sum: FATAL {rc}")
+    r = {"sum": total.value}
+    if want_sums:
+        r["sums"] = sums
+    if want_efp:
+        r["EFP_sum"] = marshal.efp_back(e)
+    if want_lay_efp:
+        r["EFP_lay_sums"] = np.array([marshal.efp_back(le[k]) for k in range(nk)])
+    return r
+
+
+def efp_op(op, a, b=None):
+    """EFP_plus / EFP_minus / EFP_to_real / real_to_EFP / EFP_real_diff on int64[6] arrays."""
+    from mom6_b200 import marshal
+    from mom6_b200._lib import Efp
+    lib = load()
+    lib.oracle_efp_to_real.restype = C.c_double
+    lib.oracle_efp_real_diff.restype = C.c_double
+    lib.oracle_real_to_efp.argtypes = [C.c_double, C.c_void_p]
+    if op == "from_real":
+        out = Efp()
+        rc = lib.oracle_real_to_efp(float(a), C.byref(out))
+        if rc:
+            raise OverflowError("Overflow in real_to_EFP conversion")
+        return marshal.efp_back(out)
+    ea = marshal.efp(a)
+    if op == "to_real":
+        return float(lib.oracle_efp_to_real(C.byref(ea)))
+    eb = marshal.efp(b)
+    if op == "diff":
+        return float(lib.oracle_efp_real_diff(C.byref(ea), C.byref(eb)))
+    out, ov = Efp(), C.c_int(0)
+    getattr(lib, "oracle_efp_" + op)(C.byref(ea), C.byref(eb), C.byref(out), C.byref(ov))
+    return marshal.efp_back(out)
+
+
+def chksum(dom, array, stagger=0, haloshift=0, symmetric=False, omit_corners=False, scale=1.0, stats=False):
+    """oracle_chksum: hchksum / uchksum / vchksum / Bchksum (MOM_checksums.F90).  Returns (bc[5], kind, stats or None)."""
+    import numpy as np
+    lib = load()
+    nk = 1 if array.ndim == 2 else array.shape[0]
+    bc = (C.c_int * 5)()
+    kind = C.c_int(0)
+    st = (C.c_double * 3)()
+    lib.oracle_chksum.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.oracle_chksum(C.byref(dom), _dp(array), stagger, nk, haloshift, int(symmetric), int(omit_corners), float(scale), bc,
+                           C.byref(kind), st if stats else None)
+    if rc != 0:
+        raise RuntimeError(f"oracle_chksum: FATAL {rc}")
+    return np.array(list(bc), dtype=np.int64), kind.value, (np.array(list(st)) if stats else None)
+
+
+def create_depth_list(dom, grid, Z_ref=0.0, min_depth_inc=1.0e-10):
+    """oracle_create_depth_list: create_depth_list (MOM_sum_output.F90:1203); returns (depth, area, vol_below)."""
+    import numpy as np
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    mls = (dom.iec - dom.isc + 1) * (dom.jec - dom.jsc + 1)
+    depth, area, vol = np.zeros(mls + 2), np.zeros(mls + 2), np.zeros(mls + 2)
+    n = C.c_int(0)
+    lib.oracle_create_depth_list.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.oracle_create_depth_list(C.byref(dom), C.byref(g), float(Z_ref), float(min_depth_inc), C.byref(n), _dp(depth), _dp(area), _dp(vol))
+    assert rc == 0
+    return depth[:n.value].copy(), area[:n.value].copy(), vol[:n.value].copy()
+
+
+def write_energy(dom, grid, gv, cs, u, v, h, T=None, S=None):
+    """oracle_write_energy: write_energy (MOM_sum_output.F90:321); cs (dict) is updated like the reference's CS."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); vg = marshal.vgrid(gv)
+    st = marshal.sum_output_cs(cs, keep)
+    out, arrs = marshal.energy_out(dom.nk, keep)
+    lib.oracle_write_energy.argtypes = [C.c_void_p] * 10
+    rc = lib.oracle_write_energy(C.byref(dom), C.byref(g), C.byref(vg), C.byref(st), _dp(u), _dp(v), _dp(h), _dp(T), _dp(S), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle_write_energy: FATAL {rc}")
+    marshal.sum_output_cs_back(st, cs)
+    return marshal.energy_out_back(out, arrs)
+
+
+def ocean_stats_line(cs, e, n, reday):
+    """oracle_ocean_stats_line: the line write_energy appends to ocean.stats (MOM_sum_output.F90:874-902)."""
+    import numpy as np
+    from mom6_b200 import marshal
+    from mom6_b200._lib import EnergyOut, _EO_SCALARS, _EO_SCALARS2
+    lib = load()
+    keep = []
+    st = marshal.sum_output_cs(cs, keep)
+    out = EnergyOut()
+    for k in _EO_SCALARS + _EO_SCALARS2:
+        setattr(out, k, float(e[k]))
+    out.max_CFL[0], out.max_CFL[1] = float(e["max_CFL"][0]), float(e["max_CFL"][1])
+    out.ntrunc = int(e["ntrunc"])
+    z = np.ascontiguousarray(e["Z_0APE"], dtype=np.float64)
+    out.Z_0APE = z.ctypes.data
+    buf = C.create_string_buffer(512)
+    lib.oracle_ocean_stats_line.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_char_p, C.c_size_t]
+    rc = lib.oracle_ocean_stats_line(C.byref(st), C.byref(out), int(n), float(reday), buf, 512)
+    assert rc == 0
+    return buf.value.decode()
