@@ -667,6 +667,40 @@ int mom6cu_write_energy(mom6cu_ctx* ctx, mom6cu_sum_output_cs* CS, const double*
 /* The line write_energy appends to ocean.stats (:874-902; day-stamped form), NUL terminated, without the newline. */
 int mom6cu_ocean_stats_line(const mom6cu_sum_output_cs* CS, const mom6cu_energy_out* e, int n, double reday, char* buf, size_t len);
 
+/* ---------------------------------------------------- ALE_regridding_and_remapping (the thermodynamic-cadence pass) */
+/* interpolate_column(nsrc, h_src, u_src, ndest, h_dest, u_dest, mask_edges)  src/ALE/MOM_remapping.F90:1247-1314 for ncol
+ * contiguous columns (h_src: ncol x nsrc, u_src: ncol x (nsrc+1), ...): the form the reference's unit tests call. */
+int mom6cu_interpolate_column(mom6cu_ctx* ctx, int ncol, int nsrc, const double* h_src, const double* u_src, int ndest,
+                              const double* h_dest, double* u_dest, int mask_edges);
+/* ALE_remap_interface_vals(CS, G, GV, h_old, h_new, int_val)  src/ALE/MOM_ALE.F90:1303-1339 (int_val: h points, nk+1 levels)
+ * and ALE_remap_vertex_vals :1342-1382 (vert_val: q points, nk+1 levels). */
+int mom6cu_ale_remap_interface_vals(mom6cu_ctx* ctx, const double* h_old, const double* h_new, double* int_val);
+int mom6cu_ale_remap_vertex_vals(mom6cu_ctx* ctx, const double* h_old, const double* h_new, double* vert_val);
+/* ALE_CS members the pass uses (src/ALE/MOM_ALE.F90:65-130) and MOM_control_struct%remap_aux_vars. */
+typedef struct mom6cu_ale_cs {
+  mom6cu_regridding_cs regridCS;          /* old_grid_weight is updated (ALE_update_regrid_weights :1719) */
+  mom6cu_remapping_cs remapCS, vel_remapCS;
+  double regrid_time_scale;
+  int remap_uv_using_old_alg, do_conv_adj, use_hybgen_unmix; /* must be 0 (frozen option set) */
+  int remap_aux_vars;
+} mom6cu_ale_cs;
+typedef struct mom6cu_ale_args {
+  double *u, *v, *h;               /* 3-D, in/out */
+  int ntr;                         /* CS%tracer_Reg%ntr */
+  double* const* tr;               /* Reg%Tr(m)%t, 3-D h, in/out */
+  const double* conc_underflow;    /* (ntr) or NULL */
+  int iT, iS;                      /* which tracers tv%T / tv%S point at (-1: not associated) */
+  double dtdia;
+  double *Kd_shear, *Kv_shear;     /* visc%Kd_shear / Kv_shear: h points, nk+1 levels, in/out; NULL = not associated */
+  double* Kv_shear_Bu;             /* visc%Kv_shear_Bu: q points, nk+1 levels */
+} mom6cu_ale_args;
+/* ALE_regridding_and_remapping(CS, G, GV, US, u, v, h, tv, dtdia, Time_end_thermo)  src/core/MOM.F90:1751-1926 without OBCs,
+ * ice shelves, particles or diagnostics: halo update of T, S, h; regrid weights; ALE_regrid; ALE_remap_tracers;
+ * ALE_remap_set_h_vel on both grids; ALE_remap_velocities; with remap_aux_vars remap_dyn_split_RK2_aux_vars (dynCS) and
+ * remap_vertvisc_aux_vars (MOM_set_viscosity.F90:2849) + the halo update of Kv_shear; h = h_new on (isc-1:iec+1, jsc-1:jec+1). */
+int mom6cu_ale_regridding_and_remapping(mom6cu_ctx* ctx, mom6cu_ale_cs* CS, const mom6cu_dyn_split_rk2_cs* dynCS,
+                                        const mom6cu_ale_args* a);
+
 #ifdef __cplusplus
 }
 #endif

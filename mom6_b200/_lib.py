@@ -248,6 +248,19 @@ class AdvectTracerArgs(C.Structure):
                 ("uhr_out", C.c_void_p), ("vhr_out", C.c_void_p)]
 
 
+class AleCS(C.Structure):
+    """mom6cu_ale_cs: the ALE_CS members ALE_regridding_and_remapping uses (src/ALE/MOM_ALE.F90:65-130)."""
+    _fields_ = [("regridCS", RegriddingCS), ("remapCS", RemappingCS), ("vel_remapCS", RemappingCS), ("regrid_time_scale", C.c_double),
+                ("remap_uv_using_old_alg", C.c_int), ("do_conv_adj", C.c_int), ("use_hybgen_unmix", C.c_int), ("remap_aux_vars", C.c_int)]
+
+
+class AleArgs(C.Structure):
+    """mom6cu_ale_args: the state ALE_regridding_and_remapping updates (src/core/MOM.F90:1751)."""
+    _fields_ = [("u", C.c_void_p), ("v", C.c_void_p), ("h", C.c_void_p), ("ntr", C.c_int), ("tr", C.POINTER(C.c_void_p)),
+                ("conc_underflow", C.c_void_p), ("iT", C.c_int), ("iS", C.c_int), ("dtdia", C.c_double), ("Kd_shear", C.c_void_p),
+                ("Kv_shear", C.c_void_p), ("Kv_shear_Bu", C.c_void_p)]
+
+
 class Efp(C.Structure):
     """mom6cu_efp: EFP_type (src/framework/MOM_coms.F90:76-78)."""
     _fields_ = [("v", C.c_int64 * 6)]
@@ -373,6 +386,10 @@ def bind(lib):
                                   C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.mom6cu_write_energy.argtypes = [vp, C.POINTER(SumOutputCS), vp, vp, vp, vp, vp, C.POINTER(EnergyOut)]
     lib.mom6cu_ocean_stats_line.argtypes = [C.POINTER(SumOutputCS), C.POINTER(EnergyOut), C.c_int, C.c_double, C.c_char_p, C.c_size_t]
+    lib.mom6cu_interpolate_column.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int]
+    lib.mom6cu_ale_remap_interface_vals.argtypes = [vp, vp, vp, vp]
+    lib.mom6cu_ale_remap_vertex_vals.argtypes = [vp, vp, vp, vp]
+    lib.mom6cu_ale_regridding_and_remapping.argtypes = [vp, C.POINTER(AleCS), C.POINTER(DynSplitRK2CS), C.POINTER(AleArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

@@ -331,6 +331,35 @@ def _ctx_methods():
 
     for f in (reproducing_sum, chksum, write_energy, ocean_stats_line):
         setattr(Context, f.__name__, f)
+    # ---- the thermodynamic-cadence ALE pass (csrc/ale.cu)
+    def interpolate_column(self, h_src, u_src, h_dest, mask_edges=False):
+        """interpolate_column, src/ALE/MOM_remapping.F90:1247, for (ncol, n) arrays of columns."""
+        h_src, u_src, h_dest = (np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64) for x in (h_src, u_src, h_dest))
+        u_dest = np.zeros((h_dest.shape[0], h_dest.shape[1] + 1))
+        self._check(self.lib.mom6cu_interpolate_column(self._h, h_src.shape[0], h_src.shape[1], _p(h_src), _p(u_src), h_dest.shape[1], _p(h_dest),
+                                                       _p(u_dest), int(mask_edges)))
+        return u_dest
+
+    def ale_remap_interface_vals(self, h_old, h_new, int_val):
+        """ALE_remap_interface_vals, src/ALE/MOM_ALE.F90:1303."""
+        return self._check(self.lib.mom6cu_ale_remap_interface_vals(self._h, _p(h_old), _p(h_new), _p(int_val)))
+
+    def ale_remap_vertex_vals(self, h_old, h_new, vert_val):
+        """ALE_remap_vertex_vals, src/ALE/MOM_ALE.F90:1342."""
+        return self._check(self.lib.mom6cu_ale_remap_vertex_vals(self._h, _p(h_old), _p(h_new), _p(vert_val)))
+
+    def ale_regridding_and_remapping(self, cs, args, dyn_cs=None):
+        """ALE_regridding_and_remapping, src/core/MOM.F90:1751; cs["regridCS"]["old_grid_weight"] is updated."""
+        keep = []
+        st = marshal.ale_cs(cs, keep)
+        dyn = marshal.dyn_split_rk2_cs(dyn_cs, keep) if dyn_cs is not None else None
+        rc = self._check(self.lib.mom6cu_ale_regridding_and_remapping(self._h, C.byref(st), C.byref(dyn) if dyn is not None else None,
+                                                                     C.byref(marshal.ale_args(args, keep))))
+        cs["regridCS"]["old_grid_weight"] = float(st.regridCS.old_grid_weight)
+        return rc
+
+    for f in (interpolate_column, ale_remap_interface_vals, ale_remap_vertex_vals, ale_regridding_and_remapping):
+        setattr(Context, f.__name__, f)
     setattr(Context, "remap_dyn_split_rk2_aux_vars", remap_dyn_split_rk2_aux_vars)
     setattr(Context, "set_dtbt", set_dtbt)
     setattr(Context, "step_dyn_split_rk2", step_dyn_split_rk2)

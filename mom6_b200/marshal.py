@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, AleCS, AleArgs, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
 
 
 def _scalars(struct, d):
@@ -230,3 +230,35 @@ def energy_out_back(st, arrs):
     r["ntrunc"] = int(st.ntrunc)
     r.update(arrs)
     return r
+
+
+def ale_cs(d, keep):
+    """d: regridCS / remapCS / vel_remapCS (dicts), regrid_time_scale, remap_aux_vars."""
+    st = AleCS()
+    st.regridCS = fill_struct(RegriddingCS(), d["regridCS"], keep)
+    st.remapCS = _scalars(RemappingCS(), d["remapCS"])
+    st.vel_remapCS = _scalars(RemappingCS(), d["vel_remapCS"])
+    st.regrid_time_scale = float(d.get("regrid_time_scale", 0.0))
+    st.remap_uv_using_old_alg = int(d.get("remap_uv_using_old_alg", 0))
+    st.do_conv_adj, st.use_hybgen_unmix = int(d.get("do_conv_adj", 0)), int(d.get("use_hybgen_unmix", 0))
+    st.remap_aux_vars = int(d.get("remap_aux_vars", 0))
+    return st
+
+
+def ale_args(a, keep):
+    st = AleArgs()
+    st.u, st.v, st.h = _addr(a["u"]), _addr(a["v"]), _addr(a["h"])
+    tr = a.get("tr") or []
+    st.ntr = len(tr)
+    arr = (C.c_void_p * max(len(tr), 1))(*[_addr(t) for t in tr])
+    keep.append(arr)
+    st.tr = arr
+    cu = a.get("conc_underflow")
+    if cu is not None:
+        cu = np.ascontiguousarray(cu, dtype=np.float64)
+        keep.append(cu)
+        st.conc_underflow = cu.ctypes.data
+    st.iT, st.iS = int(a.get("iT", -1)), int(a.get("iS", -1))
+    st.dtdia = float(a["dtdia"])
+    st.Kd_shear, st.Kv_shear, st.Kv_shear_Bu = _addr(a.get("Kd_shear")), _addr(a.get("Kv_shear")), _addr(a.get("Kv_shear_Bu"))
+    return st

@@ -1002,3 +1002,32 @@ def sum_output_cs(dom, depth_list, dt=900.0, do_APE_calc=True, use_temperature=T
               C_p=3991.86795711963, previous_calls=0, ntrunc=0)
     cs.update(units)
     return cs
+
+
+def ale_chain_inputs(ni, nj, nk, seed=SEED, land_blocks=0, dtdia=7200.0, regrid_time_scale=3600.0, remap_aux_vars=1, store_CAu=1, with_Bu=True,
+                     remapping_scheme=4, eta_amp=0.5):
+    """ALE_regridding_and_remapping inputs (src/core/MOM.F90:1751): the state, visc% and MOM_dyn_split_RK2_CS of step_dyn_inputs
+    with a sea-surface anomaly added to the top layer, three tracers (T, S and a passive one with tiny values), the Z* target grid
+    of regrid_inputs and the OM4-like remapping control structures (PPM_H4 for tracers, the same scheme for velocities)."""
+    dom, grid, gv, css, cs, a = step_dyn_inputs(ni, nj, nk, whalo=6, seed=seed, land_blocks=land_blocks, store_CAu=store_CAu)
+    r = rng(seed + 1313)
+    h = a["h"].copy()
+    h[0] += eta_amp * r.uniform(0, 1, size=h[0].shape) * grid["mask2dT"]
+    w = np.linspace(1.0, 3.0, nk); w /= w.sum()
+    regridCS = dict(regridding_scheme=2, nk=nk, min_thickness=1.0e-3, old_grid_weight=0.0, depth_of_time_filter_shallow=0.0,
+                    depth_of_time_filter_deep=0.0, Z_ref=0.0, coordinateResolution=np.ascontiguousarray(4000.0 * w))
+    remapCS = dict(remapping_scheme=remapping_scheme, boundary_extrapolation=0, force_bounds_in_subcell=0, force_bounds_in_target=1,
+                   om4_remap_via_sub_cells=1, answer_date=20190101, h_neglect=1.0e-30, h_neglect_edge=1.0e-30)
+    ale = dict(regridCS=regridCS, remapCS=remapCS, vel_remapCS=dict(remapCS), regrid_time_scale=regrid_time_scale, remap_aux_vars=remap_aux_vars)
+    passive = np.ascontiguousarray(r.uniform(0, 1, size=h.shape) * 10.0 ** r.integers(-30, 1, size=h.shape))
+    shp1 = (nk + 1,) + h.shape[1:]
+    kd = np.ascontiguousarray(r.uniform(0, 1, size=shp1) ** 6 * 1.0e-3)
+    kvb = None
+    if with_Bu:
+        q = fidx.new(dom, "q", nk=nk + 1).a
+        kvb = np.ascontiguousarray(r.uniform(0, 1, size=q.shape) ** 6 * 0.02)
+    for k in ("diffu", "diffv", "CAu_pred", "CAv_pred"):   # as a previous step would have left them
+        cs[k][...] = 1.0e-6 * r.standard_normal(cs[k].shape)
+    args = dict(u=a["u_inst"].copy(), v=a["v_inst"].copy(), h=np.ascontiguousarray(h), tr=[a["T"].copy(), a["S"].copy(), passive],
+                conc_underflow=np.array([0.0, 0.0, 1.0e-25]), iT=0, iS=1, dtdia=dtdia, Kd_shear=kd, Kv_shear=a["Kv_shear"].copy(), Kv_shear_Bu=kvb)
+    return dom, grid, gv, ale, cs, args

@@ -123,6 +123,15 @@ int oracle_write_energy(const mom6cu_domain* dom, const mom6cu_grid* G, const mo
                         const double* u, const double* v, const double* h, const double* T, const double* S, mom6cu_energy_out* out);
 int oracle_ocean_stats_line(const mom6cu_sum_output_cs* CS, const mom6cu_energy_out* e, int n, double reday, char* buf, size_t len);
 
+/* interpolate_column (MOM_remapping.F90:1247; PINNED by the vectors at :2648-2682), ALE_remap_interface_vals / _vertex_vals
+ * (MOM_ALE.F90:1303, :1342) and the order of operations of ALE_regridding_and_remapping (MOM.F90:1751-1926): ale_chain.cpp. */
+void oracle_interpolate_column(int nsrc, const double* h_src, const double* u_src, int ndest, const double* h_dest, double* u_dest,
+                               int mask_edges);
+int oracle_ale_remap_interface_vals(const mom6cu_domain* d, const mom6cu_grid* G, const double* h_old, const double* h_new, double* int_val);
+int oracle_ale_remap_vertex_vals(const mom6cu_domain* d, const mom6cu_grid* G, const double* h_old, const double* h_new, double* vert_val);
+int oracle_ale_regridding_and_remapping(const mom6cu_domain* d, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
+                                        mom6cu_ale_cs* CS, const mom6cu_dyn_split_rk2_cs* dynCS, const mom6cu_ale_args* a, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

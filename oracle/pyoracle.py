@@ -465,3 +465,44 @@ def ocean_stats_line(cs, e, n, reday):
     rc = lib.oracle_ocean_stats_line(C.byref(st), C.byref(out), int(n), float(reday), buf, 512)
     assert rc == 0
     return buf.value.decode()
+
+
+# ---- the thermodynamic-cadence ALE pass (ale_chain.cpp)
+def interpolate_column(h_src, u_src, h_dest, mask_edges=False):
+    """oracle_interpolate_column: interpolate_column (MOM_remapping.F90:1247) for one column."""
+    import numpy as np
+    lib = load()
+    h_src, u_src, h_dest = (np.ascontiguousarray(x, dtype=np.float64) for x in (h_src, u_src, h_dest))
+    u_dest = np.zeros(len(h_dest) + 1)
+    lib.oracle_interpolate_column.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.oracle_interpolate_column.restype = None
+    lib.oracle_interpolate_column(len(h_src), _dp(h_src), _dp(u_src), len(h_dest), _dp(h_dest), _dp(u_dest), int(mask_edges))
+    return u_dest
+
+
+def ale_remap_vals(dom, grid, h_old, h_new, val, vertex=False):
+    """oracle_ale_remap_interface_vals / _vertex_vals (MOM_ALE.F90:1303 / :1342), in place."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep)
+    fn = lib.oracle_ale_remap_vertex_vals if vertex else lib.oracle_ale_remap_interface_vals
+    fn.argtypes = [C.c_void_p] * 5
+    return fn(C.byref(dom), C.byref(g), _dp(h_old), _dp(h_new), _dp(val))
+
+
+def ale_regridding_and_remapping(dom, grid, gv, cs, args, dyn_cs=None, us=None, nthreads=1):
+    """oracle_ale_regridding_and_remapping: ALE_regridding_and_remapping (MOM.F90:1751-1926) on one tile."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); u = marshal.unit_scale(us or US_ONE)
+    st = marshal.ale_cs(cs, keep)
+    dyn = marshal.dyn_split_rk2_cs(dyn_cs, keep) if dyn_cs is not None else None
+    lib.oracle_ale_regridding_and_remapping.argtypes = [C.c_void_p] * 7 + [C.c_int]
+    rc = lib.oracle_ale_regridding_and_remapping(C.byref(dom), C.byref(g), C.byref(v), C.byref(u), C.byref(st),
+                                                 C.byref(dyn) if dyn is not None else None, C.byref(marshal.ale_args(args, keep)), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_ale_regridding_and_remapping: FATAL {rc}")
+    cs["regridCS"]["old_grid_weight"] = float(st.regridCS.old_grid_weight)
+    return rc

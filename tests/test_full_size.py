@@ -116,3 +116,63 @@ def test_advect_tracer_full_size_properties(ctx_factory):
         assert t1[m].min() >= lo - 1e-12 * max(1, abs(lo)) and t1[m].max() <= hi + 1e-12 * max(1, abs(hi))
     assert np.abs(a["tr"][2][:, js, is_] - 1.0).max() < 1e-13                       # a uniform tracer stays uniform
     assert not np.array_equal(tr0[0], a["tr"][0][:, js, is_])
+
+
+@pytest.mark.gpu
+def test_reproducing_sums_and_energy_full_size(ctx_factory):
+    """The parity metric at 1440 x 1080 x 75 without the oracle: the reference's own known answers (test_reproducing_sum.F90
+    :114-135: sum of 1..N == N(N+1)/2 exactly, in any order), order / layout invariance of the extended-fixed-point integers,
+    popcount checksums against numpy, and write_energy's totals against float sums of the same fields."""
+    from mom6_b200.api import make_domain
+    rng = np.random.default_rng(1)
+    dom = make_domain(NI, NJ, nk=4, halo=4)
+    grid = synthetic.make_grid(dom, 40)
+    gv = synthetic.make_vgrid()
+    ctx = ctx_factory(dom)
+    ctx.set_grid(grid); ctx.set_vgrid(gv)
+    js, is_ = _c(dom)
+    w = dict(isr=dom.isc - (dom.isd - 1), ier=dom.iec - (dom.isd - 1), jsr=dom.jsc - (dom.jsd - 1), jer=dom.jec - (dom.jsd - 1))
+    N = NI * NJ
+    a = np.zeros((dom.jed, dom.ied))
+    a[js, is_] = 1.0 + np.arange(N, dtype=np.float64).reshape(NJ, NI)
+    exact = 0.5 * float(N) * float(N + 1)
+    r0 = ctx.reproducing_sum(a, want_efp=True, **w)
+    assert r0["sum"] == exact
+    a[js, is_] = rng.permutation(a[js, is_].ravel()).reshape(NJ, NI)
+    r1 = ctx.reproducing_sum(a, want_efp=True, **w)
+    assert r1["sum"] == exact and np.array_equal(r0["EFP_sum"], r1["EFP_sum"])
+    # a 3-D field: layer sums, and the same integers whether the rows are summed at once or in two halves
+    f = np.ascontiguousarray(rng.standard_normal((4, dom.jed, dom.ied)) * 10.0 ** rng.uniform(-8, 8, (4, dom.jed, dom.ied)))
+    full = ctx.reproducing_sum(f, want_sums=True, want_lay_efp=True, **w)
+    half = (w["jsr"] + w["jer"]) // 2
+    lo = ctx.reproducing_sum(f, want_lay_efp=True, isr=w["isr"], ier=w["ier"], jsr=w["jsr"], jer=half)
+    hi = ctx.reproducing_sum(f, want_lay_efp=True, isr=w["isr"], ier=w["ier"], jsr=half + 1, jer=w["jer"])
+    from mom6_b200 import api, _lib
+    lib = _lib.load()
+    for k in range(4):
+        both = api.efp_op(lib, "plus", lo["EFP_lay_sums"][k], hi["EFP_lay_sums"][k])
+        assert api.efp_op(lib, "to_real", both) == full["sums"][k]
+        assert abs(full["sums"][k] - f[k][js, is_].sum()) <= 1e-9 * np.abs(f[k][js, is_]).sum()
+    # bit-count checksum of the computational domain == numpy's popcount
+    bc, kind, st = ctx.chksum(f, 0, haloshift=0, scale=1.0, stats=True)
+    want = int(np.unpackbits(np.ascontiguousarray(np.abs(f[:, js, is_])).view(np.uint8)).sum()) % 1000000000
+    assert kind == 1 and bc[0] == want
+    assert st[1] == f[:, js, is_].min() and st[2] == f[:, js, is_].max()
+    # write_energy: mass and kinetic energy against float sums
+    h = np.ascontiguousarray(rng.uniform(0.5, 100.0, (4, dom.jed, dom.ied)))
+    u = np.ascontiguousarray(0.1 * rng.standard_normal((4, dom.jed, dom.ied + 1)) * grid["mask2dCu"])
+    v = np.ascontiguousarray(0.1 * rng.standard_normal((4, dom.jed + 1, dom.ied)) * grid["mask2dCv"])
+    cs = dict(do_APE_calc=0, use_temperature=0, dt_in_T=900.0)
+    e = ctx.write_energy(cs, u, v, h)
+    areaTm = (grid["mask2dT"] * grid["areaT"])[js, is_]
+    mass = (h[:, js, is_] * (gv["H_to_RZ"] * areaTm)).sum()
+    assert abs(e["mass_tot"] - mass) <= 1e-11 * mass
+    j0, i0 = js.start, is_.start
+    ke = ((0.25 * gv["H_to_RZ"] * (areaTm * h[:, js, is_])) *
+          ((u[:, js, i0:i0 + NI] ** 2 + u[:, js, i0 + 1:i0 + NI + 1] ** 2) + (v[:, j0:j0 + NJ, is_] ** 2 + v[:, j0 + 1:j0 + NJ + 1, is_] ** 2))).sum()
+    assert abs(e["KE_tot"] - ke) <= 1e-11 * ke
+    cfl = max((np.abs(u[:, js, i0:i0 + NI + 1] * 900.0) * grid["IdxCu"][js, i0:i0 + NI + 1]).max(),
+              (np.abs(v[:, j0:j0 + NJ + 1, is_] * 900.0) * grid["IdyCv"][j0:j0 + NJ + 1, is_]).max())
+    assert e["max_CFL"][1] == cfl   # a maximum of identically computed products: exact
+    e2 = ctx.write_energy(cs, u, v, h)
+    assert e2["mass_chg"] == 0.0 and e2["mass_tot"] == e["mass_tot"] and cs["previous_calls"] == 2
