@@ -327,7 +327,7 @@ def _ctx_methods():
 
     def ocean_stats_line(self, cs, e, n, reday):
         """The line write_energy appends to ocean.stats (MOM_sum_output.F90:874-902)."""
-        return ocean_stats_line(self.lib, cs, e, n, reday)
+        return format_ocean_stats_line(self.lib, cs, e, n, reday)
 
     for f in (reproducing_sum, chksum, write_energy, ocean_stats_line):
         setattr(Context, f.__name__, f)
@@ -391,7 +391,7 @@ def make_domain(ni, nj, nk=1, halo=4, whalo=None, cyclic_x=True, cyclic_y=False,
     return d
 
 
-def ocean_stats_line(lib, cs, e, n, reday):
+def format_ocean_stats_line(lib, cs, e, n, reday):
     """mom6cu_ocean_stats_line on a write_energy result (host formatting only: needs no device)."""
     from . import marshal
     from ._lib import EnergyOut, _EO_SCALARS, _EO_SCALARS2
@@ -430,3 +430,6 @@ def efp_op(lib, op, a, b=None):
     out, ov = Efp(), C.c_int(0)
     getattr(lib, "mom6cu_efp_" + op)(C.byref(ea), C.byref(eb), C.byref(out), C.byref(ov))
     return marshal.efp_back(out)
+
+
+ocean_stats_line = format_ocean_stats_line
