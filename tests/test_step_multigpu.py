@@ -26,7 +26,7 @@ def _cp(x):
     return x
 
 
-def _worker(rank, world, port, npi, npj, q):
+def _worker(rank, world, port, npi, npj, q, depth_list):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -46,6 +46,16 @@ def _worker(rank, world, port, npi, npj, q):
     out = {k: _inner(dom, a[k]).copy() for k in STATE}
     out.update({"CS%" + k: _inner(dom, cs[k]).copy() for k in CSARR})
     out["dtbt"] = cs["barotropic"]["dtbt"]
+    # the reference's own layout-invariance metric: the ocean.stats line and the bit-count checksums of the final state
+    so = synthetic.sum_output_cs(dom, depth_list)
+    lines = []
+    for n in range(2):   # the second call reports the (zero) change since the first
+        e = ctx.write_energy(so, a["u_inst"], a["v_inst"], a["h"], a["T"], a["S"])
+        lines.append(ctx.ocean_stats_line(so, e, n, 0.0))
+    out["stats_lines"] = lines
+    out["energy"] = {k: e[k] for k in ("En_mass", "mass_tot", "KE_tot", "PE_tot", "Salt", "Heat", "max_CFL", "KE", "PE", "mass_lay", "Z_0APE")}
+    out["chk"] = [ctx.chksum(a["h"], 0, haloshift=0, stats=True), ctx.chksum(a["u_inst"], 1, haloshift=0, stats=True),
+                  ctx.chksum(a["v_inst"], 2, haloshift=0, stats=True)]
     q.put((rank, out))
     dist.barrier()
     ctx.close()
@@ -66,13 +76,28 @@ def test_step_two_tiles_bitwise(oracle, npi, npj):
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     world = npi * npj
-    procs = [ctxm.Process(target=_worker, args=(r, world, port, npi, npj, q)) for r in range(world)]
+    depth_list = oracle.create_depth_list(dom, grid)
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, npi, npj, q, depth_list)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
     ni, nj = SIZE[0] // npi, SIZE[1] // npj
+    # ocean.stats and checksums of the tiled run == the single-tile oracle (every rank reports the global numbers)
+    so = synthetic.sum_output_cs(dom, depth_list)
+    ref_lines = []
+    for n in range(2):
+        e_ref = oracle.write_energy(dom, grid, gv, so, a["u_inst"], a["v_inst"], a["h"], a["T"], a["S"])
+        ref_lines.append(oracle.ocean_stats_line(so, e_ref, n, 0.0))
+    ref_chk = [oracle.chksum(dom, a["h"], 0, 0, stats=True), oracle.chksum(dom, a["u_inst"], 1, 0, stats=True),
+               oracle.chksum(dom, a["v_inst"], 2, 0, stats=True)]
+    for rank, out in res.items():
+        assert out["stats_lines"] == ref_lines, (rank, out["stats_lines"], ref_lines)
+        for k, v in out["energy"].items():
+            assert np.array_equal(np.asarray(v, dtype=np.float64).view(np.int64), np.asarray(e_ref[k], dtype=np.float64).view(np.int64)), (rank, k)
+        for got, want in zip(out["chk"], ref_chk):
+            assert np.array_equal(got[0], want[0]) and got[1] == want[1] and np.array_equal(got[2], want[2]), (rank, got, want)
     bad = []
     for rank, out in res.items():
         pi, pj = rank % npi, rank // npi
