@@ -188,6 +188,14 @@ module mom6cu_interface
   end type mom6cu_advect_tracer_args
 
   !> remapping_CS (src/ALE/MOM_remapping.F90:37-85) and regridding_CS (src/ALE/MOM_regridding.F90:49-160)
+  !> mixedlayer_restrat_CS (src/parameterizations/lateral/MOM_mixed_layer_restrat.F90:42-115), the mixedlayer_restrat_OM4 members
+  type, bind(C) :: mom6cu_mle_cs
+    real(c_double) :: ml_restrat_coef, ml_restrat_coef2, front_length, MLE_MLD_decay_time, MLE_MLD_decay_time2, MLE_MLD_stretch, &
+                      MLE_tail_dh, ustar_min, vonKar, MLE_density_diff
+    integer(c_int) :: MLE_use_PBL_MLD, use_Stanley_ML, use_Bodner, fl_from_file, EOS_form
+    real(c_double) :: Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp
+    type(c_ptr)    :: MLD_filtered, MLD_filtered_slow
+  end type mom6cu_mle_cs
   type, bind(C) :: mom6cu_remapping_cs
     integer(c_int) :: remapping_scheme, boundary_extrapolation, force_bounds_in_subcell, force_bounds_in_target, &
                       om4_remap_via_sub_cells, answer_date
@@ -348,6 +356,16 @@ module mom6cu_interface
       integer(c_int), value :: n ; real(c_double), value :: reday
       character(kind=c_char), intent(out) :: buf(*) ; integer(c_size_t), value :: len
     end function mom6cu_ocean_stats_line
+    !> mixedlayer_restrat (src/parameterizations/lateral/MOM_mixed_layer_restrat.F90:149), called from step_MOM_dynamics (MOM.F90:1422)
+    integer(c_int) function mom6cu_mixedlayer_restrat(ctx, CS, h, uhtr, vhtr, T, S, ustar, dt, h_MLD, Rd_dx_h) &
+        bind(C, name="mom6cu_mixedlayer_restrat")
+      import ; type(c_ptr), value :: ctx, h, uhtr, vhtr, T, S, ustar, h_MLD, Rd_dx_h
+      type(mom6cu_mle_cs), intent(inout) :: CS ; real(c_double), value :: dt
+    end function mom6cu_mixedlayer_restrat
+    !> mu(sigma, dh) (MOM_mixed_layer_restrat.F90:717) for n values
+    integer(c_int) function mom6cu_mle_mu(ctx, n, sigma, dh, res) bind(C, name="mom6cu_mle_mu")
+      import ; type(c_ptr), value :: ctx, sigma, dh, res ; integer(c_int), value :: n
+    end function mom6cu_mle_mu
     type(c_ptr) function mom6cu_plane_alloc(ctx, name, nk) bind(C, name="mom6cu_plane_alloc")
       import ; type(c_ptr), value :: ctx ; character(kind=c_char), intent(in) :: name(*) ; integer(c_int), value :: nk
     end function mom6cu_plane_alloc

@@ -701,6 +701,29 @@ typedef struct mom6cu_ale_args {
 int mom6cu_ale_regridding_and_remapping(mom6cu_ctx* ctx, mom6cu_ale_cs* CS, const mom6cu_dyn_split_rk2_cs* dynCS,
                                         const mom6cu_ale_args* a);
 
+/* ------------------------------------------------------------- mixedlayer_restrat (first caller) */
+/* mixedlayer_restrat_CS, src/parameterizations/lateral/MOM_mixed_layer_restrat.F90:42-115, the members of the Fox-Kemper
+ * et al. (2008) general-coordinate path mixedlayer_restrat_OM4 (:189-714), and the equation of state it evaluates at the
+ * surface pressure (tv%eqn_of_state: LINEAR or WRIGHT, MOM6CU_EOS_*).  Frozen: Boussinesq, MLE_USE_PBL_MLD (MLE_DENSITY_DIFF
+ * <= 0), no Stanley SGS variance, no Bodner / bulk-mixed-layer variants, constant front length (MLE_FRONT_LENGTH >= 0, not from
+ * a file), MLE_TAIL_DH = 0 in the full routine (mu's exponent 1 + 2 dh is a real power otherwise; mom6cu_mle_mu accepts any dh). */
+typedef struct mom6cu_mle_cs {
+  double ml_restrat_coef, ml_restrat_coef2, front_length, MLE_MLD_decay_time, MLE_MLD_decay_time2, MLE_MLD_stretch, MLE_tail_dh,
+      ustar_min, vonKar, MLE_density_diff;
+  int MLE_use_PBL_MLD, use_Stanley_ML, use_Bodner, fl_from_file;
+  int EOS_form;
+  double Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp;
+  double *MLD_filtered, *MLD_filtered_slow; /* CS%MLD_filtered, CS%MLD_filtered_slow: 2-D h, in/out (slow may be NULL if decay_time2 <= 0) */
+} mom6cu_mle_cs;
+/* mixedlayer_restrat(h, uhtr, vhtr, tv, forces, dt, MLD, h_MLD, bflux, VarMix, G, GV, US, CS)  :149-186 -> mixedlayer_restrat_OM4.
+ * h, uhtr, vhtr: 3-D in/out; T, S: tv%T, tv%S; ustar: forces%ustar (2-D h); h_MLD: visc%h_ML (2-D h); Rd_dx_h: VarMix%Rd_dx_h
+ * (2-D h; NULL allowed when front_length == 0). */
+int mom6cu_mixedlayer_restrat(mom6cu_ctx* ctx, mom6cu_mle_cs* CS, double* h, double* uhtr, double* vhtr, const double* T,
+                              const double* S, const double* ustar, double dt, const double* h_MLD, const double* Rd_dx_h);
+/* mu(sigma, dh) :717-751, the shape function of the restratifying streamfunction, for n values (host or device arrays):
+ * the form the reference's unit tests call (mixedlayer_restrat_unit_tests :2014-2058). */
+int mom6cu_mle_mu(mom6cu_ctx* ctx, int n, const double* sigma, const double* dh, double* out);
+
 #ifdef __cplusplus
 }
 #endif

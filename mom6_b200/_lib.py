@@ -261,6 +261,16 @@ class AleArgs(C.Structure):
                 ("Kv_shear", C.c_void_p), ("Kv_shear_Bu", C.c_void_p)]
 
 
+class MleCS(C.Structure):
+    """mom6cu_mle_cs: mixedlayer_restrat_CS (src/parameterizations/lateral/MOM_mixed_layer_restrat.F90:42-115), OM4 path."""
+    _fields_ = ([(n, C.c_double) for n in ("ml_restrat_coef", "ml_restrat_coef2", "front_length", "MLE_MLD_decay_time",
+                                           "MLE_MLD_decay_time2", "MLE_MLD_stretch", "MLE_tail_dh", "ustar_min", "vonKar",
+                                           "MLE_density_diff")] +
+                [(n, C.c_int) for n in ("MLE_use_PBL_MLD", "use_Stanley_ML", "use_Bodner", "fl_from_file", "EOS_form")] +
+                [(n, C.c_double) for n in ("Rho_T0_S0", "dRho_dT", "dRho_dS", "dRho_dp")] +
+                [("MLD_filtered", C.c_void_p), ("MLD_filtered_slow", C.c_void_p)])
+
+
 class Efp(C.Structure):
     """mom6cu_efp: EFP_type (src/framework/MOM_coms.F90:76-78)."""
     _fields_ = [("v", C.c_int64 * 6)]
@@ -390,6 +400,8 @@ def bind(lib):
     lib.mom6cu_ale_remap_interface_vals.argtypes = [vp, vp, vp, vp]
     lib.mom6cu_ale_remap_vertex_vals.argtypes = [vp, vp, vp, vp]
     lib.mom6cu_ale_regridding_and_remapping.argtypes = [vp, C.POINTER(AleCS), C.POINTER(DynSplitRK2CS), C.POINTER(AleArgs)]
+    lib.mom6cu_mixedlayer_restrat.argtypes = [vp, C.POINTER(MleCS), vp, vp, vp, vp, vp, vp, C.c_double, vp, vp]
+    lib.mom6cu_mle_mu.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

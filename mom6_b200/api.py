@@ -358,6 +358,24 @@ def _ctx_methods():
         cs["regridCS"]["old_grid_weight"] = float(st.regridCS.old_grid_weight)
         return rc
 
+    # ---- mixedlayer_restrat (csrc/mle.cu)
+    def mixedlayer_restrat(self, cs, h, uhtr, vhtr, T, S, ustar, dt, h_MLD, Rd_dx_h=None):
+        """mixedlayer_restrat -> mixedlayer_restrat_OM4, src/parameterizations/lateral/MOM_mixed_layer_restrat.F90:149 / :189;
+        h, uhtr, vhtr and cs["MLD_filtered"], cs["MLD_filtered_slow"] are updated in place."""
+        keep = []
+        return self._check(self.lib.mom6cu_mixedlayer_restrat(self._h, C.byref(marshal.mle_cs(cs, keep)), _p(h), _p(uhtr), _p(vhtr), _p(T), _p(S),
+                                                              _p(ustar), float(dt), _p(h_MLD), _p(Rd_dx_h)))
+
+    def mle_mu(self, sigma, dh):
+        """mu(sigma, dh), MOM_mixed_layer_restrat.F90:717, elementwise on the device."""
+        sigma, dh = np.broadcast_arrays(np.asarray(sigma, dtype=np.float64), np.asarray(dh, dtype=np.float64))
+        sigma, dh = np.ascontiguousarray(sigma).ravel(), np.ascontiguousarray(dh).ravel()
+        out = np.zeros_like(sigma)
+        self._check(self.lib.mom6cu_mle_mu(self._h, sigma.size, _p(sigma), _p(dh), _p(out)))
+        return out
+
+    for f in (mixedlayer_restrat, mle_mu):
+        setattr(Context, f.__name__, f)
     for f in (interpolate_column, ale_remap_interface_vals, ale_remap_vertex_vals, ale_regridding_and_remapping):
         setattr(Context, f.__name__, f)
     setattr(Context, "remap_dyn_split_rk2_aux_vars", remap_dyn_split_rk2_aux_vars)

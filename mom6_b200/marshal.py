@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, AleCS, AleArgs, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, AleCS, AleArgs, MleCS, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
 
 
 def _scalars(struct, d):
@@ -262,3 +262,7 @@ def ale_args(a, keep):
     st.dtdia = float(a["dtdia"])
     st.Kd_shear, st.Kv_shear, st.Kv_shear_Bu = _addr(a.get("Kd_shear")), _addr(a.get("Kv_shear")), _addr(a.get("Kv_shear_Bu"))
     return st
+
+
+def mle_cs(d, keep):
+    return fill_struct(MleCS(), d, keep)

@@ -1031,3 +1031,45 @@ def ale_chain_inputs(ni, nj, nk, seed=SEED, land_blocks=0, dtdia=7200.0, regrid_
     args = dict(u=a["u_inst"].copy(), v=a["v_inst"].copy(), h=np.ascontiguousarray(h), tr=[a["T"].copy(), a["S"].copy(), passive],
                 conc_underflow=np.array([0.0, 0.0, 1.0e-25]), iT=0, iS=1, dtdia=dtdia, Kd_shear=kd, Kv_shear=a["Kv_shear"].copy(), Kv_shear_Bu=kvb)
     return dom, grid, gv, ale, cs, args
+
+
+def mle_cs_and_forcing(shp2, seed=SEED, eos="WRIGHT", **cs_over):
+    """The OM4_025-like mixedlayer_restrat_CS (FOX_KEMPER_ML_RESTRAT_COEF = 1 with MLE_FRONT_LENGTH = 500 m, MLE_MLD_DECAY_TIME = 30 d,
+    MLE_USE_PBL_MLD; mixedlayer_restrat_init, MOM_mixed_layer_restrat.F90:1618) and the 2-D inputs of a call on h-point arrays of
+    shape shp2: a boundary-layer depth h_MLD of 20-150 m (zero on some columns), u* of 0-2 cm/s (zero on some), Rd_dx_h of 0.2-1.7."""
+    r = rng(seed + 1414)
+    h_MLD = (20.0 + 130.0 * r.uniform(0, 1, size=shp2)) * (r.uniform(0, 1, size=shp2) > 0.05)
+    ustar = 0.02 * r.uniform(0, 1, size=shp2) * (r.uniform(0, 1, size=shp2) > 0.1)
+    Rd = 0.2 + 1.5 * r.uniform(0, 1, size=shp2)
+    form = dict(LINEAR=1, WRIGHT=3)[eos]
+    cs = dict(ml_restrat_coef=1.0, ml_restrat_coef2=0.0, front_length=500.0, MLE_MLD_decay_time=2.592e6, MLE_MLD_decay_time2=0.0,
+              MLE_MLD_stretch=1.0, MLE_tail_dh=0.0, ustar_min=2.0e-4 * 7.2921e-5 * (1.0e-10 + 1.0e-30), vonKar=0.41,
+              MLE_density_diff=-9.0e9, MLE_use_PBL_MLD=1, use_Stanley_ML=0, use_Bodner=0, fl_from_file=0, EOS_form=form,
+              Rho_T0_S0=1000.0, dRho_dT=-0.2, dRho_dS=0.8, dRho_dp=0.0,
+              MLD_filtered=np.ascontiguousarray(60.0 * r.uniform(0, 1, size=shp2)),
+              MLD_filtered_slow=np.ascontiguousarray(80.0 * r.uniform(0, 1, size=shp2)))
+    cs.update(cs_over)
+    return cs, dict(ustar=np.ascontiguousarray(ustar), h_MLD=np.ascontiguousarray(h_MLD), Rd_dx_h=np.ascontiguousarray(Rd))
+
+
+def mle_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, eos="WRIGHT", dt=900.0, front=2.0,
+               **cs_over):
+    """mixedlayer_restrat inputs (MOM_mixed_layer_restrat.F90:149): the Z*-like state of dyn_state, T with lateral fronts of
+    `front` degC in the upper ocean, accumulated transports uhtr / vhtr, and mle_cs_and_forcing.  Returns dom, grid, gv, cs, args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 1515)
+    h = st["h"]
+    shp2 = h.shape[1:]
+    zmid = -(np.cumsum(h, axis=0) - 0.5 * h)
+    jj, ii = np.meshgrid(np.arange(shp2[0]), np.arange(shp2[1]), indexing="ij")
+    frontal = np.sin(2 * np.pi * ii / max(ni, 1) * 3.0) * np.cos(2 * np.pi * jj / max(nj, 1) * 2.0)
+    T = 20.0 * np.exp(zmid / 1000.0) + front * frontal[None] * np.exp(zmid / 200.0) + 0.05 * r.uniform(-1, 1, size=h.shape)
+    S = 35.0 + 0.5 * np.exp(zmid / 500.0) + 0.01 * r.uniform(-1, 1, size=h.shape)
+    uhtr = np.ascontiguousarray(0.05 * st["u"] * dt * grid["dyCu"][None] * 10.0)
+    vhtr = np.ascontiguousarray(0.05 * st["v"] * dt * grid["dxCv"][None] * 10.0)
+    cs, f2 = mle_cs_and_forcing(shp2, seed, eos, **cs_over)
+    a = dict(h=np.ascontiguousarray(h), uhtr=uhtr, vhtr=vhtr, T=np.ascontiguousarray(T), S=np.ascontiguousarray(S), dt=dt, **f2)
+    return dom, grid, gv, cs, a

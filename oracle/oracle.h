@@ -132,6 +132,13 @@ int oracle_ale_remap_vertex_vals(const mom6cu_domain* d, const mom6cu_grid* G, c
 int oracle_ale_regridding_and_remapping(const mom6cu_domain* d, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
                                         mom6cu_ale_cs* CS, const mom6cu_dyn_split_rk2_cs* dynCS, const mom6cu_ale_args* a, int nthreads);
 
+/* mixedlayer_restrat -> mixedlayer_restrat_OM4 (MOM_mixed_layer_restrat.F90:149-714) and mu (:717; PINNED by the unit test
+ * vectors at :2022-2041): mle.cpp. */
+double oracle_mle_mu(double sigma, double dh);
+int oracle_mixedlayer_restrat(const mom6cu_domain* d, const mom6cu_grid* G, const mom6cu_vgrid* GV, mom6cu_mle_cs* CS, double* h,
+                              double* uhtr, double* vhtr, const double* T, const double* S, const double* ustar, double dt,
+                              const double* h_MLD, const double* Rd_dx_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -506,3 +506,27 @@ def ale_regridding_and_remapping(dom, grid, gv, cs, args, dyn_cs=None, us=None, 
         raise RuntimeError(f"oracle_ale_regridding_and_remapping: FATAL {rc}")
     cs["regridCS"]["old_grid_weight"] = float(st.regridCS.old_grid_weight)
     return rc
+
+
+# ---- mixedlayer_restrat (mle.cpp)
+def mle_mu(sigma, dh):
+    """oracle_mle_mu: mu(sigma, dh), MOM_mixed_layer_restrat.F90:717-751."""
+    lib = load()
+    lib.oracle_mle_mu.argtypes = [C.c_double, C.c_double]
+    lib.oracle_mle_mu.restype = C.c_double
+    return lib.oracle_mle_mu(float(sigma), float(dh))
+
+
+def mixedlayer_restrat(dom, grid, gv, cs, h, uhtr, vhtr, T, S, ustar, dt, h_MLD, Rd_dx_h=None):
+    """oracle_mixedlayer_restrat: mixedlayer_restrat_OM4 (MOM_mixed_layer_restrat.F90:189-714), in place."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv)
+    st = marshal.mle_cs(cs, keep)
+    lib.oracle_mixedlayer_restrat.argtypes = [C.c_void_p] * 10 + [C.c_double] + [C.c_void_p] * 2
+    rc = lib.oracle_mixedlayer_restrat(C.byref(dom), C.byref(g), C.byref(v), C.byref(st), _dp(h), _dp(uhtr), _dp(vhtr), _dp(T), _dp(S),
+                                       _dp(ustar), float(dt), _dp(h_MLD), _dp(Rd_dx_h))
+    if rc != 0:
+        raise RuntimeError(f"oracle_mixedlayer_restrat: FATAL {rc}")
+    return rc
