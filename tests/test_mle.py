@@ -45,6 +45,53 @@ def test_mu_column_code_equals_oracle(oracle, mle_host):
         assert a == b or abs(a - b) <= 4 * np.finfo(np.float64).eps
 
 
+CASES = [dict(), dict(land_blocks=4, eos="LINEAR"), dict(front_length=0.0, ml_restrat_coef=60.0, cyclic_y=True),
+         dict(MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, land_blocks=2), dict(MLE_MLD_decay_time=0.0, MLE_MLD_stretch=1.5),
+         dict(dt=7200.0, front=6.0, ml_restrat_coef=20.0, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=5.0)]
+
+
+def _unified(dom, x, st):
+    """A field in the library's unified plane layout (csrc/common.cuh): one offset for every staggering."""
+    nj, ni = dom.jed - dom.jsd + 2, dom.ied - dom.isd + 2
+    out = np.zeros(x.shape[:-2] + (nj, ni))
+    out[..., (0 if st in "vq" else 1):, (0 if st in "uq" else 1):] = x
+    return out
+
+
+def _from_unified(x, st):
+    return np.ascontiguousarray(x[..., (0 if st in "vq" else 1):, (0 if st in "uq" else 1):])
+
+
+def _run_device_code_on_host(lib, dom, grid, gv, cs, a):
+    """mixedlayer_restrat through the host build of csrc/mle_column.cuh, parameters set as mom6cu_mixedlayer_restrat sets them."""
+    nk, dt = dom.nk, a["dt"]
+    f1, f2 = cs["MLE_MLD_decay_time"] > 0.0, cs["MLE_MLD_decay_time2"] > 0.0
+    par = [nk, dt, gv["Z_to_H"], gv["Angstrom_H"], gv["H_subroundoff"], gv["H_to_Z"] * gv["g_Earth"] / gv["Rho0"], 0.25 / dt,
+           0.5 * gv["Angstrom_H"], cs["vonKar"] * 9.8696, cs["ustar_min"], cs["ml_restrat_coef"], cs["ml_restrat_coef2"], cs["front_length"],
+           cs["MLE_MLD_stretch"], cs["MLE_tail_dh"],
+           cs["MLE_MLD_decay_time"] / (dt + cs["MLE_MLD_decay_time"]) if f1 else 0.0, dt / (dt + cs["MLE_MLD_decay_time"]) if f1 else 0.0,
+           cs["MLE_MLD_decay_time2"] / (dt + cs["MLE_MLD_decay_time2"]) if f2 else 0.0, dt / (dt + cs["MLE_MLD_decay_time2"]) if f2 else 0.0,
+           int(f1), int(f2), int(cs["front_length"] > 0.0), cs["EOS_form"], cs["Rho_T0_S0"], cs["dRho_dT"], cs["dRho_dS"], cs["dRho_dp"]]
+    par = np.array(par, dtype=np.float64)
+    box = np.array([dom.isc, dom.iec, dom.jsc, dom.jec, dom.isd - 1, dom.jsd - 1], dtype=np.int32)
+    F = {k: _unified(dom, a[k], st) for k, st in (("h", "h"), ("uhtr", "u"), ("vhtr", "v"), ("T", "h"), ("S", "h"), ("ustar", "h"),
+                                                  ("h_MLD", "h"), ("Rd_dx_h", "h"))}
+    F["MLD_filtered"], F["MLD_filtered_slow"] = _unified(dom, cs["MLD_filtered"], "h"), _unified(dom, cs["MLD_filtered_slow"], "h")
+    Gd = {k: _unified(dom, grid[k], st) for k, st in (("areaT", "h"), ("IareaT", "h"), ("CoriolisBu", "q"), ("mask2dCu", "u"), ("mask2dCv", "v"),
+                                                      ("dxCu", "u"), ("dyCu", "u"), ("dxCv", "v"), ("dyCv", "v"), ("IdxCu", "u"), ("IdyCv", "v"))}
+    nj, ni = F["ustar"].shape
+    scratch = np.zeros((4 + 2 * nk, nj, ni))
+    p = lambda x: x.ctypes.data_as(C.c_void_p)   # noqa: E731
+    lib.mle_host_run.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong] + [C.c_void_p] * 22
+    lib.mle_host_run.restype = None
+    lib.mle_host_run(p(par), p(box), ni, ni * nj, p(F["h"]), p(F["uhtr"]), p(F["vhtr"]), p(F["T"]), p(F["S"]), p(F["ustar"]), p(F["h_MLD"]),
+                     p(F["Rd_dx_h"]), p(F["MLD_filtered"]), p(F["MLD_filtered_slow"]), p(Gd["areaT"]), p(Gd["IareaT"]), p(Gd["CoriolisBu"]),
+                     p(Gd["mask2dCu"]), p(Gd["mask2dCv"]), p(Gd["dxCu"]), p(Gd["dyCu"]), p(Gd["dxCv"]), p(Gd["dyCv"]), p(Gd["IdxCu"]),
+                     p(Gd["IdyCv"]), p(scratch))
+    out = {k: _from_unified(F[k], st) for k, st in (("h", "h"), ("uhtr", "u"), ("vhtr", "v"), ("MLD_filtered", "h"), ("MLD_filtered_slow", "h"))}
+    return out
+
+
 def _run_oracle(oracle, dom, grid, gv, cs, a):
     o = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
     c = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in cs.items()}
@@ -114,9 +161,24 @@ def test_oracle_rejects_options_outside_the_frozen_set(oracle):
             _run_oracle(oracle, dom, grid, gv, dict(cs, **bad), a)
 
 
-CASES = [dict(), dict(land_blocks=4, eos="LINEAR"), dict(front_length=0.0, ml_restrat_coef=60.0, cyclic_y=True),
-         dict(MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, land_blocks=2), dict(MLE_MLD_decay_time=0.0, MLE_MLD_stretch=1.5),
-         dict(dt=7200.0, front=6.0, ml_restrat_coef=20.0, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=5.0)]
+
+@pytest.mark.parametrize("kw", CASES)
+def test_device_column_code_equals_oracle_on_the_host(oracle, mle_host, kw):
+    """The column / face / update functions the kernels of csrc/mle.cu call (early exit at the base of the mixed layer, mu reused
+    between a layer's bottom and the next layer's top, h_avail evaluated in place) compiled for the host: bit for bit the oracle."""
+    for (ni, nj, nk) in ((44, 40, 20), (31, 9, 3), (20, 22, 75)):
+        dom, grid, gv, cs, a = synthetic.mle_inputs(ni, nj, nk, **kw)
+        a["uhtr"][:, 5:9, 5:30] = -0.0                                   # signed zeros must survive below the mixed layer
+        a["vhtr"][:, 5:9, 5:30] = 0.0
+        c, o = _run_oracle(oracle, dom, grid, gv, cs, a)
+        got = _run_device_code_on_host(mle_host, dom, grid, gv, cs, a)
+        assert np.array_equal(_inner(dom, o["h"]).view(np.int64), _inner(dom, got["h"]).view(np.int64)), kw
+        for k in ("uhtr", "vhtr"):
+            assert np.array_equal(o[k].view(np.int64), got[k].view(np.int64)), (k, kw)
+        ext = (slice(dom.jsc - dom.jsd - 1, dom.jec - dom.jsd + 2), slice(dom.isc - dom.isd - 1, dom.iec - dom.isd + 2))
+        for k in ("MLD_filtered", "MLD_filtered_slow"):
+            assert np.array_equal(c[k][ext].view(np.int64), got[k][ext].view(np.int64)), (k, kw)
+        assert nk < 20 or np.abs(o["uhtr"] - a["uhtr"]).max() > 0
 
 
 @pytest.mark.gpu
