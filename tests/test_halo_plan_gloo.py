@@ -98,7 +98,7 @@ def _worker(rank, world, port, npi, npj, NI, NJ, halo, cyc_x, cyc_y, q):
 
 
 @pytest.mark.parametrize("npi,npj,cyc_x,cyc_y", [(2, 1, True, False), (1, 2, True, True), (2, 2, True, False),
-                                                 (2, 1, False, False)])
+                                                 (2, 1, False, False), (4, 2, True, False)])   # 4x2: the 8-GPU layout of bench.py
 def test_halo_plan_matches_global_fill(npi, npj, cyc_x, cyc_y):
     world = npi * npj
     ctxm = mp.get_context("spawn")
