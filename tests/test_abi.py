@@ -48,3 +48,30 @@ def test_no_cpu_fallback_without_a_device():
     dom = make_domain(8, 8, nk=2)
     assert lib.mom6cu_create(C.byref(h), C.byref(dom), 0) == 1  # MOM6CU_ERR_NO_DEVICE
     assert not h.value
+
+
+def _build_hpp_host(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "hpp_host")
+    libdir = os.path.join(ROOT, "mom6_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "harness", "hpp_host.cpp"),
+                           "-L", libdir, "-lmom6cu", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_a_device(tmp_path):
+    """include/mom6cu.hpp (the compiled-language host side: the reference's procedure names over the C ABI, MOM_error(FATAL) as an
+    exception) compiles warning-free against the header and links against the library; without a GPU it refuses to run."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is visible")
+    r = subprocess.run([_build_hpp_host(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_runs_the_reference_mu_vectors(tmp_path):
+    import subprocess
+    r = subprocess.run([_build_hpp_host(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "FATAL as expected" in r.stdout, (r.returncode, r.stdout, r.stderr)
