@@ -196,6 +196,19 @@ module mom6cu_interface
     real(c_double) :: Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp
     type(c_ptr)    :: MLD_filtered, MLD_filtered_slow
   end type mom6cu_mle_cs
+  !> tracer_hor_diff_CS (src/tracer/MOM_tracer_hor_diff.F90:40-106) and the VarMix switches tracer_hordiff reads
+  type, bind(C) :: mom6cu_tracer_hor_diff_cs
+    real(c_double) :: KhTr, KhTr_min, KhTr_max, KhTr_passivity_coeff, KhTr_passivity_min, KhTr_Slope_Cff, max_diff_CFL
+    integer(c_int) :: check_diffusive_CFL, use_neutral_diffusion, use_hor_bnd_diffusion, Diffuse_ML_interior, &
+                      use_variable_mixing, Resoln_scaled_KhTr, use_MEKE_Kh
+  end type mom6cu_tracer_hor_diff_cs
+  !> the arguments of tracer_hordiff (:119); tr, df_x, df_y are arrays of c_ptr (Reg%Tr(m)%t, %df_x, %df_y)
+  type, bind(C) :: mom6cu_tracer_hordiff_args
+    type(c_ptr)    :: h
+    real(c_double) :: dt
+    integer(c_int) :: ntr
+    type(c_ptr)    :: tr, conc_underflow, Res_fn_h, Rd_dx_h, df_x, df_y
+  end type mom6cu_tracer_hordiff_args
   type, bind(C) :: mom6cu_remapping_cs
     integer(c_int) :: remapping_scheme, boundary_extrapolation, force_bounds_in_subcell, force_bounds_in_target, &
                       om4_remap_via_sub_cells, answer_date
@@ -366,6 +379,11 @@ module mom6cu_interface
     integer(c_int) function mom6cu_mle_mu(ctx, n, sigma, dh, res) bind(C, name="mom6cu_mle_mu")
       import ; type(c_ptr), value :: ctx, sigma, dh, res ; integer(c_int), value :: n
     end function mom6cu_mle_mu
+    !> tracer_hordiff (src/tracer/MOM_tracer_hor_diff.F90:119), called from step_MOM_tracer_dyn (MOM.F90:1526)
+    integer(c_int) function mom6cu_tracer_hordiff(ctx, CS, a) bind(C, name="mom6cu_tracer_hordiff")
+      import ; type(c_ptr), value :: ctx
+      type(mom6cu_tracer_hor_diff_cs), intent(in) :: CS ; type(mom6cu_tracer_hordiff_args), intent(in) :: a
+    end function mom6cu_tracer_hordiff
     type(c_ptr) function mom6cu_plane_alloc(ctx, name, nk) bind(C, name="mom6cu_plane_alloc")
       import ; type(c_ptr), value :: ctx ; character(kind=c_char), intent(in) :: name(*) ; integer(c_int), value :: nk
     end function mom6cu_plane_alloc

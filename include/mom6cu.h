@@ -724,6 +724,31 @@ int mom6cu_mixedlayer_restrat(mom6cu_ctx* ctx, mom6cu_mle_cs* CS, double* h, dou
  * the form the reference's unit tests call (mixedlayer_restrat_unit_tests :2014-2058). */
 int mom6cu_mle_mu(mom6cu_ctx* ctx, int n, const double* sigma, const double* dh, double* out);
 
+/* ----------------------------------------------------------------- tracer_hordiff (the tracer-step caller) */
+/* tracer_hor_diff_CS, src/tracer/MOM_tracer_hor_diff.F90:40-106, and the VarMix switches tracer_hordiff reads (:163-169).  Frozen: the
+ * along-surface path (:537-604; USE_NEUTRAL_DIFFUSION, USE_HORIZONTAL_BOUNDARY_DIFFUSION and DIFFUSE_ML_TO_INTERIOR off), online
+ * diffusivities (:203-340: constant KhTr, or with VarMix the KhTr_max / resolution-function / KhTr_min / passivity chain; no Eady
+ * growth-rate term (KHTR_SLOPE_CFF = 0) and no MEKE%Kh), the MAX_TR_DIFFUSION_CFL limit and the CHECK_DIFFUSIVE_CFL iteration count. */
+typedef struct mom6cu_tracer_hor_diff_cs {
+  double KhTr, KhTr_min, KhTr_max, KhTr_passivity_coeff, KhTr_passivity_min, KhTr_Slope_Cff, max_diff_CFL;
+  int check_diffusive_CFL, use_neutral_diffusion, use_hor_bnd_diffusion, Diffuse_ML_interior;
+  int use_variable_mixing, Resoln_scaled_KhTr, use_MEKE_Kh; /* VarMix%use_variable_mixing, VarMix%Resoln_scaled_KhTr, allocated(MEKE%Kh) */
+} mom6cu_tracer_hor_diff_cs;
+/* tracer_hordiff(h, dt, MEKE, VarMix, visc, G, GV, US, CS, Reg, tv)  :119: h 3-D; tr: Reg%Tr(m)%t, ntr 3-D h fields, in/out (the
+ * routine updates their halos itself); conc_underflow: ntr or NULL; Res_fn_h, Rd_dx_h: VarMix 2-D h fields (NULL unless used);
+ * df_x / df_y: Reg%Tr(m)%df_x / df_y, ntr optional 3-D u / v diagnostics (NULL array or NULL entries = not associated). */
+typedef struct mom6cu_tracer_hordiff_args {
+  const double* h;
+  double dt;
+  int ntr;
+  double* const* tr;
+  const double* conc_underflow;
+  const double *Res_fn_h, *Rd_dx_h;
+  double* const* df_x;
+  double* const* df_y;
+} mom6cu_tracer_hordiff_args;
+int mom6cu_tracer_hordiff(mom6cu_ctx* ctx, const mom6cu_tracer_hor_diff_cs* CS, const mom6cu_tracer_hordiff_args* a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,10 @@ class Context {
                           double dt, const double* h_MLD, const double* Rd_dx_h = nullptr) {                         // MOM_mixed_layer_restrat.F90:149
     check(mom6cu_mixedlayer_restrat(h_, &CS, h, uhtr, vhtr, T, S, ustar, dt, h_MLD, Rd_dx_h), "mixedlayer_restrat");
   }
+  int tracer_hordiff(const mom6cu_tracer_hor_diff_cs& CS, const mom6cu_tracer_hordiff_args& a) {                     // MOM_tracer_hor_diff.F90:119
+    check(mom6cu_tracer_hordiff(h_, &CS, &a), "tracer_hordiff");
+    return mom6cu_last_iterations(h_);
+  }
   std::vector<double> mu(const std::vector<double>& sigma, const std::vector<double>& dh) {                          // MOM_mixed_layer_restrat.F90:717
     std::vector<double> out(sigma.size());
     check(mom6cu_mle_mu(h_, (int)sigma.size(), sigma.data(), dh.data(), out.data()), "mu");

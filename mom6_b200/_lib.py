@@ -271,6 +271,20 @@ class MleCS(C.Structure):
                 [("MLD_filtered", C.c_void_p), ("MLD_filtered_slow", C.c_void_p)])
 
 
+class TracerHorDiffCS(C.Structure):
+    """mom6cu_tracer_hor_diff_cs: tracer_hor_diff_CS (src/tracer/MOM_tracer_hor_diff.F90:40-106) + the VarMix switches it reads."""
+    _fields_ = ([(n, C.c_double) for n in ("KhTr", "KhTr_min", "KhTr_max", "KhTr_passivity_coeff", "KhTr_passivity_min", "KhTr_Slope_Cff",
+                                           "max_diff_CFL")] +
+                [(n, C.c_int) for n in ("check_diffusive_CFL", "use_neutral_diffusion", "use_hor_bnd_diffusion", "Diffuse_ML_interior",
+                                        "use_variable_mixing", "Resoln_scaled_KhTr", "use_MEKE_Kh")])
+
+
+class TracerHordiffArgs(C.Structure):
+    """mom6cu_tracer_hordiff_args: the arguments of tracer_hordiff (MOM_tracer_hor_diff.F90:119)."""
+    _fields_ = [("h", C.c_void_p), ("dt", C.c_double), ("ntr", C.c_int), ("tr", C.POINTER(C.c_void_p)), ("conc_underflow", C.c_void_p),
+                ("Res_fn_h", C.c_void_p), ("Rd_dx_h", C.c_void_p), ("df_x", C.POINTER(C.c_void_p)), ("df_y", C.POINTER(C.c_void_p))]
+
+
 class Efp(C.Structure):
     """mom6cu_efp: EFP_type (src/framework/MOM_coms.F90:76-78)."""
     _fields_ = [("v", C.c_int64 * 6)]
@@ -402,6 +416,7 @@ def bind(lib):
     lib.mom6cu_ale_regridding_and_remapping.argtypes = [vp, C.POINTER(AleCS), C.POINTER(DynSplitRK2CS), C.POINTER(AleArgs)]
     lib.mom6cu_mixedlayer_restrat.argtypes = [vp, C.POINTER(MleCS), vp, vp, vp, vp, vp, vp, C.c_double, vp, vp]
     lib.mom6cu_mle_mu.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.mom6cu_tracer_hordiff.argtypes = [vp, C.POINTER(TracerHorDiffCS), C.POINTER(TracerHordiffArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

@@ -374,6 +374,13 @@ def _ctx_methods():
         self._check(self.lib.mom6cu_mle_mu(self._h, sigma.size, _p(sigma), _p(dh), _p(out)))
         return out
 
+    def tracer_hordiff(self, cs, args):
+        """tracer_hordiff, src/tracer/MOM_tracer_hor_diff.F90:119 (the along-surface path); returns the number of iterations made."""
+        keep = []
+        self._check(self.lib.mom6cu_tracer_hordiff(self._h, C.byref(marshal.tracer_hor_diff_cs(cs)), C.byref(marshal.tracer_hordiff_args(args, keep))))
+        return int(self.lib.mom6cu_last_iterations(self._h))
+
+    setattr(Context, "tracer_hordiff", tracer_hordiff)
     for f in (mixedlayer_restrat, mle_mu):
         setattr(Context, f.__name__, f)
     for f in (interpolate_column, ale_remap_interface_vals, ale_remap_vertex_vals, ale_regridding_and_remapping):

@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, AleCS, AleArgs, MleCS, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, AleCS, AleArgs, MleCS, TracerHorDiffCS, TracerHordiffArgs, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
 
 
 def _scalars(struct, d):
@@ -266,3 +266,30 @@ def ale_args(a, keep):
 
 def mle_cs(d, keep):
     return fill_struct(MleCS(), d, keep)
+
+
+def tracer_hor_diff_cs(d):
+    return _scalars(TracerHorDiffCS(), d)
+
+
+def tracer_hordiff_args(a, keep):
+    """a: dict(h, dt, tr=[...], conc_underflow=None, Res_fn_h=None, Rd_dx_h=None, df_x=None, df_y=None); df_x / df_y are lists with
+    None for the tracers whose diagnostic is not associated."""
+    s = TracerHordiffArgs()
+    s.h, s.dt = _addr(a["h"]), float(a["dt"])
+    tr = a["tr"]
+    s.ntr = len(tr)
+    ptrs = (C.c_void_p * max(len(tr), 1))(*[_addr(t) for t in tr])
+    keep.append(ptrs)
+    s.tr = C.cast(ptrs, C.POINTER(C.c_void_p))
+    if a.get("conc_underflow") is not None:
+        cu = np.ascontiguousarray(a["conc_underflow"], dtype=np.float64)
+        keep.append(cu)
+        s.conc_underflow = cu.ctypes.data
+    s.Res_fn_h, s.Rd_dx_h = _addr(a.get("Res_fn_h")), _addr(a.get("Rd_dx_h"))
+    for key in ("df_x", "df_y"):
+        if a.get(key) is not None:
+            p = (C.c_void_p * max(len(tr), 1))(*[_addr(t) for t in a[key]])
+            keep.append(p)
+            setattr(s, key, C.cast(p, C.POINTER(C.c_void_p)))
+    return s

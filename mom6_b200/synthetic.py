@@ -1073,3 +1073,35 @@ def mle_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cycl
     cs, f2 = mle_cs_and_forcing(shp2, seed, eos, **cs_over)
     a = dict(h=np.ascontiguousarray(h), uhtr=uhtr, vhtr=vhtr, T=np.ascontiguousarray(T), S=np.ascontiguousarray(S), dt=dt, **f2)
     return dom, grid, gv, cs, a
+
+
+def hordiff_cs(**over):
+    """tracer_hor_diff_init defaults (MOM_tracer_hor_diff.F90:1630-1778) with a KHTR that matters on a 25 km mesh."""
+    cs = dict(KhTr=2000.0, KhTr_min=0.0, KhTr_max=0.0, KhTr_passivity_coeff=0.0, KhTr_passivity_min=0.5, KhTr_Slope_Cff=0.0, max_diff_CFL=-1.0,
+              check_diffusive_CFL=0, use_neutral_diffusion=0, use_hor_bnd_diffusion=0, Diffuse_ML_interior=0, use_variable_mixing=0,
+              Resoln_scaled_KhTr=0, use_MEKE_Kh=0)
+    cs.update(over)
+    return cs
+
+
+def hordiff_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, ntr=3, dt=7200.0, with_df=False, **cs_over):
+    """tracer_hordiff inputs (MOM_tracer_hor_diff.F90:119): the Z*-like state of dyn_state (vanished layers included), T- and S-like
+    tracers with noise plus random / tiny-valued passive ones, VarMix's Res_fn_h and Rd_dx_h.  Returns dom, grid, gv, cs, args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 1616)
+    h = st["h"]
+    zmid = -(np.cumsum(h, axis=0) - 0.5 * h)
+    tr = [np.ascontiguousarray(20.0 * np.exp(zmid / 1000.0) + 2.0 * r.uniform(-1, 1, size=h.shape)),
+          np.ascontiguousarray(35.0 + 0.5 * r.uniform(-1, 1, size=h.shape))]
+    for m in range(2, ntr):
+        tr.append(np.ascontiguousarray(r.uniform(0, 1, size=h.shape) * 10.0 ** r.integers(-30, 1, size=h.shape)))
+    shp2 = h.shape[1:]
+    a = dict(h=np.ascontiguousarray(h), dt=dt, tr=tr[:ntr], conc_underflow=np.array(([0.0, 0.0] + [1.0e-25] * ntr)[:ntr]),
+             Res_fn_h=np.ascontiguousarray(r.uniform(0, 1, size=shp2)), Rd_dx_h=np.ascontiguousarray(0.2 + 1.5 * r.uniform(0, 1, size=shp2)))
+    if with_df:
+        a["df_x"] = [fidx.new(dom, "u", nk=nk, fill=7.0).a if m != 1 else None for m in range(ntr)]
+        a["df_y"] = [fidx.new(dom, "v", nk=nk, fill=7.0).a if m != 0 else None for m in range(ntr)]
+    return dom, grid, gv, hordiff_cs(**cs_over), a

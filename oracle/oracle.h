@@ -139,6 +139,11 @@ int oracle_mixedlayer_restrat(const mom6cu_domain* d, const mom6cu_grid* G, cons
                               double* uhtr, double* vhtr, const double* T, const double* S, const double* ustar, double dt,
                               const double* h_MLD, const double* Rd_dx_h);
 
+/* tracer_hordiff, the along-surface path (src/tracer/MOM_tracer_hor_diff.F90:119-640): hordiff.cpp.  num_itts (may be NULL) returns
+ * the number of iterations made. */
+int oracle_tracer_hordiff(const mom6cu_domain* d, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_tracer_hor_diff_cs* CS,
+                          const mom6cu_tracer_hordiff_args* a, int* num_itts);
+
 #ifdef __cplusplus
 }
 #endif

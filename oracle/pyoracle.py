@@ -530,3 +530,18 @@ def mixedlayer_restrat(dom, grid, gv, cs, h, uhtr, vhtr, T, S, ustar, dt, h_MLD,
     if rc != 0:
         raise RuntimeError(f"oracle_mixedlayer_restrat: FATAL {rc}")
     return rc
+
+
+# ---- tracer_hordiff (hordiff.cpp)
+def tracer_hordiff(dom, grid, gv, cs, a):
+    """oracle_tracer_hordiff: tracer_hordiff (MOM_tracer_hor_diff.F90:119), the along-surface path; returns the iterations made."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); c = marshal.tracer_hor_diff_cs(cs); st = marshal.tracer_hordiff_args(a, keep)
+    it = C.c_int(0)
+    lib.oracle_tracer_hordiff.argtypes = [C.c_void_p] * 6
+    rc = lib.oracle_tracer_hordiff(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(st), C.byref(it))
+    if rc:
+        raise RuntimeError(f"oracle_tracer_hordiff: FATAL {rc}")
+    return it.value

@@ -143,3 +143,25 @@ def test_oracle_ale_regridding_and_remapping_is_rotation_invariant(oracle):
     for k in ("diffu", "diffv", "CAu_pred", "CAv_pred", "u_av", "v_av"):
         assert np.array_equal(_inner(dom, ref_cs[k], ST[k]), _inner(dom, csb[k], ST[k])), k
     assert not np.array_equal(ref_a["h"], a["h"]) and aler["regridCS"]["old_grid_weight"] == ref_ale["regridCS"]["old_grid_weight"]
+
+
+@pytest.mark.parametrize("kw", [dict(KhTr=5.0e4, check_diffusive_CFL=1, with_df=True),
+                                dict(use_variable_mixing=1, Resoln_scaled_KhTr=1, KhTr_max=1500.0, KhTr_min=100.0, KhTr_passivity_coeff=2.0)])
+def test_oracle_tracer_hordiff_is_rotation_invariant(oracle, kw):
+    dom, grid, gv, cs, a = synthetic.hordiff_inputs(20, 14, 5, land_blocks=2, **kw)
+    ref = _copy(a)
+    n = oracle.tracer_hordiff(dom, grid, gv, cs, ref)
+    ar = R.rotate_fields(a, keep=("conc_underflow", "df_x", "df_y"))
+    if a.get("df_x"):                                              # flux diagnostics: (df_x, df_y) is a vector
+        ar["df_x"] = [None if f is None else -R.rot(f) for f in a["df_y"]]
+        ar["df_y"] = [None if f is None else R.rot(f) for f in a["df_x"]]
+    assert oracle.tracer_hordiff(R.rotate_domain(dom), R.rotate_grid(grid), gv, cs, ar) == n
+    for m in range(len(a["tr"])):
+        assert np.array_equal(_inner(dom, ref["tr"][m]), _inner(dom, R.unrot(ar["tr"][m]))), m
+    if a.get("df_x"):
+        for m in range(len(a["tr"])):
+            if ref["df_x"][m] is not None:
+                assert np.array_equal(_inner(dom, ref["df_x"][m], "u"), _inner(dom, R.unrot(ar["df_y"][m]), "u")), m
+            if ref["df_y"][m] is not None:
+                assert np.array_equal(_inner(dom, ref["df_y"][m], "v"), _inner(dom, -R.unrot(ar["df_x"][m]), "v")), m
+    assert not np.array_equal(ref["tr"][0], a["tr"][0])
