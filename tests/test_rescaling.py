@@ -1,0 +1,149 @@
+"""Power-of-2 dimensional rescaling -- the reference's `dim` regression tests (.testing test.dim.t / .l / .h / .z: T_RESCALE_POWER,
+L_RESCALE_POWER, H_RESCALE_POWER, Z_RESCALE_POWER must reproduce ocean.stats bit for bit; src/framework/MOM_unit_scaling.F90)
+re-expressed on the inputs of the hot path (tests/rescale.py): every dimensional input, metric and parameter of a stage is multiplied
+by the power of two its dimension [T^a L^b H^c Z^d] implies, the oracle is run on the rescaled problem and its answers, scaled back,
+must equal the un-scaled answers bit for bit.  A restatement that dropped a unit-conversion factor, mixed H with Z, or carries a
+dimensional constant of the wrong units cannot pass.  (the last of the substitute pins.)  PressureForce_FV is not covered:
+its analytic Wright integrals are restated without the reference's rho_scale / pres_scale arguments (oracle/pgf.cpp:113)."""
+import numpy as np
+import pytest
+
+import rescale as RS
+from mom6_b200 import fidx, synthetic
+
+POWERS = [(3, 0, 0, 0), (0, 5, 0, 0), (0, 0, -4, 0), (0, 0, 0, 6), (-2, 3, 7, 1)]
+
+
+def _copy(x):
+    if isinstance(x, np.ndarray):
+        return x.copy()
+    if isinstance(x, dict):
+        return {k: _copy(v) for k, v in x.items()}
+    if isinstance(x, list):
+        return [_copy(v) for v in x]
+    return x
+
+
+def _same(a, b):
+    if isinstance(a, dict):
+        return all(_same(v, b[k]) for k, v in a.items())
+    if isinstance(a, list):
+        return all(_same(x, y) for x, y in zip(a, b))
+    if isinstance(a, np.ndarray):
+        return np.array_equal(a, b)
+    return True
+
+
+def _grids(grid, gv, p):
+    return RS.scale(grid, RS.DIMS_GRID, p), RS.scale(gv, RS.DIMS_GV, p)
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_continuity(oracle, p):
+    for cs_over in (None, dict(monotonic=1), dict(simple_2nd=1), dict(vol_CFL=1, aggress_adjust=1)):
+        dom, grid, gv, cs, a = synthetic.continuity_inputs(20, 14, 5, land_blocks=2, cs_over=cs_over)
+        ref = _copy(a); oracle.continuity(dom, grid, gv, cs, ref)
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.CONT, p)
+        oracle.continuity(dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.CONT_CS, cs), p), s)
+        assert _same(ref, RS.scale(s, RS.CONT, p, inverse=True)), (p, cs_over)
+        assert np.abs(ref["uh"]).max() > 0
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_coradcalc(oracle, p):
+    for over in (dict(), dict(Coriolis_Scheme=2), dict(Coriolis_Scheme=3), dict(Coriolis_Scheme=5), dict(Coriolis_Scheme=6), dict(bound_Coriolis=1),
+                 dict(KE_Scheme=11), dict(Coriolis_En_Dis=1)):
+        dom, grid, gv, cs, a = synthetic.coradcalc_inputs(20, 14, 5, land_blocks=2, cs_over=over, diags=True, por=True)
+        ref = _copy(a); oracle.coradcalc(dom, grid, gv, cs, ref)
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.CORAD, p)
+        oracle.coradcalc(dom, gs, gvs, cs, s, us=RS.unit_scale(p))
+        assert _same(ref, RS.scale(s, RS.CORAD, p, inverse=True)), (p, over)
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_horizontal_viscosity(oracle, p):
+    for kw in (dict(), dict(Laplacian=True, Smagorinsky_Kh=True, Kh=500.0), dict(Smagorinsky_Ah=False, Ah=1e11), dict(cont_thick=True),
+               dict(Re_Ah=10.0), dict(better_bound_Ah=False)):
+        dom, grid, gv, cs, a = synthetic.hor_visc_inputs(20, 14, 5, land_blocks=2, **kw)
+        ref = _copy(a); oracle.horizontal_viscosity(dom, grid, gv, cs, ref)
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.HORVISC, p)
+        oracle.horizontal_viscosity(dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.HORVISC_CS, cs), p), s)
+        assert _same(ref, RS.scale(s, RS.HORVISC, p, inverse=True)), (p, kw)
+        assert np.abs(ref["diffu"]).max() > 0
+
+
+def _vertvisc_family(oracle, dom, grid, gv, cs, coef, sol, us=None):
+    nk = dom.nk
+    out = dict(a_u=fidx.new(dom, "u", nk=nk + 1).a, a_v=fidx.new(dom, "v", nk=nk + 1).a, h_u=fidx.new(dom, "u", nk=nk).a, h_v=fidx.new(dom, "v", nk=nk).a,
+               visc_rem_u=fidx.new(dom, "u", nk=nk).a, visc_rem_v=fidx.new(dom, "v", nk=nk).a)
+    oracle.vertvisc_coef(dom, grid, gv, cs, coef, out["a_u"], out["a_v"], out["h_u"], out["h_v"], us=us)
+    oracle.vertvisc(dom, grid, gv, cs, sol, out["a_u"], out["a_v"], out["h_u"], out["h_v"])
+    oracle.vertvisc_remnant(dom, grid, cs, out["visc_rem_u"], out["visc_rem_v"], sol["dt"], out["a_u"], out["a_v"], out["h_u"], out["h_v"],
+                            sol.get("Ray_u"), sol.get("Ray_v"))
+    return out
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_vertvisc_family(oracle, p):
+    for kw in (dict(), dict(harmonic_visc=1), dict(bottomdraglaw=0), dict(Kv_extra_bbl=1e-3), dict(Kvml_invZ2=1e-2), dict(fixed_LOTW_ML=1),
+               dict(apply_LOTW_floor=1), dict(direct_stress=1), dict(with_Ray=True, with_Bu=True)):
+        dom, grid, gv, cs, coef, sol = synthetic.vertvisc_inputs(20, 14, 6, land_blocks=2, **kw)
+        c0, s0 = _copy(coef), _copy(sol)
+        r0 = _vertvisc_family(oracle, dom, grid, gv, cs, c0, s0)
+        gs, gvs = _grids(grid, gv, p)
+        s1 = RS.scale(sol, RS.VERTVISC, p)
+        r1 = _vertvisc_family(oracle, dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.VERTVISC_CS, cs), p), RS.scale(coef, RS.VERTVISC_COEF, p), s1,
+                              us=RS.unit_scale(p))
+        assert _same(r0, RS.scale(r1, RS.VERTVISC_OUT, p, inverse=True)), (p, kw)
+        assert _same(s0, RS.scale(s1, RS.VERTVISC, p, inverse=True)), (p, kw)
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_btstep(oracle, p):
+    for kw in (dict(), dict(BT_project_velocity=1), dict(bound_BT_corr=1), dict(Sadourny=0), dict(strong_drag=1), dict(adjust_BT_cont=1)):
+        dom, grid, gv, cs, a = synthetic.btstep_inputs(20, 14, 5, whalo=6, land_blocks=2, **kw)
+        dcs = RS.with_flags(RS.BTSTEP_CS, cs)
+        c0, a0 = _copy(cs), _copy(a); oracle.btstep(dom, grid, gv, c0, a0)
+        gs, gvs = _grids(grid, gv, p)
+        c1, a1 = RS.scale(cs, dcs, p), RS.scale(a, RS.BTSTEP, p)
+        oracle.btstep(dom, gs, gvs, c1, a1)
+        assert _same(a0, RS.scale(a1, RS.BTSTEP, p, inverse=True)), (p, kw)
+        assert _same(c0, RS.scale(c1, dcs, p, inverse=True)), (p, kw)
+        assert np.abs(a0["accel_layer_u"]).max() > 0 and np.abs(a0["eta_out"] - a["eta_in"]).max() > 0
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_tracer_advection_and_diffusion(oracle, p):
+    for scheme in (0, 1, 2):
+        dom, grid, gv, cs, a = synthetic.advect_inputs(20, 14, 5, land_blocks=2, cfl=2.5, scheme=scheme, ntr=3)
+        ref = _copy(a); n = oracle.advect_tracer(dom, grid, gv, cs, ref)
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.ADVECT, p)
+        assert oracle.advect_tracer(dom, gs, gvs, RS.scale(cs, RS.ADVECT_CS, p), s) == n
+        assert _same(ref["tr"], s["tr"]), (p, scheme)
+    for kw in (dict(KhTr=5.0e4, check_diffusive_CFL=1, with_df=True), dict(KhTr=8.0e4, max_diff_CFL=2.5),
+               dict(use_variable_mixing=1, Resoln_scaled_KhTr=1, KhTr_max=1500.0, KhTr_min=100.0, KhTr_passivity_coeff=2.0)):
+        dom, grid, gv, cs, a = synthetic.hordiff_inputs(20, 14, 5, land_blocks=2, **kw)
+        ref = _copy(a); n = oracle.tracer_hordiff(dom, grid, gv, cs, ref)
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.HORDIFF, p)
+        assert oracle.tracer_hordiff(dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.HORDIFF_CS, cs), p), s) == n
+        assert _same(ref, RS.scale(s, RS.HORDIFF, p, inverse=True)), (p, kw)
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_mixedlayer_restrat(oracle, p):
+    for kw in (dict(), dict(MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, land_blocks=2), dict(front_length=0.0, ml_restrat_coef=60.0)):
+        dom, grid, gv, cs, a = synthetic.mle_inputs(20, 14, 24, MLE_MLD_stretch=3.0, **kw)
+        dcs = RS.with_flags(RS.MLE_CS, cs)
+        c0, a0 = _copy(cs), _copy(a)
+        oracle.mixedlayer_restrat(dom, grid, gv, c0, a0["h"], a0["uhtr"], a0["vhtr"], a0["T"], a0["S"], a0["ustar"], a0["dt"], a0["h_MLD"], a0["Rd_dx_h"])
+        gs, gvs = _grids(grid, gv, p)
+        c1, a1 = RS.scale(cs, dcs, p), RS.scale(a, RS.MLE, p)
+        oracle.mixedlayer_restrat(dom, gs, gvs, c1, a1["h"], a1["uhtr"], a1["vhtr"], a1["T"], a1["S"], a1["ustar"], a1["dt"], a1["h_MLD"], a1["Rd_dx_h"])
+        assert _same(a0, RS.scale(a1, RS.MLE, p, inverse=True)), (p, kw)
+        assert _same(c0, RS.scale(c1, dcs, p, inverse=True)), (p, kw)
+        assert not np.array_equal(a0["h"], a["h"])
