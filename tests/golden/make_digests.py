@@ -64,6 +64,12 @@ def cases():
     dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(44, 40, 8, whalo=6, land_blocks=2, store_CAu=1)
     oracle.step_dyn_split_rk2(dom, grid, gv, css, cs, a)
     out["step_dyn_split_rk2"] = dig(*[inner(dom, a[k]) for k in ("u_inst", "v_inst", "h", "uh", "vh", "eta_av")], inner(dom, cs["eta"]))
+    dom, grid, gv, cs, a = synthetic.mle_inputs(44, 40, 20, land_blocks=2, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5)
+    oracle.mixedlayer_restrat(dom, grid, gv, cs, a["h"], a["uhtr"], a["vhtr"], a["T"], a["S"], a["ustar"], a["dt"], a["h_MLD"], a["Rd_dx_h"])
+    out["mixedlayer_restrat"] = dig(inner(dom, a["h"]), inner(dom, a["uhtr"]), inner(dom, a["vhtr"]), inner(dom, cs["MLD_filtered"]))
+    dom, grid, gv, cs, a = synthetic.hordiff_inputs(44, 40, 8, land_blocks=2, KhTr=5.0e4, check_diffusive_CFL=1)
+    oracle.tracer_hordiff(dom, grid, gv, cs, a)
+    out["tracer_hordiff"] = dig(*[inner(dom, t) for t in a["tr"]])
     return out
 
 

@@ -74,5 +74,12 @@ def test_device_path_matches_committed_digests(ctx_factory):
     ctx.set_cs_pressureforce(css["pressureforce"]); ctx.set_cs_vertvisc(css["vertvisc"])
     ctx.step_dyn_split_rk2(cs, a)
     got["step_dyn_split_rk2"] = dig(*[inner(dom, a[k]) for k in ("u_inst", "v_inst", "h", "uh", "vh", "eta_av")], inner(dom, cs["eta"]))
+    dom, grid, gv, cs, a = synthetic.mle_inputs(44, 40, 20, land_blocks=2, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5)
+    ctx = ctx_factory(dom); ctx.set_grid(grid); ctx.set_vgrid(gv)
+    ctx.mixedlayer_restrat(cs, a["h"], a["uhtr"], a["vhtr"], a["T"], a["S"], a["ustar"], a["dt"], a["h_MLD"], a["Rd_dx_h"])
+    got["mixedlayer_restrat"] = dig(inner(dom, a["h"]), inner(dom, a["uhtr"]), inner(dom, a["vhtr"]), inner(dom, cs["MLD_filtered"]))
+    dom, grid, gv, cs, a = synthetic.hordiff_inputs(44, 40, 8, land_blocks=2, KhTr=5.0e4, check_diffusive_CFL=1)
+    ctx = ctx_factory(dom); ctx.set_grid(grid); ctx.set_vgrid(gv); ctx.tracer_hordiff(cs, a)
+    got["tracer_hordiff"] = dig(*[inner(dom, t) for t in a["tr"]])
     bad = [k for k in want if want[k] != got.get(k)]
     assert not bad, bad
