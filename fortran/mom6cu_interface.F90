@@ -209,6 +209,20 @@ module mom6cu_interface
     integer(c_int) :: ntr
     type(c_ptr)    :: tr, conc_underflow, Res_fn_h, Rd_dx_h, df_x, df_y
   end type mom6cu_tracer_hordiff_args
+  !> thickness_diffuse_CS (src/parameterizations/lateral/MOM_thickness_diffuse.F90:40-131) + the VarMix / MEKE / EOS switches it reads
+  type, bind(C) :: mom6cu_thickness_diffuse_cs
+    real(c_double) :: Khth, Khth_Min, Khth_Max, max_Khth_CFL, slope_max, kappa_smooth, dZ_subroundoff
+    integer(c_int) :: thickness_diffuse, read_khth, detangle_interfaces, interface_Kh, use_FGNV_streamfn, use_stanley_gm, &
+                      use_GME_thickness_diffuse, find_work, use_variable_mixing, Resoln_scaled_KhTh, Depth_scaled_KhTh, &
+                      use_stored_slopes, use_Visbeck, use_QG_Leith_GM, khth_struct, use_MEKE_Kh, EOS_form
+    real(c_double) :: Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp
+  end type mom6cu_thickness_diffuse_cs
+  !> the arguments of thickness_diffuse (:134)
+  type, bind(C) :: mom6cu_thickness_diffuse_args
+    type(c_ptr)    :: h, uhtr, vhtr, T, S, p_surf
+    real(c_double) :: dt
+    type(c_ptr)    :: Res_fn_u, Res_fn_v, uhGM, vhGM
+  end type mom6cu_thickness_diffuse_args
   type, bind(C) :: mom6cu_remapping_cs
     integer(c_int) :: remapping_scheme, boundary_extrapolation, force_bounds_in_subcell, force_bounds_in_target, &
                       om4_remap_via_sub_cells, answer_date
@@ -384,6 +398,11 @@ module mom6cu_interface
       import ; type(c_ptr), value :: ctx
       type(mom6cu_tracer_hor_diff_cs), intent(in) :: CS ; type(mom6cu_tracer_hordiff_args), intent(in) :: a
     end function mom6cu_tracer_hordiff
+    !> thickness_diffuse (src/parameterizations/lateral/MOM_thickness_diffuse.F90:134), called from step_MOM_dynamics (MOM.F90:1388)
+    integer(c_int) function mom6cu_thickness_diffuse(ctx, CS, a) bind(C, name="mom6cu_thickness_diffuse")
+      import ; type(c_ptr), value :: ctx
+      type(mom6cu_thickness_diffuse_cs), intent(in) :: CS ; type(mom6cu_thickness_diffuse_args), intent(in) :: a
+    end function mom6cu_thickness_diffuse
     type(c_ptr) function mom6cu_plane_alloc(ctx, name, nk) bind(C, name="mom6cu_plane_alloc")
       import ; type(c_ptr), value :: ctx ; character(kind=c_char), intent(in) :: name(*) ; integer(c_int), value :: nk
     end function mom6cu_plane_alloc

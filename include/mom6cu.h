@@ -749,6 +749,34 @@ typedef struct mom6cu_tracer_hordiff_args {
 } mom6cu_tracer_hordiff_args;
 int mom6cu_tracer_hordiff(mom6cu_ctx* ctx, const mom6cu_tracer_hor_diff_cs* CS, const mom6cu_tracer_hordiff_args* a);
 
+/* -------------------------------------------------------- thickness_diffuse (the last of the three callers) */
+/* thickness_diffuse_CS, src/parameterizations/lateral/MOM_thickness_diffuse.F90:40-131, plus the VarMix / MEKE switches the routine reads
+ * and the equation of state of tv.  Frozen: the density-gradient path of thickness_diffuse_full (:635-1670) with an equation of state
+ * (LINEAR or WRIGHT), slopes computed here (no USE_STORED_SLOPES), the limited streamfunction of :1138-1160 (no
+ * KHTH_USE_FGNV_STREAMFUNCTION), constant KHTH with the KHTH_MIN / KHTH_MAX / KHTH_MAX_CFL limits and the VarMix resolution function
+ * (no Visbeck / QG-Leith / MEKE / vertical structure / depth scaling), no interface-height diffusivity (KH_ETA_*), no detangling, no
+ * Stanley SGS variance, no GM work diagnostics (MEKE%GM_src, CS%GMwork not allocated), Boussinesq, GV%nkml = 0. */
+typedef struct mom6cu_thickness_diffuse_cs {
+  double Khth, Khth_Min, Khth_Max, max_Khth_CFL, slope_max, kappa_smooth;
+  double dZ_subroundoff; /* GV%dZ_subroundoff */
+  int thickness_diffuse, read_khth, detangle_interfaces, interface_Kh /* Kh_eta_bg > 0 or Kh_eta_vel > 0 */, use_FGNV_streamfn, use_stanley_gm,
+      use_GME_thickness_diffuse, find_work /* allocated(MEKE%GM_src) or allocated(CS%GMwork) or skeb_use_gm */;
+  int use_variable_mixing, Resoln_scaled_KhTh, Depth_scaled_KhTh, use_stored_slopes, use_Visbeck, use_QG_Leith_GM, khth_struct, use_MEKE_Kh;
+  int EOS_form; /* MOM6CU_EOS_LINEAR | MOM6CU_EOS_WRIGHT */
+  double Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp;
+} mom6cu_thickness_diffuse_cs;
+/* thickness_diffuse(h, uhtr, vhtr, tv, dt, G, GV, US, MEKE, VarMix, CDp, CS, STOCH)  :134: h, uhtr, vhtr 3-D in/out (h valid one halo point
+ * out); T, S: tv%T, tv%S (3-D h, one halo point); p_surf: tv%p_surf (2-D h) or NULL; Res_fn_u / Res_fn_v: VarMix 2-D u / v (NULL unless
+ * Resoln_scaled_KhTh); uhGM / vhGM: CDp%uhGM / vhGM, optional 3-D u / v out. */
+typedef struct mom6cu_thickness_diffuse_args {
+  double *h, *uhtr, *vhtr;
+  const double *T, *S, *p_surf;
+  double dt;
+  const double *Res_fn_u, *Res_fn_v;
+  double *uhGM, *vhGM;
+} mom6cu_thickness_diffuse_args;
+int mom6cu_thickness_diffuse(mom6cu_ctx* ctx, const mom6cu_thickness_diffuse_cs* CS, const mom6cu_thickness_diffuse_args* a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,9 @@ class Context {
                           double dt, const double* h_MLD, const double* Rd_dx_h = nullptr) {                         // MOM_mixed_layer_restrat.F90:149
     check(mom6cu_mixedlayer_restrat(h_, &CS, h, uhtr, vhtr, T, S, ustar, dt, h_MLD, Rd_dx_h), "mixedlayer_restrat");
   }
+  void thickness_diffuse(const mom6cu_thickness_diffuse_cs& CS, const mom6cu_thickness_diffuse_args& a) {           // MOM_thickness_diffuse.F90:134
+    check(mom6cu_thickness_diffuse(h_, &CS, &a), "thickness_diffuse");
+  }
   int tracer_hordiff(const mom6cu_tracer_hor_diff_cs& CS, const mom6cu_tracer_hordiff_args& a) {                     // MOM_tracer_hor_diff.F90:119
     check(mom6cu_tracer_hordiff(h_, &CS, &a), "tracer_hordiff");
     return mom6cu_last_iterations(h_);

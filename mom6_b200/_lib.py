@@ -285,6 +285,21 @@ class TracerHordiffArgs(C.Structure):
                 ("Res_fn_h", C.c_void_p), ("Rd_dx_h", C.c_void_p), ("df_x", C.POINTER(C.c_void_p)), ("df_y", C.POINTER(C.c_void_p))]
 
 
+class ThicknessDiffuseCS(C.Structure):
+    """mom6cu_thickness_diffuse_cs: thickness_diffuse_CS (MOM_thickness_diffuse.F90:40-131) + the VarMix / MEKE / EOS switches it reads."""
+    _fields_ = ([(n, C.c_double) for n in ("Khth", "Khth_Min", "Khth_Max", "max_Khth_CFL", "slope_max", "kappa_smooth", "dZ_subroundoff")] +
+                [(n, C.c_int) for n in ("thickness_diffuse", "read_khth", "detangle_interfaces", "interface_Kh", "use_FGNV_streamfn", "use_stanley_gm",
+                                        "use_GME_thickness_diffuse", "find_work", "use_variable_mixing", "Resoln_scaled_KhTh", "Depth_scaled_KhTh",
+                                        "use_stored_slopes", "use_Visbeck", "use_QG_Leith_GM", "khth_struct", "use_MEKE_Kh", "EOS_form")] +
+                [(n, C.c_double) for n in ("Rho_T0_S0", "dRho_dT", "dRho_dS", "dRho_dp")])
+
+
+class ThicknessDiffuseArgs(C.Structure):
+    """mom6cu_thickness_diffuse_args: the arguments of thickness_diffuse (MOM_thickness_diffuse.F90:134)."""
+    _fields_ = [("h", C.c_void_p), ("uhtr", C.c_void_p), ("vhtr", C.c_void_p), ("T", C.c_void_p), ("S", C.c_void_p), ("p_surf", C.c_void_p),
+                ("dt", C.c_double), ("Res_fn_u", C.c_void_p), ("Res_fn_v", C.c_void_p), ("uhGM", C.c_void_p), ("vhGM", C.c_void_p)]
+
+
 class Efp(C.Structure):
     """mom6cu_efp: EFP_type (src/framework/MOM_coms.F90:76-78)."""
     _fields_ = [("v", C.c_int64 * 6)]
@@ -417,6 +432,7 @@ def bind(lib):
     lib.mom6cu_mixedlayer_restrat.argtypes = [vp, C.POINTER(MleCS), vp, vp, vp, vp, vp, vp, C.c_double, vp, vp]
     lib.mom6cu_mle_mu.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.mom6cu_tracer_hordiff.argtypes = [vp, C.POINTER(TracerHorDiffCS), C.POINTER(TracerHordiffArgs)]
+    lib.mom6cu_thickness_diffuse.argtypes = [vp, C.POINTER(ThicknessDiffuseCS), C.POINTER(ThicknessDiffuseArgs)]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

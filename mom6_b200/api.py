@@ -380,6 +380,13 @@ def _ctx_methods():
         self._check(self.lib.mom6cu_tracer_hordiff(self._h, C.byref(marshal.tracer_hor_diff_cs(cs)), C.byref(marshal.tracer_hordiff_args(args, keep))))
         return int(self.lib.mom6cu_last_iterations(self._h))
 
+    def thickness_diffuse(self, cs, args):
+        """thickness_diffuse, src/parameterizations/lateral/MOM_thickness_diffuse.F90:134; h, uhtr, vhtr (and uhGM, vhGM) updated in place."""
+        keep = []
+        return self._check(self.lib.mom6cu_thickness_diffuse(self._h, C.byref(marshal.thickness_diffuse_cs(cs)),
+                                                             C.byref(marshal.thickness_diffuse_args(args, keep))))
+
+    setattr(Context, "thickness_diffuse", thickness_diffuse)
     setattr(Context, "tracer_hordiff", tracer_hordiff)
     for f in (mixedlayer_restrat, mle_mu):
         setattr(Context, f.__name__, f)

@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import (Grid, VGrid, ContinuityCS, ContinuityArgs, BTCont, UnitScale, CoriolisAdvCS, CorAdCalcArgs,
                    HorViscCS, HorViscArgs, BarotropicCS, BtstepArgs, BtcalcArgs, PressureForceCS,
-                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, AleCS, AleArgs, MleCS, TracerHorDiffCS, TracerHordiffArgs, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
+                   PressureForceArgs, RemappingCS, TracerAdvectCS, AdvectTracerArgs, RegriddingCS, VertviscCS, VertviscCoefArgs, VertviscArgs, DynSplitRK2CS, StepDynArgs, SetDtbtArgs, AleCS, AleArgs, MleCS, TracerHorDiffCS, TracerHordiffArgs, ThicknessDiffuseCS, ThicknessDiffuseArgs, Efp, SumOutputCS, EnergyOut, _SO_UNITS, _SO_EFPS, _EO_SCALARS, _EO_SCALARS2, fill_struct)
 
 
 def _scalars(struct, d):
@@ -293,3 +293,12 @@ def tracer_hordiff_args(a, keep):
             keep.append(p)
             setattr(s, key, C.cast(p, C.POINTER(C.c_void_p)))
     return s
+
+
+def thickness_diffuse_cs(d):
+    return _scalars(ThicknessDiffuseCS(), d)
+
+
+def thickness_diffuse_args(a, keep):
+    d = {k: a.get(k) for k, _ in ThicknessDiffuseArgs._fields_}
+    return fill_struct(ThicknessDiffuseArgs(), d, keep)

@@ -1105,3 +1105,40 @@ def hordiff_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, 
         a["df_x"] = [fidx.new(dom, "u", nk=nk, fill=7.0).a if m != 1 else None for m in range(ntr)]
         a["df_y"] = [fidx.new(dom, "v", nk=nk, fill=7.0).a if m != 0 else None for m in range(ntr)]
     return dom, grid, gv, hordiff_cs(**cs_over), a
+
+
+def thickness_diffuse_cs(**over):
+    """thickness_diffuse_init (MOM_thickness_diffuse.F90:2170-2476) as a GM-only ALE run resolves it: KHTH = 600 m2 s-1, KHTH_MAX_CFL = 0.8,
+    KHTH_SLOPE_MAX = 0.01, KD_SMOOTH = 1e-6, the Wright equation of state."""
+    cs = dict(Khth=600.0, Khth_Min=0.0, Khth_Max=0.0, max_Khth_CFL=0.8, slope_max=0.01, kappa_smooth=1.0e-6, dZ_subroundoff=1.0e-30,
+              thickness_diffuse=1, read_khth=0, detangle_interfaces=0, interface_Kh=0, use_FGNV_streamfn=0, use_stanley_gm=0,
+              use_GME_thickness_diffuse=0, find_work=0, use_variable_mixing=0, Resoln_scaled_KhTh=0, Depth_scaled_KhTh=0, use_stored_slopes=0,
+              use_Visbeck=0, use_QG_Leith_GM=0, khth_struct=0, use_MEKE_Kh=0, EOS_form=3, Rho_T0_S0=1000.0, dRho_dT=-0.2, dRho_dS=0.8, dRho_dp=0.0)
+    cs.update(over)
+    return cs
+
+
+def thickness_diffuse_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, cyclic_y=False, dt=900.0, front=2.0, with_p_surf=False,
+                             with_GM=False, **cs_over):
+    """thickness_diffuse inputs (MOM_thickness_diffuse.F90:134): the Z*-like state of dyn_state over the seamount (sloping interfaces near
+    the bottom, vanished layers), T with lateral fronts and noise, S, accumulated transports, VarMix's Res_fn_u / Res_fn_v.  Returns dom,
+    grid, gv, cs, args."""
+    dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y)
+    grid = make_grid(dom, land_blocks, seed)
+    gv = make_vgrid()
+    st = dyn_state(dom, grid, seed)
+    r = rng(seed + 1717)
+    h = st["h"]
+    shp2 = h.shape[1:]
+    zmid = -(np.cumsum(h, axis=0) - 0.5 * h)
+    jj, ii = np.meshgrid(np.arange(shp2[0]), np.arange(shp2[1]), indexing="ij")
+    frontal = np.sin(2 * np.pi * ii / max(ni, 1) * 2.0) * np.cos(2 * np.pi * jj / max(nj, 1) * 3.0)
+    T = 20.0 * np.exp(zmid / 1000.0) + front * frontal[None] * np.exp(zmid / 800.0) + 0.02 * r.uniform(-1, 1, size=h.shape)
+    S = 35.0 + 0.5 * np.exp(zmid / 500.0) + 0.01 * r.uniform(-1, 1, size=h.shape)
+    a = dict(h=np.ascontiguousarray(h), uhtr=np.ascontiguousarray(0.05 * st["u"] * dt * grid["dyCu"][None] * 10.0),
+             vhtr=np.ascontiguousarray(0.05 * st["v"] * dt * grid["dxCv"][None] * 10.0), T=np.ascontiguousarray(T), S=np.ascontiguousarray(S),
+             p_surf=np.ascontiguousarray(1.0e5 + 500.0 * r.uniform(-1, 1, size=shp2)) if with_p_surf else None, dt=dt,
+             Res_fn_u=np.ascontiguousarray(r.uniform(0, 1, size=fidx.new(dom, "u").a.shape)),
+             Res_fn_v=np.ascontiguousarray(r.uniform(0, 1, size=fidx.new(dom, "v").a.shape)),
+             uhGM=fidx.new(dom, "u", nk=nk, fill=7.0).a if with_GM else None, vhGM=fidx.new(dom, "v", nk=nk, fill=7.0).a if with_GM else None)
+    return dom, grid, gv, thickness_diffuse_cs(**cs_over), a

@@ -144,6 +144,11 @@ int oracle_mixedlayer_restrat(const mom6cu_domain* d, const mom6cu_grid* G, cons
 int oracle_tracer_hordiff(const mom6cu_domain* d, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_tracer_hor_diff_cs* CS,
                           const mom6cu_tracer_hordiff_args* a, int* num_itts);
 
+/* thickness_diffuse -> thickness_diffuse_full (MOM_thickness_diffuse.F90:134-1670), find_eta (MOM_interface_heights.F90:48), vert_fill_TS
+ * (MOM_isopycnal_slopes.F90:612), calculate_density_derivs (MOM_EOS_Wright.F90:178, MOM_EOS_linear.F90): thickdiff.cpp. */
+int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
+                             const mom6cu_thickness_diffuse_cs* CS, const mom6cu_thickness_diffuse_args* a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -545,3 +545,18 @@ def tracer_hordiff(dom, grid, gv, cs, a):
     if rc:
         raise RuntimeError(f"oracle_tracer_hordiff: FATAL {rc}")
     return it.value
+
+
+# ---- thickness_diffuse (thickdiff.cpp)
+def thickness_diffuse(dom, grid, gv, cs, a, us=None):
+    """oracle_thickness_diffuse: thickness_diffuse (MOM_thickness_diffuse.F90:134) -> thickness_diffuse_full :635, in place."""
+    from mom6_b200 import marshal
+    lib = load()
+    keep = []
+    g = marshal.grid(grid, keep); v = marshal.vgrid(gv); u = marshal.unit_scale(us or US_ONE)
+    c = marshal.thickness_diffuse_cs(cs); st = marshal.thickness_diffuse_args(a, keep)
+    lib.oracle_thickness_diffuse.argtypes = [C.c_void_p] * 6
+    rc = lib.oracle_thickness_diffuse(C.byref(dom), C.byref(g), C.byref(v), C.byref(u), C.byref(c), C.byref(st))
+    if rc:
+        raise RuntimeError(f"oracle_thickness_diffuse: FATAL {rc}")
+    return rc

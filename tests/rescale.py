@@ -99,6 +99,11 @@ MLE = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, ustar=(-1, 0, 0, 1), d
 MLE_CS = dict(ml_restrat_coef=NONDIM, ml_restrat_coef2=NONDIM, front_length=(0, 1, 0, 0), MLE_MLD_decay_time=TIME, MLE_MLD_decay_time2=TIME,
               MLE_MLD_stretch=NONDIM, MLE_tail_dh=NONDIM, ustar_min=HT, vonKar=NONDIM, MLE_density_diff=None, Rho_T0_S0=None, dRho_dT=None,
               dRho_dS=None, dRho_dp=None, MLD_filtered=THK, MLD_filtered_slow=THK)
+# thickness_diffuse (MOM_thickness_diffuse.F90:134, CS :40-131).  The equation of state takes the pressure in Pa (no EOS%RL2_T2_to_Pa
+# in the restatement), so only the H and Z rescalings leave the interface pressures -- (g_Earth*H_to_RZ)*h -- unchanged.
+THICKDIFF = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, p_surf=NONDIM, dt=TIME, Res_fn_u=NONDIM, Res_fn_v=NONDIM, uhGM=TRANSP, vhGM=TRANSP)
+THICKDIFF_CS = dict(Khth=L2T, Khth_Min=L2T, Khth_Max=L2T, max_Khth_CFL=NONDIM, slope_max=(0, -1, 0, 1), kappa_smooth=HZT, dZ_subroundoff=ZL,
+                    Rho_T0_S0=None, dRho_dT=None, dRho_dS=None, dRho_dp=None)
 
 
 def with_flags(dims, d):

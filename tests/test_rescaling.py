@@ -147,3 +147,16 @@ def test_mixedlayer_restrat(oracle, p):
         assert _same(a0, RS.scale(a1, RS.MLE, p, inverse=True)), (p, kw)
         assert _same(c0, RS.scale(c1, dcs, p, inverse=True)), (p, kw)
         assert not np.array_equal(a0["h"], a["h"])
+
+
+@pytest.mark.parametrize("p", [(0, 0, -4, 0), (0, 0, 0, 6), (0, 0, 7, -3)])
+def test_thickness_diffuse(oracle, p):
+    for kw in (dict(with_GM=True, land_blocks=2), dict(use_variable_mixing=1, Resoln_scaled_KhTh=1, Khth_Max=400.0, Khth_Min=50.0),
+               dict(EOS_form=1, Khth=3000.0, max_Khth_CFL=0.2, kappa_smooth=1.0e-4)):
+        dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(20, 14, 10, **kw)
+        ref = _copy(a); oracle.thickness_diffuse(dom, grid, gv, cs, ref)
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.THICKDIFF, p)
+        oracle.thickness_diffuse(dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.THICKDIFF_CS, cs), p), s, us=RS.unit_scale(p))
+        assert _same(ref, RS.scale(s, RS.THICKDIFF, p, inverse=True)), (p, kw)
+        assert not np.array_equal(ref["h"], a["h"])

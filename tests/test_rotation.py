@@ -165,3 +165,19 @@ def test_oracle_tracer_hordiff_is_rotation_invariant(oracle, kw):
             if ref["df_y"][m] is not None:
                 assert np.array_equal(_inner(dom, ref["df_y"][m], "v"), _inner(dom, -R.unrot(ar["df_x"][m]), "v")), m
     assert not np.array_equal(ref["tr"][0], a["tr"][0])
+
+
+@pytest.mark.parametrize("kw", [dict(with_GM=True, land_blocks=2), dict(use_variable_mixing=1, Resoln_scaled_KhTh=1, Khth_Max=400.0, Khth_Min=50.0, with_p_surf=True),
+                                dict(EOS_form=1, Khth=3000.0, max_Khth_CFL=0.2, kappa_smooth=1.0e-4)])
+def test_oracle_thickness_diffuse_is_rotation_invariant(oracle, kw):
+    dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(20, 14, 10, **kw)
+    VEC, PAIR = R.STEP_VEC + [("uhGM", "vhGM")], R.STEP_PAIR + [("Res_fn_u", "Res_fn_v")]
+    ref = _copy(a)
+    oracle.thickness_diffuse(dom, grid, gv, cs, ref)
+    ar = R.rotate_fields(a, VEC, PAIR)
+    oracle.thickness_diffuse(R.rotate_domain(dom), R.rotate_grid(grid), gv, cs, ar)
+    back = R.unrotate_fields(ar, VEC, PAIR)
+    for k, st in (("h", "h"), ("uhtr", "u"), ("vhtr", "v"), ("uhGM", "u"), ("vhGM", "v")):
+        if ref.get(k) is not None:
+            assert np.array_equal(_inner(dom, ref[k], st), _inner(dom, back[k], st)), k
+    assert not np.array_equal(ref["h"], a["h"])
