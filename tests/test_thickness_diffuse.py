@@ -2,7 +2,7 @@
 isopycnal-height diffusion of step_MOM_dynamics, MOM.F90:1388).  The reference holds no vector for this routine (parity unpinned): CPU
 tests check what the algorithm guarantees on the oracle restatement (no net transport through a face, column thickness kept, thickness
 floor, flat isopycnals at rest, slopes flattened), that the host build of the code the GPU threads run (csrc/thickdiff_column.cuh)
-equals the oracle bit for bit, and tests/test_rotation.py / test_rescaling.py hold its invariances.  GPU: tests/test_zz_thickness_diffuse_gpu.py."""
+equals the oracle bit for bit, and tests/test_rotation.py / test_rescaling.py hold its invariances.  GPU: C ABI == oracle, bit for bit."""
 import ctypes as C
 import os
 import subprocess
@@ -145,3 +145,29 @@ def test_device_column_code_equals_oracle_on_the_host(oracle, td_host, kw):
         got = _run_device_code_on_host(td_host, dom, grid, gv, cs, a)
         _assert_same(dom, ref, got, kw)
         assert not np.array_equal(ref["uhtr"], a["uhtr"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", CASES)
+def test_thickness_diffuse_bitwise(oracle, ctx_factory, kw):
+    for (ni, nj, nk) in ((44, 40, 20), (131, 9, 2), (30, 22, 75)):
+        dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(ni, nj, nk, **kw)
+        ref = _copy(a)
+        oracle.thickness_diffuse(dom, grid, gv, cs, ref)
+        ctx = ctx_factory(dom)
+        ctx.set_grid(grid); ctx.set_vgrid(gv)
+        n0 = ctx.launches
+        ctx.thickness_diffuse(cs, a)
+        assert ctx.launches - n0 >= 4
+        _assert_same(dom, ref, a, kw)
+
+
+@pytest.mark.gpu
+def test_thickness_diffuse_errors(ctx_factory):
+    from mom6_b200.api import Mom6cuError
+    dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(16, 12, 5)
+    ctx = ctx_factory(dom)
+    ctx.set_grid(grid); ctx.set_vgrid(gv)
+    for bad in (dict(use_FGNV_streamfn=1), dict(use_stored_slopes=1), dict(use_MEKE_Kh=1), dict(EOS_form=0), dict(find_work=1)):
+        with pytest.raises(Mom6cuError):
+            ctx.thickness_diffuse(dict(cs, **bad), a)
