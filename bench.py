@@ -223,6 +223,15 @@ def thermo_pass(Context, synthetic, ni, nj, device):
     out["total_ms"] = sum(v for k, v in out.items() if k.endswith("_ms"))
     out["diagnostics"] = diag
     out["mixedlayer_restrat"] = mle
+    # the other two callers of SURVEY 8f row 2 (thickness_diffuse, MOM.F90:1388; tracer_hordiff, MOM.F90:1526), timed by tools/time_callers.py
+    # in a process of its own after this context is closed: an auxiliary leg must never be able to cost the bench line
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_callers.py"), f"{ni},{nj},{NK}", str(device)], capture_output=True,
+                           text=True, timeout=240)
+        out["thickness_diffuse_and_tracer_hordiff"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else \
+            {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as ex:
+        out["thickness_diffuse_and_tracer_hordiff"] = {"error": repr(ex)}
     return out
 
 
