@@ -28,6 +28,9 @@ def scale(d, dims, p, inverse=False):
         if isinstance(v, dict):
             out[k] = scale(v, dims, p, inverse)
             continue
+        if v is None:
+            out[k] = None
+            continue
         dim = dims.get(k, "missing")
         if dim == "missing":
             raise KeyError(f"no dimension recorded for {k}")
@@ -104,6 +107,13 @@ MLE_CS = dict(ml_restrat_coef=NONDIM, ml_restrat_coef2=NONDIM, front_length=(0, 
 THICKDIFF = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, p_surf=NONDIM, dt=TIME, Res_fn_u=NONDIM, Res_fn_v=NONDIM, uhGM=TRANSP, vhGM=TRANSP)
 THICKDIFF_CS = dict(Khth=L2T, Khth_Min=L2T, Khth_Max=L2T, max_Khth_CFL=NONDIM, slope_max=(0, -1, 0, 1), kappa_smooth=HZT, dZ_subroundoff=ZL,
                     Rho_T0_S0=None, dRho_dT=None, dRho_dS=None, dRho_dp=None)
+# set_dtbt (MOM_barotropic.F90:3509-3633)
+SET_DTBT = dict(pbce=(-2, 2, -1, 0), gtot_est=(-2, 2, -1, 0), have_gtot_est=None, eta=THK, SSH_add=ZL, frhatu=NONDIM, frhatv=NONDIM, bathyT=ZL, bebt=NONDIM,
+                G_extra=NONDIM, dtbt_fraction=NONDIM, BT_Coriolis_scale=NONDIM, Z_ref=ZL, Nonlinear_continuity=None, **BT_CONT)
+# ALE_regrid, Z* (MOM_regridding.F90:846-1367): the target resolution is in Z, the thicknesses in H
+REGRID = dict(h=THK, h_new=THK, dzRegrid=THK)
+REGRID_CS = dict(regridding_scheme=None, nk=None, min_thickness=THK, old_grid_weight=NONDIM, depth_of_time_filter_shallow=THK, depth_of_time_filter_deep=THK,
+                 Z_ref=ZL, coordinateResolution=None)
 
 
 def with_flags(dims, d):

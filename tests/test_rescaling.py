@@ -160,3 +160,41 @@ def test_thickness_diffuse(oracle, p):
         oracle.thickness_diffuse(dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.THICKDIFF_CS, cs), p), s, us=RS.unit_scale(p))
         assert _same(ref, RS.scale(s, RS.THICKDIFF, p, inverse=True)), (p, kw)
         assert not np.array_equal(ref["h"], a["h"])
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_set_dtbt(oracle, p):
+    from test_step_dyn import _dtbt_args
+    for mode in ("pbce", "BT_cont", "eta", "gtot"):
+        dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(20, 14, 5, whalo=6, land_blocks=2)
+        oracle.step_dyn_split_rk2(dom, grid, gv, css, cs, a)                     # a step, so that pbce and BT_cont are set
+        args = _dtbt_args(dom, grid, cs, mode)
+        dtbt, dmax = oracle.set_dtbt(dom, grid, gv, args)
+        gs, gvs = _grids(grid, gv, p)
+        dtbt_s, dmax_s = oracle.set_dtbt(dom, gs, gvs, RS.scale(args, RS.SET_DTBT, p), us=RS.unit_scale(p))
+        f = RS.factor(RS.TIME, p)
+        assert (dtbt_s / f, dmax_s / f) == (dtbt, dmax) and dtbt > 0, (p, mode)
+
+
+@pytest.mark.parametrize("p", [(0, 0, -4, 0), (0, 0, 0, 6), (0, 0, 7, -3)])
+def test_ale_regrid_and_remap(oracle, p):
+    """Z* regridding (target resolution in Z, thicknesses in H) and the conservative remap (homogeneous in the thicknesses)."""
+    for kw in (dict(), dict(land_blocks=3, old_grid_weight=0.75, depth_of_time_filter_shallow=200.0, depth_of_time_filter_deep=1000.0), dict(min_thickness=5.0)):
+        dom, grid, gv, cs, a = synthetic.regrid_inputs(20, 14, 8, **kw)
+        ref = _copy(a)
+        assert oracle.ale_regrid(dom, grid, gv, cs, ref["h"], ref["h_new"], ref["dzRegrid"]) == 0
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.REGRID, p)
+        css = RS.scale(cs, RS.REGRID_CS, p)
+        css["coordinateResolution"] = np.ascontiguousarray(cs["coordinateResolution"] * RS.factor(RS.ZL, p))
+        assert oracle.ale_regrid(dom, gs, gvs, css, s["h"], s["h_new"], s["dzRegrid"], us=RS.unit_scale(p)) == 0
+        assert _same(ref, RS.scale(s, RS.REGRID, p, inverse=True)), (p, kw)
+        assert np.abs(ref["dzRegrid"]).max() > 0
+    for scheme in (2, 4, 5):                                                    # PLM, PPM_H4, PPM_IH4
+        dom, grid, cs, a = synthetic.remap_inputs(20, 14, 8, land_blocks=2, remapping_scheme=scheme)
+        f = RS.factor(RS.THK, p)
+        t0, t1 = a["tr"][0].copy(), a["tr"][0].copy()
+        oracle.ale_remap_scalar(dom, grid, cs, a["h_old"], a["h_new"], t0)
+        css = dict(cs, h_neglect=cs["h_neglect"] * f, h_neglect_edge=cs["h_neglect_edge"] * f)
+        oracle.ale_remap_scalar(dom, RS.scale(grid, RS.DIMS_GRID, p), css, np.ascontiguousarray(a["h_old"] * f), np.ascontiguousarray(a["h_new"] * f), t1)
+        assert np.array_equal(t0, t1) and not np.array_equal(t0, a["tr"][0]), (p, scheme)
