@@ -216,12 +216,13 @@ module mom6cu_interface
                       use_GME_thickness_diffuse, find_work, use_variable_mixing, Resoln_scaled_KhTh, Depth_scaled_KhTh, &
                       use_stored_slopes, use_Visbeck, use_QG_Leith_GM, khth_struct, use_MEKE_Kh, EOS_form
     real(c_double) :: Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp
+    real(c_double) :: FGNV_scale, N2_floor, MEKE_KhTh_fac
   end type mom6cu_thickness_diffuse_cs
   !> the arguments of thickness_diffuse (:134)
   type, bind(C) :: mom6cu_thickness_diffuse_args
     type(c_ptr)    :: h, uhtr, vhtr, T, S, p_surf
     real(c_double) :: dt
-    type(c_ptr)    :: Res_fn_u, Res_fn_v, uhGM, vhGM
+    type(c_ptr)    :: Res_fn_u, Res_fn_v, uhGM, vhGM, slope_x, slope_y, cg1, MEKE_Kh
   end type mom6cu_thickness_diffuse_args
   type, bind(C) :: mom6cu_remapping_cs
     integer(c_int) :: remapping_scheme, boundary_extrapolation, force_bounds_in_subcell, force_bounds_in_target, &

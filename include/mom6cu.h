@@ -754,8 +754,11 @@ int mom6cu_tracer_hordiff(mom6cu_ctx* ctx, const mom6cu_tracer_hor_diff_cs* CS, 
  * and the equation of state of tv.  Frozen: the density-gradient path of thickness_diffuse_full (:635-1670) with an equation of state
  * (LINEAR or WRIGHT), slopes computed here (no USE_STORED_SLOPES), the limited streamfunction of :1138-1160 (no
  * KHTH_USE_FGNV_STREAMFUNCTION), constant KHTH with the KHTH_MIN / KHTH_MAX / KHTH_MAX_CFL limits and the VarMix resolution function
- * (no Visbeck / QG-Leith / MEKE / vertical structure / depth scaling), no interface-height diffusivity (KH_ETA_*), no detangling, no
- * Stanley SGS variance, no GM work diagnostics (MEKE%GM_src, CS%GMwork not allocated), Boussinesq, GV%nkml = 0. */
+ * (no Visbeck / QG-Leith / vertical structure / depth scaling), no interface-height diffusivity (KH_ETA_*), no detangling, no
+ * Stanley SGS variance, no GM work diagnostics (MEKE%GM_src, CS%GMwork not allocated), Boussinesq, GV%nkml = 0.  Also supported (the
+ * OM4-style selection): USE_STORED_SLOPES (VarMix%slope_x / slope_y as inputs), KHTH_USE_FGNV_STREAMFUNCTION (the elliptic
+ * streamfunction of Ferrari et al. 2010, :1103-1122 + streamfn_solver :1674; VarMix%cg1 as input) and the MEKE diffusivity
+ * MEKE%KhTh_fac*sqrt(MEKE%Kh(i)*MEKE%Kh(i+1)) (:281-284; MEKE%Kh as input, not MEKE_GEOMETRIC). */
 typedef struct mom6cu_thickness_diffuse_cs {
   double Khth, Khth_Min, Khth_Max, max_Khth_CFL, slope_max, kappa_smooth;
   double dZ_subroundoff; /* GV%dZ_subroundoff */
@@ -764,6 +767,8 @@ typedef struct mom6cu_thickness_diffuse_cs {
   int use_variable_mixing, Resoln_scaled_KhTh, Depth_scaled_KhTh, use_stored_slopes, use_Visbeck, use_QG_Leith_GM, khth_struct, use_MEKE_Kh;
   int EOS_form; /* MOM6CU_EOS_LINEAR | MOM6CU_EOS_WRIGHT */
   double Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp;
+  double FGNV_scale, N2_floor; /* FGNV_FILTER_SCALE; (FGNV_STRAT_FLOOR*OMEGA)**2  (:2314-2341) */
+  double MEKE_KhTh_fac;        /* MEKE%KhTh_fac */
 } mom6cu_thickness_diffuse_cs;
 /* thickness_diffuse(h, uhtr, vhtr, tv, dt, G, GV, US, MEKE, VarMix, CDp, CS, STOCH)  :134: h, uhtr, vhtr 3-D in/out (h valid one halo point
  * out); T, S: tv%T, tv%S (3-D h, one halo point); p_surf: tv%p_surf (2-D h) or NULL; Res_fn_u / Res_fn_v: VarMix 2-D u / v (NULL unless
@@ -774,6 +779,9 @@ typedef struct mom6cu_thickness_diffuse_args {
   double dt;
   const double *Res_fn_u, *Res_fn_v;
   double *uhGM, *vhGM;
+  const double *slope_x, *slope_y; /* VarMix%slope_x / slope_y: 3-D u / v with nk+1 interfaces (use_stored_slopes) */
+  const double *cg1;               /* VarMix%cg1: 2-D h (use_FGNV_streamfn) */
+  const double *MEKE_Kh;           /* MEKE%Kh: 2-D h (use_MEKE_Kh) */
 } mom6cu_thickness_diffuse_args;
 int mom6cu_thickness_diffuse(mom6cu_ctx* ctx, const mom6cu_thickness_diffuse_cs* CS, const mom6cu_thickness_diffuse_args* a);
 

@@ -291,13 +291,14 @@ class ThicknessDiffuseCS(C.Structure):
                 [(n, C.c_int) for n in ("thickness_diffuse", "read_khth", "detangle_interfaces", "interface_Kh", "use_FGNV_streamfn", "use_stanley_gm",
                                         "use_GME_thickness_diffuse", "find_work", "use_variable_mixing", "Resoln_scaled_KhTh", "Depth_scaled_KhTh",
                                         "use_stored_slopes", "use_Visbeck", "use_QG_Leith_GM", "khth_struct", "use_MEKE_Kh", "EOS_form")] +
-                [(n, C.c_double) for n in ("Rho_T0_S0", "dRho_dT", "dRho_dS", "dRho_dp")])
+                [(n, C.c_double) for n in ("Rho_T0_S0", "dRho_dT", "dRho_dS", "dRho_dp", "FGNV_scale", "N2_floor", "MEKE_KhTh_fac")])
 
 
 class ThicknessDiffuseArgs(C.Structure):
     """mom6cu_thickness_diffuse_args: the arguments of thickness_diffuse (MOM_thickness_diffuse.F90:134)."""
     _fields_ = [("h", C.c_void_p), ("uhtr", C.c_void_p), ("vhtr", C.c_void_p), ("T", C.c_void_p), ("S", C.c_void_p), ("p_surf", C.c_void_p),
-                ("dt", C.c_double), ("Res_fn_u", C.c_void_p), ("Res_fn_v", C.c_void_p), ("uhGM", C.c_void_p), ("vhGM", C.c_void_p)]
+                ("dt", C.c_double), ("Res_fn_u", C.c_void_p), ("Res_fn_v", C.c_void_p), ("uhGM", C.c_void_p), ("vhGM", C.c_void_p),
+                ("slope_x", C.c_void_p), ("slope_y", C.c_void_p), ("cg1", C.c_void_p), ("MEKE_Kh", C.c_void_p)]
 
 
 class Efp(C.Structure):

@@ -1113,8 +1113,11 @@ def thickness_diffuse_cs(**over):
     cs = dict(Khth=600.0, Khth_Min=0.0, Khth_Max=0.0, max_Khth_CFL=0.8, slope_max=0.01, kappa_smooth=1.0e-6, dZ_subroundoff=1.0e-30,
               thickness_diffuse=1, read_khth=0, detangle_interfaces=0, interface_Kh=0, use_FGNV_streamfn=0, use_stanley_gm=0,
               use_GME_thickness_diffuse=0, find_work=0, use_variable_mixing=0, Resoln_scaled_KhTh=0, Depth_scaled_KhTh=0, use_stored_slopes=0,
-              use_Visbeck=0, use_QG_Leith_GM=0, khth_struct=0, use_MEKE_Kh=0, EOS_form=3, Rho_T0_S0=1000.0, dRho_dT=-0.2, dRho_dS=0.8, dRho_dp=0.0)
+              use_Visbeck=0, use_QG_Leith_GM=0, khth_struct=0, use_MEKE_Kh=0, EOS_form=3, Rho_T0_S0=1000.0, dRho_dT=-0.2, dRho_dS=0.8, dRho_dp=0.0,
+              FGNV_scale=1.0, N2_floor=0.0, MEKE_KhTh_fac=1.0)
     cs.update(over)
+    if cs["use_FGNV_streamfn"] and "N2_floor" not in over:
+        cs["N2_floor"] = (1.0e-15 * 7.2921e-5) ** 2            # (FGNV_STRAT_FLOOR*OMEGA)**2, MOM_thickness_diffuse.F90:2340-2341
     return cs
 
 
@@ -1140,5 +1143,11 @@ def thickness_diffuse_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cycli
              p_surf=np.ascontiguousarray(1.0e5 + 500.0 * r.uniform(-1, 1, size=shp2)) if with_p_surf else None, dt=dt,
              Res_fn_u=np.ascontiguousarray(r.uniform(0, 1, size=fidx.new(dom, "u").a.shape)),
              Res_fn_v=np.ascontiguousarray(r.uniform(0, 1, size=fidx.new(dom, "v").a.shape)),
-             uhGM=fidx.new(dom, "u", nk=nk, fill=7.0).a if with_GM else None, vhGM=fidx.new(dom, "v", nk=nk, fill=7.0).a if with_GM else None)
+             uhGM=fidx.new(dom, "u", nk=nk, fill=7.0).a if with_GM else None, vhGM=fidx.new(dom, "v", nk=nk, fill=7.0).a if with_GM else None,
+             # VarMix%slope_x / slope_y (calc_isoneutral_slopes: |slope| up to a few 1e-3, zero at the top and bottom interfaces), VarMix%cg1, MEKE%Kh
+             slope_x=np.ascontiguousarray(3.0e-3 * r.uniform(-1, 1, size=(nk + 1,) + fidx.new(dom, "u").a.shape) ** 3),
+             slope_y=np.ascontiguousarray(3.0e-3 * r.uniform(-1, 1, size=(nk + 1,) + fidx.new(dom, "v").a.shape) ** 3),
+             cg1=np.ascontiguousarray(3.0 * r.uniform(0, 1, size=shp2) * (r.uniform(0, 1, size=shp2) > 0.1)),
+             MEKE_Kh=np.ascontiguousarray(1500.0 * r.uniform(0, 1, size=shp2) ** 2))
+    a["slope_x"][0] = 0.0; a["slope_x"][-1] = 0.0; a["slope_y"][0] = 0.0; a["slope_y"][-1] = 0.0
     return dom, grid, gv, thickness_diffuse_cs(**cs_over), a

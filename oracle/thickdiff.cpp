@@ -34,10 +34,11 @@ inline void density_derivs(const mom6cu_thickness_diffuse_cs* E, double T, doubl
 
 extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
                                         const mom6cu_thickness_diffuse_cs* CS, const mom6cu_thickness_diffuse_args* a) {
-  if (CS->read_khth || CS->detangle_interfaces || CS->interface_Kh || CS->use_FGNV_streamfn || CS->use_stanley_gm || CS->use_GME_thickness_diffuse ||
-      CS->find_work || CS->Depth_scaled_KhTh || CS->use_stored_slopes || CS->use_Visbeck || CS->use_QG_Leith_GM || CS->khth_struct || CS->use_MEKE_Kh ||
-      !GV->Boussinesq)
+  if (CS->read_khth || CS->detangle_interfaces || CS->interface_Kh || CS->use_stanley_gm || CS->use_GME_thickness_diffuse ||
+      CS->find_work || CS->Depth_scaled_KhTh || CS->use_Visbeck || CS->use_QG_Leith_GM || CS->khth_struct || !GV->Boussinesq)
     return 3;
+  if ((CS->use_stored_slopes && (!a->slope_x || !a->slope_y)) || (CS->use_MEKE_Kh && !a->MEKE_Kh)) return 2;
+  if (CS->use_FGNV_streamfn && !a->cg1) return 2;  // "cg1 must be associated when using FGNV streamfunction."  :858
   if (CS->EOS_form != MOM6CU_EOS_LINEAR && CS->EOS_form != MOM6CU_EOS_WRIGHT) return 3;
   if (!CS->thickness_diffuse || !(CS->Khth > 0.0 || CS->use_variable_mixing)) return 0;  // :196-198
   if (d->nk < 2 || !(a->dt > 0.0)) return 2;
@@ -50,6 +51,12 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
   V2 p_surf, Res_fn_u, Res_fn_v;
   if (a->p_surf) p_surf = G.H((double*)a->p_surf);
   if (Resoln_scaled) { Res_fn_u = G.U((double*)a->Res_fn_u); Res_fn_v = G.V((double*)a->Res_fn_v); }
+  const bool present_slope = CS->use_stored_slopes != 0, FGNV = CS->use_FGNV_streamfn != 0;
+  V3 slope_x, slope_y;
+  V2 cg1, MEKE_Kh;
+  if (present_slope) { slope_x = G.U3((double*)a->slope_x, nz + 1); slope_y = G.V3_((double*)a->slope_y, nz + 1); }
+  if (FGNV) cg1 = G.H((double*)a->cg1);
+  if (CS->use_MEKE_Kh) MEKE_Kh = G.H((double*)a->MEKE_Kh);
   V3 uhGM, vhGM;
   if (a->uhGM) uhGM = G.U3(a->uhGM);
   if (a->vhGM) vhGM = G.V3_(a->vhGM);
@@ -69,6 +76,7 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
     e(i, j, k) = e(i, j, k + 1) + h(i, j, k) * GV->H_to_Z;
   for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I) {
     Khth_loc_u(I, j) = CS->Khth;
+    if (CS->use_MEKE_Kh) Khth_loc_u(I, j) = Khth_loc_u(I, j) + CS->MEKE_KhTh_fac * std::sqrt(MEKE_Kh(I, j) * MEKE_Kh(I + 1, j));  // :281-284
     if (Resoln_scaled) Khth_loc_u(I, j) = Khth_loc_u(I, j) * Res_fn_u(I, j);
     if (CS->Khth_Max > 0) Khth_loc_u(I, j) = fmax2(CS->Khth_Min, fmin2(Khth_loc_u(I, j), CS->Khth_Max));
     else Khth_loc_u(I, j) = fmax2(CS->Khth_Min, Khth_loc_u(I, j));
@@ -77,6 +85,7 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
   }
   for (int J = js - 1; J <= je; ++J) for (int i = is; i <= ie; ++i) {
     Khth_loc_v(i, J) = CS->Khth;
+    if (CS->use_MEKE_Kh) Khth_loc_v(i, J) = Khth_loc_v(i, J) + CS->MEKE_KhTh_fac * std::sqrt(MEKE_Kh(i, J) * MEKE_Kh(i, J + 1));  // :381-384
     if (Resoln_scaled) Khth_loc_v(i, J) = Khth_loc_v(i, J) * Res_fn_v(i, J);
     if (CS->Khth_Max > 0) Khth_loc_v(i, J) = fmax2(CS->Khth_Min, fmin2(Khth_loc_v(i, J), CS->Khth_Max));
     else Khth_loc_v(i, J) = fmax2(CS->Khth_Min, Khth_loc_v(i, J));
@@ -156,7 +165,26 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
     pres(i, j, k + 1) = pres(i, j, k) + (GV->g_Earth * GV->H_to_RZ) * h(i, j, k);
   }
   A2 uhtot = G.aU(), vhtot = G.aV();
-  std::vector<double> Sfn_unlim(nz + 2), slope2_Ratio(nz + 2);
+  std::vector<double> Sfn_unlim(nz + 2), slope2_Ratio(nz + 2), dzN2(nz + 2), c2_dz(nz + 2), c1s(nz + 2);
+  const double dz_neglect2 = dz_neglect * dz_neglect, N2_floor = CS->N2_floor;
+  // streamfn_solver :1674-1707 on Sfn_unlim(1:nz+1) with c2_h = c2_dz(1:nz), hN2 = dzN2(1:nz+1)
+  auto streamfn_solver = [&]() {
+    Sfn_unlim[1] = 0.;
+    double b_denom = dzN2[2] + c2_dz[1];
+    double beta = 1.0 / (b_denom + c2_dz[2]);
+    double d1 = beta * b_denom;
+    Sfn_unlim[2] = (beta * dzN2[2]) * Sfn_unlim[2];
+    for (int K = 3; K <= nz; ++K) {
+      c1s[K - 1] = beta * c2_dz[K - 1];
+      b_denom = dzN2[K] + d1 * c2_dz[K - 1];
+      beta = 1.0 / (b_denom + c2_dz[K]);
+      d1 = beta * b_denom;
+      Sfn_unlim[K] = beta * (dzN2[K] * Sfn_unlim[K] + c2_dz[K - 1] * Sfn_unlim[K - 1]);
+    }
+    c1s[nz] = beta * c2_dz[nz];
+    Sfn_unlim[nz + 1] = 0.;
+    for (int K = nz; K >= 2; --K) Sfn_unlim[K] = Sfn_unlim[K] + c1s[K] * Sfn_unlim[K + 1];
+  };
 
   // ---- zonal fluxes :913-1229
   for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I) {
@@ -164,7 +192,7 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
     for (int K = nz; K >= 2; --K) {
       const int k = K;
       double drdiA = 0., drdiB = 0., drdkL = 0., drdkR = 0.;
-      if (k >= nk_linear) {  // calc_derivatives
+      if ((k >= nk_linear) && (!present_slope || FGNV)) {  // calc_derivatives :921-922
         const double pres_u = 0.5 * (pres(i, j, K) + pres(i + 1, j, K));
         const double T_u = 0.25 * ((T(i, j, k) + T(i + 1, j, k)) + (T(i, j, k - 1) + T(i + 1, j, k - 1)));
         const double S_u = 0.25 * ((S(i, j, k) + S(i + 1, j, k)) + (S(i, j, k - 1) + S(i + 1, j, k - 1)));
@@ -176,28 +204,41 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
         drdkR = (drho_dT_u * (T(i + 1, j, k) - T(i + 1, j, k - 1)) + drho_dS_u * (S(i + 1, j, k) - S(i + 1, j, k - 1)));
       }
       if (k > nk_linear) {
-        const double hg2L = h(i, j, k - 1) * h(i, j, k) + h_neglect2;
-        const double hg2R = h(i + 1, j, k - 1) * h(i + 1, j, k) + h_neglect2;
-        const double haL = 0.5 * (h(i, j, k - 1) + h(i, j, k)) + h_neglect;
-        const double haR = 0.5 * (h(i + 1, j, k - 1) + h(i + 1, j, k)) + h_neglect;
-        const double dzaL = haL * GV->H_to_Z, dzaR = haR * GV->H_to_Z;
-        const double wtL = hg2L * (haR * dzaR), wtR = hg2R * (haL * dzaL);
-        const double drdz = ((wtL * drdkL) + (wtR * drdkR)) / ((dzaL * wtL) + (dzaR * wtR));
-        const double hg2A = h(i, j, k - 1) * h(i + 1, j, k - 1) + h_neglect2;
-        const double hg2B = h(i, j, k) * h(i + 1, j, k) + h_neglect2;
-        const double haA = 0.5 * (h(i, j, k - 1) + h(i + 1, j, k - 1)) + h_neglect;
-        const double haB = 0.5 * (h(i, j, k) + h(i + 1, j, k)) + h_neglect;
-        (void)G_rho0;  // N2_unlim = drdz*G_rho0 and dzN2_u feed only the FGNV streamfunction and the GM work diagnostics
-        const double wtA = hg2A * haB, wtB = hg2B * haA;
-        const double drdx = ((wtA * drdiA + wtB * drdiB) / (wtA + wtB) - drdz * (e(i, j, K) - e(i + 1, j, K))) * G.IdxCu(I, j);
-        const double mag_grad2 = (US->Z_to_L * drdx) * (US->Z_to_L * drdx) + drdz * drdz;
+        double drdz = 0., hg2A = 0., hg2B = 0., haA = 0., haB = 0.;
+        if (FGNV || !present_slope) {  // :980-1022
+          const double hg2L = h(i, j, k - 1) * h(i, j, k) + h_neglect2;
+          const double hg2R = h(i + 1, j, k - 1) * h(i + 1, j, k) + h_neglect2;
+          const double haL = 0.5 * (h(i, j, k - 1) + h(i, j, k)) + h_neglect;
+          const double haR = 0.5 * (h(i + 1, j, k - 1) + h(i + 1, j, k)) + h_neglect;
+          const double dzaL = haL * GV->H_to_Z, dzaR = haR * GV->H_to_Z;
+          const double wtL = hg2L * (haR * dzaR), wtR = hg2R * (haL * dzaL);
+          drdz = ((wtL * drdkL) + (wtR * drdkR)) / ((dzaL * wtL) + (dzaR * wtR));
+          hg2A = h(i, j, k - 1) * h(i + 1, j, k - 1) + h_neglect2;
+          hg2B = h(i, j, k) * h(i + 1, j, k) + h_neglect2;
+          haA = 0.5 * (h(i, j, k - 1) + h(i + 1, j, k - 1)) + h_neglect;
+          haB = 0.5 * (h(i, j, k) + h(i + 1, j, k)) + h_neglect;
+          const double N2_unlim = drdz * G_rho0;
+          const double dzL1 = GV->H_to_Z * h(i, j, k - 1), dzR1 = GV->H_to_Z * h(i + 1, j, k - 1);  // thickness_to_dz (Boussinesq)
+          const double dzL0 = GV->H_to_Z * h(i, j, k), dzR0 = GV->H_to_Z * h(i + 1, j, k);
+          const double dzg2A = dzL1 * dzR1 + dz_neglect2, dzg2B = dzL0 * dzR0 + dz_neglect2;
+          const double dzaA = 0.5 * (dzL1 + dzR1) + dz_neglect, dzaB = 0.5 * (dzL0 + dzR0) + dz_neglect;
+          dzN2[K] = (0.5 * (dzg2A / dzaA + dzg2B / dzaB)) * fmax2(N2_unlim, N2_floor);
+        }
         double Slope;
-        if (mag_grad2 > 0.0) {
-          Slope = drdx / std::sqrt(mag_grad2);
+        if (present_slope) {
+          Slope = slope_x(I, j, k);
           slope2_Ratio[K] = (Slope * Slope) * I_slope_max2;
         } else {
-          Slope = 0.0;
-          slope2_Ratio[K] = 1.0e20;
+          const double wtA = hg2A * haB, wtB = hg2B * haA;
+          const double drdx = ((wtA * drdiA + wtB * drdiB) / (wtA + wtB) - drdz * (e(i, j, K) - e(i + 1, j, K))) * G.IdxCu(I, j);
+          const double mag_grad2 = (US->Z_to_L * drdx) * (US->Z_to_L * drdx) + drdz * drdz;
+          if (mag_grad2 > 0.0) {
+            Slope = drdx / std::sqrt(mag_grad2);
+            slope2_Ratio[K] = (Slope * Slope) * I_slope_max2;
+          } else {
+            Slope = 0.0;
+            slope2_Ratio[K] = 1.0e20;
+          }
         }
         Slope = (1.0 - int_slope_u(I, j, K)) * Slope + int_slope_u(I, j, K) * ((e(i + 1, j, K) - e(i, j, K)) * G.IdxCu(I, j));
         slope2_Ratio[K] = (1.0 - int_slope_u(I, j, K)) * slope2_Ratio[K];
@@ -212,7 +253,23 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
             Sfn_unlim[K] = Sfn_unlim[K] * ((e(i + 1, j, K) - e(i, j, nz + 1)) / ((e(i + 1, j, K) - e(i + 1, j, K + 1)) + dz_neglect));
         }
       } else {
+        dzN2[K] = N2_floor * dz_neglect;
         Sfn_unlim[K] = 0.;
+      }
+    }
+    if (FGNV) {  // :1103-1122
+      dzN2[1] = 0.; dzN2[nz + 1] = 0.;
+      if (G.mask2dCu(I, j) > 0.) {
+        for (int k = 1; k <= nz; ++k) {
+          const double dzL = GV->H_to_Z * h(i, j, k), dzR = GV->H_to_Z * h(i + 1, j, k);
+          const double dz_harm = fmax2(dz_neglect, 2. * dzL * dzR / ((dzL + dzR) + dz_neglect));
+          const double cg = 0.5 * (cg1(i, j) + cg1(i + 1, j));
+          c2_dz[k] = CS->FGNV_scale * (cg * cg) / dz_harm;
+        }
+        for (int K = 2; K <= nz; ++K) Sfn_unlim[K] = (1. + CS->FGNV_scale) * Sfn_unlim[K];
+        streamfn_solver();
+      } else {
+        for (int K = 2; K <= nz; ++K) Sfn_unlim[K] = 0.;
       }
     }
     uhtot(I, j) = 0.0;
@@ -239,7 +296,7 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
     for (int K = nz; K >= 2; --K) {
       const int k = K;
       double drdjA = 0., drdjB = 0., drdkL = 0., drdkR = 0.;
-      if (k >= nk_linear) {
+      if ((k >= nk_linear) && (!present_slope || FGNV)) {  // calc_derivatives :1243-1244
         const double pres_v = 0.5 * (pres(i, j, K) + pres(i, j + 1, K));
         const double T_v = 0.25 * ((T(i, j, k) + T(i, j + 1, k)) + (T(i, j, k - 1) + T(i, j + 1, k - 1)));
         const double S_v = 0.25 * ((S(i, j, k) + S(i, j + 1, k)) + (S(i, j, k - 1) + S(i, j + 1, k - 1)));
@@ -251,27 +308,41 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
         drdkR = (drho_dT_v * (T(i, j + 1, k) - T(i, j + 1, k - 1)) + drho_dS_v * (S(i, j + 1, k) - S(i, j + 1, k - 1)));
       }
       if (k > nk_linear) {
-        const double hg2L = h(i, j, k - 1) * h(i, j, k) + h_neglect2;
-        const double hg2R = h(i, j + 1, k - 1) * h(i, j + 1, k) + h_neglect2;
-        const double haL = 0.5 * (h(i, j, k - 1) + h(i, j, k)) + h_neglect;
-        const double haR = 0.5 * (h(i, j + 1, k - 1) + h(i, j + 1, k)) + h_neglect;
-        const double dzaL = haL * GV->H_to_Z, dzaR = haR * GV->H_to_Z;
-        const double wtL = hg2L * (haR * dzaR), wtR = hg2R * (haL * dzaL);
-        const double drdz = ((wtL * drdkL) + (wtR * drdkR)) / ((dzaL * wtL) + (dzaR * wtR));
-        const double hg2A = h(i, j, k - 1) * h(i, j + 1, k - 1) + h_neglect2;
-        const double hg2B = h(i, j, k) * h(i, j + 1, k) + h_neglect2;
-        const double haA = 0.5 * (h(i, j, k - 1) + h(i, j + 1, k - 1)) + h_neglect;
-        const double haB = 0.5 * (h(i, j, k) + h(i, j + 1, k)) + h_neglect;
-        const double wtA = hg2A * haB, wtB = hg2B * haA;
-        const double drdy = ((wtA * drdjA + wtB * drdjB) / (wtA + wtB) - drdz * (e(i, j, K) - e(i, j + 1, K))) * G.IdyCv(i, J);
-        const double mag_grad2 = (US->Z_to_L * drdy) * (US->Z_to_L * drdy) + drdz * drdz;
+        double drdz = 0., hg2A = 0., hg2B = 0., haA = 0., haB = 0.;
+        if (FGNV || !present_slope) {  // :1300-1344
+          const double hg2L = h(i, j, k - 1) * h(i, j, k) + h_neglect2;
+          const double hg2R = h(i, j + 1, k - 1) * h(i, j + 1, k) + h_neglect2;
+          const double haL = 0.5 * (h(i, j, k - 1) + h(i, j, k)) + h_neglect;
+          const double haR = 0.5 * (h(i, j + 1, k - 1) + h(i, j + 1, k)) + h_neglect;
+          const double dzaL = haL * GV->H_to_Z, dzaR = haR * GV->H_to_Z;
+          const double wtL = hg2L * (haR * dzaR), wtR = hg2R * (haL * dzaL);
+          drdz = ((wtL * drdkL) + (wtR * drdkR)) / ((dzaL * wtL) + (dzaR * wtR));
+          hg2A = h(i, j, k - 1) * h(i, j + 1, k - 1) + h_neglect2;
+          hg2B = h(i, j, k) * h(i, j + 1, k) + h_neglect2;
+          haA = 0.5 * (h(i, j, k - 1) + h(i, j + 1, k - 1)) + h_neglect;
+          haB = 0.5 * (h(i, j, k) + h(i, j + 1, k)) + h_neglect;
+          const double N2_unlim = drdz * G_rho0;
+          const double dzL1 = GV->H_to_Z * h(i, j, k - 1), dzR1 = GV->H_to_Z * h(i, j + 1, k - 1);
+          const double dzL0 = GV->H_to_Z * h(i, j, k), dzR0 = GV->H_to_Z * h(i, j + 1, k);
+          const double dzg2A = dzL1 * dzR1 + dz_neglect2, dzg2B = dzL0 * dzR0 + dz_neglect2;
+          const double dzaA = 0.5 * (dzL1 + dzR1) + dz_neglect, dzaB = 0.5 * (dzL0 + dzR0) + dz_neglect;
+          dzN2[K] = (0.5 * (dzg2A / dzaA + dzg2B / dzaB)) * fmax2(N2_unlim, N2_floor);
+        }
         double Slope;
-        if (mag_grad2 > 0.0) {
-          Slope = drdy / std::sqrt(mag_grad2);
+        if (present_slope) {
+          Slope = slope_y(i, J, k);
           slope2_Ratio[K] = (Slope * Slope) * I_slope_max2;
         } else {
-          Slope = 0.0;
-          slope2_Ratio[K] = 1.0e20;
+          const double wtA = hg2A * haB, wtB = hg2B * haA;
+          const double drdy = ((wtA * drdjA + wtB * drdjB) / (wtA + wtB) - drdz * (e(i, j, K) - e(i, j + 1, K))) * G.IdyCv(i, J);
+          const double mag_grad2 = (US->Z_to_L * drdy) * (US->Z_to_L * drdy) + drdz * drdz;
+          if (mag_grad2 > 0.0) {
+            Slope = drdy / std::sqrt(mag_grad2);
+            slope2_Ratio[K] = (Slope * Slope) * I_slope_max2;
+          } else {
+            Slope = 0.0;
+            slope2_Ratio[K] = 1.0e20;
+          }
         }
         Slope = (1.0 - int_slope_v(i, J, K)) * Slope + int_slope_v(i, J, K) * ((e(i, j + 1, K) - e(i, j, K)) * G.IdyCv(i, J));
         slope2_Ratio[K] = (1.0 - int_slope_v(i, J, K)) * slope2_Ratio[K];
@@ -286,7 +357,23 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
             Sfn_unlim[K] = Sfn_unlim[K] * ((e(i, j + 1, K) - e(i, j, nz + 1)) / ((e(i, j + 1, K) - e(i, j + 1, K + 1)) + dz_neglect));
         }
       } else {
+        dzN2[K] = N2_floor * dz_neglect;
         Sfn_unlim[K] = 0.;
+      }
+    }
+    if (FGNV) {  // :1423-1442
+      dzN2[1] = 0.; dzN2[nz + 1] = 0.;
+      if (G.mask2dCv(i, J) > 0.) {
+        for (int k = 1; k <= nz; ++k) {
+          const double dzL = GV->H_to_Z * h(i, j, k), dzR = GV->H_to_Z * h(i, j + 1, k);
+          const double dz_harm = fmax2(dz_neglect, 2. * dzL * dzR / ((dzL + dzR) + dz_neglect));
+          const double cg = 0.5 * (cg1(i, j) + cg1(i, j + 1));
+          c2_dz[k] = CS->FGNV_scale * (cg * cg) / dz_harm;
+        }
+        for (int K = 2; K <= nz; ++K) Sfn_unlim[K] = (1. + CS->FGNV_scale) * Sfn_unlim[K];
+        streamfn_solver();
+      } else {
+        for (int K = 2; K <= nz; ++K) Sfn_unlim[K] = 0.;
       }
     }
     vhtot(i, J) = 0.0;

@@ -104,9 +104,10 @@ MLE_CS = dict(ml_restrat_coef=NONDIM, ml_restrat_coef2=NONDIM, front_length=(0, 
               dRho_dS=None, dRho_dp=None, MLD_filtered=THK, MLD_filtered_slow=THK)
 # thickness_diffuse (MOM_thickness_diffuse.F90:134, CS :40-131).  The equation of state takes the pressure in Pa (no EOS%RL2_T2_to_Pa
 # in the restatement), so only the H and Z rescalings leave the interface pressures -- (g_Earth*H_to_RZ)*h -- unchanged.
-THICKDIFF = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, p_surf=NONDIM, dt=TIME, Res_fn_u=NONDIM, Res_fn_v=NONDIM, uhGM=TRANSP, vhGM=TRANSP)
+THICKDIFF = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, p_surf=NONDIM, dt=TIME, Res_fn_u=NONDIM, Res_fn_v=NONDIM, uhGM=TRANSP, vhGM=TRANSP,
+                 slope_x=(0, -1, 0, 1), slope_y=(0, -1, 0, 1), cg1=VEL, MEKE_Kh=L2T)
 THICKDIFF_CS = dict(Khth=L2T, Khth_Min=L2T, Khth_Max=L2T, max_Khth_CFL=NONDIM, slope_max=(0, -1, 0, 1), kappa_smooth=HZT, dZ_subroundoff=ZL,
-                    Rho_T0_S0=None, dRho_dT=None, dRho_dS=None, dRho_dp=None)
+                    Rho_T0_S0=None, dRho_dT=None, dRho_dS=None, dRho_dp=None, FGNV_scale=NONDIM, N2_floor=(-2, 2, 0, -2), MEKE_KhTh_fac=NONDIM)
 # set_dtbt (MOM_barotropic.F90:3509-3633)
 SET_DTBT = dict(pbce=(-2, 2, -1, 0), gtot_est=(-2, 2, -1, 0), have_gtot_est=None, eta=THK, SSH_add=ZL, frhatu=NONDIM, frhatv=NONDIM, bathyT=ZL, bebt=NONDIM,
                 G_extra=NONDIM, dtbt_fraction=NONDIM, BT_Coriolis_scale=NONDIM, Z_ref=ZL, Nonlinear_continuity=None, **BT_CONT)

@@ -76,13 +76,15 @@ def test_tracer_hordiff_sweep(oracle, hd_host):   # noqa: F811
 
 def test_thickness_diffuse_sweep(oracle, td_host):   # noqa: F811
     moved = 0
-    for c, r, g in _draws(303, 40):
+    for c, r, g in _draws(303, 80):
         nk = int(r.choice([2, 3, 8, 40]))
         vm = int(r.integers(2))
         kw = dict(dt=float(r.choice([300.0, 900.0, 7200.0])), front=float(r.uniform(0, 6)), with_p_surf=bool(r.integers(2)), with_GM=bool(r.integers(2)),
                   EOS_form=int(r.choice([1, 3])), Khth=float(r.choice([10.0, 600.0, 5000.0])), Khth_Max=float(r.choice([0.0, 400.0])),
                   Khth_Min=float(r.choice([0.0, 50.0])), max_Khth_CFL=float(r.choice([0.1, 0.8])), slope_max=float(r.choice([1.0e-3, 1.0e-2])),
-                  kappa_smooth=float(r.choice([0.0, 1.0e-6, 1.0e-3])), use_variable_mixing=vm, Resoln_scaled_KhTh=int(r.integers(2)) * vm)
+                  kappa_smooth=float(r.choice([0.0, 1.0e-6, 1.0e-3])), use_variable_mixing=vm, Resoln_scaled_KhTh=int(r.integers(2)) * vm,
+                  use_stored_slopes=int(r.integers(2)), use_FGNV_streamfn=int(r.integers(2)), use_MEKE_Kh=int(r.integers(2)),
+                  FGNV_scale=float(r.choice([0.1, 1.0])))
         dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(g["ni"], g["nj"], nk, halo=g["halo"], seed=g["seed"], land_blocks=g["land_blocks"],
                                                                   cyclic_x=g["cyclic_x"], cyclic_y=g["cyclic_y"], **kw)
         ref = _copy(a)

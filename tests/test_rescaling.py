@@ -152,7 +152,8 @@ def test_mixedlayer_restrat(oracle, p):
 @pytest.mark.parametrize("p", [(0, 0, -4, 0), (0, 0, 0, 6), (0, 0, 7, -3)])
 def test_thickness_diffuse(oracle, p):
     for kw in (dict(with_GM=True, land_blocks=2), dict(use_variable_mixing=1, Resoln_scaled_KhTh=1, Khth_Max=400.0, Khth_Min=50.0),
-               dict(EOS_form=1, Khth=3000.0, max_Khth_CFL=0.2, kappa_smooth=1.0e-4)):
+               dict(EOS_form=1, Khth=3000.0, max_Khth_CFL=0.2, kappa_smooth=1.0e-4), dict(use_stored_slopes=1), dict(use_FGNV_streamfn=1, N2_floor=1.0e-12),
+               dict(use_FGNV_streamfn=1, use_stored_slopes=1, use_MEKE_Kh=1, Khth=0.0, use_variable_mixing=1, Resoln_scaled_KhTh=1)):
         dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(20, 14, 10, **kw)
         ref = _copy(a); oracle.thickness_diffuse(dom, grid, gv, cs, ref)
         gs, gvs = _grids(grid, gv, p)

@@ -168,10 +168,12 @@ def test_oracle_tracer_hordiff_is_rotation_invariant(oracle, kw):
 
 
 @pytest.mark.parametrize("kw", [dict(with_GM=True, land_blocks=2), dict(use_variable_mixing=1, Resoln_scaled_KhTh=1, Khth_Max=400.0, Khth_Min=50.0, with_p_surf=True),
-                                dict(EOS_form=1, Khth=3000.0, max_Khth_CFL=0.2, kappa_smooth=1.0e-4)])
+                                dict(EOS_form=1, Khth=3000.0, max_Khth_CFL=0.2, kappa_smooth=1.0e-4), dict(use_stored_slopes=1, land_blocks=2),
+                                dict(use_FGNV_streamfn=1, with_GM=True, land_blocks=2),
+                                dict(use_FGNV_streamfn=1, use_stored_slopes=1, use_MEKE_Kh=1, Khth=0.0, use_variable_mixing=1, Resoln_scaled_KhTh=1)])
 def test_oracle_thickness_diffuse_is_rotation_invariant(oracle, kw):
     dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(20, 14, 10, **kw)
-    VEC, PAIR = R.STEP_VEC + [("uhGM", "vhGM")], R.STEP_PAIR + [("Res_fn_u", "Res_fn_v")]
+    VEC, PAIR = R.STEP_VEC + [("uhGM", "vhGM"), ("slope_x", "slope_y")], R.STEP_PAIR + [("Res_fn_u", "Res_fn_v")]
     ref = _copy(a)
     oracle.thickness_diffuse(dom, grid, gv, cs, ref)
     ar = R.rotate_fields(a, VEC, PAIR)

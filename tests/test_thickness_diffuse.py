@@ -72,9 +72,11 @@ def test_oracle_flat_stratification_is_at_rest_and_slopes_are_flattened(oracle):
 
 def test_oracle_rejects_options_outside_the_frozen_set(oracle):
     dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(12, 10, 4)
-    for bad in (dict(use_FGNV_streamfn=1), dict(use_stored_slopes=1), dict(use_MEKE_Kh=1), dict(detangle_interfaces=1), dict(EOS_form=0), dict(find_work=1)):
+    for bad in (dict(use_Visbeck=1), dict(interface_Kh=1), dict(khth_struct=1), dict(detangle_interfaces=1), dict(EOS_form=0), dict(find_work=1)):
         with pytest.raises(RuntimeError):
             oracle.thickness_diffuse(dom, grid, gv, dict(cs, **bad), _copy(a))
+    with pytest.raises(RuntimeError):                                              # "cg1 must be associated when using FGNV streamfunction." (:858)
+        oracle.thickness_diffuse(dom, grid, gv, dict(cs, use_FGNV_streamfn=1), dict(_copy(a), cg1=None))
     h0 = a["h"].copy()
     assert oracle.thickness_diffuse(dom, grid, gv, dict(cs, Khth=0.0), a) == 0 and np.array_equal(h0, a["h"])      # nothing to do (:196)
 
@@ -86,7 +88,7 @@ def td_host(tmp_path_factory):
                            os.path.join(ROOT, "tests", "harness", "thickdiff_host.cpp")])
     lib = C.CDLL(so)
     lib.td_host_run.restype = None
-    lib.td_host_run.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong] + [C.c_void_p] * 20
+    lib.td_host_run.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong] + [C.c_void_p] * 26
     return lib
 
 
@@ -110,23 +112,30 @@ def _run_device_code_on_host(lib, dom, grid, gv, cs, a):
     par = np.array([nk, cs["EOS_form"], int(res), int(a["p_surf"] is not None), dt, 0.25 / dt, gv["Angstrom_H"], gv["H_subroundoff"],
                     gv["H_subroundoff"] * gv["H_subroundoff"], cs["dZ_subroundoff"], gv["H_to_Z"], gv["Z_to_H"], gv["g_Earth"] * gv["H_to_RZ"], 1.0,
                     cs["Khth"], cs["Khth_Min"], cs["Khth_Max"], cs["max_Khth_CFL"], 1.0 / (cs["slope_max"] * cs["slope_max"]), kap,
-                    1.0e-16 * np.sqrt(0.5 * kap), cs["dRho_dT"], cs["dRho_dS"]], dtype=np.float64)
+                    1.0e-16 * np.sqrt(0.5 * kap), cs["dRho_dT"], cs["dRho_dS"],
+                    int(cs["use_stored_slopes"]), int(cs["use_FGNV_streamfn"]), int(cs["use_MEKE_Kh"]), gv["g_Earth"] / gv["Rho0"],
+                    cs["dZ_subroundoff"] * cs["dZ_subroundoff"], cs["N2_floor"], cs["FGNV_scale"], cs["MEKE_KhTh_fac"]], dtype=np.float64)
     box = np.array([dom.isc, dom.iec, dom.jsc, dom.jec, dom.isd - 1, dom.jsd - 1], dtype=np.int32)
     F = {k: (None if a[k] is None else _unified(dom, a[k], st)) for k, st in (("h", "h"), ("uhtr", "u"), ("vhtr", "v"), ("T", "h"), ("S", "h"), ("p_surf", "h"),
-                                                                           ("Res_fn_u", "u"), ("Res_fn_v", "v"), ("uhGM", "u"), ("vhGM", "v"))}
+                                                                           ("Res_fn_u", "u"), ("Res_fn_v", "v"), ("uhGM", "u"), ("vhGM", "v"),
+                                                                           ("slope_x", "u"), ("slope_y", "v"), ("cg1", "h"), ("MEKE_Kh", "h"))}
     Gd = {k: _unified(dom, grid[k], st) for k, st in (("areaT", "h"), ("IareaT", "h"), ("bathyT", "h"), ("IdxCu", "u"), ("IdyCu", "u"), ("dy_Cu", "u"),
-                                                      ("IdxCv", "v"), ("IdyCv", "v"), ("dx_Cv", "v"))}
+                                                      ("IdxCv", "v"), ("IdyCv", "v"), ("dx_Cv", "v"), ("mask2dCu", "u"), ("mask2dCv", "v"))}
     nj, ni = Gd["areaT"].shape
-    scratch = np.zeros((3 * (nk + 1) + 6 * nk, nj, ni))
+    scratch = np.zeros((8 * (nk + 1) + 6 * nk, nj, ni))
     lib.td_host_run(p(par), p(box), ni, ni * nj, p(F["h"]), p(F["uhtr"]), p(F["vhtr"]), p(F["T"]), p(F["S"]), p(F["p_surf"]), p(F["Res_fn_u"]),
                     p(F["Res_fn_v"]), p(F["uhGM"]), p(F["vhGM"]), p(Gd["areaT"]), p(Gd["IareaT"]), p(Gd["bathyT"]), p(Gd["IdxCu"]), p(Gd["IdyCu"]),
-                    p(Gd["dy_Cu"]), p(Gd["IdxCv"]), p(Gd["IdyCv"]), p(Gd["dx_Cv"]), p(scratch))
+                    p(Gd["dy_Cu"]), p(Gd["IdxCv"]), p(Gd["IdyCv"]), p(Gd["dx_Cv"]), p(scratch), p(Gd["mask2dCu"]), p(Gd["mask2dCv"]), p(F["slope_x"]),
+                    p(F["slope_y"]), p(F["cg1"]), p(F["MEKE_Kh"]))
     return {k: _from_unified(F[k], st) for k, st in (("h", "h"), ("uhtr", "u"), ("vhtr", "v"), ("uhGM", "u"), ("vhGM", "v")) if F[k] is not None}
 
 
 CASES = [dict(), dict(land_blocks=4, EOS_form=1, with_GM=True), dict(land_blocks=2, cyclic_y=True, with_p_surf=True, Khth=3000.0, max_Khth_CFL=0.2),
          dict(use_variable_mixing=1, Resoln_scaled_KhTh=1, Khth_Max=400.0, Khth_Min=50.0, land_blocks=2), dict(kappa_smooth=0.0, slope_max=0.001, front=6.0),
          dict(dt=7200.0, Khth=2000.0, kappa_smooth=1.0e-4, with_GM=True)]
+# the OM4-style selection: stored slopes, the FGNV streamfunction, the MEKE diffusivity (m6td::face_ext / td_face_ext_kernel)
+EXT_CASES = [dict(use_stored_slopes=1, land_blocks=2), dict(use_FGNV_streamfn=1, land_blocks=3, with_GM=True), dict(use_MEKE_Kh=1, Khth=0.0, use_variable_mixing=1),
+         dict(use_FGNV_streamfn=1, use_stored_slopes=1, use_MEKE_Kh=1, Khth=0.0, use_variable_mixing=1, Resoln_scaled_KhTh=1, FGNV_scale=0.1, cyclic_y=True)]
 
 
 def _assert_same(dom, want, got, kw):
@@ -136,7 +145,7 @@ def _assert_same(dom, want, got, kw):
             assert np.array_equal(want[k].view(np.int64), got[k].view(np.int64)), (k, kw)
 
 
-@pytest.mark.parametrize("kw", CASES)
+@pytest.mark.parametrize("kw", CASES + EXT_CASES)
 def test_device_column_code_equals_oracle_on_the_host(oracle, td_host, kw):
     for (ni, nj, nk) in ((28, 20, 12), (9, 31, 2), (14, 12, 40)):
         dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(ni, nj, nk, **kw)
@@ -168,6 +177,6 @@ def test_thickness_diffuse_errors(ctx_factory):
     dom, grid, gv, cs, a = synthetic.thickness_diffuse_inputs(16, 12, 5)
     ctx = ctx_factory(dom)
     ctx.set_grid(grid); ctx.set_vgrid(gv)
-    for bad in (dict(use_FGNV_streamfn=1), dict(use_stored_slopes=1), dict(use_MEKE_Kh=1), dict(EOS_form=0), dict(find_work=1)):
+    for bad in (dict(use_Visbeck=1), dict(interface_Kh=1), dict(khth_struct=1), dict(EOS_form=0), dict(find_work=1)):
         with pytest.raises(Mom6cuError):
             ctx.thickness_diffuse(dict(cs, **bad), a)
