@@ -404,6 +404,11 @@ module mom6cu_interface
       import ; type(c_ptr), value :: ctx
       type(mom6cu_thickness_diffuse_cs), intent(in) :: CS ; type(mom6cu_thickness_diffuse_args), intent(in) :: a
     end function mom6cu_thickness_diffuse
+    !> pass_var / pass_vector / do_group_pass (src/framework/MOM_domains.F90) for fields that live on the device
+    integer(c_int) function mom6cu_do_group_pass(ctx, nfields, fields, stagger, nk) bind(C, name="mom6cu_do_group_pass")
+      import ; type(c_ptr), value :: ctx ; integer(c_int), value :: nfields, nk
+      type(c_ptr), intent(in) :: fields(*) ; integer(c_int), intent(in) :: stagger(*)
+    end function mom6cu_do_group_pass
     type(c_ptr) function mom6cu_plane_alloc(ctx, name, nk) bind(C, name="mom6cu_plane_alloc")
       import ; type(c_ptr), value :: ctx ; character(kind=c_char), intent(in) :: name(*) ; integer(c_int), value :: nk
     end function mom6cu_plane_alloc

@@ -396,6 +396,12 @@ int mom6cu_advect_tracer(mom6cu_ctx* ctx, const mom6cu_tracer_advect_cs* CS, con
 int mom6cu_comm_unique_id(void* out, int nbytes);
 int mom6cu_comm_init(mom6cu_ctx* ctx, const void* id_bytes, int nbytes, int rank, int nranks);
 int mom6cu_comm_destroy(mom6cu_ctx* ctx);
+/* pass_var / pass_vector / do_group_pass (src/framework/MOM_domains.F90; the calls that follow thickness_diffuse and mixedlayer_restrat in
+ * step_MOM_dynamics, MOM.F90:1396,1427) as an entry of its own, for a caller that chains the entries on resident fields: the halos of
+ * nfields fields of nk levels each (host arrays or resident planes; stagger[f] = 0 h, 1 u, 2 v, 3 q) are updated out to the full width
+ * of G's memory domain -- reentrant wrap on one tile, NCCL send/recv between tiles, closed edges untouched.  Vector components
+ * are passed like scalars (no tripolar fold or other sign-changing boundary is implemented). */
+int mom6cu_do_group_pass(mom6cu_ctx* ctx, int nfields, double* const* fields, const int* stagger, int nk);
 /* Host-only planning of one neighbour message (no device needed): for direction
  * dir in 0..7 = {E,W,N,S,NE,SW,SE,NW} returns the peer rank (-1: closed edge) and the
  * inclusive Fortran index boxes {i0,i1,j0,j1} of what is sent (from the computational

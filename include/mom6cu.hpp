@@ -134,6 +134,10 @@ class Context {
     return out;
   }
 
+  void do_group_pass(const std::vector<double*>& fields, const std::vector<int>& stagger, int nk) {                   // MOM_domains.F90 pass_var / do_group_pass
+    check(mom6cu_do_group_pass(h_, (int)fields.size(), fields.data(), stagger.data(), nk), "do_group_pass");
+  }
+
   // ---- the answer-reproducibility metric
   void write_energy(mom6cu_sum_output_cs& CS, const double* u, const double* v, const double* h, const double* T, const double* S,
                     mom6cu_energy_out& out) {                                                                        // MOM_sum_output.F90:321

@@ -434,6 +434,7 @@ def bind(lib):
     lib.mom6cu_mle_mu.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.mom6cu_tracer_hordiff.argtypes = [vp, C.POINTER(TracerHorDiffCS), C.POINTER(TracerHordiffArgs)]
     lib.mom6cu_thickness_diffuse.argtypes = [vp, C.POINTER(ThicknessDiffuseCS), C.POINTER(ThicknessDiffuseArgs)]
+    lib.mom6cu_do_group_pass.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
     lib.mom6cu_comm_unique_id.argtypes = [C.c_char_p, C.c_int]
     lib.mom6cu_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_comm_destroy.argtypes = [vp]

@@ -386,6 +386,14 @@ def _ctx_methods():
         return self._check(self.lib.mom6cu_thickness_diffuse(self._h, C.byref(marshal.thickness_diffuse_cs(cs)),
                                                              C.byref(marshal.thickness_diffuse_args(args, keep))))
 
+    def do_group_pass(self, fields, staggers, nk):
+        """pass_var / pass_vector / do_group_pass (MOM_domains.F90) on host arrays or resident planes; staggers: 'h', 'u', 'v', 'q' per field."""
+        n = len(fields)
+        ptrs = (C.c_void_p * max(n, 1))(*[_p(f) for f in fields])
+        st = (C.c_int * max(n, 1))(*[{"h": 0, "u": 1, "v": 2, "q": 3}[s] for s in staggers])
+        return self._check(self.lib.mom6cu_do_group_pass(self._h, n, ptrs, st, int(nk)))
+
+    setattr(Context, "do_group_pass", do_group_pass)
     setattr(Context, "thickness_diffuse", thickness_diffuse)
     setattr(Context, "tracer_hordiff", tracer_hordiff)
     for f in (mixedlayer_restrat, mle_mu):

@@ -96,3 +96,24 @@ int m6_bt_halo_exchange(mom6cu_ctx* c, double* eta, double* ubt, double* vbt) {
   const int st[3] = {ST_H, ST_U, ST_V};
   return m6_halo_update(c, f, st, 3, 1, 1);
 }
+
+// pass_var / pass_vector / do_group_pass for callers that chain resident entries (include/mom6cu.h)
+extern "C" int mom6cu_do_group_pass(mom6cu_ctx* c, int nfields, double* const* fields, const int* stagger, int nk) {
+  if (!c || nfields < 0 || nk < 1 || (nfields > 0 && (!fields || !stagger))) return MOM6CU_ERR_BAD_ARG;
+  if (nfields == 0) return 0;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  Stager S(c, "pass.");
+  std::vector<double*> dev(nfields);
+  std::vector<int> st(nfields);
+  int rc;
+  for (int f = 0; f < nfields; ++f) {
+    if (!fields[f] || stagger[f] < 0 || stagger[f] > 3) return c->fail(MOM6CU_ERR_BAD_ARG, "do_group_pass: field %d is null or has an invalid stagger", f);
+    st[f] = stagger[f];
+    char nm[32];
+    snprintf(nm, sizeof nm, "f%d", f);
+    if ((rc = S.io(fields[f], st[f], 0, nk, nm, &dev[f]))) return rc;
+  }
+  if ((rc = S.begin())) return rc;
+  if ((rc = m6_halo_update(c, dev.data(), st.data(), nfields, 0, nk))) return rc;
+  return S.finish();
+}
