@@ -201,13 +201,14 @@ module mom6cu_interface
     real(c_double) :: KhTr, KhTr_min, KhTr_max, KhTr_passivity_coeff, KhTr_passivity_min, KhTr_Slope_Cff, max_diff_CFL
     integer(c_int) :: check_diffusive_CFL, use_neutral_diffusion, use_hor_bnd_diffusion, Diffuse_ML_interior, &
                       use_variable_mixing, Resoln_scaled_KhTr, use_MEKE_Kh
+    real(c_double) :: MEKE_KhTr_fac
   end type mom6cu_tracer_hor_diff_cs
   !> the arguments of tracer_hordiff (:119); tr, df_x, df_y are arrays of c_ptr (Reg%Tr(m)%t, %df_x, %df_y)
   type, bind(C) :: mom6cu_tracer_hordiff_args
     type(c_ptr)    :: h
     real(c_double) :: dt
     integer(c_int) :: ntr
-    type(c_ptr)    :: tr, conc_underflow, Res_fn_h, Rd_dx_h, df_x, df_y
+    type(c_ptr)    :: tr, conc_underflow, Res_fn_h, Rd_dx_h, df_x, df_y, L2u, SN_u, L2v, SN_v, MEKE_Kh
   end type mom6cu_tracer_hordiff_args
   !> thickness_diffuse_CS (src/parameterizations/lateral/MOM_thickness_diffuse.F90:40-131) + the VarMix / MEKE / EOS switches it reads
   type, bind(C) :: mom6cu_thickness_diffuse_cs

@@ -733,12 +733,14 @@ int mom6cu_mle_mu(mom6cu_ctx* ctx, int n, const double* sigma, const double* dh,
 /* ----------------------------------------------------------------- tracer_hordiff (the tracer-step caller) */
 /* tracer_hor_diff_CS, src/tracer/MOM_tracer_hor_diff.F90:40-106, and the VarMix switches tracer_hordiff reads (:163-169).  Frozen: the
  * along-surface path (:537-604; USE_NEUTRAL_DIFFUSION, USE_HORIZONTAL_BOUNDARY_DIFFUSION and DIFFUSE_ML_TO_INTERIOR off), online
- * diffusivities (:203-340: constant KhTr, or with VarMix the KhTr_max / resolution-function / KhTr_min / passivity chain; no Eady
- * growth-rate term (KHTR_SLOPE_CFF = 0) and no MEKE%Kh), the MAX_TR_DIFFUSION_CFL limit and the CHECK_DIFFUSIVE_CFL iteration count. */
+ * diffusivities (:203-340: constant KhTr, or with VarMix the Eady growth-rate term KhTr_Slope_Cff*L2u*SN_u, MEKE%KhTr_fac*sqrt(Kh Kh) and
+ * the KhTr_max / resolution-function / KhTr_min / passivity chain), the MAX_TR_DIFFUSION_CFL limit and the CHECK_DIFFUSIVE_CFL iteration
+ * count. */
 typedef struct mom6cu_tracer_hor_diff_cs {
   double KhTr, KhTr_min, KhTr_max, KhTr_passivity_coeff, KhTr_passivity_min, KhTr_Slope_Cff, max_diff_CFL;
   int check_diffusive_CFL, use_neutral_diffusion, use_hor_bnd_diffusion, Diffuse_ML_interior;
   int use_variable_mixing, Resoln_scaled_KhTr, use_MEKE_Kh; /* VarMix%use_variable_mixing, VarMix%Resoln_scaled_KhTr, allocated(MEKE%Kh) */
+  double MEKE_KhTr_fac;                                     /* MEKE%KhTr_fac */
 } mom6cu_tracer_hor_diff_cs;
 /* tracer_hordiff(h, dt, MEKE, VarMix, visc, G, GV, US, CS, Reg, tv)  :119: h 3-D; tr: Reg%Tr(m)%t, ntr 3-D h fields, in/out (the
  * routine updates their halos itself); conc_underflow: ntr or NULL; Res_fn_h, Rd_dx_h: VarMix 2-D h fields (NULL unless used);
@@ -752,6 +754,8 @@ typedef struct mom6cu_tracer_hordiff_args {
   const double *Res_fn_h, *Rd_dx_h;
   double* const* df_x;
   double* const* df_y;
+  const double *L2u, *SN_u, *L2v, *SN_v; /* VarMix%L2u, SN_u (2-D u), L2v, SN_v (2-D v): used when KhTr_Slope_Cff > 0 */
+  const double* MEKE_Kh;                 /* MEKE%Kh (2-D h): used when use_MEKE_Kh */
 } mom6cu_tracer_hordiff_args;
 int mom6cu_tracer_hordiff(mom6cu_ctx* ctx, const mom6cu_tracer_hor_diff_cs* CS, const mom6cu_tracer_hordiff_args* a);
 

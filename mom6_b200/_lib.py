@@ -276,13 +276,14 @@ class TracerHorDiffCS(C.Structure):
     _fields_ = ([(n, C.c_double) for n in ("KhTr", "KhTr_min", "KhTr_max", "KhTr_passivity_coeff", "KhTr_passivity_min", "KhTr_Slope_Cff",
                                            "max_diff_CFL")] +
                 [(n, C.c_int) for n in ("check_diffusive_CFL", "use_neutral_diffusion", "use_hor_bnd_diffusion", "Diffuse_ML_interior",
-                                        "use_variable_mixing", "Resoln_scaled_KhTr", "use_MEKE_Kh")])
+                                        "use_variable_mixing", "Resoln_scaled_KhTr", "use_MEKE_Kh")] + [("MEKE_KhTr_fac", C.c_double)])
 
 
 class TracerHordiffArgs(C.Structure):
     """mom6cu_tracer_hordiff_args: the arguments of tracer_hordiff (MOM_tracer_hor_diff.F90:119)."""
     _fields_ = [("h", C.c_void_p), ("dt", C.c_double), ("ntr", C.c_int), ("tr", C.POINTER(C.c_void_p)), ("conc_underflow", C.c_void_p),
-                ("Res_fn_h", C.c_void_p), ("Rd_dx_h", C.c_void_p), ("df_x", C.POINTER(C.c_void_p)), ("df_y", C.POINTER(C.c_void_p))]
+                ("Res_fn_h", C.c_void_p), ("Rd_dx_h", C.c_void_p), ("df_x", C.POINTER(C.c_void_p)), ("df_y", C.POINTER(C.c_void_p)),
+                ("L2u", C.c_void_p), ("SN_u", C.c_void_p), ("L2v", C.c_void_p), ("SN_v", C.c_void_p), ("MEKE_Kh", C.c_void_p)]
 
 
 class ThicknessDiffuseCS(C.Structure):

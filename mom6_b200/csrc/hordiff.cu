@@ -25,12 +25,13 @@ template <int DIR>
 __global__ void __launch_bounds__(128) hd_khdt_kernel(const Geom G, const HdP P, const HdBox B, const double* __restrict__ lenC,
                                                       const double* __restrict__ IdC, const double* __restrict__ areaT,
                                                       const double* __restrict__ Res_fn_h, const double* __restrict__ Rd_dx_h,
-                                                      double* __restrict__ khdt) {
+                                                      const double* __restrict__ L2, const double* __restrict__ SN,
+                                                      const double* __restrict__ MEKE_Kh, double* __restrict__ khdt) {
   const int i = (DIR == 0 ? B.is - 1 : B.is) + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = (DIR == 0 ? B.js : B.js - 1) + blockIdx.y;
   if (i > B.ie || j > B.je) return;
   const long long g = G.idx(i, j);
-  khdt[g] = m6hd::khdt_face(P, g, (DIR == 0) ? 1 : G.pitch, lenC, IdC, areaT, Res_fn_h, Rd_dx_h);
+  khdt[g] = m6hd::khdt_face(P, g, (DIR == 0) ? 1 : G.pitch, lenC, IdC, areaT, Res_fn_h, Rd_dx_h, L2, SN, MEKE_Kh);
 }
 
 __global__ void __launch_bounds__(128) hd_cfl_kernel(const Geom G, const HdBox B, const double* __restrict__ khdt_x,
@@ -92,8 +93,6 @@ extern "C" int mom6cu_tracer_hordiff(mom6cu_ctx* c, const mom6cu_tracer_hor_diff
   if (!c->have_grid || !c->have_vgrid) return c->fail(MOM6CU_ERR_BAD_ARG, "tracer_hordiff: mom6cu_set_grid / mom6cu_set_vgrid have not been called");
   if (CS->use_neutral_diffusion || CS->use_hor_bnd_diffusion || CS->Diffuse_ML_interior)
     return c->fail(MOM6CU_ERR_UNSUPPORTED, "tracer_hordiff: neutral diffusion, horizontal boundary diffusion and DIFFUSE_ML_TO_INTERIOR are not implemented");
-  if (CS->use_MEKE_Kh || (CS->use_variable_mixing && CS->KhTr_Slope_Cff > 0.))
-    return c->fail(MOM6CU_ERR_UNSUPPORTED, "tracer_hordiff: MEKE%%Kh and the Eady growth-rate diffusivity (KHTR_SLOPE_CFF > 0) are not implemented");
   const int ntr = a->ntr;
   c->last_iterations = 0;
   if (ntr < 0 || (ntr > 0 && (!a->tr || !a->h))) return c->fail(MOM6CU_ERR_BAD_ARG, "tracer_hordiff: null required argument");
@@ -101,6 +100,9 @@ extern "C" int mom6cu_tracer_hordiff(mom6cu_ctx* c, const mom6cu_tracer_hor_diff
   const bool use_VarMix = CS->use_variable_mixing != 0, Resoln_scaled = use_VarMix && CS->Resoln_scaled_KhTr;
   if (Resoln_scaled && !a->Res_fn_h) return c->fail(MOM6CU_ERR_BAD_ARG, "tracer_hordiff: VarMix%%Res_fn_h is not allocated");
   if (use_VarMix && CS->KhTr_passivity_coeff > 0. && !a->Rd_dx_h) return c->fail(MOM6CU_ERR_BAD_ARG, "tracer_hordiff: VarMix%%Rd_dx_h is not allocated");
+  const bool use_Eady = use_VarMix && CS->KhTr_Slope_Cff > 0., use_MEKE = use_VarMix && CS->use_MEKE_Kh;
+  if ((use_Eady && (!a->L2u || !a->SN_u || !a->L2v || !a->SN_v)) || (use_MEKE && !a->MEKE_Kh))
+    return c->fail(MOM6CU_ERR_BAD_ARG, "tracer_hordiff: VarMix%%L2u / SN_u / L2v / SN_v or MEKE%%Kh is not allocated");
   if (!(a->dt > 0.0)) return c->fail(MOM6CU_ERR_BAD_ARG, "tracer_hordiff: dt must be positive");
   const mom6cu_domain& d = c->dom;
   const Geom& G = c->g;
@@ -112,6 +114,10 @@ extern "C" int mom6cu_tracer_hordiff(mom6cu_ctx* c, const mom6cu_tracer_hor_diff
   int rc;
   const double *d_h, *d_res = nullptr, *d_rd = nullptr;
   if ((rc = S.in3(a->h, ST_H, "h", &d_h)) || (rc = S.in2(a->Res_fn_h, ST_H, "Res_fn_h", &d_res)) || (rc = S.in2(a->Rd_dx_h, ST_H, "Rd_dx_h", &d_rd))) return rc;
+  const double *d_l2u = nullptr, *d_snu = nullptr, *d_l2v = nullptr, *d_snv = nullptr, *d_kh = nullptr;
+  if (use_Eady && ((rc = S.in2(a->L2u, ST_U, "L2u", &d_l2u)) || (rc = S.in2(a->SN_u, ST_U, "SN_u", &d_snu)) || (rc = S.in2(a->L2v, ST_V, "L2v", &d_l2v)) ||
+                   (rc = S.in2(a->SN_v, ST_V, "SN_v", &d_snv)))) return rc;
+  if (use_MEKE && (rc = S.in2(a->MEKE_Kh, ST_H, "MEKE_Kh", &d_kh))) return rc;
   std::vector<double*> TA(ntr), TB(ntr), DX(ntr, nullptr), DY(ntr, nullptr);
   for (int m = 0; m < ntr; ++m) {
     char nm[32];
@@ -131,12 +137,13 @@ extern "C" int mom6cu_tracer_hordiff(mom6cu_ctx* c, const mom6cu_tracer_hor_diff
   P.dt = a->dt; P.Idt = 1.0 / a->dt; P.h_neglect = c->vgrid.H_subroundoff; P.KhTr = CS->KhTr; P.KhTr_min = CS->KhTr_min; P.KhTr_max = CS->KhTr_max;
   P.pass_coeff = CS->KhTr_passivity_coeff; P.pass_min = CS->KhTr_passivity_min; P.max_diff_CFL = CS->max_diff_CFL;
   P.use_VarMix = use_VarMix ? 1 : 0; P.Resoln_scaled = Resoln_scaled ? 1 : 0;
+  P.use_Eady = use_Eady ? 1 : 0; P.use_MEKE = use_MEKE ? 1 : 0; P.Slope_Cff = CS->KhTr_Slope_Cff; P.KhTr_fac = CS->MEKE_KhTr_fac;
   const HdBox B = {d.isc, d.iec, d.jsc, d.jec};
   if ((rc = S.begin())) return rc;
   const int ni = d.iec - d.isc + 1, nj = d.jec - d.jsc + 1;
   const dim3 gu((ni + 1 + 127) / 128, nj), gv((ni + 127) / 128, nj + 1), gh((ni + 127) / 128, nj);
-  M6_LAUNCH(c, hd_khdt_kernel<0>, gu, 128, 0, G, P, B, Gd.dy_Cu, Gd.IdxCu, Gd.areaT, d_res, d_rd, khx);
-  M6_LAUNCH(c, hd_khdt_kernel<1>, gv, 128, 0, G, P, B, Gd.dx_Cv, Gd.IdyCv, Gd.areaT, d_res, d_rd, khy);
+  M6_LAUNCH(c, hd_khdt_kernel<0>, gu, 128, 0, G, P, B, Gd.dy_Cu, Gd.IdxCu, Gd.areaT, d_res, d_rd, d_l2u, d_snu, d_kh, khx);
+  M6_LAUNCH(c, hd_khdt_kernel<1>, gv, 128, 0, G, P, B, Gd.dx_Cv, Gd.IdyCv, Gd.areaT, d_res, d_rd, d_l2v, d_snv, d_kh, khy);
   int num_itts = 1;
   double I_numitts = 1.0;
   if (CS->check_diffusive_CFL) {  // :354-366

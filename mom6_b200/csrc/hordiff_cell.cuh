@@ -20,15 +20,19 @@ M6D_HD double fmn(double a, double b) { return (a < b) ? a : b; }
 struct Par {
   double dt, Idt, h_neglect, KhTr, KhTr_min, KhTr_max, pass_coeff, pass_min, max_diff_CFL;
   int use_VarMix, Resoln_scaled;
+  int use_Eady, use_MEKE;  // KhTr_Slope_Cff > 0 with VarMix; allocated(MEKE%Kh) with VarMix
+  double Slope_Cff, KhTr_fac;
 };
 
 // khdt_x(I,j) | khdt_y(i,J) :204-327.  g: plane offset of the face and of its western / southern cell, sd: offset to the other cell;
 // lenC = G%dy_Cu | G%dx_Cv, IdC = G%IdxCu | G%IdyCv.
 M6D_HD double khdt_face(const Par& P, const long long g, const long long sd, const double* lenC, const double* IdC, const double* areaT,
-                        const double* Res_fn_h, const double* Rd_dx_h) {
+                        const double* Res_fn_h, const double* Rd_dx_h, const double* L2, const double* SN, const double* MEKE_Kh) {
   double khdt;
   if (P.use_VarMix) {
     double Kh_loc = P.KhTr;
+    if (P.use_Eady) Kh_loc = Kh_loc + P.Slope_Cff * L2[g] * SN[g];                          // :208 | :227
+    if (P.use_MEKE) Kh_loc = Kh_loc + P.KhTr_fac * sqrt(MEKE_Kh[g] * MEKE_Kh[g + sd]);     // :209-210 | :228-229
     if (P.KhTr_max > 0.) Kh_loc = fmn(Kh_loc, P.KhTr_max);
     if (P.Resoln_scaled) Kh_loc = Kh_loc * 0.5 * (Res_fn_h[g] + Res_fn_h[g + sd]);
     double Kh = fmx(Kh_loc, P.KhTr_min);

@@ -287,6 +287,8 @@ def tracer_hordiff_args(a, keep):
         keep.append(cu)
         s.conc_underflow = cu.ctypes.data
     s.Res_fn_h, s.Rd_dx_h = _addr(a.get("Res_fn_h")), _addr(a.get("Rd_dx_h"))
+    for key in ("L2u", "SN_u", "L2v", "SN_v", "MEKE_Kh"):
+        setattr(s, key, _addr(a.get(key)))
     for key in ("df_x", "df_y"):
         if a.get(key) is not None:
             p = (C.c_void_p * max(len(tr), 1))(*[_addr(t) for t in a[key]])

@@ -1079,7 +1079,7 @@ def hordiff_cs(**over):
     """tracer_hor_diff_init defaults (MOM_tracer_hor_diff.F90:1630-1778) with a KHTR that matters on a 25 km mesh."""
     cs = dict(KhTr=2000.0, KhTr_min=0.0, KhTr_max=0.0, KhTr_passivity_coeff=0.0, KhTr_passivity_min=0.5, KhTr_Slope_Cff=0.0, max_diff_CFL=-1.0,
               check_diffusive_CFL=0, use_neutral_diffusion=0, use_hor_bnd_diffusion=0, Diffuse_ML_interior=0, use_variable_mixing=0,
-              Resoln_scaled_KhTr=0, use_MEKE_Kh=0)
+              Resoln_scaled_KhTr=0, use_MEKE_Kh=0, MEKE_KhTr_fac=1.0)
     cs.update(over)
     return cs
 
@@ -1101,6 +1101,11 @@ def hordiff_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, cyclic_x=True, 
     shp2 = h.shape[1:]
     a = dict(h=np.ascontiguousarray(h), dt=dt, tr=tr[:ntr], conc_underflow=np.array(([0.0, 0.0] + [1.0e-25] * ntr)[:ntr]),
              Res_fn_h=np.ascontiguousarray(r.uniform(0, 1, size=shp2)), Rd_dx_h=np.ascontiguousarray(0.2 + 1.5 * r.uniform(0, 1, size=shp2)))
+    # VarMix%L2u / SN_u (calc_slope_functions: a squared length of O(dx^2) and an Eady growth rate of O(1e-6 s-1)) and MEKE%Kh
+    for key, st in (("L2u", "u"), ("SN_u", "u"), ("L2v", "v"), ("SN_v", "v")):
+        amp = 6.25e8 if key.startswith("L2") else 3.0e-6
+        a[key] = np.ascontiguousarray(amp * r.uniform(0, 1, size=fidx.new(dom, st).a.shape))
+    a["MEKE_Kh"] = np.ascontiguousarray(1500.0 * r.uniform(0, 1, size=shp2) ** 2)
     if with_df:
         a["df_x"] = [fidx.new(dom, "u", nk=nk, fill=7.0).a if m != 1 else None for m in range(ntr)]
         a["df_y"] = [fidx.new(dom, "v", nk=nk, fill=7.0).a if m != 0 else None for m in range(ntr)]

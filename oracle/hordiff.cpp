@@ -15,8 +15,7 @@ using namespace orc;
 
 extern "C" int oracle_tracer_hordiff(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vgrid* GV, const mom6cu_tracer_hor_diff_cs* CS,
                                      const mom6cu_tracer_hordiff_args* a, int* num_itts_out) {
-  if (CS->use_neutral_diffusion || CS->use_hor_bnd_diffusion || CS->Diffuse_ML_interior || CS->use_MEKE_Kh) return 3;
-  if (CS->use_variable_mixing && CS->KhTr_Slope_Cff > 0.) return 3;
+  if (CS->use_neutral_diffusion || CS->use_hor_bnd_diffusion || CS->Diffuse_ML_interior) return 3;
   const OGrid G(d, Gp);
   const int is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, nz = G.ke;
   const int ntr = a->ntr;
@@ -37,6 +36,12 @@ extern "C" int oracle_tracer_hordiff(const mom6cu_domain* d, const mom6cu_grid* 
   const bool Resoln_scaled = use_VarMix && CS->Resoln_scaled_KhTr;
   if (Resoln_scaled && !a->Res_fn_h) return 2;
   if (use_VarMix && CS->KhTr_passivity_coeff > 0. && !a->Rd_dx_h) return 2;
+  const bool use_Eady = use_VarMix && CS->KhTr_Slope_Cff > 0.;  // :167
+  const bool use_MEKE = use_VarMix && CS->use_MEKE_Kh;          // allocated(MEKE%Kh), read only inside the use_VarMix branch :207-208
+  if ((use_Eady && (!a->L2u || !a->SN_u || !a->L2v || !a->SN_v)) || (use_MEKE && !a->MEKE_Kh)) return 2;
+  V2 L2u, SN_u, L2v, SN_v, MEKE_Kh;
+  if (use_Eady) { L2u = G.U((double*)a->L2u); SN_u = G.U((double*)a->SN_u); L2v = G.V((double*)a->L2v); SN_v = G.V((double*)a->SN_v); }
+  if (use_MEKE) MEKE_Kh = G.H((double*)a->MEKE_Kh);
   V2 Res_fn_h, Rd_dx_h;
   if (a->Res_fn_h) Res_fn_h = G.H((double*)a->Res_fn_h);
   if (a->Rd_dx_h) Rd_dx_h = G.H((double*)a->Rd_dx_h);
@@ -46,6 +51,8 @@ extern "C" int oracle_tracer_hordiff(const mom6cu_domain* d, const mom6cu_grid* 
     for (int j = js; j <= je; ++j) for (int I = is - 1; I <= ie; ++I) {
       const int i = I;
       double Kh_loc = CS->KhTr;
+      if (use_Eady) Kh_loc = Kh_loc + CS->KhTr_Slope_Cff * L2u(I, j) * SN_u(I, j);
+      if (use_MEKE) Kh_loc = Kh_loc + CS->MEKE_KhTr_fac * std::sqrt(MEKE_Kh(i, j) * MEKE_Kh(i + 1, j));
       if (CS->KhTr_max > 0.) Kh_loc = fmin2(Kh_loc, CS->KhTr_max);
       if (Resoln_scaled) Kh_loc = Kh_loc * 0.5 * (Res_fn_h(i, j) + Res_fn_h(i + 1, j));
       double Kh_u = fmax2(Kh_loc, CS->KhTr_min);
@@ -60,6 +67,8 @@ extern "C" int oracle_tracer_hordiff(const mom6cu_domain* d, const mom6cu_grid* 
     for (int J = js - 1; J <= je; ++J) for (int i = is; i <= ie; ++i) {
       const int j = J;
       double Kh_loc = CS->KhTr;
+      if (use_Eady) Kh_loc = Kh_loc + CS->KhTr_Slope_Cff * L2v(i, J) * SN_v(i, J);
+      if (use_MEKE) Kh_loc = Kh_loc + CS->MEKE_KhTr_fac * std::sqrt(MEKE_Kh(i, j) * MEKE_Kh(i, j + 1));
       if (CS->KhTr_max > 0.) Kh_loc = fmin2(Kh_loc, CS->KhTr_max);
       if (Resoln_scaled) Kh_loc = Kh_loc * 0.5 * (Res_fn_h(i, j) + Res_fn_h(i, j + 1));
       double Kh_v = fmax2(Kh_loc, CS->KhTr_min);

@@ -94,9 +94,10 @@ ADVECT = dict(h_end=THK, uhtr=VOL, vhtr=VOL, dt=TIME, tr=NONDIM, conc_underflow=
               vol_prev=VOL, update_vol_prev=None, uhr_out=VOL, vhr_out=VOL)
 ADVECT_CS = dict(dt=TIME, default_advect_scheme=None, useHuynhStencilBug=None)
 # tracer_hordiff (MOM_tracer_hor_diff.F90:119, CS :40-106)
-HORDIFF = dict(h=THK, dt=TIME, tr=NONDIM, conc_underflow=None, Res_fn_h=NONDIM, Rd_dx_h=NONDIM, df_x=TRANSP, df_y=TRANSP)
+HORDIFF = dict(h=THK, dt=TIME, tr=NONDIM, conc_underflow=None, Res_fn_h=NONDIM, Rd_dx_h=NONDIM, df_x=TRANSP, df_y=TRANSP, L2u=L2, L2v=L2,
+               SN_u=(-1, 0, 0, 0), SN_v=(-1, 0, 0, 0), MEKE_Kh=L2T)
 HORDIFF_CS = dict(KhTr=L2T, KhTr_min=L2T, KhTr_max=L2T, KhTr_passivity_coeff=NONDIM, KhTr_passivity_min=NONDIM, KhTr_Slope_Cff=NONDIM,
-                  max_diff_CFL=NONDIM)
+                  max_diff_CFL=NONDIM, MEKE_KhTr_fac=NONDIM)
 # mixedlayer_restrat (MOM_mixed_layer_restrat.F90:149, CS :42-115)
 MLE = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, ustar=(-1, 0, 0, 1), dt=TIME, h_MLD=THK, Rd_dx_h=NONDIM)
 MLE_CS = dict(ml_restrat_coef=NONDIM, ml_restrat_coef2=NONDIM, front_length=(0, 1, 0, 0), MLE_MLD_decay_time=TIME, MLE_MLD_decay_time2=TIME,

@@ -56,13 +56,14 @@ def test_mixedlayer_restrat_sweep(oracle, mle_host):   # noqa: F811
 
 def test_tracer_hordiff_sweep(oracle, hd_host):   # noqa: F811
     many = 0
-    for c, r, g in _draws(202, 40):
+    for c, r, g in _draws(202, 60):
         nk = int(r.choice([1, 2, 5, 30]))
         vm = int(r.integers(2))
         kw = dict(ntr=int(r.integers(1, 5)), dt=float(r.choice([900.0, 7200.0])), with_df=bool(r.integers(2)), KhTr=float(r.choice([1.0, 2000.0, 5.0e4, 3.0e5])),
                   check_diffusive_CFL=int(r.integers(2)), max_diff_CFL=float(r.choice([-1.0, 0.3, 2.5])), use_variable_mixing=vm,
                   Resoln_scaled_KhTr=int(r.integers(2)) * vm, KhTr_max=float(r.choice([0.0, 1500.0])), KhTr_min=float(r.choice([0.0, 100.0])),
-                  KhTr_passivity_coeff=float(r.choice([0.0, 2.0])))
+                  KhTr_passivity_coeff=float(r.choice([0.0, 2.0])), KhTr_Slope_Cff=float(r.choice([0.0, 0.1])), use_MEKE_Kh=int(r.integers(2)),
+                  MEKE_KhTr_fac=float(r.choice([0.5, 1.0])))
         dom, grid, gv, cs, a = synthetic.hordiff_inputs(g["ni"], g["nj"], nk, halo=g["halo"], seed=g["seed"], land_blocks=g["land_blocks"],
                                                         cyclic_x=g["cyclic_x"], cyclic_y=g["cyclic_y"], **kw)
         ref = _copy(a)

@@ -125,7 +125,8 @@ def test_tracer_advection_and_diffusion(oracle, p):
         assert oracle.advect_tracer(dom, gs, gvs, RS.scale(cs, RS.ADVECT_CS, p), s) == n
         assert _same(ref["tr"], s["tr"]), (p, scheme)
     for kw in (dict(KhTr=5.0e4, check_diffusive_CFL=1, with_df=True), dict(KhTr=8.0e4, max_diff_CFL=2.5),
-               dict(use_variable_mixing=1, Resoln_scaled_KhTr=1, KhTr_max=1500.0, KhTr_min=100.0, KhTr_passivity_coeff=2.0)):
+               dict(use_variable_mixing=1, Resoln_scaled_KhTr=1, KhTr_max=1500.0, KhTr_min=100.0, KhTr_passivity_coeff=2.0),
+               dict(use_variable_mixing=1, KhTr_Slope_Cff=0.05, use_MEKE_Kh=1, KhTr=10.0, check_diffusive_CFL=1)):
         dom, grid, gv, cs, a = synthetic.hordiff_inputs(20, 14, 5, land_blocks=2, **kw)
         ref = _copy(a); n = oracle.tracer_hordiff(dom, grid, gv, cs, ref)
         gs, gvs = _grids(grid, gv, p)

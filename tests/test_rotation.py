@@ -146,12 +146,13 @@ def test_oracle_ale_regridding_and_remapping_is_rotation_invariant(oracle):
 
 
 @pytest.mark.parametrize("kw", [dict(KhTr=5.0e4, check_diffusive_CFL=1, with_df=True),
-                                dict(use_variable_mixing=1, Resoln_scaled_KhTr=1, KhTr_max=1500.0, KhTr_min=100.0, KhTr_passivity_coeff=2.0)])
+                                dict(use_variable_mixing=1, Resoln_scaled_KhTr=1, KhTr_max=1500.0, KhTr_min=100.0, KhTr_passivity_coeff=2.0),
+                                dict(use_variable_mixing=1, KhTr_Slope_Cff=0.05, use_MEKE_Kh=1, KhTr=10.0, check_diffusive_CFL=1)])
 def test_oracle_tracer_hordiff_is_rotation_invariant(oracle, kw):
     dom, grid, gv, cs, a = synthetic.hordiff_inputs(20, 14, 5, land_blocks=2, **kw)
     ref = _copy(a)
     n = oracle.tracer_hordiff(dom, grid, gv, cs, ref)
-    ar = R.rotate_fields(a, keep=("conc_underflow", "df_x", "df_y"))
+    ar = R.rotate_fields(a, pair=[("L2u", "L2v"), ("SN_u", "SN_v")], keep=("conc_underflow", "df_x", "df_y"))
     if a.get("df_x"):                                              # flux diagnostics: (df_x, df_y) is a vector
         ar["df_x"] = [None if f is None else -R.rot(f) for f in a["df_y"]]
         ar["df_y"] = [None if f is None else R.rot(f) for f in a["df_x"]]

@@ -88,7 +88,7 @@ def hd_host(tmp_path_factory):
                            os.path.join(ROOT, "tests", "harness", "hordiff_host.cpp")])
     lib = C.CDLL(so)
     lib.hd_host_khdt.restype = C.c_double
-    lib.hd_host_khdt.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong] + [C.c_void_p] * 10
+    lib.hd_host_khdt.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong] + [C.c_void_p] * 15
     lib.hd_host_sweep.restype = None
     lib.hd_host_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 8
     return lib
@@ -111,15 +111,17 @@ def _run_device_code_on_host(lib, dom, grid, gv, cs, a):
     dt, nk = a["dt"], dom.nk
     vm = bool(cs["use_variable_mixing"])
     par = np.array([dt, 1.0 / dt, gv["H_subroundoff"], cs["KhTr"], cs["KhTr_min"], cs["KhTr_max"], cs["KhTr_passivity_coeff"],
-                    cs["KhTr_passivity_min"], cs["max_diff_CFL"], int(vm), int(vm and cs["Resoln_scaled_KhTr"])], dtype=np.float64)
+                    cs["KhTr_passivity_min"], cs["max_diff_CFL"], int(vm), int(vm and cs["Resoln_scaled_KhTr"]),
+                    int(vm and cs["KhTr_Slope_Cff"] > 0.0), int(vm and cs["use_MEKE_Kh"]), cs["KhTr_Slope_Cff"], cs["MEKE_KhTr_fac"]], dtype=np.float64)
     box = np.array([dom.isc, dom.iec, dom.jsc, dom.jec, dom.isd - 1, dom.jsd - 1], dtype=np.int32)
     Gd = {k: _unified(dom, grid[k], st) for k, st in (("dy_Cu", "u"), ("IdxCu", "u"), ("dx_Cv", "v"), ("IdyCv", "v"), ("areaT", "h"), ("IareaT", "h"))}
     res, rd = _unified(dom, a["Res_fn_h"], "h"), _unified(dom, a["Rd_dx_h"], "h")
     h = _unified(dom, a["h"], "h")
     nj, ni = res.shape
     khx, khy = np.zeros((nj, ni)), np.zeros((nj, ni))
+    V = {k: _unified(dom, a[k], st) for k, st in (("L2u", "u"), ("SN_u", "u"), ("L2v", "v"), ("SN_v", "v"), ("MEKE_Kh", "h"))}
     max_cfl = lib.hd_host_khdt(p(par), p(box), ni, p(Gd["dy_Cu"]), p(Gd["IdxCu"]), p(Gd["dx_Cv"]), p(Gd["IdyCv"]), p(Gd["areaT"]), p(Gd["IareaT"]),
-                               p(res), p(rd), p(khx), p(khy))
+                               p(res), p(rd), p(khx), p(khy), p(V["L2u"]), p(V["SN_u"]), p(V["L2v"]), p(V["SN_v"]), p(V["MEKE_Kh"]))
     eps = np.finfo(np.float64).eps
     if cs["check_diffusive_CFL"]:
         n = max(1, int(np.ceil(max_cfl - 4.0 * eps)))
@@ -161,6 +163,12 @@ CASES = [dict(), dict(land_blocks=3, KhTr=5.0e4, check_diffusive_CFL=1, with_df=
          dict(use_variable_mixing=1, KhTr=0.0, KhTr_min=800.0, max_diff_CFL=0.1, with_df=True), dict(KhTr=2.0e4, max_diff_CFL=1.5, ntr=9)]
 
 
+# the VarMix / MEKE diffusivity terms (:208-210): KHTR_SLOPE_CFF * L2u * SN_u and MEKE%KhTr_fac * sqrt(Kh Kh)
+EXT_CASES = [dict(use_variable_mixing=1, KhTr_Slope_Cff=0.1, KhTr=10.0, KhTr_max=900.0, land_blocks=2),
+             dict(use_variable_mixing=1, use_MEKE_Kh=1, KhTr=0.0, MEKE_KhTr_fac=0.5, check_diffusive_CFL=1, with_df=True),
+             dict(use_variable_mixing=1, KhTr_Slope_Cff=0.05, use_MEKE_Kh=1, Resoln_scaled_KhTr=1, KhTr_passivity_coeff=2.0, KhTr_min=50.0, cyclic_y=True)]
+
+
 def _assert_same(dom, want, got, kw):
     for m in range(len(want["tr"])):
         assert np.array_equal(_inner(dom, want["tr"][m]).view(np.int64), _inner(dom, got["tr"][m]).view(np.int64)), (m, kw)
@@ -170,7 +178,7 @@ def _assert_same(dom, want, got, kw):
                 assert np.array_equal(f.view(np.int64), got[key][m].view(np.int64)), (key, m, kw)
 
 
-@pytest.mark.parametrize("kw", CASES)
+@pytest.mark.parametrize("kw", CASES + EXT_CASES)
 def test_device_cell_code_equals_oracle_on_the_host(oracle, hd_host, kw):
     for (ni, nj, nk) in ((28, 20, 6), (9, 31, 3)):
         dom, grid, gv, cs, a = synthetic.hordiff_inputs(ni, nj, nk, **kw)
@@ -210,6 +218,6 @@ def test_tracer_hordiff_on_resident_planes_and_errors(oracle, ctx_factory):
     for m, pl in enumerate(ra["tr"]):
         got = np.zeros_like(a["tr"][m]); pl.download(got)
         assert np.array_equal(_inner(dom, ref["tr"][m]).view(np.int64), _inner(dom, got).view(np.int64)), m
-    for bad in (dict(use_neutral_diffusion=1), dict(Diffuse_ML_interior=1), dict(use_MEKE_Kh=1), dict(use_variable_mixing=1, KhTr_Slope_Cff=0.1)):
+    for bad in (dict(use_neutral_diffusion=1), dict(Diffuse_ML_interior=1), dict(use_hor_bnd_diffusion=1)):
         with pytest.raises(Mom6cuError):
             ctx.tracer_hordiff(dict(cs, **bad), a)
