@@ -710,8 +710,8 @@ int mom6cu_ale_regridding_and_remapping(mom6cu_ctx* ctx, mom6cu_ale_cs* CS, cons
 /* ------------------------------------------------------------- mixedlayer_restrat (first caller) */
 /* mixedlayer_restrat_CS, src/parameterizations/lateral/MOM_mixed_layer_restrat.F90:42-115, the members of the Fox-Kemper
  * et al. (2008) general-coordinate path mixedlayer_restrat_OM4 (:189-714), and the equation of state it evaluates at the
- * surface pressure (tv%eqn_of_state: LINEAR or WRIGHT, MOM6CU_EOS_*).  Frozen: Boussinesq, MLE_USE_PBL_MLD (MLE_DENSITY_DIFF
- * <= 0), no Stanley SGS variance, no Bodner / bulk-mixed-layer variants, constant front length (MLE_FRONT_LENGTH >= 0, not from
+ * surface pressure (tv%eqn_of_state: LINEAR or WRIGHT, MOM6CU_EOS_*).  Frozen: Boussinesq, the mixed-layer depth from MLE_USE_PBL_MLD
+ * or detected with MLE_DENSITY_DIFF > 0 (detect_mld :1503), no Stanley SGS variance, no Bodner / bulk-mixed-layer variants, constant front length (MLE_FRONT_LENGTH >= 0, not from
  * a file), MLE_TAIL_DH = 0 in the full routine (mu's exponent 1 + 2 dh is a real power otherwise; mom6cu_mle_mu accepts any dh). */
 typedef struct mom6cu_mle_cs {
   double ml_restrat_coef, ml_restrat_coef2, front_length, MLE_MLD_decay_time, MLE_MLD_decay_time2, MLE_MLD_stretch, MLE_tail_dh,

@@ -89,8 +89,8 @@ extern "C" int mom6cu_mixedlayer_restrat(mom6cu_ctx* c, mom6cu_mle_cs* CS, doubl
   if ((CS->EOS_form != MOM6CU_EOS_LINEAR && CS->EOS_form != MOM6CU_EOS_WRIGHT) || !T || !S)
     return c->fail(MOM6CU_ERR_BAD_ARG, "mixedlayer_restrat_OM4: An equation of state must be used with this module.");
   if (CS->front_length > 0. && !Rd_dx_h) return c->fail(MOM6CU_ERR_BAD_ARG, "mixedlayer_restrat_OM4: The resolution argument, Rd/dx, was not associated.");
-  if (CS->MLE_density_diff > 0.) return c->fail(MOM6CU_ERR_UNSUPPORTED, "mixedlayer_restrat_OM4: detect_mld (MLE_DENSITY_DIFF > 0) is not implemented");
-  if (!CS->MLE_use_PBL_MLD || !h_MLD) return c->fail(MOM6CU_ERR_BAD_ARG, "mixedlayer_restrat_OM4: No MLD to use for MLE parameterization.");
+  const bool detect = CS->MLE_density_diff > 0.;  // detect_mld :298-299 takes precedence over the boundary-layer depth
+  if (!detect && (!CS->MLE_use_PBL_MLD || !h_MLD)) return c->fail(MOM6CU_ERR_BAD_ARG, "mixedlayer_restrat_OM4: No MLD to use for MLE parameterization.");
   if (CS->MLE_tail_dh != 0.0)
     return c->fail(MOM6CU_ERR_UNSUPPORTED, "mixedlayer_restrat_OM4: MLE_TAIL_DH /= 0 makes mu a real power, which is not bit-reproducible across math libraries");
   if ((CS->MLE_MLD_decay_time > 0. && !CS->MLD_filtered) || (CS->MLE_MLD_decay_time2 > 0. && !CS->MLD_filtered_slow))
@@ -104,7 +104,7 @@ extern "C" int mom6cu_mixedlayer_restrat(mom6cu_ctx* c, mom6cu_mle_cs* CS, doubl
   const double *d_T, *d_S, *d_us, *d_ml, *d_rd = nullptr;
   if ((rc = St.io3(h, ST_H, "h", &d_h)) || (rc = St.io3(uhtr, ST_U, "uhtr", &d_uhtr)) || (rc = St.io3(vhtr, ST_V, "vhtr", &d_vhtr)) ||
       (rc = St.in3(T, ST_H, "T", &d_T)) || (rc = St.in3(S, ST_H, "S", &d_S)) || (rc = St.in2(ustar, ST_H, "ustar", &d_us)) ||
-      (rc = St.in2(h_MLD, ST_H, "h_MLD", &d_ml)) || (rc = St.in2(Rd_dx_h, ST_H, "Rd_dx_h", &d_rd))) return rc;
+      (rc = St.in2(detect ? nullptr : h_MLD, ST_H, "h_MLD", &d_ml)) || (rc = St.in2(Rd_dx_h, ST_H, "Rd_dx_h", &d_rd))) return rc;
   if (CS->MLD_filtered && (rc = St.io2(CS->MLD_filtered, ST_H, "MLD_filtered", &d_f1))) return rc;
   if (CS->MLD_filtered_slow && (rc = St.io2(CS->MLD_filtered_slow, ST_H, "MLD_filtered_slow", &d_f2))) return rc;
   double *d_uhml = c->plane3("mle.uhml"), *d_vhml = c->plane3("mle.vhml");
@@ -123,6 +123,7 @@ extern "C" int mom6cu_mixedlayer_restrat(mom6cu_ctx* c, mom6cu_mle_cs* CS, doubl
   if (P.filt2) { P.aFac2 = CS->MLE_MLD_decay_time2 / (dt + CS->MLE_MLD_decay_time2); P.bFac2 = dt / (dt + CS->MLE_MLD_decay_time2); }
   P.res_upscale = CS->front_length > 0.;
   P.eos = {CS->EOS_form, CS->Rho_T0_S0, CS->dRho_dT, CS->dRho_dS, CS->dRho_dp};
+  P.detect = detect ? 1 : 0; P.density_diff = CS->MLE_density_diff;
   if ((rc = St.begin())) return rc;
   const GridDev& Gd = c->grid;
   {

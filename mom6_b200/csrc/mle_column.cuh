@@ -22,13 +22,42 @@ struct Par {
   double aFac1, bFac1, aFac2, bFac2;
   int filt1, filt2, res_upscale;
   Eos eos;
+  int detect;           // MLE_DENSITY_DIFF > 0: detect_mld (:1503-1569) instead of MLE_MLD_STRETCH * h_MLD
+  double density_diff;  // CS%MLE_density_diff
 };
 
 // :302-346 (the MLD filters) and :375-412 (mixed-layer thickness and thickness-weighted density of the column at plane offset g)
 M6M_HD void column(const Par& P, const long long g, const long long pl, const double* h, const double* T, const double* S,
                    const double* h_MLD, double* MLD_filtered, double* MLD_filtered_slow, double* htot_fast, double* htot_slow,
                    double* Rml_av_fast, double* Rml_av_slow) {
-  double MLD_fast = P.stretch * h_MLD[g];
+  double MLD_fast;
+  if (P.detect) {  // detect_mld :1503-1569: the depth at which sigma-0 exceeds its surface value by MLE_DENSITY_DIFF
+    double hk = h[g];
+    double dK = 0.5 * hk, dKm1;
+    const double rhoSurf = density(P.eos, T[g], S[g], 0.);
+    double dRk = 0., dRkm1;
+    double mld = 0.;
+    for (int k = 1; k < P.nk; ++k) {
+      const long long gk = g + (long long)k * pl;
+      const double hk1 = h[gk];
+      dKm1 = dK;
+      dK = dK + 0.5 * (hk1 + hk);
+      hk = hk1;
+      dRkm1 = dRk;
+      dRk = density(P.eos, T[gk], S[gk], 0.);
+      dRk = dRk - rhoSurf;
+      const double ddRho = dRk - dRkm1;
+      if ((mld == 0.) && (ddRho > 0.) && (dRkm1 < P.density_diff) && (dRk >= P.density_diff)) {
+        const double aFac = (P.density_diff - dRkm1) / ddRho;
+        mld = dK * aFac + dKm1 * (1. - aFac);
+      }
+    }
+    mld = P.stretch * mld;
+    if ((mld == 0.) && (dRk < P.density_diff)) mld = dK;  // assume mixing to the bottom
+    MLD_fast = mld;
+  } else {
+    MLD_fast = P.stretch * h_MLD[g];
+  }
   if (P.filt1) {
     const double f = fmx(MLD_fast, P.bFac1 * MLD_fast + P.aFac1 * MLD_filtered[g]);
     MLD_filtered[g] = f;

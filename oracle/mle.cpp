@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- CPU oracle (see oracle/oracle.h).
 // Restatement of /root/reference/src/parameterizations/lateral/MOM_mixed_layer_restrat.F90: mixedlayer_restrat :149-186 ->
-// mixedlayer_restrat_OM4 :189-714 (Boussinesq; MLE_USE_PBL_MLD; no Stanley variance; constant front length), mu :717-751;
+// mixedlayer_restrat_OM4 :189-714 (Boussinesq; MLE_USE_PBL_MLD or detect_mld :1503-1569; no Stanley variance; constant front length), mu :717-751;
 // find_ustar_mech_forcing (src/core/MOM_forcing_type.F90:1236-1296, the forces%ustar / H_T_units branch :1270-1272);
 // density_elem of EOS_LINEAR (src/equation_of_state/MOM_EOS_linear.F90:60-68) and EOS_WRIGHT (MOM_EOS_Wright.F90:80-97).
 // PARITY: mu is PINNED by the reference's unit test (mixedlayer_restrat_unit_tests :2014-2041), see tests/test_mle.py;
@@ -43,12 +43,12 @@ extern "C" int oracle_mixedlayer_restrat(const mom6cu_domain* d, const mom6cu_gr
   if (!GV->Boussinesq || CS->use_Bodner || CS->use_Stanley_ML || CS->fl_from_file) return 3;
   if (CS->EOS_form != MOM6CU_EOS_LINEAR && CS->EOS_form != MOM6CU_EOS_WRIGHT) return 2;  // "An equation of state must be used with this module."
   if (CS->front_length > 0. && !Rd_dx_hp) return 2;  // "The resolution argument, Rd/dx, was not associated."
-  if (CS->MLE_density_diff > 0.) return 3;           // detect_mld :1504
-  if (!CS->MLE_use_PBL_MLD) return 2;                 // "No MLD to use for MLE parameterization."
+  if (!(CS->MLE_density_diff > 0.) && (!CS->MLE_use_PBL_MLD || !h_MLDp)) return 2;  // "No MLD to use for MLE parameterization."
   const OGrid G(d, Gp);
   const int is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, nz = G.ke;
   const V3 h = G.H3(hp), uhtr = G.U3(uhtrp), vhtr = G.V3_(vhtrp), T = G.H3((double*)Tp), S = G.H3((double*)Sp);
-  const V2 ustar = G.H((double*)ustarp), h_MLD = G.H((double*)h_MLDp), MLD_filtered = G.H(CS->MLD_filtered),
+  V2 h_MLD; if (h_MLDp) h_MLD = G.H((double*)h_MLDp);
+  const V2 ustar = G.H((double*)ustarp), MLD_filtered = G.H(CS->MLD_filtered),
            MLD_filtered_slow = G.H(CS->MLD_filtered_slow);
   V2 Rd_dx_h; if (Rd_dx_hp) Rd_dx_h = G.H((double*)Rd_dx_hp);
   A3 uhml(G.isd - 1, G.ied, G.jsd, G.jed, nz), vhml(G.isd, G.ied, G.jsd - 1, G.jed, nz), h_avail(G.isd, G.ied, G.jsd, G.jed, nz);
@@ -59,7 +59,39 @@ extern "C" int oracle_mixedlayer_restrat(const mom6cu_domain* d, const mom6cu_gr
   const double vonKar_x_pi2 = CS->vonKar * 9.8696;
   // find_ustar(forces, tv, U_star_2d, G, GV, US, halo=1, H_T_units=.true.)
   for (int j = js - 1; j <= je + 1; ++j) for (int i = is - 1; i <= ie + 1; ++i) U_star_2d(i, j) = GV->Z_to_H * ustar(i, j);
-  for (int j = js - 1; j <= je + 1; ++j) for (int i = is - 1; i <= ie + 1; ++i) MLD_fast(i, j) = CS->MLE_MLD_stretch * h_MLD(i, j);
+  if (CS->MLE_density_diff > 0.) {  // detect_mld :1503-1569 (sigma-0; no Stanley variance)
+    std::vector<double> rhoSurf(G.ied + 2), deltaRhoAtKm1(G.ied + 2), deltaRhoAtK(G.ied + 2), dK(G.ied + 2), dKm1(G.ied + 2);
+    for (int j = js - 1; j <= je + 1; ++j) {
+      for (int i = is - 1; i <= ie + 1; ++i) {
+        dK[i] = 0.5 * h(i, j, 1);
+        rhoSurf[i] = density(CS, T(i, j, 1), S(i, j, 1), 0.);
+        deltaRhoAtK[i] = 0.;
+        MLD_fast(i, j) = 0.;
+      }
+      for (int k = 2; k <= nz; ++k) {
+        for (int i = is - 1; i <= ie + 1; ++i) {
+          dKm1[i] = dK[i];
+          dK[i] = dK[i] + 0.5 * (h(i, j, k) + h(i, j, k - 1));
+          deltaRhoAtKm1[i] = deltaRhoAtK[i];
+          deltaRhoAtK[i] = density(CS, T(i, j, k), S(i, j, k), 0.);
+        }
+        for (int i = is - 1; i <= ie + 1; ++i) deltaRhoAtK[i] = deltaRhoAtK[i] - rhoSurf[i];
+        for (int i = is - 1; i <= ie + 1; ++i) {
+          const double ddRho = deltaRhoAtK[i] - deltaRhoAtKm1[i];
+          if ((MLD_fast(i, j) == 0.) && (ddRho > 0.) && (deltaRhoAtKm1[i] < CS->MLE_density_diff) && (deltaRhoAtK[i] >= CS->MLE_density_diff)) {
+            const double aFac = (CS->MLE_density_diff - deltaRhoAtKm1[i]) / ddRho;
+            MLD_fast(i, j) = dK[i] * aFac + dKm1[i] * (1. - aFac);
+          }
+        }
+      }
+      for (int i = is - 1; i <= ie + 1; ++i) {
+        MLD_fast(i, j) = CS->MLE_MLD_stretch * MLD_fast(i, j);
+        if ((MLD_fast(i, j) == 0.) && (deltaRhoAtK[i] < CS->MLE_density_diff)) MLD_fast(i, j) = dK[i];
+      }
+    }
+  } else {
+    for (int j = js - 1; j <= je + 1; ++j) for (int i = is - 1; i <= ie + 1; ++i) MLD_fast(i, j) = CS->MLE_MLD_stretch * h_MLD(i, j);
+  }
   if (CS->MLE_MLD_decay_time > 0.) {  // :316-328
     const double aFac = CS->MLE_MLD_decay_time / (dt + CS->MLE_MLD_decay_time);
     const double bFac = dt / (dt + CS->MLE_MLD_decay_time);

@@ -23,6 +23,7 @@ extern "C" void mle_host_run(const double* par, const int* box, long long pitch,
   P.stretch = par[n++]; P.tail_dh = par[n++]; P.aFac1 = par[n++]; P.bFac1 = par[n++]; P.aFac2 = par[n++]; P.bFac2 = par[n++];
   P.filt1 = (int)par[n++]; P.filt2 = (int)par[n++]; P.res_upscale = (int)par[n++];
   P.eos.form = (int)par[n++]; P.eos.Rho_T0_S0 = par[n++]; P.eos.dRho_dT = par[n++]; P.eos.dRho_dS = par[n++]; P.eos.dRho_dp = par[n++];
+  P.detect = (int)par[n++]; P.density_diff = par[n++];
   const int is = box[0], ie = box[1], js = box[2], je = box[3], i0 = box[4], j0 = box[5];
   auto idx = [&](int i, int j) { return (long long)(j - j0) * pitch + (i - i0); };
   double *hf = scratch, *hs = scratch + plane, *rf = scratch + 2 * plane, *rs = scratch + 3 * plane;

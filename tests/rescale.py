@@ -101,7 +101,7 @@ HORDIFF_CS = dict(KhTr=L2T, KhTr_min=L2T, KhTr_max=L2T, KhTr_passivity_coeff=NON
 # mixedlayer_restrat (MOM_mixed_layer_restrat.F90:149, CS :42-115)
 MLE = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, ustar=(-1, 0, 0, 1), dt=TIME, h_MLD=THK, Rd_dx_h=NONDIM)
 MLE_CS = dict(ml_restrat_coef=NONDIM, ml_restrat_coef2=NONDIM, front_length=(0, 1, 0, 0), MLE_MLD_decay_time=TIME, MLE_MLD_decay_time2=TIME,
-              MLE_MLD_stretch=NONDIM, MLE_tail_dh=NONDIM, ustar_min=HT, vonKar=NONDIM, MLE_density_diff=None, Rho_T0_S0=None, dRho_dT=None,
+              MLE_MLD_stretch=NONDIM, MLE_tail_dh=NONDIM, ustar_min=HT, vonKar=NONDIM, MLE_density_diff=NONDIM, Rho_T0_S0=None, dRho_dT=None,
               dRho_dS=None, dRho_dp=None, MLD_filtered=THK, MLD_filtered_slow=THK)
 # thickness_diffuse (MOM_thickness_diffuse.F90:134, CS :40-131).  The equation of state takes the pressure in Pa (no EOS%RL2_T2_to_Pa
 # in the restatement), so only the H and Z rescalings leave the interface pressures -- (g_Earth*H_to_RZ)*h -- unchanged.

@@ -36,12 +36,13 @@ def _draws(seed, n):
 
 def test_mixedlayer_restrat_sweep(oracle, mle_host):   # noqa: F811
     moved = 0
-    for c, r, g in _draws(101, 40):
+    for c, r, g in _draws(101, 60):
         nk = int(r.choice([2, 3, 9, 24, 75]))
         kw = dict(eos=str(r.choice(["LINEAR", "WRIGHT"])), dt=float(r.choice([300.0, 900.0, 7200.0])), front=float(r.uniform(0, 6)),
                   ml_restrat_coef=float(r.choice([1.0, 5.0, 60.0])), ml_restrat_coef2=float(r.choice([0.0, 0.5, 5.0])),
                   front_length=float(r.choice([0.0, 200.0, 500.0])), MLE_MLD_decay_time=float(r.choice([0.0, 86400.0, 2.592e6])),
-                  MLE_MLD_decay_time2=float(r.choice([0.0, 7.776e6])), MLE_MLD_stretch=float(r.choice([1.0, 1.5, 4.0])))
+                  MLE_MLD_decay_time2=float(r.choice([0.0, 7.776e6])), MLE_MLD_stretch=float(r.choice([1.0, 1.5, 4.0])),
+                  MLE_density_diff=float(r.choice([-9.0e9, -9.0e9, 0.03, 0.3])))
         dom, grid, gv, cs, a = synthetic.mle_inputs(g["ni"], g["nj"], nk, halo=g["halo"], seed=g["seed"], land_blocks=g["land_blocks"],
                                                     cyclic_x=g["cyclic_x"], cyclic_y=g["cyclic_y"], **kw)
         a["uhtr"][::2] = -0.0

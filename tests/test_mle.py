@@ -48,6 +48,9 @@ def test_mu_column_code_equals_oracle(oracle, mle_host):
 CASES = [dict(), dict(land_blocks=4, eos="LINEAR"), dict(front_length=0.0, ml_restrat_coef=60.0, cyclic_y=True),
          dict(MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, land_blocks=2), dict(MLE_MLD_decay_time=0.0, MLE_MLD_stretch=1.5),
          dict(dt=7200.0, front=6.0, ml_restrat_coef=20.0, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=5.0)]
+# the mixed-layer depth detected from the density profile (MLE_DENSITY_DIFF > 0, detect_mld :1503) instead of the boundary-layer depth
+EXT_CASES = [dict(MLE_density_diff=0.03, MLE_use_PBL_MLD=0, land_blocks=2), dict(MLE_density_diff=0.3, MLE_MLD_stretch=1.5, eos="LINEAR", cyclic_y=True),
+             dict(MLE_density_diff=1.0e-4, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5)]
 
 
 def _unified(dom, x, st):
@@ -71,7 +74,8 @@ def _run_device_code_on_host(lib, dom, grid, gv, cs, a):
            cs["MLE_MLD_stretch"], cs["MLE_tail_dh"],
            cs["MLE_MLD_decay_time"] / (dt + cs["MLE_MLD_decay_time"]) if f1 else 0.0, dt / (dt + cs["MLE_MLD_decay_time"]) if f1 else 0.0,
            cs["MLE_MLD_decay_time2"] / (dt + cs["MLE_MLD_decay_time2"]) if f2 else 0.0, dt / (dt + cs["MLE_MLD_decay_time2"]) if f2 else 0.0,
-           int(f1), int(f2), int(cs["front_length"] > 0.0), cs["EOS_form"], cs["Rho_T0_S0"], cs["dRho_dT"], cs["dRho_dS"], cs["dRho_dp"]]
+           int(f1), int(f2), int(cs["front_length"] > 0.0), cs["EOS_form"], cs["Rho_T0_S0"], cs["dRho_dT"], cs["dRho_dS"], cs["dRho_dp"],
+           int(cs["MLE_density_diff"] > 0.0), cs["MLE_density_diff"]]
     par = np.array(par, dtype=np.float64)
     box = np.array([dom.isc, dom.iec, dom.jsc, dom.jec, dom.isd - 1, dom.jsd - 1], dtype=np.int32)
     F = {k: _unified(dom, a[k], st) for k, st in (("h", "h"), ("uhtr", "u"), ("vhtr", "v"), ("T", "h"), ("S", "h"), ("ustar", "h"),
@@ -156,13 +160,13 @@ def test_oracle_restratifies(oracle):
 
 def test_oracle_rejects_options_outside_the_frozen_set(oracle):
     dom, grid, gv, cs, a = synthetic.mle_inputs(12, 10, 4)
-    for bad in (dict(use_Bodner=1), dict(MLE_use_PBL_MLD=0), dict(EOS_form=0), dict(MLE_density_diff=0.03)):
+    for bad in (dict(use_Bodner=1), dict(MLE_use_PBL_MLD=0), dict(EOS_form=0), dict(use_Stanley_ML=1)):
         with pytest.raises(RuntimeError):
             _run_oracle(oracle, dom, grid, gv, dict(cs, **bad), a)
 
 
 
-@pytest.mark.parametrize("kw", CASES)
+@pytest.mark.parametrize("kw", CASES + EXT_CASES)
 def test_device_column_code_equals_oracle_on_the_host(oracle, mle_host, kw):
     """The column / face / update functions the kernels of csrc/mle.cu call (early exit at the base of the mixed layer, mu reused
     between a layer's bottom and the next layer's top, h_avail evaluated in place) compiled for the host: bit for bit the oracle."""
@@ -178,7 +182,7 @@ def test_device_column_code_equals_oracle_on_the_host(oracle, mle_host, kw):
         ext = (slice(dom.jsc - dom.jsd - 1, dom.jec - dom.jsd + 2), slice(dom.isc - dom.isd - 1, dom.iec - dom.isd + 2))
         for k in ("MLD_filtered", "MLD_filtered_slow"):
             assert np.array_equal(c[k][ext].view(np.int64), got[k][ext].view(np.int64)), (k, kw)
-        assert nk < 20 or np.abs(o["uhtr"] - a["uhtr"]).max() > 0
+        assert nk < 20 or cs["MLE_density_diff"] > 0 or np.abs(o["uhtr"] - a["uhtr"]).max() > 0
 
 
 @pytest.mark.gpu
@@ -219,6 +223,6 @@ def test_mixedlayer_restrat_errors(ctx_factory):
     dom, grid, gv, cs, a = synthetic.mle_inputs(16, 12, 5)
     ctx = ctx_factory(dom)
     ctx.set_grid(grid); ctx.set_vgrid(gv)
-    for bad in (dict(use_Bodner=1), dict(MLE_use_PBL_MLD=0), dict(EOS_form=0), dict(MLE_density_diff=0.03), dict(MLE_tail_dh=0.1)):
+    for bad in (dict(use_Bodner=1), dict(MLE_use_PBL_MLD=0), dict(EOS_form=0), dict(use_Stanley_ML=1), dict(MLE_tail_dh=0.1)):
         with pytest.raises(Mom6cuError):
             ctx.mixedlayer_restrat(dict(cs, **bad), a["h"], a["uhtr"], a["vhtr"], a["T"], a["S"], a["ustar"], a["dt"], a["h_MLD"], a["Rd_dx_h"])

@@ -137,7 +137,8 @@ def test_tracer_advection_and_diffusion(oracle, p):
 
 @pytest.mark.parametrize("p", POWERS)
 def test_mixedlayer_restrat(oracle, p):
-    for kw in (dict(), dict(MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, land_blocks=2), dict(front_length=0.0, ml_restrat_coef=60.0)):
+    for kw in (dict(), dict(MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, land_blocks=2), dict(front_length=0.0, ml_restrat_coef=60.0),
+               dict(MLE_density_diff=0.1)):
         dom, grid, gv, cs, a = synthetic.mle_inputs(20, 14, 24, MLE_MLD_stretch=3.0, **kw)
         dcs = RS.with_flags(RS.MLE_CS, cs)
         c0, a0 = _copy(cs), _copy(a)

@@ -77,8 +77,9 @@ def test_oracle_advect_tracer_is_rotation_invariant(oracle, scheme):
     assert not np.array_equal(_inner(dom, ref["tr"][0]), _inner(dom, a["tr"][0]))
 
 
-def test_oracle_mixedlayer_restrat_is_rotation_invariant(oracle):
-    dom, grid, gv, cs, a = synthetic.mle_inputs(20, 14, 24, land_blocks=2, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, MLE_MLD_stretch=3.0)
+@pytest.mark.parametrize("kw", [dict(), dict(MLE_density_diff=0.1)])
+def test_oracle_mixedlayer_restrat_is_rotation_invariant(oracle, kw):
+    dom, grid, gv, cs, a = synthetic.mle_inputs(20, 14, 24, land_blocks=2, MLE_MLD_decay_time2=7.776e6, ml_restrat_coef2=0.5, MLE_MLD_stretch=3.0, **kw)
     cr, ar = R.rotate_fields(cs), R.rotate_fields(a, R.STEP_VEC, R.STEP_PAIR)
     c0, a0 = _copy(cs), _copy(a)
     oracle.mixedlayer_restrat(dom, grid, gv, c0, a0["h"], a0["uhtr"], a0["vhtr"], a0["T"], a0["S"], a0["ustar"], a0["dt"], a0["h_MLD"], a0["Rd_dx_h"])
