@@ -138,6 +138,38 @@ class Context {
     check(mom6cu_do_group_pass(h_, (int)fields.size(), fields.data(), stagger.data(), nk), "do_group_pass");
   }
 
+  void ALE_remap_interface_vals(const double* h_old, const double* h_new, double* int_val) {                        // MOM_ALE.F90:1303
+    check(mom6cu_ale_remap_interface_vals(h_, h_old, h_new, int_val), "ALE_remap_interface_vals");
+  }
+  void ALE_remap_vertex_vals(const double* h_old, const double* h_new, double* vert_val) {                          // MOM_ALE.F90:1342
+    check(mom6cu_ale_remap_vertex_vals(h_, h_old, h_new, vert_val), "ALE_remap_vertex_vals");
+  }
+  void interpolate_column(int ncol, int nsrc, const double* h_src, const double* u_src, int ndest, const double* h_dest, double* u_dest,
+                          bool mask_edges) {                                                                       // MOM_remapping.F90:1247
+    check(mom6cu_interpolate_column(h_, ncol, nsrc, h_src, u_src, ndest, h_dest, u_dest, mask_edges ? 1 : 0), "interpolate_column");
+  }
+  void remap_dyn_split_RK2_aux_vars(const mom6cu_remapping_cs& remapCS, const mom6cu_dyn_split_rk2_cs& CS, const double* h_old_u,
+                                    const double* h_old_v, const double* h_new_u, const double* h_new_v) {          // MOM_dynamics_split_RK2.F90:1302
+    check(mom6cu_remap_dyn_split_rk2_aux_vars(h_, &remapCS, &CS, h_old_u, h_old_v, h_new_u, h_new_v), "remap_dyn_split_RK2_aux_vars");
+  }
+  void vertvisc_get_coef(double* a_u, double* a_v, double* h_u, double* h_v) { check(mom6cu_vertvisc_get_coef(h_, a_u, a_v, h_u, h_v), "vertvisc_get_coef"); }
+  void btstep_timeloop_resident(const mom6cu_bt_timeloop_args& a, int reps, bool download) {                         // MOM_barotropic.F90:2175, repeated on resident fields
+    check(mom6cu_btstep_timeloop_resident(h_, &a, reps, download ? 1 : 0), "btstep_timeloop");
+  }
+  double total_kernel_ms() const { return mom6cu_total_kernel_ms(h_); }
+  std::vector<double> last_step_stage_ms() const {
+    std::vector<double> ms(8, 0.0);
+    const int n = mom6cu_last_step_stage_ms(h_, ms.data(), (int)ms.size());
+    ms.resize(n < 0 ? 0 : (n > 8 ? 8 : n));
+    return ms;
+  }
+  void comm_destroy() { check(mom6cu_comm_destroy(h_), "comm_destroy"); }
+  static int build_arch() { return mom6cu_build_arch(); }
+  // one neighbour message of a group pass (host-only planning; MOM_domain_infra.F90:171-216): the peer rank or -1
+  static int halo_plan(const mom6cu_domain& dom, Stagger st, bool wide, int halo, int dir, int send_box[4], int recv_box[4]) {
+    return mom6cu_halo_plan(&dom, (int)st, wide ? 1 : 0, halo, dir, send_box, recv_box);
+  }
+
   // ---- the answer-reproducibility metric
   void write_energy(mom6cu_sum_output_cs& CS, const double* u, const double* v, const double* h, const double* T, const double* S,
                     mom6cu_energy_out& out) {                                                                        // MOM_sum_output.F90:321
@@ -164,6 +196,17 @@ class Context {
  private:
   mom6cu_ctx* h_ = nullptr;
   int warnings_ = 0;
+};
+
+// EFP_type and its operators (src/framework/MOM_coms.F90:76-78, :548-684)
+struct EFP {
+  mom6cu_efp v;
+  EFP() : v() {}
+  explicit EFP(double x) : v() { const int rc = mom6cu_real_to_efp(x, &v); if (rc) throw Fatal(rc, "real_to_EFP", rc == 2 ? "NaN in real_to_EFP" : "Overflow in real_to_EFP conversion"); }
+  double to_real() const { mom6cu_efp t = v; return mom6cu_efp_to_real(&t); }
+  EFP operator+(const EFP& o) const { EFP r; int over = 0; mom6cu_efp_plus(&v, &o.v, &r.v, &over); if (over) throw Fatal(2, "EFP_plus", "Overflow in EFP_plus."); return r; }
+  EFP operator-(const EFP& o) const { EFP r; int over = 0; mom6cu_efp_minus(&v, &o.v, &r.v, &over); if (over) throw Fatal(2, "EFP_minus", "Overflow in EFP_minus."); return r; }
+  double real_diff(const EFP& o) const { return mom6cu_efp_real_diff(&v, &o.v); }
 };
 
 inline void Plane::upload(const double* host) { c_->check(mom6cu_plane_upload(c_->handle(), p_, host, st_, wide_, nk_), "plane_upload"); }

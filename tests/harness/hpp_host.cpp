@@ -7,6 +7,10 @@
 #include "../../include/mom6cu.hpp"
 
 int main() {
+  // host-only entries need no device: the EFP operators (MOM_coms.F90:548-684) and the build target
+  if (mom6cu::Context::build_arch() != 100) return 4;
+  const mom6cu::EFP a(1.5), b(2.25);
+  if ((a + b).to_real() != 3.75 || (a - b).to_real() != -0.75 || b.real_diff(a) != 0.75) return 4;
   mom6cu_domain dom;
   std::memset(&dom, 0, sizeof dom);
   const int halo = 4, ni = 8, nj = 8;

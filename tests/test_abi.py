@@ -75,3 +75,16 @@ def test_cpp_host_mirror_runs_the_reference_mu_vectors(tmp_path):
     import subprocess
     r = subprocess.run([_build_hpp_host(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0 and "FATAL as expected" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_every_declared_entry_has_python_argtypes_and_a_cpp_or_fortran_binding():
+    """The ctypes mirror declares the argument types of every entry of include/mom6cu.h (a missing declaration would let ctypes pass 32-bit
+    ints where the C side expects pointers), and every compute entry is reachable from a compiled-language binding."""
+    lib = _lib.load()
+    names = _declared()
+    untyped = [n for n in names if getattr(lib, n).argtypes is None]
+    assert not untyped, f"no argtypes in mom6_b200/_lib.py for: {untyped}"
+    hpp = open(os.path.join(ROOT, "include", "mom6cu.hpp")).read()
+    f90 = open(os.path.join(ROOT, "fortran", "mom6cu_interface.F90")).read()
+    unbound = [n for n in names if n not in hpp and n not in f90]
+    assert not unbound, f"neither include/mom6cu.hpp nor fortran/mom6cu_interface.F90 binds: {unbound}"
