@@ -1,6 +1,6 @@
 """Tile-layout invariance (the reference's `layout` regression test, .testing/Makefile: 1 PE vs LAYOUT = 2,1 / 1,2 / 2,2 must agree bit for bit)
-of the callers that need no exchange inside the call -- mixedlayer_restrat and thickness_diffuse read one halo point of h, T, S and the 2-D
-inputs -- on the oracle: each tile of the layout, cut out of the single-tile inputs with its halos, must reproduce the single-tile answer on
+of the callers of step_MOM_dynamics / step_MOM_tracer_dyn on the oracle -- mixedlayer_restrat and thickness_diffuse read one halo point of h, T,
+S and the 2-D inputs and exchange nothing inside the call; tracer_hordiff is run for the single sweep whose only exchange opens it --: each tile of the layout, cut out of the single-tile inputs with its halos, must reproduce the single-tile answer on
 its own computational domain.  (The dycore step, the barotropic solver and the ocean.stats line have their layout tests on the device:
 tests/test_step_multigpu.py, test_bt_multigpu.py, test_diag.py.)"""
 import numpy as np
@@ -85,3 +85,38 @@ def test_thickness_diffuse_layout(oracle, layout, kw):
             for k in ("h", "uhtr", "vhtr", "uhGM", "vhGM"):
                 if a.get(k) is not None:
                     assert np.array_equal(_inner_of_tile(dom_g, dom, oi, oj, ra[k], TD_ST[k]), _inner(dom, a[k], TD_ST[k])), (k, layout, pi, pj)
+
+
+HD_ST = dict(h="h", Res_fn_h="h", Rd_dx_h="h", L2u="u", SN_u="u", L2v="v", SN_v="v", MEKE_Kh="h")
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("kw", [dict(with_df=True), dict(use_variable_mixing=1, KhTr_Slope_Cff=0.05, use_MEKE_Kh=1, Resoln_scaled_KhTr=1, KhTr_max=1500.0)])
+def test_tracer_hordiff_layout(oracle, layout, kw):
+    """One sweep (num_itts = 1): the only exchange is the halo update that opens it (do_group_pass :541), which the tiles receive here as
+    the halos cut from the halo-filled single-tile tracers; the tiles themselves are run with closed edges so that nothing wraps onto a tile."""
+    from mom6_b200 import fidx
+    dom_g, grid_g, gv, cs, a_g = synthetic.hordiff_inputs(24, 20, 6, land_blocks=2, **kw)
+    for m, t in enumerate(a_g["tr"]):                                         # what do_group_pass leaves on one tile
+        f = fidx.FA(dom_g.isd, dom_g.ied, dom_g.jsd, dom_g.jed, nk=dom_g.nk); f.a[...] = t; fidx.fill_halo(dom_g, f, "h"); a_g["tr"][m] = np.ascontiguousarray(f.a)
+    ra = {k: ([x if x is None else x.copy() for x in v] if isinstance(v, list) else _copy(v)) for k, v in a_g.items()}
+    assert oracle.tracer_hordiff(dom_g, grid_g, gv, cs, ra) == 1
+    npi, npj = layout
+    for pj in range(npj):
+        for pi in range(npi):
+            dom, oi, oj = _tile(dom_g, npi, npj, pi, pj)
+            dom.cyclic_x, dom.cyclic_y = 0, 0
+            grid = _cut_all(dom_g, dom, oi, oj, grid_g, synthetic.GRID_STAGGER)
+            a = _cut_all(dom_g, dom, oi, oj, {k: v for k, v in a_g.items() if k in HD_ST}, HD_ST)
+            a.update(dt=a_g["dt"], conc_underflow=a_g["conc_underflow"], tr=[synthetic._cut(dom_g, dom, t, "h", False, oi, oj).copy() for t in a_g["tr"]])
+            for key, st in (("df_x", "u"), ("df_y", "v")):
+                if a_g.get(key) is not None:
+                    a[key] = [None if f is None else synthetic._cut(dom_g, dom, f, st, False, oi, oj).copy() for f in a_g[key]]
+            assert oracle.tracer_hordiff(dom, grid, gv, cs, a) == 1
+            for m in range(len(a["tr"])):
+                assert np.array_equal(_inner_of_tile(dom_g, dom, oi, oj, ra["tr"][m], "h"), _inner(dom, a["tr"][m], "h")), (m, layout, pi, pj)
+            for key, st in (("df_x", "u"), ("df_y", "v")):
+                for m, f in enumerate(a.get(key) or []):
+                    if f is not None:
+                        assert np.array_equal(_inner_of_tile(dom_g, dom, oi, oj, ra[key][m], st), _inner(dom, f, st)), (key, m, layout, pi, pj)
+    assert not np.array_equal(ra["tr"][0], a_g["tr"][0])
