@@ -12,7 +12,6 @@ subroutine mixedlayer_restrat_mom6cu(h, uhtr, vhtr, tv, forces, dt, h_MLD, VarMi
   use, intrinsic :: iso_c_binding
   use mom6cu_interface
   use MOM_error_handler, only : MOM_error, FATAL
-  use MOM_EOS,           only : get_EOS_name
   use MOM_forcing_type,  only : mech_forcing
   use MOM_grid,          only : ocean_grid_type
   use MOM_lateral_mixing_coeffs, only : VarMix_CS
@@ -47,17 +46,12 @@ subroutine mixedlayer_restrat_mom6cu(h, uhtr, vhtr, tv, forces, dt, h_MLD, VarMi
   c%MLE_density_diff = CS%MLE_density_diff
   c%MLE_use_PBL_MLD = merge(1, 0, CS%MLE_use_PBL_MLD) ; c%use_Stanley_ML = merge(1, 0, CS%use_Stanley_ML)
   c%use_Bodner = merge(1, 0, CS%use_Bodner) ; c%fl_from_file = merge(1, 0, CS%fl_from_file)
-  ! EOS_type keeps its form and coefficients private (MOM_EOS.F90:107-150); the public accessor is get_EOS_name (:57-58).  The LINEAR
-  ! coefficients are therefore read once, in the shim's init, with the same get_param calls EOS_init makes (RHO_T0_S0, DRHO_DT, DRHO_DS;
-  ! MOM_EOS.F90:1560-1580) into the module variables lin_Rho_T0_S0, lin_dRho_dT, lin_dRho_dS.
-  c%EOS_form = 0                                                   ! MOM6CU_EOS_*: 1 = LINEAR, 3 = WRIGHT (include/mom6cu.h)
-  if (associated(tv%eqn_of_state)) then
-    select case (trim(get_EOS_name(tv%eqn_of_state)))
-      case ("LINEAR") ; c%EOS_form = 1
-      case ("WRIGHT") ; c%EOS_form = 3
-    end select
-    c%Rho_T0_S0 = lin_Rho_T0_S0 ; c%dRho_dT = lin_dRho_dT ; c%dRho_dS = lin_dRho_dS ; c%dRho_dp = 0.0
-  endif
+  ! EOS_type keeps its form and coefficients private (MOM_EOS.F90:107-150) and offers no query for them, so the shim's init reads
+  ! them once with the same get_param calls EOS_init makes (EQN_OF_STATE, RHO_T0_S0, DRHO_DT, DRHO_DS; MOM_EOS.F90:1535-1580) into
+  ! the module variables eos_form (MOM6CU_EOS_*: 1 = LINEAR, 3 = WRIGHT, include/mom6cu.h), lin_Rho_T0_S0, lin_dRho_dT, lin_dRho_dS.
+  c%EOS_form = 0
+  if (associated(tv%eqn_of_state)) c%EOS_form = eos_form
+  c%Rho_T0_S0 = lin_Rho_T0_S0 ; c%dRho_dT = lin_dRho_dT ; c%dRho_dS = lin_dRho_dS ; c%dRho_dp = 0.0
   ! model state held by the control structure: updated in place by the library (restart fields stay on the host side of the ABI)
   c%MLD_filtered = c_null_ptr ; c%MLD_filtered_slow = c_null_ptr
   if (allocated(CS%MLD_filtered))      c%MLD_filtered      = c_loc(CS%MLD_filtered)
