@@ -3,8 +3,10 @@
 !! the second worked binding (the first is MOM_continuity_PPM_cu.F90) and shows a caller of step_MOM_dynamics (MOM.F90:1422) whose
 !! arguments are updated in place and whose control structure carries model state (CS%MLD_filtered, a restart field).
 !! The init / restart-registration routines of the reference module are kept as they are (they read parameters and allocate
-!! CS%MLD_filtered, :1618-2009); only the body of mixedlayer_restrat changes.  Not compiled in the build container (no Fortran
-!! compiler there).
+!! CS%MLD_filtered, :1618-2009).  The control structure's members are private to the module (:42), so this subroutine is a module
+!! procedure of the shadowing copy of MOM_mixed_layer_restrat.F90 -- `contains` it there and have mixedlayer_restrat (:149-186) call it
+!! where it calls mixedlayer_restrat_OM4 (:179); it is shown as a file of its own only for readability.  Not compiled in the build
+!! container (no Fortran compiler there).
 !!
 !! subroutine mixedlayer_restrat(h, uhtr, vhtr, tv, forces, dt, MLD, h_MLD, bflux, VarMix, G, GV, US, CS)
 !!   ... the reference's declarations (:150-170), arrays given the TARGET attribute ...
@@ -15,7 +17,6 @@ subroutine mixedlayer_restrat_mom6cu(h, uhtr, vhtr, tv, forces, dt, h_MLD, VarMi
   use MOM_forcing_type,  only : mech_forcing
   use MOM_grid,          only : ocean_grid_type
   use MOM_lateral_mixing_coeffs, only : VarMix_CS
-  use MOM_mixed_layer_restrat,   only : mixedlayer_restrat_CS
   use MOM_unit_scaling,  only : unit_scale_type
   use MOM_variables,     only : thermo_var_ptrs
   use MOM_verticalGrid,  only : verticalGrid_type
