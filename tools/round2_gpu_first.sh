@@ -5,7 +5,7 @@
 #  2. full-size timings of thickness_diffuse and tracer_hordiff (tools/time_callers.py) and of mixedlayer_restrat (tools/time_mle.py);
 #  3. a --set full capture of their kernels at 720x540x75 for profiles/ (read here with tools/ncu_summary.py).
 mkdir -p gpurun_out
-( timeout 300 python -m pytest tests/test_zz_thickness_diffuse_ext_gpu.py tests/test_zz_tracer_hordiff_ext_gpu.py tests/test_zz_mle_ext_gpu.py tests/test_zz_callers_chain_gpu.py tests/test_zz_callers_full_size_gpu.py -m gpu -q \
+( timeout 300 python -m pytest tests/test_zz2_thickness_diffuse_ext_gpu.py tests/test_zz3_tracer_hordiff_ext_gpu.py tests/test_zz1_mle_ext_gpu.py tests/test_zz4_callers_chain_gpu.py tests/test_zz5_callers_full_size_gpu.py -m gpu -q \
     > gpurun_out/r02_gpu_zz.log 2>&1; echo "rc=$?" >> gpurun_out/r02_gpu_zz.log )
 ( timeout 120 python tools/time_callers.py > gpurun_out/r02_time_callers.json 2> gpurun_out/r02_time_callers.err )
 ( timeout 90 python tools/time_mle.py > gpurun_out/r02_time_mle.json 2> gpurun_out/r02_time_mle.err )
