@@ -117,6 +117,9 @@ module mom6cu_interface
     real(c_double) :: rho_ref, GFS_scale, Z_ref, dZ_subroundoff
     real(c_double) :: Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp
     type(c_ptr) :: Rlay, g_prime
+    integer(c_int) :: reconstruct, Recon_Scheme, boundary_extrap, use_inaccurate_pgf_rho_anom, MassWghtInterpVanOnly, ALE_answer_date
+    real(c_double) :: h_nonvanished
+    real(c_double) :: kg_m3_to_R, RL2_T2_to_Pa, C_to_degC, S_to_ppt
   end type mom6cu_pressureforce_cs
   !> Arguments of PressureForce (src/core/MOM_PressureForce.F90:40-61)
   type, bind(C) :: mom6cu_pressureforce_args

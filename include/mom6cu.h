@@ -246,8 +246,9 @@ int mom6cu_horizontal_viscosity(mom6cu_ctx* ctx, const mom6cu_hor_visc_args* a);
  * Set_pbce_Bouss (src/core/MOM_PressureForce_Montgomery.F90:649-748).
  * PressureForce_FV_CS (:40-107) + the EOS_type / verticalGrid members the routine reads.
  * Frozen options: no tides / SAL, no Stanley SGS term, no RESET_INTXPA_INTEGRAL / CORRECTION_INTXPA, no bulk
- * mixed layer (GV%nk_rho_varies = 0), piecewise-constant T,S within layers (RECONSTRUCT_FOR_PRESSURE off or no ALE);
- * EOS forms: none (layered), LINEAR, WRIGHT (analytic integrals, EOS_quadrature off). */
+ * mixed layer (GV%nk_rho_varies = 0); T,S piecewise constant within layers (analytic integrals, EOS_quadrature off) or,
+ * with RECONSTRUCT_FOR_PRESSURE (the reference's default under ALE), PLM / PPM sub-layer profiles integrated by quadrature;
+ * EOS forms: none (layered), LINEAR, WRIGHT. */
 #define MOM6CU_EOS_NONE 0
 #define MOM6CU_EOS_LINEAR 1
 #define MOM6CU_EOS_WRIGHT 3
@@ -256,6 +257,16 @@ typedef struct mom6cu_pressureforce_cs {
   double rho_ref, GFS_scale, Z_ref, dZ_subroundoff;
   double Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp; /* EOS_LINEAR */
   const double *Rlay, *g_prime;                /* GV%Rlay(1:nk), GV%g_prime(1:nk+1), host arrays (EOS_NONE) */
+  /* RECONSTRUCT_FOR_PRESSURE (MOM_PressureForce_FV.F90:2172-2190): sub-layer T,S profiles from the ALE reconstructions
+   * (TS_PLM_edge_values / TS_PPM_edge_values, MOM_ALE.F90:1495/1581) integrated by quadrature
+   * (int_density_dz_generic_plm / _ppm, MOM_density_integrals.F90:418/874).  reconstruct = CS%reconstruct .and. use_EOS .and.
+   * associated(ALE_CSp); Recon_Scheme = PRESSURE_RECONSTRUCTION_SCHEME (1 = PLM, 2 = PPM); boundary_extrap =
+   * BOUNDARY_EXTRAPOLATION_PRESSURE; ALE_answer_date = ALE_CS%answer_date (>= 20190101 only). */
+  int reconstruct, Recon_Scheme, boundary_extrap, use_inaccurate_pgf_rho_anom, MassWghtInterpVanOnly, ALE_answer_date;
+  double h_nonvanished; /* CS%h_nonvanished [H] */
+  /* EOS_type unit conversion factors (MOM_EOS.F90:140-150); 0 is read as 1.  The device path requires them to be 1 (the
+   * reference's default); the oracle honours them (the dimensional-rescaling test of the pressure force). */
+  double kg_m3_to_R, RL2_T2_to_Pa, C_to_degC, S_to_ppt;
 } mom6cu_pressureforce_cs;
 
 /* PressureForce(h, tv, PFu, PFv, G, GV, US, CS, ALE_CSp, ADp, p_atm, pbce, eta)  MOM_PressureForce.F90:40 */

@@ -166,7 +166,10 @@ class PressureForceCS(C.Structure):
     """mom6cu_pressureforce_cs: PressureForce_FV_CS (MOM_PressureForce_FV.F90:40-107) + EOS / vertical-grid members."""
     _fields_ = ([(n, C.c_int) for n in ("EOS_form", "MassWghtInterp", "use_SSH_in_Z0p", "rho_ref_bug", "unsupported")] +
                 [(n, C.c_double) for n in ("rho_ref", "GFS_scale", "Z_ref", "dZ_subroundoff", "Rho_T0_S0", "dRho_dT", "dRho_dS",
-                                           "dRho_dp")] + [(n, C.c_void_p) for n in ("Rlay", "g_prime")])
+                                           "dRho_dp")] + [(n, C.c_void_p) for n in ("Rlay", "g_prime")] +
+                [(n, C.c_int) for n in ("reconstruct", "Recon_Scheme", "boundary_extrap", "use_inaccurate_pgf_rho_anom",
+                                        "MassWghtInterpVanOnly", "ALE_answer_date")] +
+                [(n, C.c_double) for n in ("h_nonvanished", "kg_m3_to_R", "RL2_T2_to_Pa", "C_to_degC", "S_to_ppt")])
 
 
 class PressureForceArgs(C.Structure):

@@ -75,8 +75,15 @@ def btcalc_args(a, keep):
     return fill_struct(BtcalcArgs(), a, keep)
 
 
+PGF_RECON_DEFAULTS = dict(reconstruct=0, Recon_Scheme=1, boundary_extrap=0, use_inaccurate_pgf_rho_anom=0, MassWghtInterpVanOnly=0,
+                          ALE_answer_date=99991231, h_nonvanished=0.0, kg_m3_to_R=1.0, RL2_T2_to_Pa=1.0, C_to_degC=1.0, S_to_ppt=1.0)
+
+
 def pressureforce_cs(d, keep):
-    return fill_struct(PressureForceCS(), d, keep)
+    """RECONSTRUCT_FOR_PRESSURE members default to off / unscaled when the dict does not carry them."""
+    dd = dict(PGF_RECON_DEFAULTS)
+    dd.update(d)
+    return fill_struct(PressureForceCS(), dd, keep)
 
 
 def pressureforce_args(a, keep):
