@@ -284,6 +284,9 @@ __global__ void __launch_bounds__(128, MINB) pgf_main_kernel(const Geom G, const
 
 }  // namespace
 
+#include "remap_column.cuh"
+#include "pgf_recon.cuh"
+
 int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D) {
   if (!c->have_pgf_cs) return c->fail(MOM6CU_ERR_BAD_ARG, "MOM_PressureForce_FV_Bouss: Module must be initialized before it is used.");
   if (!c->have_grid || !c->have_vgrid) return c->fail(MOM6CU_ERR_BAD_ARG, "PressureForce: grid / vertical grid not set");
@@ -310,6 +313,24 @@ int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D) {
   K.PFu = D.PFu; K.PFv = D.PFv; K.pbce = D.pbce; K.eta = D.eta;
   dim3 grid((d.iec - d.isc + 3 + 127) / 128, d.jec - d.jsc + 3);
   M6_LAUNCH(c, pgf_e_kernel, grid, 128, 0, G, K);
+  if (S.reconstruct && use_EOS && S.Recon_Scheme > 0) {  // use_ALE (:1120-1122) with PRESSURE_RECONSTRUCTION_SCHEME 1 (PLM) or 2 (PPM)
+    PgfRecon R = {};
+    R.scheme = S.Recon_Scheme; R.boundary_extrap = S.boundary_extrap; R.inaccurate = S.use_inaccurate_pgf_rho_anom;
+    R.van_only = S.MassWghtInterpVanOnly; R.h_nv = GV.H_to_Z * S.h_nonvanished; R.H_subroundoff = GV.H_subroundoff;
+    R.T_t = c->plane3k("pgf.T_t", G.nk); R.T_b = c->plane3k("pgf.T_b", G.nk);
+    R.S_t = c->plane3k("pgf.S_t", G.nk); R.S_b = c->plane3k("pgf.S_b", G.nk);
+    if (!R.T_t || !R.T_b || !R.S_t || !R.S_b) return MOM6CU_ERR_CUDA;
+    const dim3 ge(grid.x, grid.y, 2);
+    if (G.nk <= 40) M6_LAUNCH(c, pgf_ts_edges_kernel<40>, ge, 128, 0, G, K, R);
+    else if (G.nk <= 80) M6_LAUNCH(c, pgf_ts_edges_kernel<80>, ge, 128, 0, G, K, R);
+    else M6_LAUNCH(c, pgf_ts_edges_kernel<128>, ge, 128, 0, G, K, R);
+    constexpr int TX = 32, TY = 8;
+    const dim3 gr((d.iec - d.isc + 2 + TX - 2) / (TX - 1), (d.jec - d.jsc + 2 + TY - 2) / (TY - 1));
+    if (S.Recon_Scheme == 2) M6_LAUNCH(c, (pgf_recon_kernel<true, TX, TY>), gr, TX * TY, 0, G, K, R);
+    else M6_LAUNCH(c, (pgf_recon_kernel<false, TX, TY>), gr, TX * TY, 0, G, K, R);
+    M6_CUDA(c, cudaGetLastError());
+    return 0;
+  }
   {  // resident CTAs per SM: 2 (194 registers, no spills), 3 (168) or 4 (128, ~30 doubles spilled); MOM6CU_PGF_MINB overrides
     static int minb = -1;
     if (minb < 0) { const char* e = getenv("MOM6CU_PGF_MINB"); minb = e ? atoi(e) : PGF_MINB_DEFAULT; }
@@ -326,9 +347,21 @@ extern "C" int mom6cu_set_cs_pressureforce(mom6cu_ctx* c, const mom6cu_pressuref
   M6_CUDA(c, cudaSetDevice(c->device));
   if (CS->unsupported)
     return c->fail(MOM6CU_ERR_UNSUPPORTED, "PressureForce_init: tides/SAL, Stanley SGS, intxpa resets/corrections, bulk mixed layers and "
-                                           "sub-layer T,S reconstructions are outside the frozen option set of this build");
+                                           "non-Boussinesq dynamics are outside the frozen option set of this build");
   if (CS->EOS_form != MOM6CU_EOS_NONE && CS->EOS_form != MOM6CU_EOS_LINEAR && CS->EOS_form != MOM6CU_EOS_WRIGHT)
     return c->fail(MOM6CU_ERR_UNSUPPORTED, "PressureForce: No analytic integration option is available with this EOS!");
+  if (CS->reconstruct && CS->EOS_form != MOM6CU_EOS_NONE && CS->Recon_Scheme > 0) {
+    if (CS->Recon_Scheme > 2) return c->fail(MOM6CU_ERR_BAD_ARG, "PressureForce: PRESSURE_RECONSTRUCTION_SCHEME must be 1 (PLM) or 2 (PPM)");
+    if (CS->ALE_answer_date < 20190101)
+      return c->fail(MOM6CU_ERR_UNSUPPORTED, "PressureForce: ALE answer_date %d < 20190101 is not implemented", CS->ALE_answer_date);
+    if (c->g.nk > 128) return c->fail(MOM6CU_ERR_UNSUPPORTED, "PressureForce: %d levels exceed the 128-level column capacity of the T,S reconstruction", c->g.nk);
+    if (c->g.nk < (CS->Recon_Scheme == 2 ? 4 : 2)) return c->fail(MOM6CU_ERR_BAD_ARG, "PressureForce: too few layers for the T,S reconstruction");
+  }
+  {  // EOS_type unit conversion factors: the device path is the unscaled one (0 is read as 1)
+    const double sc[4] = {CS->kg_m3_to_R, CS->RL2_T2_to_Pa, CS->C_to_degC, CS->S_to_ppt};
+    for (double v : sc)
+      if (v != 0.0 && v != 1.0) return c->fail(MOM6CU_ERR_UNSUPPORTED, "PressureForce: rescaled EOS units (EOS%%kg_m3_to_R etc. /= 1) are not implemented on the device");
+  }
   c->pgf_cs = *CS;
   c->pgf_Rlay = nullptr; c->pgf_gprime = nullptr;
   if (CS->EOS_form == MOM6CU_EOS_NONE) {

@@ -265,3 +265,11 @@ extern "C" int oracle_mixedlayer_restrat(const mom6cu_domain* d, const mom6cu_gr
   }
   return 0;
 }
+
+// The density_elem restatement this file uses, for the known-answer test of the equation of state (tests/test_oracle_eos_kat.py).
+extern "C" double oracle_mle_eos_density(int form, const double* lin4, double T, double S, double p) {
+  mom6cu_mle_cs E = {};
+  E.EOS_form = form;
+  if (lin4) { E.Rho_T0_S0 = lin4[0]; E.dRho_dT = lin4[1]; E.dRho_dS = lin4[2]; E.dRho_dp = lin4[3]; }
+  return density(&E, T, S, p);
+}

@@ -47,6 +47,11 @@ struct OGrid {
   A2 aQ() const { return A2(isd - 1, ied, jsd - 1, jed); }
 };
 
+// column reconstructions of oracle/remap.cpp used outside it (1-based arrays, element 0 unused)
+void ale_plm_edge_values_column(int nk, const double* h, const double* Q, bool bdry_extrap, double h_neglect, double* Q_t, double* Q_b);
+void ale_ppm_edge_values_column(int nk, const double* h, const double* Q, bool bdry_extrap, double h_neglect, double h_neglect_edge,
+                                double* Q_t, double* Q_b);
+
 static inline double max4(double a, double b, double c, double d) { return fmax2(fmax2(fmax2(a, b), c), d); }
 static inline double min4(double a, double b, double c, double d) { return fmin2(fmin2(fmin2(a, b), c), d); }
 

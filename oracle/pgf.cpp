@@ -4,47 +4,36 @@
 //   int_density_dz_linear (src/equation_of_state/MOM_EOS_linear.F90:275-440)
 //   int_density_dz_wright (src/equation_of_state/MOM_EOS_Wright.F90:389-655), density_elem / calculate_density_derivs_elem (:80, :178)
 //   Set_pbce_Bouss (src/core/MOM_PressureForce_Montgomery.F90:649-748)
-// Frozen options: no tides/SAL, no Stanley term, no intxpa corrections/resets, nk_rho_varies = 0, layer-constant T,S.
+//   RECONSTRUCT_FOR_PRESSURE: TS_PLM_edge_values / TS_PPM_edge_values (src/ALE/MOM_ALE.F90:1495-1660) and the quadrature integrals
+//   int_density_dz_generic_plm (src/core/MOM_density_integrals.F90:418-868) / int_density_dz_generic_ppm (:874-1310)
+// Frozen options: no tides/SAL, no Stanley term, no intxpa corrections/resets, nk_rho_varies = 0.
+// The EOS elements (oracle/eos.hpp) are PINNED to the reference's check values (tests/test_oracle_eos_kat.py); the analytic layer
+// integrals are checked against Boole quadrature of that pinned density; the routine as a whole has no vector in the reference.
 #include "oracle.h"
 #include "ogrid.hpp"
+#include "eos.hpp"
 #include <cmath>
+#include <vector>
 #include <omp.h>
 
 using namespace orc;
 
 namespace {
 
-// Wright (1997) "buggy" fit used by EOS_WRIGHT, MOM_EOS_Wright.F90:23-37
-const double a0 = 7.057924e-4, a1 = 3.480336e-7, a2 = -1.112733e-7;
-const double b0 = 5.790749e8, b1 = 3.516535e6, b2 = -4.002714e4, b3 = 2.084372e2, b4 = 5.944068e5, b5 = -9.643486e3;
-const double c0 = 1.704853e5, c1 = 7.904722e2, c2 = -7.984422, c3 = 5.140652e-2, c4 = -2.302158e2, c5 = -3.079464;
+using namespace orc::wright;
 
 inline double max3(double a, double b, double c) { return fmax2(fmax2(a, b), c); }
 
-struct EOSp { int form; double Rho_T0_S0, dRho_dT, dRho_dS, dRho_dp; };
-
-inline double density(const EOSp& E, double T, double S, double p) {
-  if (E.form == MOM6CU_EOS_LINEAR) return E.Rho_T0_S0 + E.dRho_dT * T + E.dRho_dS * S + E.dRho_dp * p;  // MOM_EOS_linear.F90:66
-  const double al0 = (a0 + a1 * T) + a2 * S;  // MOM_EOS_Wright.F90:91-94
-  const double p0 = (b0 + b4 * S) + T * (b1 + T * (b2 + b3 * T) + b5 * S);
-  const double lambda = (c0 + c4 * S) + T * (c1 + T * (c2 + c3 * T) + c5 * S);
-  return (p + p0) / (lambda + al0 * (p + p0));
-}
+inline double density(const EOSp& E, double T, double S, double p) { return calculate_density(E, T, S, p, nullptr); }
 inline void density_derivs(const EOSp& E, double T, double S, double p, double& drho_dT, double& drho_dS) {
-  if (E.form == MOM6CU_EOS_LINEAR) { drho_dT = E.dRho_dT; drho_dS = E.dRho_dS; return; }  // MOM_EOS_linear.F90:131-132
-  const double al0 = (a0 + a1 * T) + a2 * S;  // MOM_EOS_Wright.F90:193-204
-  const double p0 = (b0 + b4 * S) + T * (b1 + T * ((b2 + b3 * T)) + b5 * S);
-  const double lambda = (c0 + c4 * S) + T * (c1 + T * ((c2 + c3 * T)) + c5 * S);
-  double I_denom2 = 1.0 / (lambda + al0 * (p + p0));
-  I_denom2 = I_denom2 * I_denom2;
-  drho_dT = I_denom2 * (lambda * (b1 + T * (2.0 * b2 + 3.0 * b3 * T) + b5 * S) -
-                        (p + p0) * ((p + p0) * a1 + (c1 + T * (c2 * 2.0 + c3 * 3.0 * T) + c5 * S)));
-  drho_dS = I_denom2 * (lambda * (b4 + b5 * T) - (p + p0) * ((p + p0) * a2 + (c4 + c5 * T)));
+  calculate_density_derivs(E, T, S, p, drho_dT, drho_dS);
 }
 
 struct IntArgs {
   const OGrid* G; V2 T, S, z_t, z_b, dpa, intz_dpa, intx_dpa, inty_dpa, bathyT, SSH, Z_0p;
   double rho_ref, rho_0, G_e, dz_neglect; int MassWghtInterp;
+  // unit conversion factors handed down by analytic_int_density_dz (MOM_EOS.F90:1440-1470); all 1 in an unscaled run
+  double rho_scale = 1.0, pres_scale = 1.0, temp_scale = 1.0, saln_scale = 1.0;
 };
 
 // the weights of the mass-weighted interpolation shared by both EOS forms
@@ -110,19 +99,35 @@ void int_density_dz_linear(const IntArgs& A, const EOSp& E) {
   }
 }
 
-// int_density_dz_wright, MOM_EOS_Wright.F90:389-655 (no unit rescaling: rho_scale, pres_scale, temp_scale, saln_scale absent)
+// int_density_dz_wright, MOM_EOS_Wright.F90:389-655
 void int_density_dz_wright(const IntArgs& A) {
   const OGrid& G = *A.G;
   const int is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, Isq = G.IscB, Ieq = G.IecB, Jsq = G.JscB, Jeq = G.JecB;
   const double C1_3 = 1.0 / 3.0, C1_7 = 1.0 / 7.0, C1_9 = 1.0 / 9.0, C1_90 = 1.0 / 90.0;
-  const double GxRho = A.G_e * A.rho_0, g_Earth = A.G_e, Pa_to_RL2_T2 = 1.0, rho_ref_mks = A.rho_ref, I_Rho = 1.0 / A.rho_0;
+  // :497-534 (the scale factors are always present in the call from analytic_int_density_dz when any of them differs from 1;
+  // multiplying by factors that equal 1 changes nothing, so one code path restates both calls)
+  const double GxRho = A.pres_scale * A.G_e * A.rho_0, Pa_to_RL2_T2 = 1.0 / A.pres_scale;
+  const double g_Earth = (A.pres_scale * A.G_e) * A.rho_scale;
+  const double rho_ref_mks = A.rho_ref / A.rho_scale, I_Rho = A.rho_scale / A.rho_0;
+  double a1s = a1, a2s = a2, b1s = b1, b2s = b2, b3s = b3, b4s = b4, b5s = b5, c1s = c1, c2s = c2, c3s = c3, c4s = c4, c5s = c5;
+  if (A.temp_scale != 1.0) {
+    const double ts = A.temp_scale;
+    a1s = a1s * ts;
+    b1s = b1s * ts; b2s = b2s * (ts * ts); b3s = b3s * (ts * ts * ts); b5s = b5s * ts;
+    c1s = c1s * ts; c2s = c2s * (ts * ts); c3s = c3s * (ts * ts * ts); c5s = c5s * ts;
+  }
+  if (A.saln_scale != 1.0) {
+    a2s = a2s * A.saln_scale;
+    b4s = b4s * A.saln_scale; b5s = b5s * A.saln_scale;
+    c4s = c4s * A.saln_scale; c5s = c5s * A.saln_scale;
+  }
   const bool do_massWeight = (A.MassWghtInterp & 1) != 0, top_massWeight = (A.MassWghtInterp & 2) != 0;
   const V2 &T = A.T, &S = A.S, &z_t = A.z_t, &z_b = A.z_b, &z0pres = A.Z_0p, &dpa = A.dpa;
   A2 al0_2d = G.aH(), p0_2d = G.aH(), lambda_2d = G.aH();
   for (int j = Jsq; j <= Jeq + 1; ++j) for (int i = Isq; i <= Ieq + 1; ++i) {
-    al0_2d(i, j) = (a0 + a1 * T(i, j)) + a2 * S(i, j);
-    p0_2d(i, j) = (b0 + b4 * S(i, j)) + T(i, j) * (b1 + T(i, j) * ((b2 + b3 * T(i, j))) + b5 * S(i, j));
-    lambda_2d(i, j) = (c0 + c4 * S(i, j)) + T(i, j) * (c1 + T(i, j) * ((c2 + c3 * T(i, j))) + c5 * S(i, j));
+    al0_2d(i, j) = (a0 + a1s * T(i, j)) + a2s * S(i, j);
+    p0_2d(i, j) = (b0 + b4s * S(i, j)) + T(i, j) * (b1s + T(i, j) * ((b2s + b3s * T(i, j))) + b5s * S(i, j));
+    lambda_2d(i, j) = (c0 + c4s * S(i, j)) + T(i, j) * (c1s + T(i, j) * ((c2s + c3s * T(i, j))) + c5s * S(i, j));
     const double al0 = al0_2d(i, j), p0 = p0_2d(i, j), lambda = lambda_2d(i, j);
     const double dz = z_t(i, j) - z_b(i, j);
     const double p_ave = -GxRho * (0.5 * (z_t(i, j) + z_b(i, j)) - z0pres(i, j));
@@ -170,6 +175,157 @@ void int_density_dz_wright(const IntArgs& A) {
   }
 }
 
+
+// int_density_dz_generic_plm (MOM_density_integrals.F90:418-868, ppm = false) and int_density_dz_generic_ppm (:874-1310, ppm = true)
+// for layer k: 5-point Boole quadrature in the vertical of the density anomaly of linear / parabolic T,S profiles, and a 3 x 5 point
+// quadrature along each face.  No Stanley SGS terms.  Tm, Sm are the layer means (tv%T, tv%S), used by the parabolic form only.
+struct GenArgs {
+  const OGrid* G; int k;
+  V3 T_t, T_b, S_t, S_b, Tm, Sm, e;
+  V2 dpa, intz_dpa, intx_dpa, inty_dpa, bathyT, Z_0p;
+  double rho_ref, rho_0, G_e, dz_subroundoff, h_nv;
+  int MassWghtInterp, MassWghtInterpVanOnly, use_inaccurate_form;
+};
+
+void int_density_dz_generic(const GenArgs& A, const EOSp& EOS, bool ppm) {
+  const OGrid& G = *A.G;
+  const int Isq = G.IscB, Ieq = G.IecB, Jsq = G.JscB, Jeq = G.JecB, k = A.k;
+  const V3 &T_t = A.T_t, &T_b = A.T_b, &S_t = A.S_t, &S_b = A.S_b, &e = A.e;
+  const V2 &z0pres = A.Z_0p, &bathyT = A.bathyT, &dpa = A.dpa;
+  const double C1_90 = 1.0 / 90.0, G_e = A.G_e, rho_ref = A.rho_ref, dz_subroundoff = A.dz_subroundoff;
+  const double GxRho = A.G_e * A.rho_0;
+  const double massWeightToggle = (A.MassWghtInterp & 1) ? 1. : 0., TopWeightToggle = (A.MassWghtInterp & 2) ? 1. : 0.;
+  const double massWeightNVonlyToggle = A.MassWghtInterpVanOnly ? 0. : 1.;
+  const double h_nonvanished = A.h_nv;
+  const bool use_rho_ref = ppm ? true : !A.use_inaccurate_form;   // the parabolic form always passes rho_ref to the EOS (:1059)
+  double wt_t[6], wt_b[6];
+  for (int n = 1; n <= 5; ++n) { wt_t[n] = 0.25 * (double)(5 - n); wt_b[n] = 1.0 - wt_t[n]; }
+  auto dens = [&](double T, double S, double p) { return use_rho_ref ? calculate_density(EOS, T, S, p, &rho_ref) : calculate_density(EOS, T, S, p, nullptr); };
+
+  // 1. vertical integrals (:563-614 / :1030-1077)
+  for (int j = Jsq; j <= Jeq + 1; ++j) for (int i = Isq; i <= Ieq + 1; ++i) {
+    double s6 = 0., t6 = 0.;
+    if (ppm) {
+      s6 = 3.0 * (2.0 * A.Sm(i, j, k) - (S_t(i, j, k) + S_b(i, j, k)));
+      t6 = 3.0 * (2.0 * A.Tm(i, j, k) - (T_t(i, j, k) + T_b(i, j, k)));
+    }
+    const double dz = e(i, j, k) - e(i, j, k + 1);
+    double r5[6], u5[6];
+    for (int n = 1; n <= 5; ++n) {
+      const double p5 = -GxRho * ((e(i, j, k) - z0pres(i, j)) - 0.25 * (double)(n - 1) * dz);
+      double S5, T5;
+      if (ppm) {
+        S5 = wt_t[n] * S_t(i, j, k) + wt_b[n] * (S_b(i, j, k) + s6 * wt_t[n]);
+        T5 = wt_t[n] * T_t(i, j, k) + wt_b[n] * (T_b(i, j, k) + t6 * wt_t[n]);
+      } else {
+        S5 = wt_t[n] * S_t(i, j, k) + wt_b[n] * S_b(i, j, k);
+        T5 = wt_t[n] * T_t(i, j, k) + wt_b[n] * T_b(i, j, k);
+      }
+      r5[n] = dens(T5, S5, p5);
+      u5[n] = r5[n] - rho_ref;
+    }
+    if (use_rho_ref) {
+      const double rho_anom = C1_90 * (7.0 * (r5[1] + r5[5]) + 32.0 * (r5[2] + r5[4]) + 12.0 * r5[3]);
+      dpa(i, j) = G_e * dz * rho_anom;
+      A.intz_dpa(i, j) = 0.5 * G_e * (dz * dz) * (rho_anom - C1_90 * (16.0 * (r5[4] - r5[2]) + 7.0 * (r5[5] - r5[1])));
+    } else {
+      const double rho_anom = C1_90 * (7.0 * (r5[1] + r5[5]) + 32.0 * (r5[2] + r5[4]) + 12.0 * r5[3]) - rho_ref;
+      dpa(i, j) = G_e * dz * rho_anom;
+      A.intz_dpa(i, j) = 0.5 * G_e * (dz * dz) * (rho_anom - C1_90 * (16.0 * (u5[4] - u5[2]) + 7.0 * (u5[5] - u5[1])));
+    }
+  }
+  // 2./3. horizontal integrals along x (dir 0: :617-744 / :1080-1198) and y (dir 1: :747-866 / :1201-1308)
+  for (int dir = 0; dir < 2; ++dir) {
+    const int di = dir == 0 ? 1 : 0, dj = dir == 0 ? 0 : 1;
+    const int jlo = dir == 0 ? G.jsc : Jsq, jhi = dir == 0 ? G.jec : Jeq, ilo = dir == 0 ? Isq : G.isc, ihi = dir == 0 ? Ieq : G.iec;
+    const V2& out = dir == 0 ? A.intx_dpa : A.inty_dpa;
+    for (int j = jlo; j <= jhi; ++j) for (int i = ilo; i <= ihi; ++i) {
+      const int ip = i + di, jp = j + dj;
+      double hWght = massWeightToggle * max3(0., -bathyT(i, j) - e(ip, jp, k), -bathyT(ip, jp) - e(i, j, k));
+      const double hWghtTop = TopWeightToggle * max3(0., e(ip, jp, k + 1) - e(i, j, 1), e(i, j, k + 1) - e(ip, jp, 1));
+      hWght = fmax2(hWght, hWghtTop);
+      if (((e(i, j, k) - e(i, j, k + 1)) > h_nonvanished) && ((e(ip, jp, k) - e(ip, jp, k + 1)) > h_nonvanished))
+        hWght = massWeightNVonlyToggle * hWght;
+      double Ttl, Tbl, Tml = 0., Ttr, Tbr, Tmr = 0., Stl, Sbl, Sml = 0., Str, Sbr, Smr = 0.;
+      if (hWght > 0.) {
+        const double hL = (e(i, j, k) - e(i, j, k + 1)) + dz_subroundoff;
+        const double hR = (e(ip, jp, k) - e(ip, jp, k + 1)) + dz_subroundoff;
+        const double r = (hL - hR) / (hL + hR);
+        hWght = hWght * (r * r);
+        const double iDenom = 1. / (hWght * (hR + hL) + hL * hR);
+        Ttl = ((hWght * hR) * T_t(ip, jp, k) + (hWght * hL + hR * hL) * T_t(i, j, k)) * iDenom;
+        Ttr = ((hWght * hL) * T_t(i, j, k) + (hWght * hR + hR * hL) * T_t(ip, jp, k)) * iDenom;
+        Tbl = ((hWght * hR) * T_b(ip, jp, k) + (hWght * hL + hR * hL) * T_b(i, j, k)) * iDenom;
+        Tbr = ((hWght * hL) * T_b(i, j, k) + (hWght * hR + hR * hL) * T_b(ip, jp, k)) * iDenom;
+        Stl = ((hWght * hR) * S_t(ip, jp, k) + (hWght * hL + hR * hL) * S_t(i, j, k)) * iDenom;
+        Str = ((hWght * hL) * S_t(i, j, k) + (hWght * hR + hR * hL) * S_t(ip, jp, k)) * iDenom;
+        Sbl = ((hWght * hR) * S_b(ip, jp, k) + (hWght * hL + hR * hL) * S_b(i, j, k)) * iDenom;
+        Sbr = ((hWght * hL) * S_b(i, j, k) + (hWght * hR + hR * hL) * S_b(ip, jp, k)) * iDenom;
+        if (ppm) {
+          Tml = ((hWght * hR) * A.Tm(ip, jp, k) + (hWght * hL + hR * hL) * A.Tm(i, j, k)) * iDenom;
+          Tmr = ((hWght * hL) * A.Tm(i, j, k) + (hWght * hR + hR * hL) * A.Tm(ip, jp, k)) * iDenom;
+          Sml = ((hWght * hR) * A.Sm(ip, jp, k) + (hWght * hL + hR * hL) * A.Sm(i, j, k)) * iDenom;
+          Smr = ((hWght * hL) * A.Sm(i, j, k) + (hWght * hR + hR * hL) * A.Sm(ip, jp, k)) * iDenom;
+        }
+      } else {
+        Ttl = T_t(i, j, k); Tbl = T_b(i, j, k); Ttr = T_t(ip, jp, k); Tbr = T_b(ip, jp, k);
+        Stl = S_t(i, j, k); Sbl = S_b(i, j, k); Str = S_t(ip, jp, k); Sbr = S_b(ip, jp, k);
+        if (ppm) { Tml = A.Tm(i, j, k); Tmr = A.Tm(ip, jp, k); Sml = A.Sm(i, j, k); Smr = A.Sm(ip, jp, k); }
+      }
+      double intz[6];
+      intz[1] = dpa(i, j); intz[5] = dpa(ip, jp);
+      for (int m = 2; m <= 4; ++m) {
+        const double w_left = wt_t[m], w_right = wt_b[m];
+        const double dz_x = (w_left * (e(i, j, k) - e(i, j, k + 1))) + (w_right * (e(ip, jp, k) - e(ip, jp, k + 1)));
+        double T15[6], S15[6], p15[6], r15[6];
+        p15[1] = -GxRho * ((w_left * (e(i, j, k) - z0pres(i, j))) + (w_right * (e(ip, jp, k) - z0pres(ip, jp))));
+        for (int n = 2; n <= 5; ++n) p15[n] = p15[n - 1] + GxRho * 0.25 * dz_x;
+        if (ppm) {
+          const double T_top = (w_left * Ttl) + (w_right * Ttr), T_mn = (w_left * Tml) + (w_right * Tmr), T_bot = (w_left * Tbl) + (w_right * Tbr);
+          const double S_top = (w_left * Stl) + (w_right * Str), S_mn = (w_left * Sml) + (w_right * Smr), S_bot = (w_left * Sbl) + (w_right * Sbr);
+          const double s6 = 3.0 * (2.0 * S_mn - (S_top + S_bot));
+          const double t6 = 3.0 * (2.0 * T_mn - (T_top + T_bot));
+          for (int n = 1; n <= 5; ++n) {
+            S15[n] = wt_t[n] * S_top + wt_b[n] * (S_bot + s6 * wt_t[n]);
+            T15[n] = wt_t[n] * T_top + wt_b[n] * (T_bot + t6 * wt_t[n]);
+          }
+        } else {
+          T15[1] = (w_left * Ttl) + (w_right * Ttr); T15[5] = (w_left * Tbl) + (w_right * Tbr);
+          S15[1] = (w_left * Stl) + (w_right * Str); S15[5] = (w_left * Sbl) + (w_right * Sbr);
+          for (int n = 2; n <= 4; ++n) {
+            S15[n] = wt_t[n] * S15[1] + wt_b[n] * S15[5];
+            T15[n] = wt_t[n] * T15[1] + wt_b[n] * T15[5];
+          }
+        }
+        for (int n = 1; n <= 5; ++n) r15[n] = dens(T15[n], S15[n], p15[n]);
+        if (use_rho_ref) intz[m] = (G_e * dz_x * (C1_90 * (7.0 * (r15[1] + r15[5]) + 32.0 * (r15[2] + r15[4]) + 12.0 * r15[3])));
+        else intz[m] = (G_e * dz_x * (C1_90 * (7.0 * (r15[1] + r15[5]) + 32.0 * (r15[2] + r15[4]) + 12.0 * r15[3]) - rho_ref));
+      }
+      out(i, j) = C1_90 * (7.0 * (intz[1] + intz[5]) + 32.0 * (intz[2] + intz[4]) + 12.0 * intz[3]);
+    }
+  }
+}
+
+// TS_PLM_edge_values / TS_PPM_edge_values, MOM_ALE.F90:1495-1660 (answer_date >= 20190101: h_neglect = h_neglect_edge = GV%H_subroundoff)
+void ts_edge_values(const OGrid& G, int scheme, bool bdry_extrap, double H_subroundoff, const V3& h, const V3& T, const V3& S, const V3& T_t,
+                    const V3& T_b, const V3& S_t, const V3& S_b) {
+  const int nz = G.ke;
+#pragma omp parallel for
+  for (int j = G.jsc - 1; j <= G.jec + 1; ++j) {
+    std::vector<double> hc(nz + 2), q(nz + 2), qt(nz + 2), qb(nz + 2);
+    for (int i = G.isc - 1; i <= G.iec + 1; ++i) {
+      for (int k = 1; k <= nz; ++k) hc[k] = h(i, j, k);
+      for (int f = 0; f < 2; ++f) {   // salinity first, then temperature (the order of the reference; the fields are independent)
+        const V3& Q = f == 0 ? S : T; const V3& Qt = f == 0 ? S_t : T_t; const V3& Qb = f == 0 ? S_b : T_b;
+        for (int k = 1; k <= nz; ++k) q[k] = Q(i, j, k);
+        if (scheme == 1) ale_plm_edge_values_column(nz, hc.data(), q.data(), bdry_extrap, H_subroundoff, qt.data(), qb.data());
+        else ale_ppm_edge_values_column(nz, hc.data(), q.data(), bdry_extrap, H_subroundoff, H_subroundoff, qt.data(), qb.data());
+        for (int k = 1; k <= nz; ++k) { Qt(i, j, k) = qt[k]; Qb(i, j, k) = qb[k]; }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int oracle_pressure_force(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vgrid* GV,
@@ -180,7 +336,14 @@ extern "C" int oracle_pressure_force(const mom6cu_domain* d, const mom6cu_grid* 
   const int is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, Isq = G.IscB, Ieq = G.IecB, Jsq = G.JscB, Jeq = G.JecB;
   const int nz = G.ke;
   const bool use_EOS = CS->EOS_form != MOM6CU_EOS_NONE, use_p_atm = A->p_atm != nullptr;
-  const EOSp E = {CS->EOS_form, CS->Rho_T0_S0, CS->dRho_dT, CS->dRho_dS, CS->dRho_dp};
+  EOSp E = {CS->EOS_form, CS->Rho_T0_S0, CS->dRho_dT, CS->dRho_dS, CS->dRho_dp};
+  if (CS->kg_m3_to_R != 0.0) { E.kg_m3_to_R = CS->kg_m3_to_R; E.R_to_kg_m3 = 1.0 / CS->kg_m3_to_R; }
+  if (CS->RL2_T2_to_Pa != 0.0) E.RL2_T2_to_Pa = CS->RL2_T2_to_Pa;
+  if (CS->C_to_degC != 0.0) E.C_to_degC = CS->C_to_degC;
+  if (CS->S_to_ppt != 0.0) E.S_to_ppt = CS->S_to_ppt;
+  // use_ALE = CS%reconstruct .and. use_EOS with an ALE control structure (:1120-1122); Recon_Scheme 1 = PLM, 2 = PPM (:2181)
+  const bool use_ALE = CS->reconstruct && use_EOS;
+  if (use_ALE && CS->Recon_Scheme > 0 && (CS->Recon_Scheme > 2 || CS->ALE_answer_date < 20190101 || nz < (CS->Recon_Scheme == 2 ? 4 : 2))) return 3;
   const V3 h = G.H3(A->h), PFu = G.U3(A->PFu), PFv = G.V3_(A->PFv);
   V3 T, S, pbce;
   if (use_EOS) { T = G.H3(A->T); S = G.H3(A->S); }
@@ -214,12 +377,29 @@ extern "C" int oracle_pressure_force(const mom6cu_domain* d, const mom6cu_grid* 
     else if (CS->use_SSH_in_Z0p) Z_0p(i, j) = e(i, j, 1);
     else Z_0p(i, j) = CS->Z_ref;
   }
+  // :1241-1250: sub-layer T,S profiles for the pressure integrals
+  A3 T_t(G.isd, G.ied, G.jsd, G.jed, use_ALE ? nz : 1), T_b(G.isd, G.ied, G.jsd, G.jed, use_ALE ? nz : 1);
+  A3 S_t(G.isd, G.ied, G.jsd, G.jed, use_ALE ? nz : 1), S_b(G.isd, G.ied, G.jsd, G.jed, use_ALE ? nz : 1);
+  if (use_ALE && CS->Recon_Scheme > 0) ts_edge_values(G, CS->Recon_Scheme, CS->boundary_extrap != 0, GV->H_subroundoff, h, T, S, T_t, T_b, S_t, S_b);
 #pragma omp parallel for
   for (int k = 1; k <= nz; ++k) {  // :1278-1337
     if (use_EOS) {
       IntArgs I = {&G, plane(T, k), plane(S, k), plane(e, k), plane(e, k + 1), plane(dpa, k), plane(intz_dpa, k), plane(intx_dpa, k),
                    plane(inty_dpa, k), G.bathyT, plane(e, 1), Z_0p, rho_ref, rho0_int_density, GV->g_Earth, dz_neglect, CS->MassWghtInterp};
-      if (CS->EOS_form == MOM6CU_EOS_LINEAR) int_density_dz_linear(I, E); else int_density_dz_wright(I);
+      if (use_ALE && CS->Recon_Scheme > 0) {  // :1286-1300
+        GenArgs Gn = {&G, k, T_t, T_b, S_t, S_b, T, S, e, plane(dpa, k), plane(intz_dpa, k), plane(intx_dpa, k), plane(inty_dpa, k), G.bathyT, Z_0p,
+                      rho_ref, rho0_int_density, GV->g_Earth, dz_neglect, GV->H_to_Z * CS->h_nonvanished, CS->MassWghtInterp,
+                      CS->MassWghtInterpVanOnly, CS->use_inaccurate_pgf_rho_anom};
+        int_density_dz_generic(Gn, E, CS->Recon_Scheme == 2);
+      } else if (CS->EOS_form == MOM6CU_EOS_LINEAR) {  // analytic_int_density_dz, MOM_EOS.F90:1440-1455
+        EOSp El = E;
+        El.Rho_T0_S0 = E.kg_m3_to_R * E.Rho_T0_S0; El.dRho_dT = (E.kg_m3_to_R * E.C_to_degC) * E.dRho_dT;
+        El.dRho_dS = (E.kg_m3_to_R * E.S_to_ppt) * E.dRho_dS; El.dRho_dp = (E.kg_m3_to_R * E.RL2_T2_to_Pa) * E.dRho_dp;
+        int_density_dz_linear(I, El);
+      } else {
+        I.rho_scale = E.kg_m3_to_R; I.pres_scale = E.RL2_T2_to_Pa; I.temp_scale = E.C_to_degC; I.saln_scale = E.S_to_ppt;
+        int_density_dz_wright(I);
+      }
       if (GV->Z_to_H != 1.0) for (int j = Jsq; j <= Jeq + 1; ++j) for (int i = Isq; i <= Ieq + 1; ++i) intz_dpa(i, j, k) = intz_dpa(i, j, k) * GV->Z_to_H;
     } else {
       A2 dz_geo = G.aH();
@@ -290,4 +470,16 @@ extern "C" int oracle_pressure_force(const mom6cu_domain* d, const mom6cu_grid* 
   }
   if (A->eta) for (int j = Jsq; j <= Jeq + 1; ++j) for (int i = Isq; i <= Ieq + 1; ++i) eta(i, j) = e(i, j, 1) * GV->Z_to_H;  // :1885-1887
   return 0;
+}
+
+// Accessors for the known-answer tests of the equation of state (tests/test_oracle_eos_kat.py): which = 0 density, 1 density anomaly
+// from rho_ref, 2 drho_dT, 3 drho_dS; scales = {kg_m3_to_R, RL2_T2_to_Pa, C_to_degC, S_to_ppt} or NULL.
+extern "C" double oracle_eos_eval(int which, int form, const double* lin4, const double* scales, double T, double S, double p, double rho_ref) {
+  EOSp E = {form, lin4 ? lin4[0] : 0., lin4 ? lin4[1] : 0., lin4 ? lin4[2] : 0., lin4 ? lin4[3] : 0.};
+  if (scales) { E.kg_m3_to_R = scales[0]; E.R_to_kg_m3 = 1.0 / scales[0]; E.RL2_T2_to_Pa = scales[1]; E.C_to_degC = scales[2]; E.S_to_ppt = scales[3]; }
+  if (which == 0) return calculate_density(E, T, S, p, nullptr);
+  if (which == 1) return calculate_density(E, T, S, p, &rho_ref);
+  double dT, dS;
+  calculate_density_derivs(E, T, S, p, dT, dS);
+  return which == 2 ? dT : dS;
 }

@@ -560,3 +560,22 @@ def thickness_diffuse(dom, grid, gv, cs, a, us=None):
     if rc:
         raise RuntimeError(f"oracle_thickness_diffuse: FATAL {rc}")
     return rc
+
+
+def eos_eval(which, form, T, S, p, rho_ref=0.0, lin4=None, scales=None, impl="pgf"):
+    """Equation-of-state elements: which = "rho" | "anom" | "drho_dT" | "drho_dS"; impl = "pgf" (oracle/eos.hpp), "mle", "thickdiff"."""
+    lib = load()
+    l4 = (C.c_double * 4)(*lin4) if lin4 is not None else None
+    if impl == "mle":
+        lib.oracle_mle_eos_density.restype = C.c_double
+        lib.oracle_mle_eos_density.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double]
+        return lib.oracle_mle_eos_density(form, l4, T, S, p)
+    if impl == "thickdiff":
+        a, b = C.c_double(), C.c_double()
+        lib.oracle_thickdiff_eos_derivs.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        lib.oracle_thickdiff_eos_derivs(form, l4, T, S, p, C.byref(a), C.byref(b))
+        return a.value if which == "drho_dT" else b.value
+    sc = (C.c_double * 4)(*scales) if scales is not None else None
+    lib.oracle_eos_eval.restype = C.c_double
+    lib.oracle_eos_eval.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+    return lib.oracle_eos_eval(dict(rho=0, anom=1, drho_dT=2, drho_dS=3)[which], form, l4, sc, T, S, p, rho_ref)

@@ -294,6 +294,43 @@ void PPM_boundary_extrapolation(int N, const double* h, const double* u, Poly& P
   P.c1[i1] = u0_l; P.c2[i1] = 6.0 * u1 - 4.0 * u0_l - 2.0 * u0_r; P.c3[i1] = 3.0 * (u0_r + u0_l - 2.0 * u1);
 }
 
+}  // namespace
+
+// ALE_PLM_edge_values (MOM_ALE.F90:1518-1576) for one column: Q_t, Q_b of a PLM reconstruction; arrays are 1-based (element 0 unused).
+// Used by the pressure-force restatement (TS_PLM_edge_values :1495), oracle/pgf.cpp.
+void orc::ale_plm_edge_values_column(int nk, const double* h, const double* Q, bool bdry_extrap, double h_neglect, double* Q_t, double* Q_b) {
+  vd slp(nk + 2, 0.);
+  slp[1] = 0.;
+  for (int k = 2; k <= nk - 1; ++k) slp[k] = PLM_slope_wa(h[k - 1], h[k], h[k + 1], h_neglect, Q[k - 1], Q[k], Q[k + 1]);
+  slp[nk] = 0.;
+  for (int k = 2; k <= nk - 1; ++k) {
+    const double mslp = PLM_monotonized_slope(Q[k - 1], Q[k], Q[k + 1], slp[k - 1], slp[k], slp[k + 1]);
+    Q_t[k] = Q[k] - 0.5 * mslp;
+    Q_b[k] = Q[k] + 0.5 * mslp;
+  }
+  if (bdry_extrap) {
+    double mslp = -PLM_extrapolate_slope(h[2], h[1], h_neglect, Q[2], Q[1]);
+    Q_t[1] = Q[1] - 0.5 * mslp; Q_b[1] = Q[1] + 0.5 * mslp;
+    mslp = PLM_extrapolate_slope(h[nk - 1], h[nk], h_neglect, Q[nk - 1], Q[nk]);
+    Q_t[nk] = Q[nk] - 0.5 * mslp; Q_b[nk] = Q[nk] + 0.5 * mslp;
+  } else {
+    Q_t[1] = Q[1]; Q_b[1] = Q[1]; Q_t[nk] = Q[nk]; Q_b[nk] = Q[nk];
+  }
+}
+
+// One field of TS_PPM_edge_values (MOM_ALE.F90:1620-1660; answer_date >= 20190101): edge_values_implicit_h4 + PPM_reconstruction
+// (+ PPM_boundary_extrapolation), returning ppol_E(:,1), ppol_E(:,2).  1-based arrays.
+void orc::ale_ppm_edge_values_column(int nk, const double* h, const double* Q, bool bdry_extrap, double h_neglect, double h_neglect_edge,
+                                     double* Q_t, double* Q_b) {
+  Poly P(nk);
+  edge_values_implicit_h4(nk, h, Q, P, h_neglect_edge);
+  PPM_reconstruction(nk, h, Q, P, h_neglect);
+  if (bdry_extrap) PPM_boundary_extrapolation(nk, h, Q, P, h_neglect);
+  for (int k = 1; k <= nk; ++k) { Q_t[k] = P.E1[k]; Q_b[k] = P.E2[k]; }
+}
+
+namespace {
+
 enum { INTEGRATION_PCM = 0, INTEGRATION_PLM = 1, INTEGRATION_PPM = 3 };
 
 // build_reconstructions_1d :410-550

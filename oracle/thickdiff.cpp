@@ -415,3 +415,11 @@ extern "C" int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_gri
   }
   return 0;
 }
+
+// The calculate_density_derivs restatement this file uses, for the known-answer test of the equation of state.
+extern "C" void oracle_thickdiff_eos_derivs(int form, const double* lin4, double T, double S, double p, double* drho_dT, double* drho_dS) {
+  mom6cu_thickness_diffuse_cs E = {};
+  E.EOS_form = form;
+  if (lin4) { E.dRho_dT = lin4[1]; E.dRho_dS = lin4[2]; }
+  density_derivs(&E, T, S, p, *drho_dT, *drho_dS);
+}

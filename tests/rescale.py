@@ -109,6 +109,12 @@ THICKDIFF = dict(h=THK, uhtr=VOL, vhtr=VOL, T=NONDIM, S=NONDIM, p_surf=NONDIM, d
                  slope_x=(0, -1, 0, 1), slope_y=(0, -1, 0, 1), cg1=VEL, MEKE_Kh=L2T)
 THICKDIFF_CS = dict(Khth=L2T, Khth_Min=L2T, Khth_Max=L2T, max_Khth_CFL=NONDIM, slope_max=(0, -1, 0, 1), kappa_smooth=HZT, dZ_subroundoff=ZL,
                     Rho_T0_S0=None, dRho_dT=None, dRho_dS=None, dRho_dp=None, FGNV_scale=NONDIM, N2_floor=(-2, 2, 0, -2), MEKE_KhTh_fac=NONDIM)
+# PressureForce_FV_Bouss (MOM_PressureForce_FV.F90:947-1090, CS :40-107).  Pressures are [R L2 T-2]; R is not rescaled, so the EOS conversion
+# factor RL2_T2_to_Pa (MOM_EOS.F90:144) carries [T2 L-2] and dRho_dp of the linear EOS is given in mks (scaled inside by dRdp_scale, :1443)
+PRES = (-2, 2, 0, 0)
+PGF = dict(h=THK, T=NONDIM, S=NONDIM, PFu=ACC, PFv=ACC, p_atm=PRES, pbce=(-2, 2, -1, 0), eta=THK)
+PGF_CS = dict(rho_ref=NONDIM, GFS_scale=NONDIM, Z_ref=ZL, dZ_subroundoff=ZL, Rho_T0_S0=NONDIM, dRho_dT=NONDIM, dRho_dS=NONDIM, dRho_dp=NONDIM, Rlay=NONDIM,
+              g_prime=(-2, 2, 0, -1), h_nonvanished=THK, kg_m3_to_R=NONDIM, RL2_T2_to_Pa=(2, -2, 0, 0), C_to_degC=NONDIM, S_to_ppt=NONDIM)
 # set_dtbt (MOM_barotropic.F90:3509-3633)
 SET_DTBT = dict(pbce=(-2, 2, -1, 0), gtot_est=(-2, 2, -1, 0), have_gtot_est=None, eta=THK, SSH_add=ZL, frhatu=NONDIM, frhatv=NONDIM, bathyT=ZL, bebt=NONDIM,
                 G_extra=NONDIM, dtbt_fraction=NONDIM, BT_Coriolis_scale=NONDIM, Z_ref=ZL, Nonlinear_continuity=None, **BT_CONT)

@@ -3,8 +3,8 @@ L_RESCALE_POWER, H_RESCALE_POWER, Z_RESCALE_POWER must reproduce ocean.stats bit
 re-expressed on the inputs of the hot path (tests/rescale.py): every dimensional input, metric and parameter of a stage is multiplied
 by the power of two its dimension [T^a L^b H^c Z^d] implies, the oracle is run on the rescaled problem and its answers, scaled back,
 must equal the un-scaled answers bit for bit.  A restatement that dropped a unit-conversion factor, mixed H with Z, or carries a
-dimensional constant of the wrong units cannot pass.  (the last of the substitute pins.)  PressureForce_FV is not covered:
-its analytic Wright integrals are restated without the reference's rho_scale / pres_scale arguments (oracle/pgf.cpp:113)."""
+dimensional constant of the wrong units cannot pass.  (the last of the substitute pins.)  PressureForce_FV is covered through the
+EOS conversion factors the reference carries for exactly this purpose (EOS%RL2_T2_to_Pa etc., MOM_EOS.F90:140-150)."""
 import numpy as np
 import pytest
 
@@ -163,6 +163,28 @@ def test_thickness_diffuse(oracle, p):
         oracle.thickness_diffuse(dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.THICKDIFF_CS, cs), p), s, us=RS.unit_scale(p))
         assert _same(ref, RS.scale(s, RS.THICKDIFF, p, inverse=True)), (p, kw)
         assert not np.array_equal(ref["h"], a["h"])
+
+
+@pytest.mark.parametrize("p", POWERS)
+def test_pressure_force(oracle, p):
+    """PressureForce_FV_Bouss under T, L, H, Z rescaling: analytic Wright / linear integrals with rho_scale / pres_scale (int_density_dz_wright,
+    MOM_EOS_Wright.F90:497-534), the layered form, and the quadrature integrals of RECONSTRUCT_FOR_PRESSURE through calculate_density's own
+    unit conversion (MOM_EOS.F90:332-352); Set_pbce_Bouss and the GFS_scale term included."""
+    from mom6_b200 import marshal
+    for kw in (dict(), dict(eos="LINEAR", dRho_dp=4.0e-6, MassWghtInterp=3, land_blocks=2), dict(eos="NONE"),
+               dict(with_p_atm=True, use_SSH_in_Z0p=1, MassWghtInterp=1, GFS_scale=0.5, land_blocks=2, Z_ref=1.5),
+               dict(reconstruct=1, Recon_Scheme=1, MassWghtInterp=1, land_blocks=2), dict(reconstruct=1, Recon_Scheme=2, boundary_extrap=1, with_p_atm=True),
+               dict(reconstruct=1, Recon_Scheme=1, eos="LINEAR", dRho_dp=4.0e-6, use_inaccurate_pgf_rho_anom=1, MassWghtInterpVanOnly=1, h_nonvanished=1.0e-3)):
+        dom, grid, gv, cs, a = synthetic.pressureforce_inputs(20, 14, 8, **kw)
+        cs = dict(marshal.PGF_RECON_DEFAULTS, **cs)
+        ref = _copy(a); oracle.pressure_force(dom, grid, gv, cs, ref)
+        gs, gvs = _grids(grid, gv, p)
+        s = RS.scale(a, RS.PGF, p)
+        oracle.pressure_force(dom, gs, gvs, RS.scale(cs, RS.with_flags(RS.PGF_CS, cs), p), s)
+        back = RS.scale(s, RS.PGF, p, inverse=True)
+        for k in ("PFu", "PFv", "pbce", "eta"):
+            assert np.array_equal(ref[k], back[k]), (p, kw, k, np.abs(ref[k] - back[k]).max())
+        assert np.abs(ref["PFu"]).max() > 0
 
 
 @pytest.mark.parametrize("p", POWERS)

@@ -18,8 +18,9 @@ elif stage == "continuity":
     dom, grid, gv, cs, a = synthetic.continuity_inputs(ni, nj, nk, land_blocks=40)
 elif stage == "hor_visc":
     dom, grid, gv, cs, a = synthetic.hor_visc_inputs(ni, nj, nk, land_blocks=40)
-elif stage == "pgf":
-    dom, grid, gv, cs, a = synthetic.pressureforce_inputs(ni, nj, nk, land_blocks=40)
+elif stage == "pgf":   # MOM6CU_PGF_RECON=1|2: RECONSTRUCT_FOR_PRESSURE with PLM | PPM profiles (the reference's ALE default is 1)
+    rs = int(os.environ.get("MOM6CU_PGF_RECON", "0"))
+    dom, grid, gv, cs, a = synthetic.pressureforce_inputs(ni, nj, nk, land_blocks=40, **(dict(reconstruct=1, Recon_Scheme=rs, MassWghtInterp=1) if rs else {}))
 elif stage == "remap":
     dom, grid, cs, a = synthetic.remap_inputs(ni, nj, nk, land_blocks=40)
     gv = synthetic.make_vgrid()
