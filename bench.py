@@ -37,9 +37,35 @@ BT_BYTES_PER_PT_SUBSTEP = 552   # 69 fp64 operands on the BT_cont pat
 # stage -> (calls per baroclinic step [MOM_dynamics_split_RK2.F90 line], algorithmic bytes per cell per call [SURVEY 8d])
 STEP = [("pressure_force", 1, 48), ("continuity", 3, 96), ("btcalc", 1, 32), ("bt_mass_source", 2, 8), ("btstep", 2, 136), ("coradcalc", 2, 56),
         ("horizontal_viscosity", 1, 40)]
-STAGES = ["step_MOM_dyn_split_RK2 (MOM_dynamics_split_RK2.F90:294-1205) as ONE device-resident call: PressureForce_FV_Bouss (Wright EOS) x1, "
-          "CorAdCalc x2(+1 with store_CAu), vertvisc_coef x3 + vertvisc x2 + vertvisc_remnant x3, continuity_PPM x3, btcalc x2, "
-          "bt_mass_source x2, btstep x2 (68 barotropic substeps each), horizontal_viscosity x1, the elementwise glue and the 7 group passes"]
+# DT, the prescribed DTBT > 0 (synthetic.btstep_inputs: 0.45 dx / sqrt(2 g H) with dx = 25 km, H = 4000 m) and DT_BT_FILTER of the workload
+DT, DTBT, DT_BT_FILTER = 900.0, 0.9 * 0.5 * 2.5e4 / (9.8 * 4000.0 * 2) ** 0.5, -0.25
+LAND_BLOCKS = 40                               # synthetic land: ~24 % of the 1440x1080 points (masks exercised as in a global ocean)
+PGF_RECON = dict(reconstruct=1, Recon_Scheme=1, boundary_extrap=0)   # RECONSTRUCT_FOR_PRESSURE=True, PRESSURE_RECONSTRUCTION_SCHEME=1 (PLM):
+#                                                                      the reference's defaults under ALE (MOM_PressureForce_FV.F90:2172-2190)
+
+
+def bt_substeps():
+    """nstep + nfilter of btstep for DT, DTBT, DT_BT_FILTER (MOM_barotropic.F90:780-802, :1678-1700)."""
+    import math
+    nstep = int(math.ceil(DT / DTBT - 0.0001))
+    dtbt = DT / nstep
+    dt_filt = 0.5 * max(0.0, min(DT_BT_FILTER, 2.0 * DT)) if DT_BT_FILTER >= 0.0 else 0.5 * max(0.0, DT * min(-DT_BT_FILTER, 2.0))
+    return nstep, int(math.ceil(dt_filt / dtbt))
+
+
+def workload_config():
+    """The `config` object: identical in both arms (the driver compares them)."""
+    nstep, nfilter = bt_substeps()
+    return {"workload": f"OM4_025-shaped {NI}x{NJ}x{NK} split-RK2 dynamics step",
+            "stages": ["step_MOM_dyn_split_RK2 (MOM_dynamics_split_RK2.F90:294-1205) as ONE call: PressureForce_FV_Bouss (Wright EOS, "
+                       "RECONSTRUCT_FOR_PRESSURE with PLM T,S profiles: int_density_dz_generic_plm) x1, CorAdCalc x2(+1 with store_CAu), "
+                       "vertvisc_coef x3 + vertvisc x2 + vertvisc_remnant x3, continuity_PPM x3, btcalc x2, bt_mass_source x2, "
+                       f"btstep x2 ({nstep} + {nfilter} = {nstep + nfilter} barotropic substeps each: DT = {DT:g} s, DTBT = {DTBT:.2f} s prescribed, "
+                       f"DT_BT_FILTER = {DT_BT_FILTER:g}), horizontal_viscosity x1, the elementwise glue and the 7 group passes"],
+            "stages_missing": MISSING, "land_blocks": LAND_BLOCKS, "seed": "synthetic.SEED (one global field set; tiles are cut from it)",
+            "l2": "inputs larger than L2 (about 28 GB of resident fields per 1440x1080x75 tile set are swept every step)"}
+
+
 MISSING = ["set_viscous_ML (a no-op with DYNAMIC_VISCOUS_ML=False)", "set_dtbt (calc_dtbt=False: CS%dtbt as stored)", "diagnostics / checksums"]
 
 
@@ -235,6 +261,70 @@ def thermo_pass(Context, synthetic, ni, nj, device):
     return out
 
 
+def _flatten(tree, path=()):
+    if isinstance(tree, dict):
+        for k in sorted(tree, key=str):
+            yield from _flatten(tree[k], path + (k,))
+    else:
+        yield path, tree
+
+
+def _unflatten(items):
+    out = {}
+    for path, v in items:
+        d = out
+        for k in path[:-1]:
+            d = d.setdefault(k, {})
+        d[path[-1]] = v
+    return out
+
+
+def tile_inputs(synthetic, torch, dist, world, rank, gni, gnj, npi, npj, nk=None, whalo=10):
+    """This rank's tile of ONE global synthetic field set (seed synthetic.SEED), so that every N runs the same problem and the state
+    checksums after the K steps can be compared across N (the reference's layout test, .testing/Makefile test.layout).  Rank 0 builds
+    the global inputs, cuts every rank's tile (synthetic.split_step_tile) and sends it over NCCL; nothing of this is timed."""
+    nk = NK if nk is None else nk
+    if world == 1:
+        return synthetic.step_dyn_inputs(gni, gnj, nk, whalo=whalo, land_blocks=LAND_BLOCKS, store_CAu=1)
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")   # cpu: the gloo test
+    if rank == 0:
+        dom_g, grid_g, gv, css, cs_g, a_g = synthetic.step_dyn_inputs(gni, gnj, nk, whalo=whalo, land_blocks=LAND_BLOCKS, store_CAu=1)
+        css_rest = {k: v for k, v in css.items() if k != "hor_visc"}
+        mine = None
+        for r in list(range(1, world)) + [0]:
+            dom, g, c, t, hv = synthetic.split_step_tile(dom_g, grid_g, cs_g, a_g, npi, npj, r % npi, r // npi, css["hor_visc"])
+            tree = {"grid": g, "cs": c, "a": t, "hv": hv, "gv": gv, "css": css_rest}
+            if r == 0:
+                mine = tree
+                break
+            items = list(_flatten(tree))
+            meta = [(p, ("nd", v.shape, str(v.dtype)) if isinstance(v, np.ndarray) else ("py", v)) for p, v in items]
+            dist.send_object_list([meta], dst=r)
+            for p, v in items:
+                if isinstance(v, np.ndarray):
+                    dist.send(torch.from_numpy(np.ascontiguousarray(v)).to(dev), dst=r)
+            del tree, items
+        del dom_g, grid_g, cs_g, a_g
+        tree = mine
+    else:
+        box = [None]
+        dist.recv_object_list(box, src=0)
+        items = []
+        for p, m in box[0]:
+            if m[0] == "nd":
+                buf = torch.empty(tuple(m[1]), dtype=getattr(torch, m[2]), device=dev)
+                dist.recv(buf, src=0)
+                items.append((p, buf.cpu().numpy()))
+            else:
+                items.append((p, m[1]))
+        tree = _unflatten(items)
+    pi, pj = rank % npi, rank // npi
+    dom = synthetic.make_domain(gni // npi, gnj // npj, nk=nk, halo=4, whalo=whalo, cyclic_x=True, cyclic_y=False, first_direction=0,
+                                npi=npi, npj=npj, pi=pi, pj=pj)
+    css = dict(tree["css"]); css["hor_visc"] = tree["hv"]
+    return dom, tree["grid"], tree["gv"], css, tree["cs"], tree["a"]
+
+
 def run_step(ctx, stages, times=None):
     """One baroclinic step: the implemented stages in the reference's call counts."""
     for name, calls, _ in STEP:
@@ -287,8 +377,11 @@ def cpu_reference(steps, warmup):
             return {k: clone(v) for k, v in x.items()}
         return x
 
-    base = synthetic.step_dyn_inputs(ni, nj, NK, whalo=10, land_blocks=3, store_CAu=1)
-    work = [base] + [(base[0], base[1], base[2], base[3], clone(base[4]), clone(base[5])) for _ in range(cores - 1)]
+    work = []
+    for w in range(cores):   # every rank its own tile: distinct seeds, the land-block count and PressureForce options of the GPU arm
+        t = synthetic.step_dyn_inputs(ni, nj, NK, whalo=10, land_blocks=LAND_BLOCKS, seed=synthetic.SEED + w, store_CAu=1)
+        t[3]["pressureforce"].update(PGF_RECON)
+        work.append(t)
 
     def run(w, n):
         dom, grid, gv, css, cs, a = work[w]
@@ -307,20 +400,22 @@ def cpu_reference(steps, warmup):
     t0 = time.perf_counter()
     all_workers(steps)
     t = time.perf_counter() - t0
+    land = float(np.mean([1.0 - w[1]["mask2dT"][4:-4, 4:-4].mean() for w in work]))
     return (cores * ni * nj * NK * steps / t, t, cores,
-            f"{steps} step(s) of step_MOM_dyn_split_RK2 on {cores} concurrent {ni}x{nj}x{NK} tiles (the 16x8 MPI-style decomposition of "
-            f"the workload, one single-threaded rank per core, no halo exchange)")
+            f"{warmup} warm-up + {steps} timed step(s) of step_MOM_dyn_split_RK2 on {cores} concurrent {ni}x{nj}x{NK} tiles (the tile size of a "
+            f"16x8 MPI-style decomposition of the workload, one single-threaded rank per core, each tile its own seed, land_blocks={LAND_BLOCKS} "
+            f"(land fraction {land:.2f}), no halo exchange)")
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; see module docstring)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    val, t, cores, sample = cpu_reference(args.steps, min(args.warmup, 1))
+    val, t, cores, sample = cpu_reference(args.steps, args.warmup)
     line = {"impl": "reference", "metric": "cell-updates/sec", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"OM4_025-shaped {NI}x{NJ}x{NK} split-RK2 dynamics step", "stages": STAGES, "stages_missing": MISSING},
+            "config": workload_config(),
             "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -362,9 +457,8 @@ def main():
     # strong scaling: the global domain is split into npi x npj tiles (one per GPU)
     npi, npj, pi, pj = tile_of(rank, world)
     ni, nj = gni // npi, gnj // npj
-    dom, grid, gv, css, cs, sa = synthetic.step_dyn_inputs(ni, nj, NK, whalo=10, land_blocks=40, seed=synthetic.SEED + rank, store_CAu=1)
-    if world > 1:
-        dom.npi, dom.npj, dom.pi, dom.pj = npi, npj, pi, pj
+    dom, grid, gv, css, cs, sa = tile_inputs(synthetic, torch, dist, world, rank, gni, gnj, npi, npj)
+    css["pressureforce"].update(PGF_RECON)
     ctx = Context(dom, local)
     if world > 1:
         ctx.attach_comm(dist)
@@ -395,6 +489,15 @@ def main():
         barrier()
         wall = time.perf_counter() - t0
     launches = ctx.launches - n1
+    # the reference's layout-invariance metric (bit-count checksums, MOM_checksums.F90:387-557) of the state after the W + K steps: every N
+    # steps the same global problem, so these must be identical in every line of a scaling run
+    state_chk = {}
+    try:
+        for k, stg in (("u_inst", 1), ("v_inst", 2), ("h", 0)):
+            bc, _, st = ctx.chksum(rsa[k], stg, haloshift=0, stats=True)
+            state_chk[k] = {"bitcount": int(bc[0]), "mean": float(st[0]), "min": float(st[1]), "max": float(st[2])}
+    except Exception as ex:
+        state_chk["error"] = repr(ex)
     # ---- e2e: the model state, tracers and forcing come from pinned HOST arrays every step and the new state goes back to
     # the host; the control structure (MOM_dyn_split_RK2_CS, BT_cont, barotropic_CS) and the transports stay on the device,
     # as they do between the reference's own steps.
@@ -422,7 +525,8 @@ def main():
     times, stage_passes = {}, 0
     if world == 1 and not args.no_stages:
         ctx.close()
-        domS, gridS, gvS, stages = synthetic.step_inputs(ni, nj, NK, whalo=10, land_blocks=40, seed=synthetic.SEED + rank)
+        domS, gridS, gvS, stages = synthetic.step_inputs(ni, nj, NK, whalo=10, land_blocks=LAND_BLOCKS, seed=synthetic.SEED + rank)
+        stages["pressure_force"][0].update(PGF_RECON)
         ctx = Context(domS, local)
         ctx.set_grid(gridS); ctx.set_vgrid(gvS)
         ctx.set_cs_continuity(stages["continuity"][0]); ctx.set_cs_coriolisadv(stages["coradcalc"][0])
@@ -489,14 +593,15 @@ def main():
               "algorithmic_B_per_cell": bpc}
     kernel_of = {"continuity": "cont_flux_tiled<zonal|meridional> + cont_convergence_kernel", "btstep": "bt_substep_kernel x26 + bt_col_kernel + bt_layer_accel_kernel", "vertvisc": "vv_coef_kernel + vv_solve_kernel",
                  "coradcalc": "corad_kernel", "horizontal_viscosity": "hor_visc_kernel", "btcalc": "btcalc_kernel", "bt_mass_source": "bt_mass_source_kernel",
-                 "pressure_force": "pgf_main_kernel", "step": "all stage kernels of one step"}
+                 "pressure_force": "pgf_ts_edges_kernel + pgf_recon_kernel (fp64-pipe bound: 35 EOS evaluations per cell)", "step": "all stage kernels of one step"}
     line = {"metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"OM4_025-shaped {gni}x{gnj}x{NK} split-RK2 dynamics step", "stages": STAGES, "stages_missing": MISSING,
-                       "tiles": f"{npi}x{npj}", "resident_planes": nplanes,
-                       "l2": f"inputs larger than L2 ({nplanes * ni * nj * 8 / 1e9:.1f} GB of resident fields swept per step)",
-                       "e2e": "state u,v,h + T,S + visc% + forces% from pinned host arrays each step, u,v,h,eta_av back; CS arrays and transports resident"},
+            "config": workload_config() if not args.size else dict(workload_config(), workload=f"OM4_025-shaped {gni}x{gnj}x{NK} split-RK2 dynamics step"),
+            "run": {"tiles": f"{npi}x{npj}", "resident_planes": nplanes, "resident_GB_per_rank": nplanes * ni * nj * 8 / 1e9,
+                    "e2e": "state u,v,h + T,S + visc% + forces% from pinned host arrays each step, u,v,h,eta_av back; CS arrays and transports resident"},
+            "state_checksum_after_steps": {"steps_run": args.warmup + args.steps, "fields": state_chk,
+                                           "note": "bit-count checksum + mean/min/max over the global domain; identical for every N"},
             "e2e": None if e2e_s is None else {"value": cells * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
                                                "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "ms_per_step_wall": 1e3 * wall / args.steps,

@@ -18,6 +18,7 @@
 //    evaluated by the host's libm (what the Fortran runtime calls) on the 2-D av_rem planes so that answers match
 //    the reference bit for bit; with BT_STRONG_DRAG=True everything stays on the device.
 #include "ctx.h"
+#include "pow_glibc.cuh"
 #include "bt_planes.h"
 #include "stage.h"
 #include <algorithm>
@@ -182,27 +183,30 @@ __global__ void bt_find_Cor_kernel(const Geom G, const Setup2D S) {  // btstep_f
   }
 }
 
-// Gathers the bases of bt_rem = mask * av_rem**Instep (:1497-1509) over (is-1:ie, js-1:je): 0 wherever the result is 0.
-__global__ void bt_rem_pack_kernel(m6::Geom G, const double* __restrict__ mu, const double* __restrict__ mv,
-                                   const double* __restrict__ au, const double* __restrict__ av, int is, int js, int nx, int ny,
-                                   double* __restrict__ pk, int which) {  // which: 1 = the u half, 2 = the v half, 3 = both
+// bt_rem = mask * av_rem**Instep (:1497-1509) over the faces (is-1:ie, js:je) and (is:ie, js-1:je), on the device: the real power is the
+// reference platform's own libm routine restated operation for operation (pow_glibc.cuh, bit-identical to glibc's pow on 6e8 tested
+// arguments), so no value leaves the GPU.  An argument outside that routine's validated domain (impossible for 0 < av_rem, Instep <= 1
+// unless av_rem < 1e-222) yields NaN, which the solver propagates into every output.
+__global__ void bt_rem_pow_kernel(m6::Geom G, const double* __restrict__ mu, const double* __restrict__ mv,
+                                  const double* __restrict__ au, const double* __restrict__ av, int is, int js, int nx, int ny,
+                                  double Instep, double* __restrict__ ru, double* __restrict__ rv) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nx * ny) return;
   const int i = is - 1 + n % nx, j = js - 1 + n / nx;
   const size_t g = (size_t)G.idx(i, j);
-  if (which & 1) pk[n] = (j >= js && mu[g] * au[g] > 0.0) ? au[g] : 0.0;
-  if (which & 2) pk[(size_t)nx * ny + n] = (i >= is && mv[g] * av[g] > 0.0) ? av[g] : 0.0;
-}
-__global__ void bt_rem_unpack_kernel(m6::Geom G, const double* __restrict__ mu, const double* __restrict__ mv,
-                                     const double* __restrict__ pk, int is, int js, int nx, int ny, double* __restrict__ ru,
-                                     double* __restrict__ rv) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nx * ny) return;
-  const int i = is - 1 + n % nx, j = js - 1 + n / nx;
-  const size_t g = (size_t)G.idx(i, j);
-  const double pu = pk[n], pv = pk[(size_t)nx * ny + n];
-  if (j >= js) ru[g] = (pu > 0.0) ? mu[g] * pu : 0.0;
-  if (i >= is) rv[g] = (pv > 0.0) ? mv[g] * pv : 0.0;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  if (j >= js) {
+    double r = 0.0;
+    const double m = mu[g], a = au[g];
+    if (m * a > 0.0) { bool ok = true; const double pw = m6pow::pow_glibc<true>(a, Instep, &ok); r = ok ? m * pw : qnan; }
+    ru[g] = r;
+  }
+  if (i >= is) {
+    double r = 0.0;
+    const double m = mv[g], a = av[g];
+    if (m * a > 0.0) { bool ok = true; const double pw = m6pow::pow_glibc<true>(a, Instep, &ok); r = ok ? m * pw : qnan; }
+    rv[g] = r;
+  }
 }
 
 __global__ void bt_Cor_ref_kernel(const Geom G, Pl4 f4u, Pl4 f4v, const double* ubt_Cor, const double* vbt_Cor,
@@ -439,37 +443,8 @@ int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev
   A.BT_force = (double*)P.BT_force_u; A.bt_rem = (double*)P.bt_rem_u; A.av_rem = av_rem_u;
   A.nlo = is - 1; A.nhi = ie; A.olo = js; A.ohi = je;
   M6_LAUNCH(c, bt_col_kernel<true>, grid2(ie - is + 2, je - js + 1, 128), 128, 0, G, A);
-  // ---- the viscous remnant with BT_STRONG_DRAG=False: av_rem**Instep by the host libm (:1497-1509).
-  // The base of the power is gathered on the device into one packed rectangle per face set (0 where the result is 0), the power
-  // itself is the host libm's (the only operation of the path that is not IEEE-exact, so the only one that has to be the
-  // reference platform's own routine), and mask*pow is scattered back on the device.  The u half travels on the side stream
-  // and is raised to the power while the device works through the v columns.
   const int pnx = ie - is + 2, pny = je - js + 2;  // covers (is-1:ie, js-1:je)
   const size_t npk = (size_t)pnx * pny;
-  double *dpk = nullptr, *hpk = nullptr;
-  static int nthr = 0;
-  if (nthr == 0) {
-    // thread count chosen here, not by OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to every rank, which would leave the
-    // loop on one core (MOM6CU_HOST_THREADS overrides; default = the rank's share of the host cores, at most 64)
-    const char* e = getenv("MOM6CU_HOST_THREADS");
-    const char* l = getenv("LOCAL_WORLD_SIZE");
-    const int hw = (int)std::thread::hardware_concurrency(), lws = (l && atoi(l) > 0) ? atoi(l) : 1;
-    nthr = (e && atoi(e) > 0) ? atoi(e) : std::max(1, std::min(64, hw / lws));
-  }
-  auto host_pow = [&](double* p, size_t n0) {
-    const long long nn = (long long)n0;
-#pragma omp parallel for schedule(static) num_threads(nthr)
-    for (long long n = 0; n < nn; ++n) p[n] = (p[n] > 0.0) ? std::pow(p[n], Instep) : 0.0;
-  };
-  if (!CS.strong_drag) {
-    dpk = c->buf("bt.rem_pack", 2 * npk);
-    hpk = c->host_scratch("bt.rem_pack", 2 * npk);
-    if (!dpk || !hpk) return MOM6CU_ERR_CUDA;
-    M6_LAUNCH(c, bt_rem_pack_kernel, dim3((unsigned)((npk + 127) / 128)), 128, 0, G, M.mask2dCu, M.mask2dCv, av_rem_u, av_rem_v, is, js, pnx, pny, dpk, 1);
-    M6_CUDA(c, cudaEventRecord(c->ev_side, c->stream));
-    M6_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_side, 0));
-    M6_CUDA(c, cudaMemcpyAsync(hpk, dpk, npk * sizeof(double), cudaMemcpyDeviceToHost, c->side));
-  }
   A.frhat = CS.frhatv; A.visc_rem = D.visc_rem_v; A.vel_Cor = D.V_Cor; A.vel_in = D.V_in; A.bc_accel = D.bc_accel_v;
   A.uh0 = D.vh0; A.u_uh0 = D.v_vh0; A.mask = M.mask2dCv; A.tau = D.tauy; A.tau_bot = (D.taux_bot && D.tauy_bot) ? D.tauy_bot : nullptr;
   A.IDat = CS.IDatv; A.btcl = bv;
@@ -491,22 +466,12 @@ int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev
   }
   M6_LAUNCH(c, bt_Cor_ref_kernel, grid2(ie - is + 2, je - js + 2, 128), 128, 0, G, f4u, f4v, ubt_Cor, vbt_Cor,
             (double*)P.Cor_ref_u, (double*)P.Cor_ref_v);
-  if (!CS.strong_drag) {  // the v half, then both halves back to the device
-    M6_LAUNCH(c, bt_rem_pack_kernel, dim3((unsigned)((npk + 127) / 128)), 128, 0, G, M.mask2dCu, M.mask2dCv, av_rem_u, av_rem_v, is, js, pnx, pny, dpk, 2);
-    M6_CUDA(c, cudaMemcpyAsync(hpk + npk, dpk + npk, npk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    M6_CUDA(c, cudaStreamSynchronize(c->side));
-    host_pow(hpk, npk);
-    M6_CUDA(c, cudaMemcpyAsync(dpk, hpk, npk * sizeof(double), cudaMemcpyHostToDevice, c->side));
-    M6_CUDA(c, cudaEventRecord(c->ev_side, c->side));
-    M6_CUDA(c, cudaStreamSynchronize(c->stream));
-    host_pow(hpk + npk, npk);
-    M6_CUDA(c, cudaMemcpyAsync(dpk + npk, hpk + npk, npk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    M6_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+  if (!CS.strong_drag) {  // the viscous remnant with BT_STRONG_DRAG=False (:1497-1509)
     // rows/columns outside the computational faces stay zero, as in the reference's zero-initialised wide arrays
     M6_CUDA(c, cudaMemsetAsync((double*)P.bt_rem_u, 0, pb, c->stream));
     M6_CUDA(c, cudaMemsetAsync((double*)P.bt_rem_v, 0, pb, c->stream));
-    M6_LAUNCH(c, bt_rem_unpack_kernel, dim3((unsigned)((npk + 127) / 128)), 128, 0, G, M.mask2dCu, M.mask2dCv, dpk, is, js, pnx, pny,
-              (double*)P.bt_rem_u, (double*)P.bt_rem_v);
+    M6_LAUNCH(c, bt_rem_pow_kernel, dim3((unsigned)((npk + 127) / 128)), 128, 0, G, M.mask2dCu, M.mask2dCv, av_rem_u, av_rem_v, is, js, pnx, pny,
+              Instep, (double*)P.bt_rem_u, (double*)P.bt_rem_v);
   }
   // ---- eta, eta_PF (:997-1003) and the mass source (:1549-1587) ----
   M6_LAUNCH(c, bt_copy_G_kernel, grid2(d.ied - d.isd + 1, d.jed - d.jsd + 1, 128), 128, 0, G, D.eta_in, B.eta[0], D.eta_PF_in, (double*)P.eta_PF);
