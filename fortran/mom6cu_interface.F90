@@ -162,6 +162,8 @@ module mom6cu_interface
   type, bind(C) :: mom6cu_dyn_split_rk2_cs
     real(c_double) :: be, begw
     integer(c_int) :: split_bottom_stress, store_CAu, CAu_pred_stored, visc_rem_dt_bug, hvel_scheme, unsupported
+    integer(c_int) :: dtbt_use_bt_cont, BT_Nonlinear_continuity
+    real(c_double) :: dtbt_fraction, BT_Coriolis_scale, Z_ref, dtbt_max
     type(c_ptr) :: CAu, CAv, CAu_pred, CAv_pred, PFu, PFv, diffu, diffv, visc_rem_u, visc_rem_v, u_accel_bt, v_accel_bt, &
                    u_av, v_av, h_av, pbce, eta, eta_PF, uhbt, vhbt, taux_bot, tauy_bot
     type(c_ptr) :: BT_cont, barotropic
@@ -238,6 +240,60 @@ module mom6cu_interface
     real(c_double) :: min_thickness, old_grid_weight, depth_of_time_filter_shallow, depth_of_time_filter_deep, Z_ref
     type(c_ptr) :: coordinateResolution
   end type mom6cu_regridding_cs
+
+  ! ---- generated from include/mom6cu.h by the same parser tests/test_abi_layout.py checks this file with ----
+  !> hor_visc_CS members (src/parameterizations/lateral/MOM_hor_visc.F90:38-250): switches and the precomputed metric / coefficient arrays
+  type, bind(C) :: mom6cu_hor_visc_cs
+    integer(c_int) :: Laplacian, biharmonic, no_slip, bound_Kh, better_bound_Kh, bound_Ah, better_bound_Ah, &
+                      backscatter_underbound, Smagorinsky_Kh, Smagorinsky_Ah, bound_Coriolis, use_land_mask, &
+                      add_LES_viscosity, use_cont_thick, use_cont_thick_bug, unsupported
+    real(c_double) :: Kh_bg_min, Re_Ah
+    type(c_ptr) :: dx2h, dy2h, DX_dyT, DY_dxT, reduction_xx, Kh_bg_xx, Ah_bg_xx, Kh_Max_xx, Ah_Max_xx, &
+                   Laplac2_const_xx, Biharm_const_xx, Biharm_const2_xx, Re_Ah_const_xx, dx2q, dy2q, DX_dyBu, DY_dxBu, &
+                   reduction_xy, Kh_bg_xy, Ah_bg_xy, Kh_Max_xy, Ah_Max_xy, Laplac2_const_xy, Biharm_const_xy, &
+                   Biharm_const2_xy, Re_Ah_const_xy, Idx2dyCu, Idxdy2u, Idx2dyCv, Idxdy2v
+  end type mom6cu_hor_visc_cs
+  !> btstep_timeloop's arguments (src/core/MOM_barotropic.F90:2175-2260)
+  type, bind(C) :: mom6cu_bt_timeloop_args
+    type(c_ptr) :: eta, ubt, vbt, uhbt0, vhbt0, Datu, Datv, BTCL_u, BTCL_v, eta_src, eta_PF, gtot_E, gtot_W, gtot_N, &
+                   gtot_S, f_4_u, f_4_v, bt_rem_u, bt_rem_v, BT_force_u, BT_force_v, Cor_ref_u, Cor_ref_v, &
+                   IareaT_OBCmask, IdxCu, IdyCv, u_accel_bt, v_accel_bt, eta_sum, eta_wtd, ubtav, vbtav, uhbtav, &
+                   vhbtav, ubt_wtd, vbt_wtd, wt_vel, wt_eta, wt_accel, wt_trans, wt_accel2
+    real(c_double) :: dtbt, dgeo_de, bebt, vel_underflow
+    integer(c_int) :: nstep, nfilter, use_BT_cont, find_etaav, BT_project_velocity, use_old_coriolis_bracket_bug, &
+                      use_wide_halos, min_stencil
+  end type mom6cu_bt_timeloop_args
+  !> btcalc's arguments (MOM_barotropic.F90:4360)
+  type, bind(C) :: mom6cu_btcalc_args
+    type(c_ptr) :: h, h_u, h_v, frhatu, frhatv, bathyT
+    integer(c_int) :: hvel_scheme, may_use_default
+  end type mom6cu_btcalc_args
+  !> set_dtbt's arguments (MOM_barotropic.F90:3509)
+  type, bind(C) :: mom6cu_set_dtbt_args
+    type(c_ptr) :: pbce
+    real(c_double) :: gtot_est
+    integer(c_int) :: have_gtot_est
+    type(c_ptr) :: BT_cont, eta
+    real(c_double) :: SSH_add
+    type(c_ptr) :: frhatu, frhatv, bathyT
+    real(c_double) :: bebt, G_extra, dtbt_fraction, BT_Coriolis_scale, Z_ref
+    integer(c_int) :: Nonlinear_continuity
+  end type mom6cu_set_dtbt_args
+  !> ALE_CS members and the fields ALE_regridding_and_remapping touches (src/ALE/MOM_ALE.F90:70-150, src/core/MOM.F90:1751-1926)
+  type, bind(C) :: mom6cu_ale_cs
+    type(mom6cu_regridding_cs) :: regridCS
+    type(mom6cu_remapping_cs) :: remapCS, vel_remapCS
+    real(c_double) :: regrid_time_scale
+    integer(c_int) :: remap_uv_using_old_alg, do_conv_adj, use_hybgen_unmix, remap_aux_vars
+  end type mom6cu_ale_cs
+  type, bind(C) :: mom6cu_ale_args
+    type(c_ptr) :: u, v, h
+    integer(c_int) :: ntr
+    type(c_ptr) :: tr, conc_underflow
+    integer(c_int) :: iT, iS
+    real(c_double) :: dtdia
+    type(c_ptr) :: Kd_shear, Kv_shear, Kv_shear_Bu
+  end type mom6cu_ale_args
 
   interface
     integer(c_int) function mom6cu_create(ctx, dom, device) bind(C, name="mom6cu_create")
@@ -416,6 +472,182 @@ module mom6cu_interface
     type(c_ptr) function mom6cu_plane_alloc(ctx, name, nk) bind(C, name="mom6cu_plane_alloc")
       import ; type(c_ptr), value :: ctx ; character(kind=c_char), intent(in) :: name(*) ; integer(c_int), value :: nk
     end function mom6cu_plane_alloc
+    ! ---- generated from the prototypes of include/mom6cu.h ----
+    integer(c_int) function mom6cu_ale_regridding_and_remapping(ctx, CS, dynCS, a) bind(C, name="mom6cu_ale_regridding_and_remapping")
+      import :: c_int, c_ptr, mom6cu_ale_args, mom6cu_ale_cs, mom6cu_dyn_split_rk2_cs
+      type(c_ptr), value :: ctx
+      type(mom6cu_ale_cs), intent(inout) :: CS
+      type(mom6cu_dyn_split_rk2_cs), intent(in) :: dynCS
+      type(mom6cu_ale_args), intent(in) :: a
+    end function mom6cu_ale_regridding_and_remapping
+    integer(c_int) function mom6cu_ale_remap_interface_vals(ctx, h_old, h_new, int_val) bind(C, name="mom6cu_ale_remap_interface_vals")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: h_old
+      type(c_ptr), value :: h_new
+      type(c_ptr), value :: int_val
+    end function mom6cu_ale_remap_interface_vals
+    integer(c_int) function mom6cu_ale_remap_vertex_vals(ctx, h_old, h_new, vert_val) bind(C, name="mom6cu_ale_remap_vertex_vals")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: h_old
+      type(c_ptr), value :: h_new
+      type(c_ptr), value :: vert_val
+    end function mom6cu_ale_remap_vertex_vals
+    integer(c_int) function mom6cu_btcalc(ctx, a) bind(C, name="mom6cu_btcalc")
+      import :: c_int, c_ptr, mom6cu_btcalc_args
+      type(c_ptr), value :: ctx
+      type(mom6cu_btcalc_args), intent(in) :: a
+    end function mom6cu_btcalc
+    integer(c_int) function mom6cu_btstep_timeloop_resident(ctx, a, reps, download) bind(C, name="mom6cu_btstep_timeloop_resident")
+      import :: c_int, c_ptr, mom6cu_bt_timeloop_args
+      type(c_ptr), value :: ctx
+      type(mom6cu_bt_timeloop_args), intent(in) :: a
+      integer(c_int), value :: reps
+      integer(c_int), value :: download
+    end function mom6cu_btstep_timeloop_resident
+    integer(c_int) function mom6cu_build_arch() bind(C, name="mom6cu_build_arch")
+      import :: c_int
+    end function mom6cu_build_arch
+    integer(c_int) function mom6cu_comm_destroy(ctx) bind(C, name="mom6cu_comm_destroy")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+    end function mom6cu_comm_destroy
+    subroutine mom6cu_efp_minus(a, b, out, overflow) bind(C, name="mom6cu_efp_minus")
+      import :: c_ptr, mom6cu_efp
+      type(mom6cu_efp), intent(in) :: a
+      type(mom6cu_efp), intent(in) :: b
+      type(mom6cu_efp), intent(inout) :: out
+      type(c_ptr), value :: overflow
+    end subroutine mom6cu_efp_minus
+    subroutine mom6cu_efp_plus(a, b, out, overflow) bind(C, name="mom6cu_efp_plus")
+      import :: c_ptr, mom6cu_efp
+      type(mom6cu_efp), intent(in) :: a
+      type(mom6cu_efp), intent(in) :: b
+      type(mom6cu_efp), intent(inout) :: out
+      type(c_ptr), value :: overflow
+    end subroutine mom6cu_efp_plus
+    real(c_double) function mom6cu_efp_real_diff(a, b) bind(C, name="mom6cu_efp_real_diff")
+      import :: c_double, mom6cu_efp
+      type(mom6cu_efp), intent(in) :: a
+      type(mom6cu_efp), intent(in) :: b
+    end function mom6cu_efp_real_diff
+    real(c_double) function mom6cu_efp_to_real(a) bind(C, name="mom6cu_efp_to_real")
+      import :: c_double, mom6cu_efp
+      type(mom6cu_efp), intent(inout) :: a
+    end function mom6cu_efp_to_real
+    integer(c_int) function mom6cu_halo_plan(dom, stagger, wide, halo, dir, send_box, recv_box) bind(C, name="mom6cu_halo_plan")
+      import :: c_int, c_ptr, mom6cu_domain
+      type(mom6cu_domain), intent(in) :: dom
+      integer(c_int), value :: stagger
+      integer(c_int), value :: wide
+      integer(c_int), value :: halo
+      integer(c_int), value :: dir
+      type(c_ptr), value :: send_box
+      type(c_ptr), value :: recv_box
+    end function mom6cu_halo_plan
+    integer(c_int) function mom6cu_interpolate_column(ctx, ncol, nsrc, h_src, u_src, ndest, h_dest, u_dest, mask_edges) bind(C, name="mom6cu_interpolate_column")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: ncol
+      integer(c_int), value :: nsrc
+      type(c_ptr), value :: h_src
+      type(c_ptr), value :: u_src
+      integer(c_int), value :: ndest
+      type(c_ptr), value :: h_dest
+      type(c_ptr), value :: u_dest
+      integer(c_int), value :: mask_edges
+    end function mom6cu_interpolate_column
+    integer(c_int) function mom6cu_last_iterations(ctx) bind(C, name="mom6cu_last_iterations")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+    end function mom6cu_last_iterations
+    real(c_double) function mom6cu_last_kernel_ms(ctx) bind(C, name="mom6cu_last_kernel_ms")
+      import :: c_double, c_ptr
+      type(c_ptr), value :: ctx
+    end function mom6cu_last_kernel_ms
+    integer(c_int) function mom6cu_last_step_stage_ms(ctx, ms, n) bind(C, name="mom6cu_last_step_stage_ms")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: ms
+      integer(c_int), value :: n
+    end function mom6cu_last_step_stage_ms
+    integer(c_int) function mom6cu_plane_download(ctx, plane, host, stagger, wide, nk) bind(C, name="mom6cu_plane_download")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: plane
+      type(c_ptr), value :: host
+      integer(c_int), value :: stagger
+      integer(c_int), value :: wide
+      integer(c_int), value :: nk
+    end function mom6cu_plane_download
+    integer(c_int) function mom6cu_plane_upload(ctx, plane, host, stagger, wide, nk) bind(C, name="mom6cu_plane_upload")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: plane
+      type(c_ptr), value :: host
+      integer(c_int), value :: stagger
+      integer(c_int), value :: wide
+      integer(c_int), value :: nk
+    end function mom6cu_plane_upload
+    integer(c_int) function mom6cu_real_to_efp(val, out) bind(C, name="mom6cu_real_to_efp")
+      import :: c_double, c_int, mom6cu_efp
+      real(c_double), value :: val
+      type(mom6cu_efp), intent(inout) :: out
+    end function mom6cu_real_to_efp
+    integer(c_int) function mom6cu_remap_dyn_split_rk2_aux_vars(ctx, remapCS, CS, h_old_u, h_old_v, h_new_u, h_new_v) bind(C, name="mom6cu_remap_dyn_split_rk2_aux_vars")
+      import :: c_int, c_ptr, mom6cu_dyn_split_rk2_cs, mom6cu_remapping_cs
+      type(c_ptr), value :: ctx
+      type(mom6cu_remapping_cs), intent(in) :: remapCS
+      type(mom6cu_dyn_split_rk2_cs), intent(in) :: CS
+      type(c_ptr), value :: h_old_u
+      type(c_ptr), value :: h_old_v
+      type(c_ptr), value :: h_new_u
+      type(c_ptr), value :: h_new_v
+    end function mom6cu_remap_dyn_split_rk2_aux_vars
+    integer(c_int) function mom6cu_remapping_core_h(ctx, CS, ncol, n0, h0, u0, n1, h1, u1) bind(C, name="mom6cu_remapping_core_h")
+      import :: c_int, c_ptr, mom6cu_remapping_cs
+      type(c_ptr), value :: ctx
+      type(mom6cu_remapping_cs), intent(in) :: CS
+      integer(c_int), value :: ncol
+      integer(c_int), value :: n0
+      type(c_ptr), value :: h0
+      type(c_ptr), value :: u0
+      integer(c_int), value :: n1
+      type(c_ptr), value :: h1
+      type(c_ptr), value :: u1
+    end function mom6cu_remapping_core_h
+    integer(c_int) function mom6cu_set_dtbt(ctx, a, dtbt, dtbt_max) bind(C, name="mom6cu_set_dtbt")
+      import :: c_int, c_ptr, mom6cu_set_dtbt_args
+      type(c_ptr), value :: ctx
+      type(mom6cu_set_dtbt_args), intent(in) :: a
+      type(c_ptr), value :: dtbt
+      type(c_ptr), value :: dtbt_max
+    end function mom6cu_set_dtbt
+    integer(c_int) function mom6cu_sync(ctx) bind(C, name="mom6cu_sync")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+    end function mom6cu_sync
+    real(c_double) function mom6cu_total_kernel_ms(ctx) bind(C, name="mom6cu_total_kernel_ms")
+      import :: c_double, c_ptr
+      type(c_ptr), value :: ctx
+    end function mom6cu_total_kernel_ms
+    integer(c_int) function mom6cu_vertvisc_get_coef(ctx, a_u, a_v, h_u, h_v) bind(C, name="mom6cu_vertvisc_get_coef")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: a_u
+      type(c_ptr), value :: a_v
+      type(c_ptr), value :: h_u
+      type(c_ptr), value :: h_v
+    end function mom6cu_vertvisc_get_coef
+    integer(c_long_long) function mom6cu_launch_count(ctx) bind(C, name="mom6cu_launch_count")
+      import :: c_long_long, c_ptr
+      type(c_ptr), value :: ctx
+    end function mom6cu_launch_count
+    integer(c_long_long) function mom6cu_sizeof(name) bind(C, name="mom6cu_sizeof")
+      import :: c_long_long, c_char
+      character(kind=c_char), intent(in) :: name(*)
+    end function mom6cu_sizeof
   end interface
 
   !> The one device context of this PE (one MPI rank = one tile = one GPU)

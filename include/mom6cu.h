@@ -69,6 +69,8 @@ int mom6cu_destroy(mom6cu_ctx* ctx);
 int mom6cu_last_error(const mom6cu_ctx* ctx, char* buf, size_t len);
 /* Library/build information: returns the sm arch the kernels were built for (100). */
 int mom6cu_build_arch(void);
+/* sizeof(struct <name>) of any struct declared in this header (-1: unknown name): for bindings to check their mirrors. */
+long long mom6cu_sizeof(const char* name);
 /* Number of kernel launches issued by this context since creation. */
 long long mom6cu_launch_count(const mom6cu_ctx* ctx);
 /* Block until all work queued on the context's streams is done. */

@@ -1,5 +1,6 @@
 // Context, device-memory and staging plumbing behind the C ABI.
 #include "ctx.h"
+#include <cstring>
 #include <cstdarg>
 #include <algorithm>
 
@@ -124,6 +125,50 @@ int m6_up_aos(mom6cu_ctx* c, const double* src, int nm, int stagger, int wide, d
 extern "C" {
 
 int mom6cu_build_arch(void) { return 100; }
+
+// sizeof of every struct that crosses the boundary, by name: lets a binding (ctypes, ISO_C_BINDING, ...) verify its mirror of
+// include/mom6cu.h at start-up (c_sizeof / storage_size against this) instead of discovering a layout slip as a wild pointer.
+long long mom6cu_sizeof(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "mom6cu_advect_tracer_args")) return (long long)sizeof(mom6cu_advect_tracer_args);
+  if (!strcmp(name, "mom6cu_ale_args")) return (long long)sizeof(mom6cu_ale_args);
+  if (!strcmp(name, "mom6cu_ale_cs")) return (long long)sizeof(mom6cu_ale_cs);
+  if (!strcmp(name, "mom6cu_barotropic_cs")) return (long long)sizeof(mom6cu_barotropic_cs);
+  if (!strcmp(name, "mom6cu_bt_cont")) return (long long)sizeof(mom6cu_bt_cont);
+  if (!strcmp(name, "mom6cu_bt_timeloop_args")) return (long long)sizeof(mom6cu_bt_timeloop_args);
+  if (!strcmp(name, "mom6cu_btcalc_args")) return (long long)sizeof(mom6cu_btcalc_args);
+  if (!strcmp(name, "mom6cu_btstep_args")) return (long long)sizeof(mom6cu_btstep_args);
+  if (!strcmp(name, "mom6cu_continuity_args")) return (long long)sizeof(mom6cu_continuity_args);
+  if (!strcmp(name, "mom6cu_continuity_cs")) return (long long)sizeof(mom6cu_continuity_cs);
+  if (!strcmp(name, "mom6cu_coradcalc_args")) return (long long)sizeof(mom6cu_coradcalc_args);
+  if (!strcmp(name, "mom6cu_coriolisadv_cs")) return (long long)sizeof(mom6cu_coriolisadv_cs);
+  if (!strcmp(name, "mom6cu_domain")) return (long long)sizeof(mom6cu_domain);
+  if (!strcmp(name, "mom6cu_dyn_split_rk2_cs")) return (long long)sizeof(mom6cu_dyn_split_rk2_cs);
+  if (!strcmp(name, "mom6cu_efp")) return (long long)sizeof(mom6cu_efp);
+  if (!strcmp(name, "mom6cu_energy_out")) return (long long)sizeof(mom6cu_energy_out);
+  if (!strcmp(name, "mom6cu_grid")) return (long long)sizeof(mom6cu_grid);
+  if (!strcmp(name, "mom6cu_hor_visc_args")) return (long long)sizeof(mom6cu_hor_visc_args);
+  if (!strcmp(name, "mom6cu_hor_visc_cs")) return (long long)sizeof(mom6cu_hor_visc_cs);
+  if (!strcmp(name, "mom6cu_mle_cs")) return (long long)sizeof(mom6cu_mle_cs);
+  if (!strcmp(name, "mom6cu_pressureforce_args")) return (long long)sizeof(mom6cu_pressureforce_args);
+  if (!strcmp(name, "mom6cu_pressureforce_cs")) return (long long)sizeof(mom6cu_pressureforce_cs);
+  if (!strcmp(name, "mom6cu_regridding_cs")) return (long long)sizeof(mom6cu_regridding_cs);
+  if (!strcmp(name, "mom6cu_remapping_cs")) return (long long)sizeof(mom6cu_remapping_cs);
+  if (!strcmp(name, "mom6cu_set_dtbt_args")) return (long long)sizeof(mom6cu_set_dtbt_args);
+  if (!strcmp(name, "mom6cu_step_dyn_args")) return (long long)sizeof(mom6cu_step_dyn_args);
+  if (!strcmp(name, "mom6cu_sum_output_cs")) return (long long)sizeof(mom6cu_sum_output_cs);
+  if (!strcmp(name, "mom6cu_thickness_diffuse_args")) return (long long)sizeof(mom6cu_thickness_diffuse_args);
+  if (!strcmp(name, "mom6cu_thickness_diffuse_cs")) return (long long)sizeof(mom6cu_thickness_diffuse_cs);
+  if (!strcmp(name, "mom6cu_tracer_advect_cs")) return (long long)sizeof(mom6cu_tracer_advect_cs);
+  if (!strcmp(name, "mom6cu_tracer_hor_diff_cs")) return (long long)sizeof(mom6cu_tracer_hor_diff_cs);
+  if (!strcmp(name, "mom6cu_tracer_hordiff_args")) return (long long)sizeof(mom6cu_tracer_hordiff_args);
+  if (!strcmp(name, "mom6cu_unit_scale")) return (long long)sizeof(mom6cu_unit_scale);
+  if (!strcmp(name, "mom6cu_vertvisc_args")) return (long long)sizeof(mom6cu_vertvisc_args);
+  if (!strcmp(name, "mom6cu_vertvisc_coef_args")) return (long long)sizeof(mom6cu_vertvisc_coef_args);
+  if (!strcmp(name, "mom6cu_vertvisc_cs")) return (long long)sizeof(mom6cu_vertvisc_cs);
+  if (!strcmp(name, "mom6cu_vgrid")) return (long long)sizeof(mom6cu_vgrid);
+  return -1;
+}
 
 int mom6cu_create(mom6cu_ctx** out, const mom6cu_domain* dom, int device) {
   if (!out || !dom) return MOM6CU_ERR_BAD_ARG;
