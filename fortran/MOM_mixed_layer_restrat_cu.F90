@@ -1,6 +1,6 @@
 !> Drop-in replacement for the compute entry of src/parameterizations/lateral/MOM_mixed_layer_restrat.F90: same module name and the
 !! same dummy argument list for mixedlayer_restrat (:149-186), body forwarded to the sm_100a library through mom6cu_interface.  It is
-!! the second worked binding (the first is MOM_continuity_PPM_cu.F90) and shows a caller of step_MOM_dynamics (MOM.F90:1422) whose
+!! a worked binding of a caller of the dycore (the dycore's own are fortran/bodies/*.inc, installed by fortran/install_shims.py) and shows a caller of step_MOM_dynamics (MOM.F90:1422) whose
 !! arguments are updated in place and whose control structure carries model state (CS%MLD_filtered, a restart field).
 !! The init / restart-registration routines of the reference module are kept as they are (they read parameters and allocate
 !! CS%MLD_filtered, :1618-2009).  The control structure's members are private to the module (:42), so this subroutine is a module

@@ -1,14 +1,14 @@
 !> ISO_C_BINDING interfaces to the B200-native dycore library (include/mom6cu.h, libmom6cu.so).
 !!
-!! This module is what a MOM6 maintainer adds to the source tree (e.g. under config_src/external/mom6cu/,
-!! selected at build time exactly like the other config_src/external/* and config_src/infra/FMS1|FMS2
-!! directory swaps, ac/configure.ac:227-264).  The drop-in replacement modules (MOM_continuity_PPM.F90,
-!! MOM_CoriolisAdv.F90, MOM_hor_visc.F90, MOM_barotropic.F90 ...) keep the reference's module names and
-!! public procedure signatures and forward to these interfaces; see fortran/MOM_continuity_PPM_cu.F90 for
-!! the worked example and INTEGRATION.md for the rest.
+!! This module is what a MOM6 maintainer adds to the source tree, together with the shadow copies of the modules on the hot path that
+!! fortran/install_shims.py writes (the reference's own files with a hook at the top of each replaced procedure and the binding procedures
+!! of fortran/bodies/*.inc appended), in a directory listed ahead of src/ -- the build-time directory swap MOM6 already uses for
+!! config_src/infra/FMS1|FMS2 and config_src/external/* (ac/configure.ac:227-264).  See INTEGRATION.md.
 !!
-!! NOTE: no Fortran compiler exists in the build container, so this file has not been compiled there; it
-!! uses only standard Fortran 2003 interoperability (bind(C), c_ptr, c_loc on contiguous targets).
+!! NOTE: no Fortran compiler exists in the build container, so this file has not been compiled there.  What a compiler would check is
+!! checked by parsers instead: tests/test_abi_layout.py (every bind(C) type below == its struct in include/mom6cu.h, member for member; every
+!! C entry has an interface; sizes against mom6cu_sizeof) and tests/test_fortran_shims.py (every member the bindings touch exists).
+!! Only standard Fortran 2003 interoperability is used (bind(C), c_ptr, c_loc on contiguous targets).
 module mom6cu_interface
   use, intrinsic :: iso_c_binding
   implicit none ; public
@@ -654,6 +654,12 @@ module mom6cu_interface
   type(c_ptr), save :: mom6cu_ctx = c_null_ptr
 
 contains
+
+  !> True once the driver has created the device context (mom6cu_create in initialize_MOM): the hooks the installer adds to the
+  !! reference's procedures (fortran/install_shims.py) take the device path only then, so an unmodified run is still possible.
+  logical function mom6cu_enabled()
+    mom6cu_enabled = c_associated(mom6cu_ctx)
+  end function mom6cu_enabled
 
   !> Turn a nonzero status into MOM_error(FATAL, msg) / MOM_error(WARNING, ...), the reference's error convention
   !! (src/framework/MOM_error_handler.F90).

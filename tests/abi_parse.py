@@ -50,6 +50,8 @@ def _join_continuations(src):
         if ln.lstrip().startswith("#"):
             continue
         if cur:
+            if not ln.strip():      # a comment-only or blank line inside a continued statement does not end it
+                continue
             ln = ln.lstrip()
             if ln.startswith("&"):
                 ln = ln[1:]
@@ -143,4 +145,54 @@ def fortran_bindc_interfaces(path):
         m = re.search(r"(?:function|subroutine)\s+(\w+)\s*\(.*bind\(C\s*,\s*name\s*=\s*\"(\w+)\"\)", ln, flags=re.I)
         if m:
             out[m.group(2)] = m.group(1)
+    return out
+
+
+def fortran_types(paths):
+    """{type name (lower): {member (lower): member's derived type name (lower) or None}} for every derived type defined in the sources."""
+    db = {}
+    for path in paths:
+        cur = None
+        for ln in _join_continuations(open(path, errors="replace").read()):
+            t = ln.strip()
+            m = re.match(r"type\s*(?:,\s*(?:public|private|bind\(C\)|abstract|extends\(\w+\)))*\s*(?:::)?\s*(\w+)\s*(?:;.*)?$", t, flags=re.I)
+            if m and not re.match(r"type\s*\(", t, flags=re.I) and cur is None and m.group(1).lower() not in ("is",):
+                cur = m.group(1).lower(); db.setdefault(cur, {})
+                continue
+            if cur and re.match(r"end\s*type", t, flags=re.I):
+                cur = None
+                continue
+            if cur and "::" in t:
+                spec, names = t.split("::", 1)
+                dm = re.match(r"\s*(?:type|class)\s*\(\s*(\w+)\s*\)", spec, flags=re.I)
+                dtype = dm.group(1).lower() if dm else None
+                for item in re.split(r",(?![^()]*\))", names):
+                    nm = re.match(r"\s*(\w+)", item)
+                    if nm:
+                        db[cur][nm.group(1).lower()] = dtype
+    return db
+
+
+def fortran_procedures(text):
+    """[(name, [dummy names], {dummy (lower): derived type name (lower) or None}, body text)] of the subroutines / functions in a source text."""
+    lines = _join_continuations(text)
+    out, cur = [], None
+    for ln in lines:
+        t = ln.strip()
+        m = re.match(r"(?:(?:pure|elemental|recursive|logical|integer|real)\s+)*(subroutine|function)\s+(\w+)\s*\(([^)]*)\)", t, flags=re.I)
+        if m and cur is None:
+            cur = [m.group(2), [a.strip() for a in m.group(3).split(",") if a.strip()], {}, []]
+            continue
+        if cur is not None:
+            if re.match(rf"end\s+(subroutine|function)\s+{cur[0]}\b", t, flags=re.I):
+                out.append((cur[0], cur[1], cur[2], "\n".join(cur[3]))); cur = None
+                continue
+            cur[3].append(t)
+            if "::" in t:
+                spec, names = t.split("::", 1)
+                dm = re.match(r"\s*(?:type|class)\s*\(\s*(\w+)\s*\)", spec, flags=re.I)
+                for item in re.split(r",(?![^()]*\))", names):
+                    nm = re.match(r"\s*(\w+)", item)
+                    if nm:
+                        cur[2][nm.group(1).lower()] = dm.group(1).lower() if dm else None
     return out

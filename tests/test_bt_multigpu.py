@@ -42,7 +42,7 @@ def _worker(rank, world, port, npi, npj, NI, NJ, whalo, nstep, nfilter, q):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("npi,npj", [(2, 1), (1, 2)])
+@pytest.mark.parametrize("npi,npj", [(2, 1), (1, 2), (2, 2), (4, 2)])
 def test_bt_timeloop_two_tiles_bitwise(oracle, npi, npj):
     import torch
     import torch.multiprocessing as mp

@@ -63,7 +63,7 @@ def _worker(rank, world, port, npi, npj, q, depth_list):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("npi,npj", [(2, 1), (1, 2), (2, 2)])
+@pytest.mark.parametrize("npi,npj", [(2, 1), (1, 2), (2, 2), (4, 2), (2, 4)])
 def test_step_two_tiles_bitwise(oracle, npi, npj):
     import torch
     import torch.multiprocessing as mp
