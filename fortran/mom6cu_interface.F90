@@ -648,6 +648,12 @@ module mom6cu_interface
       import :: c_long_long, c_char
       character(kind=c_char), intent(in) :: name(*)
     end function mom6cu_sizeof
+    integer(c_int) function mom6cu_plane_zero(ctx, plane, nk) bind(C, name="mom6cu_plane_zero")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: plane
+      integer(c_int), value :: nk
+    end function mom6cu_plane_zero
   end interface
 
   !> The one device context of this PE (one MPI rank = one tile = one GPU)

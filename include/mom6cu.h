@@ -105,6 +105,8 @@ double mom6cu_total_kernel_ms(const mom6cu_ctx* ctx);
 double* mom6cu_plane_alloc(mom6cu_ctx* ctx, const char* name, int nk);
 int mom6cu_plane_upload(mom6cu_ctx* ctx, double* plane, const double* host, int stagger, int wide, int nk);
 int mom6cu_plane_download(mom6cu_ctx* ctx, const double* plane, double* host, int stagger, int wide, int nk);
+/* plane(:,:,1:nk) = 0 on the device (asynchronous on the context's stream). */
+int mom6cu_plane_zero(mom6cu_ctx* ctx, double* plane, int nk);
 
 /* ------------------------------------------------------------ grid metrics */
 /* The fields of ocean_grid_type (src/core/MOM_grid.F90:75-175) the hot path reads.

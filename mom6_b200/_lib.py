@@ -398,6 +398,9 @@ def bind(lib):
     lib.mom6cu_plane_alloc.restype = C.c_void_p
     lib.mom6cu_plane_upload.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
     lib.mom6cu_plane_download.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    lib.mom6cu_plane_zero.argtypes = [vp, vp, C.c_int]
+    lib.mom6cu_sizeof.argtypes = [C.c_char_p]
+    lib.mom6cu_sizeof.restype = C.c_longlong
     lib.mom6cu_set_cs_pressureforce.argtypes = [vp, C.POINTER(PressureForceCS)]
     lib.mom6cu_pressure_force.argtypes = [vp, C.POINTER(PressureForceArgs)]
     lib.mom6cu_ale_remap_tracers.argtypes = [vp, C.POINTER(RemappingCS), vp, vp, C.c_int, C.POINTER(vp), vp]

@@ -113,6 +113,9 @@ class Plane:
         self.ctx._check(self.ctx.lib.mom6cu_plane_upload(self.ctx._h, self.ptr, host.ctypes.data, self.ST[self.stagger],
                                                          int(self.wide), self.nk))
 
+    def zero(self):
+        self.ctx._check(self.ctx.lib.mom6cu_plane_zero(self.ctx._h, self.ptr, self.nk))
+
     def download(self, host):
         self.ctx._check(self.ctx.lib.mom6cu_plane_download(self.ctx._h, self.ptr, host.ctypes.data, self.ST[self.stagger],
                                                            int(self.wide), self.nk))

@@ -278,6 +278,15 @@ int mom6cu_plane_download(mom6cu_ctx* c, const double* plane, double* host, int 
   return 0;
 }
 
+// A resident field set to zero on the device (the reference's  CS%uhtr(:,:,:) = 0.0  after tracer advection, MOM.F90:1540-1541, for a host
+// that keeps the accumulated transports resident).
+int mom6cu_plane_zero(mom6cu_ctx* c, double* plane, int nk) {
+  if (!c || !plane || nk < 1) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  M6_CUDA(c, cudaMemsetAsync(plane, 0, (size_t)c->g.plane * nk * sizeof(double), c->stream));
+  return 0;
+}
+
 int mom6cu_sync(mom6cu_ctx* c) {
   if (!c) return MOM6CU_ERR_BAD_ARG;
   M6_CUDA(c, cudaStreamSynchronize(c->stream));
