@@ -583,10 +583,23 @@ int m6_stage_barotropic_cs(mom6cu_ctx* c, Stager& S, const mom6cu_barotropic_cs*
     // tripolar polarity reversal is outside the frozen option set: the arrays must be all +1; checked on the host copy
     int ilo, ihi, jlo, jhi; m6_extent(c, ST_H, 1, &ilo, &ihi, &jlo, &jhi);
     const size_t n = (size_t)(ihi - ilo + 1) * (jhi - jlo + 1);
-    if (!m6_is_device_ptr(CSh->ua_polarity))
+    // (device-resident arrays are copied back and checked once per pointer; host arrays every call)
+    const double* pol[2] = {CSh->ua_polarity, CSh->va_polarity};
+    for (const double* p : pol) {
+      if (!p) continue;
+      const double* hp = p;
+      if (m6_is_device_ptr(p)) {
+        if (c->polarity_checked.count(p)) continue;
+        double* tmp = c->host_scratch("bt.polarity", n);
+        if (!tmp) return MOM6CU_ERR_CUDA;
+        M6_CUDA(c, cudaMemcpyAsync(tmp, p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        M6_CUDA(c, cudaStreamSynchronize(c->stream));
+        hp = tmp;
+      }
       for (size_t q = 0; q < n; ++q)
-        if ((CSh->ua_polarity && CSh->ua_polarity[q] < 0.0) || (CSh->va_polarity && CSh->va_polarity[q] < 0.0))
-          return c->fail(MOM6CU_ERR_UNSUPPORTED, "btstep: reversed polarity (tripolar fold) is outside the frozen option set");
+        if (hp[q] < 0.0) return c->fail(MOM6CU_ERR_UNSUPPORTED, "btstep: reversed polarity (tripolar fold) is outside the frozen option set");
+      if (hp != p) c->polarity_checked.insert(p);
+    }
   }
   if ((rc = S.in3(CSh->frhatu, ST_U, "cs.frhatu", &CS.frhatu)) || (rc = S.in3(CSh->frhatv, ST_V, "cs.frhatv", &CS.frhatv)) ||
       (rc = S.in2(CSh->IDatu, ST_U, "cs.IDatu", &CS.IDatu)) || (rc = S.in2(CSh->IDatv, ST_V, "cs.IDatv", &CS.IDatv)) ||

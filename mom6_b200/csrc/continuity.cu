@@ -540,8 +540,8 @@ __device__ __forceinline__ bool select_scans(int f, int ss, int nss, int nz, dou
 template <int NF, int NS>
 __host__ __device__ constexpr int task_slice(int q) { return (q * (32 / NF)) % NS + (q * (32 / NF)) / NS; }
 
-template <bool Z, int NF, int NS, int KPT>
-__global__ void __launch_bounds__(NF* NS, (KPT > 5 || NF * NS > 512) ? 1 : (NF * NS > 256 ? 2 : 512 / (NF * NS)))
+template <bool Z, int NF, int NS, int KPT, int MINB = 0>
+__global__ void __launch_bounds__(NF* NS, MINB > 0 ? MINB : ((KPT > 5 || NF * NS > 512) ? 1 : (NF * NS > 256 ? 2 : 512 / (NF * NS))))
 cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
   static_assert(NF <= 32 && (32 % NF) == 0 && NF * NS >= 4 * 32, "the four k-ordered tasks of a phase use one warp each");
   constexpr int T0 = task_slice<NF, NS>(0), T1 = task_slice<NF, NS>(1), T2 = task_slice<NF, NS>(2), T3 = task_slice<NF, NS>(3);
@@ -909,9 +909,9 @@ cont_flux_tiled(const Geom G, const ContCS CS, const FluxArgs A) {
 
 constexpr int CF_NS = 16;
 
-template <bool Z, int NF, int KPT, int NS = CF_NS>
+template <bool Z, int NF, int KPT, int NS = CF_NS, int MINB = 0>
 int launch_flux_tiled(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& A) {
-  auto kern = cont_flux_tiled<Z, NF, NS, KPT>;
+  auto kern = cont_flux_tiled<Z, NF, NS, KPT, MINB>;
   const size_t smem = ((size_t)7 * A.nk * NF + 8 * NF + 3 * NS * NF) * sizeof(double);
   M6_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((A.nhi - A.nlo + NF) / NF, A.ohi - A.olo + 1);
@@ -930,6 +930,9 @@ int launch_flux(mom6cu_ctx* c, const Geom& G, const ContCS& CS, const FluxArgs& 
   if (kpt <= 5 && nf == 8) return launch_flux_tiled<Z, 8, 2, 40>(c, G, CS, A);    // 8 faces x 40 slices x 2 layers (nk <= 80), 2 CTAs/SM
   if (kpt <= 5 && nf == 164) return launch_flux_tiled<Z, 16, 2, 40>(c, G, CS, A);  // 16 faces x 40 slices x 2 layers, 1 CTA/SM
   if (kpt <= 5 && nf == 88) return launch_flux_tiled<Z, 8, 5>(c, G, CS, A);
+  static int minb = -1;  // MOM6CU_CONT_MINB=3: the 5-layer variant compiled for 3 CTAs/SM (85 registers, spills to L1; 3 x 74 KB of shared memory)
+  if (minb < 0) { const char* e = getenv("MOM6CU_CONT_MINB"); minb = e ? atoi(e) : 0; }
+  if (kpt <= 5 && minb == 3) return launch_flux_tiled<Z, 16, 5, CF_NS, 3>(c, G, CS, A);
   if (kpt <= 5) return launch_flux_tiled<Z, 16, 5>(c, G, CS, A);
   if (kpt <= 8) return launch_flux_tiled<Z, 16, 8>(c, G, CS, A);
   // very deep columns: one thread per column

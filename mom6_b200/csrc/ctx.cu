@@ -257,7 +257,15 @@ double mom6cu_total_kernel_ms(const mom6cu_ctx* c) { return c ? c->total_ms : 0.
 double* mom6cu_plane_alloc(mom6cu_ctx* c, const char* name, int nk) {
   if (!c || !name || nk < 1) return nullptr;
   cudaSetDevice(c->device);
-  return c->buf(std::string("user.") + name, (size_t)c->g.plane * nk);
+  // A name already in use with a smaller size would be freed and reallocated by buf(), leaving the pointer handed out earlier dangling:
+  // refuse instead (the caller keeps its plane; a differently sized field needs its own name).
+  const std::string key = std::string("user.") + name;
+  auto it = c->buf_sz.find(key);
+  if (it != c->buf_sz.end() && it->second < (size_t)c->g.plane * nk) {
+    c->fail(MOM6CU_ERR_BAD_ARG, "plane_alloc: '%s' already exists with fewer levels; resident planes are never reallocated", name);
+    return nullptr;
+  }
+  return c->buf(key, (size_t)c->g.plane * nk);
 }
 
 int mom6cu_plane_upload(mom6cu_ctx* c, double* plane, const double* host, int stagger, int wide, int nk) {

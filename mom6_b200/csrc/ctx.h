@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -32,6 +33,7 @@ struct mom6cu_ctx {
   char err[1024] = {0};
   std::map<std::string, double*> bufs;
   std::map<std::string, size_t> buf_sz;
+  std::set<const void*> polarity_checked;  // resident ua_polarity / va_polarity arrays already verified to be all +1 (btstep)
   std::map<std::string, std::pair<double*, size_t>> pinned;  // page-locked host scratch
   void* comm = nullptr;  // ncclComm_t when multi-rank
   // resident grid metrics and resolved control structures

@@ -8,6 +8,7 @@
 #include "ctx.h"
 #include <nccl.h>
 #include <vector>
+#include <algorithm>
 
 using m6::Geom;
 
@@ -160,6 +161,11 @@ extern "C" int mom6cu_comm_destroy(mom6cu_ctx* c) {
 int m6_halo_nccl(mom6cu_ctx* c, double* const* fields, const int* staggers, int nfields, int wide, int nk, int halo) {
   if (!c->comm) return c->fail(MOM6CU_ERR_NCCL, "multi-rank halo exchange requested but no communicator is attached");
   if (nfields > MAXF) return c->fail(MOM6CU_ERR_BAD_ARG, "halo group of %d fields exceeds %d", nfields, MAXF);
+  {  // a halo wider than the memory halo of the fields would index outside their planes
+    const mom6cu_domain& d = c->dom;
+    const int hmax = wide ? std::min(d.isc - d.isdw, d.jsc - d.jsdw) : std::min(d.isc - d.isd, d.jsc - d.jsd);
+    if (halo > hmax) return c->fail(MOM6CU_ERR_BAD_ARG, "halo exchange of width %d requested on fields with a memory halo of %d", halo, hmax);
+  }
   const Geom& G = c->g;
   PackPlan S = {}, R = {};
   S.nf = R.nf = nfields;
@@ -202,19 +208,23 @@ int m6_halo_nccl(mom6cu_ctx* c, double* const* fields, const int* staggers, int 
   // A message sent towards direction d arrives at the peer from its direction -d: post the
   // receives in the order the peers post their sends (same DIRS order on every rank).
   static const int OPP[8] = {1, 0, 3, 2, 5, 4, 7, 6};
+  ncclResult_t post = ncclSuccess;   // the first failed post; the group is still closed so that the communicator stays usable
   ncclGroupStart();
   for (int dir = 0; dir < 8; ++dir) {
     if (!S.active[dir]) continue;
     if (peer[dir] == c->rank) continue;  // self-neighbour (reentrant with one tile in that direction)
-    ncclSend(S.buf[dir], (size_t)cnt[dir], ncclDouble, peer[dir], comm, c->stream);
+    const ncclResult_t q = ncclSend(S.buf[dir], (size_t)cnt[dir], ncclDouble, peer[dir], comm, c->stream);
+    if (q != ncclSuccess && post == ncclSuccess) post = q;
   }
   for (int dir = 0; dir < 8; ++dir) {
     const int rd = OPP[dir];  // what the peer sent towards `dir` lands in my halo on side -dir
     if (!R.active[rd]) continue;
     if (peer[rd] == c->rank) continue;
-    ncclRecv(R.buf[rd], (size_t)cnt[rd], ncclDouble, peer[rd], comm, c->stream);
+    const ncclResult_t q = ncclRecv(R.buf[rd], (size_t)cnt[rd], ncclDouble, peer[rd], comm, c->stream);
+    if (q != ncclSuccess && post == ncclSuccess) post = q;
   }
   ncclResult_t r = ncclGroupEnd();
+  if (post != ncclSuccess) return c->fail(MOM6CU_ERR_NCCL, "halo exchange: ncclSend/ncclRecv: %s", ncclGetErrorString(post));
   if (r != ncclSuccess) return c->fail(MOM6CU_ERR_NCCL, "halo exchange: %s", ncclGetErrorString(r));
   for (int dir = 0; dir < 8; ++dir) {
     if (!S.active[dir] || peer[dir] != c->rank) continue;

@@ -80,8 +80,11 @@ struct RhoFn {
 // what a column publishes per layer
 enum { Q_ET = 0, Q_EB, Q_TT, Q_TB, Q_ST, Q_SB, Q_TM, Q_SM, Q_DPA, Q_INTZ, Q_PA, Q_H, Q_N };
 
+// Not inlined, and the loop over the three sub-columns not unrolled: the two call sites (east and north face) x 3 sub-columns x 5 unrolled
+// equation-of-state evaluations were 30 copies of ~150 instructions, and instruction-cache misses were the second largest stall of the
+// kernel (ncu, profiles/r02_pgf_recon_ncu.md); the 5 evaluations of a sub-column stay unrolled for instruction-level parallelism.
 template <bool PPM>
-__device__ __forceinline__ double recon_face_integral(const PgfK& K, const PgfRecon& R, const RhoFn& rho, double GxRho, const double* L,
+__device__ __noinline__ double recon_face_integral(const PgfK& K, const PgfRecon& R, const RhoFn& rho, double GxRho, const double* L,
                                                       const double* Rt, int sq /* stride between quantities */, double bathyL, double bathyR,
                                                       double e1L, double e1R, double z0L, double z0R) {
   const double C1_90 = 1.0 / 90.0;
@@ -123,7 +126,8 @@ __device__ __forceinline__ double recon_face_integral(const PgfK& K, const PgfRe
   }
   double intz[6];
   intz[1] = L[Q_DPA * sq]; intz[5] = Rt[Q_DPA * sq];
-#pragma unroll
+  double i2 = 0., i3 = 0., i4 = 0.;
+#pragma unroll 1
   for (int m = 2; m <= 4; ++m) {
     const double w_left = 0.25 * (double)(5 - m), w_right = 1.0 - w_left;
     const double dz_x = (w_left * (eLt - eLb)) + (w_right * (eRt - eRb));
@@ -153,10 +157,12 @@ __device__ __forceinline__ double recon_face_integral(const PgfK& K, const PgfRe
       if (n > 1) p15 = p15 + GxRho * 0.25 * dz_x;
       r15[n] = rho(Tn, Sn, p15);
     }
-    if (rho.use_ref) intz[m] = (K.g_Earth * dz_x * (C1_90 * (7.0 * (r15[1] + r15[5]) + 32.0 * (r15[2] + r15[4]) + 12.0 * r15[3])));
-    else intz[m] = (K.g_Earth * dz_x * (C1_90 * (7.0 * (r15[1] + r15[5]) + 32.0 * (r15[2] + r15[4]) + 12.0 * r15[3]) - rho.rho_ref));
+    double iz;
+    if (rho.use_ref) iz = (K.g_Earth * dz_x * (C1_90 * (7.0 * (r15[1] + r15[5]) + 32.0 * (r15[2] + r15[4]) + 12.0 * r15[3])));
+    else iz = (K.g_Earth * dz_x * (C1_90 * (7.0 * (r15[1] + r15[5]) + 32.0 * (r15[2] + r15[4]) + 12.0 * r15[3]) - rho.rho_ref));
+    if (m == 2) i2 = iz; else if (m == 3) i3 = iz; else i4 = iz;
   }
-  return C1_90 * (7.0 * (intz[1] + intz[5]) + 32.0 * (intz[2] + intz[4]) + 12.0 * intz[3]);
+  return C1_90 * (7.0 * (intz[1] + intz[5]) + 32.0 * (i2 + i4) + 12.0 * i3);
 }
 
 template <bool PPM, int TX, int TY>
