@@ -80,11 +80,11 @@ struct RhoFn {
 // what a column publishes per layer
 enum { Q_ET = 0, Q_EB, Q_TT, Q_TB, Q_ST, Q_SB, Q_TM, Q_SM, Q_DPA, Q_INTZ, Q_PA, Q_H, Q_N };
 
-// Not inlined, and the loop over the three sub-columns not unrolled: the two call sites (east and north face) x 3 sub-columns x 5 unrolled
-// equation-of-state evaluations were 30 copies of ~150 instructions, and instruction-cache misses were the second largest stall of the
-// kernel (ncu, profiles/r02_pgf_recon_ncu.md); the 5 evaluations of a sub-column stay unrolled for instruction-level parallelism.
+// Inlined at both call sites with the sub-column loop unrolled: the out-of-line variant (one copy of the 15 evaluations instead of 30, to
+// relieve the instruction cache) measured 34.5 ms against 30.6 ms at 1440x1080x75 -- the call overhead and the lost overlap between
+// sub-columns cost more than the instruction-cache misses it removed.
 template <bool PPM>
-__device__ __noinline__ double recon_face_integral(const PgfK& K, const PgfRecon& R, const RhoFn& rho, double GxRho, const double* L,
+__device__ __forceinline__ double recon_face_integral(const PgfK& K, const PgfRecon& R, const RhoFn& rho, double GxRho, const double* L,
                                                       const double* Rt, int sq /* stride between quantities */, double bathyL, double bathyR,
                                                       double e1L, double e1R, double z0L, double z0R) {
   const double C1_90 = 1.0 / 90.0;
@@ -127,7 +127,7 @@ __device__ __noinline__ double recon_face_integral(const PgfK& K, const PgfRecon
   double intz[6];
   intz[1] = L[Q_DPA * sq]; intz[5] = Rt[Q_DPA * sq];
   double i2 = 0., i3 = 0., i4 = 0.;
-#pragma unroll 1
+#pragma unroll
   for (int m = 2; m <= 4; ++m) {
     const double w_left = 0.25 * (double)(5 - m), w_right = 1.0 - w_left;
     const double dz_x = (w_left * (eLt - eLb)) + (w_right * (eRt - eRb));

@@ -51,8 +51,10 @@ def _setup(ctx_factory, dom, grid, gv, css=None):
     return ctx
 
 
-def _step_case(oracle, ctx_factory, shape, nsteps, **kw):
+def _step_case(oracle, ctx_factory, shape, nsteps, pgf=None, **kw):
     dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(*shape, **kw)
+    if pgf:
+        css["pressureforce"].update(pgf)
     rcs, ra = _copy(cs), _copy(a)
     gcs, ga = cs, a
     ctx = _setup(ctx_factory, dom, grid, gv, css)
@@ -81,10 +83,17 @@ def test_step_bitwise_benchmark_size(oracle, ctx_factory):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_step_bitwise_benchmark_size_with_pressure_reconstruction(oracle, ctx_factory, scheme):
+    """The same with RECONSTRUCT_FOR_PRESSURE (PLM, PPM): the reference's default under ALE and what bench.py runs."""
+    _step_case(oracle, ctx_factory, (360, 180, 75), 1, pgf=dict(reconstruct=1, Recon_Scheme=scheme), land_blocks=12, store_CAu=1)
+
+
+@pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("MOM6CU_TEST_FULL_SIZE", "0") != "1", reason="headline-grid oracle run: set MOM6CU_TEST_FULL_SIZE=1")
 def test_step_bitwise_headline_size(oracle, ctx_factory):
     """configs[3]: 1440x1080x75, the grid and land fraction the bench runs, one whole step."""
-    _step_case(oracle, ctx_factory, (1440, 1080, 75), 1, land_blocks=40, store_CAu=1)
+    _step_case(oracle, ctx_factory, (1440, 1080, 75), 1, pgf=dict(reconstruct=1, Recon_Scheme=1), land_blocks=40, store_CAu=1)
 
 
 @pytest.mark.gpu
