@@ -35,6 +35,15 @@ SHIMS = {
     "src/core/MOM_CoriolisAdv.F90": dict(
         hooks=[("CorAdCalc", "u, v, h, uh, vh, CAu, CAv, OBC, AD, G, GV, US, CS, pbv, Waves")],
         public=[], uses=[]),
+    "src/core/MOM_PressureForce_FV.F90": dict(
+        hooks=[("PressureForce_FV_Bouss", "h, tv, PFu, PFv, G, GV, US, CS, ALE_CSp, ADp, p_atm, pbce, eta")],
+        public=[], uses=["use MOM_EOS, only : EOS_query_mom6cu", "use MOM_ALE, only : ALE_answer_date_mom6cu"]),
+    "src/parameterizations/lateral/MOM_hor_visc.F90": dict(
+        hooks=[("horizontal_viscosity", "u, v, h, uh, vh, diffu, diffv, MEKE, VarMix, G, GV, US, CS, tv, dt, OBC, BT, TD, ADp, hu_cont, hv_cont, STOCH")],
+        public=[], uses=[]),
+    # accessors only: these modules keep the members the bindings above need private
+    "src/equation_of_state/MOM_EOS.F90": dict(hooks=[], public=["EOS_query_mom6cu"], uses=[]),
+    "src/ALE/MOM_ALE.F90": dict(hooks=[], public=["ALE_answer_date_mom6cu"], uses=[]),
 }
 
 DECL = re.compile(r"^\s*(type\s*\(|class\s*\(|real\b|integer\b|logical\b|character\b|complex\b|double\s+precision\b|use\b|implicit\b|"

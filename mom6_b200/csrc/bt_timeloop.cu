@@ -27,6 +27,7 @@
 #include "bt_planes.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -237,20 +238,31 @@ __global__ void zero_rect_kernel(const Geom G, double* a, int ilo, int ihi, int 
   if (i <= ihi && j <= jhi) a[G.idx(i, j)] = 0.0;
 }
 
-constexpr int BT_TX = 64, BT_TY = 16, BT_NT = 512;
-constexpr size_t BT_SMEM = (size_t)7 * (BT_TX + 3) * (BT_TY + 3) * sizeof(double);
+// Tile of the substep kernel: 64 x 16 points, 512 threads, 71 KB of shared memory (3 CTAs/SM).  MOM6CU_BT_TILE selects alternatives for A/B
+// measurements: 1 = 32 x 16 / 256 threads (37 KB: 6 CTAs/SM in different phases), 2 = 32 x 32 / 512 threads.
+// Tried and measured slower at 4320x3240 (172 ms per 68 substeps for the plain kernel): fully unrolled phase loops (195 ms), L2 prefetch of
+// the later phases' coefficient planes in phase A (186 ms), both (206 ms).
+template <int TX, int TY, int NT, bool BT_CONT, bool PROJECT>
+int launch_substep_tile(mom6cu_ctx* c, const BtPlanes& P, const BtStep& S) {
+  constexpr size_t SMEM = (size_t)7 * (TX + 3) * (TY + 3) * sizeof(double);
+  auto kern = bt_substep_kernel<TX, TY, NT, BT_CONT, PROJECT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    M6_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_set = true;
+  }
+  dim3 grid((c->g.nx + TX - 1) / TX, (c->g.ny + TY - 1) / TY);
+  M6_LAUNCH(c, kern, grid, NT, SMEM, c->g, P, S);
+  return 0;
+}
 
 template <bool BT_CONT, bool PROJECT>
 int launch_substep(mom6cu_ctx* c, const BtPlanes& P, const BtStep& S) {
-  auto kern = bt_substep_kernel<BT_TX, BT_TY, BT_NT, BT_CONT, PROJECT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    M6_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
-    attr_set = true;
-  }
-  dim3 grid((c->g.nx + BT_TX - 1) / BT_TX, (c->g.ny + BT_TY - 1) / BT_TY);
-  M6_LAUNCH(c, kern, grid, BT_NT, BT_SMEM, c->g, P, S);
-  return 0;
+  static int tile = -1;
+  if (tile < 0) { const char* e = getenv("MOM6CU_BT_TILE"); tile = e ? atoi(e) : 0; }
+  if (tile == 1) return launch_substep_tile<32, 16, 256, BT_CONT, PROJECT>(c, P, S);
+  if (tile == 2) return launch_substep_tile<32, 32, 512, BT_CONT, PROJECT>(c, P, S);
+  return launch_substep_tile<64, 16, 512, BT_CONT, PROJECT>(c, P, S);
 }
 
 }  // namespace

@@ -321,7 +321,10 @@ int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D) {
     R.S_t = c->plane3k("pgf.S_t", G.nk); R.S_b = c->plane3k("pgf.S_b", G.nk);
     if (!R.T_t || !R.T_b || !R.S_t || !R.S_b) return MOM6CU_ERR_CUDA;
     const dim3 ge(grid.x, grid.y, 2);
-    if (G.nk <= 40) M6_LAUNCH(c, pgf_ts_edges_kernel<40>, ge, 128, 0, G, K, R);
+    static int edges_array = -1;   // MOM6CU_PGF_EDGES_ARRAY=1: the array form of the PLM edge values (testing; PPM always uses it)
+    if (edges_array < 0) { const char* e = getenv("MOM6CU_PGF_EDGES_ARRAY"); edges_array = (e && atoi(e)) ? 1 : 0; }
+    if (S.Recon_Scheme == 1 && !edges_array) M6_LAUNCH(c, pgf_ts_edges_plm_kernel, grid, 128, 0, G, K, R);
+    else if (G.nk <= 40) M6_LAUNCH(c, pgf_ts_edges_kernel<40>, ge, 128, 0, G, K, R);
     else if (G.nk <= 80) M6_LAUNCH(c, pgf_ts_edges_kernel<80>, ge, 128, 0, G, K, R);
     else M6_LAUNCH(c, pgf_ts_edges_kernel<128>, ge, 128, 0, G, K, R);
     constexpr int TX = 32, TY = 8;

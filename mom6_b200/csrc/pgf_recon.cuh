@@ -19,7 +19,7 @@
 //  * Everything is evaluated with the reference's own expression order (bitwise parity, -fmad=false); the k-recursions for pa, intx_pa,
 //    inty_pa and pbce stay sequential in registers.
 //  * Roofline: fp64 pipe.  ~35 density evaluations (one IEEE division each with the Wright form) + the interpolation arithmetic per cell,
-//    ~1.9 k fp64 instructions per cell, against 3 + 4 + 3 doubles of compulsory traffic: ~60 flop/byte, far to the right of the B200 ridge
+//    ~2.9 k fp64 instructions per cell (ncu), against 3 + 4 + 3 doubles of compulsory traffic: ~36 instructions per byte, far to the right of the B200 ridge
 //    for fp64 (~5 flop/byte), so the kernel is measured against the fp64 issue rate, not HBM.
 #pragma once
 
@@ -51,6 +51,51 @@ __global__ void __launch_bounds__(128) pgf_ts_edges_kernel(const Geom G, const P
     m6remap::PPM_reconstruction<KCAP>(nk, h, C, R.H_subroundoff, R.boundary_extrap != 0);
   }
   for (int k = 1; k <= nk; ++k) { Qt[g + (long long)(k - 1) * pl] = C.E1[k]; Qb[g + (long long)(k - 1) * pl] = C.E2[k]; }
+}
+
+// TS_PLM_edge_values (ALE_PLM_edge_values, MOM_ALE.F90:1518-1576) as a streaming sweep: one thread per column marches the layers once with the
+// three-layer windows of h, T, S and the slopes slp(k-1), slp(k), slp(k+1) in registers -- no thread-local column arrays (the array form above
+// took 4.6 ms at 1440x1080x75 in local memory; this one reads h, T, S once and writes the four edge fields once: 56 B/cell).  The arithmetic
+// is PLM_slope_wa / PLM_monotonized_slope / PLM_extrapolate_slope of remap_column.cuh, the same functions in the same order.
+__global__ void __launch_bounds__(128) pgf_ts_edges_plm_kernel(const Geom G, const PgfK K, const PgfRecon R) {
+  const int i = G.isc - 1 + blockIdx.x * blockDim.x + threadIdx.x, j = G.jsc - 1 + blockIdx.y;
+  if (i > G.iec + 1 || j > G.jec + 1) return;
+  const long long g = G.idx(i, j), pl = G.plane;
+  const int nk = K.nk;
+  const double hneg = R.H_subroundoff;
+  const bool ext = R.boundary_extrap != 0;
+  auto H = [&](int k) { return __ldg(K.h + g + (long long)(k - 1) * pl); };
+  auto Tq = [&](int k) { return __ldg(K.T + g + (long long)(k - 1) * pl); };
+  auto Sq = [&](int k) { return __ldg(K.S + g + (long long)(k - 1) * pl); };
+  auto put = [&](int k, double Tc, double mT, double Sc, double mS) {
+    const long long o = g + (long long)(k - 1) * pl;
+    R.T_t[o] = Tc - 0.5 * mT; R.T_b[o] = Tc + 0.5 * mT;
+    R.S_t[o] = Sc - 0.5 * mS; R.S_b[o] = Sc + 0.5 * mS;
+  };
+  double hm = H(1), hc = H(2), Tm = Tq(1), Tc = Tq(2), Sm = Sq(1), Sc = Sq(2);
+  if (ext) put(1, Tm, -m6remap::PLM_extrapolate_slope(hc, hm, hneg, Tc, Tm), Sm, -m6remap::PLM_extrapolate_slope(hc, hm, hneg, Sc, Sm));
+  else { const long long o = g; R.T_t[o] = Tm; R.T_b[o] = Tm; R.S_t[o] = Sm; R.S_b[o] = Sm; }
+  double hp = 0., Tp = 0., Sp = 0.;
+  double sT_m = 0., sS_m = 0., sT_c = 0., sS_c = 0.;   // slp(k-1), slp(k)
+  if (nk >= 3) {
+    hp = H(3); Tp = Tq(3); Sp = Sq(3);
+    sT_c = m6remap::PLM_slope_wa(hm, hc, hp, hneg, Tm, Tc, Tp);
+    sS_c = m6remap::PLM_slope_wa(hm, hc, hp, hneg, Sm, Sc, Sp);
+  }
+  for (int k = 2; k <= nk - 1; ++k) {
+    double hpp = 0., Tpp = 0., Spp = 0., sT_p = 0., sS_p = 0.;
+    if (k + 1 <= nk - 1) {
+      hpp = H(k + 2); Tpp = Tq(k + 2); Spp = Sq(k + 2);
+      sT_p = m6remap::PLM_slope_wa(hc, hp, hpp, hneg, Tc, Tp, Tpp);
+      sS_p = m6remap::PLM_slope_wa(hc, hp, hpp, hneg, Sc, Sp, Spp);
+    }
+    put(k, Tc, m6remap::PLM_monotonized_slope(Tm, Tc, Tp, sT_m, sT_c, sT_p), Sc, m6remap::PLM_monotonized_slope(Sm, Sc, Sp, sS_m, sS_c, sS_p));
+    hm = hc; hc = hp; hp = hpp; Tm = Tc; Tc = Tp; Tp = Tpp; Sm = Sc; Sc = Sp; Sp = Spp;
+    sT_m = sT_c; sT_c = sT_p; sS_m = sS_c; sS_c = sS_p;
+  }
+  // layer nk: (hm, hc) = (h(nk-1), h(nk))
+  if (ext) put(nk, Tc, m6remap::PLM_extrapolate_slope(hm, hc, hneg, Tm, Tc), Sc, m6remap::PLM_extrapolate_slope(hm, hc, hneg, Sm, Sc));
+  else { const long long o = g + (long long)(nk - 1) * pl; R.T_t[o] = Tc; R.T_b[o] = Tc; R.S_t[o] = Sc; R.S_b[o] = Sc; }
 }
 
 // calculate_density with / without rho_ref for an unscaled EOS (MOM_EOS.F90:332-334): density_anomaly_elem / density_elem of
