@@ -149,6 +149,9 @@ int oracle_tracer_hordiff(const mom6cu_domain* d, const mom6cu_grid* G, const mo
 int oracle_thickness_diffuse(const mom6cu_domain* d, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
                              const mom6cu_thickness_diffuse_cs* CS, const mom6cu_thickness_diffuse_args* a);
 
+/* ALE_PLM_edge_values / one field of TS_PPM_edge_values (MOM_ALE.F90:1518-1660) for one column: scheme 1 = PLM, 2 = PPM. */
+int oracle_ale_edge_values(int scheme, int nk, const double* h, const double* Q, int bdry_extrap, double h_neglect, double* Q_t, double* Q_b);
+
 /* Equation-of-state elements (oracle/eos.hpp: EOS_WRIGHT, EOS_LINEAR and the unit-rescaling wrapper of MOM_EOS.F90:308-354), PINNED by the
  * reference's check values (EOS_unit_tests, MOM_EOS.F90:2075-2131), and the copies mle.cpp / thickdiff.cpp carry. */
 double oracle_eos_eval(int which, int form, const double* lin4, const double* scales, double T, double S, double p, double rho_ref);

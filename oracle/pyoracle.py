@@ -579,3 +579,16 @@ def eos_eval(which, form, T, S, p, rho_ref=0.0, lin4=None, scales=None, impl="pg
     lib.oracle_eos_eval.restype = C.c_double
     lib.oracle_eos_eval.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     return lib.oracle_eos_eval(dict(rho=0, anom=1, drho_dT=2, drho_dS=3)[which], form, l4, sc, T, S, p, rho_ref)
+
+
+def ale_edge_values(scheme, h, Q, bdry_extrap=False, h_neglect=1.0e-30):
+    """oracle_ale_edge_values: the top / bottom edge values the pressure force reconstructs T and S with (scheme 1 = PLM, 2 = PPM)."""
+    import numpy as np
+    lib = load()
+    h = np.ascontiguousarray(h, dtype=np.float64); Q = np.ascontiguousarray(Q, dtype=np.float64)
+    qt, qb = np.zeros_like(Q), np.zeros_like(Q)
+    lib.oracle_ale_edge_values.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    rc = lib.oracle_ale_edge_values(scheme, len(h), h.ctypes.data, Q.ctypes.data, int(bdry_extrap), h_neglect, qt.ctypes.data, qb.ctypes.data)
+    if rc:
+        raise RuntimeError(f"oracle_ale_edge_values rc={rc}")
+    return qt, qb

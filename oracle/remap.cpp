@@ -679,3 +679,16 @@ int oracle_remap_dyn_split_rk2_aux_vars(const mom6cu_domain* d, const mom6cu_gri
 }
 
 }  // extern "C"
+
+// The column edge-value routines the pressure force uses (ALE_PLM_edge_values / one field of TS_PPM_edge_values), for the known-answer tests
+// (tests/test_oracle_remap_kat.py): scheme 1 = PLM, 2 = PPM (implicit h4 edge values).  0-based arrays of length nk.
+extern "C" int oracle_ale_edge_values(int scheme, int nk, const double* h, const double* Q, int bdry_extrap, double h_neglect, double* Q_t,
+                                      double* Q_b) {
+  if (nk < 2 || (scheme == 2 && nk < 4)) return 2;
+  std::vector<double> hh(nk + 2), qq(nk + 2), qt(nk + 2), qb(nk + 2);
+  for (int k = 1; k <= nk; ++k) { hh[k] = h[k - 1]; qq[k] = Q[k - 1]; }
+  if (scheme == 1) orc::ale_plm_edge_values_column(nk, hh.data(), qq.data(), bdry_extrap != 0, h_neglect, qt.data(), qb.data());
+  else orc::ale_ppm_edge_values_column(nk, hh.data(), qq.data(), bdry_extrap != 0, h_neglect, h_neglect, qt.data(), qb.data());
+  for (int k = 1; k <= nk; ++k) { Q_t[k - 1] = qt[k]; Q_b[k - 1] = qb[k]; }
+  return 0;
+}

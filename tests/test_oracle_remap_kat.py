@@ -100,3 +100,25 @@ def test_conservation_and_bounds_property(oracle):
                     assert abs((u1 * h1).sum() - (u0 * h0).sum()) <= max(4 * err, 1e-13), (scheme, extrap, om4, n0, n1)
                     if not extrap:
                         assert u1.min() >= u0.min() - 1e-12 and u1.max() <= u0.max() + 1e-12
+
+
+def test_recon1d_unit_test_vectors_pin_the_edge_values_of_the_pressure_force(oracle):
+    """The reference's class-based reconstructions hold their own check values: Recon1d_MPLM_WA.unit_tests (src/ALE/Recon1d_MPLM_WA.F90:248-262:
+    the OM4-era monotonized PLM, i.e. PLM_slope_wa + PLM_monotonized_slope) gives, for h = (2,2,2), u = (1,3,5), left edges (1,2,5) and right
+    edges (1,4,5); Recon1d_PPM_H4_2019.unit_tests (:522-530) gives, for five cells of thickness 2 and u = (1,3,5,7,9), left edges (1,2,4,6,9)
+    and right edges (1,4,6,8,9) (to 2 bits of roundoff).  The column routines RECONSTRUCT_FOR_PRESSURE uses (ALE_PLM_edge_values / TS_PPM_edge_values,
+    MOM_ALE.F90:1518-1660 -- the same PLM functions; PPM with the implicit-h4 edge values, exact for a linear profile) must reproduce them, and so
+    must the remapping reconstructions they share code with."""
+    qt, qb = oracle.ale_edge_values(1, [2., 2., 2.], [1., 3., 5.])
+    assert np.array_equal(qt, [1., 2., 5.]) and np.array_equal(qb, [1., 4., 5.])
+    qt, qb = oracle.ale_edge_values(2, [2.] * 5, [1., 3., 5., 7., 9.])
+    assert np.allclose(qt, [1., 2., 4., 6., 9.], rtol=0, atol=4 * np.finfo(float).eps * 9) and np.allclose(qb, [1., 4., 6., 8., 9.], rtol=0, atol=4e-15)
+    # with boundary extrapolation the linear profile is continued into the end cells exactly (PLM_extrapolate_slope :160)
+    qt, qb = oracle.ale_edge_values(1, [2., 2., 2.], [1., 3., 5.], bdry_extrap=True)
+    assert np.array_equal(qt, [0., 2., 4.]) and np.array_equal(qb, [2., 4., 6.])
+    # the remapping reconstructions (PLM = scheme 2, PPM_H4 = scheme 4) on the same vectors
+    E, _ = oracle.remap_reconstruct("PLM", [2., 2., 2.], [1., 3., 5.])
+    assert np.array_equal(E[0], [1., 2., 5.]) and np.array_equal(E[1], [1., 4., 5.])
+    E, _ = oracle.remap_reconstruct("edge_h4", [2.] * 5, [1., 3., 5., 7., 9.])              # explicit h4 edge values, then the PPM limiter
+    E, _ = oracle.remap_reconstruct("PPM", [2.] * 5, [1., 3., 5., 7., 9.], E=E)
+    assert np.allclose(E[0], [1., 2., 4., 6., 9.], rtol=0, atol=4e-15) and np.allclose(E[1], [1., 4., 6., 8., 9.], rtol=0, atol=4e-15)
