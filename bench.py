@@ -186,6 +186,10 @@ def step_resident(ctx, dom, cs, sa):
 
 
 THERMO_EVERY = 8   # DT_THERM / DT of OM4_025 (7200 s / 900 s)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the four kernels of one continuity_PPM call at 1440x1080x75 on one B200, from the
+# committed `ncu --set full` capture profiles/r02_cont_all_ncu.md (the predictor call shape: uhbt, u_cor and BT_cont all present)
+CONT_TRAFFIC = {"cont_flux_tiled<zonal>": 2.968966e9 + 2.912770e9, "cont_convergence_kernel<zonal>": 2.165341e9 + 0.912571e9,
+                "cont_flux_tiled<meridional>": 2.907649e9 + 2.869879e9, "cont_convergence_kernel<meridional>": 2.020983e9 + 0.899442e9}
 
 
 def thermo_pass(Context, synthetic, ni, nj, device):
@@ -719,8 +723,11 @@ def main():
         gbs = tile_cells * bpc * calls / (ms_step * 1e-3) / 1e9 if ms_step > 0 else 0.0
         in_step_tab[name] = {"calls_per_step": calls, "ms_per_step": ms_step, "share_of_step": ms_step / (dev_ms / args.steps),
                              "algorithmic_B_per_cell_per_call": bpc, "achieved_GBps": gbs, "frac_of_peak": gbs / peak}
+    if "pressure_force" in in_step_tab:   # not an HBM-bound stage with RECONSTRUCT_FOR_PRESSURE: say so next to the HBM fraction
+        in_step_tab["pressure_force"]["bound"] = ("fp64 pipe, not HBM: 35 equation-of-state evaluations per cell (~2.9 k fp64 instructions); ncu: fp64 pipe "
+                                                  "65 % active, issue slots 58 % (profiles/r02_pgf_recon_ncu.md)")
     if in_step_tab:
-        covered = sum(v["ms_per_step"] for v in in_step_tab.values())
+        covered = sum(v["ms_per_step"] for v in in_step_tab.values() if "ms_per_step" in v)
         in_step_tab["glue_and_halo_updates"] = {"ms_per_step": dev_ms / args.steps - covered, "share_of_step": 1.0 - covered / (dev_ms / args.steps)}
     if in_step_tab and world == 1:
         dom_stage = max(IN_STEP, key=lambda k: in_step_tab[k]["ms_per_step"])
@@ -750,7 +757,11 @@ def main():
             "e2e": e2e_line(cells, e2e_s, e2e_steps, h2d, d2h, cyc),
             "gpu_launches": launches, "ms_per_step_wall": 1e3 * wall / args.steps,
             "roofline": {"bound": "hbm", "kernel": kernel_of[dom_stage], "stage": dom_stage, "achieved": ds["achieved_GBps"], "peak": peak,
-                         "unit": "GB/s", "frac": ds["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ds["frac_of_peak"],
+                         "traffic": (sum(CONT_TRAFFIC.values()) if (dom_stage == "continuity" and world == 1 and (gni, gnj) == (NI, NJ)) else None),
+                         "traffic_source": "profiles/r02_cont_all_ncu.md: DRAM bytes of the 2 flux + 2 convergence launches of one call (1.58 x the "
+                                           "96 B/cell algorithmic figure, which credits uh and the intermediate h as on-chip; each flux kernel alone "
+                                           "moves 1.05 x its own compulsory 48 B/cell)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": tile_cells * ds["algorithmic_B_per_cell"],
                          "avg_launch_ms": ds.get("launch_ms"), "share_of_step": ds.get("share"),
                          "note": "algorithmic bytes of one stage call / its average CUDA-event time INSIDE the timed steps (in_step); "

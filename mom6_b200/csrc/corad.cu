@@ -15,6 +15,7 @@
 //  * Every expression keeps the reference's parenthesisation (no FMA contraction), so halo q/KE values
 //    recomputed by neighbouring CTAs are bit-identical.
 #include "ctx.h"
+#include <cstdlib>
 #include "stage.h"
 #include <cmath>
 
@@ -58,8 +59,8 @@ __device__ __forceinline__ void en_dis_minmax(const CorAdK& K, const Geom& G, lo
   else { fmax_ = uhm; fmin_ = uhc; }
 }
 
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX* TY, 3) corad_kernel(const Geom G, const CorAdK K) {
+template <int TX, int TY, int MINB = 3>
+__global__ void __launch_bounds__(TX* TY, MINB) corad_kernel(const Geom G, const CorAdK K) {
   constexpr int NT = TX * TY, QW = TX + 2, QH = TY + 2, QN = QW * QH, KW = TX + 1, KH = TY + 1, KN = KW * KH;
   __shared__ double sq[QN];    // q(I,J),   I = ti0-1 .. ti0+TX, J = tj0-1 .. tj0+TY
   __shared__ double saux[QN];  // Ih_q (AL_BLEND) or abs_vort (ROBUST_ENSTRO / bound_Coriolis)
@@ -380,7 +381,10 @@ int m6_coradcalc_run(mom6cu_ctx* c, const CorAdDev& D) {
   K.M = c->grid;
   const int nI = d.iec - (d.isc - 1) + 1, nJ = d.jec - (d.jsc - 1) + 1;
   dim3 grid(c->g.nk, (nI + CA_TX - 1) / CA_TX, (nJ + CA_TY - 1) / CA_TY);
-  M6_LAUNCH(c, (corad_kernel<CA_TX, CA_TY>), grid, CA_TX * CA_TY, 0, c->g, K);
+  static int minb = -1;   // MOM6CU_CORAD_MINB=4: compiled for 4 CTAs/SM (64 registers, spills to L1) for A/B measurements
+  if (minb < 0) { const char* e = getenv("MOM6CU_CORAD_MINB"); minb = e ? atoi(e) : 3; }
+  if (minb == 4) M6_LAUNCH(c, (corad_kernel<CA_TX, CA_TY, 4>), grid, CA_TX * CA_TY, 0, c->g, K);
+  else M6_LAUNCH(c, (corad_kernel<CA_TX, CA_TY>), grid, CA_TX * CA_TY, 0, c->g, K);
   M6_CUDA(c, cudaGetLastError());
   return 0;
 }

@@ -3,8 +3,11 @@
 // :1141-1200, FMS mpp_update_domains / mpp_do_group_update over MPI) re-done as
 //   ONE pack kernel -> ncclSend/ncclRecv to the <=8 neighbours in one NCCL group -> ONE unpack kernel
 // per group pass, all fields and all k levels of the group in the same messages.
-// The 2-D (i,j) tile decomposition, symmetric-memory edge rule, reentrant wrap and closed
-// edges follow the reference exactly (one rectangular tile per rank, all k local).
+// The 2-D (i,j) tile decomposition, reentrant wrap and closed edges follow the reference (one rectangular tile per rank, all k local).
+// One deliberate difference from FMS's symmetric-memory updates: the shared edge point of a staggered field (u at I = isc-1, v at
+// J = jsc-1) is NOT refreshed from the neighbour's iec / jec value.  Both tiles compute that point from the same inputs with the same
+// instruction sequence, so the two copies are bit-identical by construction -- which the layout tests (1 vs 2, 4, 8 tiles, bit for bit)
+// verify on every field of the step; a host that writes the edge on one side only must exchange it itself.
 #include "ctx.h"
 #include <nccl.h>
 #include <vector>

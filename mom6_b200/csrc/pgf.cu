@@ -329,7 +329,12 @@ int m6_pressure_force_run(mom6cu_ctx* c, const PgfDev& D) {
     else M6_LAUNCH(c, pgf_ts_edges_kernel<128>, ge, 128, 0, G, K, R);
     constexpr int TX = 32, TY = 8;
     const dim3 gr((d.iec - d.isc + 2 + TX - 2) / (TX - 1), (d.jec - d.jsc + 2 + TY - 2) / (TY - 1));
+    static int var = -1;
+    if (var < 0) { const char* e = getenv("MOM6CU_PGF_VAR"); var = e ? atoi(e) : 0; }
     if (S.Recon_Scheme == 2) M6_LAUNCH(c, (pgf_recon_kernel<true, TX, TY>), gr, TX * TY, 0, G, K, R);
+    else if (var == 1) M6_LAUNCH(c, (pgf_recon_kernel<false, TX, TY, 1>), gr, TX * TY, 0, G, K, R);
+    else if (var == 2) M6_LAUNCH(c, (pgf_recon_kernel<false, TX, TY, 2>), gr, TX * TY, 0, G, K, R);
+    else if (var == 3) M6_LAUNCH(c, (pgf_recon_kernel<false, TX, TY, 3>), gr, TX * TY, 0, G, K, R);
     else M6_LAUNCH(c, (pgf_recon_kernel<false, TX, TY>), gr, TX * TY, 0, G, K, R);
     M6_CUDA(c, cudaGetLastError());
     return 0;

@@ -128,7 +128,7 @@ enum { Q_ET = 0, Q_EB, Q_TT, Q_TB, Q_ST, Q_SB, Q_TM, Q_SM, Q_DPA, Q_INTZ, Q_PA, 
 // Inlined at both call sites with the sub-column loop unrolled: the out-of-line variant (one copy of the 15 evaluations instead of 30, to
 // relieve the instruction cache) measured 34.5 ms against 30.6 ms at 1440x1080x75 -- the call overhead and the lost overlap between
 // sub-columns cost more than the instruction-cache misses it removed.
-template <bool PPM>
+template <bool PPM, int MUNR>
 __device__ __forceinline__ double recon_face_integral(const PgfK& K, const PgfRecon& R, const RhoFn& rho, double GxRho, const double* L,
                                                       const double* Rt, int sq /* stride between quantities */, double bathyL, double bathyR,
                                                       double e1L, double e1R, double z0L, double z0R) {
@@ -172,7 +172,7 @@ __device__ __forceinline__ double recon_face_integral(const PgfK& K, const PgfRe
   double intz[6];
   intz[1] = L[Q_DPA * sq]; intz[5] = Rt[Q_DPA * sq];
   double i2 = 0., i3 = 0., i4 = 0.;
-#pragma unroll
+#pragma unroll MUNR
   for (int m = 2; m <= 4; ++m) {
     const double w_left = 0.25 * (double)(5 - m), w_right = 1.0 - w_left;
     const double dz_x = (w_left * (eLt - eLb)) + (w_right * (eRt - eRb));
@@ -210,8 +210,10 @@ __device__ __forceinline__ double recon_face_integral(const PgfK& K, const PgfRe
   return C1_90 * (7.0 * (intz[1] + intz[5]) + 32.0 * (i2 + i4) + 12.0 * i3);
 }
 
-template <bool PPM, int TX, int TY>
-__global__ void __launch_bounds__(TX* TY, (TX * TY <= 256) ? 2 : 1) pgf_recon_kernel(const Geom G, const PgfK K, const PgfRecon R) {
+// VAR (A/B measurements, MOM6CU_PGF_VAR): bit 0 = the sub-column loop of the face integrals not unrolled (3 x less code), bit 1 = compiled for
+// 3 CTAs/SM (<= 85 registers).
+template <bool PPM, int TX, int TY, int VAR = 0>
+__global__ void __launch_bounds__(TX* TY, (VAR & 2) ? 3 : ((TX * TY <= 256) ? 2 : 1)) pgf_recon_kernel(const Geom G, const PgfK K, const PgfRecon R) {
   constexpr int NT = TX * TY;
   __shared__ double sm[2][Q_N][NT];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, t = threadIdx.x;
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(TX* TY, (TX * TY <= 256) ? 2 : 1) pgf_recon_ke
     __syncthreads();  // the only barrier of the layer: the next layer writes the other buffer
     if (do_u) {
       const double* Rt = &sm[k & 1][0][tE];
-      const double intx_dpa = recon_face_integral<PPM>(K, R, rho, GxRho, my, Rt, NT, bathy, bathyE, e1, e1E, z0, z0E);
+      const double intx_dpa = recon_face_integral<PPM, (VAR & 1) ? 1 : 3>(K, R, rho, GxRho, my, Rt, NT, bathy, bathyE, e1, e1E, z0, z0E);
       const double hE = Rt[Q_H * NT], paE = Rt[Q_PA * NT], intzE = Rt[Q_INTZ * NT], zbE = Rt[Q_EB * NT];
       double PF = (((pa * hk + intz_dpa) - (paE * hE + intzE)) + ((hE - hk) * intx_pa - (zbE - zb) * intx_dpa * K.Z_to_H)) *
                   ((2.0 * I_Rho0 * IdxCu) / ((hk + hE) + K.h_neglect));
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(TX* TY, (TX * TY <= 256) ? 2 : 1) pgf_recon_ke
     }
     if (do_v) {
       const double* Rt = &sm[k & 1][0][tN];
-      const double inty_dpa = recon_face_integral<PPM>(K, R, rho, GxRho, my, Rt, NT, bathy, bathyN, e1, e1N, z0, z0N);
+      const double inty_dpa = recon_face_integral<PPM, (VAR & 1) ? 1 : 3>(K, R, rho, GxRho, my, Rt, NT, bathy, bathyN, e1, e1N, z0, z0N);
       const double hN = Rt[Q_H * NT], paN = Rt[Q_PA * NT], intzN = Rt[Q_INTZ * NT], zbN = Rt[Q_EB * NT];
       double PF = (((pa * hk + intz_dpa) - (paN * hN + intzN)) + ((hN - hk) * inty_pa - (zbN - zb) * inty_dpa * K.Z_to_H)) *
                   ((2.0 * I_Rho0 * IdyCv) / ((hk + hN) + K.h_neglect));
