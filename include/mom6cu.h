@@ -499,7 +499,8 @@ int mom6cu_btstep_timeloop(mom6cu_ctx* ctx, const mom6cu_bt_timeloop_args* a);
  * (USE_BT_CONT_TYPE=False), NONLIN_BT_STRESS, gradual_BT_ICs, eta_PF_start interpolation, answer_date < 20190101. */
 typedef struct mom6cu_barotropic_cs {
   int Sadourny, BT_project_velocity, strong_drag, bound_BT_corr, BT_cont_bounds, wt_uv_bug, visc_rem_u_uh0,
-      adjust_BT_cont, use_wide_halos, min_stencil, use_old_coriolis_bracket_bug, unsupported;
+      adjust_BT_cont /* refused when set: ADJUST_BT_CONT is outside the frozen option set */, use_wide_halos, min_stencil,
+      use_old_coriolis_bracket_bug, unsupported;
   double dtbt, bebt, vel_underflow, maxCFL_BT_cont, G_extra, dt_bt_filter;
   /* wide */
   const double *IareaT, *IareaT_OBCmask, *bathyT, *IdxCu, *IdyCv; /* h, h, h, u, v */

@@ -378,6 +378,8 @@ inline dim3 grid2(int ni, int nj, int bx) { return dim3((ni + bx - 1) / bx, nj);
 int m6_btstep_run(mom6cu_ctx* c, const mom6cu_barotropic_cs& CS, const BtstepDev& D) {
   if (!c->have_grid || !c->have_vgrid) return c->fail(MOM6CU_ERR_BAD_ARG, "btstep: grid / vertical grid not set");
   if (CS.unsupported) return c->fail(MOM6CU_ERR_UNSUPPORTED, "btstep: an option outside the frozen option set is enabled");
+  if (CS.adjust_BT_cont)  // adjust_local_BT_cont_types, MOM_barotropic.F90:1180-1198, 5010-5103
+    return c->fail(MOM6CU_ERR_UNSUPPORTED, "btstep: ADJUST_BT_CONT=True is outside the frozen option set");
   if (!D.have_BT_cont) return c->fail(MOM6CU_ERR_UNSUPPORTED, "btstep: USE_BT_CONT_TYPE=False is outside the frozen option set");
   const bool add_uh0 = D.uh0 != nullptr;
   if (add_uh0 && !(D.vh0 && D.u_uh0 && D.v_vh0))

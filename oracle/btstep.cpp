@@ -30,7 +30,7 @@ inline double find_uhbt(double u, const double* BTC) {  // :4610-4631
 extern "C" int oracle_btstep(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vgrid* GV,
                              const mom6cu_barotropic_cs* CS, const mom6cu_btstep_args* A, int nthreads) {
   if (nthreads > 0) omp_set_num_threads(nthreads);
-  if (CS->unsupported || !A->BT_cont) return 3;
+  if (CS->unsupported || CS->adjust_BT_cont || !A->BT_cont) return 3;  // ADJUST_BT_CONT (:1180-1198) is not restated
   const OGrid G(d, Gp);
   const int is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, Isq = G.IscB, Ieq = G.IecB, Jsq = G.JscB, Jeq = G.JecB;
   const int nz = G.ke;

@@ -1,0 +1,679 @@
+"""Python code generation for oracle/f90run/translate.py's parse trees.  TEST INFRASTRUCTURE ONLY.
+
+Every arithmetic node is emitted fully parenthesised, so Python evaluates it in the order of the Fortran parse tree: explicit
+parentheses are kept, equal-precedence operators associate left to right, '**' right to left.  '/' goes through rt.div
+(integer truncation, IEEE real division), '**' through rt.powi / rt.power (libgfortran's integer powering; libm pow)."""
+import re
+
+from .rt import INTRINSICS, mangle
+from .translate import Parser, parse_expr, tokenize, _split_top
+
+_ARITH = {"+", "-", "*", "/", "**"}
+_REAL_FN = {"sqrt", "exp", "log", "sin", "cos", "tan", "atan", "atan2", "tanh", "real", "dble", "float", "epsilon", "tiny",
+            "asin", "acos", "sinh", "cosh", "log10", "aint"}
+_INT_FN = {"int", "nint", "floor", "ceiling", "size", "lbound", "ubound", "len", "len_trim", "count"}
+_SAME_FN = {"abs", "max", "min", "sign", "mod", "modulo", "merge", "sum", "maxval", "minval"}
+
+
+def _num(text):
+    t = text
+    if "_" in t:
+        t = t[:t.index("_")]
+    t = t.replace("d", "e")
+    if "." in t or "e" in t:
+        return repr(float(t)), "r"
+    return str(int(t)), "i"
+
+
+def find_assign(st):
+    """index of the top-level assignment '=' (or '=>') in a statement, or -1"""
+    depth, q, i, n = 0, None, 0, len(st)
+    while i < n:
+        c = st[i]
+        if q:
+            if c == q:
+                q = None
+        elif c in "'\"":
+            q = c
+        elif c in "([":
+            depth += 1
+        elif c in ")]":
+            depth -= 1
+        elif c == "=" and depth == 0:
+            prev = st[i - 1] if i else ""
+            nxt = st[i + 1] if i + 1 < n else ""
+            if nxt == "=" or prev in "=/<>":
+                i += 2 if nxt == "=" else 1
+                continue
+            return i
+        i += 1
+    return -1
+
+
+class ProcGen:
+    def __init__(self, prog, mod, proc):
+        self.prog, self.mod, self.P = prog, mod, proc
+        self.lines = []
+        self.globals_assigned = set()
+        self.tmp = 0
+        self.ret = None
+
+    # ---- symbols
+    def var(self, name):
+        v = self.P.vars.get(name)
+        if v is not None:
+            return v
+        return self.mod.vars.get(name)
+
+    def is_local(self, name):
+        return name in self.P.vars
+
+    def newtmp(self, stem="t"):
+        self.tmp += 1
+        return f"_{stem}{self.tmp}"
+
+    # ---- expression types
+    def etype(self, e):
+        k = e[0]
+        if k == "num":
+            return _num(e[1])[1]
+        if k == "log":
+            return "l"
+        if k == "str":
+            return "s"
+        if k == "paren":
+            return self.etype(e[1])
+        if k == "un":
+            return "l" if e[1] == ".not." else self.etype(e[2])
+        if k == "bin":
+            op = e[1]
+            if op in _ARITH:
+                a, b = self.etype(e[2]), self.etype(e[3])
+                if op == "**":
+                    return a
+                if a == "r" or b == "r":
+                    return "r"
+                if a == "i" and b == "i":
+                    return "i"
+                return None
+            if op == "//":
+                return "s"
+            return "l"
+        if k == "ref":
+            parts = e[1]
+            name, args = parts[0]
+            if len(parts) == 1:
+                v = self.var(name)
+                if v is not None:
+                    if v.base in ("type", "class"):
+                        return "o"
+                    if v.dims is not None and (args is None or any(a[0] == "slice" for a in args)):
+                        return None  # an array value
+                    return v.kind
+                if args is not None:
+                    if name in _REAL_FN:
+                        return "r"
+                    if name in _INT_FN:
+                        return "i"
+                    if name in ("present", "associated", "allocated", "any", "all", "is_root_pe"):
+                        return "l"
+                    if name in _SAME_FN and args:
+                        ts = [self.etype(a) for a in args if a[0] != "kw"]
+                        if all(t == "r" for t in ts):
+                            return "r"
+                        if all(t == "i" for t in ts):
+                            return "i"
+                        return None
+                    f = self.prog.find_proc(self.mod, name)
+                    if f is not None and f.kind == "function":
+                        rv = f.vars.get(f.result)
+                        if rv is not None and rv.dims is None:
+                            return rv.kind
+            return None
+        return None
+
+    # ---- expressions
+    def ex(self, e):
+        k = e[0]
+        if k == "num":
+            return _num(e[1])[0]
+        if k == "log":
+            return "True" if e[1] else "False"
+        if k == "str":
+            s = e[1]
+            q = s[0]
+            return repr(s[1:-1].replace(q + q, q))
+        if k == "paren":
+            return "(" + self.ex(e[1]) + ")"
+        if k == "un":
+            if e[1] == ".not.":
+                return "(not " + self.ex(e[2]) + ")"
+            return "(-" + self.ex(e[2]) + ")"
+        if k == "bin":
+            op, a, b = e[1], e[2], e[3]
+            A, B = self.ex(a), self.ex(b)
+            if op == "/":
+                if b[0] == "num" and _num(b[1])[1] == "r" and float(_num(b[1])[0]) != 0.0:
+                    return f"({A} / {B})"
+                return f"_rt.div({A}, {B})"
+            if op == "**":
+                tb = self.etype(b)
+                if tb == "i":
+                    return f"_rt.powi({A}, {B})"
+                return f"_rt.power({A}, {B})"
+            if op in ("+", "-", "*"):
+                return f"({A} {op} {B})"
+            if op == "//":
+                return f"(str({A}) + str({B}))"
+            if op == ".and.":
+                return f"({A} and {B})"
+            if op == ".or.":
+                return f"({A} or {B})"
+            if op in (".eqv.",):
+                return f"(bool({A}) == bool({B}))"
+            if op in (".neqv.",):
+                return f"(bool({A}) != bool({B}))"
+            if op == "/=":
+                return f"({A} != {B})"
+            return f"({A} {op} {B})"
+        if k == "arr":
+            return "[" + ", ".join(self.ex(x) for x in e[1]) + "]"
+        if k == "slice":
+            return self.slice_(e)
+        if k == "kw":
+            return f"{mangle(e[1])}={self.ex(e[2])}"
+        if k == "ref":
+            return self.ref(e[1])
+        raise NotImplementedError(k)
+
+    def slice_(self, e):
+        f = lambda x: "None" if x is None else self.ex(x)
+        return f"({f(e[1])}, {f(e[2])}, {f(e[3])})"
+
+    def index(self, base, args):
+        """element or section of the array expression base"""
+        if any(a[0] == "slice" for a in args):
+            return base + ".sec(" + ", ".join(self.ex(a) for a in args) + ")"
+        n = len(args)
+        m = f"g{n}" if n <= 3 else "g"
+        return f"{base}.{m}(" + ", ".join(self.ex(a) for a in args) + ")"
+
+    def ref(self, parts):
+        name, args = parts[0]
+        v = self.var(name)
+        if v is not None or len(parts) > 1:
+            s = mangle(name)
+            if args is not None:
+                if v is not None and v.dims is None and v.base == "character":
+                    pass  # substring: the reference only does this in messages
+                else:
+                    s = self.index(s, args)
+        elif args is not None:
+            s = self.call_expr(name, args)
+        else:
+            s = mangle(name)
+        for cname, cargs in parts[1:]:
+            s = s + "." + mangle(cname)
+            if cargs is not None:
+                s = self.index(s, cargs)
+        return s
+
+    def call_expr(self, name, args):
+        if name == "present" or name == "allocated":
+            return "(" + self.ex(args[0]) + " is not None)"
+        if name == "associated":
+            if len(args) == 2:
+                return "(" + self.ex(args[0]) + " is " + self.ex(args[1]) + ")"
+            return "(" + self.ex(args[0]) + " is not None)"
+        f = self.prog.find_proc(self.mod, name)
+        if f is None and name in INTRINSICS:
+            return f"_i_{name}(" + ", ".join(self.ex(a) for a in args) + ")"
+        return mangle(name) + "(" + ", ".join(self.ex(a) for a in args) + ")"
+
+    # ---- statements
+    def emit(self, ind, text, ln=None):
+        self.lines.append("    " * ind + text + (f"  # L{ln}" if ln is not None else ""))
+
+    def coerce(self, v, e):
+        s = self.ex(e)
+        if v is None or v.dims is not None:
+            return s
+        t = self.etype(e)
+        if v.base == "real" and t != "r":
+            return f"_rt.tofloat({s})"
+        if v.base == "integer" and t != "i":
+            return f"_rt.toint({s})"
+        return s
+
+    def assign(self, ind, lhs, rhs, ln, pointer=False):
+        L = parse_expr(lhs)
+        if L[0] != "ref":
+            raise SyntaxError("bad assignment target " + lhs)
+        R = parse_expr(rhs)
+        parts = L[1]
+        name, args = parts[0]
+        if len(parts) == 1:
+            v = self.var(name)
+            if v is not None and not self.is_local(name):
+                self.globals_assigned.add(mangle(name))
+            if pointer:
+                self.emit(ind, f"{mangle(name)} = {self.ex(R)}", ln)
+                return
+            if args is None:
+                if v is not None and v.dims is not None:
+                    self.emit(ind, f"{mangle(name)} = _rt.assign_whole({mangle(name)}, {self.ex(R)})", ln)
+                else:
+                    self.emit(ind, f"{mangle(name)} = {self.coerce(v, R)}", ln)
+                return
+            self.store(ind, mangle(name), args, R, ln)
+            return
+        obj = self.ref(parts[:-1])
+        cname, cargs = parts[-1]
+        if pointer:
+            self.emit(ind, f"{obj}.{mangle(cname)} = {self.ex(R)}", ln)
+        elif cargs is None:
+            self.emit(ind, f"_rt.assign_attr({obj}, {mangle(cname)!r}, {self.ex(R)})", ln)
+        else:
+            self.store(ind, f"{obj}.{mangle(cname)}", cargs, R, ln)
+
+    def store(self, ind, base, args, R, ln):
+        if any(a[0] == "slice" for a in args):
+            self.emit(ind, f"{base}.sec(" + ", ".join(self.ex(a) for a in args) + f").assign({self.ex(R)})", ln)
+        else:
+            n = len(args)
+            m = f"s{n}" if n <= 3 else "s_"
+            self.emit(ind, f"{base}.{m}(" + ", ".join(self.ex(a) for a in args) + f", {self.ex(R)})", ln)
+
+    def designator_store(self, ind, actual, value, ln):
+        """store value into the designator expression 'actual' (copy-out of a scalar dummy argument)"""
+        if actual[0] == "kw":
+            actual = actual[2]
+        if actual[0] != "ref":
+            return
+        parts = actual[1]
+        name, args = parts[0]
+        if len(parts) == 1:
+            v = self.var(name)
+            if v is None:
+                return
+            if not self.is_local(name):
+                self.globals_assigned.add(mangle(name))
+            if args is None:
+                if v.dims is None:
+                    self.emit(ind, f"{mangle(name)} = {value}", ln)
+                return
+            if any(a[0] == "slice" for a in args):
+                return
+            n = len(args)
+            m = f"s{n}" if n <= 3 else "s_"
+            self.emit(ind, f"{mangle(name)}.{m}(" + ", ".join(self.ex(a) for a in args) + f", {value})", ln)
+            return
+        obj = self.ref(parts[:-1])
+        cname, cargs = parts[-1]
+        if cargs is None:
+            self.emit(ind, f"{obj}.{mangle(cname)} = {value}", ln)
+        elif not any(a[0] == "slice" for a in cargs):
+            n = len(cargs)
+            m = f"s{n}" if n <= 3 else "s_"
+            self.emit(ind, f"{obj}.{mangle(cname)}.{m}(" + ", ".join(self.ex(a) for a in cargs) + f", {value})", ln)
+
+    def call(self, ind, text, ln):
+        m = re.match(r"call\s+([a-z_][\w%]*)\s*(\(.*\))?\s*$", text, re.S)
+        if not m:
+            raise SyntaxError("bad call: " + text)
+        name = m.group(1)
+        args = []
+        if m.group(2):
+            p = Parser(tokenize(m.group(2)))
+            p.expect("op", "(")
+            args = p.p_args()
+        if "%" in name:
+            tgt = ".".join(mangle(x) for x in name.split("%"))
+            self.emit(ind, f"{tgt}(" + ", ".join(self.ex(a) for a in args) + ")", ln)
+            return
+        f = self.prog.find_proc(self.mod, name)
+        argtxt = ", ".join(self.ex(a) for a in args)
+        if f is None or isinstance(f, list):
+            self.emit(ind, f"{mangle(name)}({argtxt})", ln)
+            return
+        outs = f.out_scalars()
+        if not outs:
+            self.emit(ind, f"{mangle(name)}({argtxt})", ln)
+            return
+        r = self.newtmp("r")
+        self.emit(ind, f"{r} = {mangle(name)}({argtxt})", ln)
+        pos = [a for a in args if a[0] != "kw"]
+        kws = {a[1]: a for a in args if a[0] == "kw"}
+        for n, d in enumerate(outs):
+            k = f.args.index(d)
+            actual = pos[k] if k < len(pos) else kws.get(d)
+            if actual is not None:
+                self.designator_store(ind, actual, f"{r}[{n}]", ln)
+
+    def block(self, ind, nodes):
+        if not nodes:
+            self.emit(ind, "pass")
+            return
+        for nd in nodes:
+            self.node(ind, nd)
+
+    def node(self, ind, nd):
+        k = nd[0]
+        try:
+            if k == "stmt":
+                self.stmt(ind, nd[2], nd[1])
+            elif k == "if":
+                for n, (cond, blk) in enumerate(nd[2]):
+                    self.emit(ind, ("if " if n == 0 else "elif ") + self.ex(parse_expr(cond)) + ":", nd[1])
+                    self.block(ind + 1, blk)
+                if nd[3] is not None:
+                    self.emit(ind, "else:")
+                    self.block(ind + 1, nd[3])
+            elif k == "do":
+                _, ln, var, lo, hi, step, blk = nd
+                v = mangle(var)
+                a, b = self.newtmp("a"), self.newtmp("b")
+                self.emit(ind, f"{a} = {self.ex(parse_expr(lo))}; {b} = {self.ex(parse_expr(hi))}", ln)
+                if step is None:
+                    self.emit(ind, f"{v} = {a}")
+                    self.emit(ind, f"for {v} in range({a}, {b} + 1):")
+                    self.block(ind + 1, blk)
+                    self.emit(ind, "else:")
+                    self.emit(ind + 1, f"{v} = {a} if {b} < {a} else {b} + 1")
+                else:
+                    c = self.newtmp("c")
+                    self.emit(ind, f"{c} = {self.ex(parse_expr(step))}")
+                    self.emit(ind, f"{v} = {a}")
+                    self.emit(ind, f"for {v} in range({a}, ({b} + 1) if {c} > 0 else ({b} - 1), {c}):")
+                    self.block(ind + 1, blk)
+                    self.emit(ind, "else:")
+                    self.emit(ind + 1, f"{v} = {a} + max(0, ({b} - {a} + {c}) // {c}) * {c}")
+            elif k == "dowhile":
+                self.emit(ind, "while " + self.ex(parse_expr(nd[2])) + ":", nd[1])
+                self.block(ind + 1, nd[3])
+            elif k == "doforever":
+                self.emit(ind, "while True:", nd[1])
+                self.block(ind + 1, nd[2])
+            elif k == "select":
+                s = self.newtmp("sel")
+                self.emit(ind, f"{s} = {self.ex(parse_expr(nd[2]))}", nd[1])
+                first = True
+                default = None
+                for lab, blk in nd[3]:
+                    if lab is None:
+                        default = blk
+                        continue
+                    conds = []
+                    for it in _split_top(lab):
+                        if ":" in it and not it.strip().startswith(("'", '"')):
+                            lo, hi = it.split(":")
+                            c = []
+                            if lo.strip():
+                                c.append(f"{s} >= {self.ex(parse_expr(lo))}")
+                            if hi.strip():
+                                c.append(f"{s} <= {self.ex(parse_expr(hi))}")
+                            conds.append("(" + " and ".join(c) + ")")
+                        else:
+                            conds.append(f"{s} == {self.ex(parse_expr(it))}")
+                    self.emit(ind, ("if " if first else "elif ") + " or ".join(conds) + ":")
+                    self.block(ind + 1, blk)
+                    first = False
+                if default is not None:
+                    if first:
+                        self.emit(ind, "if True:")
+                    else:
+                        self.emit(ind, "else:")
+                    self.block(ind + 1, default)
+            else:
+                raise NotImplementedError(k)
+        except (SyntaxError, NotImplementedError, ValueError, IndexError, AttributeError) as err:
+            msg = f"{self.mod.name}:{nd[1]}: untranslatable ({type(err).__name__}: {err})"
+            self.emit(ind, f"raise NotImplementedError({msg!r})", nd[1])
+
+    def stmt(self, ind, st, ln):
+        if st.startswith("call ") or st.startswith("call\t"):
+            self.call(ind, st, ln)
+            return
+        if st == "return":
+            self.emit(ind, "return " + self.ret, ln)
+            return
+        if st == "exit":
+            self.emit(ind, "break", ln)
+            return
+        if st == "cycle":
+            self.emit(ind, "continue", ln)
+            return
+        if st == "continue" or st == "__internal_procedures_skipped__":
+            self.emit(ind, "pass", ln)
+            return
+        if re.match(r"(write|print|read|open|close|format|flush|rewind)\b\s*[(*]", st):
+            m = re.match(r"write\s*\(\s*([a-z_]\w*)\s*,", st)
+            v = self.var(m.group(1)) if m else None
+            if v is not None and v.base == "character":  # internal write into a message string: its text is not reproduced
+                self.emit(ind, f"{mangle(m.group(1))} = ''", ln)
+            else:
+                self.emit(ind, "pass", ln)
+            return
+        if re.match(r"(error\s+)?stop\b", st):
+            self.emit(ind, f"raise _rt.FortranStop({st!r})", ln)
+            return
+        m = re.match(r"allocate\s*\((.*)\)$", st, re.S)
+        if m:
+            for it in _split_top(m.group(1)):
+                if re.match(r"(stat|source|mold|errmsg)\s*=", it):
+                    mm = re.match(r"source\s*=\s*(.*)$", it)
+                    if mm:
+                        self.emit(ind, f"_alloc_last.assign({self.ex(parse_expr(mm.group(1)))})", ln)
+                    continue
+                e = parse_expr(it)
+                parts = e[1]
+                cname, cargs = parts[-1]
+                bounds = []
+                for a in cargs or []:
+                    if a[0] == "slice":
+                        bounds.append(f"({self.ex(a[1])}, {self.ex(a[2])})")
+                    else:
+                        bounds.append(f"(1, {self.ex(a)})")
+                tgt = self.ref(parts[:-1] + [(cname, None)]) if len(parts) > 1 else mangle(cname)
+                v = self.var(parts[0][0]) if len(parts) == 1 else None
+                kind = v.kind if v is not None else "r"
+                if len(parts) == 1 and v is not None and not self.is_local(cname):
+                    self.globals_assigned.add(mangle(cname))
+                if cargs is None:
+                    self.emit(ind, f"{tgt} = _rt.NS()", ln)
+                else:
+                    self.emit(ind, f"_alloc_last = {tgt} = _rt.alloc({kind!r}, ({', '.join(bounds)},))", ln)
+            return
+        m = re.match(r"(deallocate|nullify)\s*\((.*)\)$", st, re.S)
+        if m:
+            for it in _split_top(m.group(2)):
+                if re.match(r"stat\s*=", it):
+                    continue
+                e = parse_expr(it)
+                parts = e[1]
+                if len(parts) == 1:
+                    self.emit(ind, f"{mangle(parts[0][0])} = None", ln)
+                else:
+                    self.emit(ind, f"{self.ref(parts[:-1])}.{mangle(parts[-1][0])} = None", ln)
+            return
+        k = find_assign(st)
+        if k > 0:
+            if st[k:k + 2] == "=>":
+                self.assign(ind, st[:k].strip(), st[k + 2:].strip(), ln, pointer=True)
+            else:
+                self.assign(ind, st[:k].strip(), st[k + 1:].strip(), ln)
+            return
+        raise NotImplementedError("statement: " + st)
+
+    # ---- declarations
+    def bounds(self, dims):
+        """-> (list of lower-bound code, list of extent code or None, list of (lo,hi) code or None when deferred)"""
+        lbs, exts, full = [], [], []
+        for d in dims:
+            d = d.strip()
+            parts = _split_top(d, ":")
+            if d == "*" or d == "..":
+                lbs.append("1"); exts.append("None"); full.append(None)
+            elif len(parts) == 1:
+                hi = self.ex(parse_expr(parts[0]))
+                lbs.append("1"); exts.append(hi); full.append(("1", hi))
+            else:
+                lo = parts[0].strip()
+                hi = parts[1].strip()
+                lo_c = self.ex(parse_expr(lo)) if lo else "1"
+                if hi and hi != "*":
+                    hi_c = self.ex(parse_expr(hi))
+                    lbs.append(lo_c); exts.append(f"({hi_c}) - ({lo_c}) + 1"); full.append((lo_c, hi_c))
+                else:
+                    lbs.append(lo_c); exts.append("None"); full.append(None)
+        return lbs, exts, full
+
+    def generate(self):
+        P = self.P
+        outs = P.out_scalars()
+        if P.kind == "function":
+            self.ret = mangle(P.result)
+        else:
+            self.ret = "(" + "".join(mangle(a) + ", " for a in outs) + ")" if outs else "None"
+        body_gen = ProcGen(self.prog, self.mod, P)
+        # prologue
+        pro = []
+        for name, v in P.vars.items():
+            n = mangle(name)
+            try:
+                if v.dummy:
+                    if v.dims is not None and (v.pointer or v.allocatable):
+                        pass  # a pointer / allocatable dummy keeps the bounds of its actual argument
+                    elif v.dims is not None and v.base != "character":
+                        lbs, exts, _ = self.bounds(v.dims)
+                        pro.append(f"{n} = _rt.rebase({n}, ({', '.join(lbs)},), ({', '.join(exts)},), {P.name + ':' + name!r})")
+                    elif v.dims is None and v.base == "real":
+                        pro.append(f"if {n} is not None: {n} = float({n})")
+                    continue
+                if v.parameter:
+                    if v.dims is not None:
+                        _, _, full = self.bounds(v.dims)
+                        pro.append(f"{n} = _rt.alloc({v.kind!r}, ({', '.join('(%s, %s)' % b for b in full)},))")
+                        pro.append(f"{n}.assign({self.ex(parse_expr(v.init[1]))})")
+                    else:
+                        pro.append(f"{n} = {self.coerce(v, parse_expr(v.init[1]))}")
+                    continue
+                if name == P.result and P.kind == "function" and v.dims is None and v.base not in ("type", "class"):
+                    continue
+                if v.dims is not None and v.base not in ("character", "type", "class"):
+                    _, _, full = self.bounds(v.dims)
+                    if any(b is None for b in full) or v.pointer or v.allocatable:
+                        pro.append(f"{n} = None")
+                    else:
+                        pro.append(f"{n} = _rt.alloc({v.kind!r}, ({', '.join('(%s, %s)' % b for b in full)},))")
+                        if v.init is not None and v.init[0] == "val":
+                            pro.append(f"{n}.assign({self.ex(parse_expr(v.init[1]))})")
+                elif v.base in ("type", "class"):
+                    if v.dims is not None:
+                        _, _, full = self.bounds(v.dims)
+                        if any(b is None for b in full) or v.pointer or v.allocatable:
+                            pro.append(f"{n} = None")
+                        else:
+                            pro.append(f"{n} = _rt.alloc_types(globals(), {v.tname!r}, ({', '.join('(%s, %s)' % b for b in full)},))")
+                    else:
+                        pro.append(f"{n} = None" if v.pointer else f"{n} = _rt.new_type(globals(), {v.tname!r})")
+                elif v.init is not None and v.init[0] == "val":
+                    pro.append(f"{n} = {self.coerce(v, parse_expr(v.init[1]))}")
+                elif v.pointer:
+                    pro.append(f"{n} = None")
+            except (SyntaxError, NotImplementedError, ValueError, IndexError) as err:
+                pro.append(f"{n} = None  # declaration not translated: {err}")
+        self.lines = []
+        self.block(1, P.body)
+        body = self.lines
+        head = [f"def {mangle(P.name)}(" + ", ".join(mangle(a) + "=None" for a in P.args) + f"):  # {self.mod.name}:{P.line}"]
+        if self.globals_assigned:
+            head.append("    global " + ", ".join(sorted(self.globals_assigned)))
+        out = head + ["    " + p for p in pro] + body + ["    return " + self.ret, ""]
+        return "\n".join(out)
+
+
+class Program:
+    def __init__(self):
+        self.modules = {}
+
+    def add(self, mods):
+        for m in mods:
+            self.modules[m.name] = m
+
+    def find_proc(self, mod, name):
+        """the Proc a call to name from mod resolves to; a list of Procs for a generic; None if it is not a translated procedure"""
+        if name in mod.procs:
+            return mod.procs[name]
+        if name in mod.generics:
+            return [mod.procs[s] for s in mod.generics[name] if s in mod.procs]
+        for uname, only in mod.uses:
+            um = self.modules.get(uname)
+            if um is None:
+                continue
+            remote = name
+            if only is not None:
+                hit = [r for l, r in only if l == name]
+                if not hit:
+                    continue
+                remote = hit[0]
+            if remote in um.procs:
+                return um.procs[remote]
+            if remote in um.generics:
+                return [um.procs[s] for s in um.generics[remote] if s in um.procs]
+        return None
+
+    def gen_module(self, mod):
+        out = [f"# generated from {mod.path} by oracle/f90run -- do not commit", "import oracle.f90run.rt as _rt"]
+        for k in INTRINSICS:
+            out.append(f"_i_{k} = _rt.INTRINSICS[{k!r}]")
+        out.append("")
+        # module variables
+        for name, v in mod.vars.items():
+            n = mangle(name)
+            if v.init is not None and v.init[0] == "val" and v.dims is None:
+                pg = ProcGen(self, mod, _EmptyProc(mod))
+                try:
+                    code = pg.coerce(v, parse_expr(v.init[1]))
+                    out.append(f"try:\n    {n} = {code}\nexcept NameError:\n    {n} = None")
+                except (SyntaxError, NotImplementedError):
+                    out.append(f"{n} = None")
+            else:
+                out.append(f"{n} = None")
+        out.append("")
+        for P in mod.procs.values():
+            out.append(ProcGen(self, mod, P).generate())
+        for tname, comps in mod.types.items():
+            out.append(f"def _new_{mangle(tname)}():")
+            out.append("    o = _rt.NS()")
+            pg = ProcGen(self, mod, _EmptyProc(mod))
+            for cname, v in comps.items():
+                if v.init is not None and v.init[0] == "val" and v.dims is None:
+                    try:
+                        out.append(f"    o.{mangle(cname)} = {pg.coerce(v, parse_expr(v.init[1]))}")
+                    except (SyntaxError, NotImplementedError):
+                        pass
+                elif v.base in ("type", "class") and v.dims is None and not v.pointer and not v.allocatable:
+                    out.append(f"    o.{mangle(cname)} = _rt.new_type(globals(), {v.tname!r})")
+            out.append("    return o")
+            out.append("")
+        for g, specs in mod.generics.items():
+            specs = [s for s in specs if s in mod.procs]
+            if not specs:
+                continue
+            sig = []
+            for s in specs:
+                P = mod.procs[s]
+                sig.append("(" + mangle(s) + ", [" + ", ".join(
+                    "(%r, %r, %r)" % (mangle(a), (len(P.vars[a].dims) if (a in P.vars and P.vars[a].dims is not None) else 0),
+                                      bool(a in P.vars and P.vars[a].optional)) for a in P.args) + "])")
+            out.append(f"{mangle(g)} = _rt.generic({g!r}, [" + ", ".join(sig) + "])")
+        return "\n".join(out) + "\n"
+
+
+class _EmptyProc:
+    def __init__(self, mod):
+        self.vars, self.args, self.kind, self.result, self.name, self.line, self.body = {}, [], "subroutine", None, "<module>", 0, []
+
+    def out_scalars(self):
+        return []

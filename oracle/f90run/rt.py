@@ -1,0 +1,593 @@
+"""Run-time support for the Fortran-subset translator (oracle/f90run/translate.py).  TEST INFRASTRUCTURE ONLY.
+
+The translator turns the reference's own .F90 sources -- read where they lie under /root/reference, never copied into this repo --
+into Python that evaluates every expression in IEEE binary64 in exactly the order the Fortran text prescribes (parentheses kept,
+equal-precedence operators left to right, no FMA contraction: what gfortran -O0 -ffp-contract=off would do).  This module holds
+what the generated code calls: Fortran arrays with arbitrary lower bounds and section views, derived-type instances, the
+intrinsics and the integer/real division and power rules."""
+import math
+
+NAN = float("nan")
+INF = float("inf")
+
+
+class FortranStop(Exception):
+    pass
+
+
+class NS:
+    """A derived-type instance: components are attributes (lower case); an unset pointer / absent component reads as None."""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, mangle(k), v)
+
+    def __getattr__(self, name):  # only called when the attribute is missing
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return None
+
+    def __repr__(self):
+        return "NS(" + ", ".join(sorted(self.__dict__)) + ")"
+
+
+_PYKW = {"is", "in", "as", "or", "and", "not", "if", "else", "for", "while", "def", "del", "from", "global", "lambda", "pass",
+         "class", "return", "yield", "import", "with", "try", "raise", "none", "true", "false", "assert", "break", "continue",
+         "elif", "except", "finally", "nonlocal", "async", "await", "print", "exec", "type", "len", "range", "float", "int",
+         "tuple", "list", "math", "isinstance", "bool", "str", "abs", "min", "max", "sum"}
+
+
+def mangle(name):
+    n = name.lower()
+    return n + "_" if n in _PYKW else n
+
+
+def _prod(xs):
+    p = 1
+    for x in xs:
+        p *= x
+    return p
+
+
+class FArray:
+    """A Fortran array (or a section of one): shared flat storage, strides, lower bounds.  Element (i,j,k) lives at
+    v[b + i*s0 + j*s1 + k*s2]."""
+    __slots__ = ("v", "b", "s", "lb", "shape", "kind")
+
+    def __init__(self, v, b, s, lb, shape, kind):
+        self.v, self.b, self.s, self.lb, self.shape, self.kind = v, b, tuple(s), tuple(lb), tuple(shape), kind
+
+    # ---- construction
+    @staticmethod
+    def alloc(kind, bounds, fill=None):
+        lb = tuple(b[0] for b in bounds)
+        shape = tuple(max(0, b[1] - b[0] + 1) for b in bounds)
+        n = _prod(shape)
+        if fill is None:
+            fill = NAN if kind == "r" else (0 if kind == "i" else (False if kind == "l" else None))
+        if kind == "o":
+            v = [NS() for _ in range(n)]
+        else:
+            v = [fill] * n
+        s, acc = [], 1
+        for e in shape:
+            s.append(acc)
+            acc *= e
+        return FArray(v, -sum(l * st for l, st in zip(lb, s)), s, lb, shape, kind)
+
+    @staticmethod
+    def from_numpy(a, lb=None, kind=None):
+        """a is C-ordered with the Fortran dimensions reversed ([k,j,i] for a Fortran (i,j,k) array)."""
+        import numpy as np
+        a = np.ascontiguousarray(a)
+        shape = tuple(reversed(a.shape))
+        if kind is None:
+            kind = "r" if a.dtype.kind == "f" else ("l" if a.dtype.kind == "b" else "i")
+        v = a.ravel().tolist()
+        if lb is None:
+            lb = (1,) * len(shape)
+        s, acc = [], 1
+        for e in shape:
+            s.append(acc)
+            acc *= e
+        return FArray(v, -sum(l * st for l, st in zip(lb, s)), s, lb, shape, kind)
+
+    def to_numpy(self):
+        import numpy as np
+        dt = {"r": np.float64, "i": np.int64, "l": np.bool_}[self.kind]
+        out = np.array(self.tolist(), dtype=dt)
+        return out.reshape(tuple(reversed(self.shape)))
+
+    def tolist(self):
+        """elements in Fortran array-element order"""
+        if len(self.shape) == 1:
+            b, s0, l0 = self.b, self.s[0], self.lb[0]
+            return [self.v[b + (l0 + i) * s0] for i in range(self.shape[0])]
+        out = []
+        self._walk(len(self.shape) - 1, self.b, out)
+        return out
+
+    def _walk(self, d, off, out):
+        s, l, n = self.s[d], self.lb[d], self.shape[d]
+        if d == 0:
+            v = self.v
+            out.extend(v[off + (l + i) * s] for i in range(n))
+        else:
+            for i in range(n):
+                self._walk(d - 1, off + (l + i) * s, out)
+
+    def _offsets(self):
+        out = []
+
+        def walk(d, off):
+            s, l, n = self.s[d], self.lb[d], self.shape[d]
+            if d == 0:
+                out.extend(off + (l + i) * s for i in range(n))
+            else:
+                for i in range(n):
+                    walk(d - 1, off + (l + i) * s)
+        if self.shape:
+            walk(len(self.shape) - 1, self.b)
+        return out
+
+    def rebase(self, lbs):
+        """the same elements seen through a dummy argument declared with lower bounds lbs (explicit-shape / assumed-shape rules)"""
+        lbs = tuple(lbs)
+        if len(lbs) != len(self.shape):
+            if _prod(self.shape) == 0:
+                return self
+            raise TypeError(f"rank mismatch in argument association: actual rank {len(self.shape)}, dummy rank {len(lbs)}")
+        if lbs == self.lb:
+            return self
+        b = self.b + sum((l - nl) * s for l, nl, s in zip(self.lb, lbs, self.s))
+        return FArray(self.v, b, self.s, lbs, self.shape, self.kind)
+
+    def check_extent(self, d, n, what=""):
+        if n is not None and self.shape[d] != n:
+            raise TypeError(f"{what}: dimension {d + 1} has extent {self.shape[d]}, the dummy argument declares {n}")
+
+    # ---- element access (bounds-checked: a silent wrap-around would hide an indexing error in the caller's adapter)
+    def _chk(self, d, i):
+        l = self.lb[d]
+        if i < l or i >= l + self.shape[d]:
+            raise IndexError(f"index {i} outside {l}:{l + self.shape[d] - 1} in dimension {d + 1}")
+
+    def g1(self, i):
+        l = self.lb[0]
+        if i < l or i >= l + self.shape[0]: self._chk(0, i)
+        return self.v[self.b + i * self.s[0]]
+
+    def g2(self, i, j):
+        lb, sh = self.lb, self.shape
+        if i < lb[0] or i >= lb[0] + sh[0]: self._chk(0, i)
+        if j < lb[1] or j >= lb[1] + sh[1]: self._chk(1, j)
+        s = self.s
+        return self.v[self.b + i * s[0] + j * s[1]]
+
+    def g3(self, i, j, k):
+        lb, sh = self.lb, self.shape
+        if i < lb[0] or i >= lb[0] + sh[0]: self._chk(0, i)
+        if j < lb[1] or j >= lb[1] + sh[1]: self._chk(1, j)
+        if k < lb[2] or k >= lb[2] + sh[2]: self._chk(2, k)
+        s = self.s
+        return self.v[self.b + i * s[0] + j * s[1] + k * s[2]]
+
+    def g(self, *idx):
+        off = self.b
+        if len(idx) != len(self.shape):
+            raise IndexError(f"rank {len(self.shape)} array referenced with {len(idx)} subscripts")
+        for d, i in enumerate(idx):
+            self._chk(d, i)
+            off += i * self.s[d]
+        return self.v[off]
+
+    def _cv(self, x):
+        k = self.kind
+        if k == "r":
+            return float(x)
+        if k == "i":
+            return int(x)
+        return x
+
+    def s1(self, i, x):
+        self._chk(0, i)
+        self.v[self.b + i * self.s[0]] = self._cv(x)
+
+    def s2(self, i, j, x):
+        self._chk(0, i); self._chk(1, j)
+        s = self.s
+        self.v[self.b + i * s[0] + j * s[1]] = self._cv(x)
+
+    def s3(self, i, j, k, x):
+        self._chk(0, i); self._chk(1, j); self._chk(2, k)
+        s = self.s
+        self.v[self.b + i * s[0] + j * s[1] + k * s[2]] = self._cv(x)
+
+    def s_(self, *a):
+        idx, x = a[:-1], a[-1]
+        off = self.b
+        if len(idx) != len(self.shape):
+            raise IndexError(f"rank {len(self.shape)} array assigned with {len(idx)} subscripts")
+        for d, i in enumerate(idx):
+            self._chk(d, i)
+            off += i * self.s[d]
+        self.v[off] = self._cv(x)
+
+    # ---- sections
+    def sec(self, *items):
+        """items: an int (that dimension collapses) or a (lo, hi, step) triplet with None for an omitted bound"""
+        if len(items) != len(self.shape):
+            raise IndexError(f"rank {len(self.shape)} array sectioned with {len(items)} subscripts")
+        b, s, lb, shape = self.b, [], [], []
+        for d, it in enumerate(items):
+            if isinstance(it, tuple):
+                lo, hi, st = it
+                if lo is None: lo = self.lb[d]
+                if hi is None: hi = self.lb[d] + self.shape[d] - 1
+                if st is None: st = 1
+                n = max(0, (hi - lo + st) // st)
+                if n > 0:
+                    self._chk(d, lo); self._chk(d, lo + (n - 1) * st)
+                # new dimension has lower bound 1: element m (1-based) is old index lo + (m-1)*st
+                b += (lo - st) * self.s[d]
+                s.append(self.s[d] * st); lb.append(1); shape.append(n)
+            else:
+                self._chk(d, it)
+                b += it * self.s[d]
+        return FArray(self.v, b, s, lb, shape, self.kind)
+
+    def assign(self, x):
+        """array assignment: self = x (a scalar, or a conformable array; the right side is fully evaluated first)"""
+        offs = self._offsets()
+        v, cv = self.v, self._cv
+        if isinstance(x, FArray):
+            vals = x.tolist()
+            if len(vals) != len(offs):
+                raise ValueError(f"array assignment of non-conformable shapes {x.shape} -> {self.shape}")
+            for o, val in zip(offs, vals):
+                v[o] = cv(val)
+        elif isinstance(x, (list, tuple)):
+            if len(x) != len(offs):
+                raise ValueError("array constructor of the wrong size")
+            for o, val in zip(offs, x):
+                v[o] = cv(val)
+        else:
+            if self.kind == "o":
+                raise TypeError("scalar assignment to an array of derived type")
+            val = cv(x)
+            for o in offs:
+                v[o] = val
+
+    # ---- elementwise expressions
+    def _new(self, vals, kind=None):
+        out = FArray.alloc(kind or self.kind, [(1, n) for n in self.shape])
+        out.v[:] = vals
+        return out
+
+    def _bin(self, o, f, kind=None):
+        a = self.tolist()
+        if isinstance(o, FArray):
+            b = o.tolist()
+            if len(a) != len(b):
+                raise ValueError("non-conformable array operands")
+            return self._new([f(x, y) for x, y in zip(a, b)], kind)
+        return self._new([f(x, o) for x in a], kind)
+
+    def __add__(self, o): return self._bin(o, lambda x, y: x + y)
+    def __radd__(self, o): return self._bin(o, lambda x, y: y + x)
+    def __sub__(self, o): return self._bin(o, lambda x, y: x - y)
+    def __rsub__(self, o): return self._bin(o, lambda x, y: y - x)
+    def __mul__(self, o): return self._bin(o, lambda x, y: x * y)
+    def __rmul__(self, o): return self._bin(o, lambda x, y: y * x)
+    def __truediv__(self, o): return div(self, o)
+    def __rtruediv__(self, o): return div(o, self)
+    def __neg__(self): return self._new([-x for x in self.tolist()])
+    def __pos__(self): return self
+    def __lt__(self, o): return self._bin(o, lambda x, y: x < y, "l")
+    def __le__(self, o): return self._bin(o, lambda x, y: x <= y, "l")
+    def __gt__(self, o): return self._bin(o, lambda x, y: x > y, "l")
+    def __ge__(self, o): return self._bin(o, lambda x, y: x >= y, "l")
+
+
+def alloc(kind, bounds, fill=None):
+    return FArray.alloc(kind, bounds, fill)
+
+
+def rebase(x, lbs, extents=None, what=""):
+    if x is None:
+        return None
+    if not isinstance(x, FArray):
+        raise TypeError(f"{what}: array dummy argument associated with a {type(x).__name__}")
+    y = x.rebase(lbs)
+    if extents is not None and len(y.shape) == len(extents):
+        for d, n in enumerate(extents):
+            if n is not None and y.shape[d] != n and _prod(y.shape) != 0:
+                raise TypeError(f"{what}: dimension {d + 1} of the actual argument has extent {y.shape[d]}, the dummy declares {n}")
+    return y
+
+
+# ---- arithmetic rules ----------------------------------------------------------------------------------------------------
+def div(a, b):
+    """Fortran '/': integer division truncates toward zero; real division is IEEE (x/0 -> inf or NaN, no exception)."""
+    ta, tb = type(a), type(b)
+    if ta is int and tb is int:
+        q = abs(a) // abs(b)
+        return q if (a >= 0) == (b >= 0) else -q
+    if ta is FArray:
+        return a._bin(b, div)
+    if tb is FArray:
+        return b._bin(a, lambda y, x: div(x, y))
+    try:
+        return a / b
+    except ZeroDivisionError:
+        a = float(a)
+        if a != a or a == 0.0:
+            return NAN
+        neg = (math.copysign(1.0, a) < 0) != (math.copysign(1.0, float(b)) < 0)
+        return -INF if neg else INF
+
+
+def powi(x, n):
+    """x**n for an integer n the way libgfortran's pow_r8_i4 does it (binary powering from the low bit up)."""
+    if type(x) is int:
+        if n >= 0:
+            return x ** n
+        return 1 if x == 1 else ((-1) ** n if x == -1 else 0)
+    if type(x) is FArray:
+        return x._new([powi(e, n) for e in x.tolist()])
+    u = -n if n < 0 else n
+    if n < 0:
+        x = div(1.0, x)
+    p = 1.0
+    if u == 0:
+        return p
+    while True:
+        if u & 1:
+            p = p * x
+        u >>= 1
+        if u:
+            x = x * x
+        else:
+            break
+    return p
+
+
+def power(x, y):
+    if type(y) is int:
+        return powi(x, y)
+    if type(x) is FArray:
+        return x._new([power(e, y) for e in x.tolist()])
+    x = float(x)
+    try:
+        return math.pow(x, y)  # libm pow, the routine the compiled reference calls
+    except (OverflowError, ValueError):
+        if x == 0.0 and y < 0:
+            return INF
+        if x < 0:
+            return NAN
+        return INF
+
+
+# ---- intrinsics ----------------------------------------------------------------------------------------------------------
+def _elemental(f):
+    def g(*a):
+        for x in a:
+            if type(x) is FArray:
+                lists = [y.tolist() if type(y) is FArray else None for y in a]
+                n = len(next(l for l in lists if l is not None))
+                vals = [f(*[(l[m] if l is not None else y) for l, y in zip(lists, a)]) for m in range(n)]
+                return x._new(vals)
+        return f(*a)
+    return g
+
+
+def _max(*a):
+    # gfortran: MAX(a,b) = (a > b || isnan(b)) ? a : b evaluated left to right; equal operands keep the LATER one only for NaN
+    m = a[0]
+    for x in a[1:]:
+        if x > m or m != m:
+            m = x
+    return m
+
+
+def _min(*a):
+    m = a[0]
+    for x in a[1:]:
+        if x < m or m != m:
+            m = x
+    return m
+
+
+def _sign(a, b):
+    if type(a) is int and type(b) is int:
+        return abs(a) if b >= 0 else -abs(a)
+    return math.copysign(a, b)
+
+
+def _mod(a, b):
+    if type(a) is int and type(b) is int:
+        return a - div(a, b) * b
+    return math.fmod(a, b)
+
+
+def _modulo(a, b):
+    if type(a) is int and type(b) is int:
+        return a % b
+    r = math.fmod(a, b)
+    if r != 0 and (r < 0) != (b < 0):
+        r += b
+    return r
+
+
+def _sqrt(x):
+    try:
+        return math.sqrt(x)
+    except ValueError:
+        return NAN
+
+
+def _exp(x):
+    try:
+        return math.exp(x)
+    except OverflowError:
+        return INF
+
+
+def _log(x):
+    try:
+        return math.log(x)
+    except ValueError:
+        return -INF if x == 0 else NAN
+
+
+def _nint(x):
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def _real(x, kind=None):
+    return float(x)
+
+
+def _int(x, kind=None):
+    return int(x)  # truncates toward zero
+
+
+def _size(a, dim=None):
+    if dim is None:
+        return _prod(a.shape)
+    return a.shape[dim - 1]
+
+
+def _lbound(a, dim=None):
+    return a.lb[dim - 1] if dim is not None else list(a.lb)
+
+
+def _ubound(a, dim=None):
+    if dim is not None:
+        return a.lb[dim - 1] + a.shape[dim - 1] - 1
+    return [l + n - 1 for l, n in zip(a.lb, a.shape)]
+
+
+def _sum(a, dim=None, mask=None):
+    t = 0.0 if a.kind == "r" else 0
+    if mask is not None:
+        for x, m in zip(a.tolist(), mask.tolist()):
+            if m:
+                t = t + x
+        return t
+    for x in a.tolist():  # array-element order, as a scalar loop would add them
+        t = t + x
+    return t
+
+
+def _maxval(a, dim=None, mask=None):
+    l = a.tolist()
+    return _max(*l) if l else -1.7976931348623157e308
+
+
+def _minval(a, dim=None, mask=None):
+    l = a.tolist()
+    return _min(*l) if l else 1.7976931348623157e308
+
+
+def _any(a):
+    return any(a.tolist()) if type(a) is FArray else bool(a)
+
+
+def _all(a):
+    return all(a.tolist()) if type(a) is FArray else bool(a)
+
+
+def _merge(t, f, m):
+    return t if m else f
+
+
+def _trim(s):
+    return s.rstrip()
+
+
+INTRINSICS = {
+    "abs": _elemental(abs), "max": _elemental(_max), "min": _elemental(_min), "sqrt": _elemental(_sqrt),
+    "sign": _elemental(_sign), "mod": _mod, "modulo": _modulo, "exp": _elemental(_exp), "log": _elemental(_log),
+    "sin": math.sin, "cos": math.cos, "tan": math.tan, "atan": math.atan, "atan2": math.atan2, "tanh": math.tanh,
+    "asin": math.asin, "acos": math.acos, "sinh": math.sinh, "cosh": math.cosh, "log10": math.log10,
+    "real": _real, "dble": _real, "float": _real, "int": _int, "nint": _nint, "floor": lambda x, kind=None: int(math.floor(x)),
+    "ceiling": lambda x, kind=None: int(math.ceil(x)), "aint": lambda x: float(int(x)),
+    "size": _size, "lbound": _lbound, "ubound": _ubound, "sum": _sum, "maxval": _maxval, "minval": _minval,
+    "any": _any, "all": _all, "merge": _merge, "trim": _trim, "adjustl": lambda s: s.lstrip(), "len_trim": lambda s: len(s.rstrip()),
+    "len": len, "epsilon": lambda x: 2.220446049250313e-16, "huge": lambda x: (1.7976931348623157e308 if type(x) is float else 2147483647),
+    "tiny": lambda x: 2.2250738585072014e-308, "isnan": lambda x: x != x, "ieee_is_nan": lambda x: x != x,
+    "count": lambda a: sum(1 for x in a.tolist() if x), "null": lambda: None,
+}
+
+
+def assign_attr(obj, name, x):
+    """obj%name = x where name may be an array component (array assignment) or a scalar / pointer component"""
+    cur = obj.__dict__.get(name)
+    if type(cur) is FArray and not (type(x) is FArray and x is cur):
+        cur.assign(x)
+    else:
+        setattr(obj, name, x)
+
+
+def tofloat(x):
+    return x if type(x) is FArray else float(x)
+
+
+def toint(x):
+    return x if type(x) is FArray else int(x)
+
+
+def assign_whole(cur, x):
+    """name = x for a declared array name: array assignment into the existing storage (an unallocated allocatable takes x's shape)"""
+    if cur is None:
+        if type(x) is FArray:
+            out = FArray.alloc(x.kind, [(l, l + n - 1) for l, n in zip(x.lb, x.shape)])
+            out.assign(x)
+            return out
+        raise ValueError("assignment to an unallocated array")
+    cur.assign(x)
+    return cur
+
+
+def generic(name, specifics):
+    """a generic interface: the first specific whose dummy arguments fit the actual ones (count, keywords, array rank) is called"""
+    def rank(x):
+        return len(x.shape) if type(x) is FArray else 0
+
+    def call(*a, **kw):
+        for f, sig in specifics:
+            if len(a) > len(sig):
+                continue
+            names = [s[0] for s in sig]
+            if any(k not in names for k in kw):
+                continue
+            given = dict(zip(names, a))
+            given.update(kw)
+            ok = True
+            for n, r, opt in sig:
+                if n not in given or given[n] is None:
+                    if not opt and n not in given:
+                        ok = False
+                        break
+                    continue
+                x = given[n]
+                if (r > 0) != (type(x) is FArray) or (r > 0 and rank(x) != r):
+                    ok = False
+                    break
+            if ok:
+                return f(*a, **kw)
+        raise TypeError(f"no specific procedure of generic {name} matches the call")
+    return call
+
+
+def new_type(ns, tname):
+    """an instance of derived type tname with its default component initialisations, if the type's module was translated"""
+    f = ns.get("_new_" + mangle(tname))
+    return f() if f is not None else NS()
+
+
+def alloc_types(ns, tname, bounds):
+    a = FArray.alloc("o", bounds)
+    a.v[:] = [new_type(ns, tname) for _ in a.v]
+    return a

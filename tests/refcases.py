@@ -1,0 +1,134 @@
+"""Seeded cases shared by tests/test_reference_f90.py (oracle vs the translated reference, live), by
+tests/golden/make_reference_digests.py (writes the digests of the reference's outputs) and by tests/test_reference_golden.py
+(oracle vs those digests, runs anywhere)."""
+import hashlib
+
+import numpy as np
+
+from mom6_b200 import synthetic
+
+CASES = {}
+
+
+def case(name, stage, shape, outputs, **kw):
+    CASES[name] = dict(stage=stage, shape=shape, outputs=outputs, kw=kw)
+
+
+def _copy(x):
+    if isinstance(x, np.ndarray):
+        return x.copy()
+    if isinstance(x, dict):
+        return {k: _copy(v) for k, v in x.items()}
+    if isinstance(x, list):
+        return [_copy(v) for v in x]
+    return x
+
+
+def inner(dom, x):
+    """the computational domain of an array on G's memory domain, including the symmetric edge of staggered fields"""
+    ni, nj = dom.ied - dom.isd + 1, dom.jed - dom.jsd + 1
+    di, dj = x.shape[-1] - ni, x.shape[-2] - nj
+    j0, i0 = dom.jsc - dom.jsd, dom.isc - dom.isd
+    return x[..., j0:j0 + (dom.jec - dom.jsc + 1) + dj, i0:i0 + (dom.iec - dom.isc + 1) + di]
+
+
+def collect(dom, outputs, a, cs):
+    out = {}
+    for key in outputs:
+        src, k = (cs, key[3:]) if key.startswith("CS%") else (a, key)
+        if "." in k:
+            d, m = k.split(".")
+            v = src[d][m] if src.get(d) is not None else None
+        else:
+            v = src.get(k)
+        if v is not None:
+            out[key] = np.ascontiguousarray(inner(dom, v))
+    return out
+
+
+def digest(arrs):
+    """sha256 over the outputs with -0.0 canonicalised to +0.0 (see tests/test_reference_f90.py)"""
+    h = hashlib.sha256()
+    for k in sorted(arrs):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(arrs[k] + 0.0).tobytes())
+    return h.hexdigest()
+
+
+# ---- continuity_PPM ------------------------------------------------------------------------------------------------------
+CONT_OUT = ("h", "uh", "vh", "u_cor", "v_cor", "du_cor", "dv_cor") + tuple(
+    "BT_cont." + k for k in ("FA_u_EE", "FA_u_E0", "FA_u_W0", "FA_u_WW", "uBT_WW", "uBT_EE", "FA_v_NN", "FA_v_N0", "FA_v_S0",
+                             "FA_v_SS", "vBT_SS", "vBT_NN", "h_u", "h_v"))
+case("continuity/default", "continuity", (24, 20, 10), CONT_OUT, land_blocks=2)
+case("continuity/monotonic_volCFL_y_first", "continuity", (20, 16, 8), CONT_OUT, land_blocks=2,
+     cs_over=dict(monotonic=1, vol_CFL=1, marginal_faces=0), first_direction=1)
+case("continuity/simple2nd_aggress_no_visc_rem", "continuity", (20, 16, 8), CONT_OUT, land_blocks=2,
+     cs_over=dict(simple_2nd=1, aggress_adjust=1, better_iter=0, use_visc_rem_max=0), with_visc_rem=False)
+case("continuity/upwind_closed_no_uhbt", "continuity", (20, 16, 8), CONT_OUT, land_blocks=2, cs_over=dict(upwind_1st=1),
+     with_uhbt=False, cyclic_x=False)
+case("continuity/no_BT_cont_alias_h", "continuity", (20, 16, 6), CONT_OUT, land_blocks=1, with_BT_cont=False, alias_h=True)
+case("continuity/75_layers", "continuity", (12, 10, 75), CONT_OUT, land_blocks=1)
+
+# ---- CorAdCalc -----------------------------------------------------------------------------------------------------------
+COR_OUT = ("CAu", "CAv", "gradKEu", "gradKEv")
+for _sch in (1, 2, 3, 4, 5, 6):
+    for _ke in (10, 11, 12):
+        case(f"coradcalc/scheme{_sch}_ke{_ke}", "coradcalc", (16, 12, 3), COR_OUT, land_blocks=2, diags=(_ke == 10),
+             cs_over=dict(Coriolis_Scheme=_sch, KE_Scheme=_ke))
+case("coradcalc/pv_adv_upwind1", "coradcalc", (16, 12, 3), COR_OUT, land_blocks=2, cs_over=dict(PV_Adv_Scheme=22))
+case("coradcalc/no_slip_bound_closed", "coradcalc", (16, 12, 3), COR_OUT, land_blocks=2, cyclic_x=False,
+     cs_over=dict(no_slip=1, bound_Coriolis=1))
+case("coradcalc/en_dis_porous", "coradcalc", (16, 12, 3), COR_OUT, land_blocks=2, por=True, cs_over=dict(Coriolis_En_Dis=1))
+
+# ---- btstep --------------------------------------------------------------------------------------------------------------
+BT_OUT = ("accel_layer_u", "accel_layer_v", "eta_out", "uhbtav", "vhbtav", "etaav", "CS%ubtav", "CS%vbtav", "CS%eta_cor")
+case("btstep/default", "btstep", (16, 12, 4), BT_OUT, land_blocks=2)
+case("btstep/no_uh0_no_etaav", "btstep", (12, 10, 3), BT_OUT, land_blocks=2, with_uh0=False, with_etaav=False)
+case("btstep/bottom_stress_arakawa_hsu", "btstep", (16, 12, 4), BT_OUT, land_blocks=2, with_bot=True, Sadourny=0)
+case("btstep/strong_drag_bound_corr", "btstep", (16, 12, 4), BT_OUT, land_blocks=2, strong_drag=1, bound_BT_corr=1,
+     BT_cont_bounds=0, visc_rem_u_uh0=1)
+case("btstep/narrow_halo_bugs", "btstep", (16, 12, 4), BT_OUT, land_blocks=2, use_wide_halos=0, wt_uv_bug=1,
+     use_old_coriolis_bracket_bug=1)
+case("btstep/project_velocity_filter_y_first", "btstep", (16, 12, 4), BT_OUT, land_blocks=2, BT_project_velocity=1,
+     dt_bt_filter=600.0, bebt=0.2, first_direction=1)
+case("btstep/closed_x_G_extra", "btstep", (16, 12, 4), BT_OUT, land_blocks=1, cyclic_x=False, G_extra=0.1)
+case("btstep/doubly_periodic_one_layer", "btstep", (12, 10, 1), BT_OUT, land_blocks=0, cyclic_y=True, with_uh0=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def build(name):
+    c = CASES[name]
+    st, shape, kw = c["stage"], c["shape"], dict(c["kw"])
+    if st == "continuity":
+        return synthetic.continuity_inputs(*shape, **kw)
+    if st == "coradcalc":
+        return synthetic.coradcalc_inputs(*shape, **kw)
+    if st == "btstep":
+        return synthetic.btstep_inputs(*shape, whalo=6, **kw)
+    raise KeyError(st)
+
+
+def run_oracle(oracle, name, inputs):
+    c = CASES[name]
+    dom, grid, gv, cs, a = inputs
+    cs, a = _copy(cs), _copy(a)
+    getattr(oracle, c["stage"])(dom, grid, gv, cs, a)
+    return collect(dom, c["outputs"], a, cs)
+
+
+def run_reference(name, inputs):
+    from oracle.f90run import stages
+    c = CASES[name]
+    dom, grid, gv, cs, a = inputs
+    cs, a = _copy(cs), _copy(a)
+    if c["stage"] == "btstep":
+        stages.btstep(dom, grid, gv, cs, a, stages.wide_metrics(dom, c["kw"].get("land_blocks", 0)))
+    else:
+        getattr(stages, c["stage"])(dom, grid, gv, cs, a)
+    return collect(dom, c["outputs"], a, cs)
+
+
+def run_case(oracle, name, want_ref=True):
+    inputs = build(name)
+    orc = run_oracle(oracle, name, inputs)
+    return (run_reference(name, inputs) if want_ref else None), orc

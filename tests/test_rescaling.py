@@ -103,7 +103,7 @@ def test_vertvisc_family(oracle, p):
 
 @pytest.mark.parametrize("p", POWERS)
 def test_btstep(oracle, p):
-    for kw in (dict(), dict(BT_project_velocity=1), dict(bound_BT_corr=1), dict(Sadourny=0), dict(strong_drag=1), dict(adjust_BT_cont=1)):
+    for kw in (dict(), dict(BT_project_velocity=1), dict(bound_BT_corr=1), dict(Sadourny=0), dict(strong_drag=1), dict(visc_rem_u_uh0=1)):
         dom, grid, gv, cs, a = synthetic.btstep_inputs(20, 14, 5, whalo=6, land_blocks=2, **kw)
         dcs = RS.with_flags(RS.BTSTEP_CS, cs)
         c0, a0 = _copy(cs), _copy(a); oracle.btstep(dom, grid, gv, c0, a0)
