@@ -215,7 +215,10 @@ class ProcGen:
         for cname, cargs in parts[1:]:
             s = s + "." + mangle(cname)
             if cargs is not None:
-                s = self.index(s, cargs)
+                if self.prog.is_bound(cname):   # a type-bound function
+                    s = s + "(" + ", ".join(self.ex(a) for a in cargs) + ")"
+                else:
+                    s = self.index(s, cargs)
         return s
 
     def call_expr(self, name, args):
@@ -329,7 +332,22 @@ class ProcGen:
             args = p.p_args()
         if "%" in name:
             tgt = ".".join(mangle(x) for x in name.split("%"))
-            self.emit(ind, f"{tgt}(" + ", ".join(self.ex(a) for a in args) + ")", ln)
+            argtxt = ", ".join(self.ex(a) for a in args)
+            impls = self.prog.bound(name.split("%")[-1])
+            outs = impls[0].out_scalars() if impls else []
+            if not outs:
+                self.emit(ind, f"{tgt}({argtxt})", ln)
+                return
+            f = impls[0]
+            r = self.newtmp("r")
+            self.emit(ind, f"{r} = {tgt}({argtxt})", ln)
+            pos = [a for a in args if a[0] != "kw"]
+            kws = {a[1]: a for a in args if a[0] == "kw"}
+            for n, d in enumerate(outs):
+                k = f.args.index(d) - 1   # the passed-object dummy comes first
+                actual = pos[k] if 0 <= k < len(pos) else kws.get(d)
+                if actual is not None:
+                    self.designator_store(ind, actual, f"{r}[{n}]", ln)
             return
         f = self.prog.find_proc(self.mod, name)
         argtxt = ", ".join(self.ex(a) for a in args)
@@ -459,6 +477,13 @@ class ProcGen:
             return
         m = re.match(r"allocate\s*\((.*)\)$", st, re.S)
         if m:
+            mt = re.match(r"\s*([a-z_]\w*)\s*::\s*(.*)$", m.group(1), re.S)
+            if mt:  # typed allocation of a polymorphic object
+                e = parse_expr(mt.group(2).strip())
+                parts = e[1]
+                tgt = self.ref(parts[:-1]) + "." + mangle(parts[-1][0]) if len(parts) > 1 else mangle(parts[-1][0])
+                self.emit(ind, f"{tgt} = _rt.new_type(globals(), {mt.group(1)!r})", ln)
+                return
             for it in _split_top(m.group(1)):
                 if re.match(r"(stat|source|mold|errmsg)\s*=", it):
                     mm = re.match(r"source\s*=\s*(.*)$", it)
@@ -581,6 +606,8 @@ class ProcGen:
                     pro.append(f"{n} = {self.coerce(v, parse_expr(v.init[1]))}")
                 elif v.pointer:
                     pro.append(f"{n} = None")
+                elif v.base == "integer" and v.dims is None:
+                    pro.append(f"{n} = 0")  # an undefined integer is read without harm in places (touch_ij(i,j))
             except (SyntaxError, NotImplementedError, ValueError, IndexError) as err:
                 pro.append(f"{n} = None  # declaration not translated: {err}")
         self.lines = []
@@ -590,12 +617,32 @@ class ProcGen:
         if self.globals_assigned:
             head.append("    global " + ", ".join(sorted(self.globals_assigned)))
         out = head + ["    " + p for p in pro] + body + ["    return " + self.ret, ""]
+        if P.elemental:
+            n = mangle(P.name)
+            out.append(f"{n} = _rt.elemental({n}, {[mangle(a) for a in P.args]!r}, {[mangle(a) for a in outs]!r}, {P.kind == 'function'!r})")
+            out.append("")
         return "\n".join(out)
 
 
 class Program:
     def __init__(self):
         self.modules = {}
+
+    def bound(self, name):
+        """the procedures a type-bound name may resolve to (one per type that binds it); [] if it is not a binding name"""
+        out = []
+        for m in self.modules.values():
+            for t, binds in m.type_binds.items():
+                if name in binds and binds[name] in m.procs:
+                    out.append(m.procs[binds[name]])
+        return out
+
+    def is_bound(self, name):
+        for m in self.modules.values():
+            for binds in m.type_binds.values():
+                if name in binds:
+                    return True
+        return False
 
     def add(self, mods):
         for m in mods:
@@ -645,7 +692,11 @@ class Program:
             out.append(ProcGen(self, mod, P).generate())
         for tname, comps in mod.types.items():
             out.append(f"def _new_{mangle(tname)}():")
-            out.append("    o = _rt.NS()")
+            ext = mod.type_ext.get(tname)
+            out.append(f"    o = _rt.new_type(globals(), {ext!r})" if ext else "    o = _rt.NS()")
+            out.append(f"    o._type = {tname!r}")
+            for b, impl in mod.type_binds.get(tname, {}).items():
+                out.append(f"    o.{mangle(b)} = _rt.bind(globals(), {mangle(impl)!r}, o)")
             pg = ProcGen(self, mod, _EmptyProc(mod))
             for cname, v in comps.items():
                 if v.init is not None and v.init[0] == "val" and v.dims is None:

@@ -518,6 +518,8 @@ INTRINSICS = {
     "len": len, "epsilon": lambda x: 2.220446049250313e-16, "huge": lambda x: (1.7976931348623157e308 if type(x) is float else 2147483647),
     "tiny": lambda x: 2.2250738585072014e-308, "isnan": lambda x: x != x, "ieee_is_nan": lambda x: x != x,
     "count": lambda a: sum(1 for x in a.tolist() if x), "null": lambda: None,
+    "btest": lambda i, pos: bool((i >> pos) & 1), "ibset": lambda i, pos: i | (1 << pos), "ibclr": lambda i, pos: i & ~(1 << pos),
+    "iand": lambda i, j: i & j, "ior": lambda i, j: i | j, "ishft": lambda i, s: (i << s) if s >= 0 else (i >> -s),
 }
 
 
@@ -591,3 +593,36 @@ def alloc_types(ns, tname, bounds):
     a = FArray.alloc("o", bounds)
     a.v[:] = [new_type(ns, tname) for _ in a.v]
     return a
+
+
+def bind(ns, fname, obj):
+    """a type-bound procedure: the module procedure fname called with obj as its passed-object dummy argument"""
+    def call(*a, **k):
+        return ns[fname](obj, *a, **k)
+    return call
+
+
+def elemental(f, argnames, outs, is_function):
+    """an elemental procedure: applied element by element when any actual argument is an array"""
+    def call(*a, **k):
+        args = dict(zip(argnames, a))
+        args.update(k)
+        arrs = {n: x for n, x in args.items() if type(x) is FArray}
+        if not arrs:
+            return f(*a, **k)
+        first = next(iter(arrs.values()))
+        lists = {n: x.tolist() for n, x in arrs.items()}
+        offs = {n: arrs[n]._offsets() for n in outs if n in arrs}
+        res = []
+        for m in range(_prod(first.shape)):
+            r = f(**{n: (lists[n][m] if n in lists else x) for n, x in args.items()})
+            if is_function:
+                res.append(r)
+            else:
+                for q, o in enumerate(outs):
+                    if o in offs:
+                        arrs[o].v[offs[o][m]] = arrs[o]._cv(r[q])
+        if is_function:
+            return first._new(res, "r" if res and type(res[0]) is float else None)
+        return tuple(args.get(o) for o in outs)
+    return call

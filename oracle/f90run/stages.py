@@ -167,3 +167,164 @@ def btstep(dom, grid, gv, cs, a, wide):
     for k in ("ubtav", "vbtav", "eta_cor"):
         adapt.back(getattr(CS, k), cs[k])
     return CS.nstep_last
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+HV_LOGICAL = ("Laplacian", "biharmonic", "no_slip", "bound_Kh", "better_bound_Kh", "bound_Ah", "better_bound_Ah",
+              "backscatter_underbound", "Smagorinsky_Kh", "Smagorinsky_Ah", "bound_Coriolis", "use_land_mask", "add_LES_viscosity",
+              "use_cont_thick", "use_cont_thick_bug")
+
+
+def horizontal_viscosity(dom, grid, gv, cs, a):
+    """horizontal_viscosity, src/parameterizations/lateral/MOM_hor_visc.F90:266-2290"""
+    R = ref("src/parameterizations/lateral/MOM_hor_visc.F90")
+    F = R["mom_hor_visc"]
+    G, GV, US = _types(dom, grid, gv)
+    CS = _set(new(R, "mom_hor_visc", "hor_visc_cs", initialized=True), cs, HV_LOGICAL)
+    for k, v in cs.items():
+        if isinstance(v, np.ndarray):
+            setattr(CS, k.lower(), adapt.farr(dom, v))
+    CS.answer_date = 99991231
+    for k in ("anisotropic", "leith_kh", "leith_ah", "use_leithy", "modified_leith", "use_qg_leith_visc", "use_beta_in_leith",
+              "use_gme", "use_zb2020", "smooth_ah", "debug", "res_scale_meke", "frictwork_bug", "ey24_ebt_bs"):
+        setattr(CS, k, False)
+    fa = _fa(dom, a)
+    uh = fa.get("uh") or adapt.farr(dom, np.zeros_like(a["u"]))
+    vh = fa.get("vh") or adapt.farr(dom, np.zeros_like(a["v"]))
+    MEKE, VarMix, tv = NS(), NS(use_variable_mixing=False, resoln_scaled_kh=False, resoln_scaled_khth=False), NS()
+    F["horizontal_viscosity"](fa["u"], fa["v"], fa["h"], uh, vh, fa["diffu"], fa["diffv"], MEKE, VarMix, G, GV, US, CS, tv,
+                              a["dt"], hu_cont=fa.get("hu_cont"), hv_cont=fa.get("hv_cont"))
+    _back(fa, a, ("diffu", "diffv"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+VV_LOGICAL = ("bottomdraglaw", "harmonic_visc", "direct_stress", "fixed_LOTW_ML", "apply_LOTW_floor", "dynamic_viscous_ML")
+
+
+def _vertvisc_setup(dom, grid, gv, cs, a_u, a_v, h_u, h_v):
+    R = ref("src/parameterizations/vertical/MOM_vert_friction.F90", "src/core/MOM_forcing_type.F90")
+    G, GV, US = _types(dom, grid, gv)
+    CS = _set(new(R, "mom_vert_friction", "vertvisc_cs", initialized=True), cs, VV_LOGICAL)
+    GV.nkml = int(cs.get("nkml", 0))
+    GV.dz_subroundoff = float(cs.get("dZ_subroundoff", 1.0e-30))
+    nk = int(dom.nk)
+    lbu, lbv = adapt.stagger_lb(dom, "u"), adapt.stagger_lb(dom, "v")
+    CS.a_u, CS.a_v = FArray.from_numpy(a_u, lbu + (1,)), FArray.from_numpy(a_v, lbv + (1,))
+    CS.h_u, CS.h_v = FArray.from_numpy(h_u, lbu + (1,)), FArray.from_numpy(h_v, lbv + (1,))
+    for k in ("debug", "use_gl90_in_ssw", "stokesmixing"):
+        setattr(CS, k, False)
+    CS.pass_ke_uv = NS()
+    # vertvisc_limit_vel (:2926-3120) with its defaults (vertvisc_init :3389-3402): truncation of velocities whose CFL exceeds 0.5
+    CS.maxvel, CS.cfl_based_trunc, CS.cfl_trunc, CS.cfl_report = 3.0e8, True, 0.5, 0.5
+    CS.u_trunc_file, CS.v_trunc_file, CS.ntrunc = "", "", 0
+    return R["mom_vert_friction"], G, GV, US, CS
+
+
+def _interfaces(dom, a, st):
+    """(nk+1, nj, ni) interface array at h- or q-points -> FArray (i, j, K=1:nk+1)"""
+    if a is None:
+        return None
+    return FArray.from_numpy(a, adapt.stagger_lb(dom, st) + (1,))
+
+
+def vertvisc_coef(dom, grid, gv, cs, a, a_u, a_v, h_u, h_v):
+    """vertvisc_coef, src/parameterizations/vertical/MOM_vert_friction.F90:1357-1840 with find_coupling_coef :2314-2760"""
+    F, G, GV, US, CS = _vertvisc_setup(dom, grid, gv, cs, a_u, a_v, h_u, h_v)
+    f = lambda k: adapt.farr(dom, a[k])  # noqa: E731
+    dz = adapt.farr(dom, gv["H_to_Z"] * a["h"])   # thickness_to_dz, Boussinesq: src/core/MOM_interface_heights.F90:790-801
+    forces = NS(ustar=f("ustar"), tau_mag=None, frac_shelf_u=None, frac_shelf_v=None)
+    visc = NS(kv_bbl_u=f("Kv_bbl_u"), kv_bbl_v=f("Kv_bbl_v"), bbl_thick_u=f("bbl_thick_u"), bbl_thick_v=f("bbl_thick_v"),
+              kv_shear=_interfaces(dom, a.get("Kv_shear"), "h"), kv_shear_bu=_interfaces(dom, a.get("Kv_shear_Bu"), "q"))
+    F["vertvisc_coef"](f("u"), f("v"), f("h"), dz, forces, visc, NS(), a["dt"], G, GV, US, CS, None, NS())
+    for fa, out in ((CS.a_u, a_u), (CS.a_v, a_v), (CS.h_u, h_u), (CS.h_v, h_v)):
+        adapt.back(fa, out)
+
+
+def vertvisc_remnant(dom, grid, gv, cs, visc_rem_u, visc_rem_v, dt, a_u, a_v, h_u, h_v, Ray_u=None, Ray_v=None):
+    """vertvisc_remnant, MOM_vert_friction.F90:1229-1330"""
+    F, G, GV, US, CS = _vertvisc_setup(dom, grid, gv, cs, a_u, a_v, h_u, h_v)
+    visc = NS(ray_u=adapt.farr(dom, Ray_u), ray_v=adapt.farr(dom, Ray_v))
+    fu, fv = adapt.farr(dom, visc_rem_u), adapt.farr(dom, visc_rem_v)
+    F["vertvisc_remnant"](visc, fu, fv, dt, G, GV, US, CS)
+    adapt.back(fu, visc_rem_u); adapt.back(fv, visc_rem_v)
+
+
+def vertvisc(dom, grid, gv, cs, a, a_u, a_v, h_u, h_v):
+    """vertvisc, MOM_vert_friction.F90:557-1010"""
+    F, G, GV, US, CS = _vertvisc_setup(dom, grid, gv, cs, a_u, a_v, h_u, h_v)
+    fa = _fa(dom, a)
+    forces = NS(taux=fa["taux"], tauy=fa["tauy"])
+    visc = NS(ray_u=fa.get("Ray_u"), ray_v=fa.get("Ray_v"))
+    F["vertvisc"](fa["u"], fa["v"], fa["h"], forces, visc, a["dt"], None, NS(), NS(), G, GV, US, CS,
+                  fa.get("taux_bot"), fa.get("tauy_bot"))
+    _back(fa, a, ("u", "v", "taux_bot", "tauy_bot"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+EOS_FILES = ("src/equation_of_state/MOM_EOS.F90", "src/equation_of_state/MOM_EOS_base_type.F90",
+             "src/equation_of_state/MOM_EOS_Wright.F90", "src/equation_of_state/MOM_EOS_linear.F90")
+PGF_FILES = ("src/core/MOM_PressureForce_FV.F90", "src/core/MOM_PressureForce_Montgomery.F90", "src/core/MOM_density_integrals.F90",
+             "src/ALE/MOM_ALE.F90", "src/ALE/regrid_solvers.F90", "src/ALE/PLM_functions.F90", "src/ALE/PPM_functions.F90", "src/ALE/regrid_edge_values.F90") + EOS_FILES
+
+
+def eos_type(R, cs):
+    """EOS_type (src/equation_of_state/MOM_EOS.F90:107-152) the way EOS_init (:1540-1790) leaves it for LINEAR / WRIGHT"""
+    form = int(cs["EOS_form"])
+    if form == 0:
+        return None
+    E = new(R, "mom_eos", "eos_type")
+    E.form_of_eos = form
+    E.eos_quadrature = False
+    E.compressible = True
+    for k in ("Rho_T0_S0", "dRho_dT", "dRho_dS", "dRho_dp"):
+        setattr(E, k.lower(), float(cs.get(k, 0.0)))
+    one = lambda k: float(cs.get(k, 0.0)) or 1.0  # noqa: E731
+    E.kg_m3_to_r, E.rl2_t2_to_pa, E.c_to_degc, E.s_to_ppt = one("kg_m3_to_R"), one("RL2_T2_to_Pa"), one("C_to_degC"), one("S_to_ppt")
+    E.r_to_kg_m3, E.degc_to_c, E.ppt_to_s = 1.0 / E.kg_m3_to_r, 1.0 / E.c_to_degc, 1.0 / E.s_to_ppt
+    if form == 1:
+        E.type_ = new(R, "mom_eos_linear", "linear_eos")
+        E.type_.rho_t0_s0, E.type_.drho_dt, E.type_.drho_ds = E.rho_t0_s0, E.drho_dt, E.drho_ds
+        E.type_.drho_dp = E.drho_dp
+    elif form == 3:
+        E.type_ = new(R, "mom_eos_wright", "buggy_wright_eos")
+    else:
+        raise ValueError("EOS form outside the frozen option set")
+    return E
+
+
+def pressure_force(dom, grid, gv, cs, a, us=None):
+    """PressureForce_FV_Bouss, src/core/MOM_PressureForce_FV.F90:947-2017, with int_density_dz / int_density_dz_generic_plm /
+    _ppm (MOM_density_integrals.F90), the EOS modules, TS_PLM/PPM_edge_values (MOM_ALE.F90:1495-1660) and Set_pbce_Bouss"""
+    R = ref(*PGF_FILES)
+    F = R["mom_pressureforce_fv"]
+    G, GV, US = _types(dom, grid, gv, us)
+    G.z_ref = float(cs.get("Z_ref", 0.0))
+    GV.dz_subroundoff = float(cs.get("dZ_subroundoff", 1.0e-30))
+    GV.nk_rho_varies = 0
+    if cs.get("Rlay") is not None:
+        GV.rlay = FArray.from_numpy(np.asarray(cs["Rlay"], dtype=np.float64), (1,))
+        GV.g_prime = FArray.from_numpy(np.asarray(cs["g_prime"], dtype=np.float64), (1,))
+    CS = new(R, "mom_pressureforce_fv", "pressureforce_fv_cs", initialized=True)
+    CS.masswghtinterp = int(cs["MassWghtInterp"])
+    CS.use_ssh_in_z0p, CS.rho_ref_bug = bool(cs["use_SSH_in_Z0p"]), bool(cs["rho_ref_bug"])
+    CS.rho_ref, CS.gfs_scale, CS.rho0 = float(cs["rho_ref"]), float(cs["GFS_scale"]), float(gv["Rho0"])
+    CS.reconstruct = bool(cs.get("reconstruct", 0))
+    CS.recon_scheme = int(cs.get("Recon_Scheme", 0)) or 1
+    CS.boundary_extrap = bool(cs.get("boundary_extrap", 0))
+    CS.use_inaccurate_pgf_rho_anom = bool(cs.get("use_inaccurate_pgf_rho_anom", 0))
+    CS.masswghtinterpvanonly = bool(cs.get("MassWghtInterpVanOnly", 0))
+    CS.h_nonvanished = float(cs.get("h_nonvanished", 0.0))
+    for k in ("calculate_sal", "tides", "sal_use_bpa", "bq_sal_tides", "use_stanley_pgf", "reset_intxpa_integral", "debug",
+              "correction_intxpa", "reset_intxpa_flattest"):
+        setattr(CS, k, False)
+    E = eos_type(R, cs)
+    tv = NS(eqn_of_state=E, t=adapt.farr(dom, a.get("T")), s=adapt.farr(dom, a.get("S")), p_ref=0.0, vart=None)
+    ALE = None
+    if CS.reconstruct and E is not None:
+        ALE = new(R, "mom_ale", "ale_cs")
+        ALE.answer_date = int(cs.get("ALE_answer_date", 0)) or 99991231
+        ALE.nk = int(dom.nk)
+    fa = _fa(dom, a, skip=("T", "S"))
+    F["pressureforce_fv_bouss"](fa["h"], tv, fa["PFu"], fa["PFv"], G, GV, US, CS, ALE, None, fa.get("p_atm"),
+                                pbce=fa.get("pbce"), eta=fa.get("eta"))
+    _back(fa, a, ("PFu", "PFv", "pbce", "eta"))

@@ -465,13 +465,13 @@ _DECL = re.compile(r"^(real|integer|logical|character|type|class|double\s+precis
 
 
 class Var:
-    __slots__ = ("name", "base", "tname", "dims", "intent", "optional", "pointer", "parameter", "init", "allocatable", "dummy")
+    __slots__ = ("name", "base", "tname", "dims", "intent", "optional", "pointer", "parameter", "init", "allocatable", "dummy", "target")
 
     def __init__(self, name, base, tname=None):
         self.name, self.base, self.tname = name, base, tname
         self.dims = None
         self.intent = None
-        self.optional = self.pointer = self.parameter = self.allocatable = self.dummy = False
+        self.optional = self.pointer = self.parameter = self.allocatable = self.dummy = self.target = False
         self.init = None
 
     @property
@@ -562,6 +562,7 @@ class Proc:
         self.body = []      # nested statement tree
         self.line = 0
         self.uses = []
+        self.elemental = False
 
     def out_scalars(self):
         """dummy arguments that are scalars of intrinsic type and may be defined by the procedure (copied out to the caller)"""
@@ -586,9 +587,20 @@ class Module:
         self.generics = {}  # generic name -> [specific names]
         self.uses = []      # (module, only-list or None as [(local, remote)])
         self.types = {}     # type name -> {component name -> Var}
+        self.type_ext = {}  # type name -> parent type name or None
+        self.type_binds = {}  # type name -> {binding name -> procedure name}
 
 
-_HDR = re.compile(r"^(?:(?:pure|elemental|recursive|impure)\s+)*(?:(?:real|integer|logical)\s*(?:\([^)]*\))?\s+)?(subroutine|function)\s+([a-z_]\w*)\s*(\(.*)?$")
+def find_assign_simple(st):
+    depth = 0
+    for k, c in enumerate(st):
+        depth += (c == "(") - (c == ")")
+        if c == "=" and depth == 0 and st[k:k + 2] != "=>" and st[k - 1:k + 1] not in ("==", "/=", "<=", ">="):
+            return k
+    return -1
+
+
+_HDR = re.compile(r"^(?:(?:pure|elemental|recursive|impure|real|integer|logical)(?:\s*\([^)]*\))?\s+)*(subroutine|function)\s+([a-z_]\w*)\s*(\(.*)?$")
 
 
 def parse_use(st):
@@ -647,14 +659,32 @@ def _parse_module_spec(sts, i, mod):
         m = re.match(r"type\s*(?:,\s*[^:]*)?(?:::)?\s*([a-z_]\w*)$", st)
         if m and not st.startswith("type("):
             comps = {}
+            ext = re.search(r"extends\s*\(\s*([a-z_]\w*)\s*\)", st)
+            binds = {}
             i += 1
+            in_bind = False
             while not re.match(r"end\s*type", sts[i][1]):
-                d = parse_decl(sts[i][1])
-                if d:
-                    for v in d:
-                        comps[v.name] = v
+                t = sts[i][1]
+                if t == "contains":
+                    in_bind = True
+                elif in_bind:
+                    mm = re.match(r"procedure\s*(?:\([^)]*\))?\s*(?:,[^:]*)?::\s*(.*)$", t)
+                    if mm and "deferred" not in t:
+                        for it in _split_top(mm.group(1)):
+                            if "=>" in it:
+                                l, r = it.split("=>")
+                                binds[l.strip()] = r.strip()
+                            else:
+                                binds[it.strip()] = it.strip()
+                else:
+                    d = parse_decl(t)
+                    if d:
+                        for v in d:
+                            comps[v.name] = v
                 i += 1
             mod.types[m.group(1)] = comps
+            mod.type_ext[m.group(1)] = ext.group(1) if ext else None
+            mod.type_binds[m.group(1)] = binds
             i += 1
             continue
         m = re.match(r"(?:abstract\s+)?interface\s*([a-z_]\w*)?$", st)
@@ -695,11 +725,13 @@ def _parse_proc(sts, i, mod):
         result = name
     P = Proc(name, kind, args, result, mod)
     P.line = ln
-    m = re.match(r"^(?:(?:pure|elemental|recursive|impure)\s+)*(real|integer|logical)", st)
+    P.elemental = bool(re.search(r"\belemental\b", st.split("(")[0]))
+    m = re.search(r"\b(real|integer|logical)\b(?=.*\bfunction\b)", st.split("(")[0])
     if kind == "function" and m and result not in P.vars:
         P.vars[result] = Var(result, m.group(1))
     i += 1
     n = len(sts)
+    pending_attrs = []
     # specification part
     while i < n:
         ln, st = sts[i]
@@ -712,12 +744,25 @@ def _parse_proc(sts, i, mod):
         if st.startswith("implicit") or st.startswith("external") or st.startswith("save") or st.startswith("intrinsic"):
             i += 1
             continue
+        ma = re.match(r"(optional|pointer|target|allocatable)\s*(?:::)?\s*(.*)$", st)
+        if ma and find_assign_simple(st) < 0:
+            for nm in _split_top(ma.group(2)):
+                nm = nm.strip()
+                if nm in P.vars:
+                    setattr(P.vars[nm], ma.group(1), True)
+                else:
+                    pending_attrs.append((nm, ma.group(1)))
+            i += 1
+            continue
         d = parse_decl(st)
         if d is None:
             break
         for v in d:
             P.vars[v.name] = v
         i += 1
+    for nm, attr in pending_attrs:
+        if nm in P.vars:
+            setattr(P.vars[nm], attr, True)
     for a in args:
         if a in P.vars:
             P.vars[a].dummy = True

@@ -95,7 +95,62 @@ case("btstep/closed_x_G_extra", "btstep", (16, 12, 4), BT_OUT, land_blocks=1, cy
 case("btstep/doubly_periodic_one_layer", "btstep", (12, 10, 1), BT_OUT, land_blocks=0, cyclic_y=True, with_uh0=False)
 
 
+# ---- horizontal_viscosity ------------------------------------------------------------------------------------------------
+HV_OUT = ("diffu", "diffv")
+for _n, _kw in enumerate([
+        dict(), dict(land_blocks=4, Ah=1.0e11), dict(land_blocks=4, Laplacian=True, Kh=800.0, Smagorinsky_Kh=True),
+        dict(land_blocks=3, Laplacian=True, biharmonic=False, Kh_vel_scale=0.01),
+        dict(land_blocks=3, Laplacian=True, Smagorinsky_Kh=True, better_bound_Kh=False, better_bound_Ah=False),
+        dict(land_blocks=3, bound_Coriolis=True), dict(land_blocks=3, no_slip=True, Laplacian=True, Kh=300.0),
+        dict(land_blocks=3, use_land_mask=True, add_LES_viscosity=True, Laplacian=True, Smagorinsky_Kh=True, Kh_bg_min=50.0),
+        dict(land_blocks=3, Re_Ah=20.0), dict(land_blocks=3, cont_thick=True),
+        dict(land_blocks=2, Laplacian=True, better_bound_Ah=False, Kh=100.0),
+        dict(land_blocks=2, bound_Ah=False, better_bound_Ah=False, Smagorinsky_Ah=False, Ah_vel_scale=0.01, cyclic_y=True)]):
+    case(f"horizontal_viscosity/options{_n:02d}", "horizontal_viscosity", (16, 12, 3), HV_OUT, **_kw)
+
+# ---- vertvisc_coef -> vertvisc_remnant -> vertvisc ------------------------------------------------------------------------
+VV_OUT = ("a_u", "a_v", "h_u", "h_v", "visc_rem_u", "visc_rem_v", "u", "v", "taux_bot", "tauy_bot")
+for _n, _kw in enumerate([
+        dict(), dict(land_blocks=4, with_Bu=True, with_Ray=True), dict(harmonic_visc=1, land_blocks=3),
+        dict(bottomdraglaw=0, Kv_extra_bbl=5e-3), dict(bottomdraglaw=0, land_blocks=2, cyclic_y=True),
+        dict(Kvml_invZ2=1e-3, land_blocks=2), dict(harm_BL_val=0.5, with_Ray=True), dict(fixed_LOTW_ML=1, land_blocks=3),
+        dict(apply_LOTW_floor=1), dict(fixed_LOTW_ML=1, apply_LOTW_floor=1, Kvml_invZ2=1e-3, harmonic_visc=1),
+        dict(direct_stress=1, land_blocks=2, with_Ray=True)]):
+    case(f"vertvisc_family/options{_n:02d}", "vertvisc_family", (16, 12, 6), VV_OUT, **_kw)
+
+# ---- PressureForce_FV_Bouss ----------------------------------------------------------------------------------------------
+PF_OUT = ("PFu", "PFv", "pbce", "eta")
+for _n, _kw in enumerate([
+        dict(), dict(eos="LINEAR"), dict(eos="NONE"), dict(MassWghtInterp=1, with_p_atm=True),
+        dict(use_SSH_in_Z0p=1, MassWghtInterp=3, rho_ref_bug=1), dict(reconstruct=1, Recon_Scheme=1),
+        dict(reconstruct=1, Recon_Scheme=2), dict(reconstruct=1, Recon_Scheme=1, boundary_extrap=1, MassWghtInterp=1, eos="LINEAR"),
+        dict(reconstruct=1, Recon_Scheme=2, boundary_extrap=1, use_inaccurate_pgf_rho_anom=1)]):
+    case(f"pressure_force/options{_n:02d}", "pressure_force", (14, 10, 5), PF_OUT, land_blocks=2, **_kw)
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
+def _coefs(dom, nk):
+    from mom6_b200 import fidx
+    return [np.zeros((nk + 1,) + fidx.new(dom, "u").a.shape), np.zeros((nk + 1,) + fidx.new(dom, "v").a.shape),
+            fidx.new(dom, "u", nk=nk).a, fidx.new(dom, "v", nk=nk).a]
+
+
+def vertvisc_family(mod, dom, grid, gv, cs, coef, sol, is_oracle):
+    """vertvisc_coef, then vertvisc_remnant and vertvisc with its coefficients (the order of step_MOM_dyn_split_RK2)"""
+    nk = int(dom.nk)
+    c = _coefs(dom, nk)
+    s = _copy(sol)
+    mod.vertvisc_coef(dom, grid, gv, cs, _copy(coef), *c)
+    vru, vrv = np.zeros_like(sol["u"]), np.zeros_like(sol["v"])
+    if is_oracle:
+        mod.vertvisc_remnant(dom, grid, cs, vru, vrv, sol["dt"], *c, sol["Ray_u"], sol["Ray_v"])
+    else:
+        mod.vertvisc_remnant(dom, grid, gv, cs, vru, vrv, sol["dt"], *c, sol["Ray_u"], sol["Ray_v"])
+    mod.vertvisc(dom, grid, gv, cs, s, *c)
+    return dict(a_u=c[0], a_v=c[1], h_u=c[2], h_v=c[3], visc_rem_u=vru, visc_rem_v=vrv, u=s["u"], v=s["v"],
+                taux_bot=s["taux_bot"], tauy_bot=s["tauy_bot"])
+
+
 def build(name):
     c = CASES[name]
     st, shape, kw = c["stage"], c["shape"], dict(c["kw"])
@@ -105,11 +160,20 @@ def build(name):
         return synthetic.coradcalc_inputs(*shape, **kw)
     if st == "btstep":
         return synthetic.btstep_inputs(*shape, whalo=6, **kw)
+    if st == "horizontal_viscosity":
+        return synthetic.hor_visc_inputs(*shape, **kw)
+    if st == "vertvisc_family":
+        return synthetic.vertvisc_inputs(*shape, **kw)
+    if st == "pressure_force":
+        return synthetic.pressureforce_inputs(*shape, **kw)
     raise KeyError(st)
 
 
 def run_oracle(oracle, name, inputs):
     c = CASES[name]
+    if c["stage"] == "vertvisc_family":
+        dom, grid, gv, cs, coef, sol = inputs
+        return collect(dom, c["outputs"], vertvisc_family(oracle, dom, grid, gv, cs, coef, sol, True), {})
     dom, grid, gv, cs, a = inputs
     cs, a = _copy(cs), _copy(a)
     getattr(oracle, c["stage"])(dom, grid, gv, cs, a)
@@ -119,6 +183,9 @@ def run_oracle(oracle, name, inputs):
 def run_reference(name, inputs):
     from oracle.f90run import stages
     c = CASES[name]
+    if c["stage"] == "vertvisc_family":
+        dom, grid, gv, cs, coef, sol = inputs
+        return collect(dom, c["outputs"], vertvisc_family(stages, dom, grid, gv, cs, coef, sol, False), {})
     dom, grid, gv, cs, a = inputs
     cs, a = _copy(cs), _copy(a)
     if c["stage"] == "btstep":
