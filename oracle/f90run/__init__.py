@@ -56,7 +56,7 @@ def load(paths, extra_stubs=None, verbose=False):
     stub_ns = dict(stubs.NAMES)
     if extra_stubs:
         stub_ns.update(extra_stubs)
-    for full, mods in srcs:
+    for full, mods in srcs + srcs:   # twice: alias-only modules (MOM_continuity) re-export what they import
         for m in mods:
             ns = spaces[m.name]
             uses = list(m.uses)

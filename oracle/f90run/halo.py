@@ -33,23 +33,25 @@ def _src(lo, hi, n, clo, chi, cyclic):
 
 
 def update(a, D, xstag=None, ystag=None):
-    """fill the halo of FArray a (rank 2 or 3, horizontal dimensions first) on domain D"""
+    """fill the halo of FArray a (rank 2 or 3, horizontal dimensions first) on domain D.  The array may be seen through any
+    lower bounds (an array section passed to create_group_pass starts at 1): its position in the domain follows from its
+    extents, which are those of a memory domain with equal halos on both sides."""
     ni, nj = D.iec - D.isc + 1, D.jec - D.jsc + 1
-    ilo, jlo = a.lb[0], a.lb[1]
-    ihi, jhi = ilo + a.shape[0] - 1, jlo + a.shape[1] - 1
-    # the stagger follows from the extents: symmetric u/q arrays have one more point in i, v/q arrays one more in j
-    nxh = ihi - ilo + 1
-    nyh = jhi - jlo + 1
+    nxh, nyh = a.shape[0], a.shape[1]
     if xstag is None:
         xstag = ((nxh - ni) % 2) == 1
     if ystag is None:
         ystag = ((nyh - nj) % 2) == 1
+    wi, wj = (nxh - ni - (1 if xstag else 0)) // 2, (nyh - nj - (1 if ystag else 0)) // 2
+    ilo, jlo = D.isc - wi - (1 if xstag else 0), D.jsc - wj - (1 if ystag else 0)   # true index of the first element
+    ihi, jhi = ilo + nxh - 1, jlo + nyh - 1
     si = _src(ilo, ihi, ni, D.isc - (1 if xstag else 0), D.iec, D.cyclic_x)
     sj = _src(jlo, jhi, nj, D.jsc - (1 if ystag else 0), D.jec, D.cyclic_y)
-    v, b, s = a.v, a.b, a.s
+    v, s = a.v, a.s
+    b = a.b + a.lb[0] * s[0] + a.lb[1] * s[1]    # offset of the first horizontal element
     nk = a.shape[2] if len(a.shape) == 3 else 1
-    klo = a.lb[2] if len(a.shape) == 3 else 0
     s2 = s[2] if len(a.shape) == 3 else 0
+    b += (a.lb[2] * s2) if len(a.shape) == 3 else 0
     for jj, j in enumerate(range(jlo, jhi + 1)):
         js = sj[jj]
         for ii, i in enumerate(range(ilo, ihi + 1)):
@@ -58,9 +60,9 @@ def update(a, D, xstag=None, ystag=None):
                 continue
             if is_ is None or js is None:
                 continue
-            d = b + i * s[0] + j * s[1]
-            o = b + is_ * s[0] + js * s[1]
-            for k in range(klo, klo + nk):
+            d = b + ii * s[0] + jj * s[1]
+            o = b + (is_ - ilo) * s[0] + (js - jlo) * s[1]
+            for k in range(nk):
                 v[d + k * s2] = v[o + k * s2]
 
 

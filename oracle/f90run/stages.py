@@ -328,3 +328,155 @@ def pressure_force(dom, grid, gv, cs, a, us=None):
     F["pressureforce_fv_bouss"](fa["h"], tv, fa["PFu"], fa["PFv"], G, GV, US, CS, ALE, None, fa.get("p_atm"),
                                 pbce=fa.get("pbce"), eta=fa.get("eta"))
     _back(fa, a, ("PFu", "PFv", "pbce", "eta"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def advect_tracer(dom, grid, gv, cs, a):
+    """advect_tracer, src/tracer/MOM_tracer_advect.F90:53-365, with advect_x :370-740 and advect_y :745-1130"""
+    R = ref("src/tracer/MOM_tracer_advect.F90", "src/tracer/MOM_tracer_advect_schemes.F90")
+    F = R["mom_tracer_advect"]
+    G, GV, US = _types(dom, grid, gv)
+    CS = new(R, "mom_tracer_advect", "tracer_advect_cs")
+    CS.dt, CS.default_advect_scheme = float(cs["dt"]), int(cs["default_advect_scheme"])
+    CS.usehuynhstencilbug = bool(cs.get("useHuynhStencilBug", 0))
+    CS.debug = False
+    CS.pass_uhr_vhr_t_hprev = NS()
+    ntr = len(a["tr"])
+    Tr = FArray.alloc("o", [(1, ntr)])
+    fts = [adapt.farr(dom, t) for t in a["tr"]]
+    sch = a.get("advect_scheme") if a.get("advect_scheme") is not None else [-1] * ntr
+    cu = a.get("conc_underflow") if a.get("conc_underflow") is not None else [0.0] * ntr
+    for m, ft in enumerate(fts):
+        Tr.v[m] = NS(t=ft, advect_scheme=int(sch[m]), conc_underflow=float(cu[m]), ntr_index=m + 1, advection_xy=None, ad_x=None,
+                     ad_y=None, ad2d_x=None, ad2d_y=None, tres=None)
+    Reg = NS(ntr=ntr, tr=Tr)
+    fa = _fa(dom, a)
+    F["advect_tracer"](fa["h_end"], fa["uhtr"], fa["vhtr"], None, a["dt"], G, GV, US, CS, Reg,
+                       x_first_in=(None if a.get("x_first_in") is None else bool(a["x_first_in"])),
+                       max_iter_in=a.get("max_iter_in"), vol_prev=fa.get("vol_prev"),
+                       update_vol_prev=(bool(a["update_vol_prev"]) if a.get("update_vol_prev") is not None else None),
+                       uhr_out=fa.get("uhr_out"), vhr_out=fa.get("vhr_out"))
+    _back(fa, a, ("vol_prev", "uhr_out", "vhr_out"))
+    for ft, t in zip(fts, a["tr"]):
+        adapt.back(ft, t)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+STEP_FILES = ("src/core/MOM_dynamics_split_RK2.F90", "src/core/MOM_continuity_PPM.F90", "src/core/MOM_continuity.F90",
+              "src/core/MOM_CoriolisAdv.F90", "src/core/MOM_PressureForce.F90", "src/parameterizations/lateral/MOM_hor_visc.F90",
+              "src/parameterizations/vertical/MOM_vert_friction.F90", "src/parameterizations/vertical/MOM_set_viscosity.F90",
+              "src/core/MOM_barotropic.F90", "src/core/MOM_forcing_type.F90", "src/core/MOM_interface_heights.F90") + PGF_FILES
+STEP_CS_ARRAYS = ("CAu", "CAv", "CAu_pred", "CAv_pred", "PFu", "PFv", "diffu", "diffv", "visc_rem_u", "visc_rem_v", "u_accel_bt",
+                  "v_accel_bt", "u_av", "v_av", "h_av", "pbce", "eta", "eta_PF", "uhbt", "vhbt", "taux_bot", "tauy_bot")
+STEP_STATE = ("u_inst", "v_inst", "h", "uh", "vh", "uhtr", "vhtr", "eta_av")
+
+
+def step_dyn_split_rk2(dom, grid, gv, css, cs, a, land_blocks=0):
+    """step_MOM_dyn_split_RK2, src/core/MOM_dynamics_split_RK2.F90:294-1205, calling the reference's own continuity, CorAdCalc,
+    PressureForce, horizontal_viscosity, vertvisc*, btcalc, bt_mass_source, set_dtbt and btstep"""
+    R = ref(*STEP_FILES)
+    F = R["mom_dynamics_split_rk2"]
+    G, GV, US = _types(dom, grid, gv)
+    nk = int(dom.nk)
+    pf = css["pressureforce"]
+    G.z_ref = float(pf.get("Z_ref", 0.0))
+    GV.dz_subroundoff = float(pf.get("dZ_subroundoff", 1.0e-30))
+    GV.nk_rho_varies, GV.nkml = 0, int(css["vertvisc"].get("nkml", 0))
+    if pf.get("Rlay") is not None:
+        GV.rlay = FArray.from_numpy(np.asarray(pf["Rlay"], dtype=np.float64), (1,))
+        GV.g_prime = FArray.from_numpy(np.asarray(pf["g_prime"], dtype=np.float64), (1,))
+    # ---- the stage control structures
+    cont = _set(new(R, "mom_continuity_ppm", "continuity_ppm_cs", initialized=True), css["continuity"], CONT_LOGICAL)
+    cor = _set(new(R, "mom_coriolisadv", "coriolisadv_cs", initialized=True), css["coriolisadv"],
+               ("no_slip", "bound_Coriolis", "Coriolis_En_Dis"))
+    hv = _set(new(R, "mom_hor_visc", "hor_visc_cs", initialized=True), css["hor_visc"], HV_LOGICAL)
+    for k, v in css["hor_visc"].items():
+        if isinstance(v, np.ndarray):
+            setattr(hv, k.lower(), adapt.farr(dom, v))
+    hv.answer_date = 99991231
+    for k in ("anisotropic", "leith_kh", "leith_ah", "use_leithy", "modified_leith", "use_qg_leith_visc", "use_beta_in_leith",
+              "use_gme", "use_zb2020", "smooth_ah", "debug", "res_scale_meke", "frictwork_bug", "ey24_ebt_bs"):
+        setattr(hv, k, False)
+    pfv = new(R, "mom_pressureforce_fv", "pressureforce_fv_cs", initialized=True)
+    pfv.masswghtinterp = int(pf["MassWghtInterp"])
+    pfv.use_ssh_in_z0p, pfv.rho_ref_bug = bool(pf["use_SSH_in_Z0p"]), bool(pf["rho_ref_bug"])
+    pfv.rho_ref, pfv.gfs_scale, pfv.rho0 = float(pf["rho_ref"]), float(pf["GFS_scale"]), float(gv["Rho0"])
+    pfv.reconstruct = bool(pf.get("reconstruct", 0))
+    pfv.recon_scheme = int(pf.get("Recon_Scheme", 0)) or 1
+    pfv.boundary_extrap = bool(pf.get("boundary_extrap", 0))
+    pfv.use_inaccurate_pgf_rho_anom = bool(pf.get("use_inaccurate_pgf_rho_anom", 0))
+    pfv.masswghtinterpvanonly = bool(pf.get("MassWghtInterpVanOnly", 0))
+    pfv.h_nonvanished = float(pf.get("h_nonvanished", 0.0))
+    for k in ("calculate_sal", "tides", "sal_use_bpa", "bq_sal_tides", "use_stanley_pgf", "reset_intxpa_integral", "debug",
+              "correction_intxpa", "reset_intxpa_flattest"):
+        setattr(pfv, k, False)
+    pgf = NS(analytic_fv_pgf=True, pressureforce_fv=pfv)
+    E = eos_type(R, pf)
+    ALE = None
+    if pfv.reconstruct and E is not None:
+        ALE = new(R, "mom_ale", "ale_cs")
+        ALE.answer_date = int(pf.get("ALE_answer_date", 0)) or 99991231
+        ALE.nk = nk
+    vv = _set(new(R, "mom_vert_friction", "vertvisc_cs", initialized=True), css["vertvisc"], VV_LOGICAL)
+    lbu, lbv = adapt.stagger_lb(dom, "u"), adapt.stagger_lb(dom, "v")
+    shu, shv = a["u_inst"].shape, a["v_inst"].shape
+    vv.a_u = FArray.from_numpy(np.zeros((nk + 1,) + shu[1:]), lbu + (1,))
+    vv.a_v = FArray.from_numpy(np.zeros((nk + 1,) + shv[1:]), lbv + (1,))
+    vv.h_u, vv.h_v = FArray.from_numpy(np.zeros(shu), lbu + (1,)), FArray.from_numpy(np.zeros(shv), lbv + (1,))
+    for k in ("debug", "use_gl90_in_ssw", "stokesmixing"):
+        setattr(vv, k, False)
+    vv.pass_ke_uv = NS()
+    vv.maxvel, vv.cfl_based_trunc, vv.cfl_trunc, vv.cfl_report, vv.truncramptime = 3.0e8, True, 0.5, 0.5, 0.0
+    vv.u_trunc_file, vv.v_trunc_file, vv.ntrunc = "", "", 0
+    GV.dz_subroundoff = float(css["vertvisc"].get("dZ_subroundoff", GV.dz_subroundoff))
+    bt = barotropic_cs(R, dom, grid, gv, cs["barotropic"], wide_metrics(dom, land_blocks))
+    bt.hvel_scheme = int(cs.get("hvel_scheme", 4))
+    bt.dtbt_fraction = float(cs.get("dtbt_fraction", 0.98))
+    bt.bt_coriolis_scale = float(cs.get("BT_Coriolis_scale", 1.0))
+    bt.nonlinear_continuity = bool(cs.get("BT_Nonlinear_continuity", 0))
+    bt.dtbt_max = float(cs.get("dtbt_max", 0.0))
+    setv = new(R, "mom_set_visc", "set_visc_cs", initialized=True)
+    setv.dynamic_viscous_ml = bool(css["vertvisc"].get("dynamic_viscous_ML", 0))
+    # ---- MOM_dyn_split_RK2_CS
+    CS = new(R, "mom_dynamics_split_rk2", "mom_dyn_split_rk2_cs", module_is_initialized=True)
+    fcs = {k: adapt.farr(dom, cs[k]) for k in STEP_CS_ARRAYS}
+    for k, v in fcs.items():
+        setattr(CS, k.lower(), v)
+    BT = bt_cont_type(dom, cs["BT_cont"])
+    CS.bt_cont = BT
+    CS.be, CS.begw = float(cs["be"]), float(cs["begw"])
+    CS.split_bottom_stress, CS.store_cau = bool(cs["split_bottom_stress"]), bool(cs["store_CAu"])
+    CS.cau_pred_stored, CS.visc_rem_dt_bug = bool(cs["CAu_pred_stored"]), bool(cs["visc_rem_dt_bug"])
+    CS.dtbt_use_bt_cont = bool(cs.get("dtbt_use_bt_cont", 0))
+    CS.bt_use_layer_fluxes = True
+    for k in ("debug", "debug_obc", "fpmix", "calculate_sal", "use_tides", "remap_aux"):
+        setattr(CS, k, False)
+    CS.continuity_csp, CS.coriolisadv, CS.hor_visc, CS.pressureforce_csp = cont, cor, hv, pgf
+    CS.vertvisc_csp, CS.barotropic_csp, CS.set_visc_csp, CS.ale_csp = vv, bt, setv, ALE
+    CS.adp, CS.cdp, CS.ad_pred = NS(), NS(), NS()
+    for k in ("pass_eta", "pass_visc_rem", "pass_uvp", "pass_hp_uv", "pass_uv", "pass_h", "pass_av_uvh"):
+        setattr(CS, k, NS())
+    # ---- arguments
+    fa = {k: adapt.farr(dom, a[k]) for k in STEP_STATE}
+    f2 = lambda k: adapt.farr(dom, a.get(k))  # noqa: E731
+    tv = NS(eqn_of_state=E, t=f2("T"), s=f2("S"), p_ref=0.0, vart=None, spv_avg=None, valid_spv_halo=-1)
+    visc = NS(kv_bbl_u=f2("Kv_bbl_u"), kv_bbl_v=f2("Kv_bbl_v"), bbl_thick_u=f2("bbl_thick_u"), bbl_thick_v=f2("bbl_thick_v"),
+              kv_shear=_interfaces(dom, a.get("Kv_shear"), "h"), kv_shear_bu=_interfaces(dom, a.get("Kv_shear_Bu"), "q"),
+              ray_u=f2("Ray_u"), ray_v=f2("Ray_v"))
+    forces = NS(taux=f2("taux"), tauy=f2("tauy"), ustar=f2("ustar"), tau_mag=None, p_surf=f2("p_surf"))
+    pbv = NS(por_face_areau=adapt.farr(dom, np.ones(shu)), por_face_areav=adapt.farr(dom, np.ones(shv)))
+    VarMix = NS(use_variable_mixing=False, resoln_scaled_kh=False, resoln_scaled_khth=False)
+    F["step_mom_dyn_split_rk2"](fa["u_inst"], fa["v_inst"], fa["h"], tv, visc, 0.0, a["dt"], forces, forces.p_surf, forces.p_surf,
+                                fa["uh"], fa["vh"], fa["uhtr"], fa["vhtr"], fa["eta_av"], G, GV, US, CS, bool(a.get("calc_dtbt", 0)),
+                                VarMix, NS(), None, pbv)
+    _back(fa, a, STEP_STATE)
+    for k, v in fcs.items():
+        adapt.back(v, cs[k])
+    for k, v in cs["BT_cont"].items():
+        if v is not None:
+            adapt.back(getattr(BT, k.lower()), v)
+    for k in ("ubtav", "vbtav", "eta_cor", "frhatu", "frhatv"):
+        adapt.back(getattr(bt, k), cs["barotropic"][k])
+    cs["CAu_pred_stored"] = int(bool(CS.cau_pred_stored))
+    cs["dtbt_max"] = float(bt.dtbt_max)
+    cs["barotropic"]["dtbt"] = float(bt.dtbt)

@@ -51,4 +51,7 @@ NAMES = {
     "max_across_pes": _noop, "min_across_pes": _noop, "sum_across_pes": _noop,
     "time_type_to_real": lambda t: float(t), "real_to_time": lambda x: x,
     "ns": rt.NS,
+    "diag_update_remap_grids": _noop, "safe_alloc_ptr": _noop, "safe_alloc_alloc": _noop, "query_debugging_checks": _noop,
+    "diag_save_grids": _noop, "diag_restore_grids": _noop, "diag_copy_diag_to_storage": _noop,
+    "time_type": rt.NS, "get_diag_time_end": lambda *a, **k: 0.0,
 }

@@ -38,7 +38,10 @@ def collect(dom, outputs, a, cs):
         src, k = (cs, key[3:]) if key.startswith("CS%") else (a, key)
         if "." in k:
             d, m = k.split(".")
-            v = src[d][m] if src.get(d) is not None else None
+            if isinstance(src.get(d), list):
+                v = src[d][int(m)] if int(m) < len(src[d]) else None
+            else:
+                v = src[d][m] if src.get(d) is not None else None
         else:
             v = src.get(k)
         if v is not None:
@@ -128,6 +131,48 @@ for _n, _kw in enumerate([
     case(f"pressure_force/options{_n:02d}", "pressure_force", (14, 10, 5), PF_OUT, land_blocks=2, **_kw)
 
 
+# ---- advect_tracer -------------------------------------------------------------------------------------------------------
+AD_OUT = ("tr.0", "tr.1", "tr.2", "uhr_out", "vhr_out", "vol_prev")
+case("advect_tracer/plm", "advect_tracer", (14, 10, 4), AD_OUT)
+case("advect_tracer/ppm_h3_cfl2.5_three_tracers", "advect_tracer", (14, 10, 4), AD_OUT, scheme=1, cfl=2.5, ntr=3)
+case("advect_tracer/ppm_land", "advect_tracer", (14, 10, 4), AD_OUT, scheme=2, land_blocks=2)
+case("advect_tracer/ppm_h3_periodic_y_y_first", "advect_tracer", (14, 10, 4), AD_OUT, scheme=1, land_blocks=2, cyclic_y=True,
+     cyclic_x=False, x_first_in=0)
+case("advect_tracer/plm_cfl3.5_drained_cells", "advect_tracer", (14, 10, 4), AD_OUT, scheme=0, cfl=3.5, land_blocks=1)
+case("advect_tracer/mixed_schemes_underflow_max_iter", "advect_tracer", (14, 10, 4), AD_OUT, ntr=3, cfl=3.2, land_blocks=1,
+     advect_scheme=[2, -1, 1], conc_underflow=[0.0, 0.0, 0.6], max_iter_in=2)
+
+
+# ---- step_MOM_dyn_split_RK2: the whole step, every stage from the reference's own source ----------------------------------
+STEP_OUT = ("u_inst", "v_inst", "h", "uh", "vh", "uhtr", "vhtr", "eta_av") + tuple("CS%" + k for k in (
+    "CAu", "CAv", "CAu_pred", "CAv_pred", "PFu", "PFv", "diffu", "diffv", "visc_rem_u", "visc_rem_v", "u_accel_bt", "v_accel_bt",
+    "u_av", "v_av", "h_av", "pbce", "eta", "eta_PF", "uhbt", "vhbt", "taux_bot", "tauy_bot")) + tuple(
+    "BT%" + k for k in ("ubtav", "vbtav", "eta_cor", "frhatu", "frhatv")) + tuple("BT_cont%" + k for k in (
+        "FA_u_EE", "FA_u_E0", "FA_u_W0", "FA_u_WW", "uBT_WW", "uBT_EE", "FA_v_NN", "FA_v_N0", "FA_v_S0", "FA_v_SS", "vBT_SS",
+        "vBT_NN", "h_u", "h_v"))
+case("step/default", "step", (12, 10, 4), STEP_OUT, land_blocks=2)
+case("step/two_steps_store_CAu_set_dtbt", "step", (12, 10, 4), STEP_OUT, land_blocks=2, nsteps=2, store_CAu=1, calc_dtbt=1)
+case("step/plm_pressure_reconstruction", "step", (12, 10, 4), STEP_OUT, land_blocks=2, pgf=dict(reconstruct=1, Recon_Scheme=1))
+case("step/ppm_reconstruction_begw_split_bottom_stress", "step", (12, 10, 4), STEP_OUT, land_blocks=2, begw=0.25,
+     split_bottom_stress=1, pgf=dict(reconstruct=1, Recon_Scheme=2))
+case("step/project_velocity_no_land", "step", (12, 10, 4), STEP_OUT, land_blocks=0, BT_project_velocity=1)
+
+
+def step_collect(dom, cs, a):
+    src = dict(a)
+    for k, v in cs.items():
+        if isinstance(v, np.ndarray):
+            src["CS%" + k] = v
+    for k in ("ubtav", "vbtav", "eta_cor", "frhatu", "frhatv"):
+        src["BT%" + k] = cs["barotropic"][k]
+    for k, v in cs["BT_cont"].items():
+        if v is not None:
+            src["BT_cont%" + k] = v
+    out = {k: np.ascontiguousarray(inner(dom, src[k])) for k in STEP_OUT if src.get(k) is not None}
+    out["zero_ok:scalars"] = np.array([cs["barotropic"]["dtbt"], cs["dtbt_max"], float(cs["CAu_pred_stored"])])
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def _coefs(dom, nk):
     from mom6_b200 import fidx
@@ -166,11 +211,25 @@ def build(name):
         return synthetic.vertvisc_inputs(*shape, **kw)
     if st == "pressure_force":
         return synthetic.pressureforce_inputs(*shape, **kw)
+    if st == "advect_tracer":
+        return synthetic.advect_inputs(*shape, **kw)
+    if st == "step":
+        pgf, nsteps = kw.pop("pgf", None), kw.pop("nsteps", 1)
+        dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(*shape, **kw)
+        if pgf:
+            css["pressureforce"].update(pgf)
+        return dom, grid, gv, css, cs, a
     raise KeyError(st)
 
 
 def run_oracle(oracle, name, inputs):
     c = CASES[name]
+    if c["stage"] == "step":
+        dom, grid, gv, css, cs, a = inputs
+        cs, a = _copy(cs), _copy(a)
+        for _ in range(c["kw"].get("nsteps", 1)):
+            oracle.step_dyn_split_rk2(dom, grid, gv, css, cs, a)
+        return step_collect(dom, cs, a)
     if c["stage"] == "vertvisc_family":
         dom, grid, gv, cs, coef, sol = inputs
         return collect(dom, c["outputs"], vertvisc_family(oracle, dom, grid, gv, cs, coef, sol, True), {})
@@ -183,6 +242,12 @@ def run_oracle(oracle, name, inputs):
 def run_reference(name, inputs):
     from oracle.f90run import stages
     c = CASES[name]
+    if c["stage"] == "step":
+        dom, grid, gv, css, cs, a = inputs
+        cs, a = _copy(cs), _copy(a)
+        for _ in range(c["kw"].get("nsteps", 1)):
+            stages.step_dyn_split_rk2(dom, grid, gv, css, cs, a, land_blocks=c["kw"].get("land_blocks", 0))
+        return step_collect(dom, cs, a)
     if c["stage"] == "vertvisc_family":
         dom, grid, gv, cs, coef, sol = inputs
         return collect(dom, c["outputs"], vertvisc_family(stages, dom, grid, gv, cs, coef, sol, False), {})
