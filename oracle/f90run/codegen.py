@@ -606,8 +606,10 @@ class ProcGen:
                     pro.append(f"{n} = {self.coerce(v, parse_expr(v.init[1]))}")
                 elif v.pointer:
                     pro.append(f"{n} = None")
-                elif v.base == "integer" and v.dims is None:
-                    pro.append(f"{n} = 0")  # an undefined integer is read without harm in places (touch_ij(i,j))
+                elif v.dims is None and v.base in ("integer", "real", "logical", "character"):
+                    # undefined until assigned; given a value so that it can be passed to an intent(out) dummy argument
+                    # (a real starts as NaN, so a use before definition still shows in the results)
+                    pro.append(f"{n} = " + {"integer": "0", "real": "_rt.NAN", "logical": "False", "character": "''"}[v.base])
             except (SyntaxError, NotImplementedError, ValueError, IndexError) as err:
                 pro.append(f"{n} = None  # declaration not translated: {err}")
         self.lines = []

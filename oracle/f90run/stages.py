@@ -480,3 +480,94 @@ def step_dyn_split_rk2(dom, grid, gv, css, cs, a, land_blocks=0):
     cs["CAu_pred_stored"] = int(bool(CS.cau_pred_stored))
     cs["dtbt_max"] = float(bt.dtbt_max)
     cs["barotropic"]["dtbt"] = float(bt.dtbt)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+ALE_FILES = ("src/core/MOM.F90", "src/ALE/MOM_ALE.F90", "src/ALE/MOM_regridding.F90", "src/ALE/MOM_remapping.F90",
+             "src/ALE/coord_zlike.F90", "src/ALE/regrid_consts.F90", "src/ALE/regrid_interp.F90", "src/ALE/regrid_edge_values.F90",
+             "src/ALE/regrid_solvers.F90", "src/ALE/PCM_functions.F90", "src/ALE/PLM_functions.F90", "src/ALE/PPM_functions.F90",
+             "src/ALE/PQM_functions.F90", "src/ALE/P1M_functions.F90", "src/ALE/P3M_functions.F90", "src/ALE/polynomial_functions.F90",
+             "src/tracer/MOM_tracer_registry.F90", "src/tracer/MOM_tracer_types.F90", "src/parameterizations/vertical/MOM_set_viscosity.F90",
+             "src/core/MOM_dynamics_split_RK2.F90", "src/core/MOM_interface_heights.F90")
+REMAP_LOGICAL = ("boundary_extrapolation", "force_bounds_in_subcell", "force_bounds_in_target", "om4_remap_via_sub_cells")
+
+
+def remapping_cs(R, d):
+    """remapping_CS (src/ALE/MOM_remapping.F90:42-80) as initialize_remapping (:1640-1700) resolves it"""
+    C = _set(new(R, "mom_remapping", "remapping_cs"), d, REMAP_LOGICAL)
+    C.degree = {0: 0, 2: 1, 4: 2, 5: 2}[int(d["remapping_scheme"])]
+    return C
+
+
+def regridding_cs(R, d):
+    """regridding_CS (src/ALE/MOM_regridding.F90:47-130) for the Z* coordinate, as initialize_regridding (:200-800) and
+    set_regrid_params (:2380-2470) leave it; zlike_CS from init_coord_zlike (src/ALE/coord_zlike.F90:37-50)"""
+    C = new(R, "mom_regridding", "regridding_cs")
+    nk = int(d["nk"])
+    C.nk, C.regridding_scheme = nk, int(d["regridding_scheme"])
+    C.min_thickness = float(d["min_thickness"])
+    C.old_grid_weight = float(d["old_grid_weight"])
+    C.depth_of_time_filter_shallow = float(d["depth_of_time_filter_shallow"])
+    C.depth_of_time_filter_deep = float(d["depth_of_time_filter_deep"])
+    res = np.asarray(d["coordinateResolution"], dtype=np.float64)
+    C.coordinateresolution = FArray.from_numpy(res.copy(), (1,))
+    Z = new(R, "coord_zlike", "zlike_cs")
+    Z.nk, Z.min_thickness = nk, C.min_thickness
+    Z.coordinateresolution = FArray.from_numpy(res.copy(), (1,))
+    C.zlike_cs = Z
+    return C
+
+
+def ale_regridding_and_remapping(dom, grid, gv, ale, a, dyn_cs=None):
+    """ALE_regridding_and_remapping, src/core/MOM.F90:1751-1926, and everything it calls in MOM_ALE / MOM_regridding /
+    MOM_remapping / coord_zlike, remap_dyn_split_RK2_aux_vars (MOM_dynamics_split_RK2.F90:1211-1240) and
+    remap_vertvisc_aux_vars (MOM_set_viscosity.F90:2849-2873)"""
+    R = ref(*ALE_FILES)
+    F = R["mom"]
+    G, GV, US = _types(dom, grid, gv)
+    G.z_ref = float(ale["regridCS"].get("Z_ref", 0.0))
+    nk = int(dom.nk)
+    A = new(R, "mom_ale", "ale_cs")
+    A.regridcs, A.remapcs, A.vel_remapcs = regridding_cs(R, ale["regridCS"]), remapping_cs(R, ale["remapCS"]), \
+        remapping_cs(R, ale["vel_remapCS"])
+    A.regrid_time_scale = float(ale["regrid_time_scale"])
+    A.nk, A.answer_date = nk, 99991231
+    A.bbl_h_vel_mask, A.h_vel_mask = 0.0, 0.0
+    for k in ("remap_uv_using_old_alg", "partial_cell_vel_remap", "use_hybgen_unmix", "do_conv_adj", "conserve_ke", "debug",
+              "show_call_tree", "remap_after_initialization"):
+        setattr(A, k, False)
+    ntr = len(a["tr"])
+    fts = [adapt.farr(dom, t) for t in a["tr"]]
+    Tr = FArray.alloc("o", [(1, ntr)])
+    cu = a.get("conc_underflow") if a.get("conc_underflow") is not None else [0.0] * ntr
+    for m, ft in enumerate(fts):
+        T = new(R, "mom_tracer_types", "tracer_type")
+        T.t, T.conc_underflow, T.remap_tr, T.ntr_index = ft, float(cu[m]), True, m + 1
+        Tr.v[m] = T
+    Reg = NS(ntr=ntr, tr=Tr)
+    A.do_tendency_diag = FArray.alloc("l", [(1, ntr)])
+    tv = NS(t=(fts[a["iT"]] if a.get("iT", -1) >= 0 else None), s=(fts[a["iS"]] if a.get("iS", -1) >= 0 else None),
+            spv_avg=None, valid_spv_halo=-1, eqn_of_state=None)
+    visc = NS(kd_shear=_interfaces(dom, a.get("Kd_shear"), "h"), kv_shear=_interfaces(dom, a.get("Kv_shear"), "h"),
+              kv_shear_bu=_interfaces(dom, a.get("Kv_shear_Bu"), "q"))
+    D = None
+    fd = {}
+    if dyn_cs is not None:
+        D = NS(remap_aux=True, store_cau=bool(dyn_cs.get("store_CAu", 0)), cau_pred_stored=bool(dyn_cs.get("CAu_pred_stored", 0)))
+        for k in ("diffu", "diffv", "CAu_pred", "CAv_pred", "u_av", "v_av"):
+            fd[k] = adapt.farr(dom, dyn_cs[k])
+            setattr(D, k.lower(), fd[k])
+    CS = NS(ale_csp=A, debug=False, dyn_split_rk2_csp=D, split=True, use_alt_split=False, tracer_reg=Reg,
+            remap_aux_vars=bool(ale.get("remap_aux_vars", 0)) and D is not None, remap_uv_using_old_alg=False, use_particles=False,
+            visc=visc, obc=None, tv=tv, use_ale_algorithm=True, frac_shelf_h=None, diag=None)
+    fu, fv, fh = adapt.farr(dom, a["u"]), adapt.farr(dom, a["v"]), adapt.farr(dom, a["h"])
+    F["ale_regridding_and_remapping"](CS, G, GV, US, fu, fv, fh, tv, float(a["dtdia"]), 0.0)
+    adapt.back(fu, a["u"]); adapt.back(fv, a["v"]); adapt.back(fh, a["h"])
+    for ft, t in zip(fts, a["tr"]):
+        adapt.back(ft, t)
+    for k in ("Kd_shear", "Kv_shear", "Kv_shear_Bu"):
+        if a.get(k) is not None:
+            adapt.back(getattr(visc, k.lower()), a[k])
+    for k, v in fd.items():
+        adapt.back(v, dyn_cs[k])
+    ale["regridCS"]["old_grid_weight"] = float(A.regridcs.old_grid_weight)

@@ -158,6 +158,24 @@ case("step/ppm_reconstruction_begw_split_bottom_stress", "step", (12, 10, 4), ST
 case("step/project_velocity_no_land", "step", (12, 10, 4), STEP_OUT, land_blocks=0, BT_project_velocity=1)
 
 
+# ---- ALE_regridding_and_remapping (MOM.F90:1751) --------------------------------------------------------------------------
+ALE_OUT = ("u", "v", "h", "tr.0", "tr.1", "tr.2", "Kd_shear", "Kv_shear", "Kv_shear_Bu", "DYN%diffu", "DYN%diffv", "DYN%CAu_pred",
+           "DYN%CAv_pred", "DYN%u_av", "DYN%v_av")
+case("ale/ppm_h4_aux_vars", "ale", (12, 10, 5), ALE_OUT, land_blocks=2)
+case("ale/plm_no_store_CAu", "ale", (12, 10, 5), ALE_OUT, land_blocks=2, remapping_scheme=2, store_CAu=0)
+case("ale/ppm_ih4_no_time_filter", "ale", (12, 10, 6), ALE_OUT, land_blocks=1, remapping_scheme=5, regrid_time_scale=0.0, with_Bu=False)
+case("ale/pcm_no_aux_vars", "ale", (12, 10, 5), ALE_OUT, land_blocks=2, remapping_scheme=0, remap_aux_vars=0)
+
+
+def ale_collect(dom, ale, dcs, a):
+    src = dict(a)
+    for k in ("diffu", "diffv", "CAu_pred", "CAv_pred", "u_av", "v_av"):
+        src["DYN%" + k] = dcs[k]
+    out = collect(dom, ALE_OUT, src, {})
+    out["zero_ok:old_grid_weight"] = np.array([ale["regridCS"]["old_grid_weight"]])
+    return out
+
+
 def step_collect(dom, cs, a):
     src = dict(a)
     for k, v in cs.items():
@@ -213,6 +231,8 @@ def build(name):
         return synthetic.pressureforce_inputs(*shape, **kw)
     if st == "advect_tracer":
         return synthetic.advect_inputs(*shape, **kw)
+    if st == "ale":
+        return synthetic.ale_chain_inputs(*shape, **kw)
     if st == "step":
         pgf, nsteps = kw.pop("pgf", None), kw.pop("nsteps", 1)
         dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(*shape, **kw)
@@ -224,6 +244,11 @@ def build(name):
 
 def run_oracle(oracle, name, inputs):
     c = CASES[name]
+    if c["stage"] == "ale":
+        dom, grid, gv, ale, dcs, a = inputs
+        ale, dcs, a = _copy(ale), _copy(dcs), _copy(a)
+        oracle.ale_regridding_and_remapping(dom, grid, gv, ale, a, dyn_cs=dcs)
+        return ale_collect(dom, ale, dcs, a)
     if c["stage"] == "step":
         dom, grid, gv, css, cs, a = inputs
         cs, a = _copy(cs), _copy(a)
@@ -242,6 +267,11 @@ def run_oracle(oracle, name, inputs):
 def run_reference(name, inputs):
     from oracle.f90run import stages
     c = CASES[name]
+    if c["stage"] == "ale":
+        dom, grid, gv, ale, dcs, a = inputs
+        ale, dcs, a = _copy(ale), _copy(dcs), _copy(a)
+        stages.ale_regridding_and_remapping(dom, grid, gv, ale, a, dyn_cs=dcs)
+        return ale_collect(dom, ale, dcs, a)
     if c["stage"] == "step":
         dom, grid, gv, css, cs, a = inputs
         cs, a = _copy(cs), _copy(a)
