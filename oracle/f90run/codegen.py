@@ -464,7 +464,7 @@ class ProcGen:
         if st == "continue" or st == "__internal_procedures_skipped__":
             self.emit(ind, "pass", ln)
             return
-        if re.match(r"(write|print|read|open|close|format|flush|rewind)\b\s*[(*]", st):
+        if re.match(r"(write|read|open|close|format|flush|rewind)\b\s*[(*]", st) or re.match(r"print\b\s*['\"(*]", st):
             m = re.match(r"write\s*\(\s*([a-z_]\w*)\s*,", st)
             v = self.var(m.group(1)) if m else None
             if v is not None and v.base == "character":  # internal write into a message string: its text is not reproduced

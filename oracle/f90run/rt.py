@@ -301,7 +301,8 @@ def rebase(x, lbs, extents=None, what=""):
     y = x.rebase(lbs)
     if extents is not None and len(y.shape) == len(extents):
         for d, n in enumerate(extents):
-            if n is not None and y.shape[d] != n and _prod(y.shape) != 0:
+            # an explicit-shape dummy may be associated with a longer actual (sequence association) in its last dimension
+            if n is not None and _prod(y.shape) != 0 and (y.shape[d] < n or (y.shape[d] != n and d != len(extents) - 1)):
                 raise TypeError(f"{what}: dimension {d + 1} of the actual argument has extent {y.shape[d]}, the dummy declares {n}")
     return y
 

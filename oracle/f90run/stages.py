@@ -571,3 +571,118 @@ def ale_regridding_and_remapping(dom, grid, gv, ale, a, dyn_cs=None):
     for k, v in fd.items():
         adapt.back(v, dyn_cs[k])
     ale["regridCS"]["old_grid_weight"] = float(A.regridcs.old_grid_weight)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+TD_FILES = ("src/parameterizations/lateral/MOM_thickness_diffuse.F90", "src/core/MOM_isopycnal_slopes.F90",
+            "src/core/MOM_interface_heights.F90") + EOS_FILES
+
+
+def thickness_diffuse(dom, grid, gv, cs, a):
+    """thickness_diffuse, src/parameterizations/lateral/MOM_thickness_diffuse.F90:134-630, thickness_diffuse_full :635-1530,
+    streamfn_solver :1535-1570, vert_fill_TS (MOM_isopycnal_slopes.F90:560-640) and the EOS derivative routines"""
+    R = ref(*TD_FILES)
+    F = R["mom_thickness_diffuse"]
+    G, GV, US = _types(dom, grid, gv)
+    G.obcmaskcu, G.obcmaskcv = G.mask2dcu, G.mask2dcv   # no open boundaries: MOM_grid.F90 sets OBCmaskCu = mask2dCu
+    GV.dz_subroundoff = float(cs["dZ_subroundoff"])
+    GV.nkml, GV.semi_boussinesq = 0, False
+    CS = new(R, "mom_thickness_diffuse", "thickness_diffuse_cs", initialized=True)
+    for k in ("Khth", "Khth_Min", "Khth_Max", "max_Khth_CFL", "slope_max", "kappa_smooth", "FGNV_scale", "N2_floor"):
+        setattr(CS, k.lower(), float(cs[k]))
+    for k in ("thickness_diffuse", "read_khth", "detangle_interfaces", "use_FGNV_streamfn", "use_stanley_gm",
+              "use_GME_thickness_diffuse"):
+        setattr(CS, k.lower(), bool(cs[k]))
+    CS.kh_eta_bg, CS.kh_eta_vel, CS.khth_slope_cff = 0.0, 0.0, 0.0
+    for k in ("debug", "meke_geometric", "use_kh_in_meke", "gm_src_alt", "full_depth_khth_min", "use_gm_work_bug", "meke_src_slope_bug"):
+        setattr(CS, k, False)
+    CS.meke_src_answer_date, CS.meke_geom_answer_date = 99991231, 99991231
+    f2 = lambda k: adapt.farr(dom, a.get(k))  # noqa: E731
+    V = NS(use_variable_mixing=bool(cs["use_variable_mixing"]), resoln_scaled_khth=bool(cs["Resoln_scaled_KhTh"]),
+           depth_scaled_khth=bool(cs["Depth_scaled_KhTh"]), use_stored_slopes=bool(cs["use_stored_slopes"]),
+           use_visbeck=bool(cs["use_Visbeck"]), use_qg_leith_gm=bool(cs["use_QG_Leith_GM"]), khth_struct=None,
+           res_fn_u=f2("Res_fn_u"), res_fn_v=f2("Res_fn_v"), slope_x=_interfaces(dom, a.get("slope_x"), "u"),
+           slope_y=_interfaces(dom, a.get("slope_y"), "v"), cg1=f2("cg1"))
+    M = NS(kh=(f2("MEKE_Kh") if cs["use_MEKE_Kh"] else None), khth_fac=float(cs["MEKE_KhTh_fac"]), gm_src=None, meke=None)
+    fa = {k: adapt.farr(dom, a[k]) for k in ("h", "uhtr", "vhtr")}
+    tv = NS(eqn_of_state=eos_type(R, cs), t=f2("T"), s=f2("S"), p_surf=f2("p_surf"), spv_avg=None, vart=None)
+    CDp = NS(uhgm=f2("uhGM"), vhgm=f2("vhGM"))
+    F["thickness_diffuse"](fa["h"], fa["uhtr"], fa["vhtr"], tv, float(a["dt"]), G, GV, US, M, V, CDp, CS, NS())
+    _back(fa, a, ("h", "uhtr", "vhtr"))
+    for k, m in (("uhGM", CDp.uhgm), ("vhGM", CDp.vhgm)):
+        if a.get(k) is not None:
+            adapt.back(m, a[k])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+MLE_FILES = ("src/parameterizations/lateral/MOM_mixed_layer_restrat.F90", "src/core/MOM_forcing_type.F90",
+             "src/core/MOM_interface_heights.F90") + EOS_FILES
+
+
+def mixedlayer_restrat(dom, grid, gv, cs, a):
+    """mixedlayer_restrat, src/parameterizations/lateral/MOM_mixed_layer_restrat.F90:149-186 -> mixedlayer_restrat_OM4 :189-714
+    (with mu :1545-1575 and rmean2ts :1100-1130)"""
+    R = ref(*MLE_FILES)
+    F = R["mom_mixed_layer_restrat"]
+    G, GV, US = _types(dom, grid, gv)
+    G.obcmaskcu, G.obcmaskcv = G.mask2dcu, G.mask2dcv
+    GV.nkml, GV.semi_boussinesq = 0, False
+    CS = new(R, "mom_mixed_layer_restrat", "mixedlayer_restrat_cs", initialized=True)
+    for k in ("ml_restrat_coef", "ml_restrat_coef2", "front_length", "MLE_MLD_decay_time", "MLE_MLD_decay_time2", "MLE_MLD_stretch",
+              "MLE_tail_dh", "ustar_min", "vonKar", "MLE_density_diff"):
+        setattr(CS, k.lower(), float(cs[k]))
+    for k in ("MLE_use_PBL_MLD", "use_Stanley_ML", "use_Bodner", "fl_from_file"):
+        setattr(CS, k.lower(), bool(cs[k]))
+    CS.debug = False
+    fml, fmls = adapt.farr(dom, cs["MLD_filtered"]), adapt.farr(dom, cs["MLD_filtered_slow"])
+    CS.mld_filtered, CS.mld_filtered_slow = fml, fmls
+    f2 = lambda k: adapt.farr(dom, a.get(k))  # noqa: E731
+    fa = {k: adapt.farr(dom, a[k]) for k in ("h", "uhtr", "vhtr")}
+    tv = NS(eqn_of_state=eos_type(R, cs), t=f2("T"), s=f2("S"), vart=None, spv_avg=None)
+    forces = NS(ustar=f2("ustar"), tau_mag=None)
+    V = NS(rd_dx_h=f2("Rd_dx_h"))
+    F["mixedlayer_restrat"](fa["h"], fa["uhtr"], fa["vhtr"], tv, forces, float(a["dt"]), None, f2("h_MLD"), None, V, G, GV, US, CS)
+    _back(fa, a, ("h", "uhtr", "vhtr"))
+    adapt.back(fml, cs["MLD_filtered"]); adapt.back(fmls, cs["MLD_filtered_slow"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def tracer_hordiff(dom, grid, gv, cs, a):
+    """tracer_hordiff, src/tracer/MOM_tracer_hor_diff.F90:119-690 (the along-layer path: no neutral / boundary diffusion)"""
+    R = ref("src/tracer/MOM_tracer_hor_diff.F90", "src/tracer/MOM_tracer_types.F90")
+    F = R["mom_tracer_hor_diff"]
+    G, GV, US = _types(dom, grid, gv)
+    GV.nkml, GV.nk_rho_varies = 0, 0
+    CS = new(R, "mom_tracer_hor_diff", "tracer_hor_diff_cs")
+    for k in ("KhTr", "KhTr_min", "KhTr_max", "KhTr_passivity_coeff", "KhTr_passivity_min", "KhTr_Slope_Cff", "max_diff_CFL"):
+        setattr(CS, k.lower(), float(cs[k]))
+    for k in ("check_diffusive_CFL", "use_neutral_diffusion", "use_hor_bnd_diffusion", "Diffuse_ML_interior"):
+        setattr(CS, k.lower(), bool(cs[k]))
+    for k in ("debug", "show_call_tree", "first_call", "full_depth_khtr_min", "khtr_use_vert_struct", "recalc_neutral_surf"):
+        setattr(CS, k, False)
+    CS.ml_khtr_scale = 1.0
+    CS.pass_t = NS()
+    ntr = len(a["tr"])
+    fts = [adapt.farr(dom, t) for t in a["tr"]]
+    Tr = FArray.alloc("o", [(1, ntr)])
+    cu = a.get("conc_underflow") if a.get("conc_underflow") is not None else [0.0] * ntr
+    dfx = a.get("df_x") or [None] * ntr
+    dfy = a.get("df_y") or [None] * ntr
+    fdx, fdy = [adapt.farr(dom, x) for x in dfx], [adapt.farr(dom, x) for x in dfy]
+    for m, ft in enumerate(fts):
+        T = new(R, "mom_tracer_types", "tracer_type")
+        T.t, T.conc_underflow, T.df_x, T.df_y, T.name = ft, float(cu[m]), fdx[m], fdy[m], f"tr{m}"
+        Tr.v[m] = T
+    Reg = NS(ntr=ntr, tr=Tr)
+    f2 = lambda k: adapt.farr(dom, a.get(k))  # noqa: E731
+    V = NS(use_variable_mixing=bool(cs["use_variable_mixing"]), resoln_scaled_khtr=bool(cs["Resoln_scaled_KhTr"]),
+           res_fn_h=f2("Res_fn_h"), rd_dx_h=f2("Rd_dx_h"), l2u=f2("L2u"), l2v=f2("L2v"), sn_u=f2("SN_u"), sn_v=f2("SN_v"),
+           khtr_struct=None, ebt_struct=None)
+    M = NS(kh=(f2("MEKE_Kh") if cs["use_MEKE_Kh"] else None), khtr_fac=float(cs["MEKE_KhTr_fac"]))
+    F["tracer_hordiff"](adapt.farr(dom, a["h"]), float(a["dt"]), M, V, NS(), G, GV, US, CS, Reg, NS(t=None, s=None, p_surf=None))
+    for ft, t in zip(fts, a["tr"]):
+        adapt.back(ft, t)
+    for fl, ol in ((fdx, dfx), (fdy, dfy)):
+        for fx, ox in zip(fl, ol):
+            if ox is not None:
+                adapt.back(fx, ox)

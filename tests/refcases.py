@@ -40,6 +40,8 @@ def collect(dom, outputs, a, cs):
             d, m = k.split(".")
             if isinstance(src.get(d), list):
                 v = src[d][int(m)] if int(m) < len(src[d]) else None
+            elif src.get(d) is None:
+                v = None
             else:
                 v = src[d][m] if src.get(d) is not None else None
         else:
@@ -167,6 +169,29 @@ case("ale/ppm_ih4_no_time_filter", "ale", (12, 10, 6), ALE_OUT, land_blocks=1, r
 case("ale/pcm_no_aux_vars", "ale", (12, 10, 5), ALE_OUT, land_blocks=2, remapping_scheme=0, remap_aux_vars=0)
 
 
+# ---- the callers between dynamics steps -------------------------------------------------------------------
+TD_OUT = ("h", "uhtr", "vhtr", "uhGM", "vhGM")
+for _n, _kw in enumerate([
+        dict(land_blocks=2), dict(land_blocks=2, with_GM=True, with_p_surf=True, EOS_form=1),
+        dict(land_blocks=2, use_FGNV_streamfn=1, use_variable_mixing=1),
+        dict(land_blocks=1, use_variable_mixing=1, Resoln_scaled_KhTh=1, Khth_Max=900.0, Khth_Min=50.0),
+        dict(land_blocks=2, use_variable_mixing=1, use_stored_slopes=1), dict(land_blocks=2, use_MEKE_Kh=1, MEKE_KhTh_fac=0.5)]):
+    case(f"thickness_diffuse/options{_n:02d}", "thickness_diffuse", (14, 10, 5), TD_OUT, **_kw)
+MLE_OUT = ("h", "uhtr", "vhtr", "CS%MLD_filtered", "CS%MLD_filtered_slow")
+for _n, _kw in enumerate([
+        dict(land_blocks=2), dict(land_blocks=2, eos="LINEAR", ml_restrat_coef2=0.5, MLE_MLD_decay_time2=5.0e6),
+        dict(land_blocks=1, MLE_use_PBL_MLD=0, MLE_density_diff=0.03),
+        dict(land_blocks=1, MLE_tail_dh=0.2, MLE_MLD_stretch=1.5, cyclic_y=True)]):
+    case(f"mixedlayer_restrat/options{_n:02d}", "mixedlayer_restrat", (14, 10, 6), MLE_OUT, **_kw)
+HD_OUT = ("tr.0", "tr.1", "tr.2", "df_x.0", "df_x.2", "df_y.1", "df_y.2")
+for _n, _kw in enumerate([
+        dict(land_blocks=2), dict(land_blocks=2, with_df=True, max_diff_CFL=0.4, check_diffusive_CFL=1, KhTr=8000.0),
+        dict(land_blocks=1, use_variable_mixing=1, Resoln_scaled_KhTr=1, KhTr_Slope_Cff=0.25, KhTr_max=3000.0, KhTr_min=100.0),
+        dict(land_blocks=1, use_MEKE_Kh=1, MEKE_KhTr_fac=0.7, KhTr_passivity_coeff=3.0, cyclic_y=True),
+        dict(land_blocks=2, KhTr=5.0e4, check_diffusive_CFL=1), dict(KhTr=5.0e4, max_diff_CFL=2.5, ntr=1)]):
+    case(f"tracer_hordiff/options{_n:02d}", "tracer_hordiff", (14, 10, 5), HD_OUT, **_kw)
+
+
 def ale_collect(dom, ale, dcs, a):
     src = dict(a)
     for k in ("diffu", "diffv", "CAu_pred", "CAv_pred", "u_av", "v_av"):
@@ -233,6 +258,12 @@ def build(name):
         return synthetic.advect_inputs(*shape, **kw)
     if st == "ale":
         return synthetic.ale_chain_inputs(*shape, **kw)
+    if st == "thickness_diffuse":
+        return synthetic.thickness_diffuse_inputs(*shape, **kw)
+    if st == "mixedlayer_restrat":
+        return synthetic.mle_inputs(*shape, **kw)
+    if st == "tracer_hordiff":
+        return synthetic.hordiff_inputs(*shape, **kw)
     if st == "step":
         pgf, nsteps = kw.pop("pgf", None), kw.pop("nsteps", 1)
         dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(*shape, **kw)
@@ -260,7 +291,11 @@ def run_oracle(oracle, name, inputs):
         return collect(dom, c["outputs"], vertvisc_family(oracle, dom, grid, gv, cs, coef, sol, True), {})
     dom, grid, gv, cs, a = inputs
     cs, a = _copy(cs), _copy(a)
-    getattr(oracle, c["stage"])(dom, grid, gv, cs, a)
+    if c["stage"] == "mixedlayer_restrat":
+        oracle.mixedlayer_restrat(dom, grid, gv, cs, a["h"], a["uhtr"], a["vhtr"], a["T"], a["S"], a["ustar"], a["dt"], a["h_MLD"],
+                                  a["Rd_dx_h"])
+    else:
+        getattr(oracle, c["stage"])(dom, grid, gv, cs, a)
     return collect(dom, c["outputs"], a, cs)
 
 
