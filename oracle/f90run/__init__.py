@@ -56,7 +56,7 @@ def load(paths, extra_stubs=None, verbose=False):
     stub_ns = dict(stubs.NAMES)
     if extra_stubs:
         stub_ns.update(extra_stubs)
-    for full, mods in srcs + srcs:   # twice: alias-only modules (MOM_continuity) re-export what they import
+    for full, mods in srcs * 4:   # repeated: modules re-export what they import (MOM_continuity; testing via Recon1d_type)
         for m in mods:
             ns = spaces[m.name]
             uses = list(m.uses)
@@ -71,6 +71,7 @@ def load(paths, extra_stubs=None, verbose=False):
                     else:
                         names = list(only)
                     names += [("_new_" + t, "_new_" + t) for t in um.types]
+                    names += [("_new_" + l, "_new_" + r) for l, r in names if ("_new_" + rt.mangle(r)) in src]   # re-exported types
                     for local, remote in names:
                         key = rt.mangle(remote)
                         if key in src:

@@ -268,6 +268,9 @@ class ProcGen:
                 else:
                     self.emit(ind, f"{mangle(name)} = {self.coerce(v, R)}", ln)
                 return
+            if v is not None and v.base == "character" and v.dims is None:   # substring assignment: only used for labels
+                self.emit(ind, f"{mangle(name)} = {self.ex(R)}", ln)
+                return
             self.store(ind, mangle(name), args, R, ln)
             return
         obj = self.ref(parts[:-1])
@@ -320,6 +323,13 @@ class ProcGen:
             m = f"s{n}" if n <= 3 else "s_"
             self.emit(ind, f"{obj}.{mangle(cname)}.{m}(" + ", ".join(self.ex(a) for a in cargs) + f", {value})", ln)
 
+    def designator_or_array(self, ind, actual, value, ln):
+        """value is stored into a scalar designator; an array (or section) is filled in place by the callee"""
+        n0 = len(self.lines)
+        self.designator_store(ind, actual, value, ln)
+        if len(self.lines) == n0:
+            self.emit(ind, value, ln)
+
     def call(self, ind, text, ln):
         m = re.match(r"call\s+([a-z_][\w%]*)\s*(\(.*\))?\s*$", text, re.S)
         if not m:
@@ -348,6 +358,15 @@ class ProcGen:
                 actual = pos[k] if 0 <= k < len(pos) else kws.get(d)
                 if actual is not None:
                     self.designator_store(ind, actual, f"{r}[{n}]", ln)
+            return
+        if name == "random_number" and len(args) == 1:
+            self.designator_or_array(ind, args[0], f"_rt.random_number({self.ex(args[0])})", ln)
+            return
+        if name == "random_seed":
+            for a in args:
+                if a[0] == "kw" and a[1] == "size":
+                    self.designator_store(ind, a[2], "8", ln)
+            self.emit(ind, "_rt.random_seed()", ln)
             return
         f = self.prog.find_proc(self.mod, name)
         argtxt = ", ".join(self.ex(a) for a in args)
@@ -708,6 +727,15 @@ class Program:
                         pass
                 elif v.base in ("type", "class") and v.dims is None and not v.pointer and not v.allocatable:
                     out.append(f"    o.{mangle(cname)} = _rt.new_type(globals(), {v.tname!r})")
+                elif v.dims is not None and not v.pointer and not v.allocatable and v.base in ("real", "integer", "logical"):
+                    try:   # an explicit-shape array component with constant bounds
+                        _, _, full = pg.bounds(v.dims)
+                        if all(b is not None for b in full):
+                            out.append(f"    o.{mangle(cname)} = _rt.alloc({v.kind!r}, ({', '.join('(%s, %s)' % b for b in full)},))")
+                            if v.init is not None and v.init[0] == "val":
+                                out.append(f"    o.{mangle(cname)}.assign({pg.ex(parse_expr(v.init[1]))})")
+                    except (SyntaxError, NotImplementedError):
+                        pass
             out.append("    return o")
             out.append("")
         for g, specs in mod.generics.items():

@@ -9,6 +9,7 @@ import math
 
 NAN = float("nan")
 INF = float("inf")
+LENIENT_READS = False
 
 
 class FortranStop(Exception):
@@ -152,9 +153,16 @@ class FArray:
         if i < l or i >= l + self.shape[d]:
             raise IndexError(f"index {i} outside {l}:{l + self.shape[d] - 1} in dimension {d + 1}")
 
+    def _oob(self, d, i):
+        """an out-of-bounds READ: an error, unless LENIENT_READS is set (the reference's PPM_hybgen unit test reads u(n+1) and
+        discards it), in which case the undefined value is NaN"""
+        if LENIENT_READS:
+            return NAN
+        self._chk(d, i)
+
     def g1(self, i):
         l = self.lb[0]
-        if i < l or i >= l + self.shape[0]: self._chk(0, i)
+        if i < l or i >= l + self.shape[0]: return self._oob(0, i)
         return self.v[self.b + i * self.s[0]]
 
     def g2(self, i, j):
@@ -296,8 +304,33 @@ def alloc(kind, bounds, fill=None):
 def rebase(x, lbs, extents=None, what=""):
     if x is None:
         return None
+    if isinstance(x, (list, tuple)):   # an array constructor as the actual argument
+        flat = []
+        for e in x:
+            flat.extend(e.tolist() if type(e) is FArray else [e])
+        kind = "r" if any(type(e) is float for e in flat) else ("l" if flat and type(flat[0]) is bool else "i")
+        a = FArray.alloc(kind, [(1, len(flat))])
+        a.v[:] = [float(e) for e in flat] if kind == "r" else flat
+        x = a
     if not isinstance(x, FArray):
         raise TypeError(f"{what}: array dummy argument associated with a {type(x).__name__}")
+    if len(lbs) != len(x.shape) and extents is not None and _prod(x.shape) != 0:
+        # sequence association with a change of rank: the dummy's explicit shape is laid over the actual's elements in order
+        first = x.b + sum(l * st for l, st in zip(x.lb, x.s))
+        contiguous, acc = True, x.s[0]
+        for n, st in zip(x.shape, x.s):
+            contiguous = contiguous and st == acc
+            acc *= n
+        if not contiguous:
+            raise TypeError(f"{what}: rank-changing association with a non-contiguous actual argument")
+        total, shape = _prod(x.shape), []
+        for n in extents:
+            shape.append(n if n is not None else max(1, total // max(1, _prod(shape))))
+        st, acc = [], x.s[0]
+        for n in shape:
+            st.append(acc)
+            acc *= n
+        return FArray(x.v, first - sum(l * q for l, q in zip(lbs, st)), st, lbs, shape, x.kind)
     y = x.rebase(lbs)
     if extents is not None and len(y.shape) == len(extents):
         for d, n in enumerate(extents):
@@ -519,6 +552,8 @@ INTRINSICS = {
     "len": len, "epsilon": lambda x: 2.220446049250313e-16, "huge": lambda x: (1.7976931348623157e308 if type(x) is float else 2147483647),
     "tiny": lambda x: 2.2250738585072014e-308, "isnan": lambda x: x != x, "ieee_is_nan": lambda x: x != x,
     "count": lambda a: sum(1 for x in a.tolist() if x), "null": lambda: None,
+    "index": lambda s_, sub, back=False: (s_.rfind(sub) if back else s_.find(sub)) + 1, "scan": lambda s_, set_: next((n + 1 for n, c in enumerate(s_) if c in set_), 0),
+    "char": chr, "ichar": ord, "achar": chr, "iachar": ord, "repeat": lambda s_, n: s_ * n, "new_line": lambda c: "\n",
     "btest": lambda i, pos: bool((i >> pos) & 1), "ibset": lambda i, pos: i | (1 << pos), "ibclr": lambda i, pos: i & ~(1 << pos),
     "iand": lambda i, j: i & j, "ior": lambda i, j: i | j, "ishft": lambda i, s: (i << s) if s >= 0 else (i >> -s),
 }
@@ -627,3 +662,24 @@ def elemental(f, argnames, outs, is_function):
             return first._new(res, "r" if res and type(res[0]) is float else None)
         return tuple(args.get(o) for o in outs)
     return call
+
+
+_RNG = [12345]
+
+
+def random_seed():
+    _RNG[0] = 12345
+
+
+def _rand():
+    _RNG[0] = (_RNG[0] * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+    return (_RNG[0] >> 11) / float(1 << 53)
+
+
+def random_number(x):
+    """RANDOM_NUMBER: uniform numbers in [0,1) (the reference only uses them for self-consistency checks in its unit tests)"""
+    if type(x) is FArray:
+        for o in x._offsets():
+            x.v[o] = _rand()
+        return x
+    return _rand()

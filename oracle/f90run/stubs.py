@@ -54,4 +54,5 @@ NAMES = {
     "diag_update_remap_grids": _noop, "safe_alloc_ptr": _noop, "safe_alloc_alloc": _noop, "query_debugging_checks": _noop,
     "diag_save_grids": _noop, "diag_restore_grids": _noop, "diag_copy_diag_to_storage": _noop,
     "time_type": rt.NS, "get_diag_time_end": lambda *a, **k: 0.0,
+    "uppercase": lambda s_: s_.upper(), "lowercase": lambda s_: s_.lower(), "stdout": 6, "stderr": 0,
 }
