@@ -329,3 +329,74 @@ def run_case(oracle, name, want_ref=True):
     inputs = build(name)
     orc = run_oracle(oracle, name, inputs)
     return (run_reference(name, inputs) if want_ref else None), orc
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def _ctx(ctx_factory, dom, grid, gv):
+    ctx = ctx_factory(dom)
+    ctx.set_grid(grid)
+    ctx.set_vgrid(gv)
+    return ctx
+
+
+def run_device(ctx_factory, name, inputs):
+    """the same case through the C ABI on the GPU (tests/test_reference_golden.py)"""
+    c = CASES[name]
+    st = c["stage"]
+    if st == "step":
+        dom, grid, gv, css, cs, a = inputs
+        cs, a = _copy(cs), _copy(a)
+        ctx = _ctx(ctx_factory, dom, grid, gv)
+        ctx.set_cs_continuity(css["continuity"]); ctx.set_cs_coriolisadv(css["coriolisadv"]); ctx.set_cs_hor_visc(css["hor_visc"])
+        ctx.set_cs_pressureforce(css["pressureforce"]); ctx.set_cs_vertvisc(css["vertvisc"])
+        for _ in range(c["kw"].get("nsteps", 1)):
+            ctx.step_dyn_split_rk2(cs, a)
+        ctx.close()
+        return step_collect(dom, cs, a)
+    if st == "ale":
+        dom, grid, gv, ale, dcs, a = inputs
+        ale, dcs, a = _copy(ale), _copy(dcs), _copy(a)
+        ctx = _ctx(ctx_factory, dom, grid, gv)
+        ctx.ale_regridding_and_remapping(ale, a, dyn_cs=dcs)
+        ctx.close()
+        return ale_collect(dom, ale, dcs, a)
+    if st == "vertvisc_family":
+        dom, grid, gv, cs, coef, sol = inputs
+        nk = int(dom.nk)
+        ctx = _ctx(ctx_factory, dom, grid, gv)
+        ctx.set_cs_vertvisc(cs)
+        ctx.vertvisc_coef(_copy(coef))
+        g = _coefs(dom, nk)
+        ctx.vertvisc_get_coef(*g)
+        vru, vrv = np.zeros_like(sol["u"]), np.zeros_like(sol["v"])
+        ctx.vertvisc_remnant(vru, vrv, sol["dt"], sol["Ray_u"], sol["Ray_v"])
+        s = _copy(sol)
+        ctx.vertvisc(s)
+        ctx.close()
+        return collect(dom, c["outputs"], dict(a_u=g[0], a_v=g[1], h_u=g[2], h_v=g[3], visc_rem_u=vru, visc_rem_v=vrv, u=s["u"],
+                                               v=s["v"], taux_bot=s["taux_bot"], tauy_bot=s["tauy_bot"]), {})
+    dom, grid, gv, cs, a = inputs
+    cs, a = _copy(cs), _copy(a)
+    ctx = _ctx(ctx_factory, dom, grid, gv)
+    if st == "continuity":
+        ctx.set_cs_continuity(cs); ctx.continuity(a)
+    elif st == "coradcalc":
+        ctx.set_cs_coriolisadv(cs); ctx.coradcalc(a)
+    elif st == "horizontal_viscosity":
+        ctx.set_cs_hor_visc(cs); ctx.horizontal_viscosity(a)
+    elif st == "pressure_force":
+        ctx.set_cs_pressureforce(cs); ctx.pressure_force(a)
+    elif st == "btstep":
+        ctx.btstep(cs, a)
+    elif st == "advect_tracer":
+        ctx.advect_tracer(cs, a)
+    elif st == "thickness_diffuse":
+        ctx.thickness_diffuse(cs, a)
+    elif st == "mixedlayer_restrat":
+        ctx.mixedlayer_restrat(cs, a["h"], a["uhtr"], a["vhtr"], a["T"], a["S"], a["ustar"], a["dt"], a["h_MLD"], a["Rd_dx_h"])
+    elif st == "tracer_hordiff":
+        ctx.tracer_hordiff(cs, a)
+    else:
+        raise KeyError(st)
+    ctx.close()
+    return collect(dom, c["outputs"], a, cs)
