@@ -4,7 +4,8 @@
 // advection_xy) are not produced.  Single tile: do_group_pass is the periodic wrap of oracle_fill_halo_2d and
 // sum_across_PEs is the identity.  The loop structure (valid ranges that march inward between halo updates, the
 // domore_u / domore_v / domore_k flags, max_iter) is kept exactly, because it decides how many passes are made.
-// PARITY: UNPINNED -- the reference has no known-answer vectors for this routine.
+// PARITY: PINNED BY A REFERENCE RUN -- the reference's own MOM_tracer_advect.F90, executed by oracle/f90run, agrees bit for bit
+// (tests/test_reference_f90.py, advect_tracer/*).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <cfloat>

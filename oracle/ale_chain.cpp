@@ -5,7 +5,8 @@
 // of the order of operations of ALE_regridding_and_remapping (src/core/MOM.F90:1751-1926; no OBCs, ice shelves, particles,
 // diagnostics), which calls the routines restated in regrid.cpp / remap.cpp.
 // PARITY: interpolate_column is PINNED by the reference's unit-test vectors (MOM_remapping.F90:2648-2682), see
-// tests/test_ale_chain.py; the chain itself has no vector in the reference ("parity unpinned").
+// tests/test_ale_chain.py; the chain itself is PINNED BY A REFERENCE RUN: ALE_regridding_and_remapping of the reference's own MOM.F90,
+// executed by oracle/f90run, agrees bit for bit on 4 configurations (tests/test_reference_f90.py, ale/*).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <vector>

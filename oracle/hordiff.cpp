@@ -3,8 +3,8 @@
 // (:203-340), the diffusive-CFL iteration count (:354-372) and the along-surface diffusion loop (:537-604); the neutral /
 // boundary / epipycnal branches are outside the frozen option set.  Single tile: do_group_pass is the periodic wrap of
 // oracle_fill_halo_2d and max_across_PEs the identity.
-// PARITY: unpinned by any vector of the reference (no unit test exists for this routine); pinned by the reference's rotation test
-// re-expressed in tests/test_rotation.py and by the conservation / maximum-principle properties in tests/test_tracer_hordiff.py.
+// PARITY: PINNED BY A REFERENCE RUN -- the reference's own MOM_tracer_hor_diff.F90, executed by oracle/f90run, agrees bit for bit on 6
+// option sets (tests/test_reference_f90.py, tracer_hordiff/*); also the rotation test and the conservation / maximum-principle properties.
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <cfloat>

@@ -4,7 +4,8 @@
 // find_ustar_mech_forcing (src/core/MOM_forcing_type.F90:1236-1296, the forces%ustar / H_T_units branch :1270-1272);
 // density_elem of EOS_LINEAR (src/equation_of_state/MOM_EOS_linear.F90:60-68) and EOS_WRIGHT (MOM_EOS_Wright.F90:80-97).
 // PARITY: mu is PINNED by the reference's unit test (mixedlayer_restrat_unit_tests :2014-2041), see tests/test_mle.py;
-// the routine as a whole has no vector in the reference ("parity unpinned").
+// the routine as a whole is PINNED BY A REFERENCE RUN: the reference's own mixedlayer_restrat, executed by oracle/f90run, agrees bit for
+// bit on 4 option sets (tests/test_reference_f90.py, mixedlayer_restrat/*).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <cmath>

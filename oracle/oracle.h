@@ -9,8 +9,9 @@
  * loop-for-loop with identical parenthesisation and is compiled -O2 -ffp-contract=off.
  *   - ALE remapping: PINNED against the reference's known-answer vectors
  *     (src/ALE/MOM_remapping.F90:2072+), see tests/test_oracle_remap_kat.py.
- *   - everything else: "parity unpinned" by static vectors (the reference holds none);
- *     pinned only by the reference's own invariance properties re-expressed in tests/.
+ *   - the dycore stages, the whole step, tracer advection, the ALE pass and the three callers: PINNED BY A REFERENCE RUN --
+ *     oracle/f90run executes the reference's own Fortran source and tests/test_reference_f90.py compares bit for bit;
+ *   - write_energy as a whole and the checksums: no reference vector and no reference run ("parity unpinned").
  */
 #ifndef MOM6_ORACLE_H
 #define MOM6_ORACLE_H
@@ -80,15 +81,15 @@ int oracle_remap_dyn_split_rk2_aux_vars(const mom6cu_domain* dom, const mom6cu_g
                                         const mom6cu_dyn_split_rk2_cs* CS, const double* h_old_u, const double* h_old_v,
                                         const double* h_new_u, const double* h_new_v, int nthreads);
 
-/* advect_tracer (MOM_tracer_advect.F90:53-1152): see advect.cpp.  UNPINNED.  *iterations returns the number of passes made. */
+/* advect_tracer (MOM_tracer_advect.F90:53-1152): see advect.cpp.  Pinned by a reference run.  *iterations returns the number of passes made. */
 int oracle_advect_tracer(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_tracer_advect_cs* CS,
                          const mom6cu_advect_tracer_args* a, int* iterations);
 
-/* ALE_regrid, Z* (MOM_ALE.F90:518, MOM_regridding.F90:846-1857, coord_zlike.F90:63): see regrid.cpp.  UNPINNED. */
+/* ALE_regrid, Z* (MOM_ALE.F90:518, MOM_regridding.F90:846-1857, coord_zlike.F90:63): see regrid.cpp.  Pinned by a reference run. */
 int oracle_ale_regrid(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
                       const mom6cu_regridding_cs* CS, const double* h, double* h_new, double* dzRegrid);
 
-/* vertvisc_coef / vertvisc / vertvisc_remnant (MOM_vert_friction.F90:557-2924): see vertvisc.cpp.  UNPINNED.
+/* vertvisc_coef / vertvisc / vertvisc_remnant (MOM_vert_friction.F90:557-2924): see vertvisc.cpp.  Pinned by a reference run.
  * The CS%a_u, a_v (nk+1 levels), h_u, h_v arrays the reference keeps in vertvisc_CS are explicit arguments here. */
 int oracle_vertvisc_coef(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
                          const mom6cu_vertvisc_cs* CS, const mom6cu_vertvisc_coef_args* a, double* a_u, double* a_v, double* h_u, double* h_v);
@@ -98,7 +99,7 @@ int oracle_vertvisc_remnant(const mom6cu_domain* dom, const mom6cu_grid* G, cons
                             const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt, const double* a_u, const double* a_v,
                             const double* h_u, const double* h_v);
 
-/* step_MOM_dyn_split_RK2 (MOM_dynamics_split_RK2.F90:294-1205): see step.cpp.  UNPINNED. */
+/* step_MOM_dyn_split_RK2 (MOM_dynamics_split_RK2.F90:294-1205): see step.cpp.  Pinned by a reference run. */
 int oracle_step_dyn_split_rk2(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_unit_scale* US,
                               const mom6cu_continuity_cs* cont_cs, const mom6cu_coriolisadv_cs* corad_cs, const mom6cu_hor_visc_cs* hv_cs,
                               const mom6cu_pressureforce_cs* pgf_cs, const mom6cu_vertvisc_cs* vv_cs, mom6cu_dyn_split_rk2_cs* CS,

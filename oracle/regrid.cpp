@@ -3,7 +3,8 @@
 // MOM_regridding.F90:846-972 (Boussinesq branch :917-920, REGRIDDING_ZSTAR :925-927, negative-thickness check :962-969)
 // -> build_zstar_grid :1257-1367 -> build_zstar_column coord_zlike.F90:63-144 (no rigid top), filtered_grid_motion
 // MOM_regridding.F90:1105-1252, adjust_interface_motion :1796-1857; calc_h_new_by_dz :1008-1042.
-// PARITY: UNPINNED -- the reference has no known-answer vectors for the regridding.
+// PARITY: PINNED BY A REFERENCE RUN -- ALE_regrid as called by the reference's own ALE_regridding_and_remapping (MOM.F90), executed by
+// oracle/f90run, agrees bit for bit (tests/test_reference_f90.py, ale/*).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <cfloat>

@@ -4,7 +4,8 @@
 // set_viscous_ML a no-op; no diagnostics): the order of the stage calls, the elementwise glue (:425-430, :565-573,
 // :594-601, :681-691, :791-793, :800-804, :924-932, :961-975, :1021-1023, :1060-1072) and the group passes (single
 // tile: the periodic wrap of oracle_fill_halo_2d out to the full halo).  The stages are the oracle's own.
-// PARITY: UNPINNED (differential whole-model runs only).
+// PARITY: PINNED BY A REFERENCE RUN -- the reference's own step_MOM_dyn_split_RK2 with every stage it calls, executed by oracle/f90run,
+// agrees bit for bit on 5 configurations (tests/test_reference_f90.py, step/*).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <vector>

@@ -5,7 +5,8 @@
 // :1124-1176, the surface boundary condition :1532-1536; the v-direction twins :1236-1529); with find_eta_3d
 // (src/core/MOM_interface_heights.F90:48-112, Boussinesq), vert_fill_TS (src/core/MOM_isopycnal_slopes.F90:612-700),
 // thickness_to_dz (Boussinesq: dz = H_to_Z*h) and calculate_density_derivs of EOS_WRIGHT (MOM_EOS_Wright.F90:178-206) / EOS_LINEAR.
-// PARITY: unpinned by any vector of the reference; pinned by the rotation / rescaling invariance tests and by tests/test_thickness_diffuse.py.
+// PARITY: PINNED BY A REFERENCE RUN -- the reference's own MOM_thickness_diffuse.F90 (+ vert_fill_TS, the EOS derivative routines), executed
+// by oracle/f90run, agrees bit for bit on 6 option sets (tests/test_reference_f90.py, thickness_diffuse/*).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <cmath>

@@ -10,6 +10,12 @@ from mom6_b200 import synthetic
 CASES = {}
 
 
+DEVICE_REFUSES = {
+    # options the oracle restates (and the reference run confirms) but the CUDA path declines with MOM6CU_ERR_UNSUPPORTED
+    "mixedlayer_restrat/options03": "MLE_TAIL_DH /= 0",
+}
+
+
 def case(name, stage, shape, outputs, **kw):
     CASES[name] = dict(stage=stage, shape=shape, outputs=outputs, kw=kw)
 
