@@ -129,8 +129,9 @@ module mom6cu_interface
   !> vertvisc_CS (src/parameterizations/vertical/MOM_vert_friction.F90:48-170)
   type, bind(C) :: mom6cu_vertvisc_cs
     integer(c_int) :: bottomdraglaw, harmonic_visc, direct_stress, fixed_LOTW_ML, apply_LOTW_floor, dynamic_viscous_ML, &
-                      nkml, answer_date, unsupported
-    real(c_double) :: Hbbl, Kv, Kv_extra_bbl, Kvml_invZ2, Hmix, Hmix_stress, harm_BL_val, vonKar, vel_underflow, dZ_subroundoff
+                      nkml, answer_date, unsupported, CFL_based_trunc
+    real(c_double) :: Hbbl, Kv, Kv_extra_bbl, Kvml_invZ2, Hmix, Hmix_stress, harm_BL_val, vonKar, vel_underflow, dZ_subroundoff, &
+                      maxvel, CFL_trunc
   end type mom6cu_vertvisc_cs
   type, bind(C) :: mom6cu_vertvisc_coef_args
     type(c_ptr) :: u, v, h, Kv_bbl_u, Kv_bbl_v, bbl_thick_u, bbl_thick_v, Kv_shear, Kv_shear_Bu, ustar
@@ -640,6 +641,11 @@ module mom6cu_interface
       type(c_ptr), value :: h_u
       type(c_ptr), value :: h_v
     end function mom6cu_vertvisc_get_coef
+    integer(c_int) function mom6cu_vertvisc_ntrunc(ctx, ntrunc) bind(C, name="mom6cu_vertvisc_ntrunc")
+      import :: c_int, c_long_long, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_long_long), intent(out) :: ntrunc
+    end function mom6cu_vertvisc_ntrunc
     integer(c_long_long) function mom6cu_launch_count(ctx) bind(C, name="mom6cu_launch_count")
       import :: c_long_long, c_ptr
       type(c_ptr), value :: ctx

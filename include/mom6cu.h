@@ -322,10 +322,19 @@ int mom6cu_remapping_core_h(mom6cu_ctx* ctx, const mom6cu_remapping_cs* CS, int 
 typedef struct mom6cu_vertvisc_cs {
   int bottomdraglaw, harmonic_visc, direct_stress, fixed_LOTW_ML, apply_LOTW_floor, dynamic_viscous_ML, nkml, answer_date,
       unsupported;
+  int CFL_based_trunc; /* CFL_BASED_TRUNCATIONS (default True): see maxvel / CFL_trunc */
   double Hbbl, Kv, Kv_extra_bbl, Kvml_invZ2, Hmix, Hmix_stress, harm_BL_val, vonKar, vel_underflow;
   double dZ_subroundoff; /* GV%dZ_subroundoff */
+  /* vertvisc_limit_vel (MOM_vert_friction.F90:2926-3120), the last act of vertvisc: with CFL_based_trunc a velocity whose CFL number
+   * exceeds CFL_trunc (CFL_TRUNCATE, default 0.5) is set to the velocity of CFL 0.9*CFL_trunc; otherwise one above maxvel (MAXVEL,
+   * default 3e8 m/s) is set to 0.9*maxvel; |u| < vel_underflow is flushed to zero either way.  Truncations in columns thicker than
+   * 6 Angstrom are counted (CS%ntrunc: mom6cu_vertvisc_ntrunc).  CFL_trunc <= 0 and maxvel <= 0 switch the respective test off
+   * (a zero-filled structure limits nothing).  U_TRUNC_FILE / V_TRUNC_FILE reporting is the host's business. */
+  double maxvel, CFL_trunc;
 } mom6cu_vertvisc_cs;
 int mom6cu_set_cs_vertvisc(mom6cu_ctx* ctx, const mom6cu_vertvisc_cs* CS);
+/* CS%ntrunc: the number of velocity truncations vertvisc has made in this context so far (needs h in the vertvisc call) */
+int mom6cu_vertvisc_ntrunc(mom6cu_ctx* ctx, long long* ntrunc);
 /* vertvisc_coef(u, v, h, dz, forces, visc, tv, dt, G, GV, US, CS, OBC, VarMix)  MOM_vert_friction.F90:1357: sets the
  * resident CS%a_u, CS%a_v (nk+1 interfaces) and CS%h_u, CS%h_v (nk layers). */
 typedef struct mom6cu_vertvisc_coef_args {

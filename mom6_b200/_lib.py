@@ -216,9 +216,9 @@ class StepDynArgs(C.Structure):
 class VertviscCS(C.Structure):
     """mom6cu_vertvisc_cs: vertvisc_CS members (src/parameterizations/vertical/MOM_vert_friction.F90:48-170)."""
     _fields_ = [(n, C.c_int) for n in ("bottomdraglaw", "harmonic_visc", "direct_stress", "fixed_LOTW_ML", "apply_LOTW_floor",
-                                       "dynamic_viscous_ML", "nkml", "answer_date", "unsupported")] + \
+                                       "dynamic_viscous_ML", "nkml", "answer_date", "unsupported", "CFL_based_trunc")] + \
                [(n, C.c_double) for n in ("Hbbl", "Kv", "Kv_extra_bbl", "Kvml_invZ2", "Hmix", "Hmix_stress", "harm_BL_val", "vonKar",
-                                          "vel_underflow", "dZ_subroundoff")]
+                                          "vel_underflow", "dZ_subroundoff", "maxvel", "CFL_trunc")]
 
 
 class VertviscCoefArgs(C.Structure):
@@ -413,6 +413,7 @@ def bind(lib):
     lib.mom6cu_set_cs_vertvisc.argtypes = [vp, C.POINTER(VertviscCS)]
     lib.mom6cu_vertvisc_coef.argtypes = [vp, C.POINTER(VertviscCoefArgs)]
     lib.mom6cu_vertvisc_get_coef.argtypes = [vp, vp, vp, vp, vp]
+    lib.mom6cu_vertvisc_ntrunc.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.mom6cu_vertvisc.argtypes = [vp, C.POINTER(VertviscArgs)]
     lib.mom6cu_vertvisc_remnant.argtypes = [vp, vp, vp, vp, vp, C.c_double]
     lib.mom6cu_ale_regrid.argtypes = [vp, C.POINTER(RegriddingCS), vp, vp, vp]

@@ -253,6 +253,12 @@ def _ctx_methods():
     def vertvisc_get_coef(self, a_u=None, a_v=None, h_u=None, h_v=None):
         return self._check(self.lib.mom6cu_vertvisc_get_coef(self._h, _p(a_u), _p(a_v), _p(h_u), _p(h_v)))
 
+    def vertvisc_ntrunc(self):
+        """CS%ntrunc: velocity truncations made by vertvisc_limit_vel (MOM_vert_friction.F90:2926) in this context so far."""
+        n = C.c_longlong(0)
+        self._check(self.lib.mom6cu_vertvisc_ntrunc(self._h, C.byref(n)))
+        return int(n.value)
+
     def vertvisc(self, args):
         """vertvisc, MOM_vert_friction.F90:557."""
         keep = []

@@ -224,6 +224,11 @@ struct SolveK {
   const double *mask, *a, *hh, *Ray, *tau, *h;
   double* x;        // u / v (in/out) or the remnant (out)
   double* tau_bot;  // optional
+  // vertvisc_limit_vel :2926-3120 (lim_on: some test is active; applied on rows >= js_lim)
+  int lim_on, cfl_based, js_lim;
+  double vel_underflow, CFL_trunc, maxvel, H_report;
+  const double *face, *areaT, *IareaT;  // G%dy_Cu / dx_Cv; G%areaT, G%IareaT
+  unsigned long long* ntrunc;
 };
 
 template <int DIR, bool REM>
@@ -297,6 +302,28 @@ __global__ void __launch_bounds__(128) vv_solve_kernel(Geom G, SolveK P) {
     double t = P.H_to_RZ * (P.x[(long long)(nz - 1) * pl + g] * P.a[(long long)nz * pl + g]);
     if (P.Ray) for (int k = 1; k <= nz; ++k) { const long long o = (long long)(k - 1) * pl + g; t = t + P.H_to_RZ * (P.Ray[o] * P.x[o]); }
     P.tau_bot[g] = t;
+  }
+  if (!REM && P.lim_on && j >= P.js_lim) {
+    // vertvisc_limit_vel without truncation files (:3016-3037 for u, :3090-3111 for v): the CFL number of the face velocity in the
+    // cell it flows out of; a truncated velocity is the one of CFL 0.9*CFL_trunc.  The stress above used the untruncated velocities.
+    const long long sB = DIR ? G.pitch : 1;
+    const double dtf = dt * P.face[g];
+    const double IA0 = P.IareaT[g], IA1 = P.IareaT[g + sB];
+    for (int k = 1; k <= nz; ++k) {
+      const long long o = (long long)(k - 1) * pl + g;
+      const double u = P.x[o];
+      double un = u;
+      bool trunc = false;
+      if (fabs(u) < P.vel_underflow) un = 0.0;
+      else if (P.cfl_based) {
+        if (P.CFL_trunc > 0.0) {
+          if ((u * dtf) * IA1 < -P.CFL_trunc) { un = (-0.9 * P.CFL_trunc) * (P.areaT[g + sB] / dtf); trunc = true; }
+          else if ((u * dtf) * IA0 > P.CFL_trunc) { un = (0.9 * P.CFL_trunc) * (P.areaT[g] / dtf); trunc = true; }
+        }
+      } else if (P.maxvel > 0.0 && fabs(u) > P.maxvel) { un = copysign(0.9 * P.maxvel, u); trunc = true; }
+      if (__double_as_longlong(un) != __double_as_longlong(u)) P.x[o] = un;
+      if (trunc && P.h && (P.h[o] + P.h[o + sB] > P.H_report)) atomicAdd(P.ntrunc, 1ULL);
+    }
   }
 }
 
@@ -405,14 +432,33 @@ int m6_vertvisc_run(mom6cu_ctx* c, const VvDev& D) {
   SolveK U = {};
   U.nz = G.nk; U.direct_stress = CS.direct_stress; U.dt = D.dt; U.dt_Rho0 = D.dt / c->vgrid.H_to_RZ; U.h_neglect = c->vgrid.H_subroundoff;
   U.Hmix = CS.Hmix_stress; U.I_Hmix = CS.direct_stress ? 1.0 / CS.Hmix_stress : 0.0; U.H_to_RZ = c->vgrid.H_to_RZ; U.h = D.h;
+  U.vel_underflow = CS.vel_underflow; U.CFL_trunc = CS.CFL_trunc; U.maxvel = CS.maxvel; U.cfl_based = CS.CFL_based_trunc;
+  U.lim_on = (CS.vel_underflow > 0.0) || (CS.CFL_based_trunc ? CS.CFL_trunc > 0.0 : CS.maxvel > 0.0);
+  U.H_report = 6.0 * c->vgrid.Angstrom_H; U.areaT = c->grid.areaT; U.IareaT = c->grid.IareaT;
+  U.ntrunc = reinterpret_cast<unsigned long long*>(c->buf("vv.ntrunc", 1));
+  if (!U.ntrunc) return MOM6CU_ERR_CUDA;
   SolveK V = U;
   U.mask = c->grid.mask2dCu; U.a = K.a_u; U.hh = K.h_u; U.Ray = D.Ray_u; U.tau = D.taux; U.x = D.u; U.tau_bot = D.taux_bot;
   U.i0 = d.isc - 1; U.i1 = d.iec; U.j0 = std::min(d.jsc, d.isc); U.j1 = d.jec; U.js_stress = d.jsc; U.js_solve = d.isc;  // `do j=G%isc,G%jec` (:778)
+  U.js_lim = d.jsc; U.face = c->grid.dy_Cu;
   V.mask = c->grid.mask2dCv; V.a = K.a_v; V.hh = K.h_v; V.Ray = D.Ray_v; V.tau = D.tauy; V.x = D.v; V.tau_bot = D.tauy_bot;
   V.i0 = d.isc; V.i1 = d.iec; V.j0 = d.jsc - 1; V.j1 = d.jec; V.js_stress = V.j0; V.js_solve = V.j0;
+  V.js_lim = V.j0; V.face = c->grid.dx_Cv;
   M6_LAUNCH(c, (vv_solve_kernel<0, false>), dim3((U.i1 - U.i0 + 128) / 128, U.j1 - U.j0 + 1), 128, 0, G, U);
   M6_LAUNCH(c, (vv_solve_kernel<1, false>), dim3((V.i1 - V.i0 + 128) / 128, V.j1 - V.j0 + 1), 128, 0, G, V);
   M6_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mom6cu_vertvisc_ntrunc(mom6cu_ctx* c, long long* ntrunc) {
+  if (!c || !ntrunc) return MOM6CU_ERR_BAD_ARG;
+  M6_CUDA(c, cudaSetDevice(c->device));
+  const double* p = c->buf("vv.ntrunc", 1);
+  if (!p) return MOM6CU_ERR_CUDA;
+  unsigned long long n = 0;
+  M6_CUDA(c, cudaStreamSynchronize(c->stream));
+  M6_CUDA(c, cudaMemcpy(&n, p, sizeof(n), cudaMemcpyDeviceToHost));
+  *ntrunc = (long long)n;
   return 0;
 }
 

@@ -869,7 +869,8 @@ def vertvisc_cs(**over):
     """vertvisc_init defaults (MOM_vert_friction.F90:2929-3250) as OM4-like ALE runs resolve them."""
     cs = dict(bottomdraglaw=1, harmonic_visc=0, direct_stress=0, fixed_LOTW_ML=0, apply_LOTW_floor=0, dynamic_viscous_ML=0, nkml=0,
               answer_date=99991231, unsupported=0, Hbbl=10.0, Kv=1.0e-4, Kv_extra_bbl=0.0, Kvml_invZ2=0.0, Hmix=40.0, Hmix_stress=20.0,
-              harm_BL_val=0.0, vonKar=0.41, vel_underflow=0.0, dZ_subroundoff=1.0e-30)
+              harm_BL_val=0.0, vonKar=0.41, vel_underflow=0.0, dZ_subroundoff=1.0e-30,
+              CFL_based_trunc=1, CFL_trunc=0.5, maxvel=3.0e8)   # CFL_BASED_TRUNCATIONS, CFL_TRUNCATE, MAXVEL (:3389-3398)
     cs.update(over)
     return cs
 

@@ -215,7 +215,9 @@ def _vertvisc_setup(dom, grid, gv, cs, a_u, a_v, h_u, h_v):
         setattr(CS, k, False)
     CS.pass_ke_uv = NS()
     # vertvisc_limit_vel (:2926-3120) with its defaults (vertvisc_init :3389-3402): truncation of velocities whose CFL exceeds 0.5
-    CS.maxvel, CS.cfl_based_trunc, CS.cfl_trunc, CS.cfl_report = 3.0e8, True, 0.5, 0.5
+    CS.maxvel, CS.cfl_based_trunc = float(cs.get("maxvel", 3.0e8)), bool(cs.get("CFL_based_trunc", 1))
+    CS.cfl_trunc = float(cs.get("CFL_trunc", 0.5))
+    CS.cfl_report, CS.truncramptime = CS.cfl_trunc, 0.0
     CS.u_trunc_file, CS.v_trunc_file, CS.ntrunc = "", "", 0
     return R["mom_vert_friction"], G, GV, US, CS
 
@@ -258,6 +260,7 @@ def vertvisc(dom, grid, gv, cs, a, a_u, a_v, h_u, h_v):
     F["vertvisc"](fa["u"], fa["v"], fa["h"], forces, visc, a["dt"], None, NS(), NS(), G, GV, US, CS,
                   fa.get("taux_bot"), fa.get("tauy_bot"))
     _back(fa, a, ("u", "v", "taux_bot", "tauy_bot"))
+    return int(CS.ntrunc)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
@@ -426,7 +429,10 @@ def step_dyn_split_rk2(dom, grid, gv, css, cs, a, land_blocks=0):
     for k in ("debug", "use_gl90_in_ssw", "stokesmixing"):
         setattr(vv, k, False)
     vv.pass_ke_uv = NS()
-    vv.maxvel, vv.cfl_based_trunc, vv.cfl_trunc, vv.cfl_report, vv.truncramptime = 3.0e8, True, 0.5, 0.5, 0.0
+    vvd = css["vertvisc"]
+    vv.maxvel, vv.cfl_based_trunc = float(vvd.get("maxvel", 3.0e8)), bool(vvd.get("CFL_based_trunc", 1))
+    vv.cfl_trunc = float(vvd.get("CFL_trunc", 0.5))
+    vv.cfl_report, vv.truncramptime = vv.cfl_trunc, 0.0
     vv.u_trunc_file, vv.v_trunc_file, vv.ntrunc = "", "", 0
     GV.dz_subroundoff = float(css["vertvisc"].get("dZ_subroundoff", GV.dz_subroundoff))
     bt = barotropic_cs(R, dom, grid, gv, cs["barotropic"], wide_metrics(dom, land_blocks))

@@ -95,6 +95,7 @@ int oracle_vertvisc_coef(const mom6cu_domain* dom, const mom6cu_grid* G, const m
                          const mom6cu_vertvisc_cs* CS, const mom6cu_vertvisc_coef_args* a, double* a_u, double* a_v, double* h_u, double* h_v);
 int oracle_vertvisc(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vgrid* GV, const mom6cu_vertvisc_cs* CS,
                     const mom6cu_vertvisc_args* a, const double* a_u, const double* a_v, const double* h_u, const double* h_v);
+long long oracle_vertvisc_ntrunc(int reset); /* CS%ntrunc counted by oracle_vertvisc (vertvisc_limit_vel :2926) since the last reset */
 int oracle_vertvisc_remnant(const mom6cu_domain* dom, const mom6cu_grid* G, const mom6cu_vertvisc_cs* CS, const double* Ray_u,
                             const double* Ray_v, double* visc_rem_u, double* visc_rem_v, double dt, const double* a_u, const double* a_v,
                             const double* h_u, const double* h_v);

@@ -279,9 +279,13 @@ def vertvisc(dom, grid, gv, cs, a, a_u, a_v, h_u, h_v):
     keep = []
     g = marshal.grid(grid, keep); v = marshal.vgrid(gv); c = marshal.vertvisc_cs(cs); st = marshal.vertvisc_args(a, keep)
     lib.oracle_vertvisc.argtypes = [C.c_void_p] * 9
+    lib.oracle_vertvisc_ntrunc.restype = C.c_longlong
+    lib.oracle_vertvisc_ntrunc.argtypes = [C.c_int]
+    lib.oracle_vertvisc_ntrunc(1)
     rc = lib.oracle_vertvisc(C.byref(dom), C.byref(g), C.byref(v), C.byref(c), C.byref(st), _dp(a_u), _dp(a_v), _dp(h_u), _dp(h_v))
     if rc:
         raise RuntimeError(f"oracle_vertvisc rc={rc}")
+    return int(lib.oracle_vertvisc_ntrunc(1))   # CS%ntrunc of this call (vertvisc_limit_vel)
 
 
 def vertvisc_remnant(dom, grid, cs, visc_rem_u, visc_rem_v, dt, a_u, a_v, h_u, h_v, Ray_u=None, Ray_v=None):

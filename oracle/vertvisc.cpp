@@ -229,6 +229,8 @@ void solve_column(int nz, double dt, const double* a, const double* hh, const do
 }
 }  // namespace
 
+static long long g_ntrunc = 0;
+
 extern "C" int oracle_vertvisc(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vgrid* GV, const mom6cu_vertvisc_cs* CS,
                                const mom6cu_vertvisc_args* a, const double* a_up, const double* a_vp, const double* h_up, const double* h_vp) {
   const OGrid G(d, Gp);
@@ -292,7 +294,47 @@ extern "C" int oracle_vertvisc(const mom6cu_domain* d, const mom6cu_grid* Gp, co
       }
     }
   }
+  // vertvisc_limit_vel :2926-3120 without truncation files (the reporting branch truncates the same velocities)
+  const bool lim_on = (CS->vel_underflow > 0.0) || (CS->CFL_based_trunc ? CS->CFL_trunc > 0.0 : CS->maxvel > 0.0);
+  if (lim_on) {
+    const double maxvel = CS->maxvel, truncvel = 0.9 * maxvel, H_report = 6.0 * GV->Angstrom_H;
+    for (int k = 1; k <= nz; ++k) for (int j = js; j <= je; ++j) for (int I = Isq; I <= Ieq; ++I) {
+      bool trunc = false;
+      if (std::fabs(u(I, j, k)) < CS->vel_underflow) u(I, j, k) = 0.0;
+      else if (CS->CFL_based_trunc) {
+        if (CS->CFL_trunc > 0.0) {
+          if ((u(I, j, k) * (dt * G.dy_Cu(I, j))) * G.IareaT(I + 1, j) < -CS->CFL_trunc) {
+            u(I, j, k) = (-0.9 * CS->CFL_trunc) * (G.areaT(I + 1, j) / (dt * G.dy_Cu(I, j))); trunc = true;
+          } else if ((u(I, j, k) * (dt * G.dy_Cu(I, j))) * G.IareaT(I, j) > CS->CFL_trunc) {
+            u(I, j, k) = (0.9 * CS->CFL_trunc) * (G.areaT(I, j) / (dt * G.dy_Cu(I, j))); trunc = true;
+          }
+        }
+      } else if (maxvel > 0.0 && std::fabs(u(I, j, k)) > maxvel) { u(I, j, k) = std::copysign(truncvel, u(I, j, k)); trunc = true; }
+      if (trunc && h.p && (h(I, j, k) + h(I + 1, j, k) > H_report)) ++g_ntrunc;
+    }
+    for (int k = 1; k <= nz; ++k) for (int J = Jsq; J <= Jeq; ++J) for (int i = is; i <= ie; ++i) {
+      bool trunc = false;
+      if (std::fabs(v(i, J, k)) < CS->vel_underflow) v(i, J, k) = 0.0;
+      else if (CS->CFL_based_trunc) {
+        if (CS->CFL_trunc > 0.0) {
+          if ((v(i, J, k) * (dt * G.dx_Cv(i, J))) * G.IareaT(i, J + 1) < -CS->CFL_trunc) {
+            v(i, J, k) = (-0.9 * CS->CFL_trunc) * (G.areaT(i, J + 1) / (dt * G.dx_Cv(i, J))); trunc = true;
+          } else if ((v(i, J, k) * (dt * G.dx_Cv(i, J))) * G.IareaT(i, J) > CS->CFL_trunc) {
+            v(i, J, k) = (0.9 * CS->CFL_trunc) * (G.areaT(i, J) / (dt * G.dx_Cv(i, J))); trunc = true;
+          }
+        }
+      } else if (maxvel > 0.0 && std::fabs(v(i, J, k)) > maxvel) { v(i, J, k) = std::copysign(truncvel, v(i, J, k)); trunc = true; }
+      if (trunc && h.p && (h(i, J, k) + h(i, J + 1, k) > H_report)) ++g_ntrunc;
+    }
+  }
   return 0;
+}
+
+// CS%ntrunc: truncations counted by oracle_vertvisc since the last reset
+extern "C" long long oracle_vertvisc_ntrunc(int reset) {
+  const long long n = g_ntrunc;
+  if (reset) g_ntrunc = 0;
+  return n;
 }
 
 extern "C" int oracle_vertvisc_remnant(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vertvisc_cs* CS, const double* Ray_u,

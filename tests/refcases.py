@@ -128,6 +128,11 @@ for _n, _kw in enumerate([
         dict(apply_LOTW_floor=1), dict(fixed_LOTW_ML=1, apply_LOTW_floor=1, Kvml_invZ2=1e-3, harmonic_visc=1),
         dict(direct_stress=1, land_blocks=2, with_Ray=True)]):
     case(f"vertvisc_family/options{_n:02d}", "vertvisc_family", (16, 12, 6), VV_OUT, **_kw)
+# vertvisc_limit_vel (:2926-3120): CFL-based truncation (a time step long enough for CFL > 0.5), MAXVEL truncation, VEL_UNDERFLOW
+case("vertvisc_family/truncation_cfl", "vertvisc_family", (16, 12, 6), VV_OUT, land_blocks=2, dt=60000.0)
+case("vertvisc_family/truncation_cfl_0.2_ray", "vertvisc_family", (16, 12, 6), VV_OUT, land_blocks=1, dt=30000.0, CFL_trunc=0.2, with_Ray=True)
+case("vertvisc_family/truncation_maxvel", "vertvisc_family", (16, 12, 6), VV_OUT, land_blocks=2, CFL_based_trunc=0, maxvel=0.2)
+case("vertvisc_family/vel_underflow", "vertvisc_family", (16, 12, 6), VV_OUT, land_blocks=2, vel_underflow=0.05)
 
 # ---- PressureForce_FV_Bouss ----------------------------------------------------------------------------------------------
 PF_OUT = ("PFu", "PFv", "pbce", "eta")
@@ -164,6 +169,7 @@ case("step/plm_pressure_reconstruction", "step", (12, 10, 4), STEP_OUT, land_blo
 case("step/ppm_reconstruction_begw_split_bottom_stress", "step", (12, 10, 4), STEP_OUT, land_blocks=2, begw=0.25,
      split_bottom_stress=1, pgf=dict(reconstruct=1, Recon_Scheme=2))
 case("step/project_velocity_no_land", "step", (12, 10, 4), STEP_OUT, land_blocks=0, BT_project_velocity=1)
+case("step/cfl_truncation_in_vertvisc", "step", (12, 10, 4), STEP_OUT, land_blocks=2, vv=dict(CFL_trunc=0.001))
 
 
 # ---- ALE_regridding_and_remapping (MOM.F90:1751) --------------------------------------------------------------------------
@@ -229,6 +235,12 @@ def _coefs(dom, nk):
             fidx.new(dom, "u", nk=nk).a, fidx.new(dom, "v", nk=nk).a]
 
 
+def vv_collect(dom, outputs, d):
+    out = collect(dom, outputs, d, {})
+    out["zero_ok:ntrunc"] = np.array([float(d["ntrunc"])])   # CS%ntrunc, the count of truncated velocities
+    return out
+
+
 def vertvisc_family(mod, dom, grid, gv, cs, coef, sol, is_oracle):
     """vertvisc_coef, then vertvisc_remnant and vertvisc with its coefficients (the order of step_MOM_dyn_split_RK2)"""
     nk = int(dom.nk)
@@ -240,9 +252,9 @@ def vertvisc_family(mod, dom, grid, gv, cs, coef, sol, is_oracle):
         mod.vertvisc_remnant(dom, grid, cs, vru, vrv, sol["dt"], *c, sol["Ray_u"], sol["Ray_v"])
     else:
         mod.vertvisc_remnant(dom, grid, gv, cs, vru, vrv, sol["dt"], *c, sol["Ray_u"], sol["Ray_v"])
-    mod.vertvisc(dom, grid, gv, cs, s, *c)
+    ntrunc = mod.vertvisc(dom, grid, gv, cs, s, *c)
     return dict(a_u=c[0], a_v=c[1], h_u=c[2], h_v=c[3], visc_rem_u=vru, visc_rem_v=vrv, u=s["u"], v=s["v"],
-                taux_bot=s["taux_bot"], tauy_bot=s["tauy_bot"])
+                taux_bot=s["taux_bot"], tauy_bot=s["tauy_bot"], ntrunc=ntrunc)
 
 
 def build(name):
@@ -271,10 +283,12 @@ def build(name):
     if st == "tracer_hordiff":
         return synthetic.hordiff_inputs(*shape, **kw)
     if st == "step":
-        pgf, nsteps = kw.pop("pgf", None), kw.pop("nsteps", 1)
+        pgf, nsteps, vv = kw.pop("pgf", None), kw.pop("nsteps", 1), kw.pop("vv", None)
         dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(*shape, **kw)
         if pgf:
             css["pressureforce"].update(pgf)
+        if vv:
+            css["vertvisc"].update(vv)
         return dom, grid, gv, css, cs, a
     raise KeyError(st)
 
@@ -294,7 +308,7 @@ def run_oracle(oracle, name, inputs):
         return step_collect(dom, cs, a)
     if c["stage"] == "vertvisc_family":
         dom, grid, gv, cs, coef, sol = inputs
-        return collect(dom, c["outputs"], vertvisc_family(oracle, dom, grid, gv, cs, coef, sol, True), {})
+        return vv_collect(dom, c["outputs"], vertvisc_family(oracle, dom, grid, gv, cs, coef, sol, True))
     dom, grid, gv, cs, a = inputs
     cs, a = _copy(cs), _copy(a)
     if c["stage"] == "mixedlayer_restrat":
@@ -321,7 +335,7 @@ def run_reference(name, inputs):
         return step_collect(dom, cs, a)
     if c["stage"] == "vertvisc_family":
         dom, grid, gv, cs, coef, sol = inputs
-        return collect(dom, c["outputs"], vertvisc_family(stages, dom, grid, gv, cs, coef, sol, False), {})
+        return vv_collect(dom, c["outputs"], vertvisc_family(stages, dom, grid, gv, cs, coef, sol, False))
     dom, grid, gv, cs, a = inputs
     cs, a = _copy(cs), _copy(a)
     if c["stage"] == "btstep":
@@ -378,9 +392,10 @@ def run_device(ctx_factory, name, inputs):
         ctx.vertvisc_remnant(vru, vrv, sol["dt"], sol["Ray_u"], sol["Ray_v"])
         s = _copy(sol)
         ctx.vertvisc(s)
+        ntrunc = ctx.vertvisc_ntrunc()
         ctx.close()
-        return collect(dom, c["outputs"], dict(a_u=g[0], a_v=g[1], h_u=g[2], h_v=g[3], visc_rem_u=vru, visc_rem_v=vrv, u=s["u"],
-                                               v=s["v"], taux_bot=s["taux_bot"], tauy_bot=s["tauy_bot"]), {})
+        return vv_collect(dom, c["outputs"], dict(a_u=g[0], a_v=g[1], h_u=g[2], h_v=g[3], visc_rem_u=vru, visc_rem_v=vrv, u=s["u"],
+                                                  v=s["v"], taux_bot=s["taux_bot"], tauy_bot=s["tauy_bot"], ntrunc=ntrunc))
     dom, grid, gv, cs, a = inputs
     cs, a = _copy(cs), _copy(a)
     ctx = _ctx(ctx_factory, dom, grid, gv)

@@ -76,7 +76,7 @@ HORVISC_CS = dict(dx2q=L2, dy2q=L2, dx2h=L2, dy2h=L2, DX_dyBu=NONDIM, DY_dxBu=NO
                   Kh_Max_xy=L2T, Kh_bg_min=L2T, Re_Ah=NONDIM, Re_Ah_const_xx=L3, Re_Ah_const_xy=L3)
 # vertvisc_coef / vertvisc / vertvisc_remnant (MOM_vert_friction.F90:48-170, :557, :1229, :1357)
 VERTVISC_CS = dict(Hbbl=ZL, Kv=HZT, Kv_extra_bbl=HZT, Kvml_invZ2=HZT, Hmix=ZL, Hmix_stress=THK, harm_BL_val=NONDIM, vonKar=NONDIM, vel_underflow=VEL,
-                   dZ_subroundoff=ZL)
+                   dZ_subroundoff=ZL, maxvel=VEL, CFL_trunc=NONDIM)
 VERTVISC_COEF = dict(u=VEL, v=VEL, h=THK, Kv_bbl_u=HZT, Kv_bbl_v=HZT, bbl_thick_u=ZL, bbl_thick_v=ZL, Kv_shear=HZT, Kv_shear_Bu=HZT, ustar=(-1, 0, 0, 1),
                      dt=TIME)
 VERTVISC = dict(u=VEL, v=VEL, h=THK, taux=STRESS, tauy=STRESS, Ray_u=HT, Ray_v=HT, dt=TIME, taux_bot=STRESS, tauy_bot=STRESS)

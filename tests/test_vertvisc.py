@@ -71,7 +71,10 @@ def test_coupling_coefficients_feel_the_bottom_boundary_layer(oracle):
 CASES = [dict(), dict(land_blocks=4, with_Bu=True, with_Ray=True), dict(harmonic_visc=1, land_blocks=3), dict(bottomdraglaw=0, Kv_extra_bbl=5e-3),
          dict(bottomdraglaw=0, land_blocks=2, cyclic_y=True), dict(Kvml_invZ2=1e-3, land_blocks=2), dict(harm_BL_val=0.5, with_Ray=True),
          dict(fixed_LOTW_ML=1, land_blocks=3), dict(apply_LOTW_floor=1), dict(fixed_LOTW_ML=1, apply_LOTW_floor=1, Kvml_invZ2=1e-3, harmonic_visc=1),
-         dict(direct_stress=1, land_blocks=2, with_Ray=True)]
+         dict(direct_stress=1, land_blocks=2, with_Ray=True),
+         # vertvisc_limit_vel (:2926-3120): CFL-based truncation, MAXVEL truncation, VEL_UNDERFLOW
+         dict(land_blocks=2, dt=60000.0), dict(land_blocks=1, dt=30000.0, CFL_trunc=0.2, with_Ray=True),
+         dict(land_blocks=2, CFL_based_trunc=0, maxvel=0.2), dict(land_blocks=2, vel_underflow=0.05)]
 
 
 @pytest.mark.gpu
@@ -82,7 +85,7 @@ def test_vertvisc_family_bitwise(oracle, ctx_factory, kw):
         a_u, a_v, h_u, h_v = _coefs(dom, nk)
         oracle.vertvisc_coef(dom, grid, gv, cs, coef, a_u, a_v, h_u, h_v)
         ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in sol.items()}
-        oracle.vertvisc(dom, grid, gv, cs, ref, a_u, a_v, h_u, h_v)
+        ntrunc = oracle.vertvisc(dom, grid, gv, cs, ref, a_u, a_v, h_u, h_v)
         rru, rrv = np.zeros_like(sol["u"]), np.zeros_like(sol["v"])
         oracle.vertvisc_remnant(dom, grid, cs, rru, rrv, sol["dt"], a_u, a_v, h_u, h_v, sol["Ray_u"], sol["Ray_v"])
         ctx = ctx_factory(dom)
@@ -96,6 +99,9 @@ def test_vertvisc_family_bitwise(oracle, ctx_factory, kw):
             assert np.array_equal(cut(dom, x).view(np.int64), cut(dom, y).view(np.int64)), (name, kw, np.count_nonzero(cut(dom, x) != cut(dom, y)))
         got = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in sol.items()}
         ctx.vertvisc(got)
+        assert ctx.vertvisc_ntrunc() == ntrunc, (kw, ntrunc)
+        if "dt" in kw or "maxvel" in kw:
+            assert ntrunc > 0, kw
         for name, cut in (("u", _cu), ("v", _cv), ("taux_bot", _cu), ("tauy_bot", _cv)):
             assert np.array_equal(cut(dom, ref[name]).view(np.int64), cut(dom, got[name]).view(np.int64)), (name, kw)
         gru, grv = np.zeros_like(sol["u"]), np.zeros_like(sol["v"])
