@@ -412,7 +412,7 @@ def _ctx_methods():
     setattr(Context, "remap_dyn_split_rk2_aux_vars", remap_dyn_split_rk2_aux_vars)
     setattr(Context, "set_dtbt", set_dtbt)
     setattr(Context, "step_dyn_split_rk2", step_dyn_split_rk2)
-    for f in (set_cs_vertvisc, vertvisc_coef, vertvisc_get_coef, vertvisc, vertvisc_remnant):
+    for f in (set_cs_vertvisc, vertvisc_coef, vertvisc_get_coef, vertvisc, vertvisc_remnant, vertvisc_ntrunc):
         setattr(Context, f.__name__, f)
     setattr(Context, "ale_regrid", ale_regrid)
     setattr(Context, "advect_tracer", advect_tracer)

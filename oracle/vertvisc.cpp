@@ -5,7 +5,7 @@
 // dz = GV%H_to_Z*h [MOM_interface_heights.F90:939] and find_ustar returns forces%ustar [MOM_forcing_type.F90:1264-1268]).
 // The reference's row bound `do j=G%isc,G%jec` in the u solver (:778 etc.) is kept as written.
 // PARITY: PINNED BY A REFERENCE RUN -- the reference's own MOM_vert_friction.F90, executed by oracle/f90run, agrees bit for bit on 11
-// option sets (tests/test_reference_f90.py, vertvisc_family/*).  Not restated: vertvisc_limit_vel's CFL-based truncation (:2926-3120).
+// option sets + 4 cases that truncate velocities (vertvisc_limit_vel :2926-3120) (tests/test_reference_f90.py, vertvisc_family/*).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include <cfloat>
