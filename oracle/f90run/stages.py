@@ -692,3 +692,88 @@ def tracer_hordiff(dom, grid, gv, cs, a):
         for fx, ox in zip(fl, ol):
             if ox is not None:
                 adapt.back(fx, ox)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def _bt_small_cs(R, dom, gv):
+    """barotropic_CS with only what btcalc / bt_mass_source / set_dtbt read"""
+    CS = new(R, "mom_barotropic", "barotropic_cs", module_is_initialized=True)
+    CS.split, CS.debug, CS.calculate_sal, CS.tidal_sal_bug = True, False, False, False
+    CS.rho_bt_lin = float(gv["Rho0"])
+    CS.isdw, CS.iedw, CS.jsdw, CS.jedw = int(dom.isdw), int(dom.iedw), int(dom.jsdw), int(dom.jedw)
+    return CS
+
+
+def _wide_from_g(dom, a):
+    """a G-sized h-point array placed in a wide-halo array (zero outside G's memory domain)"""
+    wi, wj = dom.isd - dom.isdw, dom.jsd - dom.jsdw
+    w = np.zeros((dom.jedw - dom.jsdw + 1, dom.iedw - dom.isdw + 1))
+    w[wj:wj + a.shape[0], wi:wi + a.shape[1]] = a
+    return FArray.from_numpy(w, (int(dom.isdw), int(dom.jsdw)))
+
+
+def btcalc(dom, grid, gv, a):
+    """btcalc, src/core/MOM_barotropic.F90:4360-4605"""
+    R = ref("src/core/MOM_barotropic.F90")
+    G, GV, US = _types(dom, grid, gv)
+    CS = _bt_small_cs(R, dom, gv)
+    CS.hvel_scheme = int(a["hvel_scheme"])
+    fu, fv = adapt.farr(dom, a["frhatu"]), adapt.farr(dom, a["frhatv"])
+    CS.frhatu, CS.frhatv = fu, fv
+    CS.bathyt = _wide_from_g(dom, a["bathyT"])
+    R["mom_barotropic"]["btcalc"](adapt.farr(dom, a["h"]), G, GV, CS, adapt.farr(dom, a.get("h_u")), adapt.farr(dom, a.get("h_v")),
+                                 bool(a.get("may_use_default", 0)), None)
+    adapt.back(fu, a["frhatu"]); adapt.back(fv, a["frhatv"])
+
+
+def bt_mass_source(dom, grid, gv, h, eta, set_cor, eta_cor):
+    """bt_mass_source, src/core/MOM_barotropic.F90:5243-5296"""
+    R = ref("src/core/MOM_barotropic.F90")
+    G, GV, US = _types(dom, grid, gv)
+    CS = _bt_small_cs(R, dom, gv)
+    fe = adapt.farr(dom, eta_cor)
+    CS.eta_cor = fe
+    R["mom_barotropic"]["bt_mass_source"](adapt.farr(dom, h), adapt.farr(dom, eta), bool(set_cor), G, GV, CS)
+    adapt.back(fe, eta_cor)
+
+
+def set_dtbt(dom, grid, gv, a):
+    """set_dtbt, src/core/MOM_barotropic.F90:3509-3633, with find_face_areas :5146 / BT_cont_to_face_areas :5107; -> (dtbt, dtbt_max)"""
+    R = ref("src/core/MOM_barotropic.F90")
+    G, GV, US = _types(dom, grid, gv)
+    G.z_ref = float(a.get("Z_ref", 0.0))
+    CS = _bt_small_cs(R, dom, gv)
+    CS.frhatu, CS.frhatv = adapt.farr(dom, a["frhatu"]), adapt.farr(dom, a["frhatv"])
+    CS.bathyt = _wide_from_g(dom, a["bathyT"])
+    CS.bebt, CS.g_extra, CS.dtbt_fraction = float(a["bebt"]), float(a["G_extra"]), float(a["dtbt_fraction"])
+    CS.bt_coriolis_scale, CS.nonlinear_continuity = float(a["BT_Coriolis_scale"]), bool(a["Nonlinear_continuity"])
+    CS.dtbt, CS.dtbt_max = 0.0, 0.0
+    CS.dy_cu, CS.dx_cv = _wide_u(dom, grid["dy_Cu"]), _wide_v(dom, grid["dx_Cv"])
+    BT = bt_cont_type(dom, a["BT_cont"]) if a.get("BT_cont") is not None else None
+    kw = {}
+    if a.get("pbce") is not None:
+        kw["pbce"] = adapt.farr(dom, a["pbce"])
+    if a.get("have_gtot_est"):
+        kw["gtot_est"] = float(a["gtot_est"])
+    if BT is not None:
+        kw["bt_cont"] = BT
+    if a.get("eta") is not None:
+        kw["eta"] = adapt.farr(dom, a["eta"])
+    if a.get("SSH_add"):
+        kw["ssh_add"] = float(a["SSH_add"])
+    R["mom_barotropic"]["set_dtbt"](G, GV, US, CS, **kw)
+    return float(CS.dtbt), float(CS.dtbt_max)
+
+
+def _wide_u(dom, a):
+    wi, wj = dom.isd - dom.isdw, dom.jsd - dom.jsdw
+    w = np.zeros((dom.jedw - dom.jsdw + 1, dom.iedw - dom.isdw + 2))
+    w[wj:wj + a.shape[0], wi:wi + a.shape[1]] = a
+    return FArray.from_numpy(w, (int(dom.isdw) - 1, int(dom.jsdw)))
+
+
+def _wide_v(dom, a):
+    wi, wj = dom.isd - dom.isdw, dom.jsd - dom.jsdw
+    w = np.zeros((dom.jedw - dom.jsdw + 2, dom.iedw - dom.isdw + 1))
+    w[wj:wj + a.shape[0], wi:wi + a.shape[1]] = a
+    return FArray.from_numpy(w, (int(dom.isdw), int(dom.jsdw) - 1))

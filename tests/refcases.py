@@ -204,6 +204,44 @@ for _n, _kw in enumerate([
     case(f"tracer_hordiff/options{_n:02d}", "tracer_hordiff", (14, 10, 5), HD_OUT, **_kw)
 
 
+# ---- btcalc (4 thickness schemes + the default), bt_mass_source (set / accumulate), set_dtbt (4 ways of finding the wave speed) ----
+case("bt_helpers/btcalc_mass_source_set_dtbt", "bt_helpers", (16, 12, 5), (), land_blocks=2)
+
+
+def _dtbt_args(dom, grid, cs, mode):
+    a = dict(pbce=cs["pbce"], gtot_est=0.0, have_gtot_est=0, BT_cont=None, eta=None, SSH_add=0.0, frhatu=cs["barotropic"]["frhatu"],
+             frhatv=cs["barotropic"]["frhatv"], bathyT=grid["bathyT"], bebt=0.1, G_extra=0.0, dtbt_fraction=0.98,
+             BT_Coriolis_scale=1.0, Z_ref=0.0, Nonlinear_continuity=0)
+    if mode == "BT_cont":
+        a["BT_cont"] = cs["BT_cont"]
+    elif mode == "eta":
+        a["eta"] = cs["eta"]; a["Nonlinear_continuity"] = 1
+    elif mode == "gtot":
+        a["pbce"] = None; a["gtot_est"] = 9.8; a["have_gtot_est"] = 1; a["SSH_add"] = 2.0
+    return a
+
+
+def bt_helpers(inputs, btcalc, bt_mass_source, set_dtbt):
+    """the three small barotropic entries through the given backend (oracle, translated reference or device)"""
+    from mom6_b200 import fidx
+    dom, grid, gv, bcs, ba, st, scs = inputs
+    nk = int(dom.nk)
+    out = {}
+    hu, hv = np.abs(st["u"]) + 1.0, np.abs(st["v"]) + 1.0
+    for n, (scheme, huv, mud) in enumerate(((1, False, 0), (2, False, 0), (3, False, 0), (4, True, 0), (4, False, 1))):
+        a = dict(h=st["h"], h_u=hu if huv else None, h_v=hv if huv else None, frhatu=fidx.new(dom, "u", nk=nk).a,
+                 frhatv=fidx.new(dom, "v", nk=nk).a, bathyT=grid["bathyT"], hvel_scheme=scheme, may_use_default=mud)
+        btcalc(a)
+        out[f"btcalc{n}.frhatu"], out[f"btcalc{n}.frhatv"] = inner(dom, a["frhatu"]).copy(), inner(dom, a["frhatv"]).copy()
+    for set_cor in (1, 0):
+        e = bcs["eta_cor"].copy()
+        bt_mass_source(st["h"], ba["eta_in"], set_cor, e)
+        out[f"bt_mass_source{set_cor}.eta_cor"] = inner(dom, e).copy()
+    for mode in ("BT_cont", "eta", "bathy", "gtot"):
+        out["set_dtbt." + mode] = np.array(set_dtbt(_dtbt_args(dom, grid, scs, mode)))
+    return out
+
+
 def ale_collect(dom, ale, dcs, a):
     src = dict(a)
     for k in ("diffu", "diffv", "CAu_pred", "CAv_pred", "u_av", "v_av"):
@@ -276,6 +314,12 @@ def build(name):
         return synthetic.advect_inputs(*shape, **kw)
     if st == "ale":
         return synthetic.ale_chain_inputs(*shape, **kw)
+    if st == "bt_helpers":
+        from oracle import pyoracle
+        dom, grid, gv, bcs, ba = synthetic.btstep_inputs(*shape, **kw)
+        dom2, grid2, gv2, css, scs, sa = synthetic.step_dyn_inputs(*shape, **kw)
+        pyoracle.step_dyn_split_rk2(dom2, grid2, gv2, css, scs, sa)   # realistic pbce, BT_cont, eta (pinned by the step cases)
+        return dom2, grid2, gv2, bcs, ba, synthetic.dyn_state(dom2, grid2), scs
     if st == "thickness_diffuse":
         return synthetic.thickness_diffuse_inputs(*shape, **kw)
     if st == "mixedlayer_restrat":
@@ -295,6 +339,11 @@ def build(name):
 
 def run_oracle(oracle, name, inputs):
     c = CASES[name]
+    if c["stage"] == "bt_helpers":
+        dom, grid, gv = inputs[:3]
+        return bt_helpers(inputs, lambda a: oracle.btcalc(dom, grid, gv, a),
+                          lambda h, eta, sc, e: oracle.bt_mass_source(dom, grid, gv, h, eta, sc, e),
+                          lambda a: oracle.set_dtbt(dom, grid, gv, a))
     if c["stage"] == "ale":
         dom, grid, gv, ale, dcs, a = inputs
         ale, dcs, a = _copy(ale), _copy(dcs), _copy(a)
@@ -322,6 +371,11 @@ def run_oracle(oracle, name, inputs):
 def run_reference(name, inputs):
     from oracle.f90run import stages
     c = CASES[name]
+    if c["stage"] == "bt_helpers":
+        dom, grid, gv = inputs[:3]
+        return bt_helpers(inputs, lambda a: stages.btcalc(dom, grid, gv, a),
+                          lambda h, eta, sc, e: stages.bt_mass_source(dom, grid, gv, h, eta, sc, e),
+                          lambda a: stages.set_dtbt(dom, grid, gv, a))
     if c["stage"] == "ale":
         dom, grid, gv, ale, dcs, a = inputs
         ale, dcs, a = _copy(ale), _copy(dcs), _copy(a)
@@ -363,6 +417,12 @@ def run_device(ctx_factory, name, inputs):
     """the same case through the C ABI on the GPU (tests/test_reference_golden.py)"""
     c = CASES[name]
     st = c["stage"]
+    if st == "bt_helpers":
+        dom, grid, gv = inputs[:3]
+        ctx = _ctx(ctx_factory, dom, grid, gv)
+        out = bt_helpers(inputs, ctx.btcalc, ctx.bt_mass_source, ctx.set_dtbt)
+        ctx.close()
+        return out
     if st == "step":
         dom, grid, gv, css, cs, a = inputs
         cs, a = _copy(cs), _copy(a)
