@@ -23,7 +23,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SHIMS = {
     "src/core/MOM_dynamics_split_RK2.F90": dict(
         hooks=[("step_MOM_dyn_split_RK2", "u_inst, v_inst, h, tv, visc, dt, forces, p_surf_begin, p_surf_end, uh, vh, uhtr, vhtr, eta_av, G, GV, US, CS, calc_dtbt")],
-        public=[], uses=["use MOM_barotropic, only : barotropic_fill_mom6cu, barotropic_update_from_mom6cu"]),
+        public=[], uses=["use MOM_barotropic, only : barotropic_fill_mom6cu, barotropic_update_from_mom6cu",
+                         "use MOM_continuity_PPM, only : continuity_PPM_send_cs_mom6cu",
+                         "use MOM_CoriolisAdv, only : CoriolisAdv_send_cs_mom6cu", "use MOM_hor_visc, only : hor_visc_send_cs_mom6cu",
+                         "use MOM_PressureForce, only : PressureForce_send_cs_mom6cu",
+                         "use MOM_vert_friction, only : vertvisc_send_cs_mom6cu"]),
     "src/core/MOM_barotropic.F90": dict(
         hooks=[("btstep", "U_in, V_in, eta_in, dt, bc_accel_u, bc_accel_v, forces, pbce, eta_PF_in, U_Cor, V_Cor, accel_layer_u, accel_layer_v, eta_out, "
                           "uhbtav, vhbtav, G, GV, US, CS, visc_rem_u, visc_rem_v, SpV_avg, ADp, OBC, BT_cont, eta_PF_start, taux_bot, tauy_bot, uh0, vh0, "
@@ -31,16 +35,21 @@ SHIMS = {
         public=["barotropic_fill_mom6cu", "barotropic_update_from_mom6cu"], uses=[]),
     "src/core/MOM_continuity_PPM.F90": dict(
         hooks=[("continuity_PPM", "u, v, hin, h, uh, vh, dt, G, GV, US, CS, OBC, pbv, uhbt, vhbt, visc_rem_u, visc_rem_v, u_cor, v_cor, BT_cont, du_cor, dv_cor")],
-        public=[], uses=[]),
+        public=["continuity_PPM_send_cs_mom6cu"], uses=[]),
     "src/core/MOM_CoriolisAdv.F90": dict(
         hooks=[("CorAdCalc", "u, v, h, uh, vh, CAu, CAv, OBC, AD, G, GV, US, CS, pbv, Waves")],
-        public=[], uses=[]),
+        public=["CoriolisAdv_send_cs_mom6cu"], uses=[]),
     "src/core/MOM_PressureForce_FV.F90": dict(
         hooks=[("PressureForce_FV_Bouss", "h, tv, PFu, PFv, G, GV, US, CS, ALE_CSp, ADp, p_atm, pbce, eta")],
-        public=[], uses=["use MOM_EOS, only : EOS_query_mom6cu", "use MOM_ALE, only : ALE_answer_date_mom6cu"]),
+        public=["PressureForce_FV_send_cs_mom6cu"],
+        uses=["use MOM_EOS, only : EOS_query_mom6cu", "use MOM_ALE, only : ALE_answer_date_mom6cu"]),
+    "src/core/MOM_PressureForce.F90": dict(
+        hooks=[], public=["PressureForce_send_cs_mom6cu"],
+        uses=["use MOM_PressureForce_FV, only : PressureForce_FV_send_cs_mom6cu"]),
+    "src/parameterizations/vertical/MOM_vert_friction.F90": dict(hooks=[], public=["vertvisc_send_cs_mom6cu"], uses=[]),
     "src/parameterizations/lateral/MOM_hor_visc.F90": dict(
         hooks=[("horizontal_viscosity", "u, v, h, uh, vh, diffu, diffv, MEKE, VarMix, G, GV, US, CS, tv, dt, OBC, BT, TD, ADp, hu_cont, hv_cont, STOCH")],
-        public=[], uses=[]),
+        public=["hor_visc_send_cs_mom6cu"], uses=[]),
     # accessors only: these modules keep the members the bindings above need private
     "src/equation_of_state/MOM_EOS.F90": dict(hooks=[], public=["EOS_query_mom6cu"], uses=[]),
     "src/ALE/MOM_ALE.F90": dict(hooks=[], public=["ALE_answer_date_mom6cu"], uses=[]),

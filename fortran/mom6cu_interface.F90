@@ -705,4 +705,11 @@ contains
     p = c_null_ptr ; if (present(a)) p = c_loc(a)
   end function opt_loc2
 
+  !> c_loc of an allocatable 2-D array of a control structure, or c_null_ptr when it is not allocated
+  function opt_alloc2(x) result(p)
+    real(c_double), dimension(:,:), allocatable, target, intent(in) :: x
+    type(c_ptr) :: p
+    p = c_null_ptr ; if (allocated(x)) p = c_loc(x)
+  end function opt_alloc2
+
 end module mom6cu_interface

@@ -1,0 +1,138 @@
+"""A stand-in for libmom6cu.so behind the Fortran bindings, for executing fortran/bodies/*.inc without a GPU.  TEST INFRASTRUCTURE ONLY.
+
+tests/test_fortran_shims_executed.py installs the shims into a shadow copy of the reference's modules (fortran/install_shims.py),
+runs the hooked reference procedure through oracle/f90run and lets the `mom6cu_*` C entry points the bindings call land HERE: each
+stub rebuilds the dictionaries of oracle/pyoracle.py from the bind(C) structures the Fortran body filled (field by field, following
+the ctypes mirrors of mom6_b200/_lib.py, i.e. include/mom6cu.h) and calls the C++ oracle.  What this checks is the Fortran side: that
+every member the reference's control structures hand over arrives in the right field, with the right logical -> int conversion,
+array and optional-argument handling -- the part of the boundary that cannot be compiled here."""
+import ctypes as C
+
+import numpy as np
+
+from mom6_b200 import _lib
+from .rt import FArray, NS, mangle
+
+
+class Abi:
+    def __init__(self, oracle, dom, grid, gv):
+        self.oracle, self.dom, self.grid, self.gv = oracle, dom, grid, gv
+        self.css = {}
+        self.calls = []
+        self.error = ""
+
+    # ---- bind(C) structure (an NS filled by the Fortran body) -> dict of numpy arrays / scalars
+    def to_dict(self, ns, struct, pairs):
+        out = {}
+        for name, ctype in struct._fields_:
+            v = getattr(ns, mangle(name))
+            if ctype is C.c_void_p:
+                if v is None:
+                    out[name] = None
+                elif isinstance(v, FArray):
+                    a = np.ascontiguousarray(v.to_numpy(), dtype=np.float64)
+                    pairs.append((v, a))
+                    out[name] = a
+                else:
+                    raise TypeError(f"{struct.__name__}%{name}: c_loc of a {type(v).__name__}")
+            elif ctype in (C.c_int, C.c_double):
+                if v is None:
+                    raise KeyError(f"{struct.__name__}%{name} was not set by the Fortran binding")
+                out[name] = int(v) if ctype is C.c_int else float(v)
+            else:
+                out[name] = v   # pointer to a nested structure: handled by the caller
+        return out
+
+    @staticmethod
+    def back(pairs):
+        for fa, a in pairs:
+            fa.assign(FArray.from_numpy(a))
+
+    def stubs(self):
+        o, dom, grid, gv = self.oracle, self.dom, self.grid, self.gv
+        L = _lib
+
+        def set_cs(key, struct):
+            def f(ctx, c):
+                pairs = []
+                self.css[key] = self.to_dict(c, struct, pairs)
+                self.calls.append("set_cs_" + key)
+                return 0
+            return f
+
+        def run(name, fn):
+            def f(*a):
+                self.calls.append(name)
+                try:
+                    return fn(*a) or 0
+                except RuntimeError as e:   # the oracle's refusal (rc 3) or failure: what mom6cu_last_error would report
+                    self.error = str(e)
+                    return 3
+            return f
+
+        def continuity(ctx, a):
+            pairs = []
+            d = self.to_dict(a, L.ContinuityArgs, pairs)
+            if d["BT_cont"] is not None:
+                d["BT_cont"] = self.to_dict(d["BT_cont"], L.BTCont, pairs)
+            o.continuity(dom, grid, gv, self.css["continuity"], d)
+            self.back(pairs)
+
+        def coradcalc(ctx, a):
+            pairs = []
+            o.coradcalc(dom, grid, gv, self.css["coriolisadv"], self.to_dict(a, L.CorAdCalcArgs, pairs))
+            self.back(pairs)
+
+        def hor_visc(ctx, a):
+            pairs = []
+            o.horizontal_viscosity(dom, grid, gv, self.css["hor_visc"], self.to_dict(a, L.HorViscArgs, pairs))
+            self.back(pairs)
+
+        def pressure_force(ctx, a):
+            pairs = []
+            o.pressure_force(dom, grid, gv, self._pgf_cs(), self.to_dict(a, L.PressureForceArgs, pairs))
+            self.back(pairs)
+
+        def btstep(ctx, c, a):
+            pairs = []
+            cs = self.to_dict(c, L.BarotropicCS, pairs)
+            d = self.to_dict(a, L.BtstepArgs, pairs)
+            d["BT_cont"] = self.to_dict(d["BT_cont"], L.BTCont, pairs)
+            o.btstep(dom, grid, gv, cs, d)
+            self.back(pairs)
+
+        def step(ctx, c, a):
+            pairs = []
+            cs = self.to_dict(c, L.DynSplitRK2CS, pairs)
+            cs["BT_cont"] = self.to_dict(cs["BT_cont"], L.BTCont, pairs)
+            bt = cs["barotropic"]
+            cs["barotropic"] = self.to_dict(bt, L.BarotropicCS, pairs)
+            d = self.to_dict(a, L.StepDynArgs, pairs)
+            css = dict(continuity=self.css["continuity"], coriolisadv=self.css["coriolisadv"], hor_visc=self.css["hor_visc"],
+                       pressureforce=self._pgf_cs(), vertvisc=self.css["vertvisc"])
+            o.step_dyn_split_rk2(dom, grid, gv, css, cs, d)
+            self.back(pairs)
+            c.cau_pred_stored, c.dtbt_max = int(cs["CAu_pred_stored"]), float(cs["dtbt_max"])
+            bt.dtbt = float(cs["barotropic"]["dtbt"])
+
+        return {
+            "c_loc": lambda x: x, "c_null_ptr": None, "c_associated": lambda p, q=None: p is not None, "c_null_char": "\0",
+            "c_int": 4, "c_double": 8, "c_size_t": 8, "c_long_long": 8, "c_char": 1, "c_ptr": None,
+            "mom6cu_last_error": lambda ctx, buf, n: 0,
+            "mom6cu_set_cs_continuity": set_cs("continuity", L.ContinuityCS),
+            "mom6cu_set_cs_coriolisadv": set_cs("coriolisadv", L.CoriolisAdvCS),
+            "mom6cu_set_cs_hor_visc": set_cs("hor_visc", L.HorViscCS),
+            "mom6cu_set_cs_pressureforce": set_cs("pressureforce", L.PressureForceCS),
+            "mom6cu_set_cs_vertvisc": set_cs("vertvisc", L.VertviscCS),
+            "mom6cu_continuity": run("continuity", continuity), "mom6cu_coradcalc": run("coradcalc", coradcalc),
+            "mom6cu_horizontal_viscosity": run("horizontal_viscosity", hor_visc),
+            "mom6cu_pressure_force": run("pressure_force", pressure_force), "mom6cu_btstep": run("btstep", btstep),
+            "mom6cu_step_dyn_split_rk2": run("step_dyn_split_rk2", step),
+        }
+
+    def _pgf_cs(self):
+        d = dict(self.css["pressureforce"])
+        for k in ("Rlay", "g_prime"):   # GV%Rlay(1:nk), GV%g_prime(1:nk+1): 1-D host arrays
+            if d.get(k) is not None:
+                d[k] = np.ascontiguousarray(d[k]).ravel()
+        return d

@@ -57,6 +57,10 @@ class ProcGen:
         self.globals_assigned = set()
         self.tmp = 0
         self.ret = None
+        # scalar locals with an initialisation in their declaration (or the SAVE attribute) keep their value between calls
+        self.save_vars = [mangle(n) for n, v in proc.vars.items()
+                          if not v.dummy and not v.parameter and v.dims is None and v.base in ("real", "integer", "logical")
+                          and v.init is not None and v.init[0] == "val"]
 
     # ---- symbols
     def var(self, name):
@@ -472,6 +476,8 @@ class ProcGen:
             self.call(ind, st, ln)
             return
         if st == "return":
+            for n in self.save_vars:
+                self.emit(ind, f"_SAVE[{self.P.name + '.' + n!r}] = {n}", ln)
             self.emit(ind, "return " + self.ret, ln)
             return
         if st == "exit":
@@ -622,7 +628,11 @@ class ProcGen:
                     else:
                         pro.append(f"{n} = None" if v.pointer else f"{n} = _rt.new_type(globals(), {v.tname!r})")
                 elif v.init is not None and v.init[0] == "val":
-                    pro.append(f"{n} = {self.coerce(v, parse_expr(v.init[1]))}")
+                    if n in self.save_vars:
+                        pro.append(f"{n} = _SAVE[{P.name + '.' + n!r}] if {P.name + '.' + n!r} in _SAVE else "
+                                   f"{self.coerce(v, parse_expr(v.init[1]))}")
+                    else:
+                        pro.append(f"{n} = {self.coerce(v, parse_expr(v.init[1]))}")
                 elif v.pointer:
                     pro.append(f"{n} = None")
                 elif v.dims is None and v.base in ("integer", "real", "logical", "character"):
@@ -637,7 +647,8 @@ class ProcGen:
         head = [f"def {mangle(P.name)}(" + ", ".join(mangle(a) + "=None" for a in P.args) + f"):  # {self.mod.name}:{P.line}"]
         if self.globals_assigned:
             head.append("    global " + ", ".join(sorted(self.globals_assigned)))
-        out = head + ["    " + p for p in pro] + body + ["    return " + self.ret, ""]
+        out = head + ["    " + p for p in pro] + body + [f"    _SAVE[{P.name + '.' + n!r}] = {n}" for n in self.save_vars] + \
+            ["    return " + self.ret, ""]
         if P.elemental:
             n = mangle(P.name)
             out.append(f"{n} = _rt.elemental({n}, {[mangle(a) for a in P.args]!r}, {[mangle(a) for a in outs]!r}, {P.kind == 'function'!r})")
@@ -692,7 +703,7 @@ class Program:
         return None
 
     def gen_module(self, mod):
-        out = [f"# generated from {mod.path} by oracle/f90run -- do not commit", "import oracle.f90run.rt as _rt"]
+        out = [f"# generated from {mod.path} by oracle/f90run -- do not commit", "import oracle.f90run.rt as _rt", "_SAVE = {}"]
         for k in INTRINSICS:
             out.append(f"_i_{k} = _rt.INTRINSICS[{k!r}]")
         out.append("")

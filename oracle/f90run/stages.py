@@ -9,12 +9,23 @@ from . import adapt, halo, load, new
 from .rt import FArray, NS
 
 _REF = {}
+# tests/test_fortran_shims_executed.py: run the same stages with the shadow copies fortran/install_shims.py makes of some modules
+SHADOW = dict(files={}, extra_files=[], stubs={}, post_load=None, tag=None)
 
 
 def ref(*paths):
-    key = tuple(paths)
+    key = tuple(paths) + (SHADOW["tag"],)
     if key not in _REF:
-        _REF[key] = load(list(paths), extra_stubs=halo.STUBS)
+        files = [SHADOW["files"].get(p, p) for p in paths]
+        files += [f for f in SHADOW["extra_files"] if f not in files]
+        for p, q in SHADOW["files"].items():   # a shadowed module another shadowed module uses (its accessors)
+            if q not in files and SHADOW["tag"] is not None:
+                files.append(q)
+        stubs = dict(halo.STUBS)
+        stubs.update(SHADOW["stubs"])
+        _REF[key] = load(files, extra_stubs=stubs)
+        if SHADOW["post_load"] is not None:
+            SHADOW["post_load"](_REF[key])
     return _REF[key]
 
 
@@ -127,6 +138,7 @@ def barotropic_cs(R, dom, grid, gv, cs, wide_metrics):
     CS.nonlin_cont_update_period = 1
     CS.rho_bt_lin = gv["Rho0"]
     CS.hvel_scheme = 4
+    CS.dtbt_max = 0.0
     for k in ("integral_bt_cont", "integral_obcs", "nonlinear_continuity", "gradual_bt_ics", "nonlin_stress", "clip_velocity",
               "dynamic_psurf", "calculate_sal", "linear_wave_drag", "use_filter", "linear_freq_drag", "debug", "debug_bt",
               "tidal_sal_flather", "tidal_sal_bug", "debug_wide_halos"):
