@@ -50,6 +50,18 @@ SHIMS = {
     "src/parameterizations/lateral/MOM_hor_visc.F90": dict(
         hooks=[("horizontal_viscosity", "u, v, h, uh, vh, diffu, diffv, MEKE, VarMix, G, GV, US, CS, tv, dt, OBC, BT, TD, ADp, hu_cont, hv_cont, STOCH")],
         public=["hor_visc_send_cs_mom6cu"], uses=[]),
+    "src/tracer/MOM_tracer_advect.F90": dict(
+        hooks=[("advect_tracer", "h_end, uhtr, vhtr, OBC, dt, G, GV, US, CS, Reg, x_first_in, vol_prev, max_iter_in, update_vol_prev, uhr_out, vhr_out")],
+        public=[], uses=[]),
+    "src/tracer/MOM_tracer_hor_diff.F90": dict(
+        hooks=[("tracer_hordiff", "h, dt, MEKE, VarMix, visc, G, GV, US, CS, Reg, tv, do_online_flag, read_khdt_x, read_khdt_y")],
+        public=[], uses=[]),
+    "src/parameterizations/lateral/MOM_thickness_diffuse.F90": dict(
+        hooks=[("thickness_diffuse", "h, uhtr, vhtr, tv, dt, G, GV, US, MEKE, VarMix, CDp, CS, STOCH")],
+        public=[], uses=["use MOM_EOS, only : EOS_query_mom6cu"]),
+    "src/parameterizations/lateral/MOM_mixed_layer_restrat.F90": dict(
+        hooks=[("mixedlayer_restrat", "h, uhtr, vhtr, tv, forces, dt, MLD, h_MLD, bflux, VarMix, G, GV, US, CS")],
+        public=[], uses=["use MOM_EOS, only : EOS_query_mom6cu"]),
     # accessors only: these modules keep the members the bindings above need private
     "src/equation_of_state/MOM_EOS.F90": dict(hooks=[], public=["EOS_query_mom6cu"], uses=[]),
     "src/ALE/MOM_ALE.F90": dict(hooks=[], public=["ALE_answer_date_mom6cu"], uses=[]),

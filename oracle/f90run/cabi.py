@@ -26,9 +26,21 @@ class Abi:
         out = {}
         for name, ctype in struct._fields_:
             v = getattr(ns, mangle(name))
-            if ctype is C.c_void_p:
+            if ctype is C.c_void_p or isinstance(v, FArray):   # a data pointer (also double* const* and int* members)
                 if v is None:
                     out[name] = None
+                elif isinstance(v, FArray) and v.kind == "o":     # an array of c_ptr (tracer fields): a list of arrays / None
+                    lst = []
+                    for e in v.tolist():
+                        if isinstance(e, FArray):
+                            a = np.ascontiguousarray(e.to_numpy(), dtype=np.float64)
+                            pairs.append((e, a))
+                            lst.append(a)
+                        else:
+                            lst.append(None)
+                    out[name] = lst
+                elif isinstance(v, FArray) and v.kind == "i":
+                    out[name] = [int(x) for x in v.tolist()]
                 elif isinstance(v, FArray):
                     a = np.ascontiguousarray(v.to_numpy(), dtype=np.float64)
                     pairs.append((v, a))
@@ -115,7 +127,53 @@ class Abi:
             c.cau_pred_stored, c.dtbt_max = int(cs["CAu_pred_stored"]), float(cs["dtbt_max"])
             bt.dtbt = float(cs["barotropic"]["dtbt"])
 
+        def advect_tracer(ctx, c, a):
+            pairs = []
+            cs = self.to_dict(c, L.TracerAdvectCS, pairs)
+            d = self.to_dict(a, L.AdvectTracerArgs, pairs)
+            n = d["ntr"]
+            d["tr"], d["advect_scheme"] = d["tr"][:n], d["advect_scheme"][:n]
+            d["conc_underflow"] = np.ascontiguousarray(d["conc_underflow"][:n])
+            d["x_first_in"] = None if d["x_first_in"] < 0 else d["x_first_in"]
+            d["max_iter_in"] = None if d["max_iter_in"] < 0 else d["max_iter_in"]
+            o.advect_tracer(dom, grid, gv, cs, d)
+            self.back(pairs)
+
+        def mixedlayer_restrat(ctx, c, h, uhtr, vhtr, T, S, ustar, dt, h_MLD, Rd):
+            pairs = []
+            cs = self.to_dict(c, L.MleCS, pairs)
+
+            def arr(x):
+                if x is None:
+                    return None
+                a = np.ascontiguousarray(x.to_numpy(), dtype=np.float64)
+                pairs.append((x, a))
+                return a
+            o.mixedlayer_restrat(dom, grid, gv, cs, arr(h), arr(uhtr), arr(vhtr), arr(T), arr(S), arr(ustar), float(dt), arr(h_MLD), arr(Rd))
+            self.back(pairs)
+
+        def thickness_diffuse(ctx, c, a):
+            pairs = []
+            o.thickness_diffuse(dom, grid, gv, self.to_dict(c, L.ThicknessDiffuseCS, pairs), self.to_dict(a, L.ThicknessDiffuseArgs, pairs))
+            self.back(pairs)
+
+        def tracer_hordiff(ctx, c, a):
+            pairs = []
+            cs = self.to_dict(c, L.TracerHorDiffCS, pairs)
+            d = self.to_dict(a, L.TracerHordiffArgs, pairs)
+            n = d["ntr"]
+            d["tr"] = d["tr"][:n]
+            d["conc_underflow"] = np.ascontiguousarray(d["conc_underflow"][:n])
+            for k in ("df_x", "df_y"):
+                d[k] = d[k][:n] if d[k] is not None else None
+            o.tracer_hordiff(dom, grid, gv, cs, d)
+            self.back(pairs)
+
         return {
+            "mom6cu_advect_tracer": run("advect_tracer", advect_tracer),
+            "mom6cu_mixedlayer_restrat": run("mixedlayer_restrat", mixedlayer_restrat),
+            "mom6cu_thickness_diffuse": run("thickness_diffuse", thickness_diffuse),
+            "mom6cu_tracer_hordiff": run("tracer_hordiff", tracer_hordiff),
             "c_loc": lambda x: x, "c_null_ptr": None, "c_associated": lambda p, q=None: p is not None, "c_null_char": "\0",
             "c_int": 4, "c_double": 8, "c_size_t": 8, "c_long_long": 8, "c_char": 1, "c_ptr": None,
             "mom6cu_last_error": lambda ctx, buf, n: 0,

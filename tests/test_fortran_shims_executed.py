@@ -73,7 +73,12 @@ def test_hooked_step_equals_the_reference_step(shadow, name):
                                   "horizontal_viscosity/options00", "horizontal_viscosity/options02", "horizontal_viscosity/options09",
                                   "pressure_force/options00", "pressure_force/options01", "pressure_force/options03",
                                   "pressure_force/options05", "pressure_force/options08", "btstep/default",
-                                  "btstep/strong_drag_bound_corr", "btstep/project_velocity_filter_y_first"])
+                                  "btstep/strong_drag_bound_corr", "btstep/project_velocity_filter_y_first",
+                                  "advect_tracer/ppm_h3_cfl2.5_three_tracers", "advect_tracer/mixed_schemes_underflow_max_iter",
+                                  "advect_tracer/ppm_h3_periodic_y_y_first", "mixedlayer_restrat/options00",
+                                  "mixedlayer_restrat/options01", "thickness_diffuse/options01", "thickness_diffuse/options02",
+                                  "thickness_diffuse/options05", "tracer_hordiff/options01", "tracer_hordiff/options02",
+                                  "tracer_hordiff/options03"])
 def test_hooked_stage_equals_the_reference_stage(shadow, name):
     inputs = refcases.build(name)
     want = refcases.run_reference(name, inputs)
