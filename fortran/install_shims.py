@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SHIMS = {
     "src/core/MOM_dynamics_split_RK2.F90": dict(
         hooks=[("step_MOM_dyn_split_RK2", "u_inst, v_inst, h, tv, visc, dt, forces, p_surf_begin, p_surf_end, uh, vh, uhtr, vhtr, eta_av, G, GV, US, CS, calc_dtbt")],
-        public=[], uses=["use MOM_barotropic, only : barotropic_fill_mom6cu, barotropic_update_from_mom6cu",
+        public=["dyn_split_RK2_aux_fill_mom6cu"], uses=["use MOM_barotropic, only : barotropic_fill_mom6cu, barotropic_update_from_mom6cu",
                          "use MOM_continuity_PPM, only : continuity_PPM_send_cs_mom6cu",
                          "use MOM_CoriolisAdv, only : CoriolisAdv_send_cs_mom6cu", "use MOM_hor_visc, only : hor_visc_send_cs_mom6cu",
                          "use MOM_PressureForce, only : PressureForce_send_cs_mom6cu",
@@ -64,7 +64,14 @@ SHIMS = {
         public=[], uses=["use MOM_EOS, only : EOS_query_mom6cu"]),
     # accessors only: these modules keep the members the bindings above need private
     "src/equation_of_state/MOM_EOS.F90": dict(hooks=[], public=["EOS_query_mom6cu"], uses=[]),
-    "src/ALE/MOM_ALE.F90": dict(hooks=[], public=["ALE_answer_date_mom6cu"], uses=[]),
+    "src/ALE/MOM_ALE.F90": dict(hooks=[], public=["ALE_answer_date_mom6cu", "ALE_fill_mom6cu", "ALE_set_old_grid_weight_mom6cu"],
+                                uses=["use MOM_regridding, only : regridding_fill_mom6cu", "use MOM_remapping, only : remapping_fill_mom6cu"]),
+    "src/ALE/MOM_regridding.F90": dict(hooks=[], public=["regridding_fill_mom6cu"], uses=[]),
+    "src/ALE/MOM_remapping.F90": dict(hooks=[], public=["remapping_fill_mom6cu"], uses=[]),
+    "src/core/MOM.F90": dict(
+        hooks=[("ALE_regridding_and_remapping", "CS, G, GV, US, u, v, h, tv, dtdia, Time_end_thermo")], public=[],
+        uses=["use MOM_ALE, only : ALE_fill_mom6cu, ALE_set_old_grid_weight_mom6cu",
+              "use MOM_dynamics_split_RK2, only : dyn_split_RK2_aux_fill_mom6cu"]),
 }
 
 DECL = re.compile(r"^\s*(type\s*\(|class\s*\(|real\b|integer\b|logical\b|character\b|complex\b|double\s+precision\b|use\b|implicit\b|"

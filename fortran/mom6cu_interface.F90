@@ -478,7 +478,7 @@ module mom6cu_interface
       import :: c_int, c_ptr, mom6cu_ale_args, mom6cu_ale_cs, mom6cu_dyn_split_rk2_cs
       type(c_ptr), value :: ctx
       type(mom6cu_ale_cs), intent(inout) :: CS
-      type(mom6cu_dyn_split_rk2_cs), intent(in) :: dynCS
+      type(c_ptr), value :: dynCS   ! const mom6cu_dyn_split_rk2_cs*, or c_null_ptr (no auxiliary variables to remap)
       type(mom6cu_ale_args), intent(in) :: a
     end function mom6cu_ale_regridding_and_remapping
     integer(c_int) function mom6cu_ale_remap_interface_vals(ctx, h_old, h_new, int_val) bind(C, name="mom6cu_ale_remap_interface_vals")

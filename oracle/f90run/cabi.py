@@ -169,7 +169,28 @@ class Abi:
             o.tracer_hordiff(dom, grid, gv, cs, d)
             self.back(pairs)
 
+        def ale(ctx, c, dptr, a):
+            pairs = []
+            cs = dict(regridCS=self.to_dict(c.regridcs, L.RegriddingCS, pairs), remapCS=self.to_dict(c.remapcs, L.RemappingCS, pairs),
+                      vel_remapCS=self.to_dict(c.vel_remapcs, L.RemappingCS, pairs), regrid_time_scale=float(c.regrid_time_scale),
+                      remap_uv_using_old_alg=int(c.remap_uv_using_old_alg), do_conv_adj=int(c.do_conv_adj),
+                      use_hybgen_unmix=int(c.use_hybgen_unmix), remap_aux_vars=int(c.remap_aux_vars))
+            cs["regridCS"]["coordinateResolution"] = np.ascontiguousarray(cs["regridCS"]["coordinateResolution"]).ravel()
+            d = self.to_dict(a, L.AleArgs, pairs)
+            n = d["ntr"]
+            d["tr"] = d["tr"][:n]
+            d["conc_underflow"] = np.ascontiguousarray(d["conc_underflow"][:n])
+            dyn = None
+            if dptr is not None:
+                dyn = {k: v for k, v in self.to_dict(dptr, L.DynSplitRK2CS, pairs).items() if k not in ("BT_cont", "barotropic")}
+                dyn["BT_cont"] = {k: None for k, _ in L.BTCont._fields_}
+                dyn["barotropic"] = self._null_bt()
+            o.ale_regridding_and_remapping(dom, grid, gv, cs, d, dyn_cs=dyn)
+            self.back(pairs)
+            c.regridcs.old_grid_weight = float(cs["regridCS"]["old_grid_weight"])
+
         return {
+            "mom6cu_ale_regridding_and_remapping": run("ale_regridding_and_remapping", ale),
             "mom6cu_advect_tracer": run("advect_tracer", advect_tracer),
             "mom6cu_mixedlayer_restrat": run("mixedlayer_restrat", mixedlayer_restrat),
             "mom6cu_thickness_diffuse": run("thickness_diffuse", thickness_diffuse),
@@ -187,6 +208,13 @@ class Abi:
             "mom6cu_pressure_force": run("pressure_force", pressure_force), "mom6cu_btstep": run("btstep", btstep),
             "mom6cu_step_dyn_split_rk2": run("step_dyn_split_rk2", step),
         }
+
+    @staticmethod
+    def _null_bt():
+        d = {}
+        for k, ct in _lib.BarotropicCS._fields_:
+            d[k] = None if ct is C.c_void_p else (0 if ct is C.c_int else 0.0)
+        return d
 
     def _pgf_cs(self):
         d = dict(self.css["pressureforce"])

@@ -571,7 +571,8 @@ def ale_regridding_and_remapping(dom, grid, gv, ale, a, dyn_cs=None):
     D = None
     fd = {}
     if dyn_cs is not None:
-        D = NS(remap_aux=True, store_cau=bool(dyn_cs.get("store_CAu", 0)), cau_pred_stored=bool(dyn_cs.get("CAu_pred_stored", 0)))
+        D = NS(remap_aux=True, store_cau=bool(dyn_cs.get("store_CAu", 0)), cau_pred_stored=bool(dyn_cs.get("CAu_pred_stored", 0)),
+               be=float(dyn_cs.get("be", 0.6)), begw=float(dyn_cs.get("begw", 0.0)))
         for k in ("diffu", "diffv", "CAu_pred", "CAv_pred", "u_av", "v_av"):
             fd[k] = adapt.farr(dom, dyn_cs[k])
             setattr(D, k.lower(), fd[k])
