@@ -25,6 +25,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
+_LOADED = {}   # the translated shadow modules are kept across cases; only the C-ABI stand-in and the SAVEd flags are renewed
+
+
 @pytest.fixture()
 def shadow(oracle):
     """installs the shims under oracle/_ref/shims and points oracle/f90run/stages.py at the shadow copies"""
@@ -33,20 +36,36 @@ def shadow(oracle):
     import install_shims
     from oracle.f90run import cabi, stages
     out = os.path.join(ROOT, "oracle", "_ref", "shims")
-    install_shims.install(f90run.REFERENCE_ROOT, out)
-    state = {}
+    if "installed" not in _LOADED:
+        install_shims.install(f90run.REFERENCE_ROOT, out)
+        _LOADED["installed"] = True
+        _LOADED["current"] = {}
+        names = cabi.Abi(oracle, None, None, None).stubs()
+        # every stub forwards to the stand-in of the current case
+        _LOADED["stubs"] = {k: ((lambda *a, _k=k: _LOADED["current"]["stubs"][_k](*a)) if callable(v) else v) for k, v in names.items()}
+        _LOADED["plain"] = dict(stages._REF)
+        _LOADED["shadow"] = {}
+    plain = dict(stages._REF)
+    _LOADED["plain"].update(plain)
 
     def activate(dom, grid, gv):
         abi = cabi.Abi(oracle, dom, grid, gv)
-        state["abi"] = abi
+        _LOADED["current"]["stubs"] = abi.stubs()
+        _LOADED["plain"].update(stages._REF)
         stages._REF.clear()
+        stages._REF.update(_LOADED["shadow"])
         stages.SHADOW.update(files={rel: os.path.join(out, os.path.basename(rel)) for rel in install_shims.SHIMS},
-                             extra_files=[os.path.join(out, "mom6cu_interface.F90")], stubs=abi.stubs(), tag="shadow",
+                             extra_files=[os.path.join(out, "mom6cu_interface.F90")], stubs=_LOADED["stubs"], tag="shadow",
                              post_load=lambda R: [ns.__setitem__("mom6cu_ctx", "ctx") for ns in R.values() if "mom6cu_ctx" in ns])
+        for R in stages._REF.values():      # `logical, save :: cs_sent`: a new run of the model
+            for ns in R.values():
+                ns["_SAVE"].clear()
         return abi
     yield activate
+    _LOADED["shadow"].update({k: v for k, v in stages._REF.items() if k[-1] == "shadow"})
     stages.SHADOW.update(files={}, extra_files=[], stubs={}, post_load=None, tag=None)
     stages._REF.clear()
+    stages._REF.update(_LOADED["plain"])
 
 
 def _same(a, b):
