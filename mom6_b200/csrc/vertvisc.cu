@@ -231,6 +231,23 @@ struct SolveK {
   unsigned long long* ntrunc;
 };
 
+// vertvisc_limit_vel without truncation files (:3016-3037 for u, :3090-3111 for v) for one velocity: the CFL number of the face
+// velocity in the cell it flows out of; a truncated velocity is the one of CFL 0.9*CFL_trunc.  hsum = h(i,j,k) + h(i+1,j,k) (or j+1).
+__device__ __forceinline__ double vv_limit(const SolveK& P, double u, double dtf, double IA0, double IA1, double A0, double A1,
+                                           bool have_h, double hsum) {
+  double un = u;
+  bool trunc = false;
+  if (fabs(u) < P.vel_underflow) un = 0.0;
+  else if (P.cfl_based) {
+    if (P.CFL_trunc > 0.0) {
+      if ((u * dtf) * IA1 < -P.CFL_trunc) { un = (-0.9 * P.CFL_trunc) * (A1 / dtf); trunc = true; }
+      else if ((u * dtf) * IA0 > P.CFL_trunc) { un = (0.9 * P.CFL_trunc) * (A0 / dtf); trunc = true; }
+    }
+  } else if (P.maxvel > 0.0 && fabs(u) > P.maxvel) { un = copysign(0.9 * P.maxvel, u); trunc = true; }
+  if (trunc && have_h && (hsum > P.H_report)) atomicAdd(P.ntrunc, 1ULL);
+  return un;
+}
+
 template <int DIR, bool REM>
 __global__ void __launch_bounds__(128) vv_solve_kernel(Geom G, SolveK P) {
   const int i = P.i0 + blockIdx.x * blockDim.x + threadIdx.x, j = P.j0 + blockIdx.y;
@@ -239,6 +256,7 @@ __global__ void __launch_bounds__(128) vv_solve_kernel(Geom G, SolveK P) {
   const int nz = P.nz;
   const double mask = P.mask[g], dt = P.dt;
   double surface_stress = 0.0;
+  bool tau_done = false, lim_done = false;
   if (!REM && j >= P.js_stress) {
     if (P.direct_stress) {  // :705-718
       if (mask > 0.) {
@@ -287,7 +305,31 @@ __global__ void __launch_bounds__(128) vv_solve_kernel(Geom G, SolveK P) {
       xm = REM ? (hk + dt * aK * xm) * b1 : (hk * xk + dt * aK * xm) * b1;
       P.x[o] = xm;
     }
-    if (nz >= 2) {
+    // Without Rayleigh drag the bottom stress needs only the bottom velocity, so the truncation of vertvisc_limit_vel (which the
+    // reference applies after the stress) can be folded into the back-substitution: the recurrence carries the untruncated
+    // velocity in a register and the truncated one is what is stored.  No extra pass over the column.
+    const bool fuse = !REM && P.lim_on && !P.Ray && j >= P.js_lim;
+    if (fuse) {
+      lim_done = true;
+      const long long sB = DIR ? G.pitch : 1;
+      const double dtf = dt * P.face[g], IA0 = P.IareaT[g], IA1 = P.IareaT[g + sB], A0 = P.areaT[g], A1 = P.areaT[g + sB];
+      const long long ob = (long long)(nz - 1) * pl + g;
+      if (P.tau_bot && j >= P.js_stress) { P.tau_bot[g] = P.H_to_RZ * (xm * P.a[(long long)nz * pl + g]); tau_done = true; }
+      {
+        const double un = vv_limit(P, xm, dtf, IA0, IA1, A0, A1, P.h != nullptr, P.h ? P.h[ob] + P.h[ob + sB] : 0.0);
+        if (__double_as_longlong(un) != __double_as_longlong(xm)) P.x[ob] = un;
+      }
+      if (nz >= 2) {
+        double xk_n = P.x[(long long)(nz - 2) * pl + g];
+        for (int k = nz - 1; k >= 1; --k) {
+          const long long o = (long long)(k - 1) * pl + g;
+          const double xk = xk_n;
+          if (k > 1) xk_n = P.x[o - pl];
+          xm = xk + c1[k + 1] * xm;
+          P.x[o] = vv_limit(P, xm, dtf, IA0, IA1, A0, A1, P.h != nullptr, P.h ? P.h[o] + P.h[o + sB] : 0.0);
+        }
+      }
+    } else if (nz >= 2) {
       double xk_n = P.x[(long long)(nz - 2) * pl + g];
       for (int k = nz - 1; k >= 1; --k) {
         const long long o = (long long)(k - 1) * pl + g;
@@ -298,31 +340,20 @@ __global__ void __launch_bounds__(128) vv_solve_kernel(Geom G, SolveK P) {
       }
     }
   }
-  if (!REM && P.tau_bot && j >= P.js_stress) {  // :903-912
+  if (!REM && P.tau_bot && j >= P.js_stress && !tau_done) {  // :903-912
     double t = P.H_to_RZ * (P.x[(long long)(nz - 1) * pl + g] * P.a[(long long)nz * pl + g]);
     if (P.Ray) for (int k = 1; k <= nz; ++k) { const long long o = (long long)(k - 1) * pl + g; t = t + P.H_to_RZ * (P.Ray[o] * P.x[o]); }
     P.tau_bot[g] = t;
   }
-  if (!REM && P.lim_on && j >= P.js_lim) {
-    // vertvisc_limit_vel without truncation files (:3016-3037 for u, :3090-3111 for v): the CFL number of the face velocity in the
-    // cell it flows out of; a truncated velocity is the one of CFL 0.9*CFL_trunc.  The stress above used the untruncated velocities.
+  if (!REM && P.lim_on && j >= P.js_lim && !lim_done) {
+    // the separate pass (land columns, columns with Rayleigh drag): the stress above used the untruncated velocities
     const long long sB = DIR ? G.pitch : 1;
-    const double dtf = dt * P.face[g];
-    const double IA0 = P.IareaT[g], IA1 = P.IareaT[g + sB];
+    const double dtf = dt * P.face[g], IA0 = P.IareaT[g], IA1 = P.IareaT[g + sB], A0 = P.areaT[g], A1 = P.areaT[g + sB];
     for (int k = 1; k <= nz; ++k) {
       const long long o = (long long)(k - 1) * pl + g;
       const double u = P.x[o];
-      double un = u;
-      bool trunc = false;
-      if (fabs(u) < P.vel_underflow) un = 0.0;
-      else if (P.cfl_based) {
-        if (P.CFL_trunc > 0.0) {
-          if ((u * dtf) * IA1 < -P.CFL_trunc) { un = (-0.9 * P.CFL_trunc) * (P.areaT[g + sB] / dtf); trunc = true; }
-          else if ((u * dtf) * IA0 > P.CFL_trunc) { un = (0.9 * P.CFL_trunc) * (P.areaT[g] / dtf); trunc = true; }
-        }
-      } else if (P.maxvel > 0.0 && fabs(u) > P.maxvel) { un = copysign(0.9 * P.maxvel, u); trunc = true; }
+      const double un = vv_limit(P, u, dtf, IA0, IA1, A0, A1, P.h != nullptr, P.h ? P.h[o] + P.h[o + sB] : 0.0);
       if (__double_as_longlong(un) != __double_as_longlong(u)) P.x[o] = un;
-      if (trunc && P.h && (P.h[o] + P.h[o + sB] > P.H_report)) atomicAdd(P.ntrunc, 1ULL);
     }
   }
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, final GPU call: the whole GPU suite, smoke(), the bench line as the driver runs it, CorAdCalc 3 vs 4 CTAs/SM
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02_gpu_suite_final.log 2>&1; echo "rc=$?" >> gpurun_out/r02_gpu_suite_final.log )
+( timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_gpu_suite_final.log 2>&1; echo "rc=$?" >> gpurun_out/r02_gpu_suite_final.log )
 tail -5 gpurun_out/r02_gpu_suite_final.log
 ( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/r02_smoke.log ); tail -2 gpurun_out/r02_smoke.log
 for m in 3 4; do ( MOM6CU_CORAD_MINB=$m timeout 200 python tools/prof_stage.py corad 1440 1080 75 3 2>&1 | tail -1 | sed "s/^/MINB=$m /" ) >> gpurun_out/r02_corad_minb.log; done; cat gpurun_out/r02_corad_minb.log
