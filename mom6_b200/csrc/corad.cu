@@ -381,8 +381,10 @@ int m6_coradcalc_run(mom6cu_ctx* c, const CorAdDev& D) {
   K.M = c->grid;
   const int nI = d.iec - (d.isc - 1) + 1, nJ = d.jec - (d.jsc - 1) + 1;
   dim3 grid(c->g.nk, (nI + CA_TX - 1) / CA_TX, (nJ + CA_TY - 1) / CA_TY);
-  static int minb = -1;   // MOM6CU_CORAD_MINB=4: compiled for 4 CTAs/SM (64 registers, spills to L1) for A/B measurements
-  if (minb < 0) { const char* e = getenv("MOM6CU_CORAD_MINB"); minb = e ? atoi(e) : 3; }
+  // 4 CTAs/SM (64 registers, a few spills to L1) measured 4.37 ms against 5.24 ms for 3 CTAs/SM (80 registers) at 1440x1080x75
+  // (profiles/r02_corad_minb.log); MOM6CU_CORAD_MINB=3 selects the latter for A/B measurements
+  static int minb = -1;
+  if (minb < 0) { const char* e = getenv("MOM6CU_CORAD_MINB"); minb = e ? atoi(e) : 4; }
   if (minb == 4) M6_LAUNCH(c, (corad_kernel<CA_TX, CA_TY, 4>), grid, CA_TX * CA_TY, 0, c->g, K);
   else M6_LAUNCH(c, (corad_kernel<CA_TX, CA_TY>), grid, CA_TX * CA_TY, 0, c->g, K);
   M6_CUDA(c, cudaGetLastError());
