@@ -4,7 +4,8 @@
     ref["mom_continuity_ppm"]["continuity_ppm"](u, v, hin, h, uh, vh, dt, G, GV, US, CS, OBC, pbv, ...)
 
 The sources are read where they lie under REFERENCE_ROOT (/root/reference, absent on the GPU box: callers skip); the generated
-Python is cached under oracle/_ref/f90py/ (git-ignored, never committed: it is derived from the reference's text)."""
+Python lives in memory only.  F90RUN_KEEP=1 also writes it to oracle/_ref/f90py/ (git-ignored, never committed: it is derived from
+the reference's text) so that tracebacks show the generated lines while debugging."""
 import hashlib
 import os
 
@@ -41,14 +42,18 @@ def load(paths, extra_stubs=None, verbose=False):
         mods = parse_file(full, cpp)
         prog.add(mods)
         srcs.append((full, mods))
-    os.makedirs(CACHE, exist_ok=True)
+    keep = os.environ.get("F90RUN_KEEP", "0") == "1"
+    if keep:
+        os.makedirs(CACHE, exist_ok=True)
     spaces = {}
     for full, mods in srcs:
         for m in mods:
             code = prog.gen_module(m)
-            out = os.path.join(CACHE, m.name + ".py")
-            with open(out, "w") as f:
-                f.write(code)
+            out = "<f90run:%s>" % m.name
+            if keep:
+                out = os.path.join(CACHE, m.name + ".py")
+                with open(out, "w") as f:
+                    f.write(code)
             ns = {"__name__": "f90ref." + m.name}
             exec(compile(code, out, "exec"), ns)
             spaces[m.name] = ns

@@ -1,8 +1,7 @@
 """Fortran-subset -> Python translator for the reference's own sources.  TEST INFRASTRUCTURE ONLY (see oracle/README.md).
 
 There is no Fortran compiler in this image, so the reference cannot be built here.  This module is the stand-in: it reads the
-.F90 files where they lie under /root/reference (nothing is copied into the repo; the generated Python goes to oracle/_ref/,
-which is git-ignored), runs the few cpp directives MOM6 uses (MOM_memory.h, symmetric dynamic memory), parses the subset of
+.F90 files where they lie under /root/reference (nothing is copied into the repo; the generated Python lives in memory), runs the few cpp directives MOM6 uses (MOM_memory.h, symmetric dynamic memory), parses the subset of
 free-form Fortran 90 the hot-path modules are written in, and emits Python in which every floating-point expression is
 evaluated in binary64 in exactly the order the source text prescribes.  tests/test_reference_f90.py runs those translated
 reference routines on seeded inputs and compares the C++ oracle with them bit for bit; that is what pins the oracle.

@@ -30,14 +30,17 @@ _LOADED = {}   # the translated shadow modules are kept across cases; only the C
 
 @pytest.fixture()
 def shadow(oracle):
-    """installs the shims under oracle/_ref/shims and points oracle/f90run/stages.py at the shadow copies"""
+    """installs the shims in a temporary directory and points oracle/f90run/stages.py at the shadow copies"""
     import sys
     sys.path.insert(0, os.path.join(ROOT, "fortran"))
     import install_shims
     from oracle.f90run import cabi, stages
-    out = os.path.join(ROOT, "oracle", "_ref", "shims")
     if "installed" not in _LOADED:
-        install_shims.install(f90run.REFERENCE_ROOT, out)
+        # the shadow copies contain the reference's text: they live in a temporary directory outside the repository, removed at exit
+        import atexit, shutil, tempfile
+        _LOADED["dir"] = tempfile.mkdtemp(prefix="mom6cu_shims_")
+        atexit.register(shutil.rmtree, _LOADED["dir"], ignore_errors=True)
+        install_shims.install(f90run.REFERENCE_ROOT, _LOADED["dir"])
         _LOADED["installed"] = True
         _LOADED["current"] = {}
         names = cabi.Abi(oracle, None, None, None).stubs()
@@ -45,6 +48,7 @@ def shadow(oracle):
         _LOADED["stubs"] = {k: ((lambda *a, _k=k: _LOADED["current"]["stubs"][_k](*a)) if callable(v) else v) for k, v in names.items()}
         _LOADED["plain"] = dict(stages._REF)
         _LOADED["shadow"] = {}
+    out = _LOADED["dir"]
     plain = dict(stages._REF)
     _LOADED["plain"].update(plain)
 
