@@ -10,14 +10,20 @@ from mom6_b200 import synthetic
 CASES = {}
 
 
+# cases whose reference run takes minutes in the translator: run by tests/golden/make_reference_digests.py (and by
+# tests/test_reference_f90.py with F90RUN_SLOW=1); the oracle and the CUDA path are always compared with their digests
+SLOW = set()
+
 DEVICE_REFUSES = {
     # options the oracle restates (and the reference run confirms) but the CUDA path declines with MOM6CU_ERR_UNSUPPORTED
     "mixedlayer_restrat/options03": "MLE_TAIL_DH /= 0",
 }
 
 
-def case(name, stage, shape, outputs, **kw):
+def case(name, stage, shape, outputs, slow=False, **kw):
     CASES[name] = dict(stage=stage, shape=shape, outputs=outputs, kw=kw)
+    if slow:
+        SLOW.add(name)
 
 
 def _copy(x):
@@ -249,6 +255,18 @@ def ale_collect(dom, ale, dcs, a):
     out = collect(dom, ALE_OUT, src, {})
     out["zero_ok:old_grid_weight"] = np.array([ale["regridCS"]["old_grid_weight"]])
     return out
+
+
+# ---- the OM4 layer count (75): the nk-dependent kernel variants of the bench against the reference itself ------------------------
+case("step/75_layers_plm_store_CAu", "step", (12, 10, 75), STEP_OUT, slow=True, land_blocks=1, store_CAu=1,
+     pgf=dict(reconstruct=1, Recon_Scheme=1))
+case("pressure_force/75_layers_ppm", "pressure_force", (12, 10, 75), PF_OUT, slow=True, land_blocks=1, reconstruct=1, Recon_Scheme=2)
+case("vertvisc_family/75_layers", "vertvisc_family", (12, 10, 75), VV_OUT, slow=True, land_blocks=1, with_Ray=True)
+case("ale/75_layers", "ale", (12, 10, 75), ALE_OUT, slow=True, land_blocks=1)
+case("thickness_diffuse/75_layers", "thickness_diffuse", (12, 10, 75), TD_OUT, slow=True, land_blocks=1, use_FGNV_streamfn=1,
+     use_variable_mixing=1)
+case("advect_tracer/75_layers", "advect_tracer", (12, 10, 75), AD_OUT, slow=True, land_blocks=1, scheme=1, cfl=2.5)
+case("btstep/75_layers", "btstep", (12, 10, 75), BT_OUT, slow=True, land_blocks=1)
 
 
 def step_collect(dom, cs, a):

@@ -16,10 +16,14 @@ from oracle import f90run
 
 pytestmark = pytest.mark.skipif(not f90run.available(), reason="the reference tree is not present")
 
-from refcases import CASES, run_case  # noqa: E402
+import os  # noqa: E402
+
+from refcases import CASES, SLOW, run_case  # noqa: E402
+
+LIVE = sorted(n for n in CASES if n not in SLOW or os.environ.get("F90RUN_SLOW", "0") == "1")
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", LIVE)
 def test_oracle_matches_translated_reference(oracle, name):
     ref_out, orc_out = run_case(oracle, name, want_ref=True)
     bad = []
