@@ -46,7 +46,11 @@ SHIMS = {
     "src/core/MOM_PressureForce.F90": dict(
         hooks=[], public=["PressureForce_send_cs_mom6cu"],
         uses=["use MOM_PressureForce_FV, only : PressureForce_FV_send_cs_mom6cu"]),
-    "src/parameterizations/vertical/MOM_vert_friction.F90": dict(hooks=[], public=["vertvisc_send_cs_mom6cu"], uses=[]),
+    "src/parameterizations/vertical/MOM_vert_friction.F90": dict(
+        hooks=[("vertvisc_coef", "u, v, h, dz, forces, visc, tv, dt, G, GV, US, CS, OBC, VarMix"),
+               ("vertvisc", "u, v, h, forces, visc, dt, OBC, ADp, CDp, G, GV, US, CS, taux_bot, tauy_bot, fpmix, Waves"),
+               ("vertvisc_remnant", "visc, visc_rem_u, visc_rem_v, dt, G, GV, US, CS")],
+        public=["vertvisc_send_cs_mom6cu"], uses=[]),
     "src/parameterizations/lateral/MOM_hor_visc.F90": dict(
         hooks=[("horizontal_viscosity", "u, v, h, uh, vh, diffu, diffv, MEKE, VarMix, G, GV, US, CS, tv, dt, OBC, BT, TD, ADp, hu_cont, hv_cont, STOCH")],
         public=["hor_visc_send_cs_mom6cu"], uses=[]),

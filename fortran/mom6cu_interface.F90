@@ -641,10 +641,9 @@ module mom6cu_interface
       type(c_ptr), value :: h_u
       type(c_ptr), value :: h_v
     end function mom6cu_vertvisc_get_coef
-    integer(c_int) function mom6cu_vertvisc_ntrunc(ctx, ntrunc) bind(C, name="mom6cu_vertvisc_ntrunc")
-      import :: c_int, c_long_long, c_ptr
+    integer(c_long_long) function mom6cu_vertvisc_ntrunc(ctx) bind(C, name="mom6cu_vertvisc_ntrunc")
+      import :: c_long_long, c_ptr
       type(c_ptr), value :: ctx
-      integer(c_long_long), intent(out) :: ntrunc
     end function mom6cu_vertvisc_ntrunc
     integer(c_long_long) function mom6cu_launch_count(ctx) bind(C, name="mom6cu_launch_count")
       import :: c_long_long, c_ptr

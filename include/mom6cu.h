@@ -333,8 +333,9 @@ typedef struct mom6cu_vertvisc_cs {
   double maxvel, CFL_trunc;
 } mom6cu_vertvisc_cs;
 int mom6cu_set_cs_vertvisc(mom6cu_ctx* ctx, const mom6cu_vertvisc_cs* CS);
-/* CS%ntrunc: the number of velocity truncations vertvisc has made in this context so far (needs h in the vertvisc call) */
-int mom6cu_vertvisc_ntrunc(mom6cu_ctx* ctx, long long* ntrunc);
+/* CS%ntrunc: the number of velocity truncations vertvisc has made in this context so far (needs h in the vertvisc call);
+ * -1 on error (message via mom6cu_last_error) */
+long long mom6cu_vertvisc_ntrunc(mom6cu_ctx* ctx);
 /* vertvisc_coef(u, v, h, dz, forces, visc, tv, dt, G, GV, US, CS, OBC, VarMix)  MOM_vert_friction.F90:1357: sets the
  * resident CS%a_u, CS%a_v (nk+1 interfaces) and CS%h_u, CS%h_v (nk layers). */
 typedef struct mom6cu_vertvisc_coef_args {

@@ -413,7 +413,8 @@ def bind(lib):
     lib.mom6cu_set_cs_vertvisc.argtypes = [vp, C.POINTER(VertviscCS)]
     lib.mom6cu_vertvisc_coef.argtypes = [vp, C.POINTER(VertviscCoefArgs)]
     lib.mom6cu_vertvisc_get_coef.argtypes = [vp, vp, vp, vp, vp]
-    lib.mom6cu_vertvisc_ntrunc.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.mom6cu_vertvisc_ntrunc.argtypes = [vp]
+    lib.mom6cu_vertvisc_ntrunc.restype = C.c_longlong
     lib.mom6cu_vertvisc.argtypes = [vp, C.POINTER(VertviscArgs)]
     lib.mom6cu_vertvisc_remnant.argtypes = [vp, vp, vp, vp, vp, C.c_double]
     lib.mom6cu_ale_regrid.argtypes = [vp, C.POINTER(RegriddingCS), vp, vp, vp]

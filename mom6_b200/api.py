@@ -255,9 +255,10 @@ def _ctx_methods():
 
     def vertvisc_ntrunc(self):
         """CS%ntrunc: velocity truncations made by vertvisc_limit_vel (MOM_vert_friction.F90:2926) in this context so far."""
-        n = C.c_longlong(0)
-        self._check(self.lib.mom6cu_vertvisc_ntrunc(self._h, C.byref(n)))
-        return int(n.value)
+        n = int(self.lib.mom6cu_vertvisc_ntrunc(self._h))
+        if n < 0:
+            self._check(4)
+        return n
 
     def vertvisc(self, args):
         """vertvisc, MOM_vert_friction.F90:557."""

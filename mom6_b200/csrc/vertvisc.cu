@@ -481,16 +481,16 @@ int m6_vertvisc_run(mom6cu_ctx* c, const VvDev& D) {
   return 0;
 }
 
-extern "C" int mom6cu_vertvisc_ntrunc(mom6cu_ctx* c, long long* ntrunc) {
-  if (!c || !ntrunc) return MOM6CU_ERR_BAD_ARG;
-  M6_CUDA(c, cudaSetDevice(c->device));
+extern "C" long long mom6cu_vertvisc_ntrunc(mom6cu_ctx* c) {
+  if (!c) return -1;
   const double* p = c->buf("vv.ntrunc", 1);
-  if (!p) return MOM6CU_ERR_CUDA;
   unsigned long long n = 0;
-  M6_CUDA(c, cudaStreamSynchronize(c->stream));
-  M6_CUDA(c, cudaMemcpy(&n, p, sizeof(n), cudaMemcpyDeviceToHost));
-  *ntrunc = (long long)n;
-  return 0;
+  if (!p || cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+      cudaMemcpy(&n, p, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    c->fail(MOM6CU_ERR_CUDA, "vertvisc_ntrunc: the truncation counter could not be read");
+    return -1;
+  }
+  return (long long)n;
 }
 
 extern "C" int mom6cu_vertvisc(mom6cu_ctx* c, const mom6cu_vertvisc_args* a) {

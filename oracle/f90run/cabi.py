@@ -189,7 +189,41 @@ class Abi:
             self.back(pairs)
             c.regridcs.old_grid_weight = float(cs["regridCS"]["old_grid_weight"])
 
+        def vertvisc_coef(ctx, a):
+            pairs = []
+            d = self.to_dict(a, L.VertviscCoefArgs, pairs)
+            nk = d["h"].shape[0]
+            zu, zv = np.zeros((nk + 1,) + d["u"].shape[1:]), np.zeros((nk + 1,) + d["v"].shape[1:])
+            self.coef = [zu, zv, np.zeros_like(d["u"]), np.zeros_like(d["v"])]     # the library's resident CS%a_u, a_v, h_u, h_v
+            o.vertvisc_coef(dom, grid, gv, self.css["vertvisc"], d, *self.coef)
+
+        def vertvisc_get_coef(ctx, a_u, a_v, h_u, h_v):
+            for fa, x in zip((a_u, a_v, h_u, h_v), self.coef):
+                if fa is not None:
+                    fa.assign(FArray.from_numpy(x))
+
+        def vertvisc(ctx, a):
+            pairs = []
+            d = self.to_dict(a, L.VertviscArgs, pairs)
+            self.ntrunc = getattr(self, "ntrunc", 0) + o.vertvisc(dom, grid, gv, self.css["vertvisc"], d, *self.coef)
+            self.back(pairs)
+
+        def vertvisc_remnant(ctx, Ray_u, Ray_v, vru, vrv, dt):
+            pairs = []
+
+            def arr(x):
+                if x is None:
+                    return None
+                y = np.ascontiguousarray(x.to_numpy(), dtype=np.float64)
+                pairs.append((x, y))
+                return y
+            o.vertvisc_remnant(dom, grid, self.css["vertvisc"], arr(vru), arr(vrv), float(dt), *self.coef, arr(Ray_u), arr(Ray_v))
+            self.back(pairs)
+
         return {
+            "mom6cu_vertvisc_coef": run("vertvisc_coef", vertvisc_coef), "mom6cu_vertvisc_get_coef": run("vertvisc_get_coef", vertvisc_get_coef),
+            "mom6cu_vertvisc": run("vertvisc", vertvisc), "mom6cu_vertvisc_remnant": run("vertvisc_remnant", vertvisc_remnant),
+            "mom6cu_vertvisc_ntrunc": lambda ctx: getattr(self, "ntrunc", 0),
             "mom6cu_ale_regridding_and_remapping": run("ale_regridding_and_remapping", ale),
             "mom6cu_advect_tracer": run("advect_tracer", advect_tracer),
             "mom6cu_mixedlayer_restrat": run("mixedlayer_restrat", mixedlayer_restrat),

@@ -102,12 +102,14 @@ def test_hooked_step_equals_the_reference_step(shadow, name):
                                   "mixedlayer_restrat/options01", "thickness_diffuse/options01", "thickness_diffuse/options02",
                                   "thickness_diffuse/options05", "tracer_hordiff/options01", "tracer_hordiff/options02",
                                   "tracer_hordiff/options03", "ale/ppm_h4_aux_vars", "ale/plm_no_store_CAu",
-                                  "ale/ppm_ih4_no_time_filter", "ale/pcm_no_aux_vars"])
+                                  "ale/ppm_ih4_no_time_filter", "ale/pcm_no_aux_vars", "vertvisc_family/options00",
+                                  "vertvisc_family/options01", "vertvisc_family/options09", "vertvisc_family/truncation_cfl_0.2_ray"])
 def test_hooked_stage_equals_the_reference_stage(shadow, name):
     inputs = refcases.build(name)
     want = refcases.run_reference(name, inputs)
     abi = shadow(*inputs[:3])
     got = refcases.run_reference(name, inputs)
-    entry = {"ale": "ale_regridding_and_remapping"}.get(refcases.CASES[name]["stage"], refcases.CASES[name]["stage"])
+    entry = {"ale": "ale_regridding_and_remapping", "vertvisc_family": "vertvisc"}.get(refcases.CASES[name]["stage"],
+                                                                                       refcases.CASES[name]["stage"])
     assert abi.calls.count(entry) == 1, abi.calls
     _same(want, got)
