@@ -176,6 +176,9 @@ case("step/ppm_reconstruction_begw_split_bottom_stress", "step", (12, 10, 4), ST
      split_bottom_stress=1, pgf=dict(reconstruct=1, Recon_Scheme=2))
 case("step/project_velocity_no_land", "step", (12, 10, 4), STEP_OUT, land_blocks=0, BT_project_velocity=1)
 case("step/cfl_truncation_in_vertvisc", "step", (12, 10, 4), STEP_OUT, land_blocks=2, vv=dict(CFL_trunc=0.001))
+case("step/y_first_doubly_periodic", "step", (12, 10, 4), STEP_OUT, land_blocks=1, first_direction=1, cyclic_y=True, store_CAu=1)
+case("step/arakawa_hsu_bt_strong_drag_linear_eos", "step", (12, 10, 4), STEP_OUT, land_blocks=2, Sadourny=0, strong_drag=1,
+     pgf=dict(EOS_form=1, reconstruct=1, Recon_Scheme=2))
 
 
 # ---- ALE_regridding_and_remapping (MOM.F90:1751) --------------------------------------------------------------------------
