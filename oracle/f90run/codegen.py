@@ -269,6 +269,10 @@ class ProcGen:
             if args is None:
                 if v is not None and v.dims is not None:
                     self.emit(ind, f"{mangle(name)} = _rt.assign_whole({mangle(name)}, {self.ex(R)})", ln)
+                elif v is not None and v.base in ("type", "class") and not v.pointer:
+                    # intrinsic (or overloaded, component-wise) assignment of a derived type: the components are copied into the
+                    # existing object, so that a dummy argument's actual and every other reference to it see the new value
+                    self.emit(ind, f"{mangle(name)} = _rt.assign_derived({mangle(name)}, {self.ex(R)})", ln)
                 else:
                     self.emit(ind, f"{mangle(name)} = {self.coerce(v, R)}", ln)
                 return
@@ -714,14 +718,31 @@ class Program:
                 pg = ProcGen(self, mod, _EmptyProc(mod))
                 try:
                     code = pg.coerce(v, parse_expr(v.init[1]))
-                    out.append(f"try:\n    {n} = {code}\nexcept NameError:\n    {n} = None")
+                    out.append(f"try:\n    {n} = {code}\nexcept (NameError, AttributeError, TypeError):\n    {n} = None")
                 except (SyntaxError, NotImplementedError):
+                    out.append(f"{n} = None")
+            elif v.init is not None and v.init[0] == "val" and v.base in ("real", "integer", "logical"):
+                pg = ProcGen(self, mod, _EmptyProc(mod))
+                try:
+                    _, _, full = pg.bounds(v.dims)
+                    code = pg.ex(parse_expr(v.init[1]))
+                    out.append(f"try:\n    {n} = _rt.alloc({v.kind!r}, ({', '.join('(%s, %s)' % b for b in full)},))\n"
+                               f"    {n}.assign({code})\nexcept (NameError, AttributeError, TypeError):\n    {n} = None")
+                except (SyntaxError, NotImplementedError, TypeError):
                     out.append(f"{n} = None")
             else:
                 out.append(f"{n} = None")
         out.append("")
         for P in mod.procs.values():
             out.append(ProcGen(self, mod, P).generate())
+        for op, specs in mod.operators.items():
+            for sname in specs:
+                P = mod.procs.get(sname)
+                if P is None or not P.args:
+                    continue
+                v0 = P.vars.get(P.args[0])
+                if v0 is not None and v0.tname:
+                    out.append(f"_rt.register_op({op!r}, {mangle(v0.tname)!r}, {mangle(sname)})")
         for tname, comps in mod.types.items():
             out.append(f"def _new_{mangle(tname)}():")
             ext = mod.type_ext.get(tname)

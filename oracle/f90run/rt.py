@@ -16,6 +16,13 @@ class FortranStop(Exception):
     pass
 
 
+OPS = {}
+
+
+def register_op(op, tname, f):
+    OPS[(op, tname)] = f
+
+
 class NS:
     """A derived-type instance: components are attributes (lower case); an unset pointer / absent component reads as None."""
 
@@ -30,6 +37,16 @@ class NS:
 
     def __repr__(self):
         return "NS(" + ", ".join(sorted(self.__dict__)) + ")"
+
+    # operators overloaded for a derived type (interface operator(+) ...): dispatched on the type of the left operand
+    def __add__(self, o):
+        return OPS[("+", self.__dict__.get("_type"))](self, o)
+
+    def __sub__(self, o):
+        return OPS[("-", self.__dict__.get("_type"))](self, o)
+
+    def __mul__(self, o):
+        return OPS[("*", self.__dict__.get("_type"))](self, o)
 
 
 _PYKW = {"is", "in", "as", "or", "and", "not", "if", "else", "for", "while", "def", "del", "from", "global", "lambda", "pass",
@@ -683,3 +700,33 @@ def random_number(x):
             x.v[o] = _rand()
         return x
     return _rand()
+
+
+def _copy_value(x):
+    if type(x) is FArray:
+        out = FArray.alloc(x.kind, [(l, l + n - 1) for l, n in zip(x.lb, x.shape)])
+        out.v[:] = [(_copy_value(e) if isinstance(e, NS) else e) for e in x.tolist()]
+        return out
+    if isinstance(x, NS):
+        out = NS()
+        for k, v in x.__dict__.items():
+            out.__dict__[k] = v if callable(v) else _copy_value(v)
+        return out
+    return x
+
+
+def assign_derived(cur, x):
+    """a = b for derived types: value semantics.  Array and nested-type components are copied; pointer components (which the
+    translator cannot tell from allocatable ones at run time) are copied too, which is right wherever the copy is not modified
+    through the pointer afterwards."""
+    if x is None or not isinstance(x, NS):
+        return x
+    new = _copy_value(x)
+    if cur is None or not isinstance(cur, NS):
+        return new
+    # type-bound procedures are bound to the object they were created for: keep the target's own bindings
+    keep = {k: v for k, v in cur.__dict__.items() if callable(v)}
+    cur.__dict__.clear()
+    cur.__dict__.update(new.__dict__)
+    cur.__dict__.update(keep)
+    return cur

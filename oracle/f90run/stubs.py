@@ -54,5 +54,8 @@ NAMES = {
     "diag_update_remap_grids": _noop, "safe_alloc_ptr": _noop, "safe_alloc_alloc": _noop, "query_debugging_checks": _noop,
     "diag_save_grids": _noop, "diag_restore_grids": _noop, "diag_copy_diag_to_storage": _noop,
     "time_type": rt.NS, "get_diag_time_end": lambda *a, **k: 0.0,
+    "int64": 8, "int32": 4, "real64": 8, "real32": 4,
+    "num_pes": lambda: 1, "pe_here": lambda: 0, "root_pe": lambda: 0, "sync_pes": _noop, "broadcast": _noop,
+    "any_across_pes": lambda x: bool(x), "all_across_pes": lambda x: bool(x),
     "uppercase": lambda s_: s_.upper(), "lowercase": lambda s_: s_.lower(), "stdout": 6, "stderr": 0,
 }

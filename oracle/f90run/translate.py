@@ -588,6 +588,7 @@ class Module:
         self.types = {}     # type name -> {component name -> Var}
         self.type_ext = {}  # type name -> parent type name or None
         self.type_binds = {}  # type name -> {binding name -> procedure name}
+        self.operators = {}   # '+', '-', '=' ... -> [module procedures that overload it for derived types]
 
 
 def find_assign_simple(st):
@@ -684,6 +685,18 @@ def _parse_module_spec(sts, i, mod):
             mod.types[m.group(1)] = comps
             mod.type_ext[m.group(1)] = ext.group(1) if ext else None
             mod.type_binds[m.group(1)] = binds
+            i += 1
+            continue
+        mo = re.match(r"interface\s+(operator|assignment)\s*\(\s*([^)]+?)\s*\)$", st)
+        if mo:
+            specs = []
+            i += 1
+            while not re.match(r"end\s*interface", sts[i][1]):
+                mm = re.match(r"module\s+procedure\s+(.*)$", sts[i][1])
+                if mm:
+                    specs += [x.strip() for x in mm.group(1).split(",")]
+                i += 1
+            mod.operators.setdefault(mo.group(2), []).extend(specs)
             i += 1
             continue
         m = re.match(r"(?:abstract\s+)?interface\s*([a-z_]\w*)?$", st)
