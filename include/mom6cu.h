@@ -657,7 +657,9 @@ int mom6cu_efp_sum_across_pes(mom6cu_ctx* ctx, mom6cu_efp* EFPs, int nval);
 /* hchksum / uvchksum / Bchksum, src/framework/MOM_checksums.F90: chksum_h_2d :387, chksum_h_3d :1413, chksum_u_2d :1005,
  * chksum_u_3d :1782, chksum_v_2d :1209, chksum_v_3d :1986, chksum_B_2d :688, chksum_B_3d :1586; bitcount :2678.
  * stagger 0=h,1=u,2=v,3=q; nk = 1 for the 2-D forms.  haloshift < 0 means the full halo (:470); symmetric / omit_corners as
- * the optional arguments (0 = absent); scale = 1 means absent.
+ * the optional arguments (0 = absent); scale = 1 means absent.  nk > 1 selects the _3d form, which matters at B points:
+ * chksum_B_3d shifts its SW / SE / NW windows by haloshift+1 with or without `symmetric` (:1698-1706) and, with omit_corners and
+ * `symmetric`, its S and W windows too (:1712-1718); chksum_B_2d does neither (:797-809).  Both are reproduced as they are.
  *   bc[0] = bc0; then, in the order the reference prints them:
  *     kind 1 (haloshift 0, not symmetric): nothing else           (chk_sum_msg1)
  *     kind 2 (corners):  bc[1..4] = SW, SE, NW, NE                 (chk_sum_msg5)

@@ -433,7 +433,10 @@ extern "C" int mom6cu_chksum(mom6cu_ctx* c, const double* array, int stagger, in
   int win[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
   int nwin = 1;
   const bool plain = (stagger == ST_H) ? (hshift == 0) : ((hshift == 0) && !sym);
-  const int ex = (sym && su) ? 1 : 0, ey = (sym && sv) ? 1 : 0;
+  // chksum_B_3d differs from chksum_B_2d (MOM_checksums.F90:1698-1718 against :797-809): its corner windows take the extra row and
+  // column with or without `symmetric`, and with omit_corners its S and W windows widen under `symmetric`.  nk > 1 = a rank-3 array.
+  const bool q3 = (stagger == ST_Q && nk > 1);
+  const int ex = ((sym || q3) && su) ? 1 : 0, ey = ((sym || q3) && sv) ? 1 : 0;
   if (plain) *kind = 1;
   else if (hshift == 0 && stagger == ST_U) { *kind = 4; nwin = 2; win[1][0] = -1; }
   else if (hshift == 0 && stagger == ST_V) { *kind = 5; nwin = 2; win[1][1] = -1; }
@@ -446,9 +449,9 @@ extern "C" int mom6cu_chksum(mom6cu_ctx* c, const double* array, int stagger, in
   } else {
     *kind = 3; nwin = 5;
     win[1][1] = hshift;                                          // N
-    win[2][1] = -hshift - ((stagger == ST_V && sym) ? 1 : 0);    // S
-    win[3][0] = hshift;                                          // E
-    win[4][0] = -hshift - ((stagger == ST_U && sym) ? 1 : 0);    // W
+    win[2][1] = -hshift - (((stagger == ST_V || q3) && sym) ? 1 : 0);    // S
+    win[3][0] = hshift;                                                  // E
+    win[4][0] = -hshift - (((stagger == ST_U || q3) && sym) ? 1 : 0);    // W
   }
   Stager S(c, "chk.");
   int rc;

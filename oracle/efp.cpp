@@ -10,7 +10,10 @@
 //   bitcount :2678-2685.
 // PARITY: PINNED for the sums by the reference's own unit test (config_src/drivers/unit_tests/test_reproducing_sum.F90: the
 // exact sum of 1..N, order invariance under random swaps, fast == checked conversion, |standard - reproducing| bound), see
-// tests/test_oracle_efp.py.  The checksums have no vectors in the reference: "parity unpinned".
+// tests/test_oracle_efp.py, and by running MOM_coms.F90 itself (tests/test_reference_f90.py::test_efp_sums_match_the_translated_
+// reference).  The checksums: PINNED BY A REFERENCE RUN -- MOM_checksums.F90 executed by oracle/f90run, all four staggers, rank 2 and
+// 3, halo shifts, symmetric / omit_corners, scaled or not, statistics (tests/refcases.py "diag/chksum").  That run found that
+// chksum_B_3d is not chksum_B_2d with a k loop (see oracle_chksum below).
 #include "oracle.h"
 #include "efp.hpp"
 #include <cmath>
@@ -345,7 +348,11 @@ extern "C" int oracle_chksum(const mom6cu_domain* d, const double* array, int st
   const bool plain = (stagger == 0) ? (hshift == 0) : ((hshift == 0) && !sym);
   if (plain) { *kind = 1; return 0; }
   const bool do_corners = !omit_corners;
-  const int ex = (sym && su) ? 1 : 0, ey = (sym && sv) ? 1 : 0;  // the extra row / column of the symmetric forms
+  // chksum_B_3d is not chksum_B_2d with a k loop: its corner windows take the extra row and column whether or not `symmetric` is
+  // set (:1698-1706, both arms of the IF are the same), and with omit_corners its S and W windows widen under `symmetric`
+  // (:1712-1718) where the 2-d form's never do (:806-809).  A rank-3 array is what nk > 1 stands for here.
+  const bool q3 = (stagger == 3 && nk > 1);
+  const int ex = ((sym || q3) && su) ? 1 : 0, ey = ((sym || q3) && sv) ? 1 : 0;  // the extra row / column of the symmetric forms
   if (hshift == 0 && stagger == 1) { bc[1] = subchk(-hshift - 1, 0); *kind = 4; return 0; }  // chksum_u :1916-1918
   if (hshift == 0 && stagger == 2) { bc[1] = subchk(0, -hshift - 1); *kind = 5; return 0; }  // chksum_v :1325-1327
   if (do_corners) {
@@ -355,9 +362,9 @@ extern "C" int oracle_chksum(const mom6cu_domain* d, const double* array, int st
     bc[4] = subchk(hshift, hshift);              // NE
     *kind = 2;
   } else {
-    const int bS = subchk(0, -hshift - ((stagger == 2 && sym) ? 1 : 0));  // only the v form widens S (:1340-1344), the u form W
-    const int bE = subchk(hshift, 0);
-    const int bW = subchk(-hshift - ((stagger == 1 && sym) ? 1 : 0), 0);
+    const int bS = subchk(0, -hshift - (((stagger == 2 || q3) && sym) ? 1 : 0));  // the v forms widen S (:1340-1344), the u forms W,
+    const int bE = subchk(hshift, 0);                                              // the 3-d B form both
+    const int bW = subchk(-hshift - (((stagger == 1 || q3) && sym) ? 1 : 0), 0);
     const int bN = subchk(0, hshift);
     bc[1] = bN; bc[2] = bS; bc[3] = bE; bc[4] = bW;
     *kind = 3;

@@ -32,9 +32,11 @@ def _selfhash():
     return h.hexdigest()[:16]
 
 
-def load(paths, extra_stubs=None, verbose=False):
-    """Translate and link the given reference source files.  -> {module name: namespace dict}"""
+def load(paths, extra_stubs=None, verbose=False, expose=()):
+    """Translate and link the given reference source files.  -> {module name: namespace dict}.  expose: names of procedures whose
+    local variables are kept at their final RETURN, as ns["_SAVE"]["<name>.__locals__"] (for results the reference only prints)."""
     prog = Program()
+    prog.expose = set(expose)
     srcs = []
     for p in paths:
         full = os.path.join(REFERENCE_ROOT, p)

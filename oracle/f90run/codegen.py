@@ -55,6 +55,7 @@ class ProcGen:
         self.prog, self.mod, self.P = prog, mod, proc
         self.lines = []
         self.globals_assigned = set()
+        self.host_assigned = set()   # an internal procedure's assignments to its host's variables (-> nonlocal)
         self.tmp = 0
         self.ret = None
         # scalar locals with an initialisation in their declaration (or the SAVE attribute) keep their value between calls
@@ -67,10 +68,24 @@ class ProcGen:
         v = self.P.vars.get(name)
         if v is not None:
             return v
+        if self.P.host is not None and name in self.P.host.vars:
+            return self.P.host.vars[name]
         return self.mod.vars.get(name)
 
     def is_local(self, name):
-        return name in self.P.vars
+        if name in self.P.vars:
+            return True
+        if self.P.host is not None and name in self.P.host.vars:   # host association: a variable of the enclosing function
+            self.host_assigned.add(mangle(name))
+            return True
+        return False
+
+    def find_proc(self, name):
+        """what a call to name resolves to: an internal procedure of this one (or a sibling, from inside one), else as Program.find_proc"""
+        for P in (self.P, self.P.host):
+            if P is not None and name in P.internal:
+                return P.internal[name]
+        return self.prog.find_proc(self.mod, name)
 
     def newtmp(self, stem="t"):
         self.tmp += 1
@@ -128,7 +143,11 @@ class ProcGen:
                         if all(t == "i" for t in ts):
                             return "i"
                         return None
-                    f = self.prog.find_proc(self.mod, name)
+                    f = self.find_proc(name)
+                    if isinstance(f, list):  # a generic: a type only if every specific agrees
+                        ks = {(s.vars[s.result].kind if s.kind == "function" and s.vars.get(s.result) is not None
+                               and s.vars[s.result].dims is None else None) for s in f}
+                        return ks.pop() if len(ks) == 1 else None
                     if f is not None and f.kind == "function":
                         rv = f.vars.get(f.result)
                         if rv is not None and rv.dims is None:
@@ -232,7 +251,7 @@ class ProcGen:
             if len(args) == 2:
                 return "(" + self.ex(args[0]) + " is " + self.ex(args[1]) + ")"
             return "(" + self.ex(args[0]) + " is not None)"
-        f = self.prog.find_proc(self.mod, name)
+        f = self.find_proc(name)
         if f is None and name in INTRINSICS:
             return f"_i_{name}(" + ", ".join(self.ex(a) for a in args) + ")"
         return mangle(name) + "(" + ", ".join(self.ex(a) for a in args) + ")"
@@ -376,7 +395,7 @@ class ProcGen:
                     self.designator_store(ind, a[2], "8", ln)
             self.emit(ind, "_rt.random_seed()", ln)
             return
-        f = self.prog.find_proc(self.mod, name)
+        f = self.find_proc(name)
         argtxt = ", ".join(self.ex(a) for a in args)
         if f is None or isinstance(f, list):
             self.emit(ind, f"{mangle(name)}({argtxt})", ln)
@@ -490,7 +509,7 @@ class ProcGen:
         if st == "cycle":
             self.emit(ind, "continue", ln)
             return
-        if st == "continue" or st == "__internal_procedures_skipped__":
+        if st == "continue":
             self.emit(ind, "pass", ln)
             return
         if re.match(r"(write|read|open|close|format|flush|rewind)\b\s*[(*]", st) or re.match(r"print\b\s*['\"(*]", st):
@@ -639,6 +658,11 @@ class ProcGen:
                         pro.append(f"{n} = {self.coerce(v, parse_expr(v.init[1]))}")
                 elif v.pointer:
                     pro.append(f"{n} = None")
+                elif v.dims is not None and v.base == "character" and not v.allocatable:
+                    _, _, full = self.bounds(v.dims)
+                    if all(b is not None for b in full):   # an explicit-shape array of strings, blank until assigned
+                        pro.append(f"{n} = _rt.alloc('o', ({', '.join('(%s, %s)' % b for b in full)},))")
+                        pro.append(f"{n}.v[:] = [''] * len({n}.v)")
                 elif v.dims is None and v.base in ("integer", "real", "logical", "character"):
                     # undefined until assigned; given a value so that it can be passed to an intent(out) dummy argument
                     # (a real starts as NaN, so a use before definition still shows in the results)
@@ -651,8 +675,14 @@ class ProcGen:
         head = [f"def {mangle(P.name)}(" + ", ".join(mangle(a) + "=None" for a in P.args) + f"):  # {self.mod.name}:{P.line}"]
         if self.globals_assigned:
             head.append("    global " + ", ".join(sorted(self.globals_assigned)))
-        out = head + ["    " + p for p in pro] + body + [f"    _SAVE[{P.name + '.' + n!r}] = {n}" for n in self.save_vars] + \
-            ["    return " + self.ret, ""]
+        if self.host_assigned:
+            head.append("    nonlocal " + ", ".join(sorted(self.host_assigned)))
+        for q in P.internal.values():   # internal procedures: nested functions, defined once the host's locals exist
+            pro += ProcGen(self.prog, self.mod, q).generate().split("\n")
+        tail = [f"    _SAVE[{P.name + '.' + n!r}] = {n}" for n in self.save_vars]
+        if P.name in self.prog.expose:   # for tests that compare a procedure's local variables with the oracle's
+            tail.append(f"    _SAVE[{P.name + '.__locals__'!r}] = dict(locals())")
+        out = head + ["    " + p for p in pro] + body + tail + ["    return " + self.ret, ""]
         if P.elemental:
             n = mangle(P.name)
             out.append(f"{n} = _rt.elemental({n}, {[mangle(a) for a in P.args]!r}, {[mangle(a) for a in outs]!r}, {P.kind == 'function'!r})")
@@ -663,6 +693,7 @@ class ProcGen:
 class Program:
     def __init__(self):
         self.modules = {}
+        self.expose = set()   # procedures whose local variables are kept (in _SAVE['<name>.__locals__']) when they return
 
     def bound(self, name):
         """the procedures a type-bound name may resolve to (one per type that binds it); [] if it is not a binding name"""
@@ -787,6 +818,7 @@ class Program:
 class _EmptyProc:
     def __init__(self, mod):
         self.vars, self.args, self.kind, self.result, self.name, self.line, self.body = {}, [], "subroutine", None, "<module>", 0, []
+        self.internal, self.host = {}, None
 
     def out_scalars(self):
         return []

@@ -557,6 +557,16 @@ def _trim(s):
     return s.rstrip()
 
 
+def _transfer(x, mold):
+    """TRANSFER between a real(8) and an integer of the same size (the only use on the path: the bit pattern of a real)"""
+    import struct
+    if type(x) is float and type(mold) is int:
+        return struct.unpack("<q", struct.pack("<d", x))[0]
+    if type(x) is int and type(mold) is float:
+        return struct.unpack("<d", struct.pack("<q", x))[0]
+    raise NotImplementedError("transfer: only real(8) <-> integer(8) scalars")
+
+
 INTRINSICS = {
     "abs": _elemental(abs), "max": _elemental(_max), "min": _elemental(_min), "sqrt": _elemental(_sqrt),
     "sign": _elemental(_sign), "mod": _mod, "modulo": _modulo, "exp": _elemental(_exp), "log": _elemental(_log),
@@ -573,6 +583,7 @@ INTRINSICS = {
     "char": chr, "ichar": ord, "achar": chr, "iachar": ord, "repeat": lambda s_, n: s_ * n, "new_line": lambda c: "\n",
     "btest": lambda i, pos: bool((i >> pos) & 1), "ibset": lambda i, pos: i | (1 << pos), "ibclr": lambda i, pos: i & ~(1 << pos),
     "iand": lambda i, j: i & j, "ior": lambda i, j: i | j, "ishft": lambda i, s: (i << s) if s >= 0 else (i >> -s),
+    "kind": lambda x: 8 if type(x) is float else 4, "popcnt": lambda i: bin(i & 0xFFFFFFFFFFFFFFFF).count("1"), "transfer": _transfer,
 }
 
 

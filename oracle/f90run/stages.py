@@ -790,3 +790,179 @@ def _wide_v(dom, a):
     w = np.zeros((dom.jedw - dom.jsdw + 2, dom.iedw - dom.isdw + 1))
     w[wj:wj + a.shape[0], wi:wi + a.shape[1]] = a
     return FArray.from_numpy(w, (int(dom.isdw), int(dom.jsdw) - 1))
+
+
+class _Time:
+    """time_type (config_src/infra/FMS*/MOM_time_manager.F90, an FMS type) as write_energy uses it: a whole number of seconds with
+    +, -, comparisons, integer * time, time / integer and the integer quotient time / time."""
+    __slots__ = ("s",)
+
+    def __init__(self, s=0):
+        self.s = int(s)
+
+    def __add__(self, o): return _Time(self.s + o.s)
+    def __sub__(self, o): return _Time(abs(self.s - o.s))   # FMS time differences are magnitudes
+    def __mul__(self, n): return _Time(self.s * int(n))
+    __rmul__ = __mul__
+    def __truediv__(self, o): return self.s // o.s if isinstance(o, _Time) else _Time(round(self.s / o))
+    def __lt__(self, o): return self.s < o.s
+    def __le__(self, o): return self.s <= o.s
+    def __gt__(self, o): return self.s > o.s
+    def __ge__(self, o): return self.s >= o.s
+    def __eq__(self, o): return self.s == o.s
+    def __hash__(self): return hash(self.s)
+
+
+class _EnergyFile:
+    """stands in for the MOM_netcdf_file the energies are written to: keeps what write_energy hands to write_field, by variable name"""
+
+    def __init__(self):
+        self.names, self.rows = [], []
+
+    def write_field(self, field, value, reday=None):
+        row = self.rows[-1]
+        row[field.name] = value.to_numpy().copy() if isinstance(value, FArray) else float(value)
+
+    def flush(self):
+        pass
+
+
+def _sum_output_stubs(files):
+    def var_desc(name, units=None, longname=None, hor_grid=None, z_grid=None, **kw):
+        return NS(name=name)
+
+    def open_file(handle, path, vars, novars, fields, *a, **k):
+        for m in range(1, int(novars) + 1):
+            fields.s1(m, NS(name=vars.g1(m).name))
+
+    return dict(set_time=lambda seconds=0, days=0, **k: _Time(int(seconds) + 86400 * int(days)), _new_time_type=lambda: _Time(0),
+                var_desc=var_desc, create_mom_file=open_file, reopen_mom_file=open_file, open_ascii_file=lambda *a, **k: None,
+                call_tracer_stocks=lambda *a, **k: None, array_global_min_max=lambda *a, **k: None, get_time=lambda *a, **k: None,
+                get_date=lambda *a, **k: None, get_calendar_type=lambda: 0, no_calendar=0, flush_file=lambda *a, **k: None,
+                append_file=1, writeonly_file=2, single_file=1, stdout=6, max_across_pes=lambda *a, **k: None,
+                efp_sum_across_pes=lambda *a, **k: None, sum_across_pes=lambda *a, **k: None, find_eta=None, is_nan=lambda x: x != x)
+
+
+SUM_OUTPUT_FILES = ["src/diagnostics/MOM_sum_output.F90", "src/framework/MOM_coms.F90"]
+
+
+def _sum_output_ref():
+    key = ("sum_output",)
+    if key not in _REF:
+        _REF[key] = load(SUM_OUTPUT_FILES, extra_stubs=_sum_output_stubs(None), expose=("write_energy",))
+    return _REF[key]
+
+
+def create_depth_list(dom, grid, Z_ref=0.0, min_depth_inc=1.0e-10):
+    """create_depth_list, src/diagnostics/MOM_sum_output.F90:1203-1299 -> (depth, area, vol_below)"""
+    R = _sum_output_ref()
+    G, GV, US = _types(dom, grid, {})
+    G.z_ref = float(Z_ref)
+    G.isg, G.jsg = G.isc, G.jsc
+    G.domain.niglobal, G.domain.njglobal = G.iec - G.isc + 1, G.jec - G.jsc + 1
+    DL = R["mom_sum_output"]["_new_depth_list"]()
+    R["mom_sum_output"]["create_depth_list"](G, DL, float(min_depth_inc))
+    return tuple(np.array(x.tolist()) for x in (DL.depth, DL.area, DL.vol_below))
+
+
+def write_energy(dom, grid, gv, cs, u, v, h, T=None, S=None):
+    """write_energy, src/diagnostics/MOM_sum_output.F90:321-1030, on the single-PE case.  cs is the dict of
+    mom6_b200.synthetic.sum_output_cs and is updated the way oracle.pyoracle.write_energy updates it (previous_calls, ntrunc, lH and
+    the six EFP members); the reference's own Sum_output_CS lives on in cs["_f90run"] from one call to the next.  Returns the
+    oracle's result dict: what the reference hands to write_field (:970-994) and, for the numbers it only prints on the ocean.stats
+    line (En_mass, KE_tot, PE_tot, salin, temp and their anomalies), its local variables at the final RETURN."""
+    R = _sum_output_ref()
+    M = R["mom_sum_output"]
+    gvd = dict(gv)
+    gvd["g_prime"] = np.asarray(cs["g_prime"], dtype=np.float64)
+    G, GV, US = _types(dom, grid, gvd, {k: cs.get(k, 1.0) for k in ("RZL2_to_kg", "L_T_to_m_s", "Q_to_J_kg", "J_kg_to_Q", "kg_m3_to_R",
+                                                                  "m_to_Z", "m_to_L", "Z_to_m", "S_to_ppt", "C_to_degC")})
+    G.z_ref = float(cs.get("Z_ref", 0.0))
+    state = cs.setdefault("_f90run", {})
+    CS = state.get("CS")
+    if CS is None:
+        CS = M["_new_sum_output_cs"]()
+        CS.initialized = True
+        CS.do_ape_calc, CS.use_temperature = bool(cs["do_APE_calc"]), bool(cs["use_temperature"])
+        CS.dt_in_t = float(cs["dt_in_T"])
+        CS.dl = M["_new_depth_list"]()
+        CS.dl.listsize = int(cs["DL_listsize"])
+        for n in ("depth", "area", "vol_below"):
+            setattr(CS.dl, n, FArray.from_numpy(np.asarray(cs["DL_" + n], dtype=np.float64), (1,)))
+        CS.lh = FArray.alloc("i", [(1, int(dom.nk))])
+        CS.lh.v[:] = [int(x) for x in cs["lH"]]
+        CS.energysavedays, CS.energysavedays_geometric, CS.energysave_geometric = _Time(3600), _Time(0), False
+        CS.start_time, CS.write_energy_time, CS.geometric_end_time = _Time(0), _Time(0), _Time(0)
+        CS.timeunit, CS.date_stamped_output, CS.iso_date_stamped_output = 86400.0, False, False
+        CS.max_energy, CS.maxtrunc = 1.0e30, 1 << 30
+        CS.write_stocks, CS.write_min_max, CS.write_min_max_loc = False, False, False
+        CS.previous_calls = int(cs.get("previous_calls", 0))
+        CS.fileenergy_nc, CS.fileenergy_ascii, CS.energyfile = _EnergyFile(), 17, "ocean.stats"
+        CS.fields = FArray.alloc("o", [(1, 17 + 50)])   # NUM_FIELDS + MAX_FIELDS_
+        state["CS"], state["n"] = CS, 0
+    CS.ntrunc = int(cs.get("ntrunc", 0))
+    f = CS.fileenergy_nc
+    f.rows.append({})
+    tv = NS(c_p=float(cs.get("C_p", 3991.86795711963)))
+    if T is not None:
+        tv.t, tv.s = adapt.farr(dom, T), adapt.farr(dom, S)
+    n = state["n"]
+    M["write_energy"](adapt.farr(dom, u), adapt.farr(dom, v), adapt.farr(dom, h), tv, _Time(3600 * n), n, G, GV, US, CS)
+    state["n"] = n + 1
+    row, loc = f.rows[-1], M["_SAVE"]["write_energy.__locals__"]
+    names = {"En": "toten", "APE": "PE", "KE": "KE", "H0": "Z_0APE", "Mass_lay": "mass_lay", "Mass": "mass_tot", "Mass_chg": "mass_chg",
+             "Mass_anom": "mass_anom", "Salt": "Salt", "Salt_chg": "Salt_chg", "Salt_anom": "Salt_anom", "Heat": "Heat",
+             "Heat_chg": "Heat_chg", "Heat_anom": "Heat_anom"}
+    out = {names[k]: (x if isinstance(x, np.ndarray) else float(x)) for k, x in row.items() if k in names}
+    out["max_CFL"] = np.array([row["max_CFL_trans"], row["max_CFL_lin"]])
+    out["ntrunc"] = int(row["Ntrunc"])
+    for k in ("En_mass", "KE_tot", "PE_tot"):
+        out[k] = float(loc[k.lower()])
+    for k in ("Salt", "Salt_chg", "Salt_anom", "Heat", "Heat_chg", "Heat_anom", "salin", "salin_anom", "temp", "temp_anom"):
+        if k not in out:   # not written without temperature; the oracle reports them as zero
+            out[k] = float(loc[k.lower()]) if bool(cs["use_temperature"]) or k in ("Salt", "Heat") else 0.0
+    cs["previous_calls"], cs["ntrunc"] = int(CS.previous_calls), int(CS.ntrunc)
+    cs["lH"][...] = np.array(CS.lh.tolist(), dtype=np.int32)
+    for k in ("fresh_water_in_EFP", "net_salt_in_EFP", "net_heat_in_EFP", "mass_prev_EFP", "salt_prev_EFP", "heat_prev_EFP"):
+        cs[k] = np.array(getattr(CS, k.lower()).v.tolist(), dtype=np.int64)
+    return out
+
+
+CHKSUM_FILES = ["src/framework/MOM_checksums.F90", "src/framework/MOM_coms.F90"]
+
+
+def chksum(dom, array, stagger=0, haloshift=0, symmetric=False, omit_corners=False, scale=1.0, stats=False):
+    """hchksum / uchksum / vchksum / Bchksum, src/framework/MOM_checksums.F90 (chksum_h_2d :387, chksum_B_2d :688, chksum_u_2d :1005,
+    chksum_v_2d :1209 and the _3d forms :1413-2188) -> (the bit counts in the order the reference hands them to chk_sum_msg,
+    [mean, min, max] or None).  The messages themselves (formatted writes) are not reproduced: chk_sum_msg is replaced by a recorder."""
+    key = ("chksum",)
+    if key not in _REF:
+        no = lambda *a, **k: None  # noqa: E731
+        _REF[key] = load(CHKSUM_FILES, extra_stubs=dict(sum_across_pes=no, min_across_pes=no, max_across_pes=no, error_unit=0,
+                                                        is_root_pe=lambda: True))
+    m = _REF[key]["mom_checksums"]
+    seen = {"bc": [], "stats": None}
+
+    def record(fmsg, *a):
+        vals = a[:-2]   # ..., mesg, iounit
+        if len(vals) == 3 and all(type(x) is float for x in vals):
+            seen["stats"] = list(vals)
+        else:
+            seen["bc"] += [int(x) for x in vals]
+
+    for n in ("chk_sum_msg", "chk_sum_msg_nsew", "chk_sum_msg_s", "chk_sum_msg_w"):
+        m[n] = record
+    m["calculatestatistics"], m["writechksums"], m["checkfornans"], m["writehash"] = bool(stats), True, False, False
+    G = adapt.grid_type(dom, {})
+    HI = G.hi
+    HI.turns = 0
+    st = "huvq"[stagger]
+    fa = adapt.farr(dom, array, st)
+    name = "chksum_" + {"h": "h", "u": "u", "v": "v", "q": "b"}[st] + ("_2d" if array.ndim == 2 else "_3d")
+    kw = dict(haloshift=int(haloshift), omit_corners=bool(omit_corners))
+    if st != "h":
+        kw["symmetric"] = bool(symmetric)
+    if scale != 1.0:
+        kw["unscale"] = float(scale)
+    m[name](fa, "x", HI, **kw)
+    return seen["bc"], seen["stats"]

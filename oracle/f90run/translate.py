@@ -562,6 +562,8 @@ class Proc:
         self.line = 0
         self.uses = []
         self.elemental = False
+        self.internal = {}  # name -> Proc: the internal procedures after this one's CONTAINS
+        self.host = None    # the Proc an internal procedure lies in
 
     def out_scalars(self):
         """dummy arguments that are scalars of intrinsic type and may be defined by the procedure (copied out to the caller)"""
@@ -721,7 +723,7 @@ def _parse_module_spec(sts, i, mod):
     return i
 
 
-def _parse_proc(sts, i, mod):
+def _parse_proc(sts, i, mod, into=None):
     ln, st = sts[i]
     h = _HDR.match(st)
     kind, name, tail = h.group(1), h.group(2), (h.group(3) or "").strip()
@@ -780,8 +782,18 @@ def _parse_proc(sts, i, mod):
             P.vars[a].dummy = True
     # executable part, up to the matching end
     body, i = _parse_block(sts, i, ("endproc",))
+    if body and body[-1][0] == "internal":
+        _, _, first, last = body.pop()
+        j = first
+        while j < last:
+            if _HDR.match(sts[j][1]):
+                j = _parse_proc(sts, j, mod, into=P.internal)
+            else:
+                j += 1
+        for q in P.internal.values():
+            q.host = P
     P.body = body
-    mod.procs[name] = P
+    (mod.procs if into is None else into)[name] = P
     return i
 
 
@@ -798,21 +810,21 @@ def _parse_block(sts, i, stop):
         if "endproc" in stop and (_END_PROC.match(st) and not re.match(r"end\s*(if|do|select|type|interface|where|module)", st)):
             return out, i + 1
         if st == "contains":
-            if True:
-                # internal procedures are not translated: skip to the end of the host
-                depth = 0
+            # internal procedures: note where they lie (the host's _parse_proc parses them) and skip to the end of the host
+            depth = 0
+            first = i + 1
+            i += 1
+            while i < n:
+                s2 = sts[i][1]
+                if _HDR.match(s2):
+                    depth += 1
+                elif _END_PROC.match(s2) and not re.match(r"end\s*(if|do|select|type|interface|where|module)", s2):
+                    if depth == 0:
+                        out.append(("internal", ln, first, i))
+                        return out, i + 1
+                    depth -= 1
                 i += 1
-                while i < n:
-                    s2 = sts[i][1]
-                    if _HDR.match(s2):
-                        depth += 1
-                    elif _END_PROC.match(s2) and not re.match(r"end\s*(if|do|select|type|interface|where|module)", s2):
-                        if depth == 0:
-                            out.append(("stmt", ln, "__internal_procedures_skipped__"))
-                            return out, i + 1
-                        depth -= 1
-                    i += 1
-                return out, i
+            return out, i
         if "endif" in stop and re.match(r"(end\s*if|else\b|else\s*if\b|elseif\b)", st):
             return out, i
         if "enddo" in stop and re.match(r"end\s*do\b", st):

@@ -2,8 +2,10 @@
 // Restatement of /root/reference/src/diagnostics/MOM_sum_output.F90: write_energy :321-1020 (Boussinesq; tracer stocks and
 // min/max locations not included), create_depth_list :1203-1326 (single PE), the lH initialisation of depth_list_setup
 // :1194-1196, and the ocean.stats line :874-902.
-// PARITY: the sums inside are the EFP sums pinned in tests/test_oracle_efp.py; the routine as a whole has no known-answer
-// vector in the reference ("parity unpinned").
+// PARITY: PINNED BY A REFERENCE RUN -- write_energy (three successive calls on a changing state, with and without temperature,
+// with and without the APE calculation, with rescaled units) and create_depth_list of MOM_sum_output.F90 itself, executed by
+// oracle/f90run, agree bit for bit with this file (tests/refcases.py "diag/write_energy*").  The text of the ocean.stats line is
+// a formatted WRITE the translator does not reproduce: checked against its format specification only (tests/test_diag.py).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include "efp.hpp"

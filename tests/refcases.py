@@ -251,6 +251,61 @@ def bt_helpers(inputs, btcalc, bt_mass_source, set_dtbt):
     return out
 
 
+# ---- write_energy (three calls on a changing state, MOM_sum_output.F90:321) and the bit-count checksums (MOM_checksums.F90) -------
+for _n, _kw in enumerate([dict(), dict(use_temperature=False), dict(do_APE_calc=False),
+                          dict(RZL2_to_kg=2.0**-10, L_T_to_m_s=2.0**3, Z_to_m=2.0**2)]):
+    case(f"diag/write_energy{_n:02d}", "diag", (20, 16, 5), (), land_blocks=2, cs=_kw)
+case("diag/chksum", "diag", (12, 10, 3), (), chksum=True)
+
+_WE_SCALARS = ("En_mass", "toten", "KE_tot", "PE_tot", "mass_tot", "mass_chg", "mass_anom", "Salt", "Salt_chg", "Salt_anom", "Heat",
+               "Heat_chg", "Heat_anom", "salin", "salin_anom", "temp", "temp_anom")
+_WE_EFPS = ("fresh_water_in_EFP", "net_salt_in_EFP", "net_heat_in_EFP", "mass_prev_EFP", "salt_prev_EFP", "heat_prev_EFP")
+
+
+def diag_write_energy(inputs, write_energy):
+    """three write_energy calls through the given backend, the state and the truncation count changing in between"""
+    dom, a, cs = inputs[0], inputs[3], _copy(inputs[4])
+    u, v, h, T, S = (a[k].copy() for k in ("u_inst", "v_inst", "h", "T", "S"))
+    rng = np.random.default_rng(4)
+    out = {}
+    for call in range(3):
+        e = write_energy(cs, u, v, h, T, S)
+        out[f"call{call}.scalars"] = np.array([float(e[k]) for k in _WE_SCALARS] + [float(x) for x in e["max_CFL"]] +
+                                              [float(e["ntrunc"]), float(cs["previous_calls"]), float(cs["ntrunc"])])
+        for k in ("KE", "mass_lay"):
+            out[f"call{call}.{k}"] = np.array(e[k], dtype=np.float64)
+        for k in ("PE", "Z_0APE"):
+            out[f"zero_ok:call{call}.{k}"] = np.array(e[k], dtype=np.float64)
+        out[f"call{call}.EFP"] = np.array([[int(x) for x in cs[k]] for k in _WE_EFPS], dtype=np.int64)
+        out[f"call{call}.lH"] = np.array(cs["lH"], dtype=np.int64)
+        h *= 1.0 + 1.0e-3 * rng.standard_normal(h.shape)
+        u += 1.0e-3 * rng.standard_normal(u.shape); T += 0.01 * rng.standard_normal(T.shape)
+        cs["ntrunc"] = call + 1
+    return out
+
+
+def diag_chksum(inputs, chksum):
+    """every form of the checksums -- h, u, v and B points, rank 2 and 3, halo shifts 0, 1 and 2, symmetric or not, corners or
+    edges, scaled or not -- through the given backend: chksum(array, stagger, haloshift, symmetric, omit_corners, scale) ->
+    (the bit counts, zero-padded to five, [mean, min, max])"""
+    dom = inputs[0]
+    r = np.random.default_rng(7)
+    bcs, sts = [], []
+    for stagger in range(4):
+        su, sv = stagger in (1, 3), stagger in (2, 3)
+        shp = (dom.jed - dom.jsd + 1 + sv, dom.ied - dom.isd + 1 + su)
+        for nd in (2, 3):
+            a = np.ascontiguousarray(r.standard_normal(((int(dom.nk),) if nd == 3 else ()) + shp) * 10.0 ** r.integers(-8, 8, size=shp))
+            for hs in (0, 1, 2):
+                for sym in ((False, True) if stagger else (False,)):
+                    for omit in (False, True):
+                        for scale in (1.0, 0.37):
+                            bc, st = chksum(a, stagger, hs, sym, omit, scale)
+                            bcs.append([int(x) for x in bc][:5] + [0] * (5 - len(bc)))
+                            sts.append([float(x) for x in st])
+    return {"chksum.bc": np.array(bcs, dtype=np.int64), "chksum.stats": np.array(sts)}
+
+
 def ale_collect(dom, ale, dcs, a):
     src = dict(a)
     for k in ("diffu", "diffv", "CAu_pred", "CAv_pred", "u_av", "v_av"):
@@ -335,6 +390,15 @@ def build(name):
         return synthetic.advect_inputs(*shape, **kw)
     if st == "ale":
         return synthetic.ale_chain_inputs(*shape, **kw)
+    if st == "diag":
+        from oracle import pyoracle
+        if kw.get("chksum"):
+            from mom6_b200.api import make_domain
+            return (make_domain(shape[0], shape[1], nk=shape[2]),)
+        dom, grid, gv, css, dcs, a = synthetic.step_dyn_inputs(*shape, whalo=6, land_blocks=kw.get("land_blocks", 0))
+        # the depth list is host code of the reference (create_depth_list :1203); the reference leg checks this one against its own
+        cs = synthetic.sum_output_cs(dom, pyoracle.create_depth_list(dom, grid, min_depth_inc=1.0e-10), **kw.get("cs", {}))
+        return dom, grid, gv, a, cs
     if st == "bt_helpers":
         from oracle import pyoracle
         dom, grid, gv, bcs, ba = synthetic.btstep_inputs(*shape, **kw)
@@ -360,6 +424,15 @@ def build(name):
 
 def run_oracle(oracle, name, inputs):
     c = CASES[name]
+    if c["stage"] == "diag":
+        dom = inputs[0]
+        if c["kw"].get("chksum"):
+            def chk(a, stagger, hs, sym, omit, scale):
+                bc, kind, st = oracle.chksum(dom, a, stagger, hs, sym, omit, scale, stats=True)
+                return bc[:{1: 1, 2: 5, 3: 5, 4: 2, 5: 2}[kind]], st
+            return diag_chksum(inputs, chk)
+        grid, gv = inputs[1:3]
+        return diag_write_energy(inputs, lambda cs, u, v, h, T, S: oracle.write_energy(dom, grid, gv, cs, u, v, h, T, S))
     if c["stage"] == "bt_helpers":
         dom, grid, gv = inputs[:3]
         return bt_helpers(inputs, lambda a: oracle.btcalc(dom, grid, gv, a),
@@ -392,6 +465,15 @@ def run_oracle(oracle, name, inputs):
 def run_reference(name, inputs):
     from oracle.f90run import stages
     c = CASES[name]
+    if c["stage"] == "diag":
+        dom = inputs[0]
+        if c["kw"].get("chksum"):
+            return diag_chksum(inputs, lambda a, stagger, hs, sym, omit, scale: stages.chksum(dom, a, stagger, hs, sym, omit, scale, stats=True))
+        grid, gv, cs = inputs[1], inputs[2], inputs[4]
+        dl = stages.create_depth_list(dom, grid, min_depth_inc=1.0e-10)
+        for mine, theirs in zip((cs["DL_depth"], cs["DL_area"], cs["DL_vol_below"]), dl):
+            assert np.array_equal(mine, theirs), "create_depth_list: the oracle's list is not the reference's"
+        return diag_write_energy(inputs, lambda cs, u, v, h, T, S: stages.write_energy(dom, grid, gv, cs, u, v, h, T, S))
     if c["stage"] == "bt_helpers":
         dom, grid, gv = inputs[:3]
         return bt_helpers(inputs, lambda a: stages.btcalc(dom, grid, gv, a),
@@ -438,6 +520,20 @@ def run_device(ctx_factory, name, inputs):
     """the same case through the C ABI on the GPU (tests/test_reference_golden.py)"""
     c = CASES[name]
     st = c["stage"]
+    if st == "diag":
+        dom = inputs[0]
+        if c["kw"].get("chksum"):
+            ctx = ctx_factory(dom)
+
+            def chk(a, stagger, hs, sym, omit, scale):
+                bc, kind, stt = ctx.chksum(a, stagger, haloshift=hs, symmetric=sym, omit_corners=omit, scale=scale, stats=True)
+                return bc[:{1: 1, 2: 5, 3: 5, 4: 2, 5: 2}[kind]], stt
+            out = diag_chksum(inputs, chk)
+        else:
+            ctx = _ctx(ctx_factory, dom, inputs[1], inputs[2])
+            out = diag_write_energy(inputs, lambda cs, u, v, h, T, S: ctx.write_energy(cs, u, v, h, T, S))
+        ctx.close()
+        return out
     if st == "bt_helpers":
         dom, grid, gv = inputs[:3]
         ctx = _ctx(ctx_factory, dom, grid, gv)
