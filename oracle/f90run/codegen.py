@@ -6,7 +6,7 @@ parentheses are kept, equal-precedence operators associate left to right, '**' r
 import re
 
 from .rt import INTRINSICS, mangle
-from .translate import Parser, parse_expr, tokenize, _split_top
+from .translate import Parser, parse_expr, tokenize, _split_top, _match_paren
 
 _ARITH = {"+", "-", "*", "/", "**"}
 _REAL_FN = {"sqrt", "exp", "log", "sin", "cos", "tan", "atan", "atan2", "tanh", "real", "dble", "float", "epsilon", "tiny",
@@ -48,6 +48,11 @@ def find_assign(st):
             return i
         i += 1
     return -1
+
+
+# library routines that are stubbed (oracle/f90run/stubs.py, stages.py) and define scalar actual arguments: the positions of those
+# arguments; the stub returns their values as a tuple
+_STUB_OUTS = {"get_time": (1, 2)}   # get_time(Time, seconds, days), FMS time_manager
 
 
 class ProcGen:
@@ -397,6 +402,14 @@ class ProcGen:
             return
         f = self.find_proc(name)
         argtxt = ", ".join(self.ex(a) for a in args)
+        if f is None and name in _STUB_OUTS:   # a stubbed library routine that defines scalar arguments: the stub returns them
+            r = self.newtmp("r")
+            self.emit(ind, f"{r} = {mangle(name)}({argtxt})", ln)
+            pos = [a for a in args if a[0] != "kw"]
+            for n, k in enumerate(_STUB_OUTS[name]):
+                if k < len(pos):
+                    self.designator_store(ind, pos[k], f"{r}[{n}]", ln)
+            return
         if f is None or isinstance(f, list):
             self.emit(ind, f"{mangle(name)}({argtxt})", ln)
             return
@@ -413,6 +426,24 @@ class ProcGen:
             actual = pos[k] if k < len(pos) else kws.get(d)
             if actual is not None:
                 self.designator_store(ind, actual, f"{r}[{n}]", ln)
+
+    def formatted_write(self, ind, st, internal, ln):
+        """write(unit, fmt) items with an explicit format: the record is built by _rt.fwrite and either assigned to the character
+        variable (an internal write) or handed to _rt.unit_write, which keeps it if that unit is being recorded"""
+        if not st.startswith("write"):
+            raise NotImplementedError(st)
+        j = _match_paren(st, st.index("("))
+        ctl, items = _split_top(st[st.index("(") + 1:j - 1]), st[j:].strip()
+        if len(ctl) != 2 or ctl[1].strip() == "*" or "=" in ctl[1].replace("==", ""):
+            raise NotImplementedError("control list")
+        fmt = self.ex(parse_expr(ctl[1].strip()))
+        vals = [self.ex(parse_expr(it.strip())) for it in _split_top(items)] if items else []
+        rec = f"_rt.fwrite({fmt}, [{', '.join(vals)}])"
+        if internal:
+            e = parse_expr(ctl[0].strip())
+            self.designator_store(ind, e, rec, ln)
+        else:
+            self.emit(ind, f"_rt.unit_write({self.ex(parse_expr(ctl[0].strip()))}, {rec})", ln)
 
     def block(self, ind, nodes):
         if not nodes:
@@ -515,10 +546,12 @@ class ProcGen:
         if re.match(r"(write|read|open|close|format|flush|rewind)\b\s*[(*]", st) or re.match(r"print\b\s*['\"(*]", st):
             m = re.match(r"write\s*\(\s*([a-z_]\w*)\s*,", st)
             v = self.var(m.group(1)) if m else None
-            if v is not None and v.base == "character":  # internal write into a message string: its text is not reproduced
-                self.emit(ind, f"{mangle(m.group(1))} = ''", ln)
-            else:
-                self.emit(ind, "pass", ln)
+            internal = v is not None and v.base == "character" and v.dims is None
+            try:
+                self.formatted_write(ind, st, internal, ln)
+            except (SyntaxError, NotImplementedError, ValueError, IndexError, KeyError, AttributeError):
+                # list-directed output, implied DO loops, namelists ...: the text is not reproduced
+                self.emit(ind, f"{mangle(m.group(1))} = ''" if internal else "pass", ln)
             return
         if re.match(r"(error\s+)?stop\b", st):
             self.emit(ind, f"raise _rt.FortranStop({st!r})", ln)

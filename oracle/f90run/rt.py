@@ -741,3 +741,202 @@ def assign_derived(cur, x):
     cur.__dict__.update(new.__dict__)
     cur.__dict__.update(keep)
     return cur
+
+
+# ---------------------------------------------------------------------------------------------------------- formatted output
+# Fortran format-directed output for the edit descriptors the reference's diagnostics use (A, I, F, E, ES, L, Z, X, /, :, character
+# string literals, repeat counts and groups), following the Fortran 2008 standard's section 10 the way gfortran prints: plus signs
+# suppressed, a leading "0" before the decimal point of F / E only where the width allows, asterisks on overflow, two exponent
+# digits with "E" (three without it).  This is a restatement of the standard -- libgfortran is not executed -- so what a test of
+# formatted text pins is the reference's format string and output list, not its I/O library.
+UNITS = {}   # unit number -> list of records, for the units a test wants to read back (see unit_write)
+
+
+def unit_write(unit, text):
+    if type(unit) is int and unit in UNITS:
+        UNITS[unit] += text.split("\n")
+
+
+def _fmt_tokens(f):
+    """the items of a format specification (without its outer parentheses), as a nested list"""
+    out, i, n = [], 0, len(f)
+    while i < n:
+        c = f[i]
+        if c in " ,":
+            i += 1
+        elif c in "'\"":
+            j, lit = i + 1, []
+            while True:
+                if f[j] == c:
+                    if j + 1 < n and f[j + 1] == c:
+                        lit.append(c); j += 2; continue
+                    break
+                lit.append(f[j]); j += 1
+            out.append(("lit", "".join(lit)))
+            i = j + 1
+        elif c == "/":
+            out.append(("nl",)); i += 1
+        elif c == ":":
+            out.append(("colon",)); i += 1
+        else:
+            j = i
+            while j < n and f[j].isdigit():
+                j += 1
+            rep = int(f[i:j]) if j > i else None
+            if j < n and f[j] == "(":
+                depth, k = 0, j
+                while True:
+                    if f[k] in "'\"":   # skip a literal inside the group
+                        q = f[k]; k += 1
+                        while f[k] != q:
+                            k += 1
+                    elif f[k] == "(":
+                        depth += 1
+                    elif f[k] == ")":
+                        depth -= 1
+                        if depth == 0:
+                            break
+                    k += 1
+                out.append(("group", rep or 1, _fmt_tokens(f[j + 1:k])))
+                i = k + 1
+                continue
+            k = j
+            while k < n and f[k].isalpha():
+                k += 1
+            name = f[j:k].lower()
+            m = k
+            while m < n and (f[m].isdigit() or f[m] == "."):
+                m += 1
+            spec = f[k:m]
+            e = None
+            if m < n and f[m] in "eE" and name in ("e", "es", "en", "g"):
+                m2 = m + 1
+                while m2 < n and f[m2].isdigit():
+                    m2 += 1
+                e, m = int(f[m + 1:m2]), m2
+            if name == "x":
+                out.append(("x", rep or 1))
+            elif name in ("a", "i", "f", "e", "es", "l", "z"):
+                w, _, d = spec.partition(".")
+                out.append(("edit", rep or 1, name, int(w) if w else None, int(d) if d else None, e))
+            else:
+                raise NotImplementedError(f"format item {f[i:m]!r}")
+            i = m
+    return out
+
+
+def _fit(s, w):
+    if w is None or w == 0:
+        return s
+    return "*" * w if len(s) > w else s.rjust(w)
+
+
+def _edit_real(name, x, w, d, e):
+    x = float(x)
+    if x != x or x in (INF, -INF):
+        s = "NaN" if x != x else ("-Infinity" if x < 0 else "Infinity")
+        if w and len(s) > w:
+            s = s.replace("inity", "")
+        return _fit(s, w)
+    neg = math.copysign(1.0, x) < 0
+    if name == "f":
+        s = "%.*f" % (d, abs(x))
+        if w and s.startswith("0.") and len(s) + neg > w and d > 0:
+            s = s[1:]   # the optional leading zero goes first
+        return _fit(("-" if neg else "") + s, w)
+    if name == "es":
+        m, _, ex = ("%.*E" % (d, abs(x))).partition("E")
+        ex = int(ex)
+    else:   # E: 0.ddddE+ee, d significant digits
+        m, _, ex = ("%.*E" % (max(d - 1, 0), abs(x))).partition("E")
+        ex = int(ex) + (0 if abs(x) == 0.0 else 1)
+        m = "0." + m.replace(".", "")
+    ne = 2 if e is None else e
+    if abs(ex) >= 10 ** ne and e is None:
+        tail = "%+04d" % ex   # three exponent digits: the letter E is dropped
+    else:
+        tail = "E%+0*d" % (ne + 1, ex)
+    s = m + tail
+    if name == "e" and w and len(s) + neg > w:
+        s = s[1:]
+    return _fit(("-" if neg else "") + s, w)
+
+
+def _edit(name, x, w, d, e):
+    if name == "a":
+        s = str(x)
+        return s if w is None else (s[:w] if len(s) > w else s.rjust(w))
+    if name == "l":
+        return _fit("T" if x else "F", w or 2)
+    if name == "i":
+        x = int(x)
+        s = str(abs(x))
+        if d is not None:
+            s = "" if (d == 0 and x == 0) else s.rjust(d, "0")
+        return _fit(("-" if x < 0 else "") + s, w)
+    if name == "z":
+        import struct
+        v = struct.unpack("<Q", struct.pack("<d", x))[0] if type(x) is float else (int(x) & 0xFFFFFFFF)
+        s = "%X" % v
+        if d is not None:
+            s = s.rjust(d, "0")
+        return _fit(s, w)
+    return _edit_real(name, x, w, d, e)
+
+
+def fwrite(fmt, items):
+    """the record(s) WRITE(unit, fmt) items produces, records joined by newlines; a format with an edit descriptor that is not
+    implemented here gives a marker text instead (such writes are messages, never results)"""
+    try:
+        return _fwrite(fmt, items)
+    except (NotImplementedError, ValueError, TypeError, IndexError) as err:
+        return f"<formatted output not reproduced: {err}>"
+
+
+def _fwrite(fmt, items):
+    fmt = fmt.strip()
+    if not (fmt.startswith("(") and fmt.endswith(")")):
+        raise NotImplementedError("format " + fmt)
+    toks = _fmt_tokens(fmt[1:-1])
+    vals = []
+    for x in items:
+        vals += x.tolist() if type(x) is FArray else [x]
+    out, pos = [], [0]
+
+    class _Done(Exception):
+        pass
+
+    def run(ts):
+        for t in ts:
+            if t[0] == "lit":
+                out.append(t[1])
+            elif t[0] == "x":
+                out.append(" " * t[1])
+            elif t[0] == "nl":
+                out.append("\n")
+            elif t[0] == "colon":
+                if pos[0] >= len(vals):
+                    raise _Done
+            elif t[0] == "group":
+                for _ in range(t[1]):
+                    run(t[2])
+            else:
+                for _ in range(t[1]):
+                    if pos[0] >= len(vals):
+                        raise _Done
+                    out.append(_edit(t[2], vals[pos[0]], t[3], t[4], t[5]))
+                    pos[0] += 1
+
+    try:
+        run(toks)
+        guard = 0
+        while pos[0] < len(vals):   # format reversion: a new record, from the last top-level group (or the start)
+            guard += 1
+            if guard > 10000 or not any(t[0] in ("edit", "group") for t in toks):
+                raise NotImplementedError("format reversion without a data edit descriptor")
+            out.append("\n")
+            last = [n for n, t in enumerate(toks) if t[0] == "group"]
+            run(toks[last[-1]:] if last else toks)
+    except _Done:
+        pass
+    return "".join(out)

@@ -5,7 +5,7 @@ tests/test_reference_f90.py calls a stage here and the same stage of the C++ ora
 compares every output bit for bit over the computational domain.  Each function cites the reference entry it executes."""
 import numpy as np
 
-from . import adapt, halo, load, new
+from . import adapt, halo, load, new, rt
 from .rt import FArray, NS
 
 _REF = {}
@@ -837,7 +837,7 @@ def _sum_output_stubs(files):
 
     return dict(set_time=lambda seconds=0, days=0, **k: _Time(int(seconds) + 86400 * int(days)), _new_time_type=lambda: _Time(0),
                 var_desc=var_desc, create_mom_file=open_file, reopen_mom_file=open_file, open_ascii_file=lambda *a, **k: None,
-                call_tracer_stocks=lambda *a, **k: None, array_global_min_max=lambda *a, **k: None, get_time=lambda *a, **k: None,
+                call_tracer_stocks=lambda *a, **k: None, array_global_min_max=lambda *a, **k: None, get_time=lambda t, *a, **k: (t.s % 86400, t.s // 86400),
                 get_date=lambda *a, **k: None, get_calendar_type=lambda: 0, no_calendar=0, flush_file=lambda *a, **k: None,
                 append_file=1, writeonly_file=2, single_file=1, stdout=6, max_across_pes=lambda *a, **k: None,
                 efp_sum_across_pes=lambda *a, **k: None, sum_across_pes=lambda *a, **k: None, find_eta=None, is_nan=lambda x: x != x)
@@ -907,8 +907,10 @@ def write_energy(dom, grid, gv, cs, u, v, h, T=None, S=None):
     if T is not None:
         tv.t, tv.s = adapt.farr(dom, T), adapt.farr(dom, S)
     n = state["n"]
+    rt.UNITS[CS.fileenergy_ascii] = []
     M["write_energy"](adapt.farr(dom, u), adapt.farr(dom, v), adapt.farr(dom, h), tv, _Time(3600 * n), n, G, GV, US, CS)
     state["n"] = n + 1
+    state["stats_line"] = rt.UNITS.pop(CS.fileenergy_ascii)[-1]   # the record appended to ocean.stats (:880-905); n, then day n/24
     row, loc = f.rows[-1], M["_SAVE"]["write_energy.__locals__"]
     names = {"En": "toten", "APE": "PE", "KE": "KE", "H0": "Z_0APE", "Mass_lay": "mass_lay", "Mass": "mass_tot", "Mass_chg": "mass_chg",
              "Mass_anom": "mass_anom", "Salt": "Salt", "Salt_chg": "Salt_chg", "Salt_anom": "Salt_anom", "Heat": "Heat",

@@ -11,9 +11,9 @@
  *     (src/ALE/MOM_remapping.F90:2072+), see tests/test_oracle_remap_kat.py.
  *   - the dycore stages, the whole step, tracer advection, the ALE pass and the three callers: PINNED BY A REFERENCE RUN --
  *     oracle/f90run executes the reference's own Fortran source and tests/test_reference_f90.py compares bit for bit;
- *   - write_energy, create_depth_list and the bit-count checksums: PINNED BY A REFERENCE RUN as well (tests/refcases.py "diag/...");
- *     only the text of the ocean.stats line (a Fortran formatted WRITE, which f90run does not reproduce) is checked against
- *     its format specification alone (tests/test_diag.py).
+ *   - write_energy, create_depth_list and the bit-count checksums: PINNED BY A REFERENCE RUN as well (tests/refcases.py "diag/...").
+ *     The ocean.stats record comes out of the reference's own WRITE statement (its format string and output list), edited by
+ *     f90run's restatement of Fortran format-directed output -- the Fortran standard's rules, not libgfortran itself.
  */
 #ifndef MOM6_ORACLE_H
 #define MOM6_ORACLE_H

@@ -4,8 +4,9 @@
 // :1194-1196, and the ocean.stats line :874-902.
 // PARITY: PINNED BY A REFERENCE RUN -- write_energy (three successive calls on a changing state, with and without temperature,
 // with and without the APE calculation, with rescaled units) and create_depth_list of MOM_sum_output.F90 itself, executed by
-// oracle/f90run, agree bit for bit with this file (tests/refcases.py "diag/write_energy*").  The text of the ocean.stats line is
-// a formatted WRITE the translator does not reproduce: checked against its format specification only (tests/test_diag.py).
+// oracle/f90run, agree bit for bit with this file (tests/refcases.py "diag/write_energy*"), and so does the record appended to
+// ocean.stats: the reference's WRITE statement (:880-905) with its own format string and output list, edited by f90run's
+// restatement of Fortran format-directed output (the standard's rules; libgfortran itself is not executed).
 #include "oracle.h"
 #include "ogrid.hpp"
 #include "efp.hpp"

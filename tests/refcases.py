@@ -262,8 +262,9 @@ _WE_SCALARS = ("En_mass", "toten", "KE_tot", "PE_tot", "mass_tot", "mass_chg", "
 _WE_EFPS = ("fresh_water_in_EFP", "net_salt_in_EFP", "net_heat_in_EFP", "mass_prev_EFP", "salt_prev_EFP", "heat_prev_EFP")
 
 
-def diag_write_energy(inputs, write_energy):
-    """three write_energy calls through the given backend, the state and the truncation count changing in between"""
+def diag_write_energy(inputs, write_energy, stats_line):
+    """three write_energy calls through the given backend, the state and the truncation count changing in between; stats_line(cs, e,
+    n, reday) is the record the call appends to ocean.stats (step n = the call number, one hour apart)"""
     dom, a, cs = inputs[0], inputs[3], _copy(inputs[4])
     u, v, h, T, S = (a[k].copy() for k in ("u_inst", "v_inst", "h", "T", "S"))
     rng = np.random.default_rng(4)
@@ -278,6 +279,7 @@ def diag_write_energy(inputs, write_energy):
             out[f"zero_ok:call{call}.{k}"] = np.array(e[k], dtype=np.float64)
         out[f"call{call}.EFP"] = np.array([[int(x) for x in cs[k]] for k in _WE_EFPS], dtype=np.int64)
         out[f"call{call}.lH"] = np.array(cs["lH"], dtype=np.int64)
+        out[f"call{call}.stats_line"] = np.frombuffer(stats_line(cs, e, call, (3600.0 * call) / 86400.0).encode(), dtype=np.uint8).astype(np.float64)
         h *= 1.0 + 1.0e-3 * rng.standard_normal(h.shape)
         u += 1.0e-3 * rng.standard_normal(u.shape); T += 0.01 * rng.standard_normal(T.shape)
         cs["ntrunc"] = call + 1
@@ -432,7 +434,7 @@ def run_oracle(oracle, name, inputs):
                 return bc[:{1: 1, 2: 5, 3: 5, 4: 2, 5: 2}[kind]], st
             return diag_chksum(inputs, chk)
         grid, gv = inputs[1:3]
-        return diag_write_energy(inputs, lambda cs, u, v, h, T, S: oracle.write_energy(dom, grid, gv, cs, u, v, h, T, S))
+        return diag_write_energy(inputs, lambda cs, u, v, h, T, S: oracle.write_energy(dom, grid, gv, cs, u, v, h, T, S), oracle.ocean_stats_line)
     if c["stage"] == "bt_helpers":
         dom, grid, gv = inputs[:3]
         return bt_helpers(inputs, lambda a: oracle.btcalc(dom, grid, gv, a),
@@ -473,7 +475,8 @@ def run_reference(name, inputs):
         dl = stages.create_depth_list(dom, grid, min_depth_inc=1.0e-10)
         for mine, theirs in zip((cs["DL_depth"], cs["DL_area"], cs["DL_vol_below"]), dl):
             assert np.array_equal(mine, theirs), "create_depth_list: the oracle's list is not the reference's"
-        return diag_write_energy(inputs, lambda cs, u, v, h, T, S: stages.write_energy(dom, grid, gv, cs, u, v, h, T, S))
+        return diag_write_energy(inputs, lambda cs, u, v, h, T, S: stages.write_energy(dom, grid, gv, cs, u, v, h, T, S),
+                                 lambda cs, e, n, reday: cs["_f90run"]["stats_line"])
     if c["stage"] == "bt_helpers":
         dom, grid, gv = inputs[:3]
         return bt_helpers(inputs, lambda a: stages.btcalc(dom, grid, gv, a),
@@ -531,7 +534,7 @@ def run_device(ctx_factory, name, inputs):
             out = diag_chksum(inputs, chk)
         else:
             ctx = _ctx(ctx_factory, dom, inputs[1], inputs[2])
-            out = diag_write_energy(inputs, lambda cs, u, v, h, T, S: ctx.write_energy(cs, u, v, h, T, S))
+            out = diag_write_energy(inputs, lambda cs, u, v, h, T, S: ctx.write_energy(cs, u, v, h, T, S), ctx.ocean_stats_line)
         ctx.close()
         return out
     if st == "bt_helpers":
