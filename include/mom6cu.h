@@ -666,7 +666,7 @@ int mom6cu_efp_sum_across_pes(mom6cu_ctx* ctx, mom6cu_efp* EFPs, int nval);
  *     kind 3 (NSEW):     bc[1..4] = N, S, E, W                     (chk_sum_msg_NSEW)
  *     kind 4 (u symmetric, haloshift 0): bc[1] = W                 (chk_sum_msg_W)
  *     kind 5 (v symmetric, haloshift 0): bc[1] = S                 (chk_sum_msg_S)
- *     kind 6 (q symmetric, haloshift 0): bc[1] = SW                (chk_sum_msg2)
+ *   (at B points `symmetric` with haloshift 0 takes the corner or NSEW form: chk_sum_msg2 is never called by the reference)
  *   *kind receives the case; stats (NULL = calculateStatistics off) receives mean, min, max (subStats). */
 int mom6cu_chksum(mom6cu_ctx* ctx, const double* array, int stagger, int nk, int haloshift, int symmetric, int omit_corners,
                   double scale, int* bc, int* kind, double* stats);
