@@ -372,7 +372,7 @@ def dyn_state(dom, grid, seed=SEED, vel=0.3, thin_layers=True, hnoise=0.2):
 
 
 def continuity_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, with_uhbt=True, with_visc_rem=True, with_BT_cont=True,
-                      with_cor=True, first_direction=0, cyclic_x=True, cyclic_y=False, dt=900.0, alias_h=False, cs_over=None):
+                      with_cor=True, first_direction=0, cyclic_x=True, cyclic_y=False, dt=900.0, alias_h=False, cs_over=None, uhbt_noise=0.05):
     """Everything a continuity_PPM call needs (MOM_continuity_PPM.F90:86): returns dom, grid, vgrid, cs, args."""
     dom = make_domain(ni, nj, nk=nk, halo=halo, cyclic_x=cyclic_x, cyclic_y=cyclic_y, first_direction=first_direction)
     grid = make_grid(dom, land_blocks, seed)
@@ -387,16 +387,17 @@ def continuity_inputs(ni, nj, nk, halo=4, seed=SEED, land_blocks=0, with_uhbt=Tr
     if with_visc_rem:
         a["visc_rem_u"], a["visc_rem_v"] = st["visc_rem_u"], st["visc_rem_v"]
     if with_uhbt:
-        # a target transport near the layer-summed first-guess transport
+        # a target transport near the layer-summed first-guess transport (uhbt_noise ~ 1: far from it, so that the limits of
+        # zonal_flux_adjust on the velocity correction bind)
         hu = 0.5 * (st["h"][:, :, :-1] + st["h"][:, :, 1:])
         uh0 = fidx.new(dom, "u")
         uh0.a[:, 1:-1] = (st["u"][:, :, 1:-1] * hu * grid["dy_Cu"][None, :, 1:-1]).sum(axis=0)
-        uh0.a[...] = uh0.a * (1.0 + 0.05 * r.uniform(-1, 1, size=uh0.a.shape)) * grid["mask2dCu"]
+        uh0.a[...] = uh0.a * (1.0 + uhbt_noise * r.uniform(-1, 1, size=uh0.a.shape)) * grid["mask2dCu"]
         a["uhbt"] = _sym_u(dom, uh0).a
         hv = 0.5 * (st["h"][:, :-1, :] + st["h"][:, 1:, :])
         vh0 = fidx.new(dom, "v")
         vh0.a[1:-1, :] = (st["v"][:, 1:-1, :] * hv * grid["dx_Cv"][None, 1:-1, :]).sum(axis=0)
-        vh0.a[...] = vh0.a * (1.0 + 0.05 * r.uniform(-1, 1, size=vh0.a.shape)) * grid["mask2dCv"]
+        vh0.a[...] = vh0.a * (1.0 + uhbt_noise * r.uniform(-1, 1, size=vh0.a.shape)) * grid["mask2dCv"]
         a["vhbt"] = _sym_v(dom, vh0).a
         if with_cor:
             a["u_cor"] = fidx.new(dom, "u", nk=nk).a

@@ -242,6 +242,44 @@ case("mixedlayer_restrat/no_front_length", "mixedlayer_restrat", (14, 10, 16), M
 case("step/be_0.7", "step", (12, 10, 4), STEP_OUT, land_blocks=2, dyn=dict(be=0.7))
 case("step/no_visc_rem_dt_bug", "step", (12, 10, 4), STEP_OUT, land_blocks=2, dyn=dict(visc_rem_dt_bug=0))
 
+# ---- a third sweep: options that an audit (remove the option, does the oracle's answer change?) found without effect in the case that
+# ---- names them, now in a setting where they do act (each checked) -------------------------------------------------------------
+_T3 = [
+    ("btstep/coriolis_bracket_bug", "btstep", (16, 12, 4), dict(use_old_coriolis_bracket_bug=1)),
+    ("coradcalc/robust_enstro_pv_upwind1", "coradcalc", (16, 12, 3), dict(cs_over=dict(Coriolis_Scheme=3, PV_Adv_Scheme=22))),
+    ("pressure_force/rho_ref_bug", "pressure_force", (14, 10, 5), dict(rho_ref_bug=1, rho_ref=1030.0)),
+    ("pressure_force/plm_inaccurate_rho_anom", "pressure_force", (14, 10, 5), dict(reconstruct=1, Recon_Scheme=1, use_inaccurate_pgf_rho_anom=1)),
+    ("pressure_force/ppm_mass_weight_vanished_only_5m", "pressure_force", (14, 10, 5),
+     dict(reconstruct=1, Recon_Scheme=2, MassWghtInterp=1, MassWghtInterpVanOnly=1, h_nonvanished=5.0)),
+    ("horizontal_viscosity/les_added_to_background", "horizontal_viscosity", (16, 12, 3),
+     dict(Laplacian=True, Kh=300.0, Smagorinsky_Kh=True, add_LES_viscosity=True)),
+    ("horizontal_viscosity/kh_bg_min", "horizontal_viscosity", (16, 12, 3), dict(Laplacian=True, Kh=10.0, Kh_bg_min=500.0)),
+    # viscosities large enough, and a time step long enough, for the stability bounds to bind: legacy / no / better bounds
+    ("horizontal_viscosity/legacy_bounds_bind", "horizontal_viscosity", (16, 12, 3),
+     dict(Laplacian=True, Kh=5.0e4, dt=14400.0, better_bound_Kh=False, better_bound_Ah=False, Smagorinsky_Kh=True)),
+    ("horizontal_viscosity/unbounded", "horizontal_viscosity", (16, 12, 3),
+     dict(Laplacian=True, Kh=5.0e4, Ah=1.0e13, dt=14400.0, bound_Kh=False, bound_Ah=False, better_bound_Kh=False, better_bound_Ah=False)),
+    ("horizontal_viscosity/better_bound_kh_only", "horizontal_viscosity", (16, 12, 3),
+     dict(Laplacian=True, Kh=5.0e4, Ah=1.0e13, dt=14400.0, better_bound_Ah=False)),
+    ("horizontal_viscosity/better_bound_ah_only", "horizontal_viscosity", (16, 12, 3),
+     dict(Laplacian=True, Kh=5.0e4, Ah=1.0e13, dt=14400.0, better_bound_Kh=False)),
+    ("horizontal_viscosity/better_bounds_bind", "horizontal_viscosity", (16, 12, 3), dict(Laplacian=True, Kh=5.0e4, Ah=1.0e13, dt=14400.0)),
+    ("tracer_hordiff/meke_passivity_with_varmix", "tracer_hordiff", (14, 10, 5),
+     dict(use_variable_mixing=1, use_MEKE_Kh=1, MEKE_KhTr_fac=0.7, KhTr_passivity_coeff=3.0)),
+    ("tracer_hordiff/khtr_max_binds", "tracer_hordiff", (14, 10, 5), dict(use_variable_mixing=1, KhTr=8000.0, KhTr_max=3000.0)),
+    ("tracer_hordiff/diffusive_cfl_iterations", "tracer_hordiff", (14, 10, 5), dict(KhTr=2.0e5, check_diffusive_CFL=1)),
+    ("thickness_diffuse/khth_cfl_binds", "thickness_diffuse", (14, 10, 5), dict(Khth=1.0e5, max_Khth_CFL=0.05)),
+    ("thickness_diffuse/khth_max_binds", "thickness_diffuse", (14, 10, 5),
+     dict(use_variable_mixing=1, Resoln_scaled_KhTh=1, Khth=2000.0, Khth_Max=900.0)),
+    ("thickness_diffuse/p_surf_wright", "thickness_diffuse", (14, 10, 5), dict(with_p_surf=True)),
+    ("continuity/cfl_limit_binds", "continuity", (20, 16, 6), dict(uhbt_noise=3.0, dt=3600.0, cs_over=dict(CFL_limit_adjust=0.02))),
+    ("continuity/cfl_limit_binds_no_visc_rem_max", "continuity", (20, 16, 6),
+     dict(uhbt_noise=3.0, dt=3600.0, cs_over=dict(CFL_limit_adjust=0.005, use_visc_rem_max=0))),
+    ("continuity/aggress_adjust_binds", "continuity", (20, 16, 6), dict(uhbt_noise=6.0, dt=14400.0, cs_over=dict(aggress_adjust=1, vol_CFL=1))),
+]
+for _nm, _st, _shape, _kw in _T3:
+    case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), land_blocks=2, **_kw)
+
 # cases added or changed after the round's GPU budget was spent: their device legs run from tests/test_zzz_reference_golden_late.py, sorted
 # last, so that a disagreement there cannot hide the results of the files after tests/test_reference_golden.py under `pytest -x`
 LATE = {n for n in CASES if n.startswith(("diag/", "mixedlayer_restrat/"))} | {
@@ -249,7 +287,7 @@ LATE = {n for n in CASES if n.startswith(("diag/", "mixedlayer_restrat/"))} | {
     "coradcalc/al_blend_sadourny_limit", "vertvisc_family/mixing_lengths", "vertvisc_family/mixing_lengths_no_drag_law",
     "pressure_force/gfs_scale", "pressure_force/rho_ref_h_nonvanished_plm", "pressure_force/mass_weight_vanished_only_ppm",
     "tracer_hordiff/passivity_min", "thickness_diffuse/khth_cfl_slope_smoothing", "thickness_diffuse/fgnv_scale_n2_floor", "step/be_0.7",
-    "step/no_visc_rem_dt_bug"}
+    "step/no_visc_rem_dt_bug"} | {t[0] for t in _T3}
 
 # outputs a case legitimately returns as it received them
 UNTOUCHED_OK = {
