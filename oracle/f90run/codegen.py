@@ -6,7 +6,7 @@ parentheses are kept, equal-precedence operators associate left to right, '**' r
 import re
 
 from .rt import INTRINSICS, mangle
-from .translate import Parser, parse_expr, tokenize, _split_top, _match_paren
+from .translate import Parser, Var, parse_expr, tokenize, _split_top, _match_paren
 
 _ARITH = {"+", "-", "*", "/", "**"}
 _REAL_FN = {"sqrt", "exp", "log", "sin", "cos", "tan", "atan", "atan2", "tanh", "real", "dble", "float", "epsilon", "tiny",
@@ -410,6 +410,27 @@ class ProcGen:
                 if k < len(pos):
                     self.designator_store(ind, pos[k], f"{r}[{n}]", ln)
             return
+        if isinstance(f, list) and any(s.out_scalars() for s in f):
+            # a generic subroutine: which specific runs (and so which scalar arguments it defines) is known at run time; the
+            # dispatcher returns them by dummy-argument name and position, stored into the actuals that can take them
+            r, v = self.newtmp("r"), self.newtmp("v")
+            self.emit(ind, f"{r} = {mangle(name)}({argtxt})", ln)
+            npos = 0
+            for a in args:
+                kw = a[1] if a[0] == "kw" else None
+                actual = a[2] if a[0] == "kw" else a
+                if actual[0] == "ref" and not any(x is not None and any(y[0] == "slice" for y in x) for _, x in actual[1]):
+                    n0 = len(self.lines)
+                    self.designator_store(ind + 1, actual, v, ln)
+                    body = self.lines[n0:]
+                    del self.lines[n0:]
+                    if body:
+                        self.emit(ind, f"{v} = _rt.genout({r}, {npos if kw is None else None!r}, {mangle(kw) if kw else None!r})")
+                        self.emit(ind, f"if {v} is not _rt.NOOUT:")
+                        self.lines += body
+                if kw is None:
+                    npos += 1
+            return
         if f is None or isinstance(f, list):
             self.emit(ind, f"{mangle(name)}({argtxt})", ln)
             return
@@ -434,11 +455,15 @@ class ProcGen:
             raise NotImplementedError(st)
         j = _match_paren(st, st.index("("))
         ctl, items = _split_top(st[st.index("(") + 1:j - 1]), st[j:].strip()
-        if len(ctl) != 2 or ctl[1].strip() == "*" or "=" in ctl[1].replace("==", ""):
+        if len(ctl) != 2 or "=" in ctl[1].replace("==", ""):
             raise NotImplementedError("control list")
-        fmt = self.ex(parse_expr(ctl[1].strip()))
         vals = [self.ex(parse_expr(it.strip())) for it in _split_top(items)] if items else []
-        rec = f"_rt.fwrite({fmt}, [{', '.join(vals)}])"
+        if ctl[1].strip() == "*":   # list-directed: messages only (numbers are not edited the way a Fortran processor would)
+            if internal:
+                raise NotImplementedError("list-directed internal write")
+            rec = f"_rt.list_write([{', '.join(vals)}])"
+        else:
+            rec = f"_rt.fwrite({self.ex(parse_expr(ctl[1].strip()))}, [{', '.join(vals)}])"
         if internal:
             e = parse_expr(ctl[0].strip())
             self.designator_store(ind, e, rec, ln)
@@ -489,6 +514,29 @@ class ProcGen:
             elif k == "doforever":
                 self.emit(ind, "while True:", nd[1])
                 self.block(ind + 1, nd[2])
+            elif k == "seltype":
+                _, ln, assoc, expr, arms = nd
+                sel = self.ex(parse_expr(expr))
+                name = mangle(assoc)
+                if assoc != expr:
+                    self.emit(ind, f"{name} = {sel}", ln)
+                first = True
+                for guard, tname, blk in arms:
+                    # inside the arm the associate name has the guard's type (what its type-bound calls resolve against)
+                    had = self.P.vars.get(assoc)
+                    if assoc != expr:
+                        self.P.vars[assoc] = Var(assoc, "class", tname)
+                    if guard is None:
+                        self.emit(ind, "if True:" if first else "else:")
+                    else:
+                        self.emit(ind, ("if " if first else "elif ") + f"_rt.type_is({name}, {tname!r}, {guard == 'class'!r}, globals()):")
+                    self.block(ind + 1, blk)
+                    if assoc != expr:
+                        if had is None:
+                            del self.P.vars[assoc]
+                        else:
+                            self.P.vars[assoc] = had
+                    first = False
             elif k == "select":
                 s = self.newtmp("sel")
                 self.emit(ind, f"{s} = {self.ex(parse_expr(nd[2]))}", nd[1])
@@ -811,6 +859,8 @@ class Program:
             out.append(f"def _new_{mangle(tname)}():")
             ext = mod.type_ext.get(tname)
             out.append(f"    o = _rt.new_type(globals(), {ext!r})" if ext else "    o = _rt.NS()")
+            if ext:
+                out.append(f"    o._bases = tuple(o.__dict__.get('_bases') or ()) + ({ext!r},)")
             out.append(f"    o._type = {tname!r}")
             for b, impl in mod.type_binds.get(tname, {}).items():
                 out.append(f"    o.{mangle(b)} = _rt.bind(globals(), {mangle(impl)!r}, o)")
@@ -843,7 +893,8 @@ class Program:
                 P = mod.procs[s]
                 sig.append("(" + mangle(s) + ", [" + ", ".join(
                     "(%r, %r, %r)" % (mangle(a), (len(P.vars[a].dims) if (a in P.vars and P.vars[a].dims is not None) else 0),
-                                      bool(a in P.vars and P.vars[a].optional)) for a in P.args) + "])")
+                                      bool(a in P.vars and P.vars[a].optional)) for a in P.args) + "], " +
+                           repr([mangle(a) for a in P.out_scalars()]) + ")")
             out.append(f"{mangle(g)} = _rt.generic({g!r}, [" + ", ".join(sig) + "])")
         return "\n".join(out) + "\n"
 

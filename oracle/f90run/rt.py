@@ -616,13 +616,33 @@ def assign_whole(cur, x):
     return cur
 
 
+class GenOut:
+    """what a generic subroutine hands back: the scalar arguments the chosen specific defined, by dummy name, and its dummy order"""
+    __slots__ = ("names", "values")
+
+    def __init__(self, names, values):
+        self.names, self.values = names, values
+
+
+NOOUT = object()
+
+
+def genout(res, pos, kw):
+    """the value the specific procedure gave to its dummy argument at position pos (or named kw), NOOUT if it defines none there"""
+    if type(res) is not GenOut:
+        return NOOUT
+    name = kw if kw is not None else (res.names[pos] if pos is not None and pos < len(res.names) else None)
+    return res.values.get(name, NOOUT)
+
+
 def generic(name, specifics):
     """a generic interface: the first specific whose dummy arguments fit the actual ones (count, keywords, array rank) is called"""
     def rank(x):
         return len(x.shape) if type(x) is FArray else 0
 
     def call(*a, **kw):
-        for f, sig in specifics:
+        for f, sig, *more in specifics:
+            outs = more[0] if more else []
             if len(a) > len(sig):
                 continue
             names = [s[0] for s in sig]
@@ -642,7 +662,10 @@ def generic(name, specifics):
                     ok = False
                     break
             if ok:
-                return f(*a, **kw)
+                res = f(*a, **kw)
+                if outs and isinstance(res, tuple) and len(res) == len(outs):   # a subroutine that defines scalar arguments
+                    return GenOut(names, dict(zip(outs, res)))
+                return res
         raise TypeError(f"no specific procedure of generic {name} matches the call")
     return call
 
@@ -651,6 +674,19 @@ def new_type(ns, tname):
     """an instance of derived type tname with its default component initialisations, if the type's module was translated"""
     f = ns.get("_new_" + mangle(tname))
     return f() if f is not None else NS()
+
+
+def type_is(obj, tname, or_extension, ns):
+    """the guards of SELECT TYPE: TYPE IS (tname) -- the dynamic type is exactly tname -- or CLASS IS (tname) -- tname or an extension"""
+    t = getattr(obj, "_type", None)
+    if t is None:
+        return False
+    if mangle(t) == mangle(tname):
+        return True
+    if not or_extension:
+        return False
+    chain = getattr(obj, "__dict__", {}).get("_bases") or ()
+    return mangle(tname) in [mangle(b) for b in chain]
 
 
 def alloc_types(ns, tname, bounds):
@@ -755,6 +791,14 @@ UNITS = {}   # unit number -> list of records, for the units a test wants to rea
 def unit_write(unit, text):
     if type(unit) is int and unit in UNITS:
         UNITS[unit] += text.split("\n")
+
+
+def list_write(items):
+    """WRITE(unit, *) items, for messages: strings as they are, numbers by repr (NOT a Fortran processor's list-directed editing)"""
+    out = []
+    for x in items:
+        out += [repr(v) if type(v) is float else str(v) for v in (x.tolist() if type(x) is FArray else [x])]
+    return " " + " ".join(out)
 
 
 def _fmt_tokens(f):

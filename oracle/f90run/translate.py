@@ -831,6 +831,8 @@ def _parse_block(sts, i, stop):
             return out, i + 1
         if "endselect" in stop and (re.match(r"end\s*select", st) or re.match(r"case\b", st)):
             return out, i
+        if "endseltype" in stop and (re.match(r"end\s*select", st) or re.match(r"(type|class)\s+is\b", st) or re.match(r"class\s+default$", st)):
+            return out, i
         # --- if construct
         if st.startswith("if") and re.match(r"if\s*\(", st):
             j = _match_paren(st, st.index("("))
@@ -895,6 +897,29 @@ def _parse_block(sts, i, stop):
                 blk, i = _parse_block(sts, i + 1, ("endselect",))
                 cases.append((None if lab == "default" else lab[1:-1], blk))
             out.append(("select", ln, sel, cases))
+            continue
+        m = re.match(r"select\s*type\s*\(", st)
+        if m:
+            # select type ([assoc =>] selector): ('seltype', ln, associate name, selector, [(guard 'is' | 'class' | None, type name, block)])
+            j = _match_paren(st, st.index("("))
+            sel = st[st.index("(") + 1:j - 1]
+            assoc, _, expr = sel.partition("=>") if "=>" in sel else (sel, "", sel)
+            arms = []
+            i += 1
+            while True:
+                ln2, s2 = sts[i]
+                if re.match(r"end\s*select", s2):
+                    i += 1
+                    break
+                mm = re.match(r"(type|class)\s+is\s*\(\s*([a-z_]\w*)\s*\)$", s2) or re.match(r"(class)\s+(default)$", s2)
+                if not mm:
+                    raise SyntaxError(f"line {ln2}: unexpected {s2!r} inside select type")
+                blk, i = _parse_block(sts, i + 1, ("endseltype",))
+                if mm.group(2) == "default":
+                    arms.append((None, None, blk))
+                else:
+                    arms.append(("is" if mm.group(1) == "type" else "class", mm.group(2), blk))
+            out.append(("seltype", ln, assoc.strip(), expr.strip(), arms))
             continue
         out.append(("stmt", ln, st))
         i += 1

@@ -55,3 +55,35 @@ def test_reference_remapping_unit_tests_detect_a_one_ulp_class_error():
         assert R["mom_remapping"]["remapping_unit_tests"](False, num_comp_samp=3) is True
     finally:
         rt.LENIENT_READS = False
+
+
+def test_reference_eos_consistency_tests():
+    """test_EOS_consistency (src/equation_of_state/MOM_EOS.F90:2302-2660), called as EOS_unit_tests calls it (:2078-2131) for the two
+    equations of state of the frozen option set: the published density at T = 25, S = 35, p = 1e7, rho * spv = 1, the reference-density
+    offsets, every first and second derivative against finite differences of three orders, and the analytic against the quadrature
+    layer-mean specific volume.  LINEAR passes; WRIGHT with USE_WRIGHT_2ND_DERIV_BUG passes everything except drho_dT_dT -- the failure
+    the reference itself documents at :2081-2083 ("a known failure") -- and passes outright without the bug flag."""
+    from oracle.f90run import rt, stages
+    R = f90run.load(list(stages.EOS_FILES), extra_stubs=dict(stdout=6, stderr=0))
+    M = R["mom_eos"]
+
+    def run(name, check, **init):
+        rt.UNITS[0], rt.UNITS[6] = [], []
+        try:
+            E = M["_new_eos_type"]()
+            M["eos_manual_init"](E, **init)
+            failed = M["test_eos_consistency"](25.0, 35.0, 1.0e7, E, True, name, rho_check=check * E.kg_m3_to_r, avg_sv_check=True)
+            return failed, [ln for ln in rt.UNITS[0] if "disagree" in ln], len(rt.UNITS[6])
+        finally:
+            del rt.UNITS[0], rt.UNITS[6]
+
+    failed, bad, nok = run("LINEAR", 1028.0, form_of_eos=M["eos_linear"], rho_t0_s0=1000.0, drho_dt=-0.2, drho_ds=0.8, drho_dp=5.0e-7)
+    assert failed is False and not bad and nok >= 13
+    failed, bad, nok = run("WRIGHT", 1027.54303596346, form_of_eos=M["eos_wright"], use_wright_2nd_deriv_bug=True)
+    # (the translator evaluates .AND. left to right and stops at the first false operand, so the checks after the failing one are skipped)
+    assert failed is True and len(bad) == 1 and "WRIGHT drho_dT_dT" in bad[0] and nok >= 8
+    failed, bad, nok = run("WRIGHT", 1027.54303596346, form_of_eos=M["eos_wright"], use_wright_2nd_deriv_bug=False)
+    assert failed is False and not bad
+    # negative control: a check value off in the 12th digit is reported
+    failed, bad, nok = run("LINEAR", 1028.0 * (1.0 + 1.0e-11), form_of_eos=M["eos_linear"], rho_t0_s0=1000.0, drho_dt=-0.2, drho_ds=0.8, drho_dp=5.0e-7)
+    assert failed is True
