@@ -87,6 +87,9 @@ extern "C" int oracle_ale_regridding_and_remapping(const mom6cu_domain* d, const
                                                    const mom6cu_unit_scale* US, mom6cu_ale_cs* CS, const mom6cu_dyn_split_rk2_cs* dynCS,
                                                    const mom6cu_ale_args* a, int nthreads) {
   if (CS->remap_uv_using_old_alg || CS->do_conv_adj || CS->use_hybgen_unmix) return 3;
+  // remap.cpp restates the answer_date >= 20190101 expressions only: refuse the older ones, as the device does (csrc/remap.cu:120),
+  // rather than answer with the newer arithmetic (the reference run of tests/refcases.py showed that they differ)
+  if (CS->remapCS.answer_date < 20190101 || CS->vel_remapCS.answer_date < 20190101) return 3;
   const OGrid G(d, Gp);
   const int nz = G.ke;
   const size_t plH = (size_t)(d->ied - d->isd + 1) * (d->jed - d->jsd + 1);

@@ -15,6 +15,7 @@ using namespace orc;
 extern "C" int oracle_horizontal_viscosity(const mom6cu_domain* d, const mom6cu_grid* Gp, const mom6cu_vgrid* GV,
                                            const mom6cu_hor_visc_cs* CS, const mom6cu_hor_visc_args* A, int nthreads) {
   if (nthreads > 0) omp_set_num_threads(nthreads);
+  if (CS->unsupported) return 3;  // Leith / GME / MEKE / anisotropic / ZB2020 / resolution-scaled viscosities, OBCs: not restated
   const OGrid G(d, Gp);
   const int is = G.isc, ie = G.iec, js = G.jsc, je = G.jec, Isq = G.IscB, Ieq = G.IecB, Jsq = G.JscB, Jeq = G.JecB;
   const int nz = G.ke;

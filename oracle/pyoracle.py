@@ -158,7 +158,9 @@ def remapping_core_h(cs, h0, u0, h1):
     u1 = np.zeros(len(h1)); err = C.c_double(0.0)
     lib.oracle_remapping_core_h.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     c = marshal.remapping_cs(cs)
-    lib.oracle_remapping_core_h(C.byref(c), len(h0), _dp(h0), _dp(u0), len(h1), _dp(h1), _dp(u1), C.byref(err))
+    rc = lib.oracle_remapping_core_h(C.byref(c), len(h0), _dp(h0), _dp(u0), len(h1), _dp(h1), _dp(u1), C.byref(err))
+    if rc != 0:
+        raise RuntimeError(f"oracle_remapping_core_h rc={rc}")
     return u1, err.value
 
 

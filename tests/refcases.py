@@ -277,6 +277,14 @@ _T3 = [
      dict(uhbt_noise=3.0, dt=3600.0, cs_over=dict(CFL_limit_adjust=0.005, use_visc_rem_max=0))),
     ("continuity/aggress_adjust_binds", "continuity", (20, 16, 6), dict(uhbt_noise=6.0, dt=14400.0, cs_over=dict(aggress_adjust=1, vol_CFL=1))),
 ]
+# the members of ALE's regridding / remapping control structures (each checked to act); remapping answer dates before 2019 are refused
+_T3 += [("ale/" + n, "ale", (12, 10, 5), kw) for n, kw in (
+    ("min_thickness_2m", dict(regrid=dict(min_thickness=2.0))),
+    ("time_filter_depths", dict(regrid=dict(depth_of_time_filter_shallow=50.0, depth_of_time_filter_deep=600.0))),
+    ("boundary_extrapolation", dict(remap=dict(boundary_extrapolation=1), vel_remap=dict(boundary_extrapolation=1))),
+    ("no_force_bounds_in_target", dict(remap=dict(force_bounds_in_target=0), vel_remap=dict(force_bounds_in_target=0))),
+    ("not_via_sub_cells", dict(remap=dict(om4_remap_via_sub_cells=0), vel_remap=dict(om4_remap_via_sub_cells=0))),
+    ("plm_velocities_ppm_tracers", dict(vel_remap=dict(remapping_scheme=2))))]
 for _nm, _st, _shape, _kw in _T3:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), land_blocks=2, **_kw)
 
@@ -494,7 +502,12 @@ def build(name):
     if st == "advect_tracer":
         return synthetic.advect_inputs(*shape, **kw)
     if st == "ale":
-        return synthetic.ale_chain_inputs(*shape, **kw)
+        over = {k: kw.pop(k, None) for k in ("regrid", "remap", "vel_remap")}   # members of the three control structures to move
+        dom, grid, gv, ale, dcs, a = synthetic.ale_chain_inputs(*shape, **kw)
+        for k, d in over.items():
+            if d:
+                ale[k + "CS"].update(d)
+        return dom, grid, gv, ale, dcs, a
     if st == "diag":
         from oracle import pyoracle
         if kw.get("chksum"):
