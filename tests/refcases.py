@@ -285,6 +285,14 @@ _T3 += [("ale/" + n, "ale", (12, 10, 5), kw) for n, kw in (
     ("no_force_bounds_in_target", dict(remap=dict(force_bounds_in_target=0), vel_remap=dict(force_bounds_in_target=0))),
     ("not_via_sub_cells", dict(remap=dict(om4_remap_via_sub_cells=0), vel_remap=dict(om4_remap_via_sub_cells=0))),
     ("plm_velocities_ppm_tracers", dict(vel_remap=dict(remapping_scheme=2))))]
+# the coefficients of the linear equation of state, and KV without a bottom drag law
+_T3 += [("thickness_diffuse/linear_eos_coefficients", "thickness_diffuse", (14, 10, 5), dict(EOS_form=1, dRho_dT=-0.3, dRho_dS=0.7)),
+        ("mixedlayer_restrat/linear_eos_coefficients", "mixedlayer_restrat", (14, 10, 16), dict(eos="LINEAR", Rho_T0_S0=999.0, dRho_dT=-0.3, dRho_dS=0.7)),
+        ("pressure_force/linear_eos_coefficients", "pressure_force", (14, 10, 5),
+         dict(eos="LINEAR", Rho_T0_S0=999.0, dRho_dT=-0.3, dRho_dS=0.7, dRho_dp=4.0e-7)),
+        ("pressure_force/linear_eos_coefficients_ppm", "pressure_force", (14, 10, 5),
+         dict(eos="LINEAR", reconstruct=1, Recon_Scheme=2, Rho_T0_S0=999.0, dRho_dT=-0.3, dRho_dS=0.7, dRho_dp=4.0e-7)),
+        ("vertvisc_family/kv_no_drag_law", "vertvisc_family", (16, 12, 6), dict(bottomdraglaw=0, Kv=3e-3))]
 for _nm, _st, _shape, _kw in _T3:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), land_blocks=2, **_kw)
 
