@@ -292,7 +292,9 @@ _T3 += [("thickness_diffuse/linear_eos_coefficients", "thickness_diffuse", (14, 
          dict(eos="LINEAR", Rho_T0_S0=999.0, dRho_dT=-0.3, dRho_dS=0.7, dRho_dp=4.0e-7)),
         ("pressure_force/linear_eos_coefficients_ppm", "pressure_force", (14, 10, 5),
          dict(eos="LINEAR", reconstruct=1, Recon_Scheme=2, Rho_T0_S0=999.0, dRho_dT=-0.3, dRho_dS=0.7, dRho_dp=4.0e-7)),
-        ("vertvisc_family/kv_no_drag_law", "vertvisc_family", (16, 12, 6), dict(bottomdraglaw=0, Kv=3e-3))]
+        ("vertvisc_family/kv_no_drag_law", "vertvisc_family", (16, 12, 6), dict(bottomdraglaw=0, Kv=3e-3)),
+        ("btstep/min_stencil_2", "btstep", (16, 12, 4), dict(min_stencil=2)),
+        ("mixedlayer_restrat/ustar_min", "mixedlayer_restrat", (14, 10, 16), dict(ustar_min=5.0e-3))]
 for _nm, _st, _shape, _kw in _T3:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), land_blocks=2, **_kw)
 
