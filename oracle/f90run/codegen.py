@@ -685,8 +685,17 @@ class ProcGen:
     def generate(self):
         P = self.P
         outs = P.out_scalars()
+        self.fn_outs = []
         if P.kind == "function":
             self.ret = mangle(P.result)
+            # A function's value is all the translator hands back: what the function gives to its scalar intent(out) / (inout)
+            # arguments does not reach the caller.  That must not happen silently, so the value at every RETURN is compared with
+            # the value at entry and a change stops the run (_rt.fn_ret).
+            self.fn_outs = [mangle(a) for a in P.args if a in P.vars and P.vars[a].dims is None and P.vars[a].intent in ("out", "inout")
+                            and P.vars[a].base in ("real", "integer", "logical", "character")]
+            if self.fn_outs:
+                self.ret = (f"_rt.fn_ret({mangle(P.result)}, {P.name!r}, [" +
+                            ", ".join(f"({a!r}, _e_{a}, {a})" for a in self.fn_outs) + "])")
         else:
             self.ret = "(" + "".join(mangle(a) + ", " for a in outs) + ")" if outs else "None"
         body_gen = ProcGen(self.prog, self.mod, P)
@@ -754,6 +763,7 @@ class ProcGen:
         self.block(1, P.body)
         body = self.lines
         head = [f"def {mangle(P.name)}(" + ", ".join(mangle(a) + "=None" for a in P.args) + f"):  # {self.mod.name}:{P.line}"]
+        head += [f"    _e_{a} = {a}" for a in self.fn_outs]
         if self.globals_assigned:
             head.append("    global " + ", ".join(sorted(self.globals_assigned)))
         if self.host_assigned:

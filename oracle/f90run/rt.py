@@ -616,6 +616,16 @@ def assign_whole(cur, x):
     return cur
 
 
+def fn_ret(value, fname, outs):
+    """the value of a function; outs = [(dummy name, its value at entry, its value now)] for its scalar intent(out) / (inout) arguments,
+    which the translator cannot hand back: a changed one would be lost, so it stops the run instead"""
+    for name, before, now in outs:
+        if before is not None and now is not before and not (now == before):
+            raise NotImplementedError(f"{fname}: the function changed its scalar argument {name} ({before!r} -> {now!r}); "
+                                      "values a function gives to its arguments are not returned by the translator")
+    return value
+
+
 class GenOut:
     """what a generic subroutine hands back: the scalar arguments the chosen specific defined, by dummy name, and its dummy order"""
     __slots__ = ("names", "values")
