@@ -698,7 +698,6 @@ class ProcGen:
                             ", ".join(f"({a!r}, _e_{a}, {a})" for a in self.fn_outs) + "])")
         else:
             self.ret = "(" + "".join(mangle(a) + ", " for a in outs) + ")" if outs else "None"
-        body_gen = ProcGen(self.prog, self.mod, P)
         # prologue
         pro = []
         for name, v in P.vars.items():

@@ -827,7 +827,7 @@ class _EnergyFile:
         pass
 
 
-def _sum_output_stubs(files):
+def _sum_output_stubs():
     def var_desc(name, units=None, longname=None, hor_grid=None, z_grid=None, **kw):
         return NS(name=name)
 
@@ -849,14 +849,14 @@ SUM_OUTPUT_FILES = ["src/diagnostics/MOM_sum_output.F90", "src/framework/MOM_com
 def _sum_output_ref():
     key = ("sum_output",)
     if key not in _REF:
-        _REF[key] = load(SUM_OUTPUT_FILES, extra_stubs=_sum_output_stubs(None), expose=("write_energy",))
+        _REF[key] = load(SUM_OUTPUT_FILES, extra_stubs=_sum_output_stubs(), expose=("write_energy",))
     return _REF[key]
 
 
 def create_depth_list(dom, grid, Z_ref=0.0, min_depth_inc=1.0e-10):
     """create_depth_list, src/diagnostics/MOM_sum_output.F90:1203-1299 -> (depth, area, vol_below)"""
     R = _sum_output_ref()
-    G, GV, US = _types(dom, grid, {})
+    G = _types(dom, grid, {})[0]
     G.z_ref = float(Z_ref)
     G.isg, G.jsg = G.isc, G.jsc
     G.domain.niglobal, G.domain.njglobal = G.iec - G.isc + 1, G.jec - G.jsc + 1

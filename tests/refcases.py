@@ -386,7 +386,7 @@ _WE_EFPS = ("fresh_water_in_EFP", "net_salt_in_EFP", "net_heat_in_EFP", "mass_pr
 def diag_write_energy(inputs, write_energy, stats_line):
     """three write_energy calls through the given backend, the state and the truncation count changing in between; stats_line(cs, e,
     n, reday) is the record the call appends to ocean.stats (step n = the call number, one hour apart)"""
-    dom, a, cs = inputs[0], inputs[3], _copy(inputs[4])
+    a, cs = inputs[3], _copy(inputs[4])
     u, v, h, T, S = (a[k].copy() for k in ("u_inst", "v_inst", "h", "T", "S"))
     rng = np.random.default_rng(4)
     out = {}
