@@ -305,7 +305,7 @@ LATE = {n for n in CASES if n.startswith(("diag/", "mixedlayer_restrat/"))} | {
     "coradcalc/al_blend_sadourny_limit", "vertvisc_family/mixing_lengths", "vertvisc_family/mixing_lengths_no_drag_law",
     "pressure_force/gfs_scale", "pressure_force/rho_ref_h_nonvanished_plm", "pressure_force/mass_weight_vanished_only_ppm",
     "tracer_hordiff/passivity_min", "thickness_diffuse/khth_cfl_slope_smoothing", "thickness_diffuse/fgnv_scale_n2_floor", "step/be_0.7",
-    "step/no_visc_rem_dt_bug"} | {t[0] for t in _T3}
+    "step/no_visc_rem_dt_bug", "bt_helpers/set_dtbt_parameters"} | {t[0] for t in _T3}
 
 # outputs a case legitimately returns as it received them
 UNTOUCHED_OK = {
@@ -335,6 +335,8 @@ def untouched(name, inputs, out):
 
 # ---- btcalc (4 thickness schemes + the default), bt_mass_source (set / accumulate), set_dtbt (4 ways of finding the wave speed) ----
 case("bt_helpers/btcalc_mass_source_set_dtbt", "bt_helpers", (16, 12, 5), (), land_blocks=2)
+case("bt_helpers/set_dtbt_parameters", "bt_helpers", (16, 12, 5), (), land_blocks=2,
+     dtbt=dict(bebt=0.3, G_extra=0.05, dtbt_fraction=0.7, BT_Coriolis_scale=0.5, Z_ref=2.0))
 
 
 def _dtbt_args(dom, grid, cs, mode):
@@ -347,6 +349,7 @@ def _dtbt_args(dom, grid, cs, mode):
         a["eta"] = cs["eta"]; a["Nonlinear_continuity"] = 1
     elif mode == "gtot":
         a["pbce"] = None; a["gtot_est"] = 9.8; a["have_gtot_est"] = 1; a["SSH_add"] = 2.0
+    a.update(cs.get("_dtbt_over", {}))   # the parameters of set_dtbt a case moves off their defaults
     return a
 
 
@@ -529,9 +532,11 @@ def build(name):
         return dom, grid, gv, a, cs
     if st == "bt_helpers":
         from oracle import pyoracle
+        dtbt_over = kw.pop("dtbt", None)
         dom, grid, gv, bcs, ba = synthetic.btstep_inputs(*shape, **kw)
         dom2, grid2, gv2, css, scs, sa = synthetic.step_dyn_inputs(*shape, **kw)
         pyoracle.step_dyn_split_rk2(dom2, grid2, gv2, css, scs, sa)   # realistic pbce, BT_cont, eta (pinned by the step cases)
+        scs["_dtbt_over"] = dtbt_over or {}
         return dom2, grid2, gv2, bcs, ba, synthetic.dyn_state(dom2, grid2), scs
     if st == "thickness_diffuse":
         return synthetic.thickness_diffuse_inputs(*shape, **kw)
