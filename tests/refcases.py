@@ -295,6 +295,9 @@ _T3 += [("thickness_diffuse/linear_eos_coefficients", "thickness_diffuse", (14, 
         ("vertvisc_family/kv_no_drag_law", "vertvisc_family", (16, 12, 6), dict(bottomdraglaw=0, Kv=3e-3)),
         ("btstep/min_stencil_2", "btstep", (16, 12, 4), dict(min_stencil=2)),
         ("mixedlayer_restrat/ustar_min", "mixedlayer_restrat", (14, 10, 16), dict(ustar_min=5.0e-3))]
+_T3 += [("advect_tracer/vol_prev_uhr_out_one_iteration", "advect_tracer", (14, 10, 4),
+         dict(scheme=1, cfl=3.2, ntr=3, max_iter_in=1, with_vol_prev=1.01, with_uhr_out=True)),
+        ("advect_tracer/vol_prev_only_ppm", "advect_tracer", (14, 10, 4), dict(scheme=2, cfl=2.5, ntr=3, with_vol_prev=0.99))]
 for _nm, _st, _shape, _kw in _T3:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), land_blocks=2, **_kw)
 
@@ -513,7 +516,17 @@ def build(name):
     if st == "pressure_force":
         return synthetic.pressureforce_inputs(*shape, **kw)
     if st == "advect_tracer":
-        return synthetic.advect_inputs(*shape, **kw)
+        vp, ur = kw.pop("with_vol_prev", None), kw.pop("with_uhr_out", False)
+        dom, grid, gv, cs, a = synthetic.advect_inputs(*shape, **kw)
+        if vp is not None:   # the caller's own cell volumes (hprev of MOM_tracer_advect.F90:188-195, scaled), updated by the call
+            div = np.zeros_like(a["h_end"])
+            div[:, 1:-1, 1:-1] = (a["uhtr"][:, 1:-1, 2:-1] - a["uhtr"][:, 1:-1, 1:-2]) + (a["vhtr"][:, 2:-1, 1:-1] - a["vhtr"][:, 1:-2, 1:-1])
+            v = np.maximum(0.0, grid["areaT"][None] * a["h_end"] + div)
+            a["vol_prev"] = np.ascontiguousarray((v + np.maximum(0.0, 1.0e-13 * v - grid["areaT"][None] * a["h_end"])) * vp)
+            a["update_vol_prev"] = True
+        if ur:               # the transports the limited number of iterations leaves over
+            a["uhr_out"], a["vhr_out"] = np.zeros_like(a["uhtr"]), np.zeros_like(a["vhtr"])
+        return dom, grid, gv, cs, a
     if st == "ale":
         over = {k: kw.pop(k, None) for k in ("regrid", "remap", "vel_remap")}   # members of the three control structures to move
         dom, grid, gv, ale, dcs, a = synthetic.ale_chain_inputs(*shape, **kw)
