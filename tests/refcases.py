@@ -298,6 +298,11 @@ _T3 += [("thickness_diffuse/linear_eos_coefficients", "thickness_diffuse", (14, 
 _T3 += [("advect_tracer/vol_prev_uhr_out_one_iteration", "advect_tracer", (14, 10, 4),
          dict(scheme=1, cfl=3.2, ntr=3, max_iter_in=1, with_vol_prev=1.01, with_uhr_out=True)),
         ("advect_tracer/vol_prev_only_ppm", "advect_tracer", (14, 10, 4), dict(scheme=2, cfl=2.5, ntr=3, with_vol_prev=0.99))]
+# optional arguments left out
+_T3 += [("pressure_force/no_pbce_no_eta_p_atm_plm", "pressure_force", (14, 10, 5),
+         dict(with_pbce=False, with_eta=False, reconstruct=1, Recon_Scheme=1, with_p_atm=True)),
+        ("vertvisc_family/no_shear_viscosity", "vertvisc_family", (16, 12, 6), dict(with_shear=False)),
+        ("continuity/no_velocity_corrections", "continuity", (20, 16, 6), dict(with_cor=False))]
 for _nm, _st, _shape, _kw in _T3:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), land_blocks=2, **_kw)
 
