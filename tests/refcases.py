@@ -305,6 +305,16 @@ _T3 += [("pressure_force/no_pbce_no_eta_p_atm_plm", "pressure_force", (14, 10, 5
         ("continuity/no_velocity_corrections", "continuity", (20, 16, 6), dict(with_cor=False))]
 for _nm, _st, _shape, _kw in _T3:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), land_blocks=2, **_kw)
+# domain shapes the cases above leave out: closed basins, a reentrant y direction, y first
+_GEO = [("step/closed_basin_with_land", "step", (12, 10, 4), dict(land_blocks=2, cyclic_x=False)),
+        ("step/closed_basin_y_first", "step", (12, 10, 4), dict(land_blocks=0, cyclic_x=False, cyclic_y=False, first_direction=1)),
+        ("pressure_force/closed_basin_ppm", "pressure_force", (14, 10, 5), dict(land_blocks=2, cyclic_x=False, reconstruct=1, Recon_Scheme=2)),
+        ("continuity/doubly_periodic_y_first", "continuity", (20, 16, 6), dict(land_blocks=2, cyclic_y=True, first_direction=1)),
+        ("coradcalc/doubly_periodic_arakawa_lamb_gudonov", "coradcalc", (16, 12, 3),
+         dict(land_blocks=2, cyclic_y=True, cs_over=dict(Coriolis_Scheme=5, KE_Scheme=12))),
+        ("advect_tracer/closed_basin_ppm", "advect_tracer", (14, 10, 4), dict(land_blocks=0, cyclic_x=False, cyclic_y=False, scheme=2, cfl=2.5))]
+for _nm, _st, _shape, _kw in _GEO:
+    case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), **_kw)
 
 # cases added or changed after the round's GPU budget was spent: their device legs run from tests/test_zzz_reference_golden_late.py, sorted
 # last, so that a disagreement there cannot hide the results of the files after tests/test_reference_golden.py under `pytest -x`
@@ -313,7 +323,7 @@ LATE = {n for n in CASES if n.startswith(("diag/", "mixedlayer_restrat/"))} | {
     "coradcalc/al_blend_sadourny_limit", "vertvisc_family/mixing_lengths", "vertvisc_family/mixing_lengths_no_drag_law",
     "pressure_force/gfs_scale", "pressure_force/rho_ref_h_nonvanished_plm", "pressure_force/mass_weight_vanished_only_ppm",
     "tracer_hordiff/passivity_min", "thickness_diffuse/khth_cfl_slope_smoothing", "thickness_diffuse/fgnv_scale_n2_floor", "step/be_0.7",
-    "step/no_visc_rem_dt_bug", "bt_helpers/set_dtbt_parameters"} | {t[0] for t in _T3}
+    "step/no_visc_rem_dt_bug", "bt_helpers/set_dtbt_parameters"} | {t[0] for t in _T3 + _GEO}
 
 # outputs a case legitimately returns as it received them
 UNTOUCHED_OK = {
