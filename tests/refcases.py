@@ -313,6 +313,13 @@ _GEO = [("step/closed_basin_with_land", "step", (12, 10, 4), dict(land_blocks=2,
         ("coradcalc/doubly_periodic_arakawa_lamb_gudonov", "coradcalc", (16, 12, 3),
          dict(land_blocks=2, cyclic_y=True, cs_over=dict(Coriolis_Scheme=5, KE_Scheme=12))),
         ("advect_tracer/closed_basin_ppm", "advect_tracer", (14, 10, 4), dict(land_blocks=0, cyclic_x=False, cyclic_y=False, scheme=2, cfl=2.5))]
+# the whole step with every stage off its default scheme
+_GEO += [("step/monotonic_arakawa_hsu_smagorinsky_harmonic", "step", (12, 10, 4),
+          dict(land_blocks=2, cont=dict(monotonic=1), corad=dict(Coriolis_Scheme=2, KE_Scheme=12, bound_Coriolis=1),
+               hv=dict(Laplacian=True, Smagorinsky_Kh=True, Kh=300.0, bound_Coriolis=True), vv=dict(harmonic_visc=1))),
+         ("step/simple2nd_al_blend_laplacian_no_slip_direct_stress", "step", (12, 10, 4),
+          dict(land_blocks=2, cont=dict(simple_2nd=1, vol_CFL=1), corad=dict(Coriolis_Scheme=6, KE_Scheme=11, no_slip=1),
+               hv=dict(Laplacian=True, biharmonic=False, Kh=800.0, no_slip=True), vv=dict(bottomdraglaw=0, direct_stress=1)))]
 for _nm, _st, _shape, _kw in _GEO:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), **_kw)
 
@@ -574,7 +581,14 @@ def build(name):
         return synthetic.hordiff_inputs(*shape, **kw)
     if st == "step":
         pgf, nsteps, vv, dyn = kw.pop("pgf", None), kw.pop("nsteps", 1), kw.pop("vv", None), kw.pop("dyn", None)
+        cont, corad, hv = kw.pop("cont", None), kw.pop("corad", None), kw.pop("hv", None)
         dom, grid, gv, css, cs, a = synthetic.step_dyn_inputs(*shape, **kw)
+        if cont:
+            css["continuity"].update(cont)
+        if corad:
+            css["coriolisadv"].update(corad)
+        if hv:   # hor_visc_init's products depend on the options: built anew
+            css["hor_visc"] = synthetic.hor_visc_cs(dom, grid, dt=a["dt"], **hv)
         if dyn:
             cs.update(dyn)
         if pgf:
