@@ -320,6 +320,13 @@ _GEO += [("step/monotonic_arakawa_hsu_smagorinsky_harmonic", "step", (12, 10, 4)
          ("step/simple2nd_al_blend_laplacian_no_slip_direct_stress", "step", (12, 10, 4),
           dict(land_blocks=2, cont=dict(simple_2nd=1, vol_CFL=1), corad=dict(Coriolis_Scheme=6, KE_Scheme=11, no_slip=1),
                hv=dict(Laplacian=True, biharmonic=False, Kh=800.0, no_slip=True), vv=dict(bottomdraglaw=0, direct_stress=1)))]
+# one, two and three layers (the reconstructions fall back to lower order, the tridiagonal solves degenerate)
+_GEO += [("ale/two_layers", "ale", (12, 10, 2), dict(land_blocks=2)), ("ale/three_layers", "ale", (12, 10, 3), dict(land_blocks=2)),
+         ("step/one_layer", "step", (12, 10, 1), dict(land_blocks=2)), ("step/two_layers", "step", (12, 10, 2), dict(land_blocks=2)),
+         ("vertvisc_family/one_layer", "vertvisc_family", (16, 12, 1), dict(land_blocks=2, with_Ray=True)),
+         ("advect_tracer/one_layer_ppm", "advect_tracer", (14, 10, 1), dict(land_blocks=2, scheme=2, cfl=2.5)),
+         ("thickness_diffuse/two_layers", "thickness_diffuse", (14, 10, 2), dict(land_blocks=2)),
+         ("pressure_force/two_layers_plm", "pressure_force", (14, 10, 2), dict(land_blocks=2, reconstruct=1, Recon_Scheme=1))]
 for _nm, _st, _shape, _kw in _GEO:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), **_kw)
 
