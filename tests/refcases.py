@@ -327,6 +327,13 @@ _GEO += [("ale/two_layers", "ale", (12, 10, 2), dict(land_blocks=2)), ("ale/thre
          ("advect_tracer/one_layer_ppm", "advect_tracer", (14, 10, 1), dict(land_blocks=2, scheme=2, cfl=2.5)),
          ("thickness_diffuse/two_layers", "thickness_diffuse", (14, 10, 2), dict(land_blocks=2)),
          ("pressure_force/two_layers_plm", "pressure_force", (14, 10, 2), dict(land_blocks=2, reconstruct=1, Recon_Scheme=1))]
+# other time steps (another number of barotropic steps and parity of the alternating directions, larger CFL numbers)
+_GEO += [("btstep/dt_1250", "btstep", (16, 12, 4), dict(land_blocks=2, dt=1250.0)),
+         ("btstep/dt_300_y_first", "btstep", (16, 12, 4), dict(land_blocks=2, dt=300.0, first_direction=1)),
+         ("step/dt_1800", "step", (12, 10, 4), dict(land_blocks=2, dt=1800.0)),
+         ("step/dt_450_fast_flow", "step", (12, 10, 4), dict(land_blocks=2, dt=450.0, vel=0.3)),
+         ("continuity/dt_7200", "continuity", (20, 16, 6), dict(land_blocks=2, dt=7200.0)),
+         ("advect_tracer/dt_14400_cfl3.9_ppm_h3", "advect_tracer", (14, 10, 4), dict(land_blocks=2, dt=14400.0, dt_dyn=900.0, scheme=1, cfl=3.9))]
 for _nm, _st, _shape, _kw in _GEO:
     case(_nm, _st, _shape, next(c["outputs"] for c in CASES.values() if c["stage"] == _st), **_kw)
 
